@@ -1,0 +1,238 @@
+/*
+ * epimcmc.h — C ABI of libepimcmc.so, the B200-native (sm_100a) batched
+ * log-posterior evaluator + on-device sampler for the epi-mcmc model files.
+ *
+ * This is the drop-in boundary for ONE path of kdeforche/epi-mcmc: the
+ * per-proposal log-posterior evaluation that the MCMC driver calls
+ * (reference call sites, paths relative to the reference root):
+ *
+ *   R/MCMC/fitMCMC-drj.R:19-21   calcloglMCMC(params) = calclogl(transformParams(params))
+ *   R/MCMC/fitMCMC-drj.R:48-57   run_mcmc(loglike = calcloglMCMC, logprior = calclogp, ...)
+ *   R/models/model-age-groups2q.R:380-486  calclogp      (age flavour)
+ *   R/models/model-age-groups2q.R:488-602  calclogl      (age flavour)
+ *   R/models/model-age-groups2q.R:50-337   calculateModel (age flavour)
+ *   R/models/model-simple-ode-drj-cmp.R:41-129,156-257   (simple flavour)
+ *   R/models/model-agen.cpp:65-163  initmod()/derivs()   (deSolve compiled-model ABI)
+ *
+ * The reference's only native ABI is deSolve's per-RHS-call `derivs`
+ * (model-agen.cpp:103-106), which is far too fine-grained for a GPU.  The
+ * boundary therefore sits one level up, at the model-file API: an R `.Call`
+ * shim (r/epimcmc_shim.c) binds exactly the entry points
+ * declared here.
+ *
+ * Conventions: plain C, integer return codes (0 = ok), no exceptions cross the
+ * ABI, caller owns every host buffer, the library owns every device buffer,
+ * no global mutable state (contrast `static double parms[PARAM_N]`,
+ * model-agen.cpp:4-5), one handle may be used by one host thread at a time.
+ * There is NO CPU fallback: every compute entry point fails with
+ * EPI_ERR_NO_DEVICE when no CUDA device is usable.
+ */
+#ifndef EPIMCMC_H
+#define EPIMCMC_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EPI_ABI_VERSION 1
+
+/* ---- model flavours ------------------------------------------------------- */
+/* simple 1-population SEIR, 8 parameters (R/models/model-simple-ode-drj-cmp.R) */
+#define EPI_FLAVOUR_SIMPLE 0
+/* simple + effective population size Nef, 9 parameters (README.md:78-95; the
+ * model file itself is absent from the snapshot: restated from description)  */
+#define EPI_FLAVOUR_NE 1
+/* two-age-group SEEIR, 45 parameters (R/models/model-age-groups2q.R + model-agen.cpp) */
+#define EPI_FLAVOUR_AGE2Q 2
+
+#define EPI_MAX_PARAMS 48
+/* widest latency profile supported: in-box maximum is 6*9+1 = 55 taps
+ * (R/models/model-age-groups2q.R:22-23,656) */
+#define EPI_MAX_TAPS 64
+/* InvalidDataOffset, R/models/model-age-groups2q.R:5 */
+#define EPI_INVALID_DATA_OFFSET 10000
+
+/* ---- return codes --------------------------------------------------------- */
+#define EPI_OK 0
+#define EPI_ERR_ARG 1        /* bad argument / inconsistent data description   */
+#define EPI_ERR_NO_DEVICE 2  /* no usable CUDA device (there is no CPU path)   */
+#define EPI_ERR_CUDA 3       /* a CUDA runtime call failed; see epi_last_error */
+#define EPI_ERR_NOMEM 4
+#define EPI_ERR_STATE 5      /* call sequence error (e.g. sampler not initialised) */
+
+/* ---- per-evaluation status bits (int32 per proposal) ---------------------- */
+/* pass 1 found no day with died > threshold: data_offset = 10000, pass 2 skipped
+ * (R/models/model-age-groups2q.R:178-181,216,249-251,493-494)                 */
+#define EPI_ST_INVALID_OFFSET 1
+/* the reference would return NA: a hospital latency profile reaches into the
+ * first `kend` filter outputs that stats::filter leaves NA
+ * (R/models/model-age-groups2q.R:113-114 omits the hosp kernels from padding)  */
+#define EPI_ST_NA 2
+/* theta lies outside the df_params box (R/models/model-age-groups2q.R:637-663) */
+#define EPI_ST_OUT_OF_BOX 8
+/* a latency profile would need more than EPI_MAX_TAPS taps: result is NaN     */
+#define EPI_ST_UNSUPPORTED 16
+
+/* ---- theta layouts -------------------------------------------------------- */
+/* n proposals x d parameters, one proposal per row (C row-major) == an R
+ * d x n matrix in column-major order (one proposal per column)               */
+#define EPI_LAYOUT_AOS 0
+/* d x n, one parameter per row: theta[p*n + i] (structure of arrays)          */
+#define EPI_LAYOUT_SOA 1
+
+/* ---- sampler kinds -------------------------------------------------------- */
+#define EPI_SAMPLER_RWM 0 /* random-walk Metropolis, per-parameter Gaussian scale */
+#define EPI_SAMPLER_DEMC 1 /* differential evolution MC (ter Braak 2006) on a population snapshot */
+
+typedef struct epi_handle epi_handle;
+
+/* Model description: which model file, and the solver/horizon settings.
+ * `period` is FitTotalPeriod (analyses/be/age2q/settings.R:31;
+ * analyses/de/simple/settings.R:29).  `substeps` is the number of classical
+ * RK4 sub-steps per day of the fixed-step integrator that replaces
+ * deSolve::ode/LSODA (R/models/model-age-groups2q.R:163-165,211-213).         */
+typedef struct epi_model_desc {
+  int32_t flavour;
+  int32_t period;
+  int32_t substeps;
+  int32_t reserved;
+} epi_model_desc;
+
+/* Everything the model files read from R globals (data file + settings.R),
+ * snapshotted once at handle creation.  Unused members for a flavour may be
+ * 0/NULL.  All series are double (R numeric); observed counts must be
+ * non-negative integers stored as doubles.
+ *
+ * simple / Ne (R/models/model-simple-ode-drj-cmp.R:41-129,183-257):
+ *   N, lockdown_offset, lockdown_transition_period, total_deaths_at_lockdown,
+ *   dhospi[n_dhospi], dmorti[n_dmorti], dmort_last, hosp_nbinom_size,
+ *   mort_nbinom_size
+ * age-2q (R/models/model-age-groups2q.R, R/data/be/data.R:62-109,
+ *         R/data/be/data-age-all.R:160-161,372-390, analyses/be/age2q/settings.R:29-38):
+ *   y_N, o_N, lockdown_*, total_deaths_at_lockdown, d3..d8, d_reliable_cases,
+ *   d_reliable_hosp, d_hosp_o1, d_hosp_o2, y_dcasei/o_dcasei[n_dcasei],
+ *   dhospi[n_dhospi], n_dhosp (= length(dhosp)), y_dmorti/o_dmorti/o_wdmorti[n_dmorti],
+ *   dmort_last, y_ifr/o_ifr/y_hr/o_hr/g/gtrimp[n_rate], case_nbinom_size1,
+ *   case_nbinom_sizey2, case_nbinom_sizeo2, hosp_nbinom_size1, hosp_nbinom_size2,
+ *   mort_nbinom_size, hosp_last7
+ */
+typedef struct epi_data {
+  double N, y_N, o_N;
+  double total_deaths_at_lockdown;
+  double dmort_last; /* dmort[length(dmort)], only used for the df_params box */
+  int32_t lockdown_offset, lockdown_transition_period;
+  int32_t d3, d4, d5, d6, d7, d8;
+  int32_t d_reliable_cases, d_reliable_hosp, d_hosp_o1, d_hosp_o2;
+  int32_t n_dhospi, n_dhosp, n_dmorti, n_dcasei, n_rate;
+  int32_t reserved;
+  const double *dhospi;
+  const double *dmorti; /* simple: dmorti; age: unused */
+  const double *y_dcasei, *o_dcasei;
+  const double *y_dmorti, *o_dmorti, *o_wdmorti;
+  const double *y_ifr, *o_ifr, *y_hr, *o_hr, *g, *gtrimp;
+  double hosp_nbinom_size, mort_nbinom_size;
+  double case_nbinom_size1, case_nbinom_sizey2, case_nbinom_sizeo2;
+  double hosp_nbinom_size1, hosp_nbinom_size2, hosp_last7;
+} epi_data;
+
+/* ---- lifecycle ------------------------------------------------------------ */
+/* Replaces `system("R CMD SHLIB model-agen.cpp"); dyn.load("model-agen.so")`
+ * + the data/settings globals (R/models/model-age-groups2q.R:2-3).
+ * device = CUDA device ordinal.  On failure *out is NULL and the message is
+ * available from epi_last_error(NULL).                                        */
+int epi_create(const epi_model_desc *desc, const epi_data *data, int device, epi_handle **out);
+void epi_destroy(epi_handle *h);
+const char *epi_last_error(const epi_handle *h);
+int epi_abi_version(void);
+
+/* ---- model-file metadata (fit.paramnames / df_params / init) -------------- */
+/* R/models/model-age-groups2q.R:604-663; model-simple-ode-drj-cmp.R:259-270   */
+int epi_n_params(const epi_handle *h);
+const char *epi_param_name(const epi_handle *h, int i);
+int epi_df_params(const epi_handle *h, double *min, double *max, double *init);
+
+/* ---- the hot path: batched calclogl(transformParams(theta)) + calclogp(theta)
+ * Replaces n sequential calls of R/MCMC/fitMCMC-drj.R:19-21,51.
+ * theta: HOST buffer, n x d in `layout`.  logl, logp: HOST, n doubles each
+ * (either may be NULL).  status: HOST, n int32 (may be NULL).  Host<->device
+ * copies happen inside the call.                                              */
+int epi_eval(epi_handle *h, const double *theta, int64_t n, int layout,
+             double *logl, double *logp, int32_t *status);
+
+/* Same, all buffers already resident on the handle's device.  theta_soa is
+ * d x n (EPI_LAYOUT_SOA).  Launches on `stream` (a cudaStream_t passed as
+ * void*, NULL = the handle's own stream) and does not synchronise.            */
+int epi_eval_device(epi_handle *h, const double *d_theta_soa, int64_t n,
+                    double *d_logl, double *d_logp, int32_t *d_status, void *stream);
+
+/* Per-evaluation detail for parity checks: offset[n] = state$offset
+ * (data_offset or 10000), padding[n] = state$padding, terms[n*8] = the
+ * likelihood terms in reference order (age: y.loglC, o.loglC, loglH,
+ * loglHRatio, y.loglD, o.loglD; simple: loglLD, loglH, loglD), each EXCLUDING
+ * nothing (full dnbinom values).  HOST buffers, any may be NULL.              */
+int epi_eval_detail(epi_handle *h, const double *theta, int64_t n, int layout,
+                    int32_t *offset, int32_t *padding, double *terms);
+
+/* ---- calculateModel(params, period): trajectories ------------------------- */
+/* Replaces R/models/model-age-groups2q.R:50-337 / libMCMC.R:151-172 callers.
+ * theta is in MODEL space (already through transformParams).  out is HOST,
+ * n x n_series x (period) doubles for days padding+1..padding+period, series
+ * order: age: y.S,o.S,y.casei,o.casei,y.hospi,o.hospi,y.deadi,o.deadi (8);
+ * simple: S,hospi,deadi (3).                                                  */
+int epi_n_series(const epi_handle *h);
+int epi_trajectories(epi_handle *h, const double *theta, int64_t n, int layout,
+                     int32_t period, double *out, int32_t *offset, int32_t *padding);
+
+/* ---- on-device sampler (chain state never leaves the GPU) ------------------ */
+typedef struct epi_sampler_cfg {
+  int32_t kind;        /* EPI_SAMPLER_* */
+  int32_t n_chains;    /* chains on THIS device */
+  int64_t chain_id0;   /* global id of local chain 0 (Philox stream = seed, chain id) */
+  uint64_t seed;
+  double scale;        /* RWM: proposal sd = scale * (max-min) per parameter;
+                          DE-MC: gamma = scale * 2.38/sqrt(2d) */
+  double de_eps;       /* DE-MC jitter sd, relative to (max-min) */
+  double beta;         /* likelihood tempering exponent (1 = posterior) */
+  int32_t pop_size;    /* DE-MC population snapshot size (chains x ranks)      */
+  int32_t reserved;
+} epi_sampler_cfg;
+
+int epi_sampler_init(epi_handle *h, const epi_sampler_cfg *cfg, const double *theta0 /* HOST n_chains x d AOS, or NULL = init + jitter */);
+/* run n_iter fused propose -> evaluate -> accept iterations */
+int epi_sampler_run(epi_handle *h, int32_t n_iter);
+/* device pointers for the NCCL all-gather of chain states (d x n_chains SOA)  */
+int epi_sampler_state_device(epi_handle *h, double **d_theta_soa, double **d_logl, double **d_logp);
+/* install a gathered population snapshot (device pointer, pop_size x d AOS:
+ * rank-major concatenation of each rank's d x n SOA block is NOT accepted;
+ * use epi_sampler_population_buffer to gather in place)                       */
+int epi_sampler_population_buffer(epi_handle *h, double **d_pop, int64_t *n_doubles);
+int epi_sampler_population_commit(epi_handle *h, int32_t n_ranks, int32_t chains_per_rank);
+/* copy the current state to HOST: theta n_chains x d AOS, logl, logp          */
+int epi_sampler_get(epi_handle *h, double *theta, double *logl, double *logp);
+/* accumulated counters since init: iterations, accepted moves (summed over chains) */
+int epi_sampler_stats(epi_handle *h, int64_t *n_iter, int64_t *n_accept, int64_t *n_evals);
+/* record thinned draws on device: keep every `thin`-th state for up to
+ * `capacity` draws per chain; epi_sampler_draws copies them out
+ * (HOST, n_kept x n_chains x d)                                               */
+int epi_sampler_record(epi_handle *h, int32_t thin, int32_t capacity);
+int epi_sampler_draws(epi_handle *h, double *draws, double *logpost, int32_t *n_kept);
+
+/* ---- measurement helpers --------------------------------------------------- */
+/* DFMA-chain microbenchmark on the handle's device: measured FP64 TFLOP/s, the
+ * roofline denominator for the evaluation kernels (MEASURED_PEAKS.json has no
+ * FP64 entry).                                                                */
+int epi_fp64_peak(epi_handle *h, double *tflops);
+/* device time (ms) of each kernel of the most recent epi_eval/epi_eval_device
+ * when timing is enabled: [0]=pass-1 ODE, [1]=profiles+threshold, [2]=pass-2
+ * ODE, [3]=score.                                                             */
+int epi_set_timing(epi_handle *h, int enable);
+int epi_last_kernel_ms(epi_handle *h, float ms[4]);
+/* number of kernel launches issued by this handle since creation             */
+int64_t epi_launch_count(const epi_handle *h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EPIMCMC_H */
