@@ -1,0 +1,545 @@
+// epi_capi.cu — host side of libepimcmc.so: the C ABI of include/epimcmc.h.
+//
+// Handle creation snapshots the model file's R globals (data + settings) into one
+// immutable device-side DevModel: the observed series become a day-major
+// likelihood term table (R's argument recycling in dnbinom() resolved here,
+// R/models/model-age-groups2q.R:514-554,584-590), the priors become a uniform
+// term table (:433-485), df_params becomes the box.  There is no CPU path: every
+// compute entry point needs a CUDA device.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/epimcmc.h"
+#include "epi_handle.h"
+#include "epi_launch.h"
+
+using namespace epi;
+
+static thread_local std::string g_last_error;
+
+int epi_fail(epi_handle *h, int rc, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (h) h->err = buf;
+  g_last_error = buf;
+  return rc;
+}
+
+#define CUDA_OK(h, call)                                                                       \
+  do {                                                                                         \
+    cudaError_t e_ = (call);                                                                   \
+    if (e_ != cudaSuccess)                                                                     \
+      return epi_fail(h, (e_ == cudaErrorNoDevice || e_ == cudaErrorInsufficientDriver) ? EPI_ERR_NO_DEVICE : EPI_ERR_CUDA, \
+                      "%s: %s", #call, cudaGetErrorString(e_));                                \
+  } while (0)
+
+static double age_gamma() { return 1.0 / ((4.7 - (3.0 + 1.0)) * 2.0); }  // model-age-groups2q.R:8-15
+
+// ------------------------------------------------------------- metadata tables
+static const char *kAgeNames[45] = {  // fit.paramnames, model-age-groups2q.R:604-618
+    "betay0", "betao0", "betayo0", "betay1", "betao1", "betayo1", "betay2", "betao2", "betayo2",
+    "y.CR", "y.HR", "y.HL", "y.DL", "o.CR", "o.HR", "o.HL", "o.DL", "t0_morts", "t0o", "HLsd", "DLsd",
+    "fyifr", "fyhr", "t3o", "t4o", "betay4", "betao4", "betayo4", "betay5", "betao5", "betayo5",
+    "t6o", "betay6", "betao6", "betayo6", "t7o", "betay7", "betao7", "betayo7", "fy9", "fo9", "fyo9",
+    "ifrred", "y.CL", "o.CL"};
+static const char *kSimpleNames[9] = {  // model-simple-ode-drj-cmp.R:259-260 (+ Nef, README.md:91-93)
+    "R0", "Rt", "Tinf0", "Tinft", "logHR", "HL", "DL", "lockdownmort", "Nef"};
+
+static void df_params_host(int flavour, const epi_data &D, double *mn, double *mx, double *init) {
+  if (flavour == EPI_FLAVOUR_AGE2Q) {  // model-age-groups2q.R:624-663
+    const double g = age_gamma();
+    const double lo = D.lockdown_offset, ltp = D.lockdown_transition_period;
+    const double i_[45] = {2.7, 1.7, 1.7, 2.3, 0.8, 0.8, 0.6, 0.4, 0.1, 2000, 1, 10, 15, 50, 2.5, 10, 21,
+                           16, -10, 5, 5, 0.15, 0.5, D.d3 - lo - ltp, (double)(D.d4 - D.d3), 1, 0.2, 0.05,
+                           0.7, 0.2, 0.01, (double)(D.d6 - D.d5), 1.1, 0.4, 0.03, (double)(D.d7 - D.d6), 1.4, 0.4, 0.08,
+                           0.85, 0.85, 0.85, 0.4, 10, 10};
+    const double mn_[45] = {2 * g, 2 * g, 2 * g, 1 * g, 1 * g, 1 * g, 0.05 * g, 0.01 * g, 0.01 * g,
+                            3, 0.5, 6, 10, 3, 0.5, 6, 10, 0, -30, 2, 2, 0.05, 0.05, 60,
+                            10, 0.05 * g, 0.01 * g, 0.002 * g, 0.05 * g, 0.01 * g, 0.002 * g,
+                            10, 0.05 * g, 0.01 * g, 0.002 * g, 10, 0.05 * g, 0.01 * g, 0.002 * g,
+                            0.6, 0.6, 0.6, 0.1, 4, 4};
+    const double mx_[45] = {8 * g, 8 * g, 8 * g, 5 * g, 5 * g, 5 * g, 2 * g, 2 * g, 2 * g,
+                            5000, 1.5, 15, 25, 100, 6, 15, 25,
+                            std::fmax(D.dmort_last / 10, D.total_deaths_at_lockdown * 10),
+                            30, 9, 9, 1.5, 1.5, 90,
+                            50, 3 * g, 3 * g, 3 * g, 1.5 * g, 1.5 * g, 0.5 * g,
+                            50, 3 * g, 3 * g, 0.5 * g, 50, 3 * g, 3 * g, 0.5 * g,
+                            1.1, 1.1, 1.1, 0.7, 14, 14};
+    for (int i = 0; i < 45; ++i) { mn[i] = mn_[i]; mx[i] = mx_[i]; init[i] = i_[i]; }
+  } else {  // model-simple-ode-drj-cmp.R:263-270
+    const double tdl = D.total_deaths_at_lockdown;
+    const double i_[9] = {2.9, 0.9, 3, 3, std::log(0.02), 10, 20, tdl, 0.7};
+    const double mn_[9] = {0.1, 0.1, 0.1, 0.1, std::log(0.001), 5, 5, 0, 0.05};
+    const double mx_[9] = {8, 8, 8, 8, std::log(0.5), 30, 40, std::fmax(D.dmort_last / 10, tdl * 10), 1.0};
+    const int d = flavour == EPI_FLAVOUR_NE ? 9 : 8;
+    for (int i = 0; i < d; ++i) { mn[i] = mn_[i]; mx[i] = mx_[i]; init[i] = i_[i]; }
+  }
+}
+
+// ---------------------------------------------------------- likelihood table
+struct NbCall {  // one sum(dnbinom(x[x1..x2], mu = pmax(floor, m[dstart+r1 .. dstart+r2]), size, log=T))
+  int series, term;
+  const double *x;
+  int xlen, x1, x2;  // 1-based inclusive
+  int r1, r2;        // model index relative to dstart
+  const double *size;
+  int ns;
+};
+
+static bool is_count(double x) { return x >= 0 && std::isfinite(x) && x == std::nearbyint(x); }
+
+static int build_term_table(epi_handle *h, const std::vector<NbCall> &calls, const int *n_obs, int n_series) {
+  std::vector<std::vector<std::vector<Slot>>> per(n_series);
+  for (int s = 0; s < n_series; ++s) per[s].resize(n_obs[s]);
+  long double cst[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (const NbCall &c : calls) {
+    const int lx = c.x2 - c.x1 + 1, lm = c.r2 - c.r1 + 1;
+    if (lx <= 0 || lm <= 0 || c.x1 < 1 || c.x2 > c.xlen || c.r1 < 0 || c.r2 >= n_obs[c.series])
+      return epi_fail(h, EPI_ERR_ARG,
+                      "inconsistent observation windows (series %d: x[%d..%d] of %d, model rel [%d..%d] of %d): "
+                      "check d_reliable_* and the series lengths",
+                      c.series, c.x1, c.x2, c.xlen, c.r1, c.r2, n_obs[c.series]);
+    int len = lx > lm ? lx : lm;
+    if (c.ns > len) len = c.ns;
+    for (int k = 0; k < len; ++k) {  // R recycles every argument to the longest
+      const double x = c.x[c.x1 - 1 + k % lx];
+      const double size = c.size[k % c.ns];
+      const int rel = c.r1 + k % lm;
+      if (!is_count(x)) return epi_fail(h, EPI_ERR_ARG, "observed counts must be non-negative integers (got %g)", x);
+      if (!(size > 0)) return epi_fail(h, EPI_ERR_ARG, "negative-binomial size must be > 0 (got %g)", size);
+      per[c.series][rel].push_back(Slot{x, x + size});
+      cst[c.term] += lgammal((long double)x + size) - lgammal((long double)size) - lgammal((long double)x + 1.0L) +
+                     (long double)size * logl((long double)size);
+    }
+  }
+  for (int s = 0; s < n_series; ++s) {
+    size_t K = 1;
+    for (auto &v : per[s]) K = std::max(K, v.size());
+    std::vector<Slot> flat((size_t)n_obs[s] * K, Slot{0.0, 0.0});
+    for (int r = 0; r < n_obs[s]; ++r)
+      for (size_t k = 0; k < per[s][r].size(); ++k) flat[(size_t)r * K + k] = per[s][r][k];
+    Slot *d = nullptr;
+    CUDA_OK(h, cudaMalloc(&d, flat.size() * sizeof(Slot)));
+    h->owned.push_back(d);
+    CUDA_OK(h, cudaMemcpy(d, flat.data(), flat.size() * sizeof(Slot), cudaMemcpyHostToDevice));
+    h->M.slots[s] = d;
+    h->M.K[s] = (int)K;
+    h->M.n_obs[s] = n_obs[s];
+    h->n_terms += (int)flat.size();
+  }
+  for (int t = 0; t < 8; ++t) h->M.term_const[t] += (double)cst[t];
+  return EPI_OK;
+}
+
+static int upload(epi_handle *h, const double *src, int n, const double **dst) {
+  double *d = nullptr;
+  CUDA_OK(h, cudaMalloc(&d, sizeof(double) * (size_t)n));
+  h->owned.push_back(d);
+  CUDA_OK(h, cudaMemcpy(d, src, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice));
+  *dst = d;
+  return EPI_OK;
+}
+
+// ---------------------------------------------------------------- prior table
+static PriorTerm pt_sum(int ia, int ib, double c0, double ca, double cb, double mean, double sd) {
+  return PriorTerm{ia, ib, 0, 0, c0, ca, cb, mean, sd};
+}
+static PriorTerm pt_norm(int ia, double mean, double sd) { return pt_sum(ia, -1, 0, 1, 0, mean, sd); }
+static PriorTerm pt_lnorm(int ia, double meanlog, double sdlog) { return PriorTerm{ia, -1, 0, 1, 0, 1, 0, meanlog, sdlog}; }
+static PriorTerm pt_lratio(int ia, int ib, double sdlog) { return PriorTerm{ia, ib, 2, 1, 0, 0, 0, 0.0, sdlog}; }
+
+static std::vector<PriorTerm> build_prior(int flavour, const epi_data &D) {
+  std::vector<PriorTerm> p;
+  if (flavour == EPI_FLAVOUR_AGE2Q) {  // calclogp, model-age-groups2q.R:433-485 (0-based theta indices)
+    const double g = age_gamma(), lo_ltp = D.lockdown_offset + D.lockdown_transition_period;
+    const double SD = std::log(2.0), lSD = std::log(1.5);
+    p.push_back(pt_norm(18, 0, 10));
+    p.push_back(pt_sum(23, -1, lo_ltp, 1, 0, D.d3, 10));
+    p.push_back(pt_sum(23, 24, lo_ltp, 1, 1, D.d4, 10));
+    p.push_back(pt_sum(31, -1, D.d5, 1, 0, D.d6, 5));
+    p.push_back(pt_sum(31, 35, D.d5, 1, 1, D.d7, 4));
+    const int r2[12][2] = {{0, 3}, {1, 4}, {2, 5}, {3, 6}, {4, 7}, {5, 8}, {6, 25}, {7, 26}, {8, 27}, {28, 32}, {29, 33}, {30, 34}};
+    for (auto &r : r2) p.push_back(pt_lratio(r[0], r[1], SD));
+    const int r15[3][2] = {{32, 36}, {33, 37}, {34, 38}};
+    for (auto &r : r15) p.push_back(pt_lratio(r[0], r[1], lSD));
+    p.push_back(pt_norm(37, 0.5 * g, 0.2 * g));
+    p.push_back(PriorTerm{37, 40, 1, 0, 0, 0, 0, 0.5 * g, 0.2 * g});  // betao8 * fo9
+    for (int i : {39, 40, 41}) p.push_back(pt_lnorm(i, std::log(0.85), std::log(1.07)));
+    p.push_back(pt_norm(19, 5, 1));
+    p.push_back(pt_norm(20, 5, 1));
+    p.push_back(pt_norm(43, 10, 3));
+    p.push_back(pt_norm(44, 10, 3));
+    p.push_back(pt_norm(11, 13, 3));
+    p.push_back(pt_norm(15, 13, 3));
+    p.push_back(pt_norm(12, 21, 0.5));
+    p.push_back(pt_norm(16, 21, 0.5));
+    p.push_back(pt_lnorm(21, std::log(0.3), std::log(2.0)));
+    p.push_back(pt_lnorm(22, std::log(0.3), std::log(2.0)));
+    p.push_back(pt_lnorm(42, std::log(0.35), std::log(1.3)));
+    p.push_back(pt_lnorm(10, 0, lSD));
+    p.push_back(pt_lnorm(14, 0, lSD));
+  } else {  // calclogp, model-simple-ode-drj-cmp.R:156-179: G0 = Tinc + Tinf0/2, Gt = Tinc + Tinft/2
+    p.push_back(pt_norm(6, 21, 4));
+    p.push_back(pt_sum(2, -1, 3.0, 0.5, 0, 5, 1));
+    p.push_back(pt_sum(2, 3, 0.0, 0.5, -0.5, 0, 1.5));
+  }
+  return p;
+}
+
+// -------------------------------------------------------------------- create
+static int fill_model(epi_handle *h, const epi_model_desc &desc, const epi_data &D) {
+  DevModel &M = h->M;
+  std::memset(&M, 0, sizeof M);
+  M.flavour = desc.flavour;
+  M.P = desc.period;
+  M.m = desc.substeps;
+  M.lockdown_offset = D.lockdown_offset;
+  M.ltp = D.lockdown_transition_period;
+  std::vector<NbCall> calls;
+  int n_obs[kMaxSeries] = {0, 0, 0, 0, 0};
+  if (desc.flavour == EPI_FLAVOUR_AGE2Q) {
+    M.d = 45;
+    M.P1 = 60;  // period1, model-age-groups2q.R:160
+    if (desc.period < 60) return epi_fail(h, EPI_ERR_ARG, "age-2q needs period >= 60 (pass 1 integrates 60 days)");
+    if (!(D.y_N > 1 && D.o_N > 0)) return epi_fail(h, EPI_ERR_ARG, "y_N / o_N missing");
+    if (D.n_rate < 1 || !D.y_ifr || !D.o_ifr || !D.y_hr || !D.o_hr || !D.g || !D.gtrimp)
+      return epi_fail(h, EPI_ERR_ARG, "rate vectors y_ifr/o_ifr/y_hr/o_hr/g/gtrimp missing");
+    if (!D.y_dcasei || !D.o_dcasei || !D.dhospi || !D.y_dmorti || !D.o_dmorti || !D.o_wdmorti)
+      return epi_fail(h, EPI_ERR_ARG, "observed series missing");
+    M.Ny = D.y_N; M.No = D.o_N; M.N = D.y_N + D.o_N;
+    M.a1 = 1.0 / 3.0; M.a2 = 1.0 / 1.0; M.gamma = age_gamma();
+    M.ifr_y1 = D.y_ifr[0]; M.ifr_o1 = D.o_ifr[0];
+    M.d5 = D.d5; M.d8 = D.d8;
+    M.n_rate = D.n_rate;
+    M.d_hosp_o1 = D.d_hosp_o1; M.d_hosp_o2 = D.d_hosp_o2;
+    int rc;
+    if ((rc = upload(h, D.y_ifr, D.n_rate, &M.y_ifr))) return rc;
+    if ((rc = upload(h, D.o_ifr, D.n_rate, &M.o_ifr))) return rc;
+    if ((rc = upload(h, D.y_hr, D.n_rate, &M.y_hr))) return rc;
+    if ((rc = upload(h, D.o_hr, D.n_rate, &M.o_hr))) return rc;
+    if ((rc = upload(h, D.g, D.n_rate, &M.g))) return rc;
+    if ((rc = upload(h, D.gtrimp, D.n_rate, &M.gtrimp))) return rc;
+    M.n_series = 5;
+    const int nc = D.n_dcasei, nh = D.n_dhospi, nhh = D.n_dhosp, nm = D.n_dmorti;
+    const int r = D.d_reliable_cases, rh = D.d_reliable_hosp;
+    if (D.d_hosp_o1 < 0 || D.d_hosp_o2 < D.d_hosp_o1 || D.d_hosp_o2 >= nh)
+      return epi_fail(h, EPI_ERR_ARG, "d_hosp_o1/o2 outside the hospital series");
+    n_obs[0] = nc; n_obs[1] = nc; n_obs[2] = nh; n_obs[3] = nm; n_obs[4] = nm;
+    const int term_of[5] = {0, 1, 2, 4, 5};
+    const double fl[5] = {0.1, 0.1, 0.1, 0.001, 0.001};
+    for (int s = 0; s < 5; ++s) { M.term_of[s] = term_of[s]; M.floor_[s] = fl[s]; }
+    h->sizes = {D.case_nbinom_size1, D.case_nbinom_sizey2, D.case_nbinom_sizeo2, D.hosp_nbinom_size1,
+                D.hosp_nbinom_size2, D.hosp_nbinom_size2 * D.hosp_last7, D.mort_nbinom_size * 2};
+    h->size_vec.resize(nm);
+    for (int i = 0; i < nm; ++i) h->size_vec[i] = D.o_wdmorti[i] * D.mort_nbinom_size;
+    const double *sz = h->sizes.data();
+    // cases, model-age-groups2q.R:514-526 (note the x/mu length mismatch -> recycling)
+    calls.push_back({0, 0, D.y_dcasei, nc, 1, r - 1, 0, r, sz + 0, 1});
+    calls.push_back({0, 0, D.y_dcasei, nc, r, nc, r + 1, nc - 1, sz + 1, 1});
+    calls.push_back({1, 1, D.o_dcasei, nc, 1, r - 1, 0, r, sz + 0, 1});
+    calls.push_back({1, 1, D.o_dcasei, nc, r, nc, r + 1, nc - 1, sz + 2, 1});
+    // hosp, :544-554
+    calls.push_back({2, 2, D.dhospi, nh, 1, rh - 1, 0, rh, sz + 3, 1});
+    calls.push_back({2, 2, D.dhospi, nh, rh, nhh, rh + 1, nh - 1, sz + 4, 1});
+    calls.push_back({2, 2, D.dhospi, nh, nhh - 7, nhh, nh - 1 - 7, nh - 1, sz + 5, 1});
+    // deaths, :584-590
+    calls.push_back({3, 4, D.y_dmorti, nm, 1, nm, 0, nm - 1, sz + 6, 1});
+    calls.push_back({4, 5, D.o_dmorti, nm, 1, nm, 0, nm - 1, h->size_vec.data(), nm});
+    M.d3 = D.d3; M.d4 = D.d4; M.d5d = D.d5; M.d6 = D.d6; M.d7 = D.d7;
+    M.lo_ltp = D.lockdown_offset + D.lockdown_transition_period;
+  } else if (desc.flavour == EPI_FLAVOUR_SIMPLE || desc.flavour == EPI_FLAVOUR_NE) {
+    M.d = desc.flavour == EPI_FLAVOUR_NE ? 9 : 8;
+    M.P1 = desc.period;  // pass 1 covers the whole period, model-simple-ode-drj-cmp.R:82-86
+    if (!(D.N > 1)) return epi_fail(h, EPI_ERR_ARG, "N missing");
+    if (!D.dhospi || !D.dmorti || D.n_dhospi < 1 || D.n_dmorti < 1) return epi_fail(h, EPI_ERR_ARG, "dhospi/dmorti missing");
+    M.N = D.N;
+    M.a_inc = 1.0 / 3.0;
+    M.n_series = 2;
+    n_obs[0] = D.n_dhospi; n_obs[1] = D.n_dmorti;
+    M.term_of[0] = 1; M.term_of[1] = 2;
+    M.floor_[0] = 0.1; M.floor_[1] = 0.1;
+    h->sizes = {D.hosp_nbinom_size, D.mort_nbinom_size};
+    const double *sz = h->sizes.data();
+    calls.push_back({0, 1, D.dhospi, D.n_dhospi, 1, D.n_dhospi, 0, D.n_dhospi - 1, sz + 0, 1});
+    calls.push_back({1, 2, D.dmorti, D.n_dmorti, 1, D.n_dmorti, 0, D.n_dmorti - 1, sz + 1, 1});
+    // loglLD, :203-204
+    const double x = D.total_deaths_at_lockdown, size = D.mort_nbinom_size;
+    if (!is_count(x) || !(size > 0)) return epi_fail(h, EPI_ERR_ARG, "total_deaths_at_lockdown must be a count, sizes > 0");
+    M.tdl = x; M.mort_size = size;
+    M.term_const[0] = (double)(lgammal((long double)x + size) - lgammal((long double)size) - lgammal((long double)x + 1.0L) +
+                               (long double)size * logl((long double)size));
+  } else {
+    return epi_fail(h, EPI_ERR_ARG, "unknown flavour %d", desc.flavour);
+  }
+  if (desc.period < 2 || desc.period > 4096) return epi_fail(h, EPI_ERR_ARG, "period out of range");
+  if (desc.substeps < 1 || desc.substeps > 64) return epi_fail(h, EPI_ERR_ARG, "substeps out of range");
+  for (int s = 0; s < M.n_series; ++s)
+    if (n_obs[s] > desc.period) return epi_fail(h, EPI_ERR_ARG, "observed series longer than FitTotalPeriod");
+  int rc = build_term_table(h, calls, n_obs, M.n_series);
+  if (rc) return rc;
+  df_params_host(desc.flavour, D, h->box_min, h->box_max, h->init);
+  if ((rc = upload(h, h->box_min, M.d, &M.box_min))) return rc;
+  if ((rc = upload(h, h->box_max, M.d, &M.box_max))) return rc;
+  std::vector<PriorTerm> pr = build_prior(desc.flavour, D);
+  PriorTerm *dp = nullptr;
+  CUDA_OK(h, cudaMalloc(&dp, pr.size() * sizeof(PriorTerm)));
+  h->owned.push_back(dp);
+  CUDA_OK(h, cudaMemcpy(dp, pr.data(), pr.size() * sizeof(PriorTerm), cudaMemcpyHostToDevice));
+  h->PT = dp;
+  h->n_prior = (int)pr.size();
+  return EPI_OK;
+}
+
+extern "C" int epi_abi_version(void) { return EPI_ABI_VERSION; }
+
+extern "C" int epi_create(const epi_model_desc *desc, const epi_data *data, int device, epi_handle **out) {
+  if (out) *out = nullptr;
+  if (!desc || !data || !out) return epi_fail(nullptr, EPI_ERR_ARG, "null argument");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return epi_fail(nullptr, EPI_ERR_NO_DEVICE, "no CUDA device (%s); libepimcmc has no CPU fallback",
+                    e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+  if (device < 0 || device >= ndev) return epi_fail(nullptr, EPI_ERR_ARG, "device %d out of range (%d devices)", device, ndev);
+  epi_handle *h = new epi_handle();
+  h->device = device;
+  h->desc = *desc;
+  int rc = EPI_OK;
+  do {
+    if (cudaSetDevice(device) != cudaSuccess) { rc = epi_fail(h, EPI_ERR_CUDA, "cudaSetDevice(%d) failed", device); break; }
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { rc = epi_fail(h, EPI_ERR_CUDA, "stream"); break; }
+    for (auto &ev : h->ev) cudaEventCreate(&ev);
+    rc = fill_model(h, *desc, *data);
+  } while (0);
+  if (rc) {
+    std::string msg = h->err;
+    epi_destroy(h);
+    g_last_error = msg;
+    return rc;
+  }
+  *out = h;
+  return EPI_OK;
+}
+
+static void free_workspace(Workspace &w) {
+  cudaFree(w.theta); cudaFree(w.aos); cudaFree(w.hist1); cudaFree(w.hist2); cudaFree(w.W); cudaFree(w.pmeta);
+  cudaFree(w.offset); cudaFree(w.pad); cudaFree(w.status); cudaFree(w.logl); cudaFree(w.logp); cudaFree(w.terms);
+  cudaFree(w.series);
+  w = Workspace();
+}
+
+extern "C" void epi_destroy(epi_handle *h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  epi_sampler_free(h);
+  free_workspace(h->ws);
+  free_workspace(h->ws_traj);
+  for (void *p : h->owned) cudaFree(p);
+  for (auto &ev : h->ev) if (ev) cudaEventDestroy(ev);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+extern "C" const char *epi_last_error(const epi_handle *h) { return h ? h->err.c_str() : g_last_error.c_str(); }
+extern "C" int epi_n_params(const epi_handle *h) { return h ? h->M.d : 0; }
+extern "C" int epi_n_series(const epi_handle *h) { return h ? (h->M.flavour == EPI_FLAVOUR_AGE2Q ? 8 : 3) : 0; }
+extern "C" const char *epi_param_name(const epi_handle *h, int i) {
+  if (!h || i < 0 || i >= h->M.d) return nullptr;
+  return h->M.flavour == EPI_FLAVOUR_AGE2Q ? kAgeNames[i] : kSimpleNames[i];
+}
+extern "C" int epi_df_params(const epi_handle *h, double *mn, double *mx, double *init) {
+  if (!h) return EPI_ERR_ARG;
+  for (int i = 0; i < h->M.d; ++i) {
+    if (mn) mn[i] = h->box_min[i];
+    if (mx) mx[i] = h->box_max[i];
+    if (init) init[i] = h->init[i];
+  }
+  return EPI_OK;
+}
+extern "C" int64_t epi_launch_count(const epi_handle *h) { return h ? h->launches : 0; }
+
+// ----------------------------------------------------------------- workspace
+int epi_ensure_workspace(epi_handle *h, Workspace &w, const DevModel &M, int64_t n, bool want_series) {
+  const int NG = M.flavour == EPI_FLAVOUR_AGE2Q ? 2 : 1, NK = M.flavour == EPI_FLAVOUR_AGE2Q ? 6 : 2;
+  const int NS = M.flavour == EPI_FLAVOUR_AGE2Q ? 8 : 3;
+  if (n <= w.cap && M.P <= w.P && (!want_series || w.series)) return EPI_OK;
+  cudaStreamSynchronize(h->stream);
+  const int64_t cap = std::max<int64_t>(n, w.cap);
+  const int P = std::max(M.P, w.P), P1 = std::max(M.P1, w.P1);
+  const bool series = want_series || w.series;
+  free_workspace(w);
+  const int64_t tiles = (cap + kTile - 1) / kTile;
+  const int64_t ld = tiles * kTile;
+  CUDA_OK(h, cudaMalloc(&w.theta, sizeof(double) * (size_t)(M.d * ld)));
+  CUDA_OK(h, cudaMalloc(&w.aos, sizeof(double) * (size_t)(M.d * ld)));
+  CUDA_OK(h, cudaMalloc(&w.hist1, sizeof(double) * (size_t)(tiles * P1 * NG * kTile)));
+  CUDA_OK(h, cudaMalloc(&w.hist2, sizeof(double) * (size_t)(tiles * P * NG * kTile)));
+  CUDA_OK(h, cudaMalloc(&w.W, sizeof(double) * (size_t)(ld * NK * EPI_MAX_TAPS)));
+  CUDA_OK(h, cudaMalloc(&w.pmeta, sizeof(int2) * (size_t)(ld * NK)));
+  CUDA_OK(h, cudaMalloc(&w.offset, sizeof(int) * (size_t)ld));
+  CUDA_OK(h, cudaMalloc(&w.pad, sizeof(int) * (size_t)ld));
+  CUDA_OK(h, cudaMalloc(&w.status, sizeof(int) * (size_t)ld));
+  CUDA_OK(h, cudaMalloc(&w.logl, sizeof(double) * (size_t)ld));
+  CUDA_OK(h, cudaMalloc(&w.logp, sizeof(double) * (size_t)ld));
+  CUDA_OK(h, cudaMalloc(&w.terms, sizeof(double) * (size_t)ld * 8));
+  if (series) CUDA_OK(h, cudaMalloc(&w.series, sizeof(double) * (size_t)ld * NS * P));
+  w.cap = cap; w.ld = ld; w.P = P; w.P1 = P1;
+  return EPI_OK;
+}
+
+int epi_launch_eval_ws(epi_handle *h, Workspace &w, const DevModel &M, const double *d_theta, int64_t ld, int64_t n,
+                       int model_space, double *d_logl, double *d_logp, int *d_status, double *d_terms,
+                       double *d_series, cudaStream_t stream) {
+  EvalArgs a;
+  a.M = &M; a.PT = h->PT; a.n_prior = h->n_prior;
+  a.theta = d_theta; a.ld = ld; a.n = n; a.model_space = model_space;
+  a.hist1 = w.hist1; a.hist2 = w.hist2; a.W = w.W; a.pmeta = w.pmeta;
+  a.offset = w.offset; a.pad = w.pad; a.status = d_status ? d_status : w.status;
+  a.logl = d_logl; a.logp = d_logp; a.terms = d_terms; a.series_out = d_series;
+  a.stream = stream;
+  a.ev = h->timing ? h->ev : nullptr;
+  cudaError_t e = launch_eval(a);
+  h->launches += 4;
+  if (e != cudaSuccess) return epi_fail(h, EPI_ERR_CUDA, "kernel launch: %s", cudaGetErrorString(e));
+  return EPI_OK;
+}
+
+// ---------------------------------------------------------------------- eval
+extern "C" int epi_eval_device(epi_handle *h, const double *d_theta_soa, int64_t n, double *d_logl, double *d_logp,
+                               int32_t *d_status, void *stream) {
+  if (!h || !d_theta_soa || n < 0) return epi_fail(h, EPI_ERR_ARG, "bad argument");
+  if (n == 0) return EPI_OK;
+  CUDA_OK(h, cudaSetDevice(h->device));
+  int rc = epi_ensure_workspace(h, h->ws, h->M, n, false);
+  if (rc) return rc;
+  return epi_launch_eval_ws(h, h->ws, h->M, d_theta_soa, n, n, 0, d_logl, d_logp, d_status, nullptr, nullptr,
+                            stream ? (cudaStream_t)stream : h->stream);
+}
+
+static int stage_theta(epi_handle *h, Workspace &w, const double *theta, int64_t n, int layout, int d) {
+  if (layout == EPI_LAYOUT_SOA) {
+    CUDA_OK(h, cudaMemcpy2DAsync(w.theta, sizeof(double) * (size_t)w.ld, theta, sizeof(double) * (size_t)n,
+                                 sizeof(double) * (size_t)n, d, cudaMemcpyHostToDevice, h->stream));
+  } else if (layout == EPI_LAYOUT_AOS) {
+    CUDA_OK(h, cudaMemcpyAsync(w.aos, theta, sizeof(double) * (size_t)(n * d), cudaMemcpyHostToDevice, h->stream));
+    cudaError_t e = launch_aos_to_soa(w.aos, w.theta, n, d, w.ld, h->stream);
+    h->launches += 1;
+    if (e != cudaSuccess) return epi_fail(h, EPI_ERR_CUDA, "transpose: %s", cudaGetErrorString(e));
+  } else {
+    return epi_fail(h, EPI_ERR_ARG, "unknown layout %d", layout);
+  }
+  return EPI_OK;
+}
+
+extern "C" int epi_eval(epi_handle *h, const double *theta, int64_t n, int layout, double *logl, double *logp,
+                        int32_t *status) {
+  if (!h || !theta || n < 0) return epi_fail(h, EPI_ERR_ARG, "bad argument");
+  if (n == 0) return EPI_OK;
+  CUDA_OK(h, cudaSetDevice(h->device));
+  int rc = epi_ensure_workspace(h, h->ws, h->M, n, false);
+  if (rc) return rc;
+  Workspace &w = h->ws;
+  if ((rc = stage_theta(h, w, theta, n, layout, h->M.d))) return rc;
+  if ((rc = epi_launch_eval_ws(h, w, h->M, w.theta, w.ld, n, 0, w.logl, w.logp, nullptr, nullptr, nullptr, h->stream))) return rc;
+  if (logl) CUDA_OK(h, cudaMemcpyAsync(logl, w.logl, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+  if (logp) CUDA_OK(h, cudaMemcpyAsync(logp, w.logp, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+  if (status) CUDA_OK(h, cudaMemcpyAsync(status, w.status, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_OK(h, cudaStreamSynchronize(h->stream));
+  return EPI_OK;
+}
+
+extern "C" int epi_eval_detail(epi_handle *h, const double *theta, int64_t n, int layout, int32_t *offset,
+                               int32_t *padding, double *terms) {
+  if (!h || !theta || n < 0) return epi_fail(h, EPI_ERR_ARG, "bad argument");
+  if (n == 0) return EPI_OK;
+  CUDA_OK(h, cudaSetDevice(h->device));
+  int rc = epi_ensure_workspace(h, h->ws, h->M, n, false);
+  if (rc) return rc;
+  Workspace &w = h->ws;
+  if ((rc = stage_theta(h, w, theta, n, layout, h->M.d))) return rc;
+  if ((rc = epi_launch_eval_ws(h, w, h->M, w.theta, w.ld, n, 0, w.logl, w.logp, nullptr, w.terms, nullptr, h->stream))) return rc;
+  if (offset) CUDA_OK(h, cudaMemcpyAsync(offset, w.offset, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+  if (padding) CUDA_OK(h, cudaMemcpyAsync(padding, w.pad, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+  if (terms) CUDA_OK(h, cudaMemcpyAsync(terms, w.terms, sizeof(double) * (size_t)n * 8, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_OK(h, cudaStreamSynchronize(h->stream));
+  return EPI_OK;
+}
+
+extern "C" int epi_trajectories(epi_handle *h, const double *theta, int64_t n, int layout, int32_t period, double *out,
+                                int32_t *offset, int32_t *padding) {
+  if (!h || !theta || !out || n < 0) return epi_fail(h, EPI_ERR_ARG, "bad argument");
+  if (n == 0) return EPI_OK;
+  const bool age = h->M.flavour == EPI_FLAVOUR_AGE2Q;
+  if (period < (age ? 60 : 2) || period > 4096) return epi_fail(h, EPI_ERR_ARG, "period out of range");
+  CUDA_OK(h, cudaSetDevice(h->device));
+  DevModel M = h->M;  // calculateModel(params, period): same data, another horizon
+  M.P = period;
+  if (!age) M.P1 = period;
+  const int NS = age ? 8 : 3;
+  int rc = epi_ensure_workspace(h, h->ws_traj, M, n, true);
+  if (rc) return rc;
+  Workspace &w = h->ws_traj;
+  if ((rc = stage_theta(h, w, theta, n, layout, M.d))) return rc;
+  if ((rc = epi_launch_eval_ws(h, w, M, w.theta, w.ld, n, 1, nullptr, nullptr, nullptr, nullptr, w.series, h->stream))) return rc;
+  CUDA_OK(h, cudaMemcpyAsync(out, w.series, sizeof(double) * (size_t)n * NS * period, cudaMemcpyDeviceToHost, h->stream));
+  if (offset) CUDA_OK(h, cudaMemcpyAsync(offset, w.offset, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+  if (padding) CUDA_OK(h, cudaMemcpyAsync(padding, w.pad, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_OK(h, cudaStreamSynchronize(h->stream));
+  return EPI_OK;
+}
+
+// --------------------------------------------------------------- measurement
+extern "C" int epi_set_timing(epi_handle *h, int enable) {
+  if (!h) return EPI_ERR_ARG;
+  h->timing = enable != 0;
+  return EPI_OK;
+}
+
+extern "C" int epi_last_kernel_ms(epi_handle *h, float ms[4]) {
+  if (!h || !ms) return EPI_ERR_ARG;
+  if (!h->timing) return epi_fail(h, EPI_ERR_STATE, "timing not enabled");
+  CUDA_OK(h, cudaSetDevice(h->device));
+  CUDA_OK(h, cudaEventSynchronize(h->ev[4]));
+  for (int i = 0; i < 4; ++i) CUDA_OK(h, cudaEventElapsedTime(&ms[i], h->ev[i], h->ev[i + 1]));
+  return EPI_OK;
+}
+
+extern "C" int epi_fp64_peak(epi_handle *h, double *tflops) {
+  if (!h || !tflops) return EPI_ERR_ARG;
+  CUDA_OK(h, cudaSetDevice(h->device));
+  cudaDeviceProp prop;
+  CUDA_OK(h, cudaGetDeviceProperties(&prop, h->device));
+  const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 15;
+  double *buf = nullptr;
+  CUDA_OK(h, cudaMalloc(&buf, sizeof(double) * (size_t)blocks * threads));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  double best = 0;
+  for (int rep = 0; rep < 6; ++rep) {
+    cudaEventRecord(e0, h->stream);
+    launch_dfma(buf, blocks, threads, iters, h->stream);
+    cudaEventRecord(e1, h->stream);
+    cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double fl = 2.0 * 8.0 * (double)iters * blocks * threads;
+    if (rep > 0 && ms > 0) best = std::max(best, fl / (ms * 1e-3) / 1e12);
+    h->launches += 1;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(buf);
+  *tflops = best;
+  return EPI_OK;
+}

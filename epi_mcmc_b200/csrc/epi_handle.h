@@ -1,0 +1,54 @@
+// epi_handle.h — the opaque handle behind include/epimcmc.h (host side only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/epimcmc.h"
+#include "epi_device.cuh"
+
+namespace epi {
+
+// device scratch of one evaluation batch; grown on demand, never shrunk
+struct Workspace {
+  int64_t cap = 0, ld = 0;
+  int P = 0, P1 = 0;
+  double *theta = nullptr, *aos = nullptr;    // staged theta: SoA d x ld, and the AoS landing buffer
+  double *hist1 = nullptr, *hist2 = nullptr;  // S histories, [tile][day][group][32]
+  double *W = nullptr;                        // latency profiles, [chain][NK][EPI_MAX_TAPS]
+  int2 *pmeta = nullptr;                      // (dmin, n) per profile
+  int *offset = nullptr, *pad = nullptr, *status = nullptr;
+  double *logl = nullptr, *logp = nullptr, *terms = nullptr, *series = nullptr;
+};
+
+struct SamplerState;
+
+}  // namespace epi
+
+struct epi_handle {
+  int device = 0;
+  epi_model_desc desc{};
+  epi::DevModel M{};
+  const epi::PriorTerm *PT = nullptr;
+  int n_prior = 0;
+  int n_terms = 0;
+  double box_min[EPI_MAX_PARAMS]{}, box_max[EPI_MAX_PARAMS]{}, init[EPI_MAX_PARAMS]{};
+  std::vector<double> sizes, size_vec;  // NB size arguments kept alive while the term table is built
+  std::vector<void *> owned;            // device allocations freed at destroy
+  epi::Workspace ws, ws_traj;
+  epi::SamplerState *sampler = nullptr;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  bool timing = false;
+  int64_t launches = 0;
+  std::string err;
+};
+
+int epi_fail(epi_handle *h, int rc, const char *fmt, ...);
+void epi_sampler_free(epi_handle *h);
+int epi_ensure_workspace(epi_handle *h, epi::Workspace &w, const epi::DevModel &M, int64_t n, bool want_series);
+int epi_launch_eval_ws(epi_handle *h, epi::Workspace &w, const epi::DevModel &M, const double *d_theta, int64_t ld,
+                       int64_t n, int model_space, double *d_logl, double *d_logp, int *d_status, double *d_terms,
+                       double *d_series, cudaStream_t stream);

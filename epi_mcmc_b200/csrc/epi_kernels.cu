@@ -1,0 +1,862 @@
+// epi_kernels.cu — the batched log-posterior evaluation kernels (K1), sm_100a.
+//
+// One evaluation of calclogl(transformParams(theta)) + calclogp(theta)
+// (R/MCMC/fitMCMC-drj.R:19-21,51) is split into four launches with the thread
+// mapping that suits each phase:
+//
+//   k_ode<FL,false>  thread per chain   pass-1 ODE, beta0 forever        (model-age-groups2q.R:160-165)
+//   k_mid<FL>        warp per chain     latency profiles (pgamma/pnorm), died-threshold search,
+//                                       data_offset + padding            (:106-114,167-191)
+//   k_ode<FL,true>   thread per chain   pass-2 ODE with the beta(t) schedule (:193-213)
+//   k_score<FL>      warp per chain     6 convolutions, rate map, NB scoring, ratio term, prior
+//                                       (:229-331, 488-602, 380-486)
+//
+// The S(t) histories travel between the phases through HBM in a tiled layout
+// [tile = chain/32][day][group][lane = chain%32]: the thread-per-chain writer
+// stores 256 B per (day, group) fully coalesced, the warp-per-chain reader
+// gathers its chain's days once into shared memory.
+#include "epi_device.cuh"
+#include "epi_launch.h"
+
+namespace epi {
+
+template <int FL>
+struct Traits {
+  static constexpr bool kAge = (FL == EPI_FLAVOUR_AGE2Q);
+  static constexpr int NEQ = kAge ? 10 : 4;
+  static constexpr int NG = kAge ? 2 : 1;   // S series per chain
+  static constexpr int NK = kAge ? 6 : 2;   // latency profiles per chain
+};
+
+// ------------------------------------------------------------------ theta map
+// beta triple (y, o, yo) of schedule index k for the age flavour,
+// R/models/model-age-groups2q.R:52-99 (0-based theta indices here).
+__device__ __forceinline__ void age_beta(const double *__restrict__ th, int64_t ld, int k, double &by,
+                                         double &bo, double &byo) {
+  auto T = [&](int i) { return th[(int64_t)i * ld]; };
+  switch (k) {
+    case 0: by = T(0); bo = T(1); byo = T(2); break;
+    case 1: by = T(3); bo = T(4); byo = T(5); break;
+    case 2: by = T(6); bo = T(7); byo = T(8); break;
+    case 3: by = T(6); bo = T(26); byo = T(27); break;      // betay3 = betay2, betao3 = betao4, betayo3 = betayo4
+    case 4: by = T(25); bo = T(26); byo = T(27); break;
+    case 5: by = T(28); bo = T(29); byo = T(30); break;
+    case 6: by = T(32); bo = T(33); byo = T(34); break;
+    case 7:
+    case 8: by = T(36); bo = T(37); byo = T(38); break;     // beta8 = beta7
+    default: by = T(39) * T(36); bo = T(40) * T(37); byo = T(41) * T(38); break;  // beta9 = f9 * beta8
+  }
+}
+
+// segment kinds of model-agen.cpp:78-99: 1 = linear towards k+1, 0 = hold
+__device__ __forceinline__ bool age_linear(int k) { return (0x10F >> k) & 1; }  // k = 0,1,2,3,8
+
+// ---------------------------------------------------------------------- K_ode
+// Fixed-step classical RK4, m sub-steps per day, each sub-step cut again at the
+// schedule breakpoints that fall strictly inside it, the beta(t) segment frozen
+// per piece — the scheme of oracle/epi_oracle.c:ode_rk4.
+template <int FL>
+struct OdeState {
+  static constexpr int NEQ = Traits<FL>::NEQ;
+  double y[NEQ];
+  // current schedule segment: value at tk and slope per curve (slope 0 = hold)
+  double tk, b0, b1, b2, s0, s1, s2;  // age: betay/betao/betayo; simple: beta, Tinf, (unused)
+};
+
+template <int FL>
+__device__ __forceinline__ void rhs(const DevModel &M, const OdeState<FL> &st, double t, const double *y,
+                                    double *dy, double inv0, double inv1) {
+  const double dt = t - st.tk;
+  if constexpr (Traits<FL>::kAge) {
+    const double Sy = y[0], E1y = y[1], E2y = y[2], Iy = y[3], Ry = y[4];
+    const double So = y[5], E1o = y[6], E2o = y[7], Io = y[8], Ro = y[9];
+    const double Ny = M.Ny, No = M.No;
+    // bounds guard, model-agen.cpp:109-124: freeze the state
+    if (Sy < 0 || E1y < 0 || E2y < 0 || Iy < 0 || Ry < 0 || Sy > Ny || E1y > Ny || E2y > Ny || Iy > Ny ||
+        Ry > Ny || So < 0 || E1o < 0 || E2o < 0 || Io < 0 || Ro < 0 || So > No || E1o > No || E2o > No ||
+        Io > No || Ro > No) {
+#pragma unroll
+      for (int i = 0; i < 10; ++i) dy[i] = 0.0;
+      return;
+    }
+    const double betay = fma(dt, st.s0, st.b0);
+    const double betao = fma(dt, st.s1, st.b1);
+    const double betayo = fma(dt, st.s2, st.b2);
+    const double fy = Iy * inv0;  // Iy / Ny
+    const double fo = Io * inv1;  // Io / No
+    const double yinf = betay * fy * Sy;
+    const double oinf = (betao * fo + betayo * fy) * So;
+    const double yl2 = M.a1 * E1y, yi = M.a2 * E2y, yr = M.gamma * Iy;
+    const double ol2 = M.a1 * E1o, oi = M.a2 * E2o, orr = M.gamma * Io;
+    dy[0] = -yinf; dy[1] = yinf - yl2; dy[2] = yl2 - yi; dy[3] = yi - yr; dy[4] = yr;
+    dy[5] = -oinf; dy[6] = oinf - ol2; dy[7] = ol2 - oi; dy[8] = oi - orr; dy[9] = orr;
+  } else {
+    const double S = y[0], E = y[1], I = y[2], R = y[3];
+    const double N = M.N;
+    if (S < 0 || E < 0 || I < 0 || R < 0 || S > N || E > N || I > N || R > N) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) dy[i] = 0.0;
+      return;
+    }
+    const double beta = fma(dt, st.s0, st.b0);
+    const double rT = (st.s1 == 0.0) ? st.b2 : 1.0 / fma(dt, st.s1, st.b1);  // b2 caches 1/Tinf on hold segments
+    double inf;
+    if constexpr (FL == EPI_FLAVOUR_NE) {
+      const double Seff = fmax(0.0, inv1 - (N - S));  // inv1 carries Ne = Nef*N
+      inf = beta * I * inv0 * Seff;                  // inv0 = 1/Ne
+    } else {
+      inf = beta * I * inv0 * S;  // inv0 = 1/N
+    }
+    const double ei = M.a_inc * E, ir = I * rT;
+    dy[0] = -inf; dy[1] = inf - ei; dy[2] = ei - ir; dy[3] = ir;
+  }
+}
+
+template <int FL>
+__device__ __forceinline__ void rk4_piece(const DevModel &M, OdeState<FL> &st, double pa, double pb,
+                                          double inv0, double inv1) {
+  constexpr int NEQ = Traits<FL>::NEQ;
+  const double hh = pb - pa, hh2 = 0.5 * hh, tm = pa + hh2;
+  double k[NEQ], acc[NEQ], yt[NEQ];
+  rhs<FL>(M, st, pa, st.y, k, inv0, inv1);
+#pragma unroll
+  for (int i = 0; i < NEQ; ++i) { acc[i] = k[i]; yt[i] = fma(hh2, k[i], st.y[i]); }
+  rhs<FL>(M, st, tm, yt, k, inv0, inv1);
+#pragma unroll
+  for (int i = 0; i < NEQ; ++i) { acc[i] = fma(2.0, k[i], acc[i]); yt[i] = fma(hh2, k[i], st.y[i]); }
+  rhs<FL>(M, st, tm, yt, k, inv0, inv1);
+#pragma unroll
+  for (int i = 0; i < NEQ; ++i) { acc[i] = fma(2.0, k[i], acc[i]); yt[i] = fma(hh, k[i], st.y[i]); }
+  rhs<FL>(M, st, pb, yt, k, inv0, inv1);
+  const double h6 = hh / 6.0;
+#pragma unroll
+  for (int i = 0; i < NEQ; ++i) st.y[i] = fma(h6, acc[i] + k[i], st.y[i]);
+}
+
+// Breakpoints of pass 2 from theta + data_offset (model-age-groups2q.R:184-197;
+// simple: model-simple-ode-drj-cmp.R:98-99).
+template <int FL>
+__device__ __forceinline__ int breakpoints(const DevModel &M, const double *__restrict__ th, int64_t ld,
+                                           double data_offset, double *bp) {
+  if constexpr (Traits<FL>::kAge) {
+    auto T = [&](int i) { return th[(int64_t)i * ld]; };
+    const double lo = M.lockdown_offset, t0o = T(18);
+    const double t2 = data_offset + lo + M.ltp;
+    const double t3 = t2 + T(23);
+    const double t4 = t3 + T(24);
+    const double t5 = data_offset + M.d5;
+    const double t6 = t5 + T(31);
+    const double t7 = t6 + T(35);
+    const double t8 = data_offset + M.d8;
+    bp[0] = data_offset + lo + t0o;
+    bp[1] = data_offset + lo + fmax(t0o, 0.0);
+    bp[2] = t2; bp[3] = t3; bp[4] = t4; bp[5] = t5; bp[6] = t6; bp[7] = t7; bp[8] = t8; bp[9] = t8 + 7;
+    return 10;
+  } else {
+    bp[0] = data_offset + M.lockdown_offset;
+    bp[1] = data_offset + M.lockdown_offset + M.ltp;
+    return 2;
+  }
+}
+
+// (Re)select the schedule segment active on a piece that starts at pa: the
+// highest k with t_k <= pa (== the highest k with tm > t_k for a piece without
+// interior breakpoints), and the next cut.
+template <int FL>
+__device__ __noinline__ void select_segment(const DevModel &M, OdeState<FL> &st, const double *__restrict__ th,
+                                            int64_t ld, const double *bp, int nbp, double pa, double &tcut) {
+  int k = -1;
+  double tc = INFINITY;
+  for (int i = 0; i < nbp; ++i) {
+    if (bp[i] <= pa) k = i;
+    if (bp[i] > pa && bp[i] < tc) tc = bp[i];
+  }
+  tcut = tc;
+  if constexpr (Traits<FL>::kAge) {
+    double by, bo, byo;
+    age_beta(th, ld, k < 0 ? 0 : k, by, bo, byo);
+    st.b0 = by; st.b1 = bo; st.b2 = byo;
+    st.s0 = st.s1 = st.s2 = 0.0;
+    st.tk = 0.0;
+    if (k >= 0 && age_linear(k)) {
+      double ny, no, nyo;
+      age_beta(th, ld, k + 1, ny, no, nyo);
+      const double len = bp[k + 1] - bp[k];
+      st.tk = bp[k];
+      st.s0 = (ny - by) / len; st.s1 = (no - bo) / len; st.s2 = (nyo - byo) / len;
+    }
+  } else {
+    auto T = [&](int i) { return th[(int64_t)i * ld]; };
+    const double Tinf0 = T(2), Tinft = T(3);
+    const double beta0 = T(0) / Tinf0, betat = T(1) / Tinft;
+    st.tk = 0.0; st.s0 = 0.0; st.s1 = 0.0;
+    if (k < 0) { st.b0 = beta0; st.b1 = Tinf0; st.b2 = 1.0 / Tinf0; }
+    else if (k == 1) { st.b0 = betat; st.b1 = Tinft; st.b2 = 1.0 / Tinft; }
+    else {
+      const double len = bp[1] - bp[0];
+      st.tk = bp[0]; st.b0 = beta0; st.b1 = Tinf0; st.b2 = 0.0;
+      st.s0 = (betat - beta0) / len; st.s1 = (Tinft - Tinf0) / len;
+      if (st.s1 == 0.0) st.b2 = 1.0 / Tinf0;
+    }
+  }
+}
+
+template <int FL, bool PASS2>
+__global__ void __launch_bounds__(64)
+k_ode(const DevModel M, const double *__restrict__ theta, int64_t ld, int64_t n,
+      const int *__restrict__ offset, const int *__restrict__ padv, const double *__restrict__ hist1,
+      double *__restrict__ hist_out) {
+  constexpr int NEQ = Traits<FL>::NEQ, NG = Traits<FL>::NG;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double *th = theta + i;
+  const int ndays = PASS2 ? M.P : M.P1;
+  double *out = hist_out + ((i / kTile) * (int64_t)ndays * NG) * kTile + (i % kTile);
+
+  OdeState<FL> st;
+  double inv0, inv1;
+  if constexpr (Traits<FL>::kAge) {
+    st.y[0] = M.Ny - 1.0; st.y[1] = 1.0; st.y[2] = st.y[3] = st.y[4] = 0.0;
+    st.y[5] = M.No; st.y[6] = st.y[7] = st.y[8] = st.y[9] = 0.0;
+    inv0 = 1.0 / M.Ny; inv1 = 1.0 / M.No;
+  } else {
+    st.y[0] = M.N - 1.0; st.y[1] = 1.0; st.y[2] = st.y[3] = 0.0;
+    if constexpr (FL == EPI_FLAVOUR_NE) { inv1 = th[8 * ld] * M.N; inv0 = 1.0 / inv1; }
+    else { inv0 = 1.0 / M.N; inv1 = 0.0; }
+  }
+
+  double bp[kMaxBp];
+  int nbp = 0;
+  double tcut = INFINITY;
+  int t0 = 1;
+  if constexpr (PASS2) {
+    const int off = offset[i];
+    if (off == EPI_INVALID_DATA_OFFSET) {
+      // pass 2 skipped: the pass-1 rows are recycled into the P-length slices
+      // (model-age-groups2q.R:216-223)
+      const double *in = hist1 + ((i / kTile) * (int64_t)M.P1 * NG) * kTile + (i % kTile);
+      for (int d = 0; d < M.P; ++d)
+#pragma unroll
+        for (int g = 0; g < NG; ++g)
+          out[((int64_t)d * NG + g) * kTile] = in[((int64_t)(d % M.P1) * NG + g) * kTile];
+      return;
+    }
+    t0 = padv[i] + 1;
+    nbp = breakpoints<FL>(M, th, ld, (double)off, bp);
+  }
+  select_segment<FL>(M, st, th, ld, bp, nbp, (double)t0, tcut);
+
+  const int m = M.m;
+  const double h = 1.0 / (double)m;
+  out[0] = st.y[0];
+  if constexpr (NG == 2) out[kTile] = st.y[5];
+  for (int d = 1; d < ndays; ++d) {
+    const double tday = (double)(t0 + d - 1);
+    for (int s = 0; s < m; ++s) {
+      const double a = tday + (double)s * h;
+      const double b = (s == m - 1) ? tday + 1.0 : tday + (double)(s + 1) * h;
+      double pa = a;
+      if constexpr (PASS2) {
+        if (a >= tcut) select_segment<FL>(M, st, th, ld, bp, nbp, a, tcut);
+        while (tcut < b) {
+          rk4_piece<FL>(M, st, pa, tcut, inv0, inv1);
+          pa = tcut;
+          select_segment<FL>(M, st, th, ld, bp, nbp, pa, tcut);
+        }
+      }
+      rk4_piece<FL>(M, st, pa, b, inv0, inv1);
+    }
+    out[((int64_t)d * NG) * kTile] = st.y[0];
+    if constexpr (NG == 2) out[((int64_t)d * NG + 1) * kTile] = st.y[5];
+  }
+}
+
+// ---------------------------------------------------------------------- K_mid
+// Per-warp shared-memory carve-up shared by k_mid and k_score.
+struct WarpSmem {
+  double *theta;  // EPI_MAX_PARAMS
+  double *cdf;    // EPI_MAX_TAPS + 2
+  double *W;      // NK * EPI_MAX_TAPS
+  double *S;      // NG * (kPadMax + ndays)
+};
+
+template <int FL>
+__host__ __device__ constexpr int warp_smem_doubles(int ndays) {
+  return EPI_MAX_PARAMS + (EPI_MAX_TAPS + 2) + Traits<FL>::NK * EPI_MAX_TAPS + Traits<FL>::NG * (kPadMax + ndays) + 2;
+}
+
+template <int FL>
+__device__ __forceinline__ WarpSmem carve(double *base, int ndays) {
+  WarpSmem w;
+  w.theta = base;
+  w.cdf = w.theta + EPI_MAX_PARAMS;
+  w.W = w.cdf + EPI_MAX_TAPS + 2;
+  w.S = w.W + Traits<FL>::NK * EPI_MAX_TAPS;
+  return w;
+}
+
+// latency (mean, sd) of profile q in MODEL space; age order: ycase, yhosp,
+// ydied, ocase, ohosp, odied (model-age-groups2q.R:106-111); simple: hosp, died
+// with the NEGATED latency and sd 5 (model-simple-ode-drj-cmp.R:56-57).
+template <int FL>
+__device__ __forceinline__ void profile_params(const double *th, int q, double &mean, double &sd) {
+  if constexpr (Traits<FL>::kAge) {
+    const double CLsd = 5.0, HLsd = th[19], DLsd = th[20];
+    switch (q) {
+      case 0: mean = th[43]; sd = CLsd; break;
+      case 1: mean = th[11]; sd = HLsd; break;
+      case 2: mean = th[12]; sd = DLsd; break;
+      case 3: mean = th[44]; sd = CLsd; break;
+      case 4: mean = th[15]; sd = HLsd; break;
+      default: mean = th[16]; sd = DLsd; break;
+    }
+  } else {
+    mean = -(q == 0 ? th[5] : th[6]);
+    sd = 5.0;
+  }
+}
+
+// Profile extent in delay form: taps o = 0..n-1 act on x[t - dmin - o].
+// Returns false when the profile is wider than EPI_MAX_TAPS (or NaN input).
+template <int FL>
+__device__ __forceinline__ bool profile_extent(double mean, double sd, int &dmin, int &n, double &x0) {
+  if constexpr (Traits<FL>::kAge) {
+    // calcGammaProfile, model-age-groups2q.R:22-23
+    const double kb = fmax(0.0, ceil(mean - sd * 3));
+    const double ke = fmax(kb + 1, floor(mean + sd * 3));
+    if (!(ke - kb + 1 <= EPI_MAX_TAPS) || !(kb >= 0) || !(ke < 1e6)) return false;
+    dmin = (int)kb; n = (int)ke - (int)kb + 1; x0 = kb - 0.5;
+  } else {
+    // calcConvolveProfile, model-simple-ode-drj-cmp.R:17-18 (latency < 0)
+    const double ke = fmin(0.0, ceil(mean + sd * 1.5));
+    const double kb = fmin(ke - 1, floor(mean - sd * 1.5));
+    if (!(ke - kb + 1 <= EPI_MAX_TAPS) || !(kb > -1e6)) return false;
+    dmin = -(int)ke; n = (int)ke - (int)kb + 1; x0 = kb - 0.5;
+  }
+  return true;
+}
+
+// Build profile q into W[q*EPI_MAX_TAPS ..] (tap order o = 0..n-1), all lanes.
+template <int FL>
+__device__ __forceinline__ void build_profile(const WarpSmem &w, int q, double mean, double sd, int n, double x0,
+                                              int lane) {
+  // CDF at the n+1 cell edges x0 + i
+  double shape = 0, scale = 1;
+  if constexpr (Traits<FL>::kAge) { scale = sd * sd / mean; shape = mean / scale; }
+  for (int i = lane; i <= n; i += 32) {
+    const double x = x0 + (double)i;
+    double c;
+    if constexpr (Traits<FL>::kAge) c = dev_pgamma(x, shape, scale);
+    else c = dev_pnorm(x, mean, sd);
+    w.cdf[i] = c;
+  }
+  __syncwarp();
+  double part = 0.0;
+  for (int i = lane; i < n; i += 32) part += w.cdf[i] - w.cdf[i + 1];
+  const double sum = warp_sum(part);
+  for (int o = lane; o < n; o += 32) {
+    // age: values are reversed (rev(), :37): tap o <-> k = ke - o <-> cell n-1-o
+    const int cell = Traits<FL>::kAge ? (n - 1 - o) : o;
+    w.W[q * EPI_MAX_TAPS + o] = (w.cdf[cell] - w.cdf[cell + 1]) / sum;
+  }
+  __syncwarp();
+}
+
+// stage one chain's S history (ndays values per group) behind kPadMax prefill slots
+template <int FL>
+__device__ __forceinline__ void stage_history(const DevModel &M, const WarpSmem &w, const double *__restrict__ hist,
+                                              int64_t chain, int ndays, int lane) {
+  constexpr int NG = Traits<FL>::NG;
+  const int stride = kPadMax + ndays;
+  const double *in = hist + ((chain / kTile) * (int64_t)ndays * NG) * kTile + (chain % kTile);
+#pragma unroll
+  for (int g = 0; g < NG; ++g) {
+    const double s0 = Traits<FL>::kAge ? (g == 0 ? M.Ny - 1.0 : M.No) : M.N - 1.0;
+    for (int j = lane; j < kPadMax; j += 32) w.S[g * stride + j] = s0;
+    for (int j = lane; j < ndays; j += 32) w.S[g * stride + kPadMax + j] = in[((int64_t)j * NG + g) * kTile];
+  }
+  __syncwarp();
+}
+
+// convolute(), model-age-groups2q.R:42-45, at padded day index j (sim time t =
+// pad+1+j): sum_o f[o] * x[t - dmin - o]; NA (NaN) while t - dmin < n.
+__device__ __forceinline__ double conv_at(const double *__restrict__ Sg, const double *__restrict__ f, int pad,
+                                          int j, int dmin, int n) {
+  const int t = pad + 1 + j;
+  if (t - dmin < n) return NAN;
+  const double *x = Sg + kPadMax + j - dmin;  // x[t - dmin]
+  double z = 0.0;
+  for (int o = 0; o < n; ++o) z = fma(f[o], x[-o], z);
+  return z;
+}
+
+template <int FL>
+__global__ void __launch_bounds__(128)
+k_mid(const DevModel M, const double *__restrict__ theta, int64_t ld, int64_t n, const double *__restrict__ hist1,
+      int *__restrict__ offset, int *__restrict__ padv, int *__restrict__ status, double *__restrict__ Wg,
+      int2 *__restrict__ pmeta, int model_space) {
+  constexpr int NK = Traits<FL>::NK, NG = Traits<FL>::NG;
+  extern __shared__ double smem[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int64_t chain = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
+  if (chain >= n) return;
+  const int P1 = M.P1;
+  const WarpSmem w = carve<FL>(smem + (size_t)wib * warp_smem_doubles<FL>(P1), P1);
+
+  // theta -> MODEL space in shared memory (transformParams: simple exp(logHR), :136-142)
+  int oob = 0;
+  for (int p = lane; p < M.d; p += 32) {
+    double v = theta[(int64_t)p * ld + chain];
+    if (!model_space) {
+      oob |= !(v >= M.box_min[p] && v <= M.box_max[p]);
+      if (!Traits<FL>::kAge && p == 4) v = exp(v);
+    }
+    w.theta[p] = v;
+  }
+  oob = __any_sync(0xffffffffu, oob);
+  __syncwarp();
+
+  // profiles + padding (:106-114 / simple :56-59)
+  int st = oob ? EPI_ST_OUT_OF_BOX : 0;
+  int pad = 0;
+  int dmin_[NK], n_[NK];
+  bool ok = true;
+#pragma unroll
+  for (int q = 0; q < NK; ++q) {
+    double mean, sd, x0;
+    profile_params<FL>(w.theta, q, mean, sd);
+    int dmin = 0, nt = 1;
+    const bool okq = profile_extent<FL>(mean, sd, dmin, nt, x0);
+    ok = ok && okq;
+    dmin_[q] = dmin; n_[q] = nt;
+    if (okq) build_profile<FL>(w, q, mean, sd, nt, x0, lane);
+    // padding counts the case & died kernels only (age, :113-114); both kernels for simple (:59)
+    const bool in_pad = Traits<FL>::kAge ? (q != 1 && q != 4) : true;
+    if (in_pad && okq) pad = max(pad, dmin + nt - 1);
+  }
+  pad += 1;
+  if (!ok || pad > kPadMax) {
+    if (lane == 0) { offset[chain] = EPI_INVALID_DATA_OFFSET; padv[chain] = 0; status[chain] = st | EPI_ST_UNSUPPORTED; }
+    return;
+  }
+#pragma unroll
+  for (int q = 0; q < NK; ++q) {
+    for (int o = lane; o < EPI_MAX_TAPS; o += 32)
+      Wg[((int64_t)chain * NK + q) * EPI_MAX_TAPS + o] = o < n_[q] ? w.W[q * EPI_MAX_TAPS + o] : 0.0;
+    if (lane == 0) pmeta[(int64_t)chain * NK + q] = make_int2(dmin_[q], n_[q]);
+  }
+
+  // pass-1 threshold search (:167-182 / simple :88-95)
+  stage_history<FL>(M, w, hist1, chain, P1, lane);
+  const int stride = kPadMax + P1;
+  int first = -1;
+  double thr;
+  if constexpr (Traits<FL>::kAge) thr = w.theta[17]; else thr = w.theta[7];
+  for (int base = 0; base < P1 && first < 0; base += 32) {
+    const int j = base + lane;
+    bool hit = false;
+    if (j < P1) {
+      double died;
+      if constexpr (Traits<FL>::kAge) {
+        const double cy = conv_at(w.S, w.W + 2 * EPI_MAX_TAPS, pad, j, dmin_[2], n_[2]);
+        const double co = conv_at(w.S + stride, w.W + 5 * EPI_MAX_TAPS, pad, j, dmin_[5], n_[5]);
+        died = (M.Ny - cy) * M.ifr_y1 + (M.No - co) * M.ifr_o1;
+      } else {
+        const double c = conv_at(w.S, w.W + 1 * EPI_MAX_TAPS, pad, j, dmin_[1], n_[1]);
+        died = (M.N - c) * 0.007;
+      }
+      hit = died > thr;
+    }
+    const unsigned b = __ballot_sync(0xffffffffu, hit);
+    if (b) first = base + __ffs(b) - 1;
+  }
+  int off = EPI_INVALID_DATA_OFFSET;
+  if (first >= 0) off = pad + 1 + first - M.lockdown_offset;
+  if (!Traits<FL>::kAge && thr < 0) off = 1 - M.lockdown_offset;  // died[1] = 0 > threshold (simple prefill is 0, :70)
+  if (off == EPI_INVALID_DATA_OFFSET) st |= EPI_ST_INVALID_OFFSET;
+  if (lane == 0) { offset[chain] = off; padv[chain] = pad; status[chain] = st; }
+  (void)NG;
+}
+
+// -------------------------------------------------------------------- K_score
+
+__device__ __forceinline__ double prior_term(const PriorTerm &p, const double *th) {
+  const double A = th[p.ia], B = p.ib >= 0 ? th[p.ib] : 0.0;
+  double v;
+  if (p.mode == 0) v = p.c0 + p.ca * A + p.cb * B;
+  else if (p.mode == 1) v = A * B;
+  else v = A / B;
+  return p.is_ln ? dev_dlnorm_log(v, p.mean, p.sd) : dev_dnorm_log(v, p.mean, p.sd);
+}
+
+// rate vector element i (1-based) of scored profile q, model-age-groups2q.R:229-235
+__device__ __forceinline__ double age_rate(const DevModel &M, const double *th, int q, int i) {
+  const int k = i - 1;
+  const double ifrred = th[42];
+  switch (q) {
+    case 0: { const double v = th[9] * M.y_ifr[k] * (1 + (th[21] - 1) * M.g[k]); return v > 1 ? 1.0 : v; }    // gycr
+    case 1: return th[10] * M.y_hr[k] * (1 + (th[22] - 1) * M.g[k]);                                       // gyhr
+    case 2: return M.y_ifr[k] * (1 + (th[21] - 1) * M.g[k]) * (1 - ifrred * M.gtrimp[k]);                    // gyifr
+    case 3: { const double v = th[13] * M.o_ifr[k]; return v > 1 ? 1.0 : v; }                              // gocr
+    case 4: return th[14] * M.o_hr[k];                                                                     // gohr
+    default: return M.o_ifr[k] * (1 - ifrred * M.gtrimp[k]);                                               // goifr
+  }
+}
+
+__device__ __forceinline__ void window(int offset, int n, int T, int &dstart) {
+  // model-age-groups2q.R:497-512
+  int ds = offset, de = offset + n - 1;
+  if (de > T) { de = T; ds = de - n + 1; }
+  if (ds < 1) ds = 1;
+  dstart = ds;
+}
+
+// score the slots of scored series s that read model day t (value v)
+__device__ __forceinline__ double score_day(const DevModel &M, int s, int t, int dstart, double v) {
+  const int r = t - dstart;
+  if (r < 0 || r >= M.n_obs[s]) return 0.0;
+  const int K = M.K[s];
+  const Slot *sl = M.slots[s] + (size_t)r * K;
+  double acc = 0.0;
+  const double mu = dev_pmax(M.floor_[s], v);
+  double lmu = 0.0;
+  bool have = false;
+  for (int k = 0; k < K; ++k) {
+    const Slot z = sl[k];
+    if (z.xs == 0.0) continue;
+    if (!have) { lmu = log(mu); have = true; }
+    // size*log(size/(size+mu)) + x*log(mu/(size+mu)) minus its data-only part size*log(size)
+    acc += z.x * lmu - z.xs * log((z.xs - z.x) + mu);
+  }
+  return acc;
+}
+
+template <int FL>
+__global__ void __launch_bounds__(128)
+k_score(const DevModel M, const PriorTerm *__restrict__ PT, int n_prior, const double *__restrict__ theta, int64_t ld, int64_t n,
+        const double *__restrict__ hist2, const int *__restrict__ offset, const int *__restrict__ padv,
+        const double *__restrict__ Wg, const int2 *__restrict__ pmeta, int *__restrict__ status,
+        double *__restrict__ logl, double *__restrict__ logp, double *__restrict__ terms) {
+  constexpr int NK = Traits<FL>::NK;
+  extern __shared__ double smem[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int64_t chain = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
+  if (chain >= n) return;
+  const int P = M.P;
+  const WarpSmem w = carve<FL>(smem + (size_t)wib * warp_smem_doubles<FL>(P), P);
+
+  double raw[2] = {0.0, 0.0};  // untransformed theta for the prior (lane holds p = lane, lane+32)
+  for (int p = lane, c = 0; p < M.d; p += 32, ++c) {
+    double v = theta[(int64_t)p * ld + chain];
+    raw[c] = v;
+    if (!Traits<FL>::kAge && p == 4) v = exp(v);
+    w.theta[p] = v;
+  }
+  __syncwarp();
+  int st = status[chain];
+
+  // prior on the UNTRANSFORMED vector (R/MCMC/fitMCMC-drj.R:51); no prior term reads
+  // theta[4] in the simple flavour, so the staged model-space copy serves
+  double lp = 0.0;
+  for (int k = lane; k < n_prior; k += 32) lp += prior_term(PT[k], w.theta);
+  lp = warp_sum(lp);
+  (void)raw;
+
+  if (st & EPI_ST_UNSUPPORTED) {
+    if (lane == 0) {
+      if (logl) logl[chain] = NAN;
+      if (logp) logp[chain] = lp;
+      if (terms) for (int k = 0; k < 8; ++k) terms[chain * 8 + k] = NAN;
+    }
+    return;
+  }
+
+  const int pad = padv[chain];
+  const int T = pad + P;
+  const int off_raw = offset[chain];
+  const bool valid = off_raw != EPI_INVALID_DATA_OFFSET;
+  const int off = valid ? off_raw : 1;  // :493-494
+
+  for (int i = lane; i < NK * EPI_MAX_TAPS; i += 32) w.W[i] = Wg[(int64_t)chain * NK * EPI_MAX_TAPS + i];
+  int dmin_[NK], n_[NK];
+#pragma unroll
+  for (int q = 0; q < NK; ++q) { const int2 pm = pmeta[(int64_t)chain * NK + q]; dmin_[q] = pm.x; n_[q] = pm.y; }
+  stage_history<FL>(M, w, hist2, chain, P, lane);
+  const int stride = kPadMax + P;
+
+  int dstart[kMaxSeries];
+  int tlo = pad + 1;
+  for (int s = 0; s < M.n_series; ++s) { window(off, M.n_obs[s], T, dstart[s]); tlo = min(tlo, dstart[s]); }
+
+  double acc[kMaxSeries] = {0, 0, 0, 0, 0};
+  double ysum = 0.0, osum = 0.0;
+
+  if constexpr (Traits<FL>::kAge) {
+    // rate-map anchors t1 (:242,259,274,290,306,321); y.DL is used for both groups
+    int t1[6], t2[6];
+    double r_first[6], r_last[6];
+    const double ydl = w.theta[12];
+    const double lat[6] = {w.theta[43], w.theta[11], 0, w.theta[44], w.theta[15], 0};
+#pragma unroll
+    for (int q = 0; q < 6; ++q) {
+      const int shift = (q == 2 || q == 5) ? 0 : (int)rint(-ydl + lat[q]);
+      t1[q] = off_raw + shift;
+      t2[q] = min(pad + P, t1[q] + M.n_rate - 1);
+      r_first[q] = age_rate(M, w.theta, q, 1);
+      r_last[q] = age_rate(M, w.theta, q, M.n_rate);
+    }
+    double carry[6] = {0, 0, 0, 0, 0, 0};
+    const int jlo = tlo - (pad + 1);  // <= 0
+    for (int base = jlo; base < P; base += 32) {
+      const int j = base + lane;
+      const int t = pad + 1 + j;
+      double val[6];
+      double s2[6];
+#pragma unroll
+      for (int q = 0; q < 6; ++q) {
+        const int g = q / 3;
+        const double Ng = g == 0 ? M.Ny : M.No;
+        s2[q] = (j >= 0 && j < P) ? Ng - conv_at(w.S + g * stride, w.W + q * EPI_MAX_TAPS, pad, j, dmin_[q], n_[q]) : 0.0;
+        double prev = __shfl_up_sync(0xffffffffu, s2[q], 1);
+        if (lane == 0) prev = carry[q];
+        carry[q] = __shfl_sync(0xffffffffu, s2[q], 31);
+        const double inc = (j == 0) ? s2[q] : s2[q] - prev;  // c(s2[1], diff(s2)), :239
+        double v = 0.0;
+        if (j >= 0 && j < P) {
+          if (valid) {
+            if (t1[q] > pad && t2[q] > t1[q]) {  // :244-248 (later slices overwrite the shared end points)
+              const double r = (t >= t2[q]) ? r_last[q] : (t <= t1[q]) ? r_first[q] : age_rate(M, w.theta, q, t - t1[q] + 1);
+              v = inc * r;
+            }
+          } else {
+            v = inc * r_first[q];  // :250
+          }
+        }
+        val[q] = v;
+      }
+      if (j < P) {
+        // scored series: y.casei, o.casei, hospi = y.hospi + o.hospi, y.deadi, o.deadi
+        acc[0] += score_day(M, 0, t, dstart[0], val[0]);
+        acc[1] += score_day(M, 1, t, dstart[1], val[3]);
+        acc[2] += score_day(M, 2, t, dstart[2], val[1] + val[4]);
+        acc[3] += score_day(M, 3, t, dstart[3], val[2]);
+        acc[4] += score_day(M, 4, t, dstart[4], val[5]);
+        if (t >= dstart[2] + M.d_hosp_o1 && t <= dstart[2] + M.d_hosp_o2) { ysum += val[1]; osum += val[4]; }  // :563-564
+      }
+    }
+  } else {
+    // simple: hosp = (N - conv)*HR, died = (N - conv)*0.007 on the padded vector (0 before padding+1),
+    // hospi/deadi = c(v[1], diff(v)) (model-simple-ode-drj-cmp.R:115-122)
+    const double rate[2] = {w.theta[4], 0.007};
+    double carry[2] = {0, 0};
+    const int jlo = tlo - (pad + 1);
+    for (int base = jlo; base < P; base += 32) {
+      const int j = base + lane;
+      const int t = pad + 1 + j;
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const double cum = (j >= 0 && j < P) ? (M.N - conv_at(w.S, w.W + q * EPI_MAX_TAPS, pad, j, dmin_[q], n_[q])) * rate[q] : 0.0;
+        double prev = __shfl_up_sync(0xffffffffu, cum, 1);
+        if (lane == 0) prev = carry[q];
+        carry[q] = __shfl_sync(0xffffffffu, cum, 31);
+        const double inc = cum - prev;  // prev is 0 for t = pad+1 (prefill)
+        if (j < P) acc[q] += score_day(M, q, t, dstart[q], (j >= 0) ? inc : 0.0);
+      }
+    }
+  }
+
+  double tv[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int s = 0; s < M.n_series; ++s) tv[M.term_of[s]] = warp_sum(acc[s]) + M.term_const[M.term_of[s]];
+  if constexpr (Traits<FL>::kAge) {
+    ysum = warp_sum(ysum);
+    osum = warp_sum(osum);
+    tv[3] = dev_dlnorm_log(ysum / (ysum + osum), log(56.7 / 100), log(1.05));  // :565
+  } else {
+    // loglLD, model-simple-ode-drj-cmp.R:203-204
+    const double mu = dev_pmax(0.1, w.theta[7]);
+    tv[0] = M.tdl * log(mu) - (M.tdl + M.mort_size) * log(M.mort_size + mu) + M.term_const[0];
+  }
+  double ll;
+  if constexpr (Traits<FL>::kAge) ll = tv[0] + tv[1] + tv[2] + tv[3] + tv[4] + tv[5];  // :592
+  else ll = tv[0] + tv[1] + tv[2];
+  if (ll != ll) st |= EPI_ST_NA;
+  if (lane == 0) {
+    if (logl) logl[chain] = ll;
+    if (logp) logp[chain] = lp;
+    status[chain] = st;
+    if (terms) for (int k = 0; k < 8; ++k) terms[chain * 8 + k] = tv[k];
+  }
+}
+
+// ------------------------------------------------------------- trajectories
+// calculateModel() output series for days padding+1..padding+P (epi_trajectories):
+// age: y.S,o.S,y.casei,o.casei,y.hospi,o.hospi,y.deadi,o.deadi; simple: S,hospi,deadi.
+template <int FL>
+__global__ void __launch_bounds__(128)
+k_series(const DevModel M, const double *__restrict__ theta, int64_t ld, int64_t n, const double *__restrict__ hist2,
+         const int *__restrict__ offset, const int *__restrict__ padv, const double *__restrict__ Wg,
+         const int2 *__restrict__ pmeta, const int *__restrict__ status, double *__restrict__ out) {
+  constexpr int NK = Traits<FL>::NK;
+  constexpr int NS = Traits<FL>::kAge ? 8 : 3;
+  extern __shared__ double smem[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int64_t chain = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
+  if (chain >= n) return;
+  const int P = M.P;
+  const WarpSmem w = carve<FL>(smem + (size_t)wib * warp_smem_doubles<FL>(P), P);
+  double *o = out + (int64_t)chain * NS * P;
+  if (status[chain] & EPI_ST_UNSUPPORTED) {
+    for (int i = lane; i < NS * P; i += 32) o[i] = NAN;
+    return;
+  }
+  // theta is already in MODEL space here (calculateModel is called with transformed params)
+  for (int p = lane; p < M.d; p += 32) w.theta[p] = theta[(int64_t)p * ld + chain];
+  __syncwarp();
+  const int pad = padv[chain];
+  const int off_raw = offset[chain];
+  const bool valid = off_raw != EPI_INVALID_DATA_OFFSET;
+  for (int i = lane; i < NK * EPI_MAX_TAPS; i += 32) w.W[i] = Wg[(int64_t)chain * NK * EPI_MAX_TAPS + i];
+  int dmin_[NK], n_[NK];
+#pragma unroll
+  for (int q = 0; q < NK; ++q) { const int2 pm = pmeta[(int64_t)chain * NK + q]; dmin_[q] = pm.x; n_[q] = pm.y; }
+  stage_history<FL>(M, w, hist2, chain, P, lane);
+  const int stride = kPadMax + P;
+  if constexpr (Traits<FL>::kAge) {
+    int t1[6], t2[6];
+    double r_first[6], r_last[6];
+    const double ydl = w.theta[12];
+    const double lat[6] = {w.theta[43], w.theta[11], 0, w.theta[44], w.theta[15], 0};
+#pragma unroll
+    for (int q = 0; q < 6; ++q) {
+      const int shift = (q == 2 || q == 5) ? 0 : (int)rint(-ydl + lat[q]);
+      t1[q] = off_raw + shift;
+      t2[q] = min(pad + P, t1[q] + M.n_rate - 1);
+      r_first[q] = age_rate(M, w.theta, q, 1);
+      r_last[q] = age_rate(M, w.theta, q, M.n_rate);
+    }
+    const int dst[6] = {2, 4, 6, 3, 5, 7};
+    double carry[6] = {0, 0, 0, 0, 0, 0};
+    for (int base = 0; base < P; base += 32) {
+      const int j = base + lane;
+      const int t = pad + 1 + j;
+      if (j < P) { o[0 * P + j] = w.S[kPadMax + j]; o[1 * P + j] = w.S[stride + kPadMax + j]; }
+#pragma unroll
+      for (int q = 0; q < 6; ++q) {
+        const int g = q / 3;
+        const double Ng = g == 0 ? M.Ny : M.No;
+        const double s2 = (j < P) ? Ng - conv_at(w.S + g * stride, w.W + q * EPI_MAX_TAPS, pad, j, dmin_[q], n_[q]) : 0.0;
+        double prev = __shfl_up_sync(0xffffffffu, s2, 1);
+        if (lane == 0) prev = carry[q];
+        carry[q] = __shfl_sync(0xffffffffu, s2, 31);
+        const double inc = (j == 0) ? s2 : s2 - prev;
+        double v = 0.0;
+        if (valid) {
+          if (t1[q] > pad && t2[q] > t1[q]) {
+            const double r = (t >= t2[q]) ? r_last[q] : (t <= t1[q]) ? r_first[q] : age_rate(M, w.theta, q, t - t1[q] + 1);
+            v = inc * r;
+          }
+        } else {
+          v = inc * r_first[q];
+        }
+        if (j < P) o[dst[q] * P + j] = v;
+      }
+    }
+  } else {
+    const double rate[2] = {w.theta[4], 0.007};
+    double carry[2] = {0, 0};
+    for (int base = 0; base < P; base += 32) {
+      const int j = base + lane;
+      if (j < P) o[j] = w.S[kPadMax + j];
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const double cum = (j < P) ? (M.N - conv_at(w.S, w.W + q * EPI_MAX_TAPS, pad, j, dmin_[q], n_[q])) * rate[q] : 0.0;
+        double prev = __shfl_up_sync(0xffffffffu, cum, 1);
+        if (lane == 0) prev = carry[q];
+        carry[q] = __shfl_sync(0xffffffffu, cum, 31);
+        if (j < P) o[(1 + q) * P + j] = cum - prev;
+      }
+    }
+  }
+}
+
+// AoS (n x d, one proposal per row) -> SoA (d x ld) transpose, optionally applying
+// transformParams (used by the host-buffer entry points).
+__global__ void k_aos_to_soa(const double *__restrict__ aos, double *__restrict__ soa, int64_t n, int d, int64_t ld) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * d) return;
+  const int64_t c = i / d;
+  const int p = (int)(i % d);
+  soa[(int64_t)p * ld + c] = aos[i];
+}
+
+// DFMA-chain microbenchmark: 8 independent FMA chains per thread (epi_fp64_peak)
+__global__ void k_dfma(double *out, int iters) {
+  double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double b = 1.0000001, c = 1e-9;
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+    a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+  }
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+}  // namespace epi
+
+// ------------------------------------------------------------ launch wrappers
+
+namespace epi {
+
+template <int FL>
+static cudaError_t launch_eval_fl(const EvalArgs &a) {
+  const DevModel &M = *a.M;
+  const int64_t n = a.n;
+  const unsigned ode_blocks = (unsigned)((n + 63) / 64);
+  const unsigned warp_blocks = (unsigned)((n + 3) / 4);
+  const size_t smem_mid = (size_t)4 * warp_smem_doubles<FL>(M.P1) * sizeof(double);
+  const size_t smem_score = (size_t)4 * warp_smem_doubles<FL>(M.P) * sizeof(double);
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(k_mid<FL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(k_score<FL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(k_series<FL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr_done = true;
+  }
+  cudaStream_t s = a.stream;
+  if (a.ev) cudaEventRecord(a.ev[0], s);
+  k_ode<FL, false><<<ode_blocks, 64, 0, s>>>(M, a.theta, a.ld, n, nullptr, nullptr, nullptr, a.hist1);
+  if (a.ev) cudaEventRecord(a.ev[1], s);
+  k_mid<FL><<<warp_blocks, 128, smem_mid, s>>>(M, a.theta, a.ld, n, a.hist1, a.offset, a.pad, a.status, a.W, a.pmeta, a.model_space);
+  if (a.ev) cudaEventRecord(a.ev[2], s);
+  k_ode<FL, true><<<ode_blocks, 64, 0, s>>>(M, a.theta, a.ld, n, a.offset, a.pad, a.hist1, a.hist2);
+  if (a.ev) cudaEventRecord(a.ev[3], s);
+  if (a.series_out) {
+    k_series<FL><<<warp_blocks, 128, smem_score, s>>>(M, a.theta, a.ld, n, a.hist2, a.offset, a.pad, a.W, a.pmeta,
+                                                      a.status, a.series_out);
+  } else {
+    k_score<FL><<<warp_blocks, 128, smem_score, s>>>(M, a.PT, a.n_prior, a.theta, a.ld, n, a.hist2, a.offset, a.pad, a.W, a.pmeta,
+                                                     a.status, a.logl, a.logp, a.terms);
+  }
+  if (a.ev) cudaEventRecord(a.ev[4], s);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_eval(const EvalArgs &a) {
+  switch (a.M->flavour) {
+    case EPI_FLAVOUR_SIMPLE: return launch_eval_fl<EPI_FLAVOUR_SIMPLE>(a);
+    case EPI_FLAVOUR_NE: return launch_eval_fl<EPI_FLAVOUR_NE>(a);
+    default: return launch_eval_fl<EPI_FLAVOUR_AGE2Q>(a);
+  }
+}
+
+cudaError_t launch_aos_to_soa(const double *aos, double *soa, int64_t n, int d, int64_t ld, cudaStream_t s) {
+  const int64_t tot = n * d;
+  k_aos_to_soa<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(aos, soa, n, d, ld);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_dfma(double *out, int blocks, int threads, int iters, cudaStream_t s) {
+  k_dfma<<<blocks, threads, 0, s>>>(out, iters);
+  return cudaGetLastError();
+}
+
+}  // namespace epi

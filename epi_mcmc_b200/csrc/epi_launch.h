@@ -1,0 +1,30 @@
+// epi_launch.h — host-visible launch interface between epi_capi.cu and the kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "epi_device.cuh"
+
+namespace epi {
+
+struct EvalArgs {
+  const DevModel *M;
+  const PriorTerm *PT;  // device
+  int n_prior;
+  const double *theta;  // device SoA, d x ld
+  int64_t ld, n;
+  int model_space;      // theta already through transformParams (calculateModel callers)
+  double *hist1, *hist2, *W;
+  int2 *pmeta;
+  int *offset, *pad, *status;
+  double *logl, *logp, *terms;  // device, any may be null
+  double *series_out;           // non-null: write calculateModel series instead of scoring
+  cudaStream_t stream;
+  cudaEvent_t *ev;  // null or 5 events bracketing the 4 launches
+};
+
+cudaError_t launch_eval(const EvalArgs &a);
+cudaError_t launch_aos_to_soa(const double *aos, double *soa, int64_t n, int d, int64_t ld, cudaStream_t s);
+cudaError_t launch_dfma(double *out, int blocks, int threads, int iters, cudaStream_t s);
+
+}  // namespace epi

@@ -1,0 +1,410 @@
+// epi_sampler.cu — K2: the fused on-device Metropolis / DE-MC propose-accept
+// kernel and the sampler entry points of include/epimcmc.h.
+//
+// The reference drives calclogl/calclogp one parameter vector at a time from
+// drjacoby's host loop (R/MCMC/fitMCMC-drj.R:48-57).  Here the chain population
+// lives on the device for the whole run: per iteration the host only enqueues
+// the four K1 launches on the proposal buffer plus ONE k_accept_propose launch
+// that (a) takes the Metropolis decision of iteration i for every chain, (b)
+// commits accepted states, (c) optionally records the thinned draw and (d)
+// writes the proposal of iteration i+1.  Random numbers are counter-based
+// Philox4x32-10 keyed by (seed; chain id, iteration, use), so a run is
+// reproducible for any sharding of chains over GPUs.
+//
+// HBM traffic of k_accept_propose per chain and iteration (d parameters):
+// read theta (8d) + theta' (8d) + 4 log densities + status (36 B), write theta'
+// (8d) always and theta (8d) + 2 log densities on accept; DE-MC adds two
+// partner reads (16d).  See DESIGN.md §4 for the roofline.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "../../include/epimcmc.h"
+#include "epi_handle.h"
+#include "epi_launch.h"
+
+namespace epi {
+
+struct SamplerState {
+  epi_sampler_cfg cfg{};
+  int64_t ld = 0;
+  double *cur = nullptr, *prop = nullptr;  // SoA d x ld
+  double *logl = nullptr, *logp = nullptr, *logl_p = nullptr, *logp_p = nullptr;
+  int *status_p = nullptr;
+  double *lscale = nullptr;                  // per-chain log step multiplier (Robbins-Monro)
+  unsigned long long *acc = nullptr;         // accepted moves, device scalar
+  double *pop_own = nullptr;                 // own snapshot (1 rank)
+  const double *pop = nullptr;               // population snapshot [rank][d][ld_rank]
+  int pop_ranks = 0, pop_per_rank = 0;
+  int64_t pop_ld = 0;
+  double *draws = nullptr, *draws_lp = nullptr;  // [capacity][d][ld], [capacity][ld]
+  int thin = 0, capacity = 0, kept = 0;
+  int adapt = 0;
+  double adapt_target = 0.234;
+  int64_t iter = 0, evals = 0;
+};
+
+// ----------------------------------------------------------------- Philox4x32
+__host__ __device__ inline void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                              uint32_t k1, uint32_t out[4]) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint64_t p0 = (uint64_t)M0 * c0, p1 = (uint64_t)M1 * c2;
+    const uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0, hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += W0; k1 += W1;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// uniform in (0,1) from 32 bits
+__host__ __device__ inline double u01(uint32_t x) { return ((double)x + 0.5) * (1.0 / 4294967296.0); }
+
+// two standard normals from two 32-bit words (Box-Muller, FP64)
+__device__ inline void box_muller(uint32_t a, uint32_t b, double &z0, double &z1) {
+  const double r = sqrt(-2.0 * log(u01(a)));
+  double s, c;
+  sincospi(2.0 * u01(b), &s, &c);
+  z0 = r * c;
+  z1 = r * s;
+}
+
+// fold x into [lo, hi] by reflection (keeps a symmetric proposal symmetric)
+__device__ inline double reflect(double x, double lo, double hi) {
+  const double w = hi - lo;
+  if (!(w > 0)) return lo;
+  double y = fmod(x - lo, 2.0 * w);
+  if (y < 0) y += 2.0 * w;
+  if (y > w) y = 2.0 * w - y;
+  return lo + y;
+}
+
+enum { USE_ACCEPT = 0, USE_PARTNER = 1, USE_NORMAL = 16 };
+
+// Accept/reject iteration `iter` (when do_accept) and write the proposal of iteration iter+1.
+__global__ void __launch_bounds__(128)
+k_accept_propose(int d, int64_t n, int64_t ld, int kind, uint64_t seed, int64_t chain_id0, int64_t iter, int do_accept,
+                 double beta, double scale, double de_eps, const double *__restrict__ box_min,
+                 const double *__restrict__ box_max, double *__restrict__ cur, double *__restrict__ prop,
+                 double *__restrict__ logl, double *__restrict__ logp, const double *__restrict__ logl_p,
+                 const double *__restrict__ logp_p, const int *__restrict__ status_p, double *__restrict__ lscale,
+                 int adapt, double adapt_target, unsigned long long *__restrict__ acc_total,
+                 const double *__restrict__ pop, int pop_ranks, int pop_per_rank, int64_t pop_ld,
+                 double *__restrict__ draw_out, double *__restrict__ draw_lp) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = i < n;
+  const uint64_t cid = (uint64_t)(chain_id0 + i);
+  const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+  uint32_t r[4];
+  bool accepted = false;
+  if (live && do_accept) {
+    philox4x32_10((uint32_t)cid, (uint32_t)(cid >> 32), (uint32_t)iter, USE_ACCEPT, k0, k1, r);
+    const double ll0 = logl[i], lp0 = logp[i], ll1 = logl_p[i], lp1 = logp_p[i];
+    const double cur_post = beta * ll0 + lp0, new_post = beta * ll1 + lp1;
+    const bool new_ok = isfinite(new_post) && !(status_p[i] & (EPI_ST_NA | EPI_ST_UNSUPPORTED));
+    const bool cur_ok = isfinite(cur_post);
+    accepted = new_ok && (!cur_ok || log(u01(r[0])) < new_post - cur_post);
+    if (accepted) {
+      for (int p = 0; p < d; ++p) cur[(int64_t)p * ld + i] = prop[(int64_t)p * ld + i];
+      logl[i] = ll1;
+      logp[i] = lp1;
+    }
+    if (adapt) {  // Robbins-Monro on the log step size, gain 1/sqrt(iter+1)
+      lscale[i] += ((accepted ? 1.0 : 0.0) - adapt_target) * rsqrt((double)(iter + 1));
+    }
+  }
+  if (do_accept) {  // block-aggregated acceptance counter
+    const unsigned b = __ballot_sync(0xffffffffu, accepted);
+    if ((threadIdx.x & 31) == 0 && b) atomicAdd(acc_total, (unsigned long long)__popc(b));
+  }
+  if (!live) return;
+  if (draw_out) {
+    for (int p = 0; p < d; ++p) draw_out[(int64_t)p * ld + i] = cur[(int64_t)p * ld + i];
+    draw_lp[i] = logl[i] + logp[i];
+  }
+  // ---- proposal for iteration iter+1
+  const uint32_t it1 = (uint32_t)(iter + 1);
+  const double step = scale * exp(lscale[i]);
+  const double *z1 = nullptr, *z2 = nullptr;
+  double gam = 0.0;
+  if (kind == EPI_SAMPLER_DEMC && pop) {
+    philox4x32_10((uint32_t)cid, (uint32_t)(cid >> 32), it1, USE_PARTNER, k0, k1, r);
+    const uint32_t tot = (uint32_t)pop_ranks * (uint32_t)pop_per_rank;
+    uint32_t a = (uint32_t)(((uint64_t)r[0] * tot) >> 32);
+    uint32_t b = (uint32_t)(((uint64_t)r[1] * (tot - 1)) >> 32);
+    if (b >= a) b += 1;  // two distinct members of the snapshot
+    z1 = pop + ((int64_t)(a / pop_per_rank) * d) * pop_ld + (a % pop_per_rank);
+    z2 = pop + ((int64_t)(b / pop_per_rank) * d) * pop_ld + (b % pop_per_rank);
+    // ter Braak (2006): gamma = 2.38/sqrt(2d), every 10th proposal gamma = 1 (mode hopping)
+    gam = ((it1 % 10u) == 0u) ? 1.0 : step * 2.38 / sqrt(2.0 * d);
+  }
+  for (int p0 = 0; p0 < d; p0 += 4) {
+    philox4x32_10((uint32_t)cid, (uint32_t)(cid >> 32), it1, USE_NORMAL + (uint32_t)(p0 >> 2), k0, k1, r);
+    double z[4];
+    box_muller(r[0], r[1], z[0], z[1]);
+    box_muller(r[2], r[3], z[2], z[3]);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int p = p0 + q;
+      if (p >= d) break;
+      const double lo = box_min[p], hi = box_max[p];
+      const double x = cur[(int64_t)p * ld + i];
+      double y;
+      if (z1) y = x + gam * (z1[(int64_t)p * pop_ld] - z2[(int64_t)p * pop_ld]) + de_eps * (hi - lo) * z[q];
+      else y = x + step * (hi - lo) * z[q];
+      prop[(int64_t)p * ld + i] = reflect(y, lo, hi);
+    }
+  }
+}
+
+// raw Philox words for tests: out[4*j..] = philox(ctr = (j, 0, iter, use), key = seed)
+__global__ void k_philox_probe(uint64_t seed, uint32_t iter, uint32_t use, int n, uint32_t *out) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  uint32_t r[4];
+  philox4x32_10((uint32_t)j, 0u, iter, use, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+  for (int q = 0; q < 4; ++q) out[4 * j + q] = r[q];
+}
+
+}  // namespace epi
+
+using namespace epi;
+
+#define CUDA_OK(h, call)                                                                              \
+  do {                                                                                                \
+    cudaError_t e_ = (call);                                                                          \
+    if (e_ != cudaSuccess) return epi_fail(h, EPI_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
+  } while (0)
+
+void epi_sampler_free(epi_handle *h) {
+  SamplerState *s = h->sampler;
+  if (!s) return;
+  cudaFree(s->cur); cudaFree(s->prop); cudaFree(s->logl); cudaFree(s->logp); cudaFree(s->logl_p); cudaFree(s->logp_p);
+  cudaFree(s->status_p); cudaFree(s->lscale); cudaFree(s->acc); cudaFree(s->pop_own); cudaFree(s->draws); cudaFree(s->draws_lp);
+  delete s;
+  h->sampler = nullptr;
+}
+
+static int launch_ap(epi_handle *h, SamplerState *s, int do_accept, double *draw_out, double *draw_lp) {
+  const int64_t n = s->cfg.n_chains;
+  k_accept_propose<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(
+      h->M.d, n, s->ld, s->cfg.kind, s->cfg.seed, s->cfg.chain_id0, s->iter, do_accept, s->cfg.beta, s->cfg.scale,
+      s->cfg.de_eps, h->M.box_min, h->M.box_max, s->cur, s->prop, s->logl, s->logp, s->logl_p, s->logp_p, s->status_p,
+      s->lscale, s->adapt, s->adapt_target, s->acc, s->pop, s->pop_ranks, s->pop_per_rank, s->pop_ld, draw_out, draw_lp);
+  h->launches += 1;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return epi_fail(h, EPI_ERR_CUDA, "k_accept_propose: %s", cudaGetErrorString(e));
+  return EPI_OK;
+}
+
+extern "C" int epi_sampler_init(epi_handle *h, const epi_sampler_cfg *cfg, const double *theta0) {
+  if (!h || !cfg || cfg->n_chains < 1) return epi_fail(h, EPI_ERR_ARG, "bad sampler config");
+  if (cfg->kind != EPI_SAMPLER_RWM && cfg->kind != EPI_SAMPLER_DEMC) return epi_fail(h, EPI_ERR_ARG, "unknown sampler kind");
+  CUDA_OK(h, cudaSetDevice(h->device));
+  epi_sampler_free(h);
+  SamplerState *s = new SamplerState();
+  h->sampler = s;
+  s->cfg = *cfg;
+  if (!(s->cfg.beta > 0)) s->cfg.beta = 1.0;
+  const int d = h->M.d;
+  const int64_t n = cfg->n_chains;
+  s->ld = (n + kTile - 1) / kTile * kTile;
+  const size_t mat = sizeof(double) * (size_t)(d * s->ld), vec = sizeof(double) * (size_t)s->ld;
+  CUDA_OK(h, cudaMalloc(&s->cur, mat));
+  CUDA_OK(h, cudaMalloc(&s->prop, mat));
+  CUDA_OK(h, cudaMalloc(&s->logl, vec));
+  CUDA_OK(h, cudaMalloc(&s->logp, vec));
+  CUDA_OK(h, cudaMalloc(&s->logl_p, vec));
+  CUDA_OK(h, cudaMalloc(&s->logp_p, vec));
+  CUDA_OK(h, cudaMalloc(&s->status_p, sizeof(int) * (size_t)s->ld));
+  CUDA_OK(h, cudaMalloc(&s->lscale, vec));
+  CUDA_OK(h, cudaMalloc(&s->acc, sizeof(unsigned long long)));
+  CUDA_OK(h, cudaMemsetAsync(s->lscale, 0, vec, h->stream));
+  CUDA_OK(h, cudaMemsetAsync(s->acc, 0, sizeof(unsigned long long), h->stream));
+  CUDA_OK(h, cudaMemsetAsync(s->cur, 0, mat, h->stream));
+  CUDA_OK(h, cudaMemsetAsync(s->prop, 0, mat, h->stream));
+  int rc = epi_ensure_workspace(h, h->ws, h->M, n, false);
+  if (rc) return rc;
+  // initial state: theta0 (n x d AoS) or the model file's init with a small Philox jitter
+  std::vector<double> host((size_t)d * s->ld, 0.0);
+  for (int64_t i = 0; i < n; ++i) {
+    for (int p = 0; p < d; ++p) {
+      double v;
+      if (theta0) {
+        v = theta0[i * d + p];
+      } else {
+        uint32_t r[4];
+        const uint64_t cid = (uint64_t)(cfg->chain_id0 + i);
+        philox4x32_10((uint32_t)cid, (uint32_t)(cid >> 32), 0xFFFFFFFFu, (uint32_t)p, (uint32_t)cfg->seed,
+                      (uint32_t)(cfg->seed >> 32), r);
+        const double w = h->box_max[p] - h->box_min[p];
+        v = h->init[p] + 0.02 * w * (u01(r[0]) - 0.5);
+        v = std::fmin(std::fmax(v, h->box_min[p]), h->box_max[p]);
+      }
+      host[(size_t)p * s->ld + i] = v;
+    }
+  }
+  CUDA_OK(h, cudaMemcpyAsync(s->cur, host.data(), mat, cudaMemcpyHostToDevice, h->stream));
+  CUDA_OK(h, cudaStreamSynchronize(h->stream));
+  // log posterior of the initial state
+  rc = epi_launch_eval_ws(h, h->ws, h->M, s->cur, s->ld, n, 0, s->logl, s->logp, s->status_p, nullptr, nullptr, h->stream);
+  if (rc) return rc;
+  s->evals += n;
+  if (cfg->kind == EPI_SAMPLER_DEMC) {  // default population: a snapshot of this rank's own chains
+    CUDA_OK(h, cudaMalloc(&s->pop_own, mat));
+    CUDA_OK(h, cudaMemcpyAsync(s->pop_own, s->cur, mat, cudaMemcpyDeviceToDevice, h->stream));
+    s->pop = s->pop_own; s->pop_ranks = 1; s->pop_per_rank = (int)n; s->pop_ld = s->ld;
+    if (n < 3) return epi_fail(h, EPI_ERR_ARG, "DE-MC needs at least 3 chains");
+  }
+  s->iter = 0;
+  rc = launch_ap(h, s, /*do_accept=*/0, nullptr, nullptr);  // proposal of iteration 1
+  if (rc) return rc;
+  CUDA_OK(h, cudaStreamSynchronize(h->stream));
+  return EPI_OK;
+}
+
+extern "C" int epi_sampler_run(epi_handle *h, int32_t n_iter) {
+  if (!h || !h->sampler) return epi_fail(h, EPI_ERR_STATE, "sampler not initialised");
+  SamplerState *s = h->sampler;
+  CUDA_OK(h, cudaSetDevice(h->device));
+  const int64_t n = s->cfg.n_chains;
+  for (int it = 0; it < n_iter; ++it) {
+    int rc = epi_launch_eval_ws(h, h->ws, h->M, s->prop, s->ld, n, 0, s->logl_p, s->logp_p, s->status_p, nullptr, nullptr,
+                                h->stream);
+    if (rc) return rc;
+    s->evals += n;
+    s->iter += 1;
+    double *dout = nullptr, *dlp = nullptr;
+    if (s->draws && s->thin > 0 && (s->iter % s->thin) == 0 && s->kept < s->capacity) {
+      dout = s->draws + (size_t)s->kept * h->M.d * s->ld;
+      dlp = s->draws_lp + (size_t)s->kept * s->ld;
+      s->kept += 1;
+    }
+    if ((rc = launch_ap(h, s, 1, dout, dlp))) return rc;
+  }
+  CUDA_OK(h, cudaStreamSynchronize(h->stream));
+  return EPI_OK;
+}
+
+extern "C" int epi_sampler_adapt(epi_handle *h, int enable, double target_accept) {
+  if (!h || !h->sampler) return epi_fail(h, EPI_ERR_STATE, "sampler not initialised");
+  h->sampler->adapt = enable != 0;
+  if (target_accept > 0 && target_accept < 1) h->sampler->adapt_target = target_accept;
+  return EPI_OK;
+}
+
+extern "C" int epi_sampler_state_device(epi_handle *h, double **d_theta_soa, double **d_logl, double **d_logp, int64_t *ld) {
+  if (!h || !h->sampler) return epi_fail(h, EPI_ERR_STATE, "sampler not initialised");
+  if (d_theta_soa) *d_theta_soa = h->sampler->cur;
+  if (d_logl) *d_logl = h->sampler->logl;
+  if (d_logp) *d_logp = h->sampler->logp;
+  if (ld) *ld = h->sampler->ld;
+  return EPI_OK;
+}
+
+extern "C" int epi_sampler_set_population(epi_handle *h, const double *d_pop, int32_t n_ranks, int32_t chains_per_rank,
+                                          int64_t ld_rank) {
+  if (!h || !h->sampler) return epi_fail(h, EPI_ERR_STATE, "sampler not initialised");
+  SamplerState *s = h->sampler;
+  if (!d_pop) {  // refresh the built-in single-rank snapshot from the current state
+    if (!s->pop_own) return epi_fail(h, EPI_ERR_STATE, "no own population (sampler kind is not DE-MC)");
+    CUDA_OK(h, cudaSetDevice(h->device));
+    CUDA_OK(h, cudaMemcpyAsync(s->pop_own, s->cur, sizeof(double) * (size_t)(h->M.d * s->ld), cudaMemcpyDeviceToDevice, h->stream));
+    s->pop = s->pop_own; s->pop_ranks = 1; s->pop_per_rank = s->cfg.n_chains; s->pop_ld = s->ld;
+    return EPI_OK;
+  }
+  if (n_ranks < 1 || chains_per_rank < 1 || (int64_t)n_ranks * chains_per_rank < 3 || ld_rank < chains_per_rank)
+    return epi_fail(h, EPI_ERR_ARG, "bad population shape");
+  s->pop = d_pop; s->pop_ranks = n_ranks; s->pop_per_rank = chains_per_rank; s->pop_ld = ld_rank;
+  return EPI_OK;
+}
+
+extern "C" int epi_sampler_get(epi_handle *h, double *theta, double *logl, double *logp) {
+  if (!h || !h->sampler) return epi_fail(h, EPI_ERR_STATE, "sampler not initialised");
+  SamplerState *s = h->sampler;
+  CUDA_OK(h, cudaSetDevice(h->device));
+  const int d = h->M.d;
+  const int64_t n = s->cfg.n_chains;
+  if (theta) {
+    std::vector<double> host((size_t)d * s->ld);
+    CUDA_OK(h, cudaMemcpyAsync(host.data(), s->cur, sizeof(double) * host.size(), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_OK(h, cudaStreamSynchronize(h->stream));
+    for (int64_t i = 0; i < n; ++i)
+      for (int p = 0; p < d; ++p) theta[i * d + p] = host[(size_t)p * s->ld + i];
+  }
+  if (logl) CUDA_OK(h, cudaMemcpyAsync(logl, s->logl, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+  if (logp) CUDA_OK(h, cudaMemcpyAsync(logp, s->logp, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_OK(h, cudaStreamSynchronize(h->stream));
+  return EPI_OK;
+}
+
+extern "C" int epi_sampler_stats(epi_handle *h, int64_t *n_iter, int64_t *n_accept, int64_t *n_evals) {
+  if (!h || !h->sampler) return epi_fail(h, EPI_ERR_STATE, "sampler not initialised");
+  SamplerState *s = h->sampler;
+  CUDA_OK(h, cudaSetDevice(h->device));
+  unsigned long long acc = 0;
+  CUDA_OK(h, cudaMemcpyAsync(&acc, s->acc, sizeof acc, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_OK(h, cudaStreamSynchronize(h->stream));
+  if (n_iter) *n_iter = s->iter;
+  if (n_accept) *n_accept = (int64_t)acc;
+  if (n_evals) *n_evals = s->evals;
+  return EPI_OK;
+}
+
+extern "C" int epi_sampler_record(epi_handle *h, int32_t thin, int32_t capacity) {
+  if (!h || !h->sampler) return epi_fail(h, EPI_ERR_STATE, "sampler not initialised");
+  SamplerState *s = h->sampler;
+  CUDA_OK(h, cudaSetDevice(h->device));
+  CUDA_OK(h, cudaStreamSynchronize(h->stream));
+  cudaFree(s->draws); cudaFree(s->draws_lp);
+  s->draws = s->draws_lp = nullptr;
+  s->thin = thin; s->capacity = capacity; s->kept = 0;
+  if (thin > 0 && capacity > 0) {
+    CUDA_OK(h, cudaMalloc(&s->draws, sizeof(double) * (size_t)capacity * h->M.d * s->ld));
+    CUDA_OK(h, cudaMalloc(&s->draws_lp, sizeof(double) * (size_t)capacity * s->ld));
+  }
+  return EPI_OK;
+}
+
+extern "C" int epi_sampler_draws(epi_handle *h, double *draws, double *logpost, int32_t *n_kept) {
+  if (!h || !h->sampler) return epi_fail(h, EPI_ERR_STATE, "sampler not initialised");
+  SamplerState *s = h->sampler;
+  CUDA_OK(h, cudaSetDevice(h->device));
+  const int d = h->M.d;
+  const int64_t n = s->cfg.n_chains;
+  if (n_kept) *n_kept = s->kept;
+  if (draws && s->kept > 0) {  // device [k][p][ld] -> host [k][chain][p]
+    std::vector<double> host((size_t)d * s->ld);
+    for (int k = 0; k < s->kept; ++k) {
+      CUDA_OK(h, cudaMemcpyAsync(host.data(), s->draws + (size_t)k * d * s->ld, sizeof(double) * host.size(),
+                                 cudaMemcpyDeviceToHost, h->stream));
+      CUDA_OK(h, cudaStreamSynchronize(h->stream));
+      for (int64_t i = 0; i < n; ++i)
+        for (int p = 0; p < d; ++p) draws[((size_t)k * n + i) * d + p] = host[(size_t)p * s->ld + i];
+    }
+  }
+  if (logpost && s->kept > 0) {
+    CUDA_OK(h, cudaMemcpy2DAsync(logpost, sizeof(double) * (size_t)n, s->draws_lp, sizeof(double) * (size_t)s->ld,
+                                 sizeof(double) * (size_t)n, s->kept, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_OK(h, cudaStreamSynchronize(h->stream));
+  }
+  return EPI_OK;
+}
+
+// test hook: raw Philox4x32-10 words from the device
+extern "C" int epi_philox_probe(epi_handle *h, uint64_t seed, uint32_t iter, uint32_t use, int32_t n, uint32_t *out) {
+  if (!h || !out || n < 1) return epi_fail(h, EPI_ERR_ARG, "bad argument");
+  CUDA_OK(h, cudaSetDevice(h->device));
+  uint32_t *d = nullptr;
+  CUDA_OK(h, cudaMalloc(&d, sizeof(uint32_t) * 4 * (size_t)n));
+  k_philox_probe<<<(n + 127) / 128, 128, 0, h->stream>>>(seed, iter, use, n, d);
+  h->launches += 1;
+  CUDA_OK(h, cudaMemcpyAsync(out, d, sizeof(uint32_t) * 4 * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_OK(h, cudaStreamSynchronize(h->stream));
+  cudaFree(d);
+  return EPI_OK;
+}

@@ -195,20 +195,25 @@ typedef struct epi_sampler_cfg {
                           DE-MC: gamma = scale * 2.38/sqrt(2d) */
   double de_eps;       /* DE-MC jitter sd, relative to (max-min) */
   double beta;         /* likelihood tempering exponent (1 = posterior) */
-  int32_t pop_size;    /* DE-MC population snapshot size (chains x ranks)      */
-  int32_t reserved;
+  int32_t reserved0, reserved1;
 } epi_sampler_cfg;
 
 int epi_sampler_init(epi_handle *h, const epi_sampler_cfg *cfg, const double *theta0 /* HOST n_chains x d AOS, or NULL = init + jitter */);
 /* run n_iter fused propose -> evaluate -> accept iterations */
 int epi_sampler_run(epi_handle *h, int32_t n_iter);
-/* device pointers for the NCCL all-gather of chain states (d x n_chains SOA)  */
-int epi_sampler_state_device(epi_handle *h, double **d_theta_soa, double **d_logl, double **d_logp);
-/* install a gathered population snapshot (device pointer, pop_size x d AOS:
- * rank-major concatenation of each rank's d x n SOA block is NOT accepted;
- * use epi_sampler_population_buffer to gather in place)                       */
-int epi_sampler_population_buffer(epi_handle *h, double **d_pop, int64_t *n_doubles);
-int epi_sampler_population_commit(epi_handle *h, int32_t n_ranks, int32_t chains_per_rank);
+/* Robbins-Monro adaptation of each chain's step multiplier towards
+ * target_accept (burn-in only: switch it off before recording draws)          */
+int epi_sampler_adapt(epi_handle *h, int enable, double target_accept);
+/* device pointers of the current chain states (d x ld SOA, ld >= n_chains) for
+ * the NCCL all-gather of the DE-MC population; the pointers stay valid until
+ * the next epi_sampler_init / epi_destroy                                      */
+int epi_sampler_state_device(epi_handle *h, double **d_theta_soa, double **d_logl, double **d_logp, int64_t *ld);
+/* install the gathered population snapshot the DE-MC proposals draw partners
+ * from: caller-owned DEVICE memory laid out [rank][d][ld_rank] (exactly what an
+ * all-gather of every rank's d x ld state block produces).  d_pop == NULL
+ * refreshes the built-in single-rank snapshot from the current state.        */
+int epi_sampler_set_population(epi_handle *h, const double *d_pop, int32_t n_ranks, int32_t chains_per_rank,
+                               int64_t ld_rank);
 /* copy the current state to HOST: theta n_chains x d AOS, logl, logp          */
 int epi_sampler_get(epi_handle *h, double *theta, double *logl, double *logp);
 /* accumulated counters since init: iterations, accepted moves (summed over chains) */
@@ -231,6 +236,9 @@ int epi_set_timing(epi_handle *h, int enable);
 int epi_last_kernel_ms(epi_handle *h, float ms[4]);
 /* number of kernel launches issued by this handle since creation             */
 int64_t epi_launch_count(const epi_handle *h);
+/* test hook: raw Philox4x32-10 words generated on the device,
+ * out[4*j..4*j+3] = philox(counter = (j, 0, iter, use), key = seed)           */
+int epi_philox_probe(epi_handle *h, uint64_t seed, uint32_t iter, uint32_t use, int32_t n, uint32_t *out);
 
 #ifdef __cplusplus
 }

@@ -129,6 +129,8 @@ typedef struct {
   double values[EPI_MAX_TAPS + 2]; /* 1-based */
 } profile_t;
 
+static void jitter_weights(double *v1, int n); /* conditioning probe, see oracle_set_jitter */
+
 /* calcGammaProfile(mean, sd): R/models/model-age-groups2q.R:17-40.
  * Returns 0, or -1 if the profile needs more than EPI_MAX_TAPS taps. */
 static int calc_gamma_profile(double mean, double sd, profile_t *r) {
@@ -154,6 +156,7 @@ static int calc_gamma_profile(double mean, double sd, profile_t *r) {
     r->values[i] = r->values[r->n + 1 - i];
     r->values[r->n + 1 - i] = t;
   }
+  jitter_weights(r->values, r->n);
   return 0;
 }
 
@@ -175,6 +178,7 @@ static int calc_convolve_profile(double latency, double latency_sd, profile_t *r
     ++i;
   }
   for (i = 1; i <= r->n; ++i) r->values[i] = r->values[i] / sum;
+  jitter_weights(r->values, r->n);
   return 0;
 }
 
@@ -320,6 +324,8 @@ static void derivs_simple(const rhs_t *p, int seg, double t, const double *y, do
   ydot[3] = got_removed;
 }
 
+static void jitter_rows(double *out, int nday, int neq);
+
 static void derivs(const rhs_t *p, int neq, int seg, double t, const double *y, double *ydot) {
   if (neq == 10)
     derivs_age(p, seg, t, y, ydot);
@@ -387,6 +393,39 @@ static void ode_rk4(const rhs_t *p, int neq, const double *Y0, int t0, int nday,
       }
     }
     memcpy(out + (size_t)d * neq, y, sizeof(double) * neq);
+  }
+  jitter_rows(out, nday, neq);
+}
+
+/* Conditioning probe (tests only): when set, every reported ODE row and every
+ * latency-profile weight is multiplied by (1 + k*2^-52) with a pseudo-random
+ * integer |k| <= ulps.  It
+ * emulates the rounding noise any other correctly rounded FP64 implementation of
+ * the same scheme carries after ~10^3 steps, so that |logl(jitter) - logl| measures
+ * how ill-conditioned the REFERENCE algorithm (differences of N - filter(S)) is at
+ * a given theta.  Never set outside tests/ and make_fixtures.py. */
+static int g_jitter_ulps = 0;
+static unsigned g_jitter_seed = 0;
+void oracle_set_jitter(int ulps, unsigned seed) { g_jitter_ulps = ulps; g_jitter_seed = seed; }
+
+static void jitter_rows(double *out, int nday, int neq) {
+  if (g_jitter_ulps <= 0) return;
+  for (int d = 1; d < nday; ++d)
+    for (int i = 0; i < neq; ++i) {
+      unsigned h = (unsigned)d * 2654435761u ^ (unsigned)(i + 1) * 40503u ^ g_jitter_seed * 2246822519u;
+      h ^= h >> 15; h *= 2246822519u; h ^= h >> 13; h *= 3266489917u; h ^= h >> 16;
+      const int k = (int)(h % (unsigned)(2 * g_jitter_ulps + 1)) - g_jitter_ulps;
+      out[(size_t)d * neq + i] *= 1.0 + (double)k * 0x1p-52;
+    }
+}
+
+static void jitter_weights(double *v1, int n) {
+  if (g_jitter_ulps <= 0) return;
+  for (int i = 1; i <= n; ++i) {
+    unsigned h = (unsigned)i * 2654435761u ^ g_jitter_seed * 2246822519u ^ (unsigned)n * 97u;
+    h ^= h >> 15; h *= 2246822519u; h ^= h >> 13; h *= 3266489917u; h ^= h >> 16;
+    const int k = (int)(h % (unsigned)(2 * g_jitter_ulps + 1)) - g_jitter_ulps;
+    v1[i] *= 1.0 + (double)k * 0x1p-52;
   }
 }
 

@@ -24,6 +24,7 @@ int oracle_eval(const epi_model_desc *desc, const epi_data *D, const double *the
                 int32_t *padding, double *terms8);
 int oracle_trajectory(const epi_model_desc *desc, const epi_data *D, const double *theta_model,
                       int period, double *out, double *states, int32_t *offset, int32_t *padding);
+void oracle_set_jitter(int ulps, unsigned seed);
 int oracle_profile(int kind, double mean, double sd, double *values, int *kbegin, int *kend);
 #ifdef __cplusplus
 }

@@ -46,6 +46,8 @@ def lib():
         L.oracle_trajectory.argtypes = [C.POINTER(_capi.ModelDesc), C.POINTER(_capi.Data), _dp, C.c_int,
                                         _dp, _dp, _ip, _ip]
         L.oracle_profile.argtypes = [C.c_int, C.c_double, C.c_double, _dp, _ip, _ip]
+        L.oracle_set_jitter.argtypes = [C.c_int, C.c_uint]
+        L.oracle_set_jitter.restype = None
         _lib = L
     return _lib
 
@@ -96,6 +98,23 @@ def trajectory(flavour, data: dict, theta_model, period, substeps=4, calc_period
     if rc:
         raise ValueError("latency profile too wide")
     return out, states, off.value, pad.value
+
+
+def conditioning(flavour, data, theta, period, substeps, logl, ulps=32, n_draws=3, n_threads=8):
+    """How ill-conditioned the reference algorithm is at each theta: the largest change of
+    logl when every reported ODE state is perturbed by up to `ulps` ulps (oracle_set_jitter).
+    The parity bar of the GPU tests is max(1e-10 * |logl|, 4 x this)."""
+    cond = np.zeros(len(logl))
+    try:
+        for k in range(n_draws):
+            lib().oracle_set_jitter(ulps, 1000 + k)
+            r = evaluate(flavour, data, theta, period, substeps, n_threads)
+            with np.errstate(invalid="ignore"):
+                dlt = np.abs(r["logl"] - logl)
+            cond = np.maximum(cond, np.where(np.isfinite(dlt), dlt, 0.0))
+    finally:
+        lib().oracle_set_jitter(0, 0)
+    return cond
 
 
 def profile(kind, mean, sd):

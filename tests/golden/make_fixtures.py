@@ -138,6 +138,11 @@ def ecdc_dataset(geo, d1, transition, data_days, flavour):
                            "sizes/period from analyses/de/simple/settings.R:29-32")
 
 
+def conditioning(fl, ds, theta, P, m, logl):
+    """see oracle.conditioning: the reference algorithm's own rounding sensitivity at theta"""
+    return oracle.conditioning(fl, ds, theta, P, m, logl)
+
+
 def golden(ds, n_random, seed):
     """theta set = init + box-interior draws; values from the oracle at m = 1 and m = 4."""
     fl, P = ds["flavour"], ds["period"]
@@ -152,7 +157,9 @@ def golden(ds, n_random, seed):
     out = dict(dataset=ds["name"], flavour=fl, period=P, theta=theta.tolist(), results={})
     for m in (1, 4):
         r = oracle.evaluate(fl, ds, theta, P, m)
+        cond = conditioning(fl, ds, theta, P, m, r["logl"])
         out["results"][str(m)] = dict(
+            cond=cond.tolist(),
             logl=[None if np.isnan(v) else v for v in r["logl"].tolist()],
             logp=r["logp"].tolist(), status=r["status"].tolist(), offset=r["offset"].tolist(),
             padding=r["padding"].tolist(),

@@ -1,0 +1,66 @@
+"""CPU tests of the boundary: the library loads, exports every symbol the header declares,
+and refuses to compute without a GPU (no CPU fallback).  No compute calls here."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from conftest import ROOT
+
+
+def _header_symbols():
+    src = open(os.path.join(ROOT, "include", "epimcmc.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(epi_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_and_ctypes_symbol_lists_agree():
+    from epi_mcmc_b200 import _capi
+    assert sorted(_capi.SYMBOLS) == _header_symbols()
+
+
+def test_library_exports_every_declared_symbol():
+    import __graft_entry__ as g
+    g.build()
+    from epi_mcmc_b200 import _capi
+    lib = C.CDLL(_capi.LIB_PATH)
+    for name in _header_symbols():
+        assert hasattr(lib, name), name
+    assert lib.epi_abi_version() == 1
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device epi_create must fail with EPI_ERR_NO_DEVICE — the product never
+    routes through the oracle or any CPU path."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from epi_mcmc_b200 import _capi
+    from epi_mcmc_b200.model import Model, load_dataset
+    with pytest.raises(_capi.EpiError, match="EPI_ERR_NO_DEVICE"):
+        Model(load_dataset("S120"))
+
+
+def test_product_does_not_reference_oracle():
+    """nothing under epi_mcmc_b200/ imports, links or names the oracle"""
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "epi_mcmc_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".sh")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "libepi_oracle" not in txt and "from oracle" not in txt and "import oracle" not in txt, f
+
+
+def test_struct_layout_matches_header():
+    """ctypes mirror of epi_data / epi_model_desc / epi_sampler_cfg has the C sizes"""
+    import subprocess
+    import tempfile
+    from epi_mcmc_b200 import _capi
+    src = '#include <stdio.h>\n#include "epimcmc.h"\nint main(){printf("%zu %zu %zu\\n", sizeof(epi_model_desc), sizeof(epi_data), sizeof(epi_sampler_cfg));return 0;}\n'
+    with tempfile.TemporaryDirectory() as td:
+        c = os.path.join(td, "s.c")
+        open(c, "w").write(src)
+        exe = os.path.join(td, "s")
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
+        sizes = [int(v) for v in subprocess.check_output([exe]).split()]
+    assert sizes == [C.sizeof(_capi.ModelDesc), C.sizeof(_capi.Data), C.sizeof(_capi.SamplerCfg)]

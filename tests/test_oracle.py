@@ -1,0 +1,200 @@
+"""CPU tests of the oracle (no GPU): the nmath restatements against scipy/mpmath, the RHS
+against the reference's own compiled model-agen.cpp, the whole log-posterior against an
+independent numpy/scipy transliteration of the R model files (same fixed-step scheme: index
+semantics to ~1e-10; scipy LSODA at deSolve's defaults: solver tolerance), and the committed
+golden vectors."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import r_semantics as R
+from conftest import DATASETS, ROOT, load_golden, nan_array, rel_err
+
+
+def ds_load(name):
+    with open(os.path.join(ROOT, "epi_mcmc_b200", "datasets", name + ".json")) as f:
+        return json.load(f)
+
+
+def test_pgamma_against_mpmath_and_scipy(oracle):
+    import mpmath as mp
+    from scipy import special
+    mp.mp.dps = 40
+    L = oracle.lib()
+    rng = np.random.default_rng(0)
+    worst = 0.0
+    for _ in range(200):
+        mean, sd = rng.uniform(4, 25), rng.uniform(2, 9)
+        scale = sd * sd / mean
+        shape = mean / scale
+        q = rng.uniform(0.5, mean + 3 * sd + 1)
+        exact = float(mp.gammainc(shape, 0, q / scale, regularized=True))
+        worst = max(worst, abs(L.oracle_pgamma(q, shape, scale) - exact) / exact)
+        assert abs(special.gammainc(shape, q / scale) - exact) / exact < 1e-12
+    assert worst < 5e-13
+    assert L.oracle_pgamma(-0.5, 4.0, 2.0) == 0.0  # F(k - 0.5) with k = 0, model-age-groups2q.R:31
+
+
+def test_densities_against_scipy(oracle):
+    from scipy import stats
+    L = oracle.lib()
+    rng = np.random.default_rng(1)
+    for _ in range(200):
+        x = float(rng.integers(0, 3000))
+        size = float(rng.choice([0.01, 1, 20, 40, 120, 240]))
+        mu = rng.uniform(0.001, 3000)
+        ref = stats.nbinom.logpmf(x, size, size / (size + mu))
+        assert abs(L.oracle_dnbinom_mu_log(x, size, mu) - ref) <= 1e-9 * max(1.0, abs(ref))
+        v, m, s = rng.uniform(0.01, 50), rng.uniform(-3, 30), rng.uniform(0.05, 10)
+        assert abs(L.oracle_dnorm_log(v, m, s) - stats.norm.logpdf(v, m, s)) < 1e-12 * max(1, abs(stats.norm.logpdf(v, m, s)))
+        assert abs(L.oracle_dlnorm_log(v, m / 10, s / 10) - stats.lognorm.logpdf(v, s=s / 10, scale=np.exp(m / 10))) < 1e-10
+        assert abs(L.oracle_pnorm(v, m, s) - stats.norm.cdf(v, m, s)) < 1e-15
+    assert L.oracle_dnbinom_mu_log(0.0, 5.0, 2.0) == pytest.approx(5 * np.log(5 / 7), rel=1e-14)
+    assert L.oracle_dnbinom_mu_log(1.5, 5.0, 2.0) == -np.inf    # non-integer x: R returns -Inf
+    assert np.isnan(L.oracle_dnbinom_mu_log(3.0, 5.0, np.nan))  # NA propagates
+
+
+def test_gamma_profile_semantics(oracle):
+    """calcGammaProfile (model-age-groups2q.R:17-40): extents, normalisation, rev() (an
+    asymmetric kernel shows the mirror), against the numpy transliteration."""
+    for mean, sd in [(10, 5), (21, 5), (4, 5), (15, 9), (10.3, 2.2), (6, 9), (25, 2)]:
+        v, kb, ke = oracle.profile(0, mean, sd)
+        ref = R.Age2q.calcGammaProfile(mean, sd)
+        assert kb == ref["kbegin"] and ke == ref["kend"] and len(v) == len(ref["values"])
+        assert abs(v.sum() - 1) < 1e-14
+        assert np.abs(v - ref["values"]).max() < 1e-13
+    v, kb, ke = oracle.profile(0, 4.0, 5.0)   # shape 0.64: mass piles up at delay 0..1
+    assert kb == -19 and ke == 0 and v[-1] > v[0]   # reversed: the LAST tap holds P(kbegin = 0)
+    with pytest.raises(ValueError):
+        oracle.profile(0, 10.0, 40.0)             # 241 taps > EPI_MAX_TAPS
+
+
+def test_normal_profile_semantics(oracle):
+    """calcConvolveProfile (model-simple-ode-drj-cmp.R:15-34), called with the negated latency"""
+    for lat in (5.0, 10.0, 20.2, 30.0, 40.0):
+        v, kb, ke = oracle.profile(1, -lat, 5.0)
+        ref = R.Simple.calcConvolveProfile(-lat, 5.0)
+        assert kb == ref["kbegin"] and ke == ref["kend"]
+        assert np.abs(v - ref["values"]).max() < 1e-14
+
+
+def test_rhs_matches_reference_binary(oracle):
+    """The restated derivs() against the reference's own model-agen.cpp compiled from where it
+    lies (oracle/_ref, built by oracle/Makefile): bit-exact, including non-monotone breakpoints
+    (index-priority if-chain), t exactly on a breakpoint and the bounds guard."""
+    try:
+        ref = oracle.RefRHS()
+    except FileNotFoundError:
+        pytest.skip("oracle/_ref not built (reference tree absent)")
+    rng = np.random.default_rng(3)
+    gamma = oracle.lib().oracle_age_gamma()
+    tidx = [5, 6, 7, 17, 21, 25, 29, 33, 37, 41]
+    for trial in range(600):
+        parms = np.zeros(45)
+        parms[:5] = [8.55e6, 2.95e6, 1 / 3, 1, gamma]
+        ts = np.sort(rng.uniform(30, 330, 10)) if trial % 3 else rng.uniform(30, 330, 10)
+        for k, i in enumerate(tidx):
+            parms[i] = ts[k]
+        for i in range(8, 45):
+            if i not in tidx:
+                parms[i] = rng.uniform(0.01, 4)
+        y = np.concatenate([rng.dirichlet(np.ones(5)) * 8.55e6, rng.dirichlet(np.ones(5)) * 2.95e6])
+        if trial % 50 == 0:
+            y[rng.integers(10)] = -1.0
+        t = rng.uniform(0, 360) if trial % 7 else ts[rng.integers(10)]
+        ref.init(parms)
+        a, _ = ref.derivs(t, y)
+        assert np.array_equal(a, oracle.derivs_age(parms, t, y))
+
+
+@pytest.mark.parametrize("name", ["A300", "S120", "NE120", "DE"])
+def test_oracle_vs_numpy_transliteration_same_scheme(name, oracle):
+    """Index semantics (filter alignment + mirror, two-pass offset, rate-map slices, dnbinom
+    recycling, window clamps, NA and invalid-offset branches) against an independent
+    vector-style transliteration of the R files using the same fixed-step scheme."""
+    ds = ds_load(name)
+    g = load_golden(name)
+    theta = np.array(g["theta"])
+    idx = list(range(0, len(theta), 3))[:14]
+    res = oracle.evaluate(ds["flavour"], ds, theta[idx], ds["period"], 4)
+    for k, i in enumerate(idx):
+        if ds["flavour"] == "age2q":
+            M = R.Age2q(ds, ds["period"], "rk4", 4)
+            ll, terms, st = M.calclogl(theta[i])
+        else:
+            M = R.Simple(ds, ds["period"], "rk4", 4, ne=ds["flavour"] == "ne")
+            p = theta[i].copy()
+            p[4] = np.exp(p[4])
+            ll, terms, st = M.calclogl(p)
+        lp = M.calclogp(theta[i])
+        assert st["padding"] == res["padding"][k]
+        assert (res["offset"][k] == 10000) == bool(res["status"][k] & 1)
+        if not res["status"][k] & 1:
+            assert st["offset"] == res["offset"][k]
+        assert rel_err(ll, res["logl"][k]) < 2e-9     # scipy's nbinom/gammainc carry ~1e-10 of their own
+        assert rel_err(lp, res["logp"][k]) < 1e-13
+
+
+@pytest.mark.parametrize("name,tol_m4,tol_lsoda", [("A300", 0.02, 0.05), ("S120", 1e-3, 1e-2)])
+def test_fixed_step_scheme_vs_lsoda(name, tol_m4, tol_lsoda, oracle):
+    """The oracle's breakpoint-cut RK4 (m = 4) against scipy LSODA: (a) at deSolve's defaults
+    rtol = atol = 1e-6, hmax = 1 (the reference's own solver noise) and (b) tight.  At the model
+    file's init the m = 4 scheme is as close to the tight solution as LSODA(1e-6) is."""
+    ds = ds_load(name)
+    g = load_golden(name)
+    th = np.array(g["theta"])[0]
+    o4 = oracle.evaluate(ds["flavour"], ds, th[None], ds["period"], 4)["logl"][0]
+    if ds["flavour"] == "age2q":
+        mk = lambda integ: R.Age2q(ds, ds["period"], integ, 4).calclogl(th)[0]
+    else:
+        p = th.copy()
+        p[4] = np.exp(p[4])
+        mk = lambda integ: R.Simple(ds, ds["period"], integ, 4).calclogl(p)[0]
+    tight, loose = mk("lsoda_tight"), mk("lsoda")
+    assert abs(o4 - tight) < tol_m4
+    assert abs(loose - tight) < tol_lsoda
+    assert abs(o4 - tight) <= max(abs(loose - tight), 1e-4) * 1.5
+
+
+@pytest.mark.parametrize("name", DATASETS)
+def test_golden_vectors_reproduce(name, oracle):
+    """The committed goldens are what the oracle computes today (guards against silent drift)."""
+    ds = ds_load(name)
+    g = load_golden(name)
+    theta = np.array(g["theta"])
+    for m in ("1", "4"):
+        r = oracle.evaluate(ds["flavour"], ds, theta, ds["period"], int(m), n_threads=4)
+        res = g["results"][m]
+        assert np.array_equal(r["status"], res["status"]) and np.array_equal(r["offset"], res["offset"])
+        assert np.array_equal(r["padding"], res["padding"])
+        assert rel_err(r["logl"], nan_array(res["logl"])).max() < 1e-13
+        assert rel_err(r["logp"], np.array(res["logp"])).max() < 1e-14
+
+
+def test_oracle_threads_agree(oracle):
+    ds = ds_load("S120")
+    th = np.array(load_golden("S120")["theta"])
+    a = oracle.evaluate("simple", ds, th, 120, 4, n_threads=1)
+    b = oracle.evaluate("simple", ds, th, 120, 4, n_threads=8)
+    assert np.array_equal(a["logl"], b["logl"], equal_nan=True) and np.array_equal(a["status"], b["status"])
+
+
+def test_invalid_offset_and_na_branches(oracle):
+    ds = ds_load("A300")
+    mn, mx, init = oracle.df_params("age2q", ds, 300)
+    th = np.tile(init, (3, 1))
+    th[0, 0:3] = mn[0:3]
+    th[0, 17] = mx[17]
+    th[1, [11, 15]] = 15.0
+    th[1, 19] = 9.0
+    th[1, [12, 16]] = 10.0
+    th[1, 20] = 2.0
+    th[1, [43, 44]] = 4.0
+    th[1, 17] = 0.0
+    th[2, 19] = 40.0
+    r = oracle.evaluate("age2q", ds, th, 300, 4)
+    assert r["offset"][0] == 10000 and r["status"][0] & 1 and np.isfinite(r["logl"][0])
+    assert r["status"][1] & 2 and np.isnan(r["logl"][1])
+    assert r["status"][2] & 16 and np.isnan(r["logl"][2])
