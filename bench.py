@@ -1,0 +1,358 @@
+#!/usr/bin/env python
+"""bench.py — log-posterior evals/s of the epi-mcmc hot path on N B200s.
+
+  python bench.py --gpus N --steps K --warmup W          (N > 1: launched under torchrun)
+  python bench.py --impl reference --gpus N --steps K --warmup W
+
+One "step" = one pass of the hot path (calclogl(transformParams(theta)) + calclogp(theta))
+over one batch of `--chains` proposals PER GPU (weak scaling; chains are independent, no
+data-path collective).  Workload = BASELINE.json configs[2]: the age-structured model
+(model-age-groups2q) on the synthetic A300 series, 65,536 chains per GPU, RK4 m = 4.
+
+JSON line keys beyond the base contract:
+  roofline      dominant kernel (pass-2 ODE) against the FP64 DFMA peak measured live
+  cpu_baseline  the CPU oracle ("port": R is not installed) on a bounded sample, all host threads
+  e2e           the same metric through epi_eval() with pinned HOST buffers (H2D + D2H inside)
+  kernels       mean device ms of the four launches of one step
+  f_alg         algorithmic FLOP per evaluation (SURVEY.md §8d formula) and the whole-step fraction
+  sampler       fused propose/accept DE-MC run: evals/s inside the sampler and ESS/s
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "log_posterior_evals_per_s"
+UNIT = "evals/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="A300")
+    ap.add_argument("--chains", type=int, default=65536)
+    ap.add_argument("--substeps", type=int, default=4)
+    ap.add_argument("--no-sampler", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sampler-iters", type=int, default=120)
+    return ap.parse_args()
+
+
+def make_theta(ds_name, n, seed, mn, mx, init):
+    """proposals where a running sampler spends its time: +-0.5 % of the box width around the
+    model file's init (= the mode of the synthetic data), so every chain does the full work
+    (valid data_offset, pass 2 integrated).  Box-uniform draws would let ~1/3 of the chains skip
+    pass 2 and flatter the number."""
+    rng = np.random.default_rng(seed)
+    th = init + (rng.uniform(size=(n, len(init))) - 0.5) * 0.01 * (mx - mn)
+    return np.clip(th, mn, mx)
+
+
+def f_alg(flavour, P, m, taps_mean, n_terms, n_prior):
+    """ALGORITHMIC FLOP per evaluation, SURVEY.md §8d"""
+    age = flavour == "age2q"
+    S, K, C1, C2 = (10, 6, 2, 6) if age else (4, 2, 1, 2)
+    P1 = 60 if age else P
+    F_rhs = 124 if age else 72
+    steps = m * (P1 + P)
+    ode = steps * (4 * F_rhs + 14 * S)
+    total = ode + K * (taps_mean + 2) * 240 + (C2 * P + C1 * P1) * 2 * taps_mean + 6 * C2 * P + 72 * n_terms + 40 * n_prior
+    ode2 = m * P * (4 * F_rhs + 14 * S)
+    return dict(total=total, ode=ode, ode_pass2=ode2)
+
+
+def mean_taps(flavour, theta):
+    if flavour != "age2q":
+        return 16.0
+    t = []
+    for lat, sd in ((theta[:, 43], 5.0), (theta[:, 11], theta[:, 19]), (theta[:, 12], theta[:, 20]),
+                    (theta[:, 44], 5.0), (theta[:, 15], theta[:, 19]), (theta[:, 16], theta[:, 20])):
+        kb = np.maximum(0, np.ceil(lat - 3 * sd))
+        ke = np.maximum(kb + 1, np.floor(lat + 3 * sd))
+        t.append(ke - kb + 1)
+    return float(np.mean(t))
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md)"""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                out = subprocess.check_output(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}",
+                                               "--format=csv,noheader,nounits"], timeout=5).decode().strip()
+                self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(r[3 + k].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def cpu_baseline(ds, theta, substeps, budget_s=15.0):
+    """the CPU oracle (kind 'port': R/deSolve are not installed) on a bounded sample of the
+    same theta batch with every host thread"""
+    from oracle import oracle
+    oracle.build()
+    cores = os.cpu_count() or 1
+    probe = theta[: 4 * cores]
+    t0 = time.perf_counter()
+    oracle.evaluate(ds["flavour"], ds, probe, ds["period"], substeps, n_threads=cores)
+    rate = len(probe) / (time.perf_counter() - t0)
+    n = int(min(len(theta), max(len(probe), rate * budget_s)))
+    t0 = time.perf_counter()
+    oracle.evaluate(ds["flavour"], ds, theta[:n], ds["period"], substeps, n_threads=cores)
+    dt = time.perf_counter() - t0
+    return {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"first {n} proposals of the step's batch, oracle/epi_oracle.c (RK4 m={substeps}), {cores} pthreads, {dt:.1f} s"}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path is R + deSolve, absent
+    from this image; its restatement (oracle/) is timed instead, all host threads, on a bounded
+    sample of the same config.  Rank 0 only."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    from epi_mcmc_b200.model import load_dataset
+    from oracle import oracle
+    oracle.build()
+    ds = load_dataset(args.workload)
+    mn, mx, init = oracle.df_params(ds["flavour"], ds, ds["period"])
+    cores = os.cpu_count() or 1
+    probe = make_theta(args.workload, 4 * cores, 7, mn, mx, init)
+    t0 = time.perf_counter()
+    oracle.evaluate(ds["flavour"], ds, probe, ds["period"], args.substeps, n_threads=cores)
+    rate = len(probe) / (time.perf_counter() - t0)
+    total_budget = 120.0
+    per_step = max(4 * cores, int(rate * total_budget / max(1, args.steps + args.warmup)))
+    per_step = min(per_step, args.chains)
+    theta = make_theta(args.workload, per_step, 1234, mn, mx, init)
+    for _ in range(args.warmup):
+        oracle.evaluate(ds["flavour"], ds, theta, ds["period"], args.substeps, n_threads=cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        oracle.evaluate(ds["flavour"], ds, theta, ds["period"], args.substeps, n_threads=cores)
+    dt = time.perf_counter() - t0
+    value = per_step * args.steps / dt
+    sample = f"{per_step} proposals per step (bounded sample of the {args.chains}-chain batch), {cores} pthreads"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: age-structured model-age-groups2q, synthetic 300-day series, "
+                                   f"{args.chains} chains per GPU, RK4 m={args.substeps}",
+                       "reference_arm": "CPU restatement oracle/epi_oracle.c (R + deSolve + drjacoby are not installed)"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    import torch
+    from epi_mcmc_b200.dist import Comm
+    from epi_mcmc_b200.model import Model, load_dataset
+
+    comm = Comm()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the evaluation path has no CPU fallback")
+    dev = comm.local_rank
+    torch.cuda.set_device(dev)
+    ds = load_dataset(args.workload)
+    M = Model(ds, substeps=args.substeps, device=dev)
+    n, d = args.chains, M.d
+    mn, mx, init = M.df_params["min"], M.df_params["max"], M.df_params["init"]
+    theta = make_theta(args.workload, n, 1234 + comm.rank, mn, mx, init)
+
+    # ---- device-resident arm: theta SoA already in HBM when the timed region starts
+    th_dev = torch.from_numpy(np.ascontiguousarray(theta.T)).to(f"cuda:{dev}")
+    logl = torch.empty(n, dtype=torch.float64, device=f"cuda:{dev}")
+    logp = torch.empty_like(logl)
+    status = torch.empty(n, dtype=torch.int32, device=f"cuda:{dev}")
+    stream = torch.cuda.Stream(device=dev)   # the kernels are launched on THIS stream; so are the timing events
+    stream.wait_stream(torch.cuda.current_stream(dev))
+
+    def step():
+        M.eval_device(th_dev.data_ptr(), n, logl.data_ptr(), logp.data_ptr(), status.data_ptr(), stream.cuda_stream)
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize(dev)
+    clocks = ClockSampler(dev)
+    clocks.start()
+    comm.barrier()
+    torch.cuda.synchronize(dev)
+    launches0 = M.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    torch.cuda.synchronize(dev)
+    comm.barrier()
+    ms = comm.max_over_ranks(e0.elapsed_time(e1))
+    launches = M.launch_count() - launches0
+    value = comm.world * n * args.steps / (ms * 1e-3)
+
+    # ---- per-kernel device times (CUDA events on the launching stream, same timed loop shape)
+    M.set_timing(True)
+    kms = np.zeros(4)
+    reps = max(3, min(args.steps, 10))
+    for _ in range(reps):
+        step()
+        kms += np.array(M.last_kernel_ms())
+    kms /= reps
+    M.set_timing(False)
+    torch.cuda.synchronize(dev)
+
+    # ---- e2e arm: the public C-ABI call with pinned HOST buffers, copies inside the timed region
+    th_host = torch.from_numpy(theta.copy()).pin_memory()
+    ll_host = torch.empty(n, dtype=torch.float64).pin_memory()
+    lp_host = torch.empty(n, dtype=torch.float64).pin_memory()
+    st_host = torch.empty(n, dtype=torch.int32).pin_memory()
+    from epi_mcmc_b200 import _capi
+    import ctypes as C
+
+    def e2e_step():
+        _capi.check(M._lib.epi_eval(M._h, C.cast(th_host.data_ptr(), C.POINTER(C.c_double)), n, _capi.LAYOUT_AOS,
+                                    C.cast(ll_host.data_ptr(), C.POINTER(C.c_double)),
+                                    C.cast(lp_host.data_ptr(), C.POINTER(C.c_double)),
+                                    C.cast(st_host.data_ptr(), C.POINTER(C.c_int32))), M._h)
+
+    for _ in range(max(1, args.warmup)):
+        e2e_step()
+    comm.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()       # returns after the D2H copies completed (stream synchronised inside)
+    e2e_s = comm.max_over_ranks(time.perf_counter() - t0)
+    e2e_value = comm.world * n * args.steps / e2e_s
+    assert np.allclose(ll_host.numpy(), logl.cpu().numpy(), rtol=0, atol=0, equal_nan=True)
+    clocks.stop_flag = True
+    clocks.join(timeout=2)
+
+    # ---- roofline of the dominant kernel
+    peak_tf = M.fp64_peak_tflops()
+    fa = f_alg(ds["flavour"], ds["period"], args.substeps, mean_taps(ds["flavour"], theta), _n_terms(M), 38 if ds["flavour"] == "age2q" else 3)
+    ode2_ms = float(kms[2])
+    achieved_tf = fa["ode_pass2"] * n / (ode2_ms * 1e-3) / 1e12
+    step_ms = ms / args.steps
+    whole_tf = fa["total"] * n / (step_ms * 1e-3) / 1e12
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": comm.world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": f"{args.workload}: age-structured model-age-groups2q, synthetic 300-day series, "
+                               f"{n} chains per GPU, RK4 m={args.substeps} (BASELINE.json configs[2])",
+                   "chains_per_gpu": n, "params": d, "period": ds["period"], "substeps": args.substeps,
+                   "theta": "init +- 0.5% of the df_params box (every chain integrates both passes)",
+                   "l2": "inputs larger than L2: the S-history/profile working set of one step is "
+                         f"{_ws_mb(ds, n):.0f} MB vs 126 MB L2",
+                   "parallelism": f"chains sharded over {comm.world} GPU(s), no data-path collective"},
+        "clocks": clocks.summary(),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n * d * 8), "d2h_bytes_per_step": int(n * 20)},
+        "gpu_launches": int(launches),
+        "kernels": {"ode_pass1_ms": float(kms[0]), "profiles_threshold_ms": float(kms[1]), "ode_pass2_ms": float(kms[2]),
+                    "score_ms": float(kms[3])},
+        "roofline": {"bound": "fp64", "kernel": "k_ode<age2q,pass2>", "achieved": achieved_tf, "peak": peak_tf,
+                     "unit": "TFLOP/s", "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": None,
+                     "peak_source": "measured live: DFMA-chain microbenchmark epi_fp64_peak (MEASURED_PEAKS.json has no FP64 entry; "
+                                    "nominal 37.2 TFLOP/s = 148 SM x 64 DFMA/clk x 2 x 1.965 GHz)",
+                     "algorithmic_flop_per_launch": fa["ode_pass2"] * n},
+        "f_alg": {"per_eval": fa["total"], "ode_share": fa["ode"] / fa["total"], "whole_step_tflops": whole_tf,
+                  "whole_step_frac": whole_tf / peak_tf if peak_tf else None},
+    }
+    if comm.rank == 0 and comm.world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(ds, theta, args.substeps)
+    if not args.no_sampler:
+        line["sampler"] = sampler_leg(M, comm, args)
+    if comm.rank == 0:
+        print(json.dumps(line))
+    M.close()
+    comm.close()
+
+
+def _n_terms(M):
+    # rows of the likelihood term table (a-7): age-2q with n obs days: 2(n+2) + (n+10) + 1 + 2n
+    ds = M.data
+    if ds["flavour"] == "age2q":
+        n = ds["n_dcasei"]
+        return 2 * (n + 2) + (ds["n_dhospi"] + 10) + 1 + 2 * ds["n_dmorti"]
+    return ds["n_dhospi"] + ds["n_dmorti"] + 1
+
+
+def _ws_mb(ds, n):
+    P = ds["period"]
+    if ds["flavour"] == "age2q":
+        return n * ((P + 60) * 2 * 8 + 6 * 64 * 8) / 1e6
+    return n * (2 * P * 8 + 2 * 64 * 8) / 1e6
+
+
+def sampler_leg(M, comm, args):
+    """DE-MC with the fused propose/accept kernel: chain state stays on the GPU; the population
+    is all-gathered over NCCL every 10 iterations.  evals/s inside the sampler, and ESS/s
+    (coda spectral ESS, pooled over chains, min/median over fitkeyparamnames)."""
+    import torch
+    from epi_mcmc_b200.sampler import Sampler, pooled_ess
+    n = args.chains
+    S = Sampler(M, n, kind="demc", seed=42, chain_id0=comm.rank * n)
+    comm.attach(S)
+    iters = args.sampler_iters
+    S.adapt(True)
+    for _ in range(2):                       # short burn-in, untimed
+        S.run(10)
+        comm.exchange(S)
+    S.adapt(False)
+    S.record(1, iters)
+    torch.cuda.synchronize()
+    comm.barrier()
+    ev0 = S.stats()["evals"]
+    t0 = time.perf_counter()
+    done = 0
+    while done < iters:
+        S.run(10)
+        comm.exchange(S)
+        done += 10
+    torch.cuda.synchronize()
+    dt = comm.max_over_ranks(time.perf_counter() - t0)
+    st = S.stats()
+    draws, _ = S.draws()
+    keys = [M.fit_paramnames.index(k) for k in M.fitkeyparamnames if k in M.fit_paramnames]
+    ess = pooled_ess(draws[:, :, keys], max_chains=64)
+    return {"kind": "DE-MC, population snapshot all-gathered every 10 iterations", "chains_per_gpu": n,
+            "iterations": iters, "evals_per_s": comm.world * (st["evals"] - ev0) / dt, "accept_rate": st["accept_rate"],
+            "ess_per_s_min": comm.world * float(ess.min()) / dt, "ess_per_s_median": comm.world * float(np.median(ess)) / dt,
+            "note": "ESS of this rank's chains scaled by the rank count; short run, chains still warming up"}
+
+
+if __name__ == "__main__":
+    main()

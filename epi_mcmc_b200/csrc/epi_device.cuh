@@ -59,38 +59,50 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
-// Regularised lower incomplete gamma P(a, x), x = q/scale: same algorithm and
-// stopping rules as oracle_pgamma (series below a+1, Lentz continued fraction
-// above), i.e. R's pgamma(q, shape, scale) of model-age-groups2q.R:31-32.
-__device__ inline double dev_pgamma(double q, double shape, double scale) {
+// Regularised lower incomplete gamma P(a, x), x = q/scale, i.e. R's pgamma(q, shape, scale) of
+// model-age-groups2q.R:31-32.  Same split as oracle_pgamma (power series below a+1, continued
+// fraction above) but arranged for the GPU (ncu, profiles/r1_v1: the textbook loops are one long
+// dependent chain through an FP64 division per term):
+//   - series: four terms per trip, their four divisions independent of the running product;
+//   - continued fraction: Wallis forward recurrence of numerator/denominator (two independent
+//     FMA chains, no division inside the loop), convergence tested every four terms.
+// Agreement with the oracle is a few ulp (tests: < 1e-13 relative on every profile weight).
+// lga = lgamma(shape), hoisted by the caller because every CDF point of a profile shares it.
+__device__ inline double dev_pgamma(double q, double shape, double scale, double lga) {
   const double x = q / scale, a = shape;
   if (!(x > 0.0)) return (x <= 0.0) ? 0.0 : x;  // NaN propagates
-  const double lpre = -x + a * log(x) - lgamma(a);
+  const double pre = exp(-x + a * log(x) - lga);
   if (x < a + 1.0) {
     double ap = a, del = 1.0 / a, sum = del;
-    for (int n = 0; n < 100000; ++n) {
-      ap += 1.0;
-      del *= x / ap;
-      sum += del;
-      if (fabs(del) < fabs(sum) * 1e-17) break;
+    for (int n = 0; n < 25000; ++n) {
+      const double r1 = x / (ap + 1.0), r2 = x / (ap + 2.0), r3 = x / (ap + 3.0), r4 = x / (ap + 4.0);
+      const double d1 = del * r1, d2 = d1 * r2, d3 = d2 * r3, d4 = d3 * r4;
+      sum += d1; sum += d2; sum += d3; sum += d4;
+      del = d4;
+      ap += 4.0;
+      if (!(fabs(d4) >= fabs(sum) * 1e-17)) break;
     }
-    return sum * exp(lpre);
+    return sum * pre;
   }
-  const double tiny = 1e-300;
-  double b = x + 1.0 - a, c = 1.0 / tiny, d = 1.0 / b, h = d;
-  for (int i = 1; i < 100000; ++i) {
-    const double an = -(double)i * ((double)i - a);
-    b += 2.0;
-    d = an * d + b;
-    if (fabs(d) < tiny) d = tiny;
-    c = b + an / c;
-    if (fabs(c) < tiny) c = tiny;
-    d = 1.0 / d;
-    const double del = d * c;
-    h *= del;
-    if (fabs(del - 1.0) < 1e-17) break;
+  // Q(a,x) = pre / (b0 + a1/(b1 + a2/(b2 + ...))), b_i = x + 2i + 1 - a, a_i = -i (i - a)
+  double b = x + 1.0 - a;
+  double Am1 = 1.0, A = b, Bm1 = 0.0, B = 1.0;  // A_{-1}, A_0, B_{-1}, B_0
+  double hprev = 1.0 / b, h = hprev;
+  for (int i = 1; i < 100000; i += 4) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const double fi = (double)(i + u);
+      const double an = -fi * (fi - a);
+      b += 2.0;
+      const double An = fma(b, A, an * Am1), Bn = fma(b, B, an * Bm1);
+      Am1 = A; A = An; Bm1 = B; B = Bn;
+    }
+    if (fabs(A) > 1e150) { A *= 1e-150; Am1 *= 1e-150; B *= 1e-150; Bm1 *= 1e-150; }
+    h = B / A;
+    if (!(fabs(h - hprev) > 1.2e-16 * fabs(h))) break;
+    hprev = h;
   }
-  return 1.0 - exp(lpre) * h;
+  return 1.0 - pre * h;
 }
 
 __device__ __forceinline__ double dev_pnorm(double q, double mean, double sd) {

@@ -55,51 +55,75 @@ __device__ __forceinline__ bool age_linear(int k) { return (0x10F >> k) & 1; }  
 // Fixed-step classical RK4, m sub-steps per day, each sub-step cut again at the
 // schedule breakpoints that fall strictly inside it, the beta(t) segment frozen
 // per piece — the scheme of oracle/epi_oracle.c:ode_rk4.
-template <int FL>
-struct OdeState {
-  static constexpr int NEQ = Traits<FL>::NEQ;
-  double y[NEQ];
-  // current schedule segment: value at tk and slope per curve (slope 0 = hold)
-  double tk, b0, b1, b2, s0, s1, s2;  // age: betay/betao/betayo; simple: beta, Tinf, (unused)
+//
+// ncu (profiles/r1_v1_*): with the bounds guard of model-agen.cpp:109-124 written
+// as 20 FP64 compares + "dy = 0" the compiler if-converts it into ~20 DSETP +
+// ~40 SEL/CS2R/IMAD.MOV per stage: the FP64 pipe spends 1/3 of its cycles on
+// compares and only 34 % of the issued instructions are FP64 math.  The guard
+// almost never fires, so each stage only computes a CONSERVATIVE "maybe out of
+// bounds" flag on the integer pipe (which is otherwise idle); when no stage of a
+// step raises it the unguarded arithmetic is exactly what the guarded code would
+// have produced, otherwise the step is redone by the exact guarded slow path.
+
+// current schedule segment: value at tk and slope per curve (slope 0 = hold)
+struct Seg {
+  double tk, b0, b1, b2, s0, s1, s2;  // age: betay/betao/betayo; simple: beta, Tinf, 1/Tinf cache
 };
 
-template <int FL>
-__device__ __forceinline__ void rhs(const DevModel &M, const OdeState<FL> &st, double t, const double *y,
-                                    double *dy, double inv0, double inv1) {
-  const double dt = t - st.tk;
+// y > N or y < 0 or NaN  =>  bit 63 of (bits(N) - bits(y)) | bits(y) is set (conservative: it is
+// also set for -0.0, which the slow path then treats exactly)
+__device__ __forceinline__ unsigned long long oob_bits(double y, unsigned long long nbits) {
+  const unsigned long long b = (unsigned long long)__double_as_longlong(y);
+  return (nbits - b) | b;
+}
+
+template <int FL, bool GUARDED>
+__device__ __forceinline__ void rhs(const DevModel &M, const Seg &sg, double t, const double *y, double *dy,
+                                    double inv0, double inv1, unsigned long long nb0, unsigned long long nb1,
+                                    unsigned long long &flag) {
+  const double dt = t - sg.tk;
   if constexpr (Traits<FL>::kAge) {
     const double Sy = y[0], E1y = y[1], E2y = y[2], Iy = y[3], Ry = y[4];
     const double So = y[5], E1o = y[6], E2o = y[7], Io = y[8], Ro = y[9];
-    const double Ny = M.Ny, No = M.No;
-    // bounds guard, model-agen.cpp:109-124: freeze the state
-    if (Sy < 0 || E1y < 0 || E2y < 0 || Iy < 0 || Ry < 0 || Sy > Ny || E1y > Ny || E2y > Ny || Iy > Ny ||
-        Ry > Ny || So < 0 || E1o < 0 || E2o < 0 || Io < 0 || Ro < 0 || So > No || E1o > No || E2o > No ||
-        Io > No || Ro > No) {
+    if constexpr (GUARDED) {
+      const double Ny = M.Ny, No = M.No;
+      // bounds guard, model-agen.cpp:109-124: freeze the state
+      if (Sy < 0 || E1y < 0 || E2y < 0 || Iy < 0 || Ry < 0 || Sy > Ny || E1y > Ny || E2y > Ny || Iy > Ny ||
+          Ry > Ny || So < 0 || E1o < 0 || E2o < 0 || Io < 0 || Ro < 0 || So > No || E1o > No || E2o > No ||
+          Io > No || Ro > No) {
 #pragma unroll
-      for (int i = 0; i < 10; ++i) dy[i] = 0.0;
-      return;
+        for (int i = 0; i < 10; ++i) dy[i] = 0.0;
+        return;
+      }
+    } else {
+      flag |= oob_bits(Sy, nb0) | oob_bits(E1y, nb0) | oob_bits(E2y, nb0) | oob_bits(Iy, nb0) | oob_bits(Ry, nb0) |
+              oob_bits(So, nb1) | oob_bits(E1o, nb1) | oob_bits(E2o, nb1) | oob_bits(Io, nb1) | oob_bits(Ro, nb1);
     }
-    const double betay = fma(dt, st.s0, st.b0);
-    const double betao = fma(dt, st.s1, st.b1);
-    const double betayo = fma(dt, st.s2, st.b2);
+    const double betay = fma(dt, sg.s0, sg.b0);
+    const double betao = fma(dt, sg.s1, sg.b1);
+    const double betayo = fma(dt, sg.s2, sg.b2);
     const double fy = Iy * inv0;  // Iy / Ny
     const double fo = Io * inv1;  // Io / No
     const double yinf = betay * fy * Sy;
-    const double oinf = (betao * fo + betayo * fy) * So;
-    const double yl2 = M.a1 * E1y, yi = M.a2 * E2y, yr = M.gamma * Iy;
-    const double ol2 = M.a1 * E1o, oi = M.a2 * E2o, orr = M.gamma * Io;
-    dy[0] = -yinf; dy[1] = yinf - yl2; dy[2] = yl2 - yi; dy[3] = yi - yr; dy[4] = yr;
-    dy[5] = -oinf; dy[6] = oinf - ol2; dy[7] = ol2 - oi; dy[8] = oi - orr; dy[9] = orr;
+    const double oinf = fma(betao, fo, betayo * fy) * So;
+    const double yl2 = M.a1 * E1y, yr = M.gamma * Iy;  // a2 = 1/Tinc2 = 1 (model-age-groups2q.R:10,14)
+    const double ol2 = M.a1 * E1o, orr = M.gamma * Io;
+    dy[0] = -yinf; dy[1] = yinf - yl2; dy[2] = yl2 - E2y; dy[3] = E2y - yr; dy[4] = yr;
+    dy[5] = -oinf; dy[6] = oinf - ol2; dy[7] = ol2 - E2o; dy[8] = E2o - orr; dy[9] = orr;
   } else {
     const double S = y[0], E = y[1], I = y[2], R = y[3];
     const double N = M.N;
-    if (S < 0 || E < 0 || I < 0 || R < 0 || S > N || E > N || I > N || R > N) {
+    if constexpr (GUARDED) {
+      if (S < 0 || E < 0 || I < 0 || R < 0 || S > N || E > N || I > N || R > N) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) dy[i] = 0.0;
-      return;
+        for (int i = 0; i < 4; ++i) dy[i] = 0.0;
+        return;
+      }
+    } else {
+      flag |= oob_bits(S, nb0) | oob_bits(E, nb0) | oob_bits(I, nb0) | oob_bits(R, nb0);
     }
-    const double beta = fma(dt, st.s0, st.b0);
-    const double rT = (st.s1 == 0.0) ? st.b2 : 1.0 / fma(dt, st.s1, st.b1);  // b2 caches 1/Tinf on hold segments
+    const double beta = fma(dt, sg.s0, sg.b0);
+    const double rT = (sg.s1 == 0.0) ? sg.b2 : 1.0 / fma(dt, sg.s1, sg.b1);  // b2 caches 1/Tinf on hold segments
     double inf;
     if constexpr (FL == EPI_FLAVOUR_NE) {
       const double Seff = fmax(0.0, inv1 - (N - S));  // inv1 carries Ne = Nef*N
@@ -112,25 +136,41 @@ __device__ __forceinline__ void rhs(const DevModel &M, const OdeState<FL> &st, d
   }
 }
 
-template <int FL>
-__device__ __forceinline__ void rk4_piece(const DevModel &M, OdeState<FL> &st, double pa, double pb,
-                                          double inv0, double inv1) {
+template <int FL, bool GUARDED>
+__device__ __forceinline__ bool rk4_try(const DevModel &M, const Seg &sg, const double *y, double *ynew, double pa,
+                                        double pb, double inv0, double inv1, unsigned long long nb0,
+                                        unsigned long long nb1) {
   constexpr int NEQ = Traits<FL>::NEQ;
   const double hh = pb - pa, hh2 = 0.5 * hh, tm = pa + hh2;
   double k[NEQ], acc[NEQ], yt[NEQ];
-  rhs<FL>(M, st, pa, st.y, k, inv0, inv1);
+  unsigned long long flag = 0;
+  rhs<FL, GUARDED>(M, sg, pa, y, k, inv0, inv1, nb0, nb1, flag);
 #pragma unroll
-  for (int i = 0; i < NEQ; ++i) { acc[i] = k[i]; yt[i] = fma(hh2, k[i], st.y[i]); }
-  rhs<FL>(M, st, tm, yt, k, inv0, inv1);
+  for (int i = 0; i < NEQ; ++i) { acc[i] = k[i]; yt[i] = fma(hh2, k[i], y[i]); }
+  rhs<FL, GUARDED>(M, sg, tm, yt, k, inv0, inv1, nb0, nb1, flag);
 #pragma unroll
-  for (int i = 0; i < NEQ; ++i) { acc[i] = fma(2.0, k[i], acc[i]); yt[i] = fma(hh2, k[i], st.y[i]); }
-  rhs<FL>(M, st, tm, yt, k, inv0, inv1);
+  for (int i = 0; i < NEQ; ++i) { acc[i] = fma(2.0, k[i], acc[i]); yt[i] = fma(hh2, k[i], y[i]); }
+  rhs<FL, GUARDED>(M, sg, tm, yt, k, inv0, inv1, nb0, nb1, flag);
 #pragma unroll
-  for (int i = 0; i < NEQ; ++i) { acc[i] = fma(2.0, k[i], acc[i]); yt[i] = fma(hh, k[i], st.y[i]); }
-  rhs<FL>(M, st, pb, yt, k, inv0, inv1);
+  for (int i = 0; i < NEQ; ++i) { acc[i] = fma(2.0, k[i], acc[i]); yt[i] = fma(hh, k[i], y[i]); }
+  rhs<FL, GUARDED>(M, sg, pb, yt, k, inv0, inv1, nb0, nb1, flag);
   const double h6 = hh / 6.0;
 #pragma unroll
-  for (int i = 0; i < NEQ; ++i) st.y[i] = fma(h6, acc[i] + k[i], st.y[i]);
+  for (int i = 0; i < NEQ; ++i) ynew[i] = fma(h6, acc[i] + k[i], y[i]);
+  return (long long)flag >= 0;  // no stage raised the maybe-out-of-bounds bit
+}
+
+template <int FL>
+__device__ __forceinline__ void rk4_piece(const DevModel &M, const Seg &sg, double *y, double pa, double pb,
+                                          double inv0, double inv1, unsigned long long nb0, unsigned long long nb1) {
+  constexpr int NEQ = Traits<FL>::NEQ;
+  double yn[NEQ];
+  if (!rk4_try<FL, false>(M, sg, y, yn, pa, pb, inv0, inv1, nb0, nb1)) {
+    // rare: redo the step with the reference's guard evaluated exactly in FP64
+    rk4_try<FL, true>(M, sg, y, yn, pa, pb, inv0, inv1, 0ull, 0ull);
+  }
+#pragma unroll
+  for (int i = 0; i < NEQ; ++i) y[i] = yn[i];
 }
 
 // Breakpoints of pass 2 from theta + data_offset (model-age-groups2q.R:184-197;
@@ -163,46 +203,48 @@ __device__ __forceinline__ int breakpoints(const DevModel &M, const double *__re
 // highest k with t_k <= pa (== the highest k with tm > t_k for a piece without
 // interior breakpoints), and the next cut.
 template <int FL>
-__device__ __noinline__ void select_segment(const DevModel &M, OdeState<FL> &st, const double *__restrict__ th,
-                                            int64_t ld, const double *bp, int nbp, double pa, double &tcut) {
+__device__ __noinline__ Seg select_segment(const DevModel &M, const double *__restrict__ th, int64_t ld,
+                                           const double *bp, int nbp, double pa, double *tcut) {
   int k = -1;
   double tc = INFINITY;
   for (int i = 0; i < nbp; ++i) {
     if (bp[i] <= pa) k = i;
     if (bp[i] > pa && bp[i] < tc) tc = bp[i];
   }
-  tcut = tc;
+  *tcut = tc;
+  Seg sg;
   if constexpr (Traits<FL>::kAge) {
     double by, bo, byo;
     age_beta(th, ld, k < 0 ? 0 : k, by, bo, byo);
-    st.b0 = by; st.b1 = bo; st.b2 = byo;
-    st.s0 = st.s1 = st.s2 = 0.0;
-    st.tk = 0.0;
+    sg.b0 = by; sg.b1 = bo; sg.b2 = byo;
+    sg.s0 = sg.s1 = sg.s2 = 0.0;
+    sg.tk = 0.0;
     if (k >= 0 && age_linear(k)) {
       double ny, no, nyo;
       age_beta(th, ld, k + 1, ny, no, nyo);
       const double len = bp[k + 1] - bp[k];
-      st.tk = bp[k];
-      st.s0 = (ny - by) / len; st.s1 = (no - bo) / len; st.s2 = (nyo - byo) / len;
+      sg.tk = bp[k];
+      sg.s0 = (ny - by) / len; sg.s1 = (no - bo) / len; sg.s2 = (nyo - byo) / len;
     }
   } else {
     auto T = [&](int i) { return th[(int64_t)i * ld]; };
     const double Tinf0 = T(2), Tinft = T(3);
     const double beta0 = T(0) / Tinf0, betat = T(1) / Tinft;
-    st.tk = 0.0; st.s0 = 0.0; st.s1 = 0.0;
-    if (k < 0) { st.b0 = beta0; st.b1 = Tinf0; st.b2 = 1.0 / Tinf0; }
-    else if (k == 1) { st.b0 = betat; st.b1 = Tinft; st.b2 = 1.0 / Tinft; }
+    sg.tk = 0.0; sg.s0 = 0.0; sg.s1 = 0.0; sg.s2 = 0.0;
+    if (k < 0) { sg.b0 = beta0; sg.b1 = Tinf0; sg.b2 = 1.0 / Tinf0; }
+    else if (k == 1) { sg.b0 = betat; sg.b1 = Tinft; sg.b2 = 1.0 / Tinft; }
     else {
       const double len = bp[1] - bp[0];
-      st.tk = bp[0]; st.b0 = beta0; st.b1 = Tinf0; st.b2 = 0.0;
-      st.s0 = (betat - beta0) / len; st.s1 = (Tinft - Tinf0) / len;
-      if (st.s1 == 0.0) st.b2 = 1.0 / Tinf0;
+      sg.tk = bp[0]; sg.b0 = beta0; sg.b1 = Tinf0; sg.b2 = 0.0;
+      sg.s0 = (betat - beta0) / len; sg.s1 = (Tinft - Tinf0) / len;
+      if (sg.s1 == 0.0) sg.b2 = 1.0 / Tinf0;
     }
   }
+  return sg;
 }
 
 template <int FL, bool PASS2>
-__global__ void __launch_bounds__(64)
+__global__ void __maxnreg__(144)
 k_ode(const DevModel M, const double *__restrict__ theta, int64_t ld, int64_t n,
       const int *__restrict__ offset, const int *__restrict__ padv, const double *__restrict__ hist1,
       double *__restrict__ hist_out) {
@@ -213,16 +255,20 @@ k_ode(const DevModel M, const double *__restrict__ theta, int64_t ld, int64_t n,
   const int ndays = PASS2 ? M.P : M.P1;
   double *out = hist_out + ((i / kTile) * (int64_t)ndays * NG) * kTile + (i % kTile);
 
-  OdeState<FL> st;
+  double y[NEQ];
   double inv0, inv1;
+  unsigned long long nb0, nb1 = 0;
   if constexpr (Traits<FL>::kAge) {
-    st.y[0] = M.Ny - 1.0; st.y[1] = 1.0; st.y[2] = st.y[3] = st.y[4] = 0.0;
-    st.y[5] = M.No; st.y[6] = st.y[7] = st.y[8] = st.y[9] = 0.0;
+    y[0] = M.Ny - 1.0; y[1] = 1.0; y[2] = y[3] = y[4] = 0.0;
+    y[5] = M.No; y[6] = y[7] = y[8] = y[9] = 0.0;
     inv0 = 1.0 / M.Ny; inv1 = 1.0 / M.No;
+    nb0 = (unsigned long long)__double_as_longlong(M.Ny);
+    nb1 = (unsigned long long)__double_as_longlong(M.No);
   } else {
-    st.y[0] = M.N - 1.0; st.y[1] = 1.0; st.y[2] = st.y[3] = 0.0;
+    y[0] = M.N - 1.0; y[1] = 1.0; y[2] = y[3] = 0.0;
     if constexpr (FL == EPI_FLAVOUR_NE) { inv1 = th[8 * ld] * M.N; inv0 = 1.0 / inv1; }
     else { inv0 = 1.0 / M.N; inv1 = 0.0; }
+    nb0 = (unsigned long long)__double_as_longlong(M.N);
   }
 
   double bp[kMaxBp];
@@ -244,12 +290,12 @@ k_ode(const DevModel M, const double *__restrict__ theta, int64_t ld, int64_t n,
     t0 = padv[i] + 1;
     nbp = breakpoints<FL>(M, th, ld, (double)off, bp);
   }
-  select_segment<FL>(M, st, th, ld, bp, nbp, (double)t0, tcut);
+  Seg sg = select_segment<FL>(M, th, ld, bp, nbp, (double)t0, &tcut);
 
   const int m = M.m;
   const double h = 1.0 / (double)m;
-  out[0] = st.y[0];
-  if constexpr (NG == 2) out[kTile] = st.y[5];
+  out[0] = y[0];
+  if constexpr (NG == 2) out[kTile] = y[5];
   for (int d = 1; d < ndays; ++d) {
     const double tday = (double)(t0 + d - 1);
     for (int s = 0; s < m; ++s) {
@@ -257,17 +303,17 @@ k_ode(const DevModel M, const double *__restrict__ theta, int64_t ld, int64_t n,
       const double b = (s == m - 1) ? tday + 1.0 : tday + (double)(s + 1) * h;
       double pa = a;
       if constexpr (PASS2) {
-        if (a >= tcut) select_segment<FL>(M, st, th, ld, bp, nbp, a, tcut);
+        if (a >= tcut) sg = select_segment<FL>(M, th, ld, bp, nbp, a, &tcut);
         while (tcut < b) {
-          rk4_piece<FL>(M, st, pa, tcut, inv0, inv1);
+          rk4_piece<FL>(M, sg, y, pa, tcut, inv0, inv1, nb0, nb1);
           pa = tcut;
-          select_segment<FL>(M, st, th, ld, bp, nbp, pa, tcut);
+          sg = select_segment<FL>(M, th, ld, bp, nbp, pa, &tcut);
         }
       }
-      rk4_piece<FL>(M, st, pa, b, inv0, inv1);
+      rk4_piece<FL>(M, sg, y, pa, b, inv0, inv1, nb0, nb1);
     }
-    out[((int64_t)d * NG) * kTile] = st.y[0];
-    if constexpr (NG == 2) out[((int64_t)d * NG + 1) * kTile] = st.y[5];
+    out[((int64_t)d * NG) * kTile] = y[0];
+    if constexpr (NG == 2) out[((int64_t)d * NG + 1) * kTile] = y[5];
   }
 }
 
@@ -343,10 +389,12 @@ __device__ __forceinline__ void build_profile(const WarpSmem &w, int q, double m
   // CDF at the n+1 cell edges x0 + i
   double shape = 0, scale = 1;
   if constexpr (Traits<FL>::kAge) { scale = sd * sd / mean; shape = mean / scale; }
+  double lga = 0.0;
+  if constexpr (Traits<FL>::kAge) lga = lgamma(shape);  // once per profile, not once per CDF point
   for (int i = lane; i <= n; i += 32) {
     const double x = x0 + (double)i;
     double c;
-    if constexpr (Traits<FL>::kAge) c = dev_pgamma(x, shape, scale);
+    if constexpr (Traits<FL>::kAge) c = dev_pgamma(x, shape, scale, lga);
     else c = dev_pnorm(x, mean, sd);
     w.cdf[i] = c;
   }
@@ -531,38 +579,142 @@ __device__ __forceinline__ double score_day(const DevModel &M, int s, int t, int
   return acc;
 }
 
+// ---- shared-memory carve-up of k_score / k_series (per warp) -------------------
+// theta[EPI_MAX_PARAMS] | Wabs[NG][EPI_MAX_TAPS][4] | S[NG][kPadMax + P]
+// Wabs holds the KG = NK/NG latency profiles of one S group indexed by ABSOLUTE delay
+// (zero outside a profile's support), so that one sweep over the delay feeds KG
+// independent FMA chains from a single S load.
 template <int FL>
-__global__ void __launch_bounds__(128)
+__host__ __device__ constexpr int score_smem_doubles(int ndays) {
+  // even, so that every warp's Wabs stays 16-byte aligned for the double2 weight loads
+  return (EPI_MAX_PARAMS + Traits<FL>::NG * EPI_MAX_TAPS * 4 + Traits<FL>::NG * (kPadMax + ndays) + 3) & ~1;
+}
+
+struct ScoreSmem {
+  double *theta, *Wabs, *S;
+};
+
+template <int FL>
+__device__ __forceinline__ ScoreSmem carve_score(double *base) {
+  ScoreSmem w;
+  w.theta = base;
+  w.Wabs = base + EPI_MAX_PARAMS;
+  w.S = w.Wabs + Traits<FL>::NG * EPI_MAX_TAPS * 4;
+  return w;
+}
+
+// Stage theta (MODEL space), the profiles in absolute-delay form and the S history.
+// Returns per-group sweep bounds [lo, hi] and per-profile (dmin, n).
+template <int FL>
+__device__ __forceinline__ void stage_score(const DevModel &M, const ScoreSmem &w, const double *__restrict__ theta,
+                                            int64_t ld, int64_t chain, bool to_model_space,
+                                            const double *__restrict__ hist2, const double *__restrict__ Wg,
+                                            const int2 *__restrict__ pmeta, int P, int lane, int *dmin_, int *n_,
+                                            int *lo, int *hi) {
+  constexpr int NK = Traits<FL>::NK, NG = Traits<FL>::NG, KG = NK / NG;
+  for (int p = lane; p < M.d; p += 32) {
+    double v = theta[(int64_t)p * ld + chain];
+    if (to_model_space && !Traits<FL>::kAge && p == 4) v = exp(v);  // transformParams, :136-142
+    w.theta[p] = v;
+  }
+  for (int i = lane; i < NG * EPI_MAX_TAPS * 4; i += 32) w.Wabs[i] = 0.0;
+  __syncwarp();
+#pragma unroll
+  for (int g = 0; g < NG; ++g) { lo[g] = EPI_MAX_TAPS; hi[g] = 0; }
+#pragma unroll
+  for (int q = 0; q < NK; ++q) {
+    const int2 pm = pmeta[(int64_t)chain * NK + q];
+    dmin_[q] = pm.x; n_[q] = pm.y;
+    const int g = q / KG;
+    lo[g] = min(lo[g], pm.x);
+    hi[g] = max(hi[g], pm.x + pm.y - 1);
+    for (int o = lane; o < pm.y; o += 32)
+      w.Wabs[(g * EPI_MAX_TAPS + pm.x + o) * 4 + (q % KG)] = Wg[((int64_t)chain * NK + q) * EPI_MAX_TAPS + o];
+  }
+  const int stride = kPadMax + P;
+  const double *in = hist2 + ((chain / kTile) * (int64_t)P * NG) * kTile + (chain % kTile);
+#pragma unroll
+  for (int g = 0; g < NG; ++g) {
+    const double s0 = Traits<FL>::kAge ? (g == 0 ? M.Ny - 1.0 : M.No) : M.N - 1.0;
+    for (int j = lane; j < kPadMax; j += 32) w.S[g * stride + j] = s0;
+    for (int j = lane; j < P; j += 32) w.S[g * stride + kPadMax + j] = in[((int64_t)j * NG + g) * kTile];
+  }
+  __syncwarp();
+}
+
+// convolute() (model-age-groups2q.R:42-45) of the KG profiles of one S group at the two
+// padded day indices ja and ja + 32 in ONE sweep over the delay d:
+//   conv_q(t) = sum_d Wabs[d][q] * S[t - d]
+// (ncu, profiles/r1_v1: the per-profile serial FMA chain with two LDS per FMA left the
+// FP64 pipe 17 % busy; here every S load feeds KG chains and every weight load 2 days.)
+template <int KG>
+__device__ __forceinline__ void conv_group2(const double *__restrict__ Sg, const double *__restrict__ Wabs, int lo,
+                                            int hi, int ja, int P, double *ca, double *cb) {
+  const int j0 = min(max(ja, 0), P - 1), j1 = min(max(ja + 32, 0), P - 1);  // out-of-range days are discarded later
+  const double *xa = Sg + kPadMax + j0, *xb = Sg + kPadMax + j1;
+#pragma unroll
+  for (int q = 0; q < KG; ++q) { ca[q] = 0.0; cb[q] = 0.0; }
+  for (int d = lo; d <= hi; ++d) {
+    const double x0 = xa[-d], x1 = xb[-d];
+    const double2 w01 = *reinterpret_cast<const double2 *>(Wabs + d * 4);
+    ca[0] = fma(w01.x, x0, ca[0]); cb[0] = fma(w01.x, x1, cb[0]);
+    ca[1] = fma(w01.y, x0, ca[1]); cb[1] = fma(w01.y, x1, cb[1]);
+    if constexpr (KG == 3) {
+      const double w2 = Wabs[d * 4 + 2];
+      ca[2] = fma(w2, x0, ca[2]); cb[2] = fma(w2, x1, cb[2]);
+    }
+  }
+}
+
+// the three-slice rate map of model-age-groups2q.R:240-251 for the six series
+struct AgeMap {
+  int t1[6], t2[6];
+  double r_first[6], r_last[6];
+  bool valid;
+  int pad;
+  __device__ __forceinline__ void init(const DevModel &M, const double *th, int off_raw, int pad_, int P) {
+    valid = off_raw != EPI_INVALID_DATA_OFFSET;
+    pad = pad_;
+    const double ydl = th[12];  // y.DL is used for both groups (:290,306)
+    const double lat[6] = {th[43], th[11], 0, th[44], th[15], 0};
+#pragma unroll
+    for (int q = 0; q < 6; ++q) {
+      const int shift = (q == 2 || q == 5) ? 0 : (int)rint(-ydl + lat[q]);
+      t1[q] = off_raw + shift;
+      t2[q] = min(pad + P, t1[q] + M.n_rate - 1);
+      r_first[q] = age_rate(M, th, q, 1);
+      r_last[q] = age_rate(M, th, q, M.n_rate);
+    }
+  }
+  __device__ __forceinline__ double value(const DevModel &M, const double *th, int q, int t, double inc) const {
+    if (!valid) return inc * r_first[q];              // :250
+    if (!(t1[q] > pad && t2[q] > t1[q])) return 0.0;  // :244
+    const double r = (t >= t2[q]) ? r_last[q] : (t <= t1[q]) ? r_first[q] : age_rate(M, th, q, t - t1[q] + 1);
+    return inc * r;  // later slices overwrite the shared end points (:245-247)
+  }
+};
+
+template <int FL>
+__global__ void __launch_bounds__(128, 4)
 k_score(const DevModel M, const PriorTerm *__restrict__ PT, int n_prior, const double *__restrict__ theta, int64_t ld, int64_t n,
         const double *__restrict__ hist2, const int *__restrict__ offset, const int *__restrict__ padv,
         const double *__restrict__ Wg, const int2 *__restrict__ pmeta, int *__restrict__ status,
         double *__restrict__ logl, double *__restrict__ logp, double *__restrict__ terms) {
-  constexpr int NK = Traits<FL>::NK;
+  constexpr int NK = Traits<FL>::NK, NG = Traits<FL>::NG;
   extern __shared__ double smem[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int64_t chain = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
   if (chain >= n) return;
   const int P = M.P;
-  const WarpSmem w = carve<FL>(smem + (size_t)wib * warp_smem_doubles<FL>(P), P);
-
-  double raw[2] = {0.0, 0.0};  // untransformed theta for the prior (lane holds p = lane, lane+32)
-  for (int p = lane, c = 0; p < M.d; p += 32, ++c) {
-    double v = theta[(int64_t)p * ld + chain];
-    raw[c] = v;
-    if (!Traits<FL>::kAge && p == 4) v = exp(v);
-    w.theta[p] = v;
-  }
-  __syncwarp();
+  const ScoreSmem w = carve_score<FL>(smem + (size_t)wib * score_smem_doubles<FL>(P));
   int st = status[chain];
 
-  // prior on the UNTRANSFORMED vector (R/MCMC/fitMCMC-drj.R:51); no prior term reads
-  // theta[4] in the simple flavour, so the staged model-space copy serves
-  double lp = 0.0;
-  for (int k = lane; k < n_prior; k += 32) lp += prior_term(PT[k], w.theta);
-  lp = warp_sum(lp);
-  (void)raw;
-
   if (st & EPI_ST_UNSUPPORTED) {
+    for (int p = lane; p < M.d; p += 32) w.theta[p] = theta[(int64_t)p * ld + chain];
+    __syncwarp();
+    double lp = 0.0;
+    for (int k = lane; k < n_prior; k += 32) lp += prior_term(PT[k], w.theta);
+    lp = warp_sum(lp);
     if (lane == 0) {
       if (logl) logl[chain] = NAN;
       if (logp) logp[chain] = lp;
@@ -571,17 +723,19 @@ k_score(const DevModel M, const PriorTerm *__restrict__ PT, int n_prior, const d
     return;
   }
 
+  int dmin_[NK], n_[NK], lo[NG], hi[NG];
+  stage_score<FL>(M, w, theta, ld, chain, true, hist2, Wg, pmeta, P, lane, dmin_, n_, lo, hi);
+
+  // prior on the UNTRANSFORMED vector (R/MCMC/fitMCMC-drj.R:51); no prior term reads
+  // theta[4] in the simple flavour, so the staged model-space copy serves
+  double lp = 0.0;
+  for (int k = lane; k < n_prior; k += 32) lp += prior_term(PT[k], w.theta);
+  lp = warp_sum(lp);
+
   const int pad = padv[chain];
   const int T = pad + P;
   const int off_raw = offset[chain];
-  const bool valid = off_raw != EPI_INVALID_DATA_OFFSET;
-  const int off = valid ? off_raw : 1;  // :493-494
-
-  for (int i = lane; i < NK * EPI_MAX_TAPS; i += 32) w.W[i] = Wg[(int64_t)chain * NK * EPI_MAX_TAPS + i];
-  int dmin_[NK], n_[NK];
-#pragma unroll
-  for (int q = 0; q < NK; ++q) { const int2 pm = pmeta[(int64_t)chain * NK + q]; dmin_[q] = pm.x; n_[q] = pm.y; }
-  stage_history<FL>(M, w, hist2, chain, P, lane);
+  const int off = off_raw != EPI_INVALID_DATA_OFFSET ? off_raw : 1;  // :493-494
   const int stride = kPadMax + P;
 
   int dstart[kMaxSeries];
@@ -590,58 +744,44 @@ k_score(const DevModel M, const PriorTerm *__restrict__ PT, int n_prior, const d
 
   double acc[kMaxSeries] = {0, 0, 0, 0, 0};
   double ysum = 0.0, osum = 0.0;
+  const int jlo = tlo - (pad + 1);  // <= 0: scored days before padding+1 read the 0 prefill
 
   if constexpr (Traits<FL>::kAge) {
-    // rate-map anchors t1 (:242,259,274,290,306,321); y.DL is used for both groups
-    int t1[6], t2[6];
-    double r_first[6], r_last[6];
-    const double ydl = w.theta[12];
-    const double lat[6] = {w.theta[43], w.theta[11], 0, w.theta[44], w.theta[15], 0};
-#pragma unroll
-    for (int q = 0; q < 6; ++q) {
-      const int shift = (q == 2 || q == 5) ? 0 : (int)rint(-ydl + lat[q]);
-      t1[q] = off_raw + shift;
-      t2[q] = min(pad + P, t1[q] + M.n_rate - 1);
-      r_first[q] = age_rate(M, w.theta, q, 1);
-      r_last[q] = age_rate(M, w.theta, q, M.n_rate);
-    }
+    AgeMap map;
+    map.init(M, w.theta, off_raw, pad, P);
     double carry[6] = {0, 0, 0, 0, 0, 0};
-    const int jlo = tlo - (pad + 1);  // <= 0
-    for (int base = jlo; base < P; base += 32) {
-      const int j = base + lane;
-      const int t = pad + 1 + j;
-      double val[6];
-      double s2[6];
+    for (int base = jlo; base < P; base += 64) {
+      double ca[6], cb[6];
+      conv_group2<3>(w.S, w.Wabs, lo[0], hi[0], base + lane, P, ca, cb);
+      conv_group2<3>(w.S + stride, w.Wabs + EPI_MAX_TAPS * 4, lo[1], hi[1], base + lane, P, ca + 3, cb + 3);
 #pragma unroll
-      for (int q = 0; q < 6; ++q) {
-        const int g = q / 3;
-        const double Ng = g == 0 ? M.Ny : M.No;
-        s2[q] = (j >= 0 && j < P) ? Ng - conv_at(w.S + g * stride, w.W + q * EPI_MAX_TAPS, pad, j, dmin_[q], n_[q]) : 0.0;
-        double prev = __shfl_up_sync(0xffffffffu, s2[q], 1);
-        if (lane == 0) prev = carry[q];
-        carry[q] = __shfl_sync(0xffffffffu, s2[q], 31);
-        const double inc = (j == 0) ? s2[q] : s2[q] - prev;  // c(s2[1], diff(s2)), :239
-        double v = 0.0;
-        if (j >= 0 && j < P) {
-          if (valid) {
-            if (t1[q] > pad && t2[q] > t1[q]) {  // :244-248 (later slices overwrite the shared end points)
-              const double r = (t >= t2[q]) ? r_last[q] : (t <= t1[q]) ? r_first[q] : age_rate(M, w.theta, q, t - t1[q] + 1);
-              v = inc * r;
-            }
-          } else {
-            v = inc * r_first[q];  // :250
-          }
+      for (int half = 0; half < 2; ++half) {
+        const int j = base + 32 * half + lane;
+        const int t = pad + 1 + j;
+        const bool in = j >= 0 && j < P;
+        double val[6];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+          const double Ng = q < 3 ? M.Ny : M.No;
+          double c = half ? cb[q] : ca[q];
+          if (t - dmin_[q] < n_[q]) c = NAN;  // stats::filter leaves the first n-1 outputs NA
+          const double s2 = in ? Ng - c : 0.0;
+          double prev = __shfl_up_sync(0xffffffffu, s2, 1);
+          if (lane == 0) prev = carry[q];
+          carry[q] = __shfl_sync(0xffffffffu, s2, 31);
+          const double inc = (j == 0) ? s2 : s2 - prev;  // c(s2[1], diff(s2)), :239
+          val[q] = in ? map.value(M, w.theta, q, t, inc) : 0.0;
         }
-        val[q] = v;
-      }
-      if (j < P) {
-        // scored series: y.casei, o.casei, hospi = y.hospi + o.hospi, y.deadi, o.deadi
-        acc[0] += score_day(M, 0, t, dstart[0], val[0]);
-        acc[1] += score_day(M, 1, t, dstart[1], val[3]);
-        acc[2] += score_day(M, 2, t, dstart[2], val[1] + val[4]);
-        acc[3] += score_day(M, 3, t, dstart[3], val[2]);
-        acc[4] += score_day(M, 4, t, dstart[4], val[5]);
-        if (t >= dstart[2] + M.d_hosp_o1 && t <= dstart[2] + M.d_hosp_o2) { ysum += val[1]; osum += val[4]; }  // :563-564
+        if (j < P) {
+          // scored series: y.casei, o.casei, hospi = y.hospi + o.hospi, y.deadi, o.deadi
+          // (profile order: ycase, yhosp, ydied, ocase, ohosp, odied)
+          acc[0] += score_day(M, 0, t, dstart[0], val[0]);
+          acc[1] += score_day(M, 1, t, dstart[1], val[3]);
+          acc[2] += score_day(M, 2, t, dstart[2], val[1] + val[4]);
+          acc[3] += score_day(M, 3, t, dstart[3], val[2]);
+          acc[4] += score_day(M, 4, t, dstart[4], val[5]);
+          if (t >= dstart[2] + M.d_hosp_o1 && t <= dstart[2] + M.d_hosp_o2) { ysum += val[1]; osum += val[4]; }  // :563-564
+        }
       }
     }
   } else {
@@ -649,18 +789,25 @@ k_score(const DevModel M, const PriorTerm *__restrict__ PT, int n_prior, const d
     // hospi/deadi = c(v[1], diff(v)) (model-simple-ode-drj-cmp.R:115-122)
     const double rate[2] = {w.theta[4], 0.007};
     double carry[2] = {0, 0};
-    const int jlo = tlo - (pad + 1);
-    for (int base = jlo; base < P; base += 32) {
-      const int j = base + lane;
-      const int t = pad + 1 + j;
+    for (int base = jlo; base < P; base += 64) {
+      double ca[2], cb[2];
+      conv_group2<2>(w.S, w.Wabs, lo[0], hi[0], base + lane, P, ca, cb);
 #pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        const double cum = (j >= 0 && j < P) ? (M.N - conv_at(w.S, w.W + q * EPI_MAX_TAPS, pad, j, dmin_[q], n_[q])) * rate[q] : 0.0;
-        double prev = __shfl_up_sync(0xffffffffu, cum, 1);
-        if (lane == 0) prev = carry[q];
-        carry[q] = __shfl_sync(0xffffffffu, cum, 31);
-        const double inc = cum - prev;  // prev is 0 for t = pad+1 (prefill)
-        if (j < P) acc[q] += score_day(M, q, t, dstart[q], (j >= 0) ? inc : 0.0);
+      for (int half = 0; half < 2; ++half) {
+        const int j = base + 32 * half + lane;
+        const int t = pad + 1 + j;
+        const bool in = j >= 0 && j < P;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          double c = half ? cb[q] : ca[q];
+          if (t - dmin_[q] < n_[q]) c = NAN;
+          const double cum = in ? (M.N - c) * rate[q] : 0.0;
+          double prev = __shfl_up_sync(0xffffffffu, cum, 1);
+          if (lane == 0) prev = carry[q];
+          carry[q] = __shfl_sync(0xffffffffu, cum, 31);
+          const double inc = cum - prev;  // prev is 0 for t = pad+1 (prefill)
+          if (j < P) acc[q] += score_day(M, q, t, dstart[q], (j >= 0) ? inc : 0.0);
+        }
       }
     }
   }
@@ -692,88 +839,80 @@ k_score(const DevModel M, const PriorTerm *__restrict__ PT, int n_prior, const d
 // calculateModel() output series for days padding+1..padding+P (epi_trajectories):
 // age: y.S,o.S,y.casei,o.casei,y.hospi,o.hospi,y.deadi,o.deadi; simple: S,hospi,deadi.
 template <int FL>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 4)
 k_series(const DevModel M, const double *__restrict__ theta, int64_t ld, int64_t n, const double *__restrict__ hist2,
          const int *__restrict__ offset, const int *__restrict__ padv, const double *__restrict__ Wg,
          const int2 *__restrict__ pmeta, const int *__restrict__ status, double *__restrict__ out) {
-  constexpr int NK = Traits<FL>::NK;
+  constexpr int NK = Traits<FL>::NK, NG = Traits<FL>::NG;
   constexpr int NS = Traits<FL>::kAge ? 8 : 3;
   extern __shared__ double smem[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int64_t chain = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
   if (chain >= n) return;
   const int P = M.P;
-  const WarpSmem w = carve<FL>(smem + (size_t)wib * warp_smem_doubles<FL>(P), P);
+  const ScoreSmem w = carve_score<FL>(smem + (size_t)wib * score_smem_doubles<FL>(P));
   double *o = out + (int64_t)chain * NS * P;
   if (status[chain] & EPI_ST_UNSUPPORTED) {
     for (int i = lane; i < NS * P; i += 32) o[i] = NAN;
     return;
   }
   // theta is already in MODEL space here (calculateModel is called with transformed params)
-  for (int p = lane; p < M.d; p += 32) w.theta[p] = theta[(int64_t)p * ld + chain];
-  __syncwarp();
+  int dmin_[NK], n_[NK], lo[NG], hi[NG];
+  stage_score<FL>(M, w, theta, ld, chain, false, hist2, Wg, pmeta, P, lane, dmin_, n_, lo, hi);
   const int pad = padv[chain];
   const int off_raw = offset[chain];
-  const bool valid = off_raw != EPI_INVALID_DATA_OFFSET;
-  for (int i = lane; i < NK * EPI_MAX_TAPS; i += 32) w.W[i] = Wg[(int64_t)chain * NK * EPI_MAX_TAPS + i];
-  int dmin_[NK], n_[NK];
-#pragma unroll
-  for (int q = 0; q < NK; ++q) { const int2 pm = pmeta[(int64_t)chain * NK + q]; dmin_[q] = pm.x; n_[q] = pm.y; }
-  stage_history<FL>(M, w, hist2, chain, P, lane);
   const int stride = kPadMax + P;
   if constexpr (Traits<FL>::kAge) {
-    int t1[6], t2[6];
-    double r_first[6], r_last[6];
-    const double ydl = w.theta[12];
-    const double lat[6] = {w.theta[43], w.theta[11], 0, w.theta[44], w.theta[15], 0};
-#pragma unroll
-    for (int q = 0; q < 6; ++q) {
-      const int shift = (q == 2 || q == 5) ? 0 : (int)rint(-ydl + lat[q]);
-      t1[q] = off_raw + shift;
-      t2[q] = min(pad + P, t1[q] + M.n_rate - 1);
-      r_first[q] = age_rate(M, w.theta, q, 1);
-      r_last[q] = age_rate(M, w.theta, q, M.n_rate);
-    }
+    AgeMap map;
+    map.init(M, w.theta, off_raw, pad, P);
     const int dst[6] = {2, 4, 6, 3, 5, 7};
     double carry[6] = {0, 0, 0, 0, 0, 0};
-    for (int base = 0; base < P; base += 32) {
-      const int j = base + lane;
-      const int t = pad + 1 + j;
-      if (j < P) { o[0 * P + j] = w.S[kPadMax + j]; o[1 * P + j] = w.S[stride + kPadMax + j]; }
+    for (int base = 0; base < P; base += 64) {
+      double ca[6], cb[6];
+      conv_group2<3>(w.S, w.Wabs, lo[0], hi[0], base + lane, P, ca, cb);
+      conv_group2<3>(w.S + stride, w.Wabs + EPI_MAX_TAPS * 4, lo[1], hi[1], base + lane, P, ca + 3, cb + 3);
 #pragma unroll
-      for (int q = 0; q < 6; ++q) {
-        const int g = q / 3;
-        const double Ng = g == 0 ? M.Ny : M.No;
-        const double s2 = (j < P) ? Ng - conv_at(w.S + g * stride, w.W + q * EPI_MAX_TAPS, pad, j, dmin_[q], n_[q]) : 0.0;
-        double prev = __shfl_up_sync(0xffffffffu, s2, 1);
-        if (lane == 0) prev = carry[q];
-        carry[q] = __shfl_sync(0xffffffffu, s2, 31);
-        const double inc = (j == 0) ? s2 : s2 - prev;
-        double v = 0.0;
-        if (valid) {
-          if (t1[q] > pad && t2[q] > t1[q]) {
-            const double r = (t >= t2[q]) ? r_last[q] : (t <= t1[q]) ? r_first[q] : age_rate(M, w.theta, q, t - t1[q] + 1);
-            v = inc * r;
-          }
-        } else {
-          v = inc * r_first[q];
+      for (int half = 0; half < 2; ++half) {
+        const int j = base + 32 * half + lane;
+        const int t = pad + 1 + j;
+        const bool in = j < P;
+        if (in) { o[0 * P + j] = w.S[kPadMax + j]; o[1 * P + j] = w.S[stride + kPadMax + j]; }
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+          const double Ng = q < 3 ? M.Ny : M.No;
+          double c = half ? cb[q] : ca[q];
+          if (t - dmin_[q] < n_[q]) c = NAN;
+          const double s2 = in ? Ng - c : 0.0;
+          double prev = __shfl_up_sync(0xffffffffu, s2, 1);
+          if (lane == 0) prev = carry[q];
+          carry[q] = __shfl_sync(0xffffffffu, s2, 31);
+          const double inc = (j == 0) ? s2 : s2 - prev;
+          if (in) o[dst[q] * P + j] = map.value(M, w.theta, q, t, inc);
         }
-        if (j < P) o[dst[q] * P + j] = v;
       }
     }
   } else {
     const double rate[2] = {w.theta[4], 0.007};
     double carry[2] = {0, 0};
-    for (int base = 0; base < P; base += 32) {
-      const int j = base + lane;
-      if (j < P) o[j] = w.S[kPadMax + j];
+    for (int base = 0; base < P; base += 64) {
+      double ca[2], cb[2];
+      conv_group2<2>(w.S, w.Wabs, lo[0], hi[0], base + lane, P, ca, cb);
 #pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        const double cum = (j < P) ? (M.N - conv_at(w.S, w.W + q * EPI_MAX_TAPS, pad, j, dmin_[q], n_[q])) * rate[q] : 0.0;
-        double prev = __shfl_up_sync(0xffffffffu, cum, 1);
-        if (lane == 0) prev = carry[q];
-        carry[q] = __shfl_sync(0xffffffffu, cum, 31);
-        if (j < P) o[(1 + q) * P + j] = cum - prev;
+      for (int half = 0; half < 2; ++half) {
+        const int j = base + 32 * half + lane;
+        const int t = pad + 1 + j;
+        const bool in = j < P;
+        if (in) o[j] = w.S[kPadMax + j];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          double c = half ? cb[q] : ca[q];
+          if (t - dmin_[q] < n_[q]) c = NAN;
+          const double cum = in ? (M.N - c) * rate[q] : 0.0;
+          double prev = __shfl_up_sync(0xffffffffu, cum, 1);
+          if (lane == 0) prev = carry[q];
+          carry[q] = __shfl_sync(0xffffffffu, cum, 31);
+          if (in) o[(1 + q) * P + j] = cum - prev;
+        }
       }
     }
   }
@@ -810,10 +949,10 @@ template <int FL>
 static cudaError_t launch_eval_fl(const EvalArgs &a) {
   const DevModel &M = *a.M;
   const int64_t n = a.n;
-  const unsigned ode_blocks = (unsigned)((n + 63) / 64);
+  const unsigned ode_blocks = (unsigned)((n + 31) / 32);
   const unsigned warp_blocks = (unsigned)((n + 3) / 4);
   const size_t smem_mid = (size_t)4 * warp_smem_doubles<FL>(M.P1) * sizeof(double);
-  const size_t smem_score = (size_t)4 * warp_smem_doubles<FL>(M.P) * sizeof(double);
+  const size_t smem_score = (size_t)4 * score_smem_doubles<FL>(M.P) * sizeof(double);
   static bool attr_done = false;
   if (!attr_done) {
     cudaFuncSetAttribute(k_mid<FL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -823,11 +962,11 @@ static cudaError_t launch_eval_fl(const EvalArgs &a) {
   }
   cudaStream_t s = a.stream;
   if (a.ev) cudaEventRecord(a.ev[0], s);
-  k_ode<FL, false><<<ode_blocks, 64, 0, s>>>(M, a.theta, a.ld, n, nullptr, nullptr, nullptr, a.hist1);
+  k_ode<FL, false><<<ode_blocks, 32, 0, s>>>(M, a.theta, a.ld, n, nullptr, nullptr, nullptr, a.hist1);
   if (a.ev) cudaEventRecord(a.ev[1], s);
   k_mid<FL><<<warp_blocks, 128, smem_mid, s>>>(M, a.theta, a.ld, n, a.hist1, a.offset, a.pad, a.status, a.W, a.pmeta, a.model_space);
   if (a.ev) cudaEventRecord(a.ev[2], s);
-  k_ode<FL, true><<<ode_blocks, 64, 0, s>>>(M, a.theta, a.ld, n, a.offset, a.pad, a.hist1, a.hist2);
+  k_ode<FL, true><<<ode_blocks, 32, 0, s>>>(M, a.theta, a.ld, n, a.offset, a.pad, a.hist1, a.hist2);
   if (a.ev) cudaEventRecord(a.ev[3], s);
   if (a.series_out) {
     k_series<FL><<<warp_blocks, 128, smem_score, s>>>(M, a.theta, a.ld, n, a.hist2, a.offset, a.pad, a.W, a.pmeta,

@@ -1,0 +1,199 @@
+"""On-device population sampler (K2) behind the reference driver's call shape.
+
+The reference driver (R/MCMC/fitMCMC-drj.R:47-62) calls drjacoby::run_mcmc four
+times, prints ESS and acceptance, and writes the cold-rung sampling draws to
+`<outputfile>_<chain>` with the columns `chain, phase, iteration, <params>,
+logprior, loglikelihood`.  `run_mcmc` below keeps that call shape and output
+schema, but the chains live on the GPU: every iteration is the four K1 launches
+plus one fused accept/propose launch (csrc/epi_sampler.cu), the host only
+sequences launches and, for DE-MC on several GPUs, triggers the NCCL all-gather
+of the population every `exchange_every` iterations (dist.py).
+"""
+from __future__ import annotations
+
+import csv
+import ctypes as C
+
+import numpy as np
+
+from . import _capi
+
+KINDS = {"rwm": _capi.SAMPLER_RWM, "demc": _capi.SAMPLER_DEMC}
+
+
+class Sampler:
+    def __init__(self, model, n_chains: int, kind: str = "demc", seed: int = 42, scale: float | None = None,
+                 de_eps: float = 1e-4, beta: float = 1.0, chain_id0: int = 0, theta0=None):
+        self.model = model
+        self._lib = model._lib
+        self._h = model._h
+        self.n_chains = int(n_chains)
+        self.kind = kind
+        if scale is None:
+            scale = 1.0 if kind == "demc" else 0.02 / np.sqrt(model.d)
+        cfg = _capi.SamplerCfg(KINDS[kind], self.n_chains, int(chain_id0), int(seed), float(scale), float(de_eps),
+                               float(beta), 0, 0)
+        t0 = None
+        if theta0 is not None:
+            t0 = np.ascontiguousarray(np.asarray(theta0, dtype=np.float64))
+            assert t0.shape == (self.n_chains, model.d)
+        _capi.check(self._lib.epi_sampler_init(self._h, C.byref(cfg), _capi.as_dp(t0) if t0 is not None else None),
+                    self._h)
+
+    def run(self, n_iter: int):
+        _capi.check(self._lib.epi_sampler_run(self._h, int(n_iter)), self._h)
+
+    def adapt(self, enable: bool, target: float = 0.234):
+        _capi.check(self._lib.epi_sampler_adapt(self._h, int(enable), float(target)), self._h)
+
+    def record(self, thin: int, capacity: int):
+        _capi.check(self._lib.epi_sampler_record(self._h, int(thin), int(capacity)), self._h)
+
+    def refresh_population(self):
+        """single-GPU DE-MC: re-snapshot the population from the current states"""
+        _capi.check(self._lib.epi_sampler_set_population(self._h, None, 0, 0, 0), self._h)
+
+    def set_population(self, d_pop_ptr: int, n_ranks: int, chains_per_rank: int, ld_rank: int):
+        _capi.check(self._lib.epi_sampler_set_population(self._h, d_pop_ptr, n_ranks, chains_per_rank, ld_rank), self._h)
+
+    def state_device(self):
+        """(theta_ptr, logl_ptr, logp_ptr, ld): raw device pointers of the d x ld SoA state"""
+        th, ll, lp = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        ld = C.c_int64()
+        _capi.check(self._lib.epi_sampler_state_device(self._h, C.byref(th), C.byref(ll), C.byref(lp), C.byref(ld)), self._h)
+        return th.value, ll.value, lp.value, ld.value
+
+    def get(self):
+        d, n = self.model.d, self.n_chains
+        theta, logl, logp = np.empty((n, d)), np.empty(n), np.empty(n)
+        _capi.check(self._lib.epi_sampler_get(self._h, _capi.as_dp(theta), _capi.as_dp(logl), _capi.as_dp(logp)), self._h)
+        return theta, logl, logp
+
+    def stats(self) -> dict:
+        it, acc, ev = C.c_int64(), C.c_int64(), C.c_int64()
+        _capi.check(self._lib.epi_sampler_stats(self._h, C.byref(it), C.byref(acc), C.byref(ev)), self._h)
+        n = max(1, it.value * self.n_chains)
+        return dict(iterations=it.value, accepted=acc.value, evals=ev.value, accept_rate=acc.value / n)
+
+    def draws(self):
+        """(draws[k, chain, d], logpost[k, chain]) of the recorded thinned states"""
+        kept = C.c_int32()
+        _capi.check(self._lib.epi_sampler_draws(self._h, None, None, C.byref(kept)), self._h)
+        k = kept.value
+        out = np.empty((k, self.n_chains, self.model.d))
+        lp = np.empty((k, self.n_chains))
+        if k:
+            _capi.check(self._lib.epi_sampler_draws(self._h, _capi.as_dp(out), _capi.as_dp(lp), C.byref(kept)), self._h)
+        return out, lp
+
+
+# ----------------------------------------------------------------------------- ESS
+def _spectrum0_ar(x: np.ndarray) -> float:
+    """coda::spectrum0.ar: spectral density at frequency zero from an AR(p) fit (Yule-Walker,
+    order by AIC, p <= 10*log10(n)).  This is what coda::effectiveSize — and the ESS drjacoby
+    prints (fitMCMC-drj.R:58) — is built on."""
+    n = len(x)
+    x = x - x.mean()
+    v = float(x @ x) / n
+    if v <= 0:
+        return 0.0
+    pmax = max(1, min(n - 1, int(np.floor(10 * np.log10(n)))))
+    acov = np.array([float(x[: n - k] @ x[k:]) / n for k in range(pmax + 1)])
+    # Levinson-Durbin
+    best_aic, best = n * np.log(v), (v, np.zeros(0))
+    phi = np.zeros(0)
+    err = acov[0]
+    for p in range(1, pmax + 1):
+        k = (acov[p] - phi @ acov[p - 1:0:-1][: p - 1]) / err if p > 1 else acov[1] / err
+        phi = np.concatenate([phi - k * phi[::-1], [k]])
+        err = err * (1 - k * k)
+        if err <= 0:
+            break
+        aic = n * np.log(err) + 2 * p
+        if aic < best_aic:
+            best_aic, best = aic, (err * n / (n - (p + 1)), phi.copy())
+    var_pred, coef = best
+    return float(var_pred / (1.0 - coef.sum()) ** 2)
+
+
+def effective_size(chain: np.ndarray) -> float:
+    """coda::effectiveSize for one chain of scalar draws"""
+    x = np.asarray(chain, dtype=np.float64)
+    n = len(x)
+    if n < 4 or np.var(x) == 0:
+        return 0.0
+    s0 = _spectrum0_ar(x)
+    return float(min(n, n * np.var(x, ddof=1) / s0)) if s0 > 0 else 0.0
+
+
+def pooled_ess(draws: np.ndarray, max_chains: int = 256) -> np.ndarray:
+    """draws[k, chain, d] -> ESS per parameter, summed over chains (independent chains add;
+    coda's convention for mcmc.list).  For very wide populations a seeded subset of
+    `max_chains` chains is measured and scaled up."""
+    k, n, d = draws.shape
+    idx = np.arange(n)
+    if n > max_chains:
+        idx = np.random.default_rng(0).choice(n, max_chains, replace=False)
+    ess = np.zeros(d)
+    for p in range(d):
+        ess[p] = sum(effective_size(draws[:, c, p]) for c in idx)
+    return ess * (n / len(idx))
+
+
+# ------------------------------------------------------------------------ run_mcmc
+def run_mcmc(model, burnin: int = 1000, samples: int = 500, chains: int = 4096, kind: str = "demc", seed: int = 42,
+             thin: int = 1, exchange_every: int = 10, comm=None, **sampler_kw):
+    """The call the reference driver makes (fitMCMC-drj.R:48-57) — burn-in then sampling —
+    for a whole population of chains on the GPU.  Returns a dict with `output` (drjacoby
+    schema, sampling phase), `diagnostics` (ess per parameter, acceptance) and raw `draws`."""
+    rank, world = (comm.rank, comm.world) if comm is not None else (0, 1)
+    S = Sampler(model, chains, kind=kind, seed=seed, chain_id0=rank * chains, **sampler_kw)
+    if comm is not None and kind == "demc":
+        comm.attach(S)
+
+    def advance(n):
+        done = 0
+        while done < n:
+            step = min(exchange_every, n - done)
+            S.run(step)
+            done += step
+            if kind == "demc":
+                comm.exchange(S) if comm is not None else S.refresh_population()
+
+    S.adapt(True)
+    advance(burnin)
+    S.adapt(False)
+    keep = max(1, samples // thin)
+    S.record(thin, keep)
+    advance(samples)
+    draws, logpost = S.draws()
+    st = S.stats()
+    ess = pooled_ess(draws) if len(draws) >= 4 else np.zeros(model.d)
+    return dict(draws=draws, logpost=logpost, sampler=S,
+                diagnostics=dict(ess=dict(zip(model.fit_paramnames, ess)), accept_rate=st["accept_rate"],
+                                 evals=st["evals"], iterations=st["iterations"]))
+
+
+def write_chain_csv(path: str, model, draws: np.ndarray, chain: int, logprior=None, loglike=None, label=None):
+    """One chain's sampling draws in the file format fitMCMC-drj.R:60-62 writes with
+    write.csv(subset(output, rung == 20 & phase == "sampling")) and libMCMC.R:6-24 reads back:
+    a row-name column, then chain, rung, phase, iteration, <fit.paramnames>, logprior, loglikelihood."""
+    k = draws.shape[0]
+    with open(path, "w", newline="") as f:
+        w = csv.writer(f, quoting=csv.QUOTE_NONNUMERIC)
+        w.writerow(["", "chain", "rung", "phase", "iteration"] + list(model.fit_paramnames) + ["logprior", "loglikelihood"])
+        for i in range(k):
+            row = [str(i + 1), label or f"chain{chain + 1}", 20, "sampling", i + 1] + [float(v) for v in draws[i, chain]]
+            row += [float(logprior[i, chain]) if logprior is not None else float("nan"),
+                    float(loglike[i, chain]) if loglike is not None else float("nan")]
+            w.writerow(row)
+
+
+def write_max_csv(path: str, theta_best: np.ndarray):
+    """max.csv warm-start file read by fitMCMC-drj.R:8-13 (`init <- r$x[2:(length(init)+1)]`):
+    write.csv of c(maxLogP, params) as column x (model-2s-age-k.R:842-856)."""
+    with open(path, "w", newline="") as f:
+        w = csv.writer(f, quoting=csv.QUOTE_NONNUMERIC)
+        w.writerow(["", "x"])
+        for i, v in enumerate(theta_best):
+            w.writerow([str(i + 1), float(v)])
