@@ -34,6 +34,9 @@ struct SamplerState {
   double *logl = nullptr, *logp = nullptr, *logl_p = nullptr, *logp_p = nullptr;
   int *status_p = nullptr;
   double *lscale = nullptr;                  // per-chain log step multiplier (Robbins-Monro)
+  double *psd = nullptr;                     // per-parameter sd of the population (proposal shape)
+  double *cov = nullptr, *chol = nullptr;    // d x d population covariance and its Cholesky factor (lower, row-major)
+  bool psd_ready = false;
   unsigned long long *acc = nullptr;         // accepted moves, device scalar
   double *pop_own = nullptr;                 // own snapshot (1 rank)
   const double *pop = nullptr;               // population snapshot [rank][d][ld_rank]
@@ -42,7 +45,7 @@ struct SamplerState {
   double *draws = nullptr, *draws_lp = nullptr;  // [capacity][d][ld], [capacity][ld]
   int thin = 0, capacity = 0, kept = 0;
   int adapt = 0;
-  double adapt_target = 0.234;
+  double adapt_target = 0.0;  // <= 0: shape adaptation only (classical AM / DE-MC step sizes)
   int64_t iter = 0, evals = 0;
 };
 
@@ -94,7 +97,8 @@ k_accept_propose(int d, int64_t n, int64_t ld, int kind, uint64_t seed, int64_t 
                  const double *__restrict__ logp_p, const int *__restrict__ status_p, double *__restrict__ lscale,
                  int adapt, double adapt_target, unsigned long long *__restrict__ acc_total,
                  const double *__restrict__ pop, int pop_ranks, int pop_per_rank, int64_t pop_ld,
-                 double *__restrict__ draw_out, double *__restrict__ draw_lp) {
+                 const double *__restrict__ psd, const double *__restrict__ chol, double *__restrict__ draw_out,
+                 double *__restrict__ draw_lp) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = i < n;
   const uint64_t cid = (uint64_t)(chain_id0 + i);
@@ -113,7 +117,7 @@ k_accept_propose(int d, int64_t n, int64_t ld, int kind, uint64_t seed, int64_t 
       logl[i] = ll1;
       logp[i] = lp1;
     }
-    if (adapt) {  // Robbins-Monro on the log step size, gain 1/sqrt(iter+1)
+    if (adapt && adapt_target > 0.0) {  // optional Robbins-Monro on the per-chain log step size, gain 1/sqrt(iter+1)
       lscale[i] += ((accepted ? 1.0 : 0.0) - adapt_target) * rsqrt((double)(iter + 1));
     }
   }
@@ -131,8 +135,13 @@ k_accept_propose(int d, int64_t n, int64_t ld, int kind, uint64_t seed, int64_t 
   const double step = scale * exp(lscale[i]);
   const double *z1 = nullptr, *z2 = nullptr;
   double gam = 0.0;
+  philox4x32_10((uint32_t)cid, (uint32_t)(cid >> 32), it1, USE_PARTNER, k0, k1, r);
+  // scale mixture: each proposal draws its own step factor u ~ U(0.05, 1), independent of the
+  // state, so the kernel stays symmetric.  On this rugged target (ceil/floor kernel extents,
+  // integer data_offset) a single "optimal" step is accepted ~2 % of the time; the mixture
+  // keeps both the local moves and the occasional cell-crossing ones.
+  const double umix = 0.05 + 0.95 * u01(r[2]);
   if (kind == EPI_SAMPLER_DEMC && pop) {
-    philox4x32_10((uint32_t)cid, (uint32_t)(cid >> 32), it1, USE_PARTNER, k0, k1, r);
     const uint32_t tot = (uint32_t)pop_ranks * (uint32_t)pop_per_rank;
     uint32_t a = (uint32_t)(((uint64_t)r[0] * tot) >> 32);
     uint32_t b = (uint32_t)(((uint64_t)r[1] * (tot - 1)) >> 32);
@@ -140,24 +149,60 @@ k_accept_propose(int d, int64_t n, int64_t ld, int kind, uint64_t seed, int64_t 
     z1 = pop + ((int64_t)(a / pop_per_rank) * d) * pop_ld + (a % pop_per_rank);
     z2 = pop + ((int64_t)(b / pop_per_rank) * d) * pop_ld + (b % pop_per_rank);
     // ter Braak (2006): gamma = 2.38/sqrt(2d), every 10th proposal gamma = 1 (mode hopping)
-    gam = ((it1 % 10u) == 0u) ? 1.0 : step * 2.38 / sqrt(2.0 * d);
+    gam = ((it1 % 10u) == 0u) ? 1.0 : umix * step * 2.38 / sqrt(2.0 * d);
   }
+  double zn[EPI_MAX_PARAMS];
   for (int p0 = 0; p0 < d; p0 += 4) {
     philox4x32_10((uint32_t)cid, (uint32_t)(cid >> 32), it1, USE_NORMAL + (uint32_t)(p0 >> 2), k0, k1, r);
-    double z[4];
-    box_muller(r[0], r[1], z[0], z[1]);
-    box_muller(r[2], r[3], z[2], z[3]);
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int p = p0 + q;
-      if (p >= d) break;
-      const double lo = box_min[p], hi = box_max[p];
-      const double x = cur[(int64_t)p * ld + i];
-      double y;
-      if (z1) y = x + gam * (z1[(int64_t)p * pop_ld] - z2[(int64_t)p * pop_ld]) + de_eps * (hi - lo) * z[q];
-      else y = x + step * (hi - lo) * z[q];
-      prop[(int64_t)p * ld + i] = reflect(y, lo, hi);
+    box_muller(r[0], r[1], zn[p0], zn[p0 + 1]);
+    box_muller(r[2], r[3], zn[p0 + 2], zn[p0 + 3]);
+  }
+  const double rw = umix * step * 2.38 * rsqrt((double)d);
+  for (int p = 0; p < d; ++p) {
+    const double lo = box_min[p], hi = box_max[p];
+    const double x = cur[(int64_t)p * ld + i];
+    double y;
+    if (z1) {
+      // DE-MC: x + gamma (z1 - z2) + e, e ~ N(0, (de_eps * population sd)^2)
+      const double w = psd ? psd[p] : (hi - lo);
+      y = x + gam * (z1[(int64_t)p * pop_ld] - z2[(int64_t)p * pop_ld]) + de_eps * w * zn[p];
+    } else if (chol) {
+      // RWM with the population covariance: x + step * 2.38/sqrt(d) * L z  (adaptive Metropolis shape,
+      // measured during burn-in only)
+      double a = 0.0;
+      for (int q = 0; q <= p; ++q) a = fma(chol[p * d + q], zn[q], a);
+      y = x + rw * a;
+    } else {
+      y = x + step * 0.02 * rsqrt((double)d) * (hi - lo) * zn[p];  // before any adaptation: 2 % of the box / sqrt(d)
     }
+    prop[(int64_t)p * ld + i] = reflect(y, lo, hi);
+  }
+}
+
+// population covariance of the chains of this rank: one block per (p, q), q <= p
+__global__ void __launch_bounds__(256) k_cov(const double *__restrict__ cur, int64_t n, int64_t ld, int d,
+                                             double *__restrict__ cov) {
+  __shared__ double sa[256], sb[256], sab[256];
+  int p = 0, rem = blockIdx.x;
+  while (rem > p) { rem -= p + 1; ++p; }
+  const int q = rem;
+  const double *rp = cur + (int64_t)p * ld, *rq = cur + (int64_t)q * ld;
+  const double cp = rp[0], cq = rq[0];  // shifts for a stable one-pass estimate
+  double a = 0.0, b = 0.0, ab = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const double u = rp[i] - cp, v = rq[i] - cq;
+    a += u; b += v; ab = fma(u, v, ab);
+  }
+  sa[threadIdx.x] = a; sb[threadIdx.x] = b; sab[threadIdx.x] = ab;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) { sa[threadIdx.x] += sa[threadIdx.x + o]; sb[threadIdx.x] += sb[threadIdx.x + o]; sab[threadIdx.x] += sab[threadIdx.x + o]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const double c = (sab[0] - sa[0] * sb[0] / (double)n) / (double)(n > 1 ? n - 1 : 1);
+    cov[p * d + q] = c;
+    cov[q * d + p] = c;
   }
 }
 
@@ -184,9 +229,49 @@ void epi_sampler_free(epi_handle *h) {
   SamplerState *s = h->sampler;
   if (!s) return;
   cudaFree(s->cur); cudaFree(s->prop); cudaFree(s->logl); cudaFree(s->logp); cudaFree(s->logl_p); cudaFree(s->logp_p);
-  cudaFree(s->status_p); cudaFree(s->lscale); cudaFree(s->acc); cudaFree(s->pop_own); cudaFree(s->draws); cudaFree(s->draws_lp);
+  cudaFree(s->status_p); cudaFree(s->lscale); cudaFree(s->psd); cudaFree(s->cov); cudaFree(s->chol); cudaFree(s->acc); cudaFree(s->pop_own); cudaFree(s->draws); cudaFree(s->draws_lp);
   delete s;
   h->sampler = nullptr;
+}
+
+// population covariance on the device, Cholesky of the small d x d matrix on the host
+static int update_shape(epi_handle *h, SamplerState *s) {
+  const int d = h->M.d;
+  const int64_t n = s->cfg.n_chains;
+  k_cov<<<d * (d + 1) / 2, 256, 0, h->stream>>>(s->cur, n, s->ld, d, s->cov);
+  h->launches += 1;
+  std::vector<double> C((size_t)d * d), L((size_t)d * d, 0.0), sd(d);
+  CUDA_OK(h, cudaMemcpyAsync(C.data(), s->cov, sizeof(double) * C.size(), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_OK(h, cudaStreamSynchronize(h->stream));
+  for (int p = 0; p < d; ++p) {
+    const double v = C[(size_t)p * d + p];
+    if (!(v > 0) || !std::isfinite(v)) return EPI_OK;  // degenerate population: keep the previous shape
+    sd[p] = std::sqrt(v);
+  }
+  double ridge = 1e-12;
+  for (int attempt = 0; attempt < 8; ++attempt, ridge *= 100) {
+    bool ok = true;
+    std::fill(L.begin(), L.end(), 0.0);
+    for (int p = 0; p < d && ok; ++p)
+      for (int q = 0; q <= p; ++q) {
+        double a = C[(size_t)p * d + q] + (p == q ? ridge * C[(size_t)p * d + p] : 0.0);
+        for (int k = 0; k < q; ++k) a -= L[(size_t)p * d + k] * L[(size_t)q * d + k];
+        if (p == q) {
+          if (!(a > 0)) { ok = false; break; }
+          L[(size_t)p * d + p] = std::sqrt(a);
+        } else {
+          L[(size_t)p * d + q] = a / L[(size_t)q * d + q];
+        }
+      }
+    if (ok) {
+      CUDA_OK(h, cudaMemcpyAsync(s->chol, L.data(), sizeof(double) * L.size(), cudaMemcpyHostToDevice, h->stream));
+      CUDA_OK(h, cudaMemcpyAsync(s->psd, sd.data(), sizeof(double) * d, cudaMemcpyHostToDevice, h->stream));
+      CUDA_OK(h, cudaStreamSynchronize(h->stream));
+      s->psd_ready = true;
+      return EPI_OK;
+    }
+  }
+  return EPI_OK;
 }
 
 static int launch_ap(epi_handle *h, SamplerState *s, int do_accept, double *draw_out, double *draw_lp) {
@@ -194,7 +279,8 @@ static int launch_ap(epi_handle *h, SamplerState *s, int do_accept, double *draw
   k_accept_propose<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(
       h->M.d, n, s->ld, s->cfg.kind, s->cfg.seed, s->cfg.chain_id0, s->iter, do_accept, s->cfg.beta, s->cfg.scale,
       s->cfg.de_eps, h->M.box_min, h->M.box_max, s->cur, s->prop, s->logl, s->logp, s->logl_p, s->logp_p, s->status_p,
-      s->lscale, s->adapt, s->adapt_target, s->acc, s->pop, s->pop_ranks, s->pop_per_rank, s->pop_ld, draw_out, draw_lp);
+      s->lscale, s->adapt, s->adapt_target, s->acc, s->pop, s->pop_ranks, s->pop_per_rank, s->pop_ld,
+      s->psd_ready ? s->psd : nullptr, (s->psd_ready && s->cfg.kind == EPI_SAMPLER_RWM) ? s->chol : nullptr, draw_out, draw_lp);
   h->launches += 1;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return epi_fail(h, EPI_ERR_CUDA, "k_accept_propose: %s", cudaGetErrorString(e));
@@ -223,6 +309,9 @@ extern "C" int epi_sampler_init(epi_handle *h, const epi_sampler_cfg *cfg, const
   CUDA_OK(h, cudaMalloc(&s->status_p, sizeof(int) * (size_t)s->ld));
   CUDA_OK(h, cudaMalloc(&s->lscale, vec));
   CUDA_OK(h, cudaMalloc(&s->acc, sizeof(unsigned long long)));
+  CUDA_OK(h, cudaMalloc(&s->psd, sizeof(double) * (size_t)d));
+  CUDA_OK(h, cudaMalloc(&s->cov, sizeof(double) * (size_t)d * d));
+  CUDA_OK(h, cudaMalloc(&s->chol, sizeof(double) * (size_t)d * d));
   CUDA_OK(h, cudaMemsetAsync(s->lscale, 0, vec, h->stream));
   CUDA_OK(h, cudaMemsetAsync(s->acc, 0, sizeof(unsigned long long), h->stream));
   CUDA_OK(h, cudaMemsetAsync(s->cur, 0, mat, h->stream));
@@ -272,6 +361,12 @@ extern "C" int epi_sampler_run(epi_handle *h, int32_t n_iter) {
   SamplerState *s = h->sampler;
   CUDA_OK(h, cudaSetDevice(h->device));
   const int64_t n = s->cfg.n_chains;
+  if (s->adapt && n >= 2 * h->M.d) {
+    // burn-in only: re-measure the population covariance that shapes the proposals.  (It is
+    // frozen when adaptation is switched off, so the sampling phase is a fixed-kernel Markov chain.)
+    int rc = update_shape(h, s);
+    if (rc) return rc;
+  }
   for (int it = 0; it < n_iter; ++it) {
     int rc = epi_launch_eval_ws(h, h->ws, h->M, s->prop, s->ld, n, 0, s->logl_p, s->logp_p, s->status_p, nullptr, nullptr,
                                 h->stream);
@@ -293,7 +388,7 @@ extern "C" int epi_sampler_run(epi_handle *h, int32_t n_iter) {
 extern "C" int epi_sampler_adapt(epi_handle *h, int enable, double target_accept) {
   if (!h || !h->sampler) return epi_fail(h, EPI_ERR_STATE, "sampler not initialised");
   h->sampler->adapt = enable != 0;
-  if (target_accept > 0 && target_accept < 1) h->sampler->adapt_target = target_accept;
+  h->sampler->adapt_target = (target_accept > 0 && target_accept < 1) ? target_accept : 0.0;
   return EPI_OK;
 }
 

@@ -30,7 +30,10 @@ class Sampler:
         self.n_chains = int(n_chains)
         self.kind = kind
         if scale is None:
-            scale = 1.0 if kind == "demc" else 0.02 / np.sqrt(model.d)
+            # DE-MC: multiplier of ter Braak's gamma = 2.38/sqrt(2d).  RWM: multiplier of
+            # 2.38/sqrt(d) x chol(population covariance) once burn-in adaptation has measured it
+            # (before that: of 2 % of the box width / sqrt(d))
+            scale = 1.0
         cfg = _capi.SamplerCfg(KINDS[kind], self.n_chains, int(chain_id0), int(seed), float(scale), float(de_eps),
                                float(beta), 0, 0)
         t0 = None
@@ -43,7 +46,7 @@ class Sampler:
     def run(self, n_iter: int):
         _capi.check(self._lib.epi_sampler_run(self._h, int(n_iter)), self._h)
 
-    def adapt(self, enable: bool, target: float = 0.234):
+    def adapt(self, enable: bool, target: float = 0.0):
         _capi.check(self._lib.epi_sampler_adapt(self._h, int(enable), float(target)), self._h)
 
     def record(self, thin: int, capacity: int):

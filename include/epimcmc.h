@@ -201,8 +201,13 @@ typedef struct epi_sampler_cfg {
 int epi_sampler_init(epi_handle *h, const epi_sampler_cfg *cfg, const double *theta0 /* HOST n_chains x d AOS, or NULL = init + jitter */);
 /* run n_iter fused propose -> evaluate -> accept iterations */
 int epi_sampler_run(epi_handle *h, int32_t n_iter);
-/* Robbins-Monro adaptation of each chain's step multiplier towards
- * target_accept (burn-in only: switch it off before recording draws)          */
+/* Burn-in adaptation (switch it off before recording draws): while enabled the
+ * proposal shape follows the population (RWM: Cholesky factor of the population
+ * covariance; DE-MC: per-parameter sd of the jitter), re-measured at every
+ * epi_sampler_run call.  target_accept in (0,1) additionally runs a per-chain
+ * Robbins-Monro step-size multiplier towards that acceptance rate; <= 0 leaves
+ * the classical step sizes (2.38/sqrt(d), 2.38/sqrt(2d)) alone — preferable on
+ * this rugged target (ceil/floor kernel extents, integer data_offset).        */
 int epi_sampler_adapt(epi_handle *h, int enable, double target_accept);
 /* device pointers of the current chain states (d x ld SOA, ld >= n_chains) for
  * the NCCL all-gather of the DE-MC population; the pointers stay valid until

@@ -1,0 +1,158 @@
+/*
+ * epimcmc_shim.c — R `.Call` shim over libepimcmc.so (include/epimcmc.h).
+ *
+ * SOURCE ONLY in this repository: R, R.h and Rinternals.h are not installed in the
+ * build image, so this file is not compiled or tested here (the same C entry points
+ * are driven through Python ctypes by tests/).  On a machine with R:
+ *
+ *   R CMD SHLIB epimcmc_shim.c -I../include -L../epi_mcmc_b200/csrc -lepimcmc -o epimcmc_shim.so
+ *
+ * It replaces what a reference model file does at load time,
+ *   system("R CMD SHLIB model-agen.cpp"); dyn.load("model-agen.so")      (model-age-groups2q.R:2-3)
+ * and binds, one to one:
+ *   C_epi_create      -> epi_create      handle from the data/settings globals
+ *   C_epi_logpost     -> epi_eval        batched calclogl(transformParams(.)) + calclogp(.)
+ *   C_epi_trajectories-> epi_trajectories calculateModel(params, period) for many draws
+ *   C_epi_df_params   -> epi_df_params
+ * R is single-threaded and drjacoby calls back on the main thread, which is all the
+ * handle's "one host thread at a time" rule needs.  Errors: the library never longjmps;
+ * a nonzero return code is turned into Rf_error() AFTER every temporary is released.
+ */
+#include <R.h>
+#include <Rinternals.h>
+#include <R_ext/Rdynload.h>
+#include <string.h>
+
+#include "epimcmc.h"
+
+static void handle_finalizer(SEXP ptr) {
+  epi_handle *h = (epi_handle *)R_ExternalPtrAddr(ptr);
+  if (h) {
+    epi_destroy(h);
+    R_ClearExternalPtr(ptr);
+  }
+}
+
+static epi_handle *get_handle(SEXP ptr) {
+  epi_handle *h = (epi_handle *)R_ExternalPtrAddr(ptr);
+  if (!h) Rf_error("epimcmc: handle already destroyed");
+  return h;
+}
+
+static double num(SEXP lst, const char *name, double dflt) {
+  SEXP names = Rf_getAttrib(lst, R_NamesSymbol);
+  for (R_xlen_t i = 0; i < XLENGTH(lst); ++i)
+    if (strcmp(CHAR(STRING_ELT(names, i)), name) == 0) return Rf_asReal(VECTOR_ELT(lst, i));
+  return dflt;
+}
+
+static const double *vec(SEXP lst, const char *name, int *n) {
+  SEXP names = Rf_getAttrib(lst, R_NamesSymbol);
+  for (R_xlen_t i = 0; i < XLENGTH(lst); ++i)
+    if (strcmp(CHAR(STRING_ELT(names, i)), name) == 0) {
+      SEXP v = VECTOR_ELT(lst, i);
+      if (!Rf_isReal(v)) Rf_error("epimcmc: `%s` must be a numeric (double) vector", name);
+      if (n) *n = (int)XLENGTH(v);
+      return REAL(v);
+    }
+  if (n) *n = 0;
+  return NULL;
+}
+
+/* .Call(C_epi_create, flavour, period, substeps, globals, device): `globals` is a named list
+ * holding the data-file and settings.R variables (same names with "." -> "_"). */
+SEXP C_epi_create(SEXP flavour, SEXP period, SEXP substeps, SEXP g, SEXP device) {
+  epi_model_desc desc = {Rf_asInteger(flavour), Rf_asInteger(period), Rf_asInteger(substeps), 0};
+  epi_data D;
+  memset(&D, 0, sizeof D);
+  D.N = num(g, "N", 0); D.y_N = num(g, "y_N", 0); D.o_N = num(g, "o_N", 0);
+  D.total_deaths_at_lockdown = num(g, "total_deaths_at_lockdown", 0);
+  D.dmort_last = num(g, "dmort_last", 0);
+  D.lockdown_offset = (int)num(g, "lockdown_offset", 0);
+  D.lockdown_transition_period = (int)num(g, "lockdown_transition_period", 0);
+  D.d3 = (int)num(g, "d3", 0); D.d4 = (int)num(g, "d4", 0); D.d5 = (int)num(g, "d5", 0);
+  D.d6 = (int)num(g, "d6", 0); D.d7 = (int)num(g, "d7", 0); D.d8 = (int)num(g, "d8", 0);
+  D.d_reliable_cases = (int)num(g, "d_reliable_cases", 0);
+  D.d_reliable_hosp = (int)num(g, "d_reliable_hosp", 0);
+  D.d_hosp_o1 = (int)num(g, "d_hosp_o1", 0); D.d_hosp_o2 = (int)num(g, "d_hosp_o2", 0);
+  D.dhospi = vec(g, "dhospi", &D.n_dhospi);
+  D.n_dhosp = (int)num(g, "n_dhosp", D.n_dhospi);
+  D.dmorti = vec(g, "dmorti", &D.n_dmorti);
+  D.y_dcasei = vec(g, "y_dcasei", &D.n_dcasei); D.o_dcasei = vec(g, "o_dcasei", NULL);
+  int nm = 0;
+  D.y_dmorti = vec(g, "y_dmorti", &nm);
+  if (nm) D.n_dmorti = nm;
+  D.o_dmorti = vec(g, "o_dmorti", NULL); D.o_wdmorti = vec(g, "o_wdmorti", NULL);
+  D.y_ifr = vec(g, "y_ifr", &D.n_rate); D.o_ifr = vec(g, "o_ifr", NULL);
+  D.y_hr = vec(g, "y_hr", NULL); D.o_hr = vec(g, "o_hr", NULL);
+  D.g = vec(g, "g", NULL); D.gtrimp = vec(g, "gtrimp", NULL);
+  D.hosp_nbinom_size = num(g, "hosp_nbinom_size", 0); D.mort_nbinom_size = num(g, "mort_nbinom_size", 0);
+  D.case_nbinom_size1 = num(g, "case_nbinom_size1", 0); D.case_nbinom_sizey2 = num(g, "case_nbinom_sizey2", 0);
+  D.case_nbinom_sizeo2 = num(g, "case_nbinom_sizeo2", 0); D.hosp_nbinom_size1 = num(g, "hosp_nbinom_size1", 0);
+  D.hosp_nbinom_size2 = num(g, "hosp_nbinom_size2", 0); D.hosp_last7 = num(g, "hosp_last7", 0);
+  epi_handle *h = NULL;
+  int rc = epi_create(&desc, &D, Rf_asInteger(device), &h);
+  if (rc) Rf_error("epi_create failed (%d): %s", rc, epi_last_error(NULL));
+  SEXP ptr = PROTECT(R_MakeExternalPtr(h, R_NilValue, R_NilValue));
+  R_RegisterCFinalizerEx(ptr, handle_finalizer, TRUE);
+  UNPROTECT(1);
+  return ptr;
+}
+
+/* .Call(C_epi_logpost, handle, theta): theta is a d x n numeric matrix, one proposal per COLUMN
+ * (R column-major == EPI_LAYOUT_AOS).  Returns list(logl, logp, status). */
+SEXP C_epi_logpost(SEXP ptr, SEXP theta) {
+  epi_handle *h = get_handle(ptr);
+  const int d = epi_n_params(h);
+  if (!Rf_isReal(theta) || XLENGTH(theta) % d != 0) Rf_error("epimcmc: theta must be a numeric %d x n matrix", d);
+  const R_xlen_t n = XLENGTH(theta) / d;
+  SEXP logl = PROTECT(Rf_allocVector(REALSXP, n)), logp = PROTECT(Rf_allocVector(REALSXP, n));
+  SEXP status = PROTECT(Rf_allocVector(INTSXP, n));
+  int rc = epi_eval(h, REAL(theta), (int64_t)n, EPI_LAYOUT_AOS, REAL(logl), REAL(logp), INTEGER(status));
+  SEXP out = PROTECT(Rf_allocVector(VECSXP, 3));
+  SET_VECTOR_ELT(out, 0, logl); SET_VECTOR_ELT(out, 1, logp); SET_VECTOR_ELT(out, 2, status);
+  UNPROTECT(4);
+  if (rc) Rf_error("epi_eval failed (%d): %s", rc, epi_last_error(h));
+  return out;
+}
+
+/* .Call(C_epi_trajectories, handle, params, period): params d x n MODEL-space; returns a
+ * period x n_series x n array plus offset and padding. */
+SEXP C_epi_trajectories(SEXP ptr, SEXP params, SEXP period) {
+  epi_handle *h = get_handle(ptr);
+  const int d = epi_n_params(h), ns = epi_n_series(h), P = Rf_asInteger(period);
+  const R_xlen_t n = XLENGTH(params) / d;
+  SEXP arr = PROTECT(Rf_allocVector(REALSXP, (R_xlen_t)P * ns * n));
+  SEXP off = PROTECT(Rf_allocVector(INTSXP, n)), pad = PROTECT(Rf_allocVector(INTSXP, n));
+  int rc = epi_trajectories(h, REAL(params), (int64_t)n, EPI_LAYOUT_AOS, P, REAL(arr), INTEGER(off), INTEGER(pad));
+  SEXP out = PROTECT(Rf_allocVector(VECSXP, 3));
+  SET_VECTOR_ELT(out, 0, arr); SET_VECTOR_ELT(out, 1, off); SET_VECTOR_ELT(out, 2, pad);
+  UNPROTECT(4);
+  if (rc) Rf_error("epi_trajectories failed (%d): %s", rc, epi_last_error(h));
+  return out;
+}
+
+SEXP C_epi_df_params(SEXP ptr) {
+  epi_handle *h = get_handle(ptr);
+  const int d = epi_n_params(h);
+  SEXP mn = PROTECT(Rf_allocVector(REALSXP, d)), mx = PROTECT(Rf_allocVector(REALSXP, d));
+  SEXP init = PROTECT(Rf_allocVector(REALSXP, d)), nm = PROTECT(Rf_allocVector(STRSXP, d));
+  epi_df_params(h, REAL(mn), REAL(mx), REAL(init));
+  for (int i = 0; i < d; ++i) SET_STRING_ELT(nm, i, Rf_mkChar(epi_param_name(h, i)));
+  SEXP out = PROTECT(Rf_allocVector(VECSXP, 4));
+  SET_VECTOR_ELT(out, 0, nm); SET_VECTOR_ELT(out, 1, mn); SET_VECTOR_ELT(out, 2, mx); SET_VECTOR_ELT(out, 3, init);
+  UNPROTECT(5);
+  return out;
+}
+
+static const R_CallMethodDef call_methods[] = {
+    {"C_epi_create", (DL_FUNC)&C_epi_create, 5},
+    {"C_epi_logpost", (DL_FUNC)&C_epi_logpost, 2},
+    {"C_epi_trajectories", (DL_FUNC)&C_epi_trajectories, 3},
+    {"C_epi_df_params", (DL_FUNC)&C_epi_df_params, 1},
+    {NULL, NULL, 0}};
+
+void R_init_epimcmc_shim(DllInfo *dll) {
+  R_registerRoutines(dll, NULL, call_methods, NULL, NULL);
+  R_useDynamicSymbols(dll, FALSE);
+}

@@ -73,25 +73,79 @@ def test_state_is_consistent_and_inside_the_box():
     M.close()
 
 
-def test_rwm_and_demc_agree_on_the_posterior():
-    """two different samplers, one target (simple model, synthetic S120): pooled posterior means
-    agree within Monte-Carlo error, and the truth used to generate the data is covered."""
+def _start(mn, mx, init, n, seed):
+    """start inside the main mode: the target is rugged (HL, DL enter through ceil/floor kernel
+    extents, the threshold through an integer data_offset) and has shallow local modes that trap
+    ~10 % of widely dispersed starts for any local sampler — which is what the reference's
+    20-rung parallel tempering is for (fitMCMC-drj.R:53)"""
+    rng = np.random.default_rng(seed)
+    return np.clip(init + 0.02 * (mx - mn) * (rng.uniform(size=(n, len(init))) - 0.5), mn, mx)
+
+
+def _cpu_reference_sampler(oracle, ds, m, n_chains, burnin, samples, thin, seed):
+    """An independent CPU sampler on the ORACLE density: population-adaptive Metropolis in numpy
+    (proposal covariance = 2.38^2/d x pooled covariance, refreshed during burn-in only)."""
+    rng = np.random.default_rng(seed)
+    mn, mx, init = oracle.df_params(ds["flavour"], ds, ds["period"])
+    d = len(init)
+    x = _start(mn, mx, init, n_chains, seed + 100)
+
+    def post(th):
+        r = oracle.evaluate(ds["flavour"], ds, th, ds["period"], m, n_threads=16)
+        lp = r["logl"] + r["logp"]
+        return np.where(np.isfinite(lp), lp, -np.inf)
+
+    def reflect(y):
+        w = mx - mn
+        z = np.mod(y - mn, 2 * w)
+        z = np.where(z > w, 2 * w - z, z)
+        return mn + z
+
+    lp = post(x)
+    L = np.diag(0.02 * (mx - mn) / np.sqrt(d))
+    keep = []
+    for it in range(burnin + samples):
+        if it < burnin and it % 50 == 0 and it > 0:
+            C = np.cov(x.T) + 1e-12 * np.diag((mx - mn) ** 2)
+            L = np.linalg.cholesky(C) * 2.38 / np.sqrt(d)
+        y = reflect(x + rng.standard_normal((n_chains, d)) @ L.T)
+        lq = post(y)
+        acc = np.log(rng.uniform(size=n_chains)) < lq - lp
+        x[acc], lp[acc] = y[acc], lq[acc]
+        if it >= burnin and (it - burnin) % thin == 0:
+            keep.append(x.copy())
+    return np.array(keep).reshape(-1, d)
+
+
+def test_samplers_agree_on_the_posterior(oracle):
+    """One target (simple model, synthetic S120), three samplers: GPU DE-MC, GPU adaptive-covariance
+    RWM, and an independent CPU Metropolis sampler on the oracle density.  Posterior means and
+    10/90 % quantiles agree within Monte-Carlo error (the north_star's statistical parity check;
+    the reference's own sampler, drjacoby, is not installed)."""
+    from epi_mcmc_b200.model import load_dataset
     from epi_mcmc_b200.sampler import run_mcmc
-    M = _model("S120", 2)
-    r1 = run_mcmc(M, burnin=600, samples=300, chains=1024, kind="demc", seed=1, thin=3)
-    r2 = run_mcmc(M, burnin=1500, samples=600, chains=1024, kind="rwm", seed=2, thin=6)
+    ds = load_dataset("S120")
+    M = _model("S120", 1)
+    mn, mx, init = M.df_params["min"], M.df_params["max"], M.df_params["init"]
+    r1 = run_mcmc(M, burnin=8000, samples=4000, chains=2048, kind="demc", seed=1, thin=40)
+    r2 = run_mcmc(M, burnin=8000, samples=4000, chains=2048, kind="rwm", seed=2, thin=40)
     d1 = r1["draws"].reshape(-1, M.d)
     d2 = r2["draws"].reshape(-1, M.d)
-    sd = d1.std(axis=0)
-    z = np.abs(d1.mean(axis=0) - d2.mean(axis=0)) / sd
-    assert (z < 0.35).all(), z
-    q1, q2 = np.quantile(d1, [0.1, 0.9], axis=0), np.quantile(d2, [0.1, 0.9], axis=0)
-    assert (np.abs(q1 - q2) / sd < 0.5).all()
+    d3 = _cpu_reference_sampler(oracle, ds, 1, n_chains=256, burnin=4000, samples=3000, thin=10, seed=3)
+    sd = d3.std(axis=0)
+    print("means", d1.mean(0), d2.mean(0), d3.mean(0), "sds", d1.std(0), d2.std(0), sd)
+    for name, dd in (("demc", d1), ("rwm", d2)):
+        z = np.abs(dd.mean(axis=0) - d3.mean(axis=0)) / sd
+        assert (z < 0.25).all(), (name, z)
+        qa, qb = np.quantile(dd, [0.1, 0.9], axis=0), np.quantile(d3, [0.1, 0.9], axis=0)
+        assert (np.abs(qa - qb) / sd < 0.3).all(), (name, np.abs(qa - qb) / sd)
+        assert (np.abs(dd.std(axis=0) / sd - 1) < 0.35).all(), (name, dd.std(axis=0) / sd)
     truth = M.df_params["init"]
     lo, hi = np.quantile(d1, [0.001, 0.999], axis=0)
-    assert ((truth >= lo) & (truth <= hi))[:7].all()
-    assert 0.05 < r1["diagnostics"]["accept_rate"] < 0.8
-    assert min(r1["diagnostics"]["ess"].values()) > 100
+    assert ((truth >= lo) & (truth <= hi)).all()
+    print("accept", r1["diagnostics"]["accept_rate"], r2["diagnostics"]["accept_rate"], "ess", r1["diagnostics"]["ess"], r2["diagnostics"]["ess"])
+    assert 0.03 < r1["diagnostics"]["accept_rate"] < 0.8 and 0.03 < r2["diagnostics"]["accept_rate"] < 0.8
+    assert min(r1["diagnostics"]["ess"].values()) > 200
     M.close()
 
 
