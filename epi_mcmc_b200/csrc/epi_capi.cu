@@ -11,6 +11,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -317,6 +318,10 @@ extern "C" int epi_create(const epi_model_desc *desc, const epi_data *data, int 
   do {
     if (cudaSetDevice(device) != cudaSuccess) { rc = epi_fail(h, EPI_ERR_CUDA, "cudaSetDevice(%d) failed", device); break; }
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { rc = epi_fail(h, EPI_ERR_CUDA, "stream"); break; }
+    if (cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking) != cudaSuccess) { rc = epi_fail(h, EPI_ERR_CUDA, "stream"); break; }
+    cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
+    { const char *env = getenv("EPI_SPLIT_STREAMS"); h->split = (env && env[0] == '1'); }
     for (auto &ev : h->ev) cudaEventCreate(&ev);
     rc = fill_model(h, *desc, *data);
   } while (0);
@@ -347,6 +352,9 @@ extern "C" void epi_destroy(epi_handle *h) {
   for (void *p : h->owned) cudaFree(p);
   for (auto &ev : h->ev) if (ev) cudaEventDestroy(ev);
   if (h->stream) cudaStreamDestroy(h->stream);
+  if (h->stream2) cudaStreamDestroy(h->stream2);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
   delete h;
 }
 
@@ -397,19 +405,55 @@ int epi_ensure_workspace(epi_handle *h, Workspace &w, const DevModel &M, int64_t
   return EPI_OK;
 }
 
+static EvalArgs make_args(epi_handle *h, Workspace &w, const DevModel &M, const double *d_theta, int64_t ld, int64_t n,
+                          int64_t first, int model_space, double *d_logl, double *d_logp, int *d_status,
+                          double *d_terms, double *d_series, cudaStream_t stream) {
+  // the chain range [first, first + n) of a batch; `first` is a multiple of the 32-chain tile
+  const int NG = M.flavour == EPI_FLAVOUR_AGE2Q ? 2 : 1, NK = M.flavour == EPI_FLAVOUR_AGE2Q ? 6 : 2;
+  const int NS = M.flavour == EPI_FLAVOUR_AGE2Q ? 8 : 3;
+  EvalArgs a;
+  a.M = &M; a.PT = h->PT; a.n_prior = h->n_prior;
+  a.theta = d_theta + first; a.ld = ld; a.n = n; a.model_space = model_space;
+  a.hist1 = w.hist1 + (first / kTile) * (int64_t)M.P1 * NG * kTile;
+  a.hist2 = w.hist2 + (first / kTile) * (int64_t)M.P * NG * kTile;
+  a.W = w.W + first * NK * EPI_MAX_TAPS;
+  a.pmeta = w.pmeta + first * NK;
+  a.offset = w.offset + first; a.pad = w.pad + first;
+  a.status = (d_status ? d_status : w.status) + first;
+  a.logl = d_logl ? d_logl + first : nullptr;
+  a.logp = d_logp ? d_logp + first : nullptr;
+  a.terms = d_terms ? d_terms + first * 8 : nullptr;
+  a.series_out = d_series ? d_series + first * NS * M.P : nullptr;
+  a.stream = stream;
+  a.ev = nullptr;
+  return a;
+}
+
 int epi_launch_eval_ws(epi_handle *h, Workspace &w, const DevModel &M, const double *d_theta, int64_t ld, int64_t n,
                        int model_space, double *d_logl, double *d_logp, int *d_status, double *d_terms,
                        double *d_series, cudaStream_t stream) {
-  EvalArgs a;
-  a.M = &M; a.PT = h->PT; a.n_prior = h->n_prior;
-  a.theta = d_theta; a.ld = ld; a.n = n; a.model_space = model_space;
-  a.hist1 = w.hist1; a.hist2 = w.hist2; a.W = w.W; a.pmeta = w.pmeta;
-  a.offset = w.offset; a.pad = w.pad; a.status = d_status ? d_status : w.status;
-  a.logl = d_logl; a.logp = d_logp; a.terms = d_terms; a.series_out = d_series;
-  a.stream = stream;
-  a.ev = h->timing ? h->ev : nullptr;
-  cudaError_t e = launch_eval(a);
-  h->launches += 4;
+  cudaError_t e;
+  // Large batches are cut in two halves that run on two streams.  Every phase of the pipeline is
+  // latency bound on its own (ncu, profiles/r1_v2: FP64 pipe 42-50 % busy in the ODE kernels,
+  // 26 % in the LDS/log-heavy score kernel), so letting the ODE kernel of one half share the SMs
+  // with the score/profile kernel of the other half fills issue slots neither can use alone.
+  const int64_t half = ((n / 2 + 127) / 128) * 128;
+  if (h->split && !h->timing && n >= 16384 && half < n) {
+    EvalArgs a0 = make_args(h, w, M, d_theta, ld, half, 0, model_space, d_logl, d_logp, d_status, d_terms, d_series, stream);
+    EvalArgs a1 = make_args(h, w, M, d_theta, ld, n - half, half, model_space, d_logl, d_logp, d_status, d_terms, d_series, h->stream2);
+    cudaEventRecord(h->ev_fork, stream);
+    cudaStreamWaitEvent(h->stream2, h->ev_fork, 0);
+    e = launch_eval(a0);
+    if (e == cudaSuccess) e = launch_eval(a1);
+    cudaEventRecord(h->ev_join, h->stream2);
+    cudaStreamWaitEvent(stream, h->ev_join, 0);
+    h->launches += 8;
+  } else {
+    EvalArgs a = make_args(h, w, M, d_theta, ld, n, 0, model_space, d_logl, d_logp, d_status, d_terms, d_series, stream);
+    a.ev = h->timing ? h->ev : nullptr;
+    e = launch_eval(a);
+    h->launches += 4;
+  }
   if (e != cudaSuccess) return epi_fail(h, EPI_ERR_CUDA, "kernel launch: %s", cudaGetErrorString(e));
   return EPI_OK;
 }

@@ -39,7 +39,9 @@ struct epi_handle {
   std::vector<void *> owned;            // device allocations freed at destroy
   epi::Workspace ws, ws_traj;
   epi::SamplerState *sampler = nullptr;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr, stream2 = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool split = false;  // EPI_SPLIT_STREAMS=1: run the two halves of a large batch on two streams (measured slower: 6.41 vs 6.03 ms)
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   bool timing = false;
   int64_t launches = 0;

@@ -68,19 +68,38 @@ __device__ __forceinline__ bool age_linear(int k) { return (0x10F >> k) & 1; }  
 // current schedule segment: value at tk and slope per curve (slope 0 = hold)
 struct Seg {
   double tk, b0, b1, b2, s0, s1, s2;  // age: betay/betao/betayo; simple: beta, Tinf, 1/Tinf cache
+  bool fast_ok;                       // beta(t) >= 0 on the whole segment (premise of the fast guard)
 };
 
 // y > N or y < 0 or NaN  =>  bit 63 of (bits(N) - bits(y)) | bits(y) is set (conservative: it is
 // also set for -0.0, which the slow path then treats exactly)
-__device__ __forceinline__ unsigned long long oob_bits(double y, unsigned long long nbits) {
-  const unsigned long long b = (unsigned long long)__double_as_longlong(y);
-  return (nbits - b) | b;
+// Fast-path out-of-bounds test on the integer pipe, per group of states (S first).  It may only
+// err on the safe side (a raised flag sends the step to the exact guarded path):
+//   * "x < 0": OR of the high words, sign bit (also raised by -0.0; the exact path sorts that out);
+//   * "x > N" for the non-S states: max of their high words >= high word of N, i.e. x within
+//     2^-20 of N or above (never true in practice: E, I, R stay far below N);
+//   * "S > N" needs no test at all: S starts at N-1 (older group: exactly N, and "S > N" is
+//     strict) and every stage derivative of S is -(beta >= 0)*(I >= 0)/N*(S >= 0) <= 0 whenever the
+//     guard let that stage through, so fma(c, k, S) <= S by monotone rounding.  The premise
+//     beta(t) >= 0 is checked once per schedule segment (Seg::fast_ok).
+// ncu/bench (profiles/r1_summary.md): the previous 64-bit form cost 30 ALU-pipe instructions per
+// stage and more than half of the ODE kernel time (2.07 ms -> 0.99 ms with the test removed).
+// (As unsigned integers the high words of negative doubles are >= 0x80000000 > hi(N), so one
+// unsigned max over the non-S states covers both "x < 0" and "x > N" for them; only S needs its
+// own sign test.)
+__device__ __forceinline__ unsigned oob_group5(double S, double a, double b, double c, double d, unsigned nhi_m1) {
+  const unsigned mx = max(max((unsigned)__double2hiint(a), (unsigned)__double2hiint(b)),
+                          max((unsigned)__double2hiint(c), (unsigned)__double2hiint(d)));
+  return (nhi_m1 - mx) | (unsigned)__double2hiint(S);  // bit 31 set <=> maybe out of bounds
+}
+__device__ __forceinline__ unsigned oob_group4(double S, double a, double b, double c, unsigned nhi_m1) {
+  const unsigned mx = max(max((unsigned)__double2hiint(a), (unsigned)__double2hiint(b)), (unsigned)__double2hiint(c));
+  return (nhi_m1 - mx) | (unsigned)__double2hiint(S);
 }
 
 template <int FL, bool GUARDED>
 __device__ __forceinline__ void rhs(const DevModel &M, const Seg &sg, double t, const double *y, double *dy,
-                                    double inv0, double inv1, unsigned long long nb0, unsigned long long nb1,
-                                    unsigned long long &flag) {
+                                    double inv0, double inv1, unsigned nb0, unsigned nb1, unsigned &flag) {
   const double dt = t - sg.tk;
   if constexpr (Traits<FL>::kAge) {
     const double Sy = y[0], E1y = y[1], E2y = y[2], Iy = y[3], Ry = y[4];
@@ -96,8 +115,7 @@ __device__ __forceinline__ void rhs(const DevModel &M, const Seg &sg, double t, 
         return;
       }
     } else {
-      flag |= oob_bits(Sy, nb0) | oob_bits(E1y, nb0) | oob_bits(E2y, nb0) | oob_bits(Iy, nb0) | oob_bits(Ry, nb0) |
-              oob_bits(So, nb1) | oob_bits(E1o, nb1) | oob_bits(E2o, nb1) | oob_bits(Io, nb1) | oob_bits(Ro, nb1);
+      flag |= oob_group5(Sy, E1y, E2y, Iy, Ry, nb0) | oob_group5(So, E1o, E2o, Io, Ro, nb1);
     }
     const double betay = fma(dt, sg.s0, sg.b0);
     const double betao = fma(dt, sg.s1, sg.b1);
@@ -120,7 +138,7 @@ __device__ __forceinline__ void rhs(const DevModel &M, const Seg &sg, double t, 
         return;
       }
     } else {
-      flag |= oob_bits(S, nb0) | oob_bits(E, nb0) | oob_bits(I, nb0) | oob_bits(R, nb0);
+      flag |= oob_group4(S, E, I, R, nb0);
     }
     const double beta = fma(dt, sg.s0, sg.b0);
     const double rT = (sg.s1 == 0.0) ? sg.b2 : 1.0 / fma(dt, sg.s1, sg.b1);  // b2 caches 1/Tinf on hold segments
@@ -138,12 +156,11 @@ __device__ __forceinline__ void rhs(const DevModel &M, const Seg &sg, double t, 
 
 template <int FL, bool GUARDED>
 __device__ __forceinline__ bool rk4_try(const DevModel &M, const Seg &sg, const double *y, double *ynew, double pa,
-                                        double pb, double inv0, double inv1, unsigned long long nb0,
-                                        unsigned long long nb1) {
+                                        double pb, double inv0, double inv1, unsigned nb0, unsigned nb1) {
   constexpr int NEQ = Traits<FL>::NEQ;
   const double hh = pb - pa, hh2 = 0.5 * hh, tm = pa + hh2;
   double k[NEQ], acc[NEQ], yt[NEQ];
-  unsigned long long flag = 0;
+  unsigned flag = 0;
   rhs<FL, GUARDED>(M, sg, pa, y, k, inv0, inv1, nb0, nb1, flag);
 #pragma unroll
   for (int i = 0; i < NEQ; ++i) { acc[i] = k[i]; yt[i] = fma(hh2, k[i], y[i]); }
@@ -157,17 +174,17 @@ __device__ __forceinline__ bool rk4_try(const DevModel &M, const Seg &sg, const 
   const double h6 = hh / 6.0;
 #pragma unroll
   for (int i = 0; i < NEQ; ++i) ynew[i] = fma(h6, acc[i] + k[i], y[i]);
-  return (long long)flag >= 0;  // no stage raised the maybe-out-of-bounds bit
+  return (int)flag >= 0;  // no stage raised the maybe-out-of-bounds bit
 }
 
 template <int FL>
 __device__ __forceinline__ void rk4_piece(const DevModel &M, const Seg &sg, double *y, double pa, double pb,
-                                          double inv0, double inv1, unsigned long long nb0, unsigned long long nb1) {
+                                          double inv0, double inv1, unsigned nb0, unsigned nb1) {
   constexpr int NEQ = Traits<FL>::NEQ;
   double yn[NEQ];
-  if (!rk4_try<FL, false>(M, sg, y, yn, pa, pb, inv0, inv1, nb0, nb1)) {
+  if (!sg.fast_ok || !rk4_try<FL, false>(M, sg, y, yn, pa, pb, inv0, inv1, nb0, nb1)) {
     // rare: redo the step with the reference's guard evaluated exactly in FP64
-    rk4_try<FL, true>(M, sg, y, yn, pa, pb, inv0, inv1, 0ull, 0ull);
+    rk4_try<FL, true>(M, sg, y, yn, pa, pb, inv0, inv1, 0u, 0u);
   }
 #pragma unroll
   for (int i = 0; i < NEQ; ++i) y[i] = yn[i];
@@ -225,6 +242,9 @@ __device__ __noinline__ Seg select_segment(const DevModel &M, const double *__re
       const double len = bp[k + 1] - bp[k];
       sg.tk = bp[k];
       sg.s0 = (ny - by) / len; sg.s1 = (no - bo) / len; sg.s2 = (nyo - byo) / len;
+      sg.fast_ok = by >= 0 && bo >= 0 && byo >= 0 && ny >= 0 && no >= 0 && nyo >= 0 && len > 0;
+    } else {
+      sg.fast_ok = by >= 0 && bo >= 0 && byo >= 0;
     }
   } else {
     auto T = [&](int i) { return th[(int64_t)i * ld]; };
@@ -239,6 +259,7 @@ __device__ __noinline__ Seg select_segment(const DevModel &M, const double *__re
       sg.s0 = (betat - beta0) / len; sg.s1 = (Tinft - Tinf0) / len;
       if (sg.s1 == 0.0) sg.b2 = 1.0 / Tinf0;
     }
+    sg.fast_ok = beta0 >= 0 && betat >= 0 && bp[1] > bp[0];
   }
   return sg;
 }
@@ -257,18 +278,18 @@ k_ode(const DevModel M, const double *__restrict__ theta, int64_t ld, int64_t n,
 
   double y[NEQ];
   double inv0, inv1;
-  unsigned long long nb0, nb1 = 0;
+  unsigned nb0, nb1 = 0;  // high words of the group sizes, minus one
   if constexpr (Traits<FL>::kAge) {
     y[0] = M.Ny - 1.0; y[1] = 1.0; y[2] = y[3] = y[4] = 0.0;
     y[5] = M.No; y[6] = y[7] = y[8] = y[9] = 0.0;
     inv0 = 1.0 / M.Ny; inv1 = 1.0 / M.No;
-    nb0 = (unsigned long long)__double_as_longlong(M.Ny);
-    nb1 = (unsigned long long)__double_as_longlong(M.No);
+    nb0 = (unsigned)__double2hiint(M.Ny) - 1u;
+    nb1 = (unsigned)__double2hiint(M.No) - 1u;
   } else {
     y[0] = M.N - 1.0; y[1] = 1.0; y[2] = y[3] = 0.0;
     if constexpr (FL == EPI_FLAVOUR_NE) { inv1 = th[8 * ld] * M.N; inv0 = 1.0 / inv1; }
     else { inv0 = 1.0 / M.N; inv1 = 0.0; }
-    nb0 = (unsigned long long)__double_as_longlong(M.N);
+    nb0 = (unsigned)__double2hiint(M.N) - 1u;
   }
 
   double bp[kMaxBp];
@@ -325,12 +346,13 @@ k_ode(const DevModel M, const double *__restrict__ theta, int64_t ld, int64_t n,
 // (ncu, profiles/r1_v2); the pair split doubles the warps and halves registers per thread.
 struct Seg2 {
   double tk, bA, sA, bB, sB;  // y lane: A = betay, B = 0;  o lane: A = betao, B = betayo
+  bool fast_ok;               // all three beta curves >= 0 on the segment (premise of the fast guard)
 };
 
 template <bool GUARDED>
 __device__ __forceinline__ void rhs_age2(double a1, double gamma, const Seg2 &sg, double t, const double *y, double *dy,
-                                         double invN, double Ngrp, unsigned long long nb, unsigned pairmask, int even_lane,
-                                         unsigned long long &flag) {
+                                         double invN, double Ngrp, unsigned nb, unsigned pairmask, int even_lane,
+                                         unsigned &flag) {
   const double S = y[0], E1 = y[1], E2 = y[2], I = y[3], R = y[4];
   if constexpr (GUARDED) {
     // bounds guard over all ten states of the chain, model-agen.cpp:109-124
@@ -351,7 +373,7 @@ __device__ __forceinline__ void rhs_age2(double a1, double gamma, const Seg2 &sg
     const double l2 = a1 * E1, rm = gamma * I;
     dy[0] = -inf; dy[1] = inf - l2; dy[2] = l2 - E2; dy[3] = E2 - rm; dy[4] = rm;
   } else {
-    flag |= oob_bits(S, nb) | oob_bits(E1, nb) | oob_bits(E2, nb) | oob_bits(I, nb) | oob_bits(R, nb);
+    flag |= oob_group5(S, E1, E2, I, R, nb);
     const double f_own = I * invN;
     const double fy = __shfl_sync(pairmask, f_own, even_lane);
     const double dt = t - sg.tk;
@@ -364,11 +386,11 @@ __device__ __forceinline__ void rhs_age2(double a1, double gamma, const Seg2 &sg
 
 template <bool GUARDED>
 __device__ __forceinline__ bool rk4_try_age2(double a1, double gamma, const Seg2 &sg, const double *y, double *ynew,
-                                             double pa, double pb, double invN, double Ngrp, unsigned long long nb,
+                                             double pa, double pb, double invN, double Ngrp, unsigned nb,
                                              unsigned pairmask, int even_lane) {
   const double hh = pb - pa, hh2 = 0.5 * hh, tm = pa + hh2;
   double k[5], acc[5], yt[5];
-  unsigned long long flag = 0;
+  unsigned flag = 0;
   rhs_age2<GUARDED>(a1, gamma, sg, pa, y, k, invN, Ngrp, nb, pairmask, even_lane, flag);
 #pragma unroll
   for (int i = 0; i < 5; ++i) { acc[i] = k[i]; yt[i] = fma(hh2, k[i], y[i]); }
@@ -383,15 +405,15 @@ __device__ __forceinline__ bool rk4_try_age2(double a1, double gamma, const Seg2
 #pragma unroll
   for (int i = 0; i < 5; ++i) ynew[i] = fma(h6, acc[i] + k[i], y[i]);
   if constexpr (GUARDED) return true;
-  const int own_bad = (long long)flag < 0;
+  const int own_bad = (int)flag < 0;
   return !(own_bad | __shfl_xor_sync(pairmask, own_bad, 1));
 }
 
 __device__ __forceinline__ void rk4_piece_age2(double a1, double gamma, const Seg2 &sg, double *y, double pa, double pb,
-                                               double invN, double Ngrp, unsigned long long nb, unsigned pairmask,
+                                               double invN, double Ngrp, unsigned nb, unsigned pairmask,
                                                int even_lane) {
   double yn[5];
-  if (!rk4_try_age2<false>(a1, gamma, sg, y, yn, pa, pb, invN, Ngrp, nb, pairmask, even_lane)) {
+  if (!sg.fast_ok || !rk4_try_age2<false>(a1, gamma, sg, y, yn, pa, pb, invN, Ngrp, nb, pairmask, even_lane)) {
     // rare: redo the step with the reference's guard evaluated exactly in FP64
     rk4_try_age2<true>(a1, gamma, sg, y, yn, pa, pb, invN, Ngrp, nb, pairmask, even_lane);
   }
@@ -421,6 +443,9 @@ __device__ __noinline__ Seg2 select_segment_age2(const double *__restrict__ th, 
     sg.tk = bp[k];
     sg.sA = is_o ? (no - bo) / len : (ny - by) / len;
     sg.sB = is_o ? (nyo - byo) / len : 0.0;
+    sg.fast_ok = by >= 0 && bo >= 0 && byo >= 0 && ny >= 0 && no >= 0 && nyo >= 0 && len > 0;
+  } else {
+    sg.fast_ok = by >= 0 && bo >= 0 && byo >= 0;
   }
   return sg;
 }
@@ -442,7 +467,7 @@ k_ode_age2(const DevModel M, const double *__restrict__ theta, int64_t ld, int64
 
   const double Ngrp = g ? M.No : M.Ny;
   const double invN = 1.0 / Ngrp;
-  const unsigned long long nb = (unsigned long long)__double_as_longlong(Ngrp);
+  const unsigned nb = (unsigned)__double2hiint(Ngrp) - 1u;
   double y[5];
   y[0] = g ? M.No : M.Ny - 1.0; y[1] = g ? 0.0 : 1.0; y[2] = y[3] = y[4] = 0.0;  // model-age-groups2q.R:157-158
 
