@@ -117,7 +117,12 @@ static int build_term_table(epi_handle *h, const std::vector<NbCall> &calls, con
       const int rel = c.r1 + k % lm;
       if (!is_count(x)) return epi_fail(h, EPI_ERR_ARG, "observed counts must be non-negative integers (got %g)", x);
       if (!(size > 0)) return epi_fail(h, EPI_ERR_ARG, "negative-binomial size must be > 0 (got %g)", size);
-      per[c.series][rel].push_back(Slot{x, x + size});
+      // terms of one (series, day) that share a size merge into one slot:
+      //   sum_k [x_k log(mu) - (x_k + size) log(size + mu)] = (sum x_k) log(mu) - (sum (x_k + size)) log(size + mu)
+      bool merged = false;
+      for (Slot &sl : per[c.series][rel])
+        if (sl.size == size) { sl.x += x; sl.xs += x + size; merged = true; break; }
+      if (!merged) per[c.series][rel].push_back(Slot{x, x + size, size, 0.0});
       cst[c.term] += lgammal((long double)x + size) - lgammal((long double)size) - lgammal((long double)x + 1.0L) +
                      (long double)size * logl((long double)size);
     }
@@ -125,7 +130,7 @@ static int build_term_table(epi_handle *h, const std::vector<NbCall> &calls, con
   for (int s = 0; s < n_series; ++s) {
     size_t K = 1;
     for (auto &v : per[s]) K = std::max(K, v.size());
-    std::vector<Slot> flat((size_t)n_obs[s] * K, Slot{0.0, 0.0});
+    std::vector<Slot> flat((size_t)n_obs[s] * K, Slot{0.0, 0.0, 0.0, 0.0});
     for (int r = 0; r < n_obs[s]; ++r)
       for (size_t k = 0; k < per[s][r].size(); ++k) flat[(size_t)r * K + k] = per[s][r][k];
     Slot *d = nullptr;

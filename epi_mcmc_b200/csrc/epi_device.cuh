@@ -21,8 +21,10 @@ constexpr int kNaFlagTerms = 8;
 // dnbinom() term that reads model day (dstart + rel).  (R recycling resolved on
 // the host, see build_term_table in epi_capi.cu.)
 struct Slot {
-  double x;   // observed count
-  double xs;  // x + size  (0 => empty slot)
+  double x;     // sum of the observed counts of the merged dnbinom() terms
+  double xs;    // sum of (x + size) over them  (0 => empty slot)
+  double size;  // their common size
+  double pad;   // 32-byte slots: two aligned 16-byte loads
 };
 
 struct DevModel {
@@ -68,11 +70,15 @@ __device__ __forceinline__ double warp_sum(double v) {
 //     FMA chains, no division inside the loop), convergence tested every four terms.
 // Agreement with the oracle is a few ulp (tests: < 1e-13 relative on every profile weight).
 // lga = lgamma(shape), hoisted by the caller because every CDF point of a profile shares it.
-__device__ inline double dev_pgamma(double q, double shape, double scale, double lga) {
+// METHOD: 0 = power series (x < a+1), 1 = continued fraction (x >= a+1).  The caller sorts the CDF
+// points of a chain by method so that a warp round never executes both (ncu, profiles/r1_v3: with
+// mixed rounds the two loops ran back to back for every round).
+template <int METHOD>
+__device__ __forceinline__ double dev_pgamma_m(double q, double shape, double scale, double lga) {
   const double x = q / scale, a = shape;
   if (!(x > 0.0)) return (x <= 0.0) ? 0.0 : x;  // NaN propagates
   const double pre = exp(-x + a * log(x) - lga);
-  if (x < a + 1.0) {
+  if constexpr (METHOD == 0) {
     double ap = a, del = 1.0 / a, sum = del;
     for (int n = 0; n < 25000; ++n) {
       const double r1 = x / (ap + 1.0), r2 = x / (ap + 2.0), r3 = x / (ap + 3.0), r4 = x / (ap + 4.0);
@@ -83,26 +89,27 @@ __device__ inline double dev_pgamma(double q, double shape, double scale, double
       if (!(fabs(d4) >= fabs(sum) * 1e-17)) break;
     }
     return sum * pre;
-  }
-  // Q(a,x) = pre / (b0 + a1/(b1 + a2/(b2 + ...))), b_i = x + 2i + 1 - a, a_i = -i (i - a)
-  double b = x + 1.0 - a;
-  double Am1 = 1.0, A = b, Bm1 = 0.0, B = 1.0;  // A_{-1}, A_0, B_{-1}, B_0
-  double hprev = 1.0 / b, h = hprev;
-  for (int i = 1; i < 100000; i += 4) {
+  } else {
+    // Q(a,x) = pre / (b0 + a1/(b1 + a2/(b2 + ...))), b_i = x + 2i + 1 - a, a_i = -i (i - a)
+    double b = x + 1.0 - a;
+    double Am1 = 1.0, A = b, Bm1 = 0.0, B = 1.0;  // A_{-1}, A_0, B_{-1}, B_0
+    double hprev = 1.0 / b, h = hprev;
+    for (int i = 1; i < 100000; i += 4) {
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const double fi = (double)(i + u);
-      const double an = -fi * (fi - a);
-      b += 2.0;
-      const double An = fma(b, A, an * Am1), Bn = fma(b, B, an * Bm1);
-      Am1 = A; A = An; Bm1 = B; B = Bn;
+      for (int u = 0; u < 4; ++u) {
+        const double fi = (double)(i + u);
+        const double an = -fi * (fi - a);
+        b += 2.0;
+        const double An = fma(b, A, an * Am1), Bn = fma(b, B, an * Bm1);
+        Am1 = A; A = An; Bm1 = B; B = Bn;
+      }
+      if (fabs(A) > 1e150) { A *= 1e-150; Am1 *= 1e-150; B *= 1e-150; Bm1 *= 1e-150; }
+      h = B / A;
+      if (!(fabs(h - hprev) > 1.2e-16 * fabs(h))) break;
+      hprev = h;
     }
-    if (fabs(A) > 1e150) { A *= 1e-150; Am1 *= 1e-150; B *= 1e-150; Bm1 *= 1e-150; }
-    h = B / A;
-    if (!(fabs(h - hprev) > 1.2e-16 * fabs(h))) break;
-    hprev = h;
+    return 1.0 - pre * h;
   }
-  return 1.0 - pre * h;
 }
 
 __device__ __forceinline__ double dev_pnorm(double q, double mean, double sd) {

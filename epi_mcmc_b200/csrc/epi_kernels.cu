@@ -589,27 +589,50 @@ __device__ __forceinline__ bool profile_extent(double mean, double sd, int &dmin
 template <int FL>
 __device__ __forceinline__ void build_profiles(const WarpSmem &w, const int *n_, int lane) {
   constexpr int NK = Traits<FL>::NK;
-  int off[NK + 1];
-  off[0] = 0;
-#pragma unroll
-  for (int q = 0; q < NK; ++q) off[q + 1] = off[q] + n_[q] + 1;
   if constexpr (Traits<FL>::kAge) {
     if (lane < NK) w.pp[lane * 4 + 3] = lgamma(w.pp[lane * 4 + 1]);  // once per profile
     __syncwarp();
-  }
-  for (int idx = lane; idx < off[NK]; idx += 32) {
-    int q = 0;
+    // split every profile's edge list at x = (shape + 1) * scale: points below go to the
+    // power-series list, the rest to the continued-fraction list
+    int ns[NK], offA[NK + 1], offB[NK + 1];
+    offA[0] = offB[0] = 0;
 #pragma unroll
-    for (int k = 1; k < NK; ++k) q += (idx >= off[k]);
-    int base = 0;
+    for (int q = 0; q < NK; ++q) {
+      const double xs = (w.pp[q * 4 + 1] + 1.0) * w.pp[q * 4 + 2] - w.pp[q * 4 + 0];  // first i with x0 + i >= (a+1)*scale
+      int k = (xs > 0.0) ? (int)ceil(xs) : 0;
+      ns[q] = min(max(k, 0), n_[q] + 1);
+      offA[q + 1] = offA[q] + ns[q];
+      offB[q + 1] = offB[q] + (n_[q] + 1 - ns[q]);
+    }
 #pragma unroll
-    for (int k = 1; k < NK; ++k) base = (idx >= off[k]) ? off[k] : base;
-    const int i = idx - base;
-    const double x = w.pp[q * 4 + 0] + (double)i;
-    double c;
-    if constexpr (Traits<FL>::kAge) c = dev_pgamma(x, w.pp[q * 4 + 1], w.pp[q * 4 + 2], w.pp[q * 4 + 3]);
-    else c = dev_pnorm(x, w.pp[q * 4 + 1], w.pp[q * 4 + 2]);
-    w.cdf[q * kCdfStride + i] = c;
+    for (int method = 0; method < 2; ++method) {
+      const int *off = method ? offB : offA;
+      for (int idx = lane; idx < off[NK]; idx += 32) {
+        int q = 0, base = 0;
+#pragma unroll
+        for (int k = 1; k < NK; ++k) { const bool ge = idx >= off[k]; q += ge; base = ge ? off[k] : base; }
+        int nsq = 0;
+#pragma unroll
+        for (int k = 0; k < NK; ++k) nsq = (k == q) ? ns[k] : nsq;
+        const int i = idx - base + (method ? nsq : 0);
+        const double x = w.pp[q * 4 + 0] + (double)i;
+        const double c = method ? dev_pgamma_m<1>(x, w.pp[q * 4 + 1], w.pp[q * 4 + 2], w.pp[q * 4 + 3])
+                                : dev_pgamma_m<0>(x, w.pp[q * 4 + 1], w.pp[q * 4 + 2], w.pp[q * 4 + 3]);
+        w.cdf[q * kCdfStride + i] = c;
+      }
+    }
+  } else {
+    int off[NK + 1];
+    off[0] = 0;
+#pragma unroll
+    for (int q = 0; q < NK; ++q) off[q + 1] = off[q] + n_[q] + 1;
+    for (int idx = lane; idx < off[NK]; idx += 32) {
+      int q = 0, base = 0;
+#pragma unroll
+      for (int k = 1; k < NK; ++k) { const bool ge = idx >= off[k]; q += ge; base = ge ? off[k] : base; }
+      const int i = idx - base;
+      w.cdf[q * kCdfStride + i] = dev_pnorm(w.pp[q * 4 + 0] + (double)i, w.pp[q * 4 + 1], w.pp[q * 4 + 2]);
+    }
   }
   __syncwarp();
 #pragma unroll
@@ -794,11 +817,12 @@ __device__ __forceinline__ double score_day(const DevModel &M, int s, int t, int
   double lmu = 0.0;
   bool have = false;
   for (int k = 0; k < K; ++k) {
-    const Slot z = sl[k];
-    if (z.xs == 0.0) continue;
+    const double2 a = __ldg(reinterpret_cast<const double2 *>(sl + k));      // (x, xs)
+    if (a.y == 0.0) continue;
+    const double size = __ldg(reinterpret_cast<const double *>(sl + k) + 2);
     if (!have) { lmu = log(mu); have = true; }
     // size*log(size/(size+mu)) + x*log(mu/(size+mu)) minus its data-only part size*log(size)
-    acc += z.x * lmu - z.xs * log((z.xs - z.x) + mu);
+    acc += a.x * lmu - a.y * log(size + mu);
   }
   return acc;
 }
@@ -853,7 +877,7 @@ __device__ __forceinline__ void stage_score(const DevModel &M, const ScoreSmem &
     lo[g] = min(lo[g], pm.x);
     hi[g] = max(hi[g], pm.x + pm.y - 1);
     for (int o = lane; o < pm.y; o += 32)
-      w.Wabs[(g * EPI_MAX_TAPS + pm.x + o) * 4 + (q % KG)] = Wg[((int64_t)chain * NK + q) * EPI_MAX_TAPS + o];
+      w.Wabs[(g * EPI_MAX_TAPS + pm.x + o) * 4 + (q % KG)] = __ldcs(Wg + ((int64_t)chain * NK + q) * EPI_MAX_TAPS + o);
   }
   const int stride = kPadMax + P;
   const double *in = hist2 + ((chain / kTile) * (int64_t)P * NG) * kTile + (chain % kTile);
@@ -861,7 +885,8 @@ __device__ __forceinline__ void stage_score(const DevModel &M, const ScoreSmem &
   for (int g = 0; g < NG; ++g) {
     const double s0 = Traits<FL>::kAge ? (g == 0 ? M.Ny - 1.0 : M.No) : M.N - 1.0;
     for (int j = lane; j < kPadMax; j += 32) w.S[g * stride + j] = s0;
-    for (int j = lane; j < P; j += 32) w.S[g * stride + kPadMax + j] = in[((int64_t)j * NG + g) * kTile];
+    // streamed once: keep it out of L1, which the shared term table and rate vectors live in
+    for (int j = lane; j < P; j += 32) w.S[g * stride + kPadMax + j] = __ldcs(in + ((int64_t)j * NG + g) * kTile);
   }
   __syncwarp();
 }
