@@ -85,33 +85,49 @@ def mean_taps(flavour, theta):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md)"""
+    """nvidia-smi clocks + throttle reasons DURING the timed regions (B200_PROFILING.md): one
+    nvidia-smi process streaming a sample every 50 ms"""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], False
+        self.index, self.rows, self.stop_flag, self.proc = index, [], False, None
 
     def run(self):
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-        while not self.stop_flag:
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                if self.stop_flag:
+                    break
+                self.rows.append([c.strip() for c in line.strip().split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        self.stop_flag = True
+        if self.proc is not None:
             try:
-                out = subprocess.check_output(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}",
-                                               "--format=csv,noheader,nounits"], timeout=5).decode().strip()
-                self.rows.append([c.strip() for c in out.split(",")])
+                self.proc.terminate()
             except Exception:
                 pass
-            time.sleep(0.2)
+        self.join(timeout=2)
 
     def summary(self):
-        if not self.rows:
+        rows = [r for r in self.rows if len(r) >= 7]
+        if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
-        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        num = lambda v: float(v) if v.replace(".", "", 1).isdigit() else None
+        sm = [num(r[0]) for r in rows if num(r[0]) is not None]
+        mx = [num(r[1]) for r in rows if num(r[1]) is not None]
+        pw = [num(r[2]) for r in rows if num(r[2]) is not None]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for k, n in enumerate(names) if any(r[3 + k].lower().startswith("active") for r in self.rows)]
+        reasons = [n for k, n in enumerate(names) if any(r[3 + k].lower().startswith("active") for r in rows)]
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.rows)}
+                "power_w_max": max(pw) if pw else None, "reasons": reasons, "samples": len(rows)}
 
 
 def cpu_baseline(ds, theta, substeps, budget_s=15.0):
@@ -208,6 +224,7 @@ def main():
     torch.cuda.synchronize(dev)
     clocks = ClockSampler(dev)
     clocks.start()
+    time.sleep(0.3)   # let nvidia-smi start streaming before the timed region
     comm.barrier()
     torch.cuda.synchronize(dev)
     launches0 = M.launch_count()
@@ -256,8 +273,7 @@ def main():
     e2e_s = comm.max_over_ranks(time.perf_counter() - t0)
     e2e_value = comm.world * n * args.steps / e2e_s
     assert np.allclose(ll_host.numpy(), logl.cpu().numpy(), rtol=0, atol=0, equal_nan=True)
-    clocks.stop_flag = True
-    clocks.join(timeout=2)
+    clocks.stop()
 
     # ---- roofline of the dominant kernel
     peak_tf = M.fp64_peak_tflops()
