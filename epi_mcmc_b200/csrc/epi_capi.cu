@@ -547,6 +547,45 @@ extern "C" int epi_trajectories(epi_handle *h, const double *theta, int64_t n, i
   return EPI_OK;
 }
 
+extern "C" int epi_quantiles(epi_handle *h, const double *theta, int64_t n, int layout, int32_t period, int32_t startoffset,
+                             int32_t series_a, int32_t series_b, const double *probs, int32_t n_probs, double *out) {
+  if (!h || !theta || !probs || !out || n < 1 || n_probs < 1 || period < 1) return epi_fail(h, EPI_ERR_ARG, "bad argument");
+  if (n > 8192) return epi_fail(h, EPI_ERR_ARG, "epi_quantiles supports at most 8192 draws (got %lld)", (long long)n);
+  const bool age = h->M.flavour == EPI_FLAVOUR_AGE2Q;
+  const int NS = age ? 8 : 3;
+  if (series_a < 0 || series_a >= NS || series_b >= NS) return epi_fail(h, EPI_ERR_ARG, "series index out of range");
+  const int simperiod = 3 * period;  // libMCMC.R:153
+  if (simperiod < (age ? 60 : 2) || simperiod > 4096) return epi_fail(h, EPI_ERR_ARG, "period out of range");
+  CUDA_OK(h, cudaSetDevice(h->device));
+  DevModel M = h->M;
+  M.P = simperiod;
+  if (!age) M.P1 = simperiod;
+  int rc = epi_ensure_workspace(h, h->ws_traj, M, n, true);
+  if (rc) return rc;
+  Workspace &w = h->ws_traj;
+  if ((rc = stage_theta(h, w, theta, n, layout, M.d))) return rc;
+  if ((rc = epi_launch_eval_ws(h, w, M, w.theta, w.ld, n, 1, nullptr, nullptr, nullptr, nullptr, w.series, h->stream))) return rc;
+  double *d_probs = nullptr, *d_out = nullptr;
+  CUDA_OK(h, cudaMalloc(&d_probs, sizeof(double) * (size_t)n_probs));
+  CUDA_OK(h, cudaMalloc(&d_out, sizeof(double) * (size_t)period * n_probs));
+  CUDA_OK(h, cudaMemcpyAsync(d_probs, probs, sizeof(double) * (size_t)n_probs, cudaMemcpyHostToDevice, h->stream));
+  // values before padding+1: the pre-filled state (model-age-groups2q.R:118-134)
+  auto prefill = [&](int sidx) -> double {
+    if (sidx < 0) return 0.0;
+    if (age) return sidx == 0 ? M.Ny - 1.0 : sidx == 1 ? M.No : 0.0;
+    return sidx == 0 ? M.N - 1.0 : 0.0;
+  };
+  cudaError_t e = launch_quantiles(w.series, w.offset, w.pad, n, NS, simperiod, period, startoffset, series_a, series_b,
+                                   prefill(series_a), prefill(series_b), d_probs, n_probs, d_out, h->stream);
+  h->launches += 1;
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, sizeof(double) * (size_t)period * n_probs, cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  cudaFree(d_probs);
+  cudaFree(d_out);
+  if (e != cudaSuccess) return epi_fail(h, EPI_ERR_CUDA, "epi_quantiles: %s", cudaGetErrorString(e));
+  return EPI_OK;
+}
+
 // --------------------------------------------------------------- measurement
 extern "C" int epi_set_timing(epi_handle *h, int enable) {
   if (!h) return EPI_ERR_ARG;

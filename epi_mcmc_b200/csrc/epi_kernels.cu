@@ -1167,6 +1167,62 @@ k_series(const DevModel M, const double *__restrict__ theta, int64_t ld, int64_t
   }
 }
 
+// ------------------------------------------------------------------ quantiles
+// quantileData (R/lib/libMCMC.R:151-172): one block per output day; the n draws' values of that
+// day are gathered (takeAndPad alignment by each draw's data_offset), bitonic-sorted in shared
+// memory with NA last, and the R type-7 quantiles are interpolated.
+__global__ void __launch_bounds__(256)
+k_quantiles(const double *__restrict__ series, const int *__restrict__ offset, const int *__restrict__ padv, int64_t n,
+            int NS, int simperiod, int startoffset, int sa, int sb, double prefill_a, double prefill_b,
+            const double *__restrict__ probs, int n_probs, int npow2, double *__restrict__ out) {
+  extern __shared__ double v[];
+  __shared__ int n_valid;
+  const int j = blockIdx.x + 1;  // day, 1-based
+  if (threadIdx.x == 0) n_valid = 0;
+  __syncthreads();
+  int mine = 0;
+  for (int i = threadIdx.x; i < npow2; i += blockDim.x) {
+    double x = INFINITY;  // NA sorts last
+    if (i < n) {
+      const int off = offset[i], pad = padv[i];
+      const long long sidx = (long long)off - startoffset - 1 + j;  // sim index read by takeAndPad
+      if (off != EPI_INVALID_DATA_OFFSET && sidx >= 1 && sidx <= simperiod && off - startoffset >= 1) {
+        const double *base = series + (int64_t)i * NS * simperiod;
+        const int k = (int)sidx - pad - 1;  // index into the stored days padding+1..padding+simperiod
+        double a = k >= 0 ? base[(int64_t)sa * simperiod + k] : prefill_a;
+        if (sb >= 0) a += k >= 0 ? base[(int64_t)sb * simperiod + k] : prefill_b;
+        if (a == a) { x = a; ++mine; }
+      }
+    }
+    v[i] = x;
+  }
+  atomicAdd(&n_valid, mine);
+  __syncthreads();
+  for (int k = 2; k <= npow2; k <<= 1)
+    for (int s = k >> 1; s > 0; s >>= 1) {
+      for (int i = threadIdx.x; i < npow2; i += blockDim.x) {
+        const int p = i ^ s;
+        if (p > i) {
+          const bool up = (i & k) == 0;
+          const double a = v[i], b = v[p];
+          if ((a > b) == up) { v[i] = b; v[p] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  const int m = n_valid;
+  for (int q = threadIdx.x; q < n_probs; q += blockDim.x) {
+    double r = NAN;
+    if (m > 0) {  // R quantile type 7
+      const double hq = (double)(m - 1) * probs[q];
+      const int lo = (int)floor(hq);
+      const int hi = min(lo + 1, m - 1);
+      r = v[lo] + (hq - (double)lo) * (v[hi] - v[lo]);
+    }
+    out[(int64_t)blockIdx.x * n_probs + q] = r;
+  }
+}
+
 // AoS (n x d, one proposal per row) -> SoA (d x ld) transpose, optionally applying
 // transformParams (used by the host-buffer entry points).
 __global__ void k_aos_to_soa(const double *__restrict__ aos, double *__restrict__ soa, int64_t n, int d, int64_t ld) {
@@ -1250,6 +1306,18 @@ cudaError_t launch_eval(const EvalArgs &a) {
 cudaError_t launch_aos_to_soa(const double *aos, double *soa, int64_t n, int d, int64_t ld, cudaStream_t s) {
   const int64_t tot = n * d;
   k_aos_to_soa<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(aos, soa, n, d, ld);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_quantiles(const double *series, const int *offset, const int *pad, int64_t n, int NS, int simperiod,
+                             int period, int startoffset, int sa, int sb, double prefill_a, double prefill_b,
+                             const double *d_probs, int n_probs, double *d_out, cudaStream_t s) {
+  int npow2 = 1;
+  while (npow2 < n) npow2 <<= 1;
+  const size_t smem = sizeof(double) * (size_t)npow2;
+  cudaFuncSetAttribute(k_quantiles, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  k_quantiles<<<period, 256, smem, s>>>(series, offset, pad, n, NS, simperiod, startoffset, sa, sb, prefill_a, prefill_b,
+                                        d_probs, n_probs, npow2, d_out);
   return cudaGetLastError();
 }
 

@@ -25,6 +25,9 @@ struct EvalArgs {
 
 cudaError_t launch_eval(const EvalArgs &a);
 cudaError_t launch_aos_to_soa(const double *aos, double *soa, int64_t n, int d, int64_t ld, cudaStream_t s);
+cudaError_t launch_quantiles(const double *series, const int *offset, const int *pad, int64_t n, int NS, int simperiod,
+                             int period, int startoffset, int sa, int sb, double prefill_a, double prefill_b,
+                             const double *d_probs, int n_probs, double *d_out, cudaStream_t s);
 cudaError_t launch_dfma(double *out, int blocks, int threads, int iters, cudaStream_t s);
 
 }  // namespace epi

@@ -172,6 +172,22 @@ class Model:
         st["offset"] = int(off[0])
         return st
 
+    def quantileData(self, sample, fun, startoffset: int, period: int, quantiles):
+        """libMCMC.R:151-172.  sample: (n, d) posterior draws in SAMPLER space (rows of the
+        posterior table; transformParams is applied like the reference does); fun: a series name
+        from `self.series_names` or a tuple of two names whose sum is wanted (the reference passes
+        closures such as `function(state, params) state$y.hospi + state$o.hospi`).  Returns a
+        (period, len(quantiles)) array; everything runs on the device."""
+        names = (fun,) if isinstance(fun, str) else tuple(fun)
+        idx = [self.series_names.index(nm) for nm in names] + [-1]
+        th = np.ascontiguousarray(self.transformParams(np.atleast_2d(np.asarray(sample, dtype=np.float64))))
+        probs = np.ascontiguousarray(np.asarray(quantiles, dtype=np.float64))
+        out = np.empty((int(period), len(probs)))
+        _capi.check(self._lib.epi_quantiles(self._h, _capi.as_dp(th), th.shape[0], _capi.LAYOUT_AOS, int(period),
+                                            int(startoffset), idx[0], idx[1], _capi.as_dp(probs), len(probs),
+                                            _capi.as_dp(out)), self._h)
+        return out
+
     def calcNominalState(self, state: dict) -> dict:
         """model-age-groups2q.R:367-376"""
         s = dict(state)

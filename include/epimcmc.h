@@ -185,6 +185,17 @@ int epi_n_series(const epi_handle *h);
 int epi_trajectories(epi_handle *h, const double *theta, int64_t n, int layout,
                      int32_t period, double *out, int32_t *offset, int32_t *padding);
 
+/* quantileData(sample, fun, startoffset, period, quantiles) of R/lib/libMCMC.R:151-172:
+ * calculateModel(params, 3*period) for each of the n posterior draws (theta in
+ * MODEL space), v = takeAndPad(fun(state), state$offset - startoffset, 3*period)
+ * (libMCMC.R:26-36), then per day j = 1..period the R type-7 quantiles of v[j]
+ * over the draws with na.rm = TRUE — all on the device (one sort per day).
+ * fun(state) = series_a (+ series_b when >= 0), indices into the epi_trajectories
+ * series order.  Draws with an invalid data_offset count as NA.  n <= 8192.
+ * out: HOST, period x n_probs, row-major (NaN where every draw is NA).          */
+int epi_quantiles(epi_handle *h, const double *theta, int64_t n, int layout, int32_t period, int32_t startoffset,
+                  int32_t series_a, int32_t series_b, const double *probs, int32_t n_probs, double *out);
+
 /* ---- on-device sampler (chain state never leaves the GPU) ------------------ */
 typedef struct epi_sampler_cfg {
   int32_t kind;        /* EPI_SAMPLER_* */

@@ -196,3 +196,37 @@ def test_trajectories_match_oracle(name, oracle):
     chk = np.array(gi["checksum"])
     assert (np.abs(s0[0].sum(axis=1) - chk) <= 1e-10 * np.abs(chk) + floor * s0.shape[2]).all()
     M.close()
+
+
+@pytest.mark.parametrize("name,fun", [("A300", ("y.hospi", "o.hospi")), ("A300", "y.deadi"), ("S120", "hospi")])
+def test_quantile_data_matches_reference_semantics(name, fun, oracle):
+    """quantileData (libMCMC.R:151-172) on the device against the oracle + numpy: per posterior draw
+    calculateModel(params, 3 * period), takeAndPad by the draw's data_offset, per-day R type-7
+    quantiles with na.rm."""
+    from epi_mcmc_b200.model import load_dataset
+    ds = load_dataset(name)
+    M = _model(name, 4)
+    mn, mx, init = M.df_params["min"], M.df_params["max"], M.df_params["init"]
+    rng = np.random.default_rng(5)
+    n, period, startoffset = 200, 100, 3
+    sample = np.clip(init + (rng.uniform(size=(n, M.d)) - 0.5) * 0.04 * (mx - mn), mn, mx)
+    probs = [0.05, 0.5, 0.95]
+    got = M.quantileData(sample, fun, startoffset, period, probs)
+    names = (fun,) if isinstance(fun, str) else fun
+    simperiod = 3 * period
+    data = np.full((simperiod, n), np.nan)
+    model_th = M.transformParams(sample)
+    for i in range(n):
+        ser, _, off, pad = oracle.trajectory(ds["flavour"], ds, model_th[i], ds["period"], 4, calc_period=simperiod)
+        if off == 10000:
+            continue
+        vec = np.zeros(pad + simperiod)                      # fun(state): full-length sim-indexed vector
+        for nm in names:
+            vec[pad:] += ser[M.series_names.index(nm)]
+        o = off - startoffset
+        take = vec[o - 1:simperiod]                          # takeAndPad(data, offset, l): data[offset:min(l, length)]
+        data[:len(take), i] = take
+    ref = np.nanquantile(data[:period], probs, axis=1).T     # numpy 'linear' == R type 7
+    scale = np.nanmax(np.abs(ref)) + 1e-300
+    assert np.abs(got - ref).max() <= 1e-9 * scale + 32 * 2.0 ** -52 * ds["N"]
+    M.close()
