@@ -61,7 +61,7 @@ class Data(C.Structure):
 class SamplerCfg(C.Structure):
     _fields_ = [("kind", C.c_int32), ("n_chains", C.c_int32), ("chain_id0", C.c_int64),
                 ("seed", C.c_uint64), ("scale", C.c_double), ("de_eps", C.c_double),
-                ("beta", C.c_double), ("reserved0", C.c_int32), ("reserved1", C.c_int32)]
+                ("beta", C.c_double), ("n_rungs", C.c_int32), ("reserved", C.c_int32), ("gti_pow", C.c_double)]
 
 
 _SERIES_FIELDS = ("dhospi", "dmorti", "y_dcasei", "o_dcasei", "y_dmorti", "o_dmorti", "o_wdmorti",
@@ -103,7 +103,7 @@ SYMBOLS = (
     "epi_param_name", "epi_df_params", "epi_eval", "epi_eval_device", "epi_eval_detail",
     "epi_n_series", "epi_trajectories", "epi_quantiles", "epi_sampler_init", "epi_sampler_run",
     "epi_sampler_adapt", "epi_sampler_state_device", "epi_sampler_set_population",
-    "epi_sampler_get", "epi_sampler_stats", "epi_sampler_record", "epi_sampler_draws",
+    "epi_sampler_get", "epi_sampler_stats", "epi_sampler_pt_stats", "epi_sampler_record", "epi_sampler_draws",
     "epi_fp64_peak", "epi_set_timing", "epi_last_kernel_ms", "epi_launch_count", "epi_philox_probe",
 )
 
@@ -143,6 +143,7 @@ def load():
     lib.epi_philox_probe.argtypes = [vp, C.c_uint64, C.c_uint32, C.c_uint32, i32, C.POINTER(C.c_uint32)]
     lib.epi_sampler_get.argtypes = [vp, _dp, _dp, _dp]
     lib.epi_sampler_stats.argtypes = [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]
+    lib.epi_sampler_pt_stats.argtypes = [vp, C.POINTER(i64), C.POINTER(i64)]
     lib.epi_sampler_record.argtypes = [vp, i32, i32]
     lib.epi_sampler_draws.argtypes = [vp, _dp, _dp, ip]
     lib.epi_fp64_peak.argtypes = [vp, _dp]

@@ -35,7 +35,10 @@ struct SamplerState {
   int *status_p = nullptr;
   double *lscale = nullptr;                  // per-chain log step multiplier (Robbins-Monro)
   double *psd = nullptr;                     // per-parameter sd of the population (proposal shape)
-  double *cov = nullptr, *chol = nullptr;    // d x d population covariance and its Cholesky factor (lower, row-major)
+  double *cov = nullptr, *chol = nullptr;    // per rung: d x d population covariance and its Cholesky factor (lower, row-major)
+  int n_rungs = 1, cpr = 0;                  // parallel tempering: rungs and chains per rung
+  double *beta_rung = nullptr;               // device, n_rungs
+  unsigned long long *swaps = nullptr;       // device: [0] proposed, [1] accepted
   bool psd_ready = false;
   unsigned long long *acc = nullptr;         // accepted moves, device scalar
   double *pop_own = nullptr;                 // own snapshot (1 rank)
@@ -86,12 +89,12 @@ __device__ inline double reflect(double x, double lo, double hi) {
   return lo + y;
 }
 
-enum { USE_ACCEPT = 0, USE_PARTNER = 1, USE_NORMAL = 16 };
+enum { USE_ACCEPT = 0, USE_PARTNER = 1, USE_SWAP = 2, USE_NORMAL = 16 };
 
 // Accept/reject iteration `iter` (when do_accept) and write the proposal of iteration iter+1.
 __global__ void __launch_bounds__(128)
 k_accept_propose(int d, int64_t n, int64_t ld, int kind, uint64_t seed, int64_t chain_id0, int64_t iter, int do_accept,
-                 double beta, double scale, double de_eps, const double *__restrict__ box_min,
+                 double beta0, const double *__restrict__ beta_rung, int cpr, double scale, double de_eps, const double *__restrict__ box_min,
                  const double *__restrict__ box_max, double *__restrict__ cur, double *__restrict__ prop,
                  double *__restrict__ logl, double *__restrict__ logp, const double *__restrict__ logl_p,
                  const double *__restrict__ logp_p, const int *__restrict__ status_p, double *__restrict__ lscale,
@@ -105,6 +108,8 @@ k_accept_propose(int d, int64_t n, int64_t ld, int kind, uint64_t seed, int64_t 
   const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
   uint32_t r[4];
   bool accepted = false;
+  const int rung = (beta_rung && live) ? (int)(i / cpr) : 0;
+  const double beta = beta_rung ? beta_rung[rung] : beta0;
   if (live && do_accept) {
     philox4x32_10((uint32_t)cid, (uint32_t)(cid >> 32), (uint32_t)iter, USE_ACCEPT, k0, k1, r);
     const double ll0 = logl[i], lp0 = logp[i], ll1 = logl_p[i], lp1 = logp_p[i];
@@ -142,12 +147,15 @@ k_accept_propose(int d, int64_t n, int64_t ld, int kind, uint64_t seed, int64_t 
   // keeps both the local moves and the occasional cell-crossing ones.
   const double umix = 0.05 + 0.95 * u01(r[2]);
   if (kind == EPI_SAMPLER_DEMC && pop) {
-    const uint32_t tot = (uint32_t)pop_ranks * (uint32_t)pop_per_rank;
+    // partners come from the chain's own temperature rung (cpr members per rank)
+    const uint32_t per_rank = beta_rung ? (uint32_t)cpr : (uint32_t)pop_per_rank;
+    const uint32_t first = beta_rung ? (uint32_t)rung * (uint32_t)cpr : 0u;
+    const uint32_t tot = (uint32_t)pop_ranks * per_rank;
     uint32_t a = (uint32_t)(((uint64_t)r[0] * tot) >> 32);
     uint32_t b = (uint32_t)(((uint64_t)r[1] * (tot - 1)) >> 32);
     if (b >= a) b += 1;  // two distinct members of the snapshot
-    z1 = pop + ((int64_t)(a / pop_per_rank) * d) * pop_ld + (a % pop_per_rank);
-    z2 = pop + ((int64_t)(b / pop_per_rank) * d) * pop_ld + (b % pop_per_rank);
+    z1 = pop + ((int64_t)(a / per_rank) * d) * pop_ld + first + (a % per_rank);
+    z2 = pop + ((int64_t)(b / per_rank) * d) * pop_ld + first + (b % per_rank);
     // ter Braak (2006): gamma = 2.38/sqrt(2d), every 10th proposal gamma = 1 (mode hopping)
     gam = ((it1 % 10u) == 0u) ? 1.0 : umix * step * 2.38 / sqrt(2.0 * d);
   }
@@ -170,7 +178,8 @@ k_accept_propose(int d, int64_t n, int64_t ld, int kind, uint64_t seed, int64_t 
       // RWM with the population covariance: x + step * 2.38/sqrt(d) * L z  (adaptive Metropolis shape,
       // measured during burn-in only)
       double a = 0.0;
-      for (int q = 0; q <= p; ++q) a = fma(chol[p * d + q], zn[q], a);
+      const double *L = chol + (size_t)rung * d * d;
+      for (int q = 0; q <= p; ++q) a = fma(L[p * d + q], zn[q], a);
       y = x + rw * a;
     } else {
       y = x + step * 0.02 * rsqrt((double)d) * (hi - lo) * zn[p];  // before any adaptation: 2 % of the box / sqrt(d)
@@ -180,8 +189,11 @@ k_accept_propose(int d, int64_t n, int64_t ld, int kind, uint64_t seed, int64_t 
 }
 
 // population covariance of the chains of this rank: one block per (p, q), q <= p
-__global__ void __launch_bounds__(256) k_cov(const double *__restrict__ cur, int64_t n, int64_t ld, int d,
-                                             double *__restrict__ cov) {
+__global__ void __launch_bounds__(256) k_cov(const double *__restrict__ cur_all, int64_t n, int64_t ld, int d,
+                                             double *__restrict__ cov_all) {
+  // blockIdx.y = temperature rung: chains [rung * n, (rung + 1) * n)
+  const double *cur = cur_all + (int64_t)blockIdx.y * n;
+  double *cov = cov_all + (size_t)blockIdx.y * d * d;
   __shared__ double sa[256], sb[256], sab[256];
   int p = 0, rem = blockIdx.x;
   while (rem > p) { rem -= p + 1; ++p; }
@@ -203,6 +215,44 @@ __global__ void __launch_bounds__(256) k_cov(const double *__restrict__ cur, int
     const double c = (sab[0] - sa[0] * sb[0] / (double)n) / (double)(n > 1 ? n - 1 : 1);
     cov[p * d + q] = c;
     cov[q * d + p] = c;
+  }
+}
+
+// Parallel tempering: Metropolis swap of the states of chain j on rung r and rung r+1 for the rung
+// pairs of the current parity (drjacoby's adjacent-rung swaps, R/MCMC/fitMCMC-drj.R:48-57).
+__global__ void __launch_bounds__(128)
+k_pt_swap(int d, int cpr, int n_rungs, int64_t ld, int parity, uint64_t seed, int64_t chain_id0, int64_t iter,
+          const double *__restrict__ beta_rung, double *__restrict__ cur, double *__restrict__ logl,
+          double *__restrict__ logp, unsigned long long *__restrict__ counters) {
+  const int n_pairs = (n_rungs - parity) / 2;
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  bool prop = false, acc = false;
+  if (t < (int64_t)n_pairs * cpr) {
+    const int r = parity + 2 * (int)(t / cpr), j = (int)(t % cpr);
+    const int64_t i0 = (int64_t)r * cpr + j, i1 = i0 + cpr;
+    const double l0 = logl[i0], l1 = logl[i1];
+    if (isfinite(l0) && isfinite(l1)) {
+      prop = true;
+      uint32_t w[4];
+      const uint64_t cid = (uint64_t)(chain_id0 + i0);
+      philox4x32_10((uint32_t)cid, (uint32_t)(cid >> 32), (uint32_t)iter, USE_SWAP, (uint32_t)seed, (uint32_t)(seed >> 32), w);
+      acc = log(u01(w[0])) < (beta_rung[r] - beta_rung[r + 1]) * (l1 - l0);
+      if (acc) {
+        for (int p = 0; p < d; ++p) {
+          const double a = cur[(int64_t)p * ld + i0];
+          cur[(int64_t)p * ld + i0] = cur[(int64_t)p * ld + i1];
+          cur[(int64_t)p * ld + i1] = a;
+        }
+        logl[i0] = l1; logl[i1] = l0;
+        const double p0 = logp[i0];
+        logp[i0] = logp[i1]; logp[i1] = p0;
+      }
+    }
+  }
+  const unsigned bp = __ballot_sync(0xffffffffu, prop), ba = __ballot_sync(0xffffffffu, acc);
+  if ((threadIdx.x & 31) == 0) {
+    if (bp) atomicAdd(counters, (unsigned long long)__popc(bp));
+    if (ba) atomicAdd(counters + 1, (unsigned long long)__popc(ba));
   }
 }
 
@@ -229,55 +279,60 @@ void epi_sampler_free(epi_handle *h) {
   SamplerState *s = h->sampler;
   if (!s) return;
   cudaFree(s->cur); cudaFree(s->prop); cudaFree(s->logl); cudaFree(s->logp); cudaFree(s->logl_p); cudaFree(s->logp_p);
-  cudaFree(s->status_p); cudaFree(s->lscale); cudaFree(s->psd); cudaFree(s->cov); cudaFree(s->chol); cudaFree(s->acc); cudaFree(s->pop_own); cudaFree(s->draws); cudaFree(s->draws_lp);
+  cudaFree(s->status_p); cudaFree(s->lscale); cudaFree(s->psd); cudaFree(s->cov); cudaFree(s->chol); cudaFree(s->beta_rung); cudaFree(s->swaps); cudaFree(s->acc); cudaFree(s->pop_own); cudaFree(s->draws); cudaFree(s->draws_lp);
   delete s;
   h->sampler = nullptr;
 }
 
-// population covariance on the device, Cholesky of the small d x d matrix on the host
+// population covariance on the device (per temperature rung), Cholesky of the small d x d
+// matrices on the host
 static int update_shape(epi_handle *h, SamplerState *s) {
-  const int d = h->M.d;
-  const int64_t n = s->cfg.n_chains;
-  k_cov<<<d * (d + 1) / 2, 256, 0, h->stream>>>(s->cur, n, s->ld, d, s->cov);
+  const int d = h->M.d, R = s->n_rungs;
+  const int64_t n = s->cpr;
+  k_cov<<<dim3(d * (d + 1) / 2, R), 256, 0, h->stream>>>(s->cur, n, s->ld, d, s->cov);
   h->launches += 1;
-  std::vector<double> C((size_t)d * d), L((size_t)d * d, 0.0), sd(d);
+  std::vector<double> C((size_t)R * d * d), L((size_t)R * d * d, 0.0), sd(d);
   CUDA_OK(h, cudaMemcpyAsync(C.data(), s->cov, sizeof(double) * C.size(), cudaMemcpyDeviceToHost, h->stream));
   CUDA_OK(h, cudaStreamSynchronize(h->stream));
-  for (int p = 0; p < d; ++p) {
-    const double v = C[(size_t)p * d + p];
-    if (!(v > 0) || !std::isfinite(v)) return EPI_OK;  // degenerate population: keep the previous shape
-    sd[p] = std::sqrt(v);
-  }
-  double ridge = 1e-12;
-  for (int attempt = 0; attempt < 8; ++attempt, ridge *= 100) {
-    bool ok = true;
-    std::fill(L.begin(), L.end(), 0.0);
-    for (int p = 0; p < d && ok; ++p)
-      for (int q = 0; q <= p; ++q) {
-        double a = C[(size_t)p * d + q] + (p == q ? ridge * C[(size_t)p * d + p] : 0.0);
-        for (int k = 0; k < q; ++k) a -= L[(size_t)p * d + k] * L[(size_t)q * d + k];
-        if (p == q) {
-          if (!(a > 0)) { ok = false; break; }
-          L[(size_t)p * d + p] = std::sqrt(a);
-        } else {
-          L[(size_t)p * d + q] = a / L[(size_t)q * d + q];
-        }
-      }
-    if (ok) {
-      CUDA_OK(h, cudaMemcpyAsync(s->chol, L.data(), sizeof(double) * L.size(), cudaMemcpyHostToDevice, h->stream));
-      CUDA_OK(h, cudaMemcpyAsync(s->psd, sd.data(), sizeof(double) * d, cudaMemcpyHostToDevice, h->stream));
-      CUDA_OK(h, cudaStreamSynchronize(h->stream));
-      s->psd_ready = true;
-      return EPI_OK;
+  for (int r = 0; r < R; ++r) {
+    const double *Cr = C.data() + (size_t)r * d * d;
+    double *Lr = L.data() + (size_t)r * d * d;
+    for (int p = 0; p < d; ++p) {
+      const double v = Cr[(size_t)p * d + p];
+      if (!(v > 0) || !std::isfinite(v)) return EPI_OK;  // degenerate population: keep the previous shape
+      if (r == R - 1) sd[p] = std::sqrt(v);              // jitter scale: the cold rung's spread
     }
+    bool ok = false;
+    double ridge = 1e-12;
+    for (int attempt = 0; attempt < 8 && !ok; ++attempt, ridge *= 100) {
+      ok = true;
+      std::fill(Lr, Lr + (size_t)d * d, 0.0);
+      for (int p = 0; p < d && ok; ++p)
+        for (int q = 0; q <= p; ++q) {
+          double a = Cr[(size_t)p * d + q] + (p == q ? ridge * Cr[(size_t)p * d + p] : 0.0);
+          for (int k = 0; k < q; ++k) a -= Lr[(size_t)p * d + k] * Lr[(size_t)q * d + k];
+          if (p == q) {
+            if (!(a > 0)) { ok = false; break; }
+            Lr[(size_t)p * d + p] = std::sqrt(a);
+          } else {
+            Lr[(size_t)p * d + q] = a / Lr[(size_t)q * d + q];
+          }
+        }
+    }
+    if (!ok) return EPI_OK;
   }
+  CUDA_OK(h, cudaMemcpyAsync(s->chol, L.data(), sizeof(double) * L.size(), cudaMemcpyHostToDevice, h->stream));
+  CUDA_OK(h, cudaMemcpyAsync(s->psd, sd.data(), sizeof(double) * d, cudaMemcpyHostToDevice, h->stream));
+  CUDA_OK(h, cudaStreamSynchronize(h->stream));
+  s->psd_ready = true;
   return EPI_OK;
 }
 
 static int launch_ap(epi_handle *h, SamplerState *s, int do_accept, double *draw_out, double *draw_lp) {
   const int64_t n = s->cfg.n_chains;
   k_accept_propose<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(
-      h->M.d, n, s->ld, s->cfg.kind, s->cfg.seed, s->cfg.chain_id0, s->iter, do_accept, s->cfg.beta, s->cfg.scale,
+      h->M.d, n, s->ld, s->cfg.kind, s->cfg.seed, s->cfg.chain_id0, s->iter, do_accept, s->cfg.beta,
+      s->n_rungs > 1 ? s->beta_rung : nullptr, s->cpr, s->cfg.scale,
       s->cfg.de_eps, h->M.box_min, h->M.box_max, s->cur, s->prop, s->logl, s->logp, s->logl_p, s->logp_p, s->status_p,
       s->lscale, s->adapt, s->adapt_target, s->acc, s->pop, s->pop_ranks, s->pop_per_rank, s->pop_ld,
       s->psd_ready ? s->psd : nullptr, (s->psd_ready && s->cfg.kind == EPI_SAMPLER_RWM) ? s->chol : nullptr, draw_out, draw_lp);
@@ -310,8 +365,22 @@ extern "C" int epi_sampler_init(epi_handle *h, const epi_sampler_cfg *cfg, const
   CUDA_OK(h, cudaMalloc(&s->lscale, vec));
   CUDA_OK(h, cudaMalloc(&s->acc, sizeof(unsigned long long)));
   CUDA_OK(h, cudaMalloc(&s->psd, sizeof(double) * (size_t)d));
-  CUDA_OK(h, cudaMalloc(&s->cov, sizeof(double) * (size_t)d * d));
-  CUDA_OK(h, cudaMalloc(&s->chol, sizeof(double) * (size_t)d * d));
+  s->n_rungs = cfg->n_rungs > 1 ? cfg->n_rungs : 1;
+  if (cfg->n_chains % s->n_rungs) return epi_fail(h, EPI_ERR_ARG, "n_chains must be a multiple of n_rungs");
+  s->cpr = cfg->n_chains / s->n_rungs;
+  CUDA_OK(h, cudaMalloc(&s->cov, sizeof(double) * (size_t)s->n_rungs * d * d));
+  CUDA_OK(h, cudaMalloc(&s->chol, sizeof(double) * (size_t)s->n_rungs * d * d));
+  CUDA_OK(h, cudaMalloc(&s->swaps, 2 * sizeof(unsigned long long)));
+  CUDA_OK(h, cudaMemsetAsync(s->swaps, 0, 2 * sizeof(unsigned long long), h->stream));
+  {
+    std::vector<double> br(s->n_rungs, 1.0);
+    const double pw = cfg->gti_pow > 0 ? cfg->gti_pow : 1.0;
+    for (int r = 0; r < s->n_rungs; ++r)
+      br[r] = s->n_rungs > 1 ? std::pow((double)r / (double)(s->n_rungs - 1), pw) : 1.0;
+    CUDA_OK(h, cudaMalloc(&s->beta_rung, sizeof(double) * (size_t)s->n_rungs));
+    CUDA_OK(h, cudaMemcpyAsync(s->beta_rung, br.data(), sizeof(double) * br.size(), cudaMemcpyHostToDevice, h->stream));
+    CUDA_OK(h, cudaStreamSynchronize(h->stream));
+  }
   CUDA_OK(h, cudaMemsetAsync(s->lscale, 0, vec, h->stream));
   CUDA_OK(h, cudaMemsetAsync(s->acc, 0, sizeof(unsigned long long), h->stream));
   CUDA_OK(h, cudaMemsetAsync(s->cur, 0, mat, h->stream));
@@ -347,7 +416,7 @@ extern "C" int epi_sampler_init(epi_handle *h, const epi_sampler_cfg *cfg, const
     CUDA_OK(h, cudaMalloc(&s->pop_own, mat));
     CUDA_OK(h, cudaMemcpyAsync(s->pop_own, s->cur, mat, cudaMemcpyDeviceToDevice, h->stream));
     s->pop = s->pop_own; s->pop_ranks = 1; s->pop_per_rank = (int)n; s->pop_ld = s->ld;
-    if (n < 3) return epi_fail(h, EPI_ERR_ARG, "DE-MC needs at least 3 chains");
+    if (s->cpr < 3) return epi_fail(h, EPI_ERR_ARG, "DE-MC needs at least 3 chains per rung");
   }
   s->iter = 0;
   rc = launch_ap(h, s, /*do_accept=*/0, nullptr, nullptr);  // proposal of iteration 1
@@ -361,7 +430,7 @@ extern "C" int epi_sampler_run(epi_handle *h, int32_t n_iter) {
   SamplerState *s = h->sampler;
   CUDA_OK(h, cudaSetDevice(h->device));
   const int64_t n = s->cfg.n_chains;
-  if (s->adapt && n >= 2 * h->M.d) {
+  if (s->adapt && s->cpr >= 2 * h->M.d) {
     // burn-in only: re-measure the population covariance that shapes the proposals.  (It is
     // frozen when adaptation is switched off, so the sampling phase is a fixed-kernel Markov chain.)
     int rc = update_shape(h, s);
@@ -380,8 +449,31 @@ extern "C" int epi_sampler_run(epi_handle *h, int32_t n_iter) {
       s->kept += 1;
     }
     if ((rc = launch_ap(h, s, 1, dout, dlp))) return rc;
+    if (s->n_rungs > 1) {
+      const int parity = (int)(s->iter & 1);
+      const int64_t pairs = (int64_t)((s->n_rungs - parity) / 2) * s->cpr;
+      if (pairs > 0) {
+        k_pt_swap<<<(unsigned)((pairs + 127) / 128), 128, 0, h->stream>>>(h->M.d, s->cpr, s->n_rungs, s->ld, parity,
+                                                                         s->cfg.seed, s->cfg.chain_id0, s->iter, s->beta_rung,
+                                                                         s->cur, s->logl, s->logp, s->swaps);
+        h->launches += 1;
+        // the proposal of the next iteration was drawn around the pre-swap state: redraw it
+        if ((rc = launch_ap(h, s, 0, nullptr, nullptr))) return rc;
+      }
+    }
   }
   CUDA_OK(h, cudaStreamSynchronize(h->stream));
+  return EPI_OK;
+}
+
+extern "C" int epi_sampler_pt_stats(epi_handle *h, int64_t *proposed, int64_t *accepted) {
+  if (!h || !h->sampler) return epi_fail(h, EPI_ERR_STATE, "sampler not initialised");
+  unsigned long long c[2] = {0, 0};
+  CUDA_OK(h, cudaSetDevice(h->device));
+  CUDA_OK(h, cudaMemcpyAsync(c, h->sampler->swaps, sizeof c, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_OK(h, cudaStreamSynchronize(h->stream));
+  if (proposed) *proposed = (int64_t)c[0];
+  if (accepted) *accepted = (int64_t)c[1];
   return EPI_OK;
 }
 

@@ -23,19 +23,25 @@ KINDS = {"rwm": _capi.SAMPLER_RWM, "demc": _capi.SAMPLER_DEMC}
 
 class Sampler:
     def __init__(self, model, n_chains: int, kind: str = "demc", seed: int = 42, scale: float | None = None,
-                 de_eps: float = 1e-4, beta: float = 1.0, chain_id0: int = 0, theta0=None):
+                 de_eps: float = 1e-4, beta: float = 1.0, chain_id0: int = 0, theta0=None, rungs: int = 1,
+                 GTI_pow: float = 1.0):
+        """n_chains is the total on this device; with `rungs` > 1 (parallel tempering, the
+        reference driver uses rungs = 20, GTI_pow = 1: fitMCMC-drj.R:53-56) chain i sits on rung
+        i // (n_chains // rungs) and the LAST rung is the cold one."""
         self.model = model
         self._lib = model._lib
         self._h = model._h
         self.n_chains = int(n_chains)
         self.kind = kind
+        self.rungs = max(1, int(rungs))
+        self.chains_per_rung = self.n_chains // self.rungs
         if scale is None:
             # DE-MC: multiplier of ter Braak's gamma = 2.38/sqrt(2d).  RWM: multiplier of
             # 2.38/sqrt(d) x chol(population covariance) once burn-in adaptation has measured it
             # (before that: of 2 % of the box width / sqrt(d))
             scale = 1.0
         cfg = _capi.SamplerCfg(KINDS[kind], self.n_chains, int(chain_id0), int(seed), float(scale), float(de_eps),
-                               float(beta), 0, 0)
+                               float(beta), self.rungs, 0, float(GTI_pow))
         t0 = None
         if theta0 is not None:
             t0 = np.ascontiguousarray(np.asarray(theta0, dtype=np.float64))
@@ -77,6 +83,18 @@ class Sampler:
         _capi.check(self._lib.epi_sampler_stats(self._h, C.byref(it), C.byref(acc), C.byref(ev)), self._h)
         n = max(1, it.value * self.n_chains)
         return dict(iterations=it.value, accepted=acc.value, evals=ev.value, accept_rate=acc.value / n)
+
+    def pt_stats(self) -> dict:
+        prop, acc = C.c_int64(), C.c_int64()
+        _capi.check(self._lib.epi_sampler_pt_stats(self._h, C.byref(prop), C.byref(acc)), self._h)
+        return dict(proposed=prop.value, accepted=acc.value, swap_rate=acc.value / max(1, prop.value))
+
+    def cold(self, a):
+        """slice of a per-chain array (last axis = chain, or axis 1 of draws[k, chain, d]) that
+        belongs to the cold rung"""
+        lo = (self.rungs - 1) * self.chains_per_rung
+        a = np.asarray(a)
+        return a[:, lo:lo + self.chains_per_rung] if a.ndim >= 2 else a[lo:lo + self.chains_per_rung]
 
     def draws(self):
         """(draws[k, chain, d], logpost[k, chain]) of the recorded thinned states"""
@@ -145,12 +163,14 @@ def pooled_ess(draws: np.ndarray, max_chains: int = 256) -> np.ndarray:
 
 # ------------------------------------------------------------------------ run_mcmc
 def run_mcmc(model, burnin: int = 1000, samples: int = 500, chains: int = 4096, kind: str = "demc", seed: int = 42,
-             thin: int = 1, exchange_every: int = 10, comm=None, **sampler_kw):
+             thin: int = 1, exchange_every: int = 10, comm=None, rungs: int = 1, GTI_pow: float = 1.0, **sampler_kw):
     """The call the reference driver makes (fitMCMC-drj.R:48-57) — burn-in then sampling —
     for a whole population of chains on the GPU.  Returns a dict with `output` (drjacoby
     schema, sampling phase), `diagnostics` (ess per parameter, acceptance) and raw `draws`."""
     rank, world = (comm.rank, comm.world) if comm is not None else (0, 1)
-    S = Sampler(model, chains, kind=kind, seed=seed, chain_id0=rank * chains, **sampler_kw)
+    # `chains` = chains per rung, like drjacoby's `chains` x `rungs` layout; draws are the cold rung's
+    S = Sampler(model, chains * max(1, rungs), kind=kind, seed=seed, chain_id0=rank * chains * max(1, rungs),
+                rungs=rungs, GTI_pow=GTI_pow, **sampler_kw)
     if comm is not None and kind == "demc":
         comm.attach(S)
 
@@ -170,6 +190,8 @@ def run_mcmc(model, burnin: int = 1000, samples: int = 500, chains: int = 4096, 
     S.record(thin, keep)
     advance(samples)
     draws, logpost = S.draws()
+    if rungs > 1 and len(draws):
+        draws, logpost = S.cold(draws), S.cold(logpost)
     st = S.stats()
     ess = pooled_ess(draws) if len(draws) >= 4 else np.zeros(model.d)
     return dict(draws=draws, logpost=logpost, sampler=S,

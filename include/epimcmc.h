@@ -206,7 +206,11 @@ typedef struct epi_sampler_cfg {
                           DE-MC: gamma = scale * 2.38/sqrt(2d) */
   double de_eps;       /* DE-MC jitter sd, relative to (max-min) */
   double beta;         /* likelihood tempering exponent (1 = posterior) */
-  int32_t reserved0, reserved1;
+  int32_t n_rungs;     /* parallel tempering: temperature rungs (<= 1: none).  n_chains must be a
+                          multiple; chain i sits on rung i / (n_chains / n_rungs); the LAST rung is the
+                          cold one (beta = 1), as in drjacoby (fitMCMC-drj.R:53,62)                     */
+  int32_t reserved;
+  double gti_pow;      /* beta_r = ((r) / (n_rungs - 1)) ^ gti_pow, r = 0 .. n_rungs-1 (GTI_pow, :56)   */
 } epi_sampler_cfg;
 
 int epi_sampler_init(epi_handle *h, const epi_sampler_cfg *cfg, const double *theta0 /* HOST n_chains x d AOS, or NULL = init + jitter */);
@@ -232,6 +236,8 @@ int epi_sampler_set_population(epi_handle *h, const double *d_pop, int32_t n_ran
                                int64_t ld_rank);
 /* copy the current state to HOST: theta n_chains x d AOS, logl, logp          */
 int epi_sampler_get(epi_handle *h, double *theta, double *logl, double *logp);
+/* parallel-tempering swap counters since init (adjacent-rung Metropolis swaps) */
+int epi_sampler_pt_stats(epi_handle *h, int64_t *proposed, int64_t *accepted);
 /* accumulated counters since init: iterations, accepted moves (summed over chains) */
 int epi_sampler_stats(epi_handle *h, int64_t *n_iter, int64_t *n_accept, int64_t *n_evals);
 /* record thinned draws on device: keep every `thin`-th state for up to

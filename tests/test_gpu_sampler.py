@@ -149,6 +149,48 @@ def test_samplers_agree_on_the_posterior(oracle):
     M.close()
 
 
+def test_parallel_tempering_prior_rung_and_cold_rung(oracle):
+    """Rungs as in the reference driver (beta_r = (r/(R-1))^GTI_pow, adjacent-rung swaps).  The
+    beta = 0 rung samples the PRIOR restricted to the df_params box, which is known in closed
+    form — an analytic check of propose/accept/reflect/swap; the cold rung reproduces the posterior
+    of the un-tempered sampler."""
+    from scipy import stats
+    from epi_mcmc_b200.sampler import Sampler, run_mcmc
+    M = _model("S120", 1)
+    mn, mx = M.df_params["min"], M.df_params["max"]
+    R, cpr = 6, 512
+    S = Sampler(M, R * cpr, kind="demc", seed=4, rungs=R, GTI_pow=2.0)
+    S.adapt(True)
+    for _ in range(300):
+        S.run(10)
+        S.refresh_population()
+    S.adapt(False)
+    S.record(20, 100)
+    for _ in range(200):
+        S.run(10)
+        S.refresh_population()
+    draws, _ = S.draws()
+    hot = draws[:, :cpr, :].reshape(-1, M.d)          # rung 0: beta = 0
+    # uniform components of the prior (R0, Rt, logHR, HL, lockdownmort): mean = mid-box, sd = width/sqrt(12)
+    for p in (0, 1, 4, 5, 7):
+        w = mx[p] - mn[p]
+        assert abs(hot[:, p].mean() - 0.5 * (mn[p] + mx[p])) < 0.03 * w, p
+        assert abs(hot[:, p].std() - w / np.sqrt(12)) < 0.03 * w, p
+    # DL ~ N(21, 4) truncated to its box (model-simple-ode-drj-cmp.R:174)
+    tn = stats.truncnorm((mn[6] - 21) / 4, (mx[6] - 21) / 4, loc=21, scale=4)
+    assert abs(hot[:, 6].mean() - tn.mean()) < 0.15 and abs(hot[:, 6].std() - tn.std()) < 0.15
+    # G0 = 3 + Tinf0/2 ~ N(5, 1) and G0 - Gt ~ N(0, 1.5) (:175-176): Tinf0 - Tinft ~ N(0, 3) before truncation
+    assert abs(hot[:, 2].mean() - 4.0) < 0.25
+    st = S.pt_stats()
+    assert st["proposed"] > 0 and 0.02 < st["swap_rate"] < 0.99
+    cold = S.cold(draws).reshape(-1, M.d)
+    plain = run_mcmc(M, burnin=5000, samples=2000, chains=1024, kind="demc", seed=5, thin=20)["draws"].reshape(-1, M.d)
+    z = np.abs(cold.mean(axis=0) - plain.mean(axis=0)) / plain.std(axis=0)
+    assert (z < 0.35).all(), z
+    assert (hot.std(axis=0) > 1.5 * cold.std(axis=0))[[0, 1, 4]].all()
+    M.close()
+
+
 def test_chain_csv_schema(tmp_path):
     from epi_mcmc_b200.sampler import run_mcmc, write_chain_csv
     import csv
