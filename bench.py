@@ -179,13 +179,30 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: age-structured model-age-groups2q, synthetic 300-day series, "
-                                   f"{args.chains} chains per GPU, RK4 m={args.substeps}",
+            "config": {"workload": workload_name(args, ds["period"]), "chains_per_gpu": args.chains,
+                       "params": len(init), "period": ds["period"], "substeps": args.substeps,
+                       "theta": "init +- 0.5% of the df_params box (every chain integrates both passes)",
                        "reference_arm": "CPU restatement oracle/epi_oracle.c (R + deSolve + drjacoby are not installed)"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
+
+
+def workload_name(args, period):
+    return (f"{args.workload}: age-structured model-age-groups2q, synthetic {period}-day series, "
+            f"{args.chains} chains per GPU, RK4 m={args.substeps} (BASELINE.json configs[2])")
+
+
+def emit(line: dict):
+    """the ONE JSON line of the contract, on the real stdout"""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+# Everything else any library prints to fd 1 (NCCL's version banner, for one) goes to stderr, so
+# that stdout carries exactly one JSON line.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
 
 
 def main():
@@ -287,8 +304,7 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": comm.world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": f"{args.workload}: age-structured model-age-groups2q, synthetic 300-day series, "
-                               f"{n} chains per GPU, RK4 m={args.substeps} (BASELINE.json configs[2])",
+        "config": {"workload": workload_name(args, ds["period"]),
                    "chains_per_gpu": n, "params": d, "period": ds["period"], "substeps": args.substeps,
                    "theta": "init +- 0.5% of the df_params box (every chain integrates both passes)",
                    "l2": "inputs larger than L2: the S-history/profile working set of one step is "
@@ -312,7 +328,7 @@ def main():
     if not args.no_sampler:
         line["sampler"] = sampler_leg(M, comm, args)
     if comm.rank == 0:
-        print(json.dumps(line))
+        emit(line)
     M.close()
     comm.close()
 
