@@ -129,6 +129,33 @@ __device__ __forceinline__ double dev_dlnorm_log(double x, double meanlog, doubl
   return -(kLnSqrt2Pi + 0.5 * y * y + log(x * sdlog));
 }
 
+// Table-driven natural logarithm for the negative-binomial terms (two logs per term, ~2,400 per
+// evaluation: 29 % of the score kernel's instructions with the library log, ncu profiles/r1_v5).
+// a = 2^e * m, m in [1,2); the top 7 mantissa bits pick c = 1 + (i + 1/2)/128 from a shared-memory
+// table of (1/c, log c); r = m/c - 1 has |r| <= 2^-8, so log1p(r) needs six terms.  Absolute error
+// ~2e-16 (the library's is 1 ulp); zero, denormal, negative, inf and NaN inputs take the library path.
+constexpr int kLogTabN = 128;
+__device__ __forceinline__ void fill_log_table(double2 *tab, int tid, int nthreads) {
+  for (int i = tid; i < kLogTabN; i += nthreads) {
+    const double c = 1.0 + ((double)i + 0.5) / (double)kLogTabN;
+    tab[i] = make_double2(1.0 / c, log(c));
+  }
+}
+__device__ __forceinline__ double tlog(double a, const double2 *__restrict__ tab) {
+  const int hi = __double2hiint(a);
+  if ((unsigned)(hi - 0x00100000) >= 0x7fe00000u) return log(a);
+  const int e = (hi >> 20) - 1023;
+  const double2 t = tab[(hi >> 13) & (kLogTabN - 1)];
+  const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(a));
+  const double r = fma(m, t.x, -1.0);
+  double p = fma(r, -1.0 / 6.0, 0.2);
+  p = fma(p, r, -0.25);
+  p = fma(p, r, 1.0 / 3.0);
+  p = fma(p, r, -0.5);
+  const double l = fma(r * r, p, r);
+  return fma((double)e, 0.693147180559945309417232, t.y + l);
+}
+
 // R pmax(floor, v): NA propagates (CUDA fmax would swallow the NaN)
 __device__ __forceinline__ double dev_pmax(double lo, double v) { return (v < lo) ? lo : v; }
 

@@ -807,7 +807,8 @@ __device__ __forceinline__ void window(int offset, int n, int T, int &dstart) {
 }
 
 // score the slots of scored series s that read model day t (value v)
-__device__ __forceinline__ double score_day(const DevModel &M, int s, int t, int dstart, double v) {
+__device__ __forceinline__ double score_day(const DevModel &M, const double2 *__restrict__ ltab, int s, int t, int dstart,
+                                            double v) {
   const int r = t - dstart;
   if (r < 0 || r >= M.n_obs[s]) return 0.0;
   const int K = M.K[s];
@@ -820,9 +821,9 @@ __device__ __forceinline__ double score_day(const DevModel &M, int s, int t, int
     const double2 a = __ldg(reinterpret_cast<const double2 *>(sl + k));      // (x, xs)
     if (a.y == 0.0) continue;
     const double size = __ldg(reinterpret_cast<const double *>(sl + k) + 2);
-    if (!have) { lmu = log(mu); have = true; }
+    if (!have) { lmu = tlog(mu, ltab); have = true; }
     // size*log(size/(size+mu)) + x*log(mu/(size+mu)) minus its data-only part size*log(size)
-    acc += a.x * lmu - a.y * log(size + mu);
+    acc += a.x * lmu - a.y * tlog(size + mu, ltab);
   }
   return acc;
 }
@@ -953,9 +954,12 @@ k_score(const DevModel M, const PriorTerm *__restrict__ PT, int n_prior, const d
   extern __shared__ double smem[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int64_t chain = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
+  double2 *ltab = reinterpret_cast<double2 *>(smem);  // block-shared log table, then the per-warp regions
+  fill_log_table(ltab, threadIdx.x, blockDim.x);
+  __syncthreads();
   if (chain >= n) return;
   const int P = M.P;
-  const ScoreSmem w = carve_score<FL>(smem + (size_t)wib * score_smem_doubles<FL>(P));
+  const ScoreSmem w = carve_score<FL>(smem + 2 * kLogTabN + (size_t)wib * score_smem_doubles<FL>(P));
   int st = status[chain];
 
   if (st & EPI_ST_UNSUPPORTED) {
@@ -1024,11 +1028,11 @@ k_score(const DevModel M, const PriorTerm *__restrict__ PT, int n_prior, const d
         if (j < P) {
           // scored series: y.casei, o.casei, hospi = y.hospi + o.hospi, y.deadi, o.deadi
           // (profile order: ycase, yhosp, ydied, ocase, ohosp, odied)
-          acc[0] += score_day(M, 0, t, dstart[0], val[0]);
-          acc[1] += score_day(M, 1, t, dstart[1], val[3]);
-          acc[2] += score_day(M, 2, t, dstart[2], val[1] + val[4]);
-          acc[3] += score_day(M, 3, t, dstart[3], val[2]);
-          acc[4] += score_day(M, 4, t, dstart[4], val[5]);
+          acc[0] += score_day(M, ltab, 0, t, dstart[0], val[0]);
+          acc[1] += score_day(M, ltab, 1, t, dstart[1], val[3]);
+          acc[2] += score_day(M, ltab, 2, t, dstart[2], val[1] + val[4]);
+          acc[3] += score_day(M, ltab, 3, t, dstart[3], val[2]);
+          acc[4] += score_day(M, ltab, 4, t, dstart[4], val[5]);
           if (t >= dstart[2] + M.d_hosp_o1 && t <= dstart[2] + M.d_hosp_o2) { ysum += val[1]; osum += val[4]; }  // :563-564
         }
       }
@@ -1055,7 +1059,7 @@ k_score(const DevModel M, const PriorTerm *__restrict__ PT, int n_prior, const d
           if (lane == 0) prev = carry[q];
           carry[q] = __shfl_sync(0xffffffffu, cum, 31);
           const double inc = cum - prev;  // prev is 0 for t = pad+1 (prefill)
-          if (j < P) acc[q] += score_day(M, q, t, dstart[q], (j >= 0) ? inc : 0.0);
+          if (j < P) acc[q] += score_day(M, ltab, q, t, dstart[q], (j >= 0) ? inc : 0.0);
         }
       }
     }
@@ -1257,7 +1261,7 @@ static cudaError_t launch_eval_fl(const EvalArgs &a) {
   const unsigned ode_blocks = (unsigned)((n + 31) / 32);
   const unsigned warp_blocks = (unsigned)((n + 3) / 4);
   const size_t smem_mid = (size_t)4 * warp_smem_doubles<FL>(M.P1) * sizeof(double);
-  const size_t smem_score = (size_t)4 * score_smem_doubles<FL>(M.P) * sizeof(double);
+  const size_t smem_score = ((size_t)4 * score_smem_doubles<FL>(M.P) + 2 * kLogTabN) * sizeof(double);
   static bool attr_done = false;
   if (!attr_done) {
     cudaFuncSetAttribute(k_mid<FL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
