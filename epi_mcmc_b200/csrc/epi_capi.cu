@@ -326,7 +326,8 @@ extern "C" int epi_create(const epi_model_desc *desc, const epi_data *data, int 
     if (cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking) != cudaSuccess) { rc = epi_fail(h, EPI_ERR_CUDA, "stream"); break; }
     cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
-    { const char *env = getenv("EPI_SPLIT_STREAMS"); h->split = (env && env[0] == '1'); }
+    cudaEventCreateWithFlags(&h->ev_stagger, cudaEventDisableTiming);
+    { const char *env = getenv("EPI_SPLIT_STREAMS"); h->split = (env && (env[0] == '1' || env[0] == '2')); h->split_mode = (env && env[0] == '2') ? 2 : 1; }
     for (auto &ev : h->ev) cudaEventCreate(&ev);
     rc = fill_model(h, *desc, *data);
   } while (0);
@@ -395,8 +396,9 @@ int epi_ensure_workspace(epi_handle *h, Workspace &w, const DevModel &M, int64_t
   const int64_t ld = tiles * kTile;
   CUDA_OK(h, cudaMalloc(&w.theta, sizeof(double) * (size_t)(M.d * ld)));
   CUDA_OK(h, cudaMalloc(&w.aos, sizeof(double) * (size_t)(M.d * ld)));
-  CUDA_OK(h, cudaMalloc(&w.hist1, sizeof(double) * (size_t)(tiles * P1 * NG * kTile)));
-  CUDA_OK(h, cudaMalloc(&w.hist2, sizeof(double) * (size_t)(tiles * P * NG * kTile)));
+  // S histories: [chain][group][pitch], pitch = days rounded up to even (16-byte aligned rows for the bulk copies)
+  CUDA_OK(h, cudaMalloc(&w.hist1, sizeof(double) * (size_t)(ld * NG * ((P1 + 1) & ~1))));
+  CUDA_OK(h, cudaMalloc(&w.hist2, sizeof(double) * (size_t)(ld * NG * ((P + 1) & ~1))));
   CUDA_OK(h, cudaMalloc(&w.W, sizeof(double) * (size_t)(ld * NK * EPI_MAX_TAPS)));
   CUDA_OK(h, cudaMalloc(&w.pmeta, sizeof(int2) * (size_t)(ld * NK)));
   CUDA_OK(h, cudaMalloc(&w.offset, sizeof(int) * (size_t)ld));
@@ -419,8 +421,8 @@ static EvalArgs make_args(epi_handle *h, Workspace &w, const DevModel &M, const 
   EvalArgs a;
   a.M = &M; a.PT = h->PT; a.n_prior = h->n_prior;
   a.theta = d_theta + first; a.ld = ld; a.n = n; a.model_space = model_space;
-  a.hist1 = w.hist1 + (first / kTile) * (int64_t)M.P1 * NG * kTile;
-  a.hist2 = w.hist2 + (first / kTile) * (int64_t)M.P * NG * kTile;
+  a.hist1 = w.hist1 + first * NG * (int64_t)((M.P1 + 1) & ~1);
+  a.hist2 = w.hist2 + first * NG * (int64_t)((M.P + 1) & ~1);
   a.W = w.W + first * NK * EPI_MAX_TAPS;
   a.pmeta = w.pmeta + first * NK;
   a.offset = w.offset + first; a.pad = w.pad + first;
@@ -448,7 +450,9 @@ int epi_launch_eval_ws(epi_handle *h, Workspace &w, const DevModel &M, const dou
     EvalArgs a1 = make_args(h, w, M, d_theta, ld, n - half, half, model_space, d_logl, d_logp, d_status, d_terms, d_series, h->stream2);
     cudaEventRecord(h->ev_fork, stream);
     cudaStreamWaitEvent(h->stream2, h->ev_fork, 0);
+    if (h->split_mode == 2) a0.ev_after_mid = h->ev_stagger;  // half B starts when half A has finished k_mid
     e = launch_eval(a0);
+    if (h->split_mode == 2) cudaStreamWaitEvent(h->stream2, h->ev_stagger, 0);
     if (e == cudaSuccess) e = launch_eval(a1);
     cudaEventRecord(h->ev_join, h->stream2);
     cudaStreamWaitEvent(stream, h->ev_join, 0);

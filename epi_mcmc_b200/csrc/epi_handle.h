@@ -40,7 +40,8 @@ struct epi_handle {
   epi::Workspace ws, ws_traj;
   epi::SamplerState *sampler = nullptr;
   cudaStream_t stream = nullptr, stream2 = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_stagger = nullptr;
+  int split_mode = 1;
   bool split = false;  // EPI_SPLIT_STREAMS=1: run the two halves of a large batch on two streams (measured slower: 6.41 vs 6.03 ms)
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   bool timing = false;

@@ -20,6 +20,42 @@
 
 namespace epi {
 
+// S histories in HBM: hist[(chain * NG + group) * pitch + day], pitch = days rounded up to even so
+// that every row is 16-byte aligned.  The thread-per-chain ODE writer scatters 8 B per (day, group)
+// (L2 merges the four days of a 32-byte sector before write-back); the warp-per-chain readers then
+// pull a whole row into shared memory with ONE 1-D bulk copy on the TMA unit (cp.async.bulk, SASS
+// UBLKCP) instead of ~600 strided 8-byte loads per chain (profiles/r1_v5: history staging was 8 %
+// of the score kernel's stall samples).
+__host__ __device__ constexpr int hist_pitch(int ndays) { return (ndays + 1) & ~1; }
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *mbar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(mbar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *mbar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(mbar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, unsigned bytes, uint64_t *mbar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(mbar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *mbar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(mbar)),
+      "r"(parity)
+      : "memory");
+}
+
 template <int FL>
 struct Traits {
   static constexpr bool kAge = (FL == EPI_FLAVOUR_AGE2Q);
@@ -274,7 +310,8 @@ k_ode(const DevModel M, const double *__restrict__ theta, int64_t ld, int64_t n,
   if (i >= n) return;
   const double *th = theta + i;
   const int ndays = PASS2 ? M.P : M.P1;
-  double *out = hist_out + ((i / kTile) * (int64_t)ndays * NG) * kTile + (i % kTile);
+  const int pitch = hist_pitch(ndays);
+  double *out = hist_out + (i * NG) * (int64_t)pitch;
 
   double y[NEQ];
   double inv0, inv1;
@@ -301,11 +338,11 @@ k_ode(const DevModel M, const double *__restrict__ theta, int64_t ld, int64_t n,
     if (off == EPI_INVALID_DATA_OFFSET) {
       // pass 2 skipped: the pass-1 rows are recycled into the P-length slices
       // (model-age-groups2q.R:216-223)
-      const double *in = hist1 + ((i / kTile) * (int64_t)M.P1 * NG) * kTile + (i % kTile);
+      const int pitch1 = hist_pitch(M.P1);
+      const double *in = hist1 + (i * NG) * (int64_t)pitch1;
       for (int d = 0; d < M.P; ++d)
 #pragma unroll
-        for (int g = 0; g < NG; ++g)
-          out[((int64_t)d * NG + g) * kTile] = in[((int64_t)(d % M.P1) * NG + g) * kTile];
+        for (int g = 0; g < NG; ++g) out[g * pitch + d] = in[g * pitch1 + d % M.P1];
       return;
     }
     t0 = padv[i] + 1;
@@ -316,7 +353,7 @@ k_ode(const DevModel M, const double *__restrict__ theta, int64_t ld, int64_t n,
   const int m = M.m;
   const double h = 1.0 / (double)m;
   out[0] = y[0];
-  if constexpr (NG == 2) out[kTile] = y[5];
+  if constexpr (NG == 2) out[pitch] = y[5];
   for (int d = 1; d < ndays; ++d) {
     const double tday = (double)(t0 + d - 1);
     for (int s = 0; s < m; ++s) {
@@ -333,8 +370,8 @@ k_ode(const DevModel M, const double *__restrict__ theta, int64_t ld, int64_t n,
       }
       rk4_piece<FL>(M, sg, y, pa, b, inv0, inv1, nb0, nb1);
     }
-    out[((int64_t)d * NG) * kTile] = y[0];
-    if constexpr (NG == 2) out[((int64_t)d * NG + 1) * kTile] = y[5];
+    out[d] = y[0];
+    if constexpr (NG == 2) out[pitch + d] = y[5];
   }
 }
 
@@ -463,7 +500,7 @@ k_ode_age2(const DevModel M, const double *__restrict__ theta, int64_t ld, int64
   const unsigned pairmask = 3u << even_lane;
   const double *th = theta + i;
   const int ndays = PASS2 ? M.P : M.P1;
-  double *out = hist_out + ((i / kTile) * (int64_t)ndays * 2 + g) * kTile + (i % kTile);
+  double *out = hist_out + (i * 2 + g) * (int64_t)hist_pitch(ndays);
 
   const double Ngrp = g ? M.No : M.Ny;
   const double invN = 1.0 / Ngrp;
@@ -479,8 +516,8 @@ k_ode_age2(const DevModel M, const double *__restrict__ theta, int64_t ld, int64
     const int off = offset[i];
     if (off == EPI_INVALID_DATA_OFFSET) {
       // pass 2 skipped: the pass-1 rows are recycled into the P-length slices (:216-223)
-      const double *in = hist1 + ((i / kTile) * (int64_t)M.P1 * 2 + g) * kTile + (i % kTile);
-      for (int d = 0; d < M.P; ++d) out[(int64_t)d * 2 * kTile] = in[(int64_t)(d % M.P1) * 2 * kTile];
+      const double *in = hist1 + (i * 2 + g) * (int64_t)hist_pitch(M.P1);
+      for (int d = 0; d < M.P; ++d) out[d] = in[d % M.P1];
       return;
     }
     t0 = padv[i] + 1;
@@ -507,7 +544,7 @@ k_ode_age2(const DevModel M, const double *__restrict__ theta, int64_t ld, int64
       }
       rk4_piece_age2(a1, gamma, sg, y, pa, b, invN, Ngrp, nb, pairmask, even_lane);
     }
-    out[(int64_t)d * 2 * kTile] = y[0];
+    out[d] = y[0];
   }
 }
 
@@ -515,17 +552,19 @@ k_ode_age2(const DevModel M, const double *__restrict__ theta, int64_t ld, int64
 // Per-warp shared-memory carve-up shared by k_mid and k_score.
 constexpr int kCdfStride = EPI_MAX_TAPS + 1;  // n + 1 cell edges per profile
 struct WarpSmem {
-  double *theta;  // EPI_MAX_PARAMS
-  double *pp;     // NK * 4: per-profile (x0, shape|mean, scale|sd, lgamma(shape))
-  double *cdf;    // NK * kCdfStride
-  double *W;      // NK * EPI_MAX_TAPS
-  double *S;      // NG * (kPadMax + ndays)
+  double *theta;   // EPI_MAX_PARAMS
+  double *pp;      // NK * 4: per-profile (x0, shape|mean, scale|sd, lgamma(shape))
+  double *cdf;     // NK * kCdfStride
+  double *W;       // NK * EPI_MAX_TAPS
+  double *S;       // NG * (kPadMax + hist_pitch(ndays))
+  uint64_t *mbar;  // completion barrier of the bulk history copy
 };
 
 template <int FL>
 __host__ __device__ constexpr int warp_smem_doubles(int ndays) {
-  return EPI_MAX_PARAMS + Traits<FL>::NK * 4 + Traits<FL>::NK * kCdfStride + Traits<FL>::NK * EPI_MAX_TAPS +
-         Traits<FL>::NG * (kPadMax + ndays) + 2;
+  // even (16-byte aligned sub-regions); the last two doubles hold the warp's mbarrier
+  return (EPI_MAX_PARAMS + Traits<FL>::NK * 4 + Traits<FL>::NK * kCdfStride + Traits<FL>::NK * EPI_MAX_TAPS +
+          Traits<FL>::NG * (kPadMax + hist_pitch(ndays)) + 3) & ~1;
 }
 
 template <int FL>
@@ -536,6 +575,7 @@ __device__ __forceinline__ WarpSmem carve(double *base, int ndays) {
   w.cdf = w.pp + Traits<FL>::NK * 4;
   w.W = w.cdf + Traits<FL>::NK * kCdfStride;
   w.S = w.W + Traits<FL>::NK * EPI_MAX_TAPS;
+  w.mbar = reinterpret_cast<uint64_t *>(base + warp_smem_doubles<FL>(ndays) - 2);
   return w;
 }
 
@@ -651,19 +691,32 @@ __device__ __forceinline__ void build_profiles(const WarpSmem &w, const int *n_,
   __syncwarp();
 }
 
-// stage one chain's S history (ndays values per group) behind kPadMax prefill slots
+// stage one chain's S history (ndays values per group) behind kPadMax prefill slots: issue the
+// bulk copies (one elected lane), fill the prefill slots meanwhile, then wait for the bytes
 template <int FL>
-__device__ __forceinline__ void stage_history(const DevModel &M, const WarpSmem &w, const double *__restrict__ hist,
-                                              int64_t chain, int ndays, int lane) {
+__device__ __forceinline__ void stage_history_begin(double *S, uint64_t *mbar, const double *__restrict__ hist,
+                                                    int64_t chain, int ndays, int lane) {
   constexpr int NG = Traits<FL>::NG;
-  const int stride = kPadMax + ndays;
-  const double *in = hist + ((chain / kTile) * (int64_t)ndays * NG) * kTile + (chain % kTile);
+  const int pitch = hist_pitch(ndays), stride = kPadMax + pitch;
+  if (lane == 0) mbar_init(mbar, 1);
+  __syncwarp();
+  if (lane == 0) {
+    const unsigned bytes = (unsigned)pitch * 8u;
+    mbar_expect_tx(mbar, bytes * NG);
+#pragma unroll
+    for (int g = 0; g < NG; ++g) bulk_g2s(S + g * stride + kPadMax, hist + (chain * NG + g) * (int64_t)pitch, bytes, mbar);
+  }
+}
+template <int FL>
+__device__ __forceinline__ void stage_history_end(const DevModel &M, double *S, uint64_t *mbar, int ndays, int lane) {
+  constexpr int NG = Traits<FL>::NG;
+  const int stride = kPadMax + hist_pitch(ndays);
 #pragma unroll
   for (int g = 0; g < NG; ++g) {
     const double s0 = Traits<FL>::kAge ? (g == 0 ? M.Ny - 1.0 : M.No) : M.N - 1.0;
-    for (int j = lane; j < kPadMax; j += 32) w.S[g * stride + j] = s0;
-    for (int j = lane; j < ndays; j += 32) w.S[g * stride + kPadMax + j] = in[((int64_t)j * NG + g) * kTile];
+    for (int j = lane; j < kPadMax; j += 32) S[g * stride + j] = s0;
   }
+  mbar_wait(mbar, 0);
   __syncwarp();
 }
 
@@ -691,6 +744,7 @@ k_mid(const DevModel M, const double *__restrict__ theta, int64_t ld, int64_t n,
   if (chain >= n) return;
   const int P1 = M.P1;
   const WarpSmem w = carve<FL>(smem + (size_t)wib * warp_smem_doubles<FL>(P1), P1);
+  stage_history_begin<FL>(w.S, w.mbar, hist1, chain, P1, lane);  // asynchronous; consumed after the profiles
 
   // theta -> MODEL space in shared memory (transformParams: simple exp(logHR), :136-142)
   int oob = 0;
@@ -730,6 +784,7 @@ k_mid(const DevModel M, const double *__restrict__ theta, int64_t ld, int64_t n,
   pad += 1;
   if (!ok || pad > kPadMax) {
     if (lane == 0) { offset[chain] = EPI_INVALID_DATA_OFFSET; padv[chain] = 0; status[chain] = st | EPI_ST_UNSUPPORTED; }
+    mbar_wait(w.mbar, 0);  // never leave with a bulk copy into this block's shared memory in flight
     return;
   }
   __syncwarp();
@@ -742,8 +797,8 @@ k_mid(const DevModel M, const double *__restrict__ theta, int64_t ld, int64_t n,
   }
 
   // pass-1 threshold search (:167-182 / simple :88-95)
-  stage_history<FL>(M, w, hist1, chain, P1, lane);
-  const int stride = kPadMax + P1;
+  stage_history_end<FL>(M, w.S, w.mbar, P1, lane);
+  const int stride = kPadMax + hist_pitch(P1);
   int first = -1;
   double thr;
   if constexpr (Traits<FL>::kAge) thr = w.theta[17]; else thr = w.theta[7];
@@ -836,19 +891,21 @@ __device__ __forceinline__ double score_day(const DevModel &M, const double2 *__
 template <int FL>
 __host__ __device__ constexpr int score_smem_doubles(int ndays) {
   // even, so that every warp's Wabs stays 16-byte aligned for the double2 weight loads
-  return (EPI_MAX_PARAMS + Traits<FL>::NG * EPI_MAX_TAPS * 4 + Traits<FL>::NG * (kPadMax + ndays) + 3) & ~1;
+  return (EPI_MAX_PARAMS + Traits<FL>::NG * EPI_MAX_TAPS * 4 + Traits<FL>::NG * (kPadMax + hist_pitch(ndays)) + 3) & ~1;
 }
 
 struct ScoreSmem {
   double *theta, *Wabs, *S;
+  uint64_t *mbar;
 };
 
 template <int FL>
-__device__ __forceinline__ ScoreSmem carve_score(double *base) {
+__device__ __forceinline__ ScoreSmem carve_score(double *base, int ndays) {
   ScoreSmem w;
   w.theta = base;
   w.Wabs = base + EPI_MAX_PARAMS;
   w.S = w.Wabs + Traits<FL>::NG * EPI_MAX_TAPS * 4;
+  w.mbar = reinterpret_cast<uint64_t *>(base + score_smem_doubles<FL>(ndays) - 2);
   return w;
 }
 
@@ -861,6 +918,7 @@ __device__ __forceinline__ void stage_score(const DevModel &M, const ScoreSmem &
                                             const int2 *__restrict__ pmeta, int P, int lane, int *dmin_, int *n_,
                                             int *lo, int *hi) {
   constexpr int NK = Traits<FL>::NK, NG = Traits<FL>::NG, KG = NK / NG;
+  stage_history_begin<FL>(w.S, w.mbar, hist2, chain, P, lane);  // asynchronous bulk copy of the S rows
   for (int p = lane; p < M.d; p += 32) {
     double v = theta[(int64_t)p * ld + chain];
     if (to_model_space && !Traits<FL>::kAge && p == 4) v = exp(v);  // transformParams, :136-142
@@ -880,16 +938,7 @@ __device__ __forceinline__ void stage_score(const DevModel &M, const ScoreSmem &
     for (int o = lane; o < pm.y; o += 32)
       w.Wabs[(g * EPI_MAX_TAPS + pm.x + o) * 4 + (q % KG)] = __ldcs(Wg + ((int64_t)chain * NK + q) * EPI_MAX_TAPS + o);
   }
-  const int stride = kPadMax + P;
-  const double *in = hist2 + ((chain / kTile) * (int64_t)P * NG) * kTile + (chain % kTile);
-#pragma unroll
-  for (int g = 0; g < NG; ++g) {
-    const double s0 = Traits<FL>::kAge ? (g == 0 ? M.Ny - 1.0 : M.No) : M.N - 1.0;
-    for (int j = lane; j < kPadMax; j += 32) w.S[g * stride + j] = s0;
-    // streamed once: keep it out of L1, which the shared term table and rate vectors live in
-    for (int j = lane; j < P; j += 32) w.S[g * stride + kPadMax + j] = __ldcs(in + ((int64_t)j * NG + g) * kTile);
-  }
-  __syncwarp();
+  stage_history_end<FL>(M, w.S, w.mbar, P, lane);
 }
 
 // convolute() (model-age-groups2q.R:42-45) of the KG profiles of one S group at the two
@@ -959,7 +1008,7 @@ k_score(const DevModel M, const PriorTerm *__restrict__ PT, int n_prior, const d
   __syncthreads();
   if (chain >= n) return;
   const int P = M.P;
-  const ScoreSmem w = carve_score<FL>(smem + 2 * kLogTabN + (size_t)wib * score_smem_doubles<FL>(P));
+  const ScoreSmem w = carve_score<FL>(smem + 2 * kLogTabN + (size_t)wib * score_smem_doubles<FL>(P), P);
   int st = status[chain];
 
   if (st & EPI_ST_UNSUPPORTED) {
@@ -989,7 +1038,7 @@ k_score(const DevModel M, const PriorTerm *__restrict__ PT, int n_prior, const d
   const int T = pad + P;
   const int off_raw = offset[chain];
   const int off = off_raw != EPI_INVALID_DATA_OFFSET ? off_raw : 1;  // :493-494
-  const int stride = kPadMax + P;
+  const int stride = kPadMax + hist_pitch(P);
 
   int dstart[kMaxSeries];
   int tlo = pad + 1;
@@ -1103,7 +1152,7 @@ k_series(const DevModel M, const double *__restrict__ theta, int64_t ld, int64_t
   const int64_t chain = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
   if (chain >= n) return;
   const int P = M.P;
-  const ScoreSmem w = carve_score<FL>(smem + (size_t)wib * score_smem_doubles<FL>(P));
+  const ScoreSmem w = carve_score<FL>(smem + (size_t)wib * score_smem_doubles<FL>(P), P);
   double *o = out + (int64_t)chain * NS * P;
   if (status[chain] & EPI_ST_UNSUPPORTED) {
     for (int i = lane; i < NS * P; i += 32) o[i] = NAN;
@@ -1114,7 +1163,7 @@ k_series(const DevModel M, const double *__restrict__ theta, int64_t ld, int64_t
   stage_score<FL>(M, w, theta, ld, chain, false, hist2, Wg, pmeta, P, lane, dmin_, n_, lo, hi);
   const int pad = padv[chain];
   const int off_raw = offset[chain];
-  const int stride = kPadMax + P;
+  const int stride = kPadMax + hist_pitch(P);
   if constexpr (Traits<FL>::kAge) {
     AgeMap map;
     map.init(M, w.theta, off_raw, pad, P);
@@ -1284,6 +1333,7 @@ static cudaError_t launch_eval_fl(const EvalArgs &a) {
   if (a.ev) cudaEventRecord(a.ev[1], s);
   k_mid<FL><<<warp_blocks, 128, smem_mid, s>>>(M, a.theta, a.ld, n, a.hist1, a.offset, a.pad, a.status, a.W, a.pmeta, a.model_space);
   if (a.ev) cudaEventRecord(a.ev[2], s);
+  if (a.ev_after_mid) cudaEventRecord(a.ev_after_mid, s);
   if (use_pair) {
     if constexpr (Traits<FL>::kAge) k_ode_age2<true><<<pair_blocks, 64, 0, s>>>(M, a.theta, a.ld, n, a.offset, a.pad, a.hist1, a.hist2);
   } else k_ode<FL, true><<<ode_blocks, 32, 0, s>>>(M, a.theta, a.ld, n, a.offset, a.pad, a.hist1, a.hist2);

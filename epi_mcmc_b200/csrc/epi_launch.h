@@ -21,6 +21,7 @@ struct EvalArgs {
   double *series_out;           // non-null: write calculateModel series instead of scoring
   cudaStream_t stream;
   cudaEvent_t *ev;  // null or 5 events bracketing the 4 launches
+  cudaEvent_t ev_after_mid = nullptr;  // optional: recorded after k_mid (stagger point of the two-stream mode)
 };
 
 cudaError_t launch_eval(const EvalArgs &a);
