@@ -103,7 +103,7 @@ SYMBOLS = (
     "epi_param_name", "epi_df_params", "epi_eval", "epi_eval_device", "epi_eval_detail",
     "epi_n_series", "epi_trajectories", "epi_quantiles", "epi_sampler_init", "epi_sampler_run",
     "epi_sampler_adapt", "epi_sampler_state_device", "epi_sampler_set_population",
-    "epi_sampler_get", "epi_sampler_stats", "epi_sampler_pt_stats", "epi_sampler_record", "epi_sampler_draws",
+    "epi_sampler_get", "epi_sampler_stats", "epi_sampler_pt_stats", "epi_sampler_record", "epi_sampler_draws", "epi_sampler_draws_subset",
     "epi_fp64_peak", "epi_set_timing", "epi_last_kernel_ms", "epi_launch_count", "epi_philox_probe",
 )
 
@@ -146,6 +146,7 @@ def load():
     lib.epi_sampler_pt_stats.argtypes = [vp, C.POINTER(i64), C.POINTER(i64)]
     lib.epi_sampler_record.argtypes = [vp, i32, i32]
     lib.epi_sampler_draws.argtypes = [vp, _dp, _dp, ip]
+    lib.epi_sampler_draws_subset.argtypes = [vp, i32, i32, _dp, _dp, ip]
     lib.epi_fp64_peak.argtypes = [vp, _dp]
     lib.epi_set_timing.argtypes = [vp, C.c_int]
     lib.epi_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]

@@ -953,6 +953,7 @@ __device__ __forceinline__ void conv_group2(const double *__restrict__ Sg, const
   const double *xa = Sg + kPadMax + j0, *xb = Sg + kPadMax + j1;
 #pragma unroll
   for (int q = 0; q < KG; ++q) { ca[q] = 0.0; cb[q] = 0.0; }
+#pragma unroll 4
   for (int d = lo; d <= hi; ++d) {
     const double x0 = xa[-d], x1 = xb[-d];
     const double2 w01 = *reinterpret_cast<const double2 *>(Wabs + d * 4);

@@ -582,6 +582,25 @@ extern "C" int epi_sampler_draws(epi_handle *h, double *draws, double *logpost, 
   return EPI_OK;
 }
 
+extern "C" int epi_sampler_draws_subset(epi_handle *h, int32_t first, int32_t n_sub, double *draws, double *logpost,
+                                        int32_t *n_kept) {
+  if (!h || !h->sampler) return epi_fail(h, EPI_ERR_STATE, "sampler not initialised");
+  SamplerState *s = h->sampler;
+  if (first < 0 || n_sub < 1 || first + n_sub > s->cfg.n_chains) return epi_fail(h, EPI_ERR_ARG, "chain range out of bounds");
+  CUDA_OK(h, cudaSetDevice(h->device));
+  if (n_kept) *n_kept = s->kept;
+  if (s->kept == 0) return EPI_OK;
+  const int d = h->M.d;
+  if (draws)  // device [k][p][ld] -> host [k][p][n_sub]: one strided copy
+    CUDA_OK(h, cudaMemcpy2DAsync(draws, sizeof(double) * (size_t)n_sub, s->draws + first, sizeof(double) * (size_t)s->ld,
+                                 sizeof(double) * (size_t)n_sub, (size_t)s->kept * d, cudaMemcpyDeviceToHost, h->stream));
+  if (logpost)
+    CUDA_OK(h, cudaMemcpy2DAsync(logpost, sizeof(double) * (size_t)n_sub, s->draws_lp + first, sizeof(double) * (size_t)s->ld,
+                                 sizeof(double) * (size_t)n_sub, (size_t)s->kept, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_OK(h, cudaStreamSynchronize(h->stream));
+  return EPI_OK;
+}
+
 // test hook: raw Philox4x32-10 words from the device
 extern "C" int epi_philox_probe(epi_handle *h, uint64_t seed, uint32_t iter, uint32_t use, int32_t n, uint32_t *out) {
   if (!h || !out || n < 1) return epi_fail(h, EPI_ERR_ARG, "bad argument");

@@ -96,6 +96,18 @@ class Sampler:
         a = np.asarray(a)
         return a[:, lo:lo + self.chains_per_rung] if a.ndim >= 2 else a[lo:lo + self.chains_per_rung]
 
+    def draws_subset(self, first: int, n_sub: int):
+        """draws[k, chain, d] and logpost[k, chain] of chains [first, first + n_sub) only"""
+        kept = C.c_int32()
+        _capi.check(self._lib.epi_sampler_draws_subset(self._h, int(first), int(n_sub), None, None, C.byref(kept)), self._h)
+        k = kept.value
+        out = np.empty((k, self.model.d, n_sub))
+        lp = np.empty((k, n_sub))
+        if k:
+            _capi.check(self._lib.epi_sampler_draws_subset(self._h, int(first), int(n_sub), _capi.as_dp(out),
+                                                           _capi.as_dp(lp), C.byref(kept)), self._h)
+        return np.ascontiguousarray(out.transpose(0, 2, 1)), lp
+
     def draws(self):
         """(draws[k, chain, d], logpost[k, chain]) of the recorded thinned states"""
         kept = C.c_int32()

@@ -245,6 +245,9 @@ int epi_sampler_stats(epi_handle *h, int64_t *n_iter, int64_t *n_accept, int64_t
  * (HOST, n_kept x n_chains x d)                                               */
 int epi_sampler_record(epi_handle *h, int32_t thin, int32_t capacity);
 int epi_sampler_draws(epi_handle *h, double *draws, double *logpost, int32_t *n_kept);
+/* the recorded draws of chains [first, first + n_sub) only, in the device layout:
+ * draws HOST n_kept x d x n_sub, logpost HOST n_kept x n_sub (either may be NULL) */
+int epi_sampler_draws_subset(epi_handle *h, int32_t first, int32_t n_sub, double *draws, double *logpost, int32_t *n_kept);
 
 /* ---- measurement helpers --------------------------------------------------- */
 /* DFMA-chain microbenchmark on the handle's device: measured FP64 TFLOP/s, the
