@@ -30,6 +30,10 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# DRAM bytes per launch of each kernel (read + write) from the committed ncu --set full capture of
+# this exact workload (profiles/r1_v7_ncu_full.txt); only reported when the run matches that workload
+NCU_TRAFFIC = {}
+
 METRIC = "log_posterior_evals_per_s"
 UNIT = "evals/s"
 
@@ -69,8 +73,13 @@ def f_alg(flavour, P, m, taps_mean, n_terms, n_prior):
     steps = m * (P1 + P)
     ode = steps * (4 * F_rhs + 14 * S)
     total = ode + K * (taps_mean + 2) * 240 + (C2 * P + C1 * P1) * 2 * taps_mean + 6 * C2 * P + 72 * n_terms + 40 * n_prior
-    ode2 = m * P * (4 * F_rhs + 14 * S)
-    return dict(total=total, ode=ode, ode_pass2=ode2)
+    per_kernel = {
+        "ode_pass1": m * P1 * (4 * F_rhs + 14 * S),
+        "profiles_threshold": K * (taps_mean + 2) * 240 + C1 * P1 * 2 * taps_mean,
+        "ode_pass2": m * P * (4 * F_rhs + 14 * S),
+        "score": C2 * P * 2 * taps_mean + 6 * C2 * P + 72 * n_terms + 40 * n_prior,
+    }
+    return dict(total=total, ode=ode, per_kernel=per_kernel)
 
 
 def mean_taps(flavour, theta):
@@ -293,11 +302,20 @@ def main():
     assert np.allclose(ll_host.numpy(), logl.cpu().numpy(), rtol=0, atol=0, equal_nan=True)
     clocks.stop()
 
-    # ---- roofline of the dominant kernel
+    # ---- rooflines: every launch of the step against the FP64 peak measured live; `roofline` is the
+    # kernel with the largest share of the step
     peak_tf = M.fp64_peak_tflops()
-    fa = f_alg(ds["flavour"], ds["period"], args.substeps, mean_taps(ds["flavour"], theta), _n_terms(M), 38 if ds["flavour"] == "age2q" else 3)
-    ode2_ms = float(kms[2])
-    achieved_tf = fa["ode_pass2"] * n / (ode2_ms * 1e-3) / 1e12
+    fa = f_alg(ds["flavour"], ds["period"], args.substeps, mean_taps(ds["flavour"], theta), _n_terms(M),
+               38 if ds["flavour"] == "age2q" else 3)
+    knames = ["ode_pass1", "profiles_threshold", "ode_pass2", "score"]
+    kernel_fn = {"ode_pass1": "k_ode<pass1>", "profiles_threshold": "k_mid", "ode_pass2": "k_ode<pass2>", "score": "k_score"}
+    per_kernel = {}
+    for k, msk in zip(knames, kms):
+        tf = fa["per_kernel"][k] * n / (float(msk) * 1e-3) / 1e12
+        per_kernel[k] = {"kernel": kernel_fn[k], "ms": float(msk), "algorithmic_flop_per_launch": fa["per_kernel"][k] * n,
+                         "achieved": tf, "frac": tf / peak_tf if peak_tf else None,
+                         "traffic": NCU_TRAFFIC.get(k)}
+    dom = knames[int(np.argmax(kms))]
     step_ms = ms / args.steps
     whole_tf = fa["total"] * n / (step_ms * 1e-3) / 1e12
 
@@ -316,11 +334,15 @@ def main():
         "gpu_launches": int(launches),
         "kernels": {"ode_pass1_ms": float(kms[0]), "profiles_threshold_ms": float(kms[1]), "ode_pass2_ms": float(kms[2]),
                     "score_ms": float(kms[3])},
-        "roofline": {"bound": "fp64", "kernel": "k_ode<age2q,pass2>", "achieved": achieved_tf, "peak": peak_tf,
-                     "unit": "TFLOP/s", "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": None,
+        "roofline": {"bound": "fp64", "kernel": per_kernel[dom]["kernel"], "achieved": per_kernel[dom]["achieved"],
+                     "peak": peak_tf, "unit": "TFLOP/s", "frac": per_kernel[dom]["frac"],
+                     "traffic": per_kernel[dom]["traffic"],
                      "peak_source": "measured live: DFMA-chain microbenchmark epi_fp64_peak (MEASURED_PEAKS.json has no FP64 entry; "
                                     "nominal 37.2 TFLOP/s = 148 SM x 64 DFMA/clk x 2 x 1.965 GHz)",
-                     "algorithmic_flop_per_launch": fa["ode_pass2"] * n},
+                     "algorithmic_flop_per_launch": per_kernel[dom]["algorithmic_flop_per_launch"],
+                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, "
+                                       "profiles/r1_v7_ncu_full.txt (65,536 chains, A300)"},
+        "roofline_all": per_kernel,
         "f_alg": {"per_eval": fa["total"], "ode_share": fa["ode"] / fa["total"], "whole_step_tflops": whole_tf,
                   "whole_step_frac": whole_tf / peak_tf if peak_tf else None},
     }

@@ -121,8 +121,8 @@ static int build_term_table(epi_handle *h, const std::vector<NbCall> &calls, con
       //   sum_k [x_k log(mu) - (x_k + size) log(size + mu)] = (sum x_k) log(mu) - (sum (x_k + size)) log(size + mu)
       bool merged = false;
       for (Slot &sl : per[c.series][rel])
-        if (sl.size == size) { sl.x += x; sl.xs += x + size; merged = true; break; }
-      if (!merged) per[c.series][rel].push_back(Slot{x, x + size, size, 0.0});
+        if (sl.size == size) { sl.x += (float)x; sl.n += 1.0f; merged = true; break; }
+      if (!merged) per[c.series][rel].push_back(Slot{size, (float)x, 1.0f});
       cst[c.term] += lgammal((long double)x + size) - lgammal((long double)size) - lgammal((long double)x + 1.0L) +
                      (long double)size * logl((long double)size);
     }
@@ -130,7 +130,11 @@ static int build_term_table(epi_handle *h, const std::vector<NbCall> &calls, con
   for (int s = 0; s < n_series; ++s) {
     size_t K = 1;
     for (auto &v : per[s]) K = std::max(K, v.size());
-    std::vector<Slot> flat((size_t)n_obs[s] * K, Slot{0.0, 0.0, 0.0, 0.0});
+    std::vector<Slot> flat((size_t)n_obs[s] * K, Slot{0.0, 0.0f, 0.0f});
+    for (auto &v : per[s])
+      for (Slot &sl : v)
+        if (!(sl.x < 16777216.0f))
+          return epi_fail(h, EPI_ERR_ARG, "observed counts of one day sum to %g >= 2^24: not representable in the term table", (double)sl.x);
     for (int r = 0; r < n_obs[s]; ++r)
       for (size_t k = 0; k < per[s][r].size(); ++k) flat[(size_t)r * K + k] = per[s][r][k];
     Slot *d = nullptr;

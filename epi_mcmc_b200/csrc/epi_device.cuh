@@ -21,11 +21,20 @@ constexpr int kNaFlagTerms = 8;
 // dnbinom() term that reads model day (dstart + rel).  (R recycling resolved on
 // the host, see build_term_table in epi_capi.cu.)
 struct Slot {
-  double x;     // sum of the observed counts of the merged dnbinom() terms
-  double xs;    // sum of (x + size) over them  (0 => empty slot)
-  double size;  // their common size
-  double pad;   // 32-byte slots: two aligned 16-byte loads
+  double size;  // common size of the merged dnbinom() terms
+  float x;      // sum of their observed counts (integers < 2^24: exact in a float)
+  float n;      // how many terms were merged (0 => empty slot); sum of (x + size) = x + n * size
 };
+static_assert(sizeof(Slot) == 16, "one 16-byte load per slot");
+__device__ __forceinline__ Slot ldg_slot(const Slot *p) {
+  const double2 raw = __ldg(reinterpret_cast<const double2 *>(p));
+  Slot s;
+  s.size = raw.x;
+  const long long b = __double_as_longlong(raw.y);
+  s.x = __int_as_float((int)(b & 0xffffffffll));
+  s.n = __int_as_float((int)(b >> 32));
+  return s;
+}
 
 struct DevModel {
   int flavour, P, m, d;

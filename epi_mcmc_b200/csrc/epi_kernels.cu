@@ -839,20 +839,6 @@ __device__ __forceinline__ double prior_term(const PriorTerm &p, const double *t
   return p.is_ln ? dev_dlnorm_log(v, p.mean, p.sd) : dev_dnorm_log(v, p.mean, p.sd);
 }
 
-// rate vector element i (1-based) of scored profile q, model-age-groups2q.R:229-235
-__device__ __forceinline__ double age_rate(const DevModel &M, const double *th, int q, int i) {
-  const int k = i - 1;
-  const double ifrred = th[42];
-  switch (q) {
-    case 0: { const double v = th[9] * M.y_ifr[k] * (1 + (th[21] - 1) * M.g[k]); return v > 1 ? 1.0 : v; }    // gycr
-    case 1: return th[10] * M.y_hr[k] * (1 + (th[22] - 1) * M.g[k]);                                       // gyhr
-    case 2: return M.y_ifr[k] * (1 + (th[21] - 1) * M.g[k]) * (1 - ifrred * M.gtrimp[k]);                    // gyifr
-    case 3: { const double v = th[13] * M.o_ifr[k]; return v > 1 ? 1.0 : v; }                              // gocr
-    case 4: return th[14] * M.o_hr[k];                                                                     // gohr
-    default: return M.o_ifr[k] * (1 - ifrred * M.gtrimp[k]);                                               // goifr
-  }
-}
-
 __device__ __forceinline__ void window(int offset, int n, int T, int &dstart) {
   // model-age-groups2q.R:497-512
   int ds = offset, de = offset + n - 1;
@@ -862,25 +848,43 @@ __device__ __forceinline__ void window(int offset, int n, int T, int &dstart) {
 }
 
 // score the slots of scored series s that read model day t (value v)
-__device__ __forceinline__ double score_day(const DevModel &M, const double2 *__restrict__ ltab, int s, int t, int dstart,
-                                            double v) {
-  const int r = t - dstart;
-  if (r < 0 || r >= M.n_obs[s]) return 0.0;
-  const int K = M.K[s];
-  const Slot *sl = M.slots[s] + (size_t)r * K;
-  double acc = 0.0;
+// One scored series at model day t: x*log(mu) - (x + n*size)*log(size + mu) summed over the slots of
+// that day (= size*log(size/(size+mu)) + x*log(mu/(size+mu)) minus its data-only part size*log(size)).
+// `first` is slot 0, already loaded by the caller together with the other series' (ILP).
+__device__ __forceinline__ double score_slots(const DevModel &M, const double2 *__restrict__ ltab, int s, int r, bool in_range,
+                                              const Slot &first, double v) {
+  if (!in_range) return 0.0;
   const double mu = dev_pmax(M.floor_[s], v);
-  double lmu = 0.0;
-  bool have = false;
-  for (int k = 0; k < K; ++k) {
-    const double2 a = __ldg(reinterpret_cast<const double2 *>(sl + k));      // (x, xs)
-    if (a.y == 0.0) continue;
-    const double size = __ldg(reinterpret_cast<const double *>(sl + k) + 2);
-    if (!have) { lmu = tlog(mu, ltab); have = true; }
-    // size*log(size/(size+mu)) + x*log(mu/(size+mu)) minus its data-only part size*log(size)
-    acc += a.x * lmu - a.y * tlog(size + mu, ltab);
+  double acc = 0.0;
+  if (first.n != 0.0f) {
+    const double x = (double)first.x;
+    acc = x * tlog(mu, ltab) - fma((double)first.n, first.size, x) * tlog(first.size + mu, ltab);
+  }
+  const int K = M.K[s];
+  for (int k = 1; k < K; ++k) {  // rare: days with terms of several sizes (the last-8-days hospital weight)
+    const Slot z = ldg_slot(M.slots[s] + (size_t)r * K + k);
+    if (z.n == 0.0f) continue;
+    const double x = (double)z.x;
+    acc += x * tlog(mu, ltab) - fma((double)z.n, z.size, x) * tlog(z.size + mu, ltab);
   }
   return acc;
+}
+
+// all scored series of one model day: slot 0 of every series is fetched before any is evaluated
+template <int NS>
+__device__ __forceinline__ void score_day_all(const DevModel &M, const double2 *__restrict__ ltab, int t, const int *dstart,
+                                              const double *v, double *acc) {
+  Slot first[NS];
+  int r[NS];
+  bool ok[NS];
+#pragma unroll
+  for (int s = 0; s < NS; ++s) {
+    r[s] = t - dstart[s];
+    ok[s] = r[s] >= 0 && r[s] < M.n_obs[s];
+    first[s] = ok[s] ? ldg_slot(M.slots[s] + (size_t)r[s] * M.K[s]) : Slot{0.0, 0.0f, 0.0f};
+  }
+#pragma unroll
+  for (int s = 0; s < NS; ++s) acc[s] += score_slots(M, ltab, s, r[s], ok[s], first[s], v[s]);
 }
 
 // ---- shared-memory carve-up of k_score / k_series (per warp) -------------------
@@ -966,15 +970,19 @@ __device__ __forceinline__ void conv_group2(const double *__restrict__ Sg, const
   }
 }
 
-// the three-slice rate map of model-age-groups2q.R:240-251 for the six series
+// the three-slice rate map of model-age-groups2q.R:240-251 for the six series.
+// For a valid data_offset the rate applied at sim day t is rate[i], i = 1 for t <= t1,
+// t - t1 + 1 for t1 < t < t2, and length(rate) for t >= t2 (the later slice assignments overwrite
+// the shared end points), where t2 = min(padding + period, t1 + length(rate) - 1); the whole map
+// is skipped (series stays 0) unless t1 > padding && t2 > t1.  The index is computed branch-free so
+// that the eleven base-vector loads of a day are issued back to back (profiles/r1_v7: the serial
+// load -> branch -> load chains were 24 % long-scoreboard stalls).
 struct AgeMap {
   int t1[6], t2[6];
-  double r_first[6], r_last[6];
+  bool on[6];  // t1 > pad && t2 > t1, or invalid offset (then rate[1] everywhere, :250)
   bool valid;
-  int pad;
-  __device__ __forceinline__ void init(const DevModel &M, const double *th, int off_raw, int pad_, int P) {
+  __device__ __forceinline__ void init(const DevModel &M, const double *th, int off_raw, int pad, int P) {
     valid = off_raw != EPI_INVALID_DATA_OFFSET;
-    pad = pad_;
     const double ydl = th[12];  // y.DL is used for both groups (:290,306)
     const double lat[6] = {th[43], th[11], 0, th[44], th[15], 0};
 #pragma unroll
@@ -982,15 +990,36 @@ struct AgeMap {
       const int shift = (q == 2 || q == 5) ? 0 : (int)rint(-ydl + lat[q]);
       t1[q] = off_raw + shift;
       t2[q] = min(pad + P, t1[q] + M.n_rate - 1);
-      r_first[q] = age_rate(M, th, q, 1);
-      r_last[q] = age_rate(M, th, q, M.n_rate);
+      on[q] = !valid || (t1[q] > pad && t2[q] > t1[q]);
     }
   }
-  __device__ __forceinline__ double value(const DevModel &M, const double *th, int q, int t, double inc) const {
-    if (!valid) return inc * r_first[q];              // :250
-    if (!(t1[q] > pad && t2[q] > t1[q])) return 0.0;  // :244
-    const double r = (t >= t2[q]) ? r_last[q] : (t <= t1[q]) ? r_first[q] : age_rate(M, th, q, t - t1[q] + 1);
-    return inc * r;  // later slices overwrite the shared end points (:245-247)
+  // 0-based index into the rate vectors for profile q at sim day t
+  __device__ __forceinline__ int index(const DevModel &M, int q, int t) const {
+    const int i = (t >= t2[q]) ? M.n_rate : max(t - t1[q] + 1, 1);
+    return (valid ? i : 1) - 1;
+  }
+  // val[q] = inc[q] * rate_q(t) for the six profiles (ycase, yhosp, ydied, ocase, ohosp, odied)
+  __device__ __forceinline__ void values(const DevModel &M, const double *th, int t, const double *inc, double *val) const {
+    int k[6];
+#pragma unroll
+    for (int q = 0; q < 6; ++q) k[q] = index(M, q, t);
+    // all loads first (model-age-groups2q.R:229-235)
+    const double yifr0 = __ldg(M.y_ifr + k[0]), g0 = __ldg(M.g + k[0]);
+    const double yhr1 = __ldg(M.y_hr + k[1]), g1 = __ldg(M.g + k[1]);
+    const double yifr2 = __ldg(M.y_ifr + k[2]), g2 = __ldg(M.g + k[2]), gt2 = __ldg(M.gtrimp + k[2]);
+    const double oifr3 = __ldg(M.o_ifr + k[3]);
+    const double ohr4 = __ldg(M.o_hr + k[4]);
+    const double oifr5 = __ldg(M.o_ifr + k[5]), gt5 = __ldg(M.gtrimp + k[5]);
+    const double ifrred = th[42];
+    double r[6];
+    r[0] = th[9] * yifr0 * (1 + (th[21] - 1) * g0);   r[0] = r[0] > 1 ? 1.0 : r[0];  // gycr = pmin(1, .)
+    r[1] = th[10] * yhr1 * (1 + (th[22] - 1) * g1);                                   // gyhr
+    r[2] = yifr2 * (1 + (th[21] - 1) * g2) * (1 - ifrred * gt2);                      // gyifr
+    r[3] = th[13] * oifr3;                            r[3] = r[3] > 1 ? 1.0 : r[3];  // gocr
+    r[4] = th[14] * ohr4;                                                             // gohr
+    r[5] = oifr5 * (1 - ifrred * gt5);                                                // goifr
+#pragma unroll
+    for (int q = 0; q < 6; ++q) val[q] = on[q] ? inc[q] * r[q] : 0.0;
   }
 };
 
@@ -1062,7 +1091,7 @@ k_score(const DevModel M, const PriorTerm *__restrict__ PT, int n_prior, const d
         const int j = base + 32 * half + lane;
         const int t = pad + 1 + j;
         const bool in = j >= 0 && j < P;
-        double val[6];
+        double val[6], inc[6];
 #pragma unroll
         for (int q = 0; q < 6; ++q) {
           const double Ng = q < 3 ? M.Ny : M.No;
@@ -1072,17 +1101,19 @@ k_score(const DevModel M, const PriorTerm *__restrict__ PT, int n_prior, const d
           double prev = __shfl_up_sync(0xffffffffu, s2, 1);
           if (lane == 0) prev = carry[q];
           carry[q] = __shfl_sync(0xffffffffu, s2, 31);
-          const double inc = (j == 0) ? s2 : s2 - prev;  // c(s2[1], diff(s2)), :239
-          val[q] = in ? map.value(M, w.theta, q, t, inc) : 0.0;
+          inc[q] = (j == 0) ? s2 : s2 - prev;  // c(s2[1], diff(s2)), :239
+        }
+        if (in) {
+          map.values(M, w.theta, t, inc, val);
+        } else {
+#pragma unroll
+          for (int q = 0; q < 6; ++q) val[q] = 0.0;  // days before padding+1 hold the 0 prefill
         }
         if (j < P) {
           // scored series: y.casei, o.casei, hospi = y.hospi + o.hospi, y.deadi, o.deadi
           // (profile order: ycase, yhosp, ydied, ocase, ohosp, odied)
-          acc[0] += score_day(M, ltab, 0, t, dstart[0], val[0]);
-          acc[1] += score_day(M, ltab, 1, t, dstart[1], val[3]);
-          acc[2] += score_day(M, ltab, 2, t, dstart[2], val[1] + val[4]);
-          acc[3] += score_day(M, ltab, 3, t, dstart[3], val[2]);
-          acc[4] += score_day(M, ltab, 4, t, dstart[4], val[5]);
+          const double v5[5] = {val[0], val[3], val[1] + val[4], val[2], val[5]};
+          score_day_all<5>(M, ltab, t, dstart, v5, acc);
           if (t >= dstart[2] + M.d_hosp_o1 && t <= dstart[2] + M.d_hosp_o2) { ysum += val[1]; osum += val[4]; }  // :563-564
         }
       }
@@ -1100,6 +1131,7 @@ k_score(const DevModel M, const PriorTerm *__restrict__ PT, int n_prior, const d
         const int j = base + 32 * half + lane;
         const int t = pad + 1 + j;
         const bool in = j >= 0 && j < P;
+        double v2[2];
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
           double c = half ? cb[q] : ca[q];
@@ -1108,9 +1140,9 @@ k_score(const DevModel M, const PriorTerm *__restrict__ PT, int n_prior, const d
           double prev = __shfl_up_sync(0xffffffffu, cum, 1);
           if (lane == 0) prev = carry[q];
           carry[q] = __shfl_sync(0xffffffffu, cum, 31);
-          const double inc = cum - prev;  // prev is 0 for t = pad+1 (prefill)
-          if (j < P) acc[q] += score_day(M, ltab, q, t, dstart[q], (j >= 0) ? inc : 0.0);
+          v2[q] = (j >= 0) ? cum - prev : 0.0;  // prev is 0 for t = pad+1 (prefill)
         }
+        if (j < P) score_day_all<2>(M, ltab, t, dstart, v2, acc);
       }
     }
   }
@@ -1180,6 +1212,7 @@ k_series(const DevModel M, const double *__restrict__ theta, int64_t ld, int64_t
         const int t = pad + 1 + j;
         const bool in = j < P;
         if (in) { o[0 * P + j] = w.S[kPadMax + j]; o[1 * P + j] = w.S[stride + kPadMax + j]; }
+        double inc[6], val[6];
 #pragma unroll
         for (int q = 0; q < 6; ++q) {
           const double Ng = q < 3 ? M.Ny : M.No;
@@ -1189,8 +1222,12 @@ k_series(const DevModel M, const double *__restrict__ theta, int64_t ld, int64_t
           double prev = __shfl_up_sync(0xffffffffu, s2, 1);
           if (lane == 0) prev = carry[q];
           carry[q] = __shfl_sync(0xffffffffu, s2, 31);
-          const double inc = (j == 0) ? s2 : s2 - prev;
-          if (in) o[dst[q] * P + j] = map.value(M, w.theta, q, t, inc);
+          inc[q] = (j == 0) ? s2 : s2 - prev;
+        }
+        if (in) {
+          map.values(M, w.theta, t, inc, val);
+#pragma unroll
+          for (int q = 0; q < 6; ++q) o[dst[q] * P + j] = val[q];
         }
       }
     }
