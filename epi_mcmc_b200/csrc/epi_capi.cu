@@ -403,7 +403,7 @@ int epi_ensure_workspace(epi_handle *h, Workspace &w, const DevModel &M, int64_t
   // S histories: [chain][group][pitch], pitch = days rounded up to even (16-byte aligned rows for the bulk copies)
   CUDA_OK(h, cudaMalloc(&w.hist1, sizeof(double) * (size_t)(ld * NG * ((P1 + 1) & ~1))));
   CUDA_OK(h, cudaMalloc(&w.hist2, sizeof(double) * (size_t)(ld * NG * ((P + 1) & ~1))));
-  CUDA_OK(h, cudaMalloc(&w.W, sizeof(double) * (size_t)(ld * NK * EPI_MAX_TAPS)));
+  CUDA_OK(h, cudaMalloc(&w.W, sizeof(double) * (size_t)(ld * NG * EPI_MAX_TAPS * 4)));  // [chain][group][delay][4]
   CUDA_OK(h, cudaMalloc(&w.pmeta, sizeof(int2) * (size_t)(ld * NK)));
   CUDA_OK(h, cudaMalloc(&w.offset, sizeof(int) * (size_t)ld));
   CUDA_OK(h, cudaMalloc(&w.pad, sizeof(int) * (size_t)ld));
@@ -427,7 +427,7 @@ static EvalArgs make_args(epi_handle *h, Workspace &w, const DevModel &M, const 
   a.theta = d_theta + first; a.ld = ld; a.n = n; a.model_space = model_space;
   a.hist1 = w.hist1 + first * NG * (int64_t)((M.P1 + 1) & ~1);
   a.hist2 = w.hist2 + first * NG * (int64_t)((M.P + 1) & ~1);
-  a.W = w.W + first * NK * EPI_MAX_TAPS;
+  a.W = w.W + first * NG * EPI_MAX_TAPS * 4;
   a.pmeta = w.pmeta + first * NK;
   a.offset = w.offset + first; a.pad = w.pad + first;
   a.status = (d_status ? d_status : w.status) + first;

@@ -789,11 +789,29 @@ k_mid(const DevModel M, const double *__restrict__ theta, int64_t ld, int64_t n,
   }
   __syncwarp();
   build_profiles<FL>(w, n_, lane);
+  // profiles to HBM already in the absolute-delay layout k_score convolves with,
+  // Wabs[group][delay 0..63][4] (column = profile within the group, zero outside its support), so
+  // that the reader can take the whole 2 KB per group with one bulk copy
+  {
+    constexpr int KG = NK / NG;
+    int *meta = reinterpret_cast<int *>(w.cdf);  // the CDF scratch is free again: (dmin, n) per profile
 #pragma unroll
-  for (int q = 0; q < NK; ++q) {
-    for (int o = lane; o < EPI_MAX_TAPS; o += 32)
-      Wg[((int64_t)chain * NK + q) * EPI_MAX_TAPS + o] = o < n_[q] ? w.W[q * EPI_MAX_TAPS + o] : 0.0;
-    if (lane == 0) pmeta[(int64_t)chain * NK + q] = make_int2(dmin_[q], n_[q]);
+    for (int q = 0; q < NK; ++q)
+      if (lane == 0) { meta[2 * q] = dmin_[q]; meta[2 * q + 1] = n_[q]; }
+    __syncwarp();
+    double *dst = Wg + (int64_t)chain * NG * EPI_MAX_TAPS * 4;
+    for (int i = lane; i < NG * EPI_MAX_TAPS * 4; i += 32) {
+      const int c = i & 3, dly = (i >> 2) & (EPI_MAX_TAPS - 1), q = (i / (EPI_MAX_TAPS * 4)) * KG + c;
+      double v = 0.0;
+      if (c < KG) {
+        const unsigned o = (unsigned)(dly - meta[2 * q]);
+        if (o < (unsigned)meta[2 * q + 1]) v = w.W[q * EPI_MAX_TAPS + o];
+      }
+      dst[i] = v;
+    }
+#pragma unroll
+    for (int q = 0; q < NK; ++q)
+      if (lane == 0) pmeta[(int64_t)chain * NK + q] = make_int2(dmin_[q], n_[q]);
   }
 
   // pass-1 threshold search (:167-182 / simple :88-95)
@@ -870,22 +888,26 @@ __device__ __forceinline__ double score_slots(const DevModel &M, const double2 *
   return acc;
 }
 
-// all scored series of one model day: slot 0 of every series is fetched before any is evaluated
+// all scored series of one model day: slot 0 of every series is fetched (DaySlots::load, issued
+// by the caller BEFORE it computes the day's model values) and only then evaluated
 template <int NS>
-__device__ __forceinline__ void score_day_all(const DevModel &M, const double2 *__restrict__ ltab, int t, const int *dstart,
-                                              const double *v, double *acc) {
+struct DaySlots {
   Slot first[NS];
   int r[NS];
   bool ok[NS];
+  __device__ __forceinline__ void load(const DevModel &M, int t, const int *dstart, bool live) {
 #pragma unroll
-  for (int s = 0; s < NS; ++s) {
-    r[s] = t - dstart[s];
-    ok[s] = r[s] >= 0 && r[s] < M.n_obs[s];
-    first[s] = ok[s] ? ldg_slot(M.slots[s] + (size_t)r[s] * M.K[s]) : Slot{0.0, 0.0f, 0.0f};
+    for (int s = 0; s < NS; ++s) {
+      r[s] = t - dstart[s];
+      ok[s] = live && r[s] >= 0 && r[s] < M.n_obs[s];
+      first[s] = ok[s] ? ldg_slot(M.slots[s] + (size_t)r[s] * M.K[s]) : Slot{0.0, 0.0f, 0.0f};
+    }
   }
+  __device__ __forceinline__ void score(const DevModel &M, const double2 *__restrict__ ltab, const double *v, double *acc) const {
 #pragma unroll
-  for (int s = 0; s < NS; ++s) acc[s] += score_slots(M, ltab, s, r[s], ok[s], first[s], v[s]);
-}
+    for (int s = 0; s < NS; ++s) acc[s] += score_slots(M, ltab, s, r[s], ok[s], first[s], v[s]);
+  }
+};
 
 // ---- shared-memory carve-up of k_score / k_series (per warp) -------------------
 // theta[EPI_MAX_PARAMS] | Wabs[NG][EPI_MAX_TAPS][4] | S[NG][kPadMax + P]
@@ -922,13 +944,24 @@ __device__ __forceinline__ void stage_score(const DevModel &M, const ScoreSmem &
                                             const int2 *__restrict__ pmeta, int P, int lane, int *dmin_, int *n_,
                                             int *lo, int *hi) {
   constexpr int NK = Traits<FL>::NK, NG = Traits<FL>::NG, KG = NK / NG;
-  stage_history_begin<FL>(w.S, w.mbar, hist2, chain, P, lane);  // asynchronous bulk copy of the S rows
+  // asynchronous bulk copies (TMA unit): the S rows and the profiles, one mbarrier
+  {
+    const int pitch = hist_pitch(P), stride = kPadMax + pitch;
+    if (lane == 0) mbar_init(w.mbar, 1);
+    __syncwarp();
+    if (lane == 0) {
+      const unsigned hb = (unsigned)pitch * 8u, wb = (unsigned)(NG * EPI_MAX_TAPS * 4 * 8);
+      mbar_expect_tx(w.mbar, hb * NG + wb);
+#pragma unroll
+      for (int g = 0; g < NG; ++g) bulk_g2s(w.S + g * stride + kPadMax, hist2 + (chain * NG + g) * (int64_t)pitch, hb, w.mbar);
+      bulk_g2s(w.Wabs, Wg + (int64_t)chain * NG * EPI_MAX_TAPS * 4, wb, w.mbar);
+    }
+  }
   for (int p = lane; p < M.d; p += 32) {
     double v = theta[(int64_t)p * ld + chain];
     if (to_model_space && !Traits<FL>::kAge && p == 4) v = exp(v);  // transformParams, :136-142
     w.theta[p] = v;
   }
-  for (int i = lane; i < NG * EPI_MAX_TAPS * 4; i += 32) w.Wabs[i] = 0.0;
   __syncwarp();
 #pragma unroll
   for (int g = 0; g < NG; ++g) { lo[g] = EPI_MAX_TAPS; hi[g] = 0; }
@@ -939,8 +972,6 @@ __device__ __forceinline__ void stage_score(const DevModel &M, const ScoreSmem &
     const int g = q / KG;
     lo[g] = min(lo[g], pm.x);
     hi[g] = max(hi[g], pm.x + pm.y - 1);
-    for (int o = lane; o < pm.y; o += 32)
-      w.Wabs[(g * EPI_MAX_TAPS + pm.x + o) * 4 + (q % KG)] = __ldcs(Wg + ((int64_t)chain * NK + q) * EPI_MAX_TAPS + o);
   }
   stage_history_end<FL>(M, w.S, w.mbar, P, lane);
 }
@@ -1091,6 +1122,8 @@ k_score(const DevModel M, const PriorTerm *__restrict__ PT, int n_prior, const d
         const int j = base + 32 * half + lane;
         const int t = pad + 1 + j;
         const bool in = j >= 0 && j < P;
+        DaySlots<5> slots;
+        slots.load(M, t, dstart, j < P);
         double val[6], inc[6];
 #pragma unroll
         for (int q = 0; q < 6; ++q) {
@@ -1113,7 +1146,7 @@ k_score(const DevModel M, const PriorTerm *__restrict__ PT, int n_prior, const d
           // scored series: y.casei, o.casei, hospi = y.hospi + o.hospi, y.deadi, o.deadi
           // (profile order: ycase, yhosp, ydied, ocase, ohosp, odied)
           const double v5[5] = {val[0], val[3], val[1] + val[4], val[2], val[5]};
-          score_day_all<5>(M, ltab, t, dstart, v5, acc);
+          slots.score(M, ltab, v5, acc);
           if (t >= dstart[2] + M.d_hosp_o1 && t <= dstart[2] + M.d_hosp_o2) { ysum += val[1]; osum += val[4]; }  // :563-564
         }
       }
@@ -1131,6 +1164,8 @@ k_score(const DevModel M, const PriorTerm *__restrict__ PT, int n_prior, const d
         const int j = base + 32 * half + lane;
         const int t = pad + 1 + j;
         const bool in = j >= 0 && j < P;
+        DaySlots<2> slots;
+        slots.load(M, t, dstart, j < P);
         double v2[2];
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
@@ -1142,7 +1177,7 @@ k_score(const DevModel M, const PriorTerm *__restrict__ PT, int n_prior, const d
           carry[q] = __shfl_sync(0xffffffffu, cum, 31);
           v2[q] = (j >= 0) ? cum - prev : 0.0;  // prev is 0 for t = pad+1 (prefill)
         }
-        if (j < P) score_day_all<2>(M, ltab, t, dstart, v2, acc);
+        if (j < P) slots.score(M, ltab, v2, acc);
       }
     }
   }
