@@ -331,6 +331,7 @@ extern "C" int epi_create(const epi_model_desc *desc, const epi_data *data, int 
     cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&h->ev_stagger, cudaEventDisableTiming);
+    { const char *env = getenv("EPI_PASS2_RESTART"); h->restart = !(env && env[0] == '0'); }
     { const char *env = getenv("EPI_SPLIT_STREAMS"); h->split = (env && (env[0] == '1' || env[0] == '2')); h->split_mode = (env && env[0] == '2') ? 2 : 1; }
     for (auto &ev : h->ev) cudaEventCreate(&ev);
     rc = fill_model(h, *desc, *data);
@@ -346,7 +347,7 @@ extern "C" int epi_create(const epi_model_desc *desc, const epi_data *data, int 
 }
 
 static void free_workspace(Workspace &w) {
-  cudaFree(w.theta); cudaFree(w.aos); cudaFree(w.hist1); cudaFree(w.hist2); cudaFree(w.W); cudaFree(w.pmeta);
+  cudaFree(w.theta); cudaFree(w.aos); cudaFree(w.hist1); cudaFree(w.hist2); cudaFree(w.ckpt); cudaFree(w.W); cudaFree(w.pmeta);
   cudaFree(w.offset); cudaFree(w.pad); cudaFree(w.status); cudaFree(w.logl); cudaFree(w.logp); cudaFree(w.terms);
   cudaFree(w.series);
   w = Workspace();
@@ -403,6 +404,10 @@ int epi_ensure_workspace(epi_handle *h, Workspace &w, const DevModel &M, int64_t
   // S histories: [chain][group][pitch], pitch = days rounded up to even (16-byte aligned rows for the bulk copies)
   CUDA_OK(h, cudaMalloc(&w.hist1, sizeof(double) * (size_t)(ld * NG * ((P1 + 1) & ~1))));
   CUDA_OK(h, cudaMalloc(&w.hist2, sizeof(double) * (size_t)(ld * NG * ((P + 1) & ~1))));
+  {
+    const int NEQ = M.flavour == EPI_FLAVOUR_AGE2Q ? 10 : 4;
+    CUDA_OK(h, cudaMalloc(&w.ckpt, sizeof(double) * (size_t)(ld * NEQ * (P1 < 64 ? P1 : 64))));
+  }
   CUDA_OK(h, cudaMalloc(&w.W, sizeof(double) * (size_t)(ld * NG * EPI_MAX_TAPS * 4)));  // [chain][group][delay][4]
   CUDA_OK(h, cudaMalloc(&w.pmeta, sizeof(int2) * (size_t)(ld * NK)));
   CUDA_OK(h, cudaMalloc(&w.offset, sizeof(int) * (size_t)ld));
@@ -428,6 +433,8 @@ static EvalArgs make_args(epi_handle *h, Workspace &w, const DevModel &M, const 
   a.hist1 = w.hist1 + first * NG * (int64_t)((M.P1 + 1) & ~1);
   a.hist2 = w.hist2 + first * NG * (int64_t)((M.P + 1) & ~1);
   a.W = w.W + first * NG * EPI_MAX_TAPS * 4;
+  // (`first` is a multiple of the 32-chain checkpoint tile)
+  a.ckpt = h->restart ? w.ckpt + first * (M.flavour == EPI_FLAVOUR_AGE2Q ? 10 : 4) * (int64_t)(M.P1 < 64 ? M.P1 : 64) : nullptr;
   a.pmeta = w.pmeta + first * NK;
   a.offset = w.offset + first; a.pad = w.pad + first;
   a.status = (d_status ? d_status : w.status) + first;

@@ -16,7 +16,8 @@ struct Workspace {
   int64_t cap = 0, ld = 0;
   int P = 0, P1 = 0;
   double *theta = nullptr, *aos = nullptr;    // staged theta: SoA d x ld, and the AoS landing buffer
-  double *hist1 = nullptr, *hist2 = nullptr;  // S histories, [tile][day][group][32]
+  double *hist1 = nullptr, *hist2 = nullptr;  // S histories, [chain][group][pitch]
+  double *ckpt = nullptr;                     // pass-1 checkpoints, [chain][state][ckpt days]
   double *W = nullptr;                        // latency profiles, [chain][NK][EPI_MAX_TAPS]
   int2 *pmeta = nullptr;                      // (dmin, n) per profile
   int *offset = nullptr, *pad = nullptr, *status = nullptr;
@@ -42,6 +43,7 @@ struct epi_handle {
   cudaStream_t stream = nullptr, stream2 = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_stagger = nullptr;
   int split_mode = 1;
+  bool restart = true;  // pass 2 resumes from the pass-1 checkpoint (EPI_PASS2_RESTART=0: re-integrate everything)
   bool split = false;  // EPI_SPLIT_STREAMS=1: run the two halves of a large batch on two streams (measured slower: 6.41 vs 6.03 ms)
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   bool timing = false;

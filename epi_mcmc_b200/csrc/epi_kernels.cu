@@ -28,6 +28,15 @@ namespace epi {
 // of the score kernel's stall samples).
 __host__ __device__ constexpr int hist_pitch(int ndays) { return (ndays + 1) & ~1; }
 
+// Pass-2 restart.  Both passes use the same fixed-step scheme and pass 2 has beta0 until its first
+// breakpoint, so its first D = floor(min breakpoint) - t0 days are BIT-identical to pass 1
+// (SURVEY.md §8d allows the restart provided the reduced step count is reported: bench.py does).
+// Pass 1 therefore checkpoints the full state at every day boundary — tiled so that a warp's store
+// of one state is one contiguous 256 B line, ckpt[((tile*cdays + d)*NEQ + i)*32 + lane]; a
+// chain-major layout made pass 1 LSU bound, 0.24 -> 1.14 ms — and pass 2 resumes from day D
+// instead of re-integrating it.
+__host__ __device__ constexpr int ckpt_days(int P1) { return P1 < 64 ? P1 : 64; }
+
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *mbar, unsigned count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(mbar)), "r"(count));
@@ -304,7 +313,7 @@ template <int FL, bool PASS2>
 __global__ void __maxnreg__(144)
 k_ode(const DevModel M, const double *__restrict__ theta, int64_t ld, int64_t n,
       const int *__restrict__ offset, const int *__restrict__ padv, const double *__restrict__ hist1,
-      double *__restrict__ hist_out) {
+      double *__restrict__ hist_out, double *__restrict__ ckpt) {
   constexpr int NEQ = Traits<FL>::NEQ, NG = Traits<FL>::NG;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -348,13 +357,42 @@ k_ode(const DevModel M, const double *__restrict__ theta, int64_t ld, int64_t n,
     t0 = padv[i] + 1;
     nbp = breakpoints<FL>(M, th, ld, (double)off, bp);
   }
-  Seg sg = select_segment<FL>(M, th, ld, bp, nbp, (double)t0, &tcut);
+  const int cdays = ckpt_days(M.P1);
+  // element (d, q) of this chain: ck[(d * NEQ + q) * kTile]
+  double *ck = ckpt ? ckpt + ((i / kTile) * (int64_t)cdays * NEQ) * kTile + (i % kTile) : nullptr;
+  int d0 = 0;  // last day already known
+  if constexpr (PASS2) {
+    if (ck) {
+      double minbp = INFINITY;
+      for (int k = 0; k < nbp; ++k) minbp = fmin(minbp, bp[k]);
+      const double dd = floor(minbp) - (double)t0;
+      d0 = dd > 0 ? (int)fmin(dd, (double)min(cdays - 1, ndays - 1)) : 0;
+      if (d0 > 0) {
+        const int pitch1 = hist_pitch(M.P1);
+        const double *in = hist1 + (i * NG) * (int64_t)pitch1;
+        for (int d = 0; d <= d0; ++d)
+#pragma unroll
+          for (int g = 0; g < NG; ++g) out[g * pitch + d] = in[g * pitch1 + d];
+#pragma unroll
+        for (int q = 0; q < NEQ; ++q) y[q] = ck[((int64_t)d0 * NEQ + q) * kTile];
+      }
+    }
+  }
+  Seg sg = select_segment<FL>(M, th, ld, bp, nbp, (double)(t0 + d0), &tcut);
 
   const int m = M.m;
   const double h = 1.0 / (double)m;
-  out[0] = y[0];
-  if constexpr (NG == 2) out[pitch] = y[5];
-  for (int d = 1; d < ndays; ++d) {
+  if (d0 == 0) {
+    out[0] = y[0];
+    if constexpr (NG == 2) out[pitch] = y[5];
+  }
+  if constexpr (!PASS2) {
+    if (ck) {
+#pragma unroll
+      for (int q = 0; q < NEQ; ++q) ck[q * kTile] = y[q];
+    }
+  }
+  for (int d = d0 + 1; d < ndays; ++d) {
     const double tday = (double)(t0 + d - 1);
     for (int s = 0; s < m; ++s) {
       const double a = tday + (double)s * h;
@@ -372,6 +410,12 @@ k_ode(const DevModel M, const double *__restrict__ theta, int64_t ld, int64_t n,
     }
     out[d] = y[0];
     if constexpr (NG == 2) out[pitch + d] = y[5];
+    if constexpr (!PASS2) {
+      if (ck && d < cdays) {
+#pragma unroll
+        for (int q = 0; q < NEQ; ++q) ck[((int64_t)d * NEQ + q) * kTile] = y[q];
+      }
+    }
   }
 }
 
@@ -490,7 +534,8 @@ __device__ __noinline__ Seg2 select_segment_age2(const double *__restrict__ th, 
 template <bool PASS2>
 __global__ void __maxnreg__(128)
 k_ode_age2(const DevModel M, const double *__restrict__ theta, int64_t ld, int64_t n, const int *__restrict__ offset,
-           const int *__restrict__ padv, const double *__restrict__ hist1, double *__restrict__ hist_out) {
+           const int *__restrict__ padv, const double *__restrict__ hist1, double *__restrict__ hist_out,
+           double *__restrict__ ckpt) {
   constexpr int FL = EPI_FLAVOUR_AGE2Q;
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t i = tid >> 1;  // chain
@@ -523,12 +568,35 @@ k_ode_age2(const DevModel M, const double *__restrict__ theta, int64_t ld, int64
     t0 = padv[i] + 1;
     nbp = breakpoints<FL>(M, th, ld, (double)off, bp);
   }
-  Seg2 sg = select_segment_age2(th, ld, bp, nbp, (double)t0, g, &tcut);
+  const int cdays = ckpt_days(M.P1);
+  double *ck = ckpt ? ckpt + ((i / kTile) * (int64_t)cdays * 10 + g * 5) * kTile + (i % kTile) : nullptr;
+  int d0 = 0;
+  if constexpr (PASS2) {
+    if (ck) {
+      double minbp = INFINITY;
+      for (int k = 0; k < nbp; ++k) minbp = fmin(minbp, bp[k]);
+      const double dd = floor(minbp) - (double)t0;
+      d0 = dd > 0 ? (int)fmin(dd, (double)min(cdays - 1, ndays - 1)) : 0;
+      if (d0 > 0) {
+        const double *in = hist1 + (i * 2 + g) * (int64_t)hist_pitch(M.P1);
+        for (int d = 0; d <= d0; ++d) out[d] = in[d];
+#pragma unroll
+        for (int q = 0; q < 5; ++q) y[q] = ck[((int64_t)d0 * 10 + q) * kTile];
+      }
+    }
+  }
+  Seg2 sg = select_segment_age2(th, ld, bp, nbp, (double)(t0 + d0), g, &tcut);
 
   const int m = M.m;
   const double h = 1.0 / (double)m, a1 = M.a1, gamma = M.gamma;
-  out[0] = y[0];
-  for (int d = 1; d < ndays; ++d) {
+  if (d0 == 0) out[0] = y[0];
+  if constexpr (!PASS2) {
+    if (ck) {
+#pragma unroll
+      for (int q = 0; q < 5; ++q) ck[q * kTile] = y[q];
+    }
+  }
+  for (int d = d0 + 1; d < ndays; ++d) {
     const double tday = (double)(t0 + d - 1);
     for (int s = 0; s < m; ++s) {
       const double a = tday + (double)s * h;
@@ -545,6 +613,12 @@ k_ode_age2(const DevModel M, const double *__restrict__ theta, int64_t ld, int64
       rk4_piece_age2(a1, gamma, sg, y, pa, b, invN, Ngrp, nb, pairmask, even_lane);
     }
     out[d] = y[0];
+    if constexpr (!PASS2) {
+      if (ck && d < cdays) {
+#pragma unroll
+        for (int q = 0; q < 5; ++q) ck[((int64_t)d * 10 + q) * kTile] = y[q];
+      }
+    }
   }
 }
 
@@ -1401,15 +1475,15 @@ static cudaError_t launch_eval_fl(const EvalArgs &a) {
   if (!n_sm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
   const bool use_pair = Traits<FL>::kAge && n <= (int64_t)n_sm * 256;
   if (use_pair) {
-    if constexpr (Traits<FL>::kAge) k_ode_age2<false><<<pair_blocks, 64, 0, s>>>(M, a.theta, a.ld, n, nullptr, nullptr, nullptr, a.hist1);
-  } else k_ode<FL, false><<<ode_blocks, 32, 0, s>>>(M, a.theta, a.ld, n, nullptr, nullptr, nullptr, a.hist1);
+    if constexpr (Traits<FL>::kAge) k_ode_age2<false><<<pair_blocks, 64, 0, s>>>(M, a.theta, a.ld, n, nullptr, nullptr, nullptr, a.hist1, a.ckpt);
+  } else k_ode<FL, false><<<ode_blocks, 32, 0, s>>>(M, a.theta, a.ld, n, nullptr, nullptr, nullptr, a.hist1, a.ckpt);
   if (a.ev) cudaEventRecord(a.ev[1], s);
   k_mid<FL><<<warp_blocks, 128, smem_mid, s>>>(M, a.theta, a.ld, n, a.hist1, a.offset, a.pad, a.status, a.W, a.pmeta, a.model_space);
   if (a.ev) cudaEventRecord(a.ev[2], s);
   if (a.ev_after_mid) cudaEventRecord(a.ev_after_mid, s);
   if (use_pair) {
-    if constexpr (Traits<FL>::kAge) k_ode_age2<true><<<pair_blocks, 64, 0, s>>>(M, a.theta, a.ld, n, a.offset, a.pad, a.hist1, a.hist2);
-  } else k_ode<FL, true><<<ode_blocks, 32, 0, s>>>(M, a.theta, a.ld, n, a.offset, a.pad, a.hist1, a.hist2);
+    if constexpr (Traits<FL>::kAge) k_ode_age2<true><<<pair_blocks, 64, 0, s>>>(M, a.theta, a.ld, n, a.offset, a.pad, a.hist1, a.hist2, a.ckpt);
+  } else k_ode<FL, true><<<ode_blocks, 32, 0, s>>>(M, a.theta, a.ld, n, a.offset, a.pad, a.hist1, a.hist2, a.ckpt);
   if (a.ev) cudaEventRecord(a.ev[3], s);
   if (a.series_out) {
     k_series<FL><<<warp_blocks, 128, smem_score, s>>>(M, a.theta, a.ld, n, a.hist2, a.offset, a.pad, a.W, a.pmeta,

@@ -15,6 +15,7 @@ struct EvalArgs {
   int64_t ld, n;
   int model_space;      // theta already through transformParams (calculateModel callers)
   double *hist1, *hist2, *W;
+  double *ckpt;  // pass-1 day-boundary states for the pass-2 restart (null: re-integrate from day 0)
   int2 *pmeta;
   int *offset, *pad, *status;
   double *logl, *logp, *terms;  // device, any may be null
