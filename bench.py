@@ -31,8 +31,11 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 # DRAM bytes per launch of each kernel (read + write) from the committed ncu --set full capture of
-# this exact workload (profiles/r1_v7_ncu_full.txt); only reported when the run matches that workload
-NCU_TRAFFIC = {}
+# this exact workload (profiles/r1_v10_ncu_full.txt); only reported when the run matches that workload
+NCU_TRAFFIC = {"ode_pass1": 344.6e6, "profiles_threshold": 300.7e6, "ode_pass2": 483.2e6, "score": 616.2e6}
+# sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active of the same capture
+NCU_FP64_PIPE_PCT = {"ode_pass1": 60.4, "profiles_threshold": 55.5, "ode_pass2": 56.0, "score": 26.8}
+NCU_WORKLOAD = ("A300", 65536, 4)
 
 METRIC = "log_posterior_evals_per_s"
 UNIT = "evals/s"
@@ -200,8 +203,10 @@ def run_reference(args):
 
 
 def workload_name(args, period):
-    return (f"{args.workload}: age-structured model-age-groups2q, synthetic {period}-day series, "
-            f"{args.chains} chains per GPU, RK4 m={args.substeps} (BASELINE.json configs[2])")
+    what = {"A": "age-structured model-age-groups2q (BASELINE.json configs[2])",
+            "S": "simple SEIR model-simple-ode-drj-cmp (BASELINE.json configs[3])",
+            "N": "simple SEIR + effective population size Ne (BASELINE.json configs[1])"}.get(args.workload[0], args.workload)
+    return f"{args.workload}: {what}, synthetic {period}-day series, {args.chains} chains per GPU, RK4 m={args.substeps}"
 
 
 def emit(line: dict):
@@ -327,13 +332,15 @@ def main():
     knames = ["ode_pass1", "profiles_threshold", "ode_pass2", "score"]
     kernel_fn = {"ode_pass1": "k_ode<pass1>", "profiles_threshold": "k_mid", "ode_pass2": "k_ode<pass2>", "score": "k_score"}
     per_kernel = {}
+    ncu_match = (args.workload, n, args.substeps) == NCU_WORKLOAD
     for k, msk in zip(knames, kms):
         tf = fa["per_kernel_executed"][k] * n / (float(msk) * 1e-3) / 1e12
         per_kernel[k] = {"kernel": kernel_fn[k], "ms": float(msk),
                          "algorithmic_flop_per_launch": fa["per_kernel_executed"][k] * n,
                          "algorithmic_flop_per_launch_without_restart": fa["per_kernel"][k] * n,
                          "achieved": tf, "frac": tf / peak_tf if peak_tf else None,
-                         "traffic": NCU_TRAFFIC.get(k)}
+                         "traffic": NCU_TRAFFIC.get(k) if ncu_match else None,
+                         "fp64_pipe_pct_ncu": NCU_FP64_PIPE_PCT.get(k) if ncu_match else None}
     dom = knames[int(np.argmax(kms))]
     step_ms = ms / args.steps
     whole_tf = fa["total_executed"] * n / (step_ms * 1e-3) / 1e12
@@ -360,7 +367,7 @@ def main():
                                     "nominal 37.2 TFLOP/s = 148 SM x 64 DFMA/clk x 2 x 1.965 GHz)",
                      "algorithmic_flop_per_launch": per_kernel[dom]["algorithmic_flop_per_launch"],
                      "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, "
-                                       "profiles/r1_v7_ncu_full.txt (65,536 chains, A300)"},
+                                       "profiles/r1_v10_ncu_full.txt (65,536 chains, A300)"},
         "roofline_all": per_kernel,
         "f_alg": {"per_eval": fa["total"], "per_eval_with_pass2_restart": fa["total_executed"],
                   "pass2_restart_days_mean": d_mean, "ode_share": fa["ode"] / fa["total"],
