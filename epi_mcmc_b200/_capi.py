@@ -14,10 +14,11 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "csrc", "libepimcmc.so")
 
-FLAVOUR_SIMPLE, FLAVOUR_NE, FLAVOUR_AGE2Q = 0, 1, 2
-FLAVOURS = {"simple": FLAVOUR_SIMPLE, "ne": FLAVOUR_NE, "age2q": FLAVOUR_AGE2Q}
-N_PARAMS = {FLAVOUR_SIMPLE: 8, FLAVOUR_NE: 9, FLAVOUR_AGE2Q: 45}
-N_SERIES = {FLAVOUR_SIMPLE: 3, FLAVOUR_NE: 3, FLAVOUR_AGE2Q: 8}
+FLAVOUR_SIMPLE, FLAVOUR_NE, FLAVOUR_AGE2Q, FLAVOUR_AGE2I = 0, 1, 2, 3
+FLAVOURS = {"simple": FLAVOUR_SIMPLE, "ne": FLAVOUR_NE, "age2q": FLAVOUR_AGE2Q, "age2i": FLAVOUR_AGE2I}
+AGE_FLAVOURS = (FLAVOUR_AGE2Q, FLAVOUR_AGE2I)
+N_PARAMS = {FLAVOUR_SIMPLE: 8, FLAVOUR_NE: 9, FLAVOUR_AGE2Q: 45, FLAVOUR_AGE2I: 36}
+N_SERIES = {FLAVOUR_SIMPLE: 3, FLAVOUR_NE: 3, FLAVOUR_AGE2Q: 8, FLAVOUR_AGE2I: 8}
 MAX_PARAMS = 48
 INVALID_DATA_OFFSET = 10000
 

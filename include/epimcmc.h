@@ -46,11 +46,18 @@ extern "C" {
 #define EPI_FLAVOUR_NE 1
 /* two-age-group SEEIR, 45 parameters (R/models/model-age-groups2q.R + model-agen.cpp) */
 #define EPI_FLAVOUR_AGE2Q 2
+/* two-age-group SEEIR, earlier generation: 36 parameters, 8-breakpoint schedule,
+ * pass 1 over the whole period (R/models/model-age-groups2i.R + model-agef.cpp,
+ * analyses/be/age/settings.R)                                                 */
+#define EPI_FLAVOUR_AGE2I 3
 
 #define EPI_MAX_PARAMS 48
 /* widest latency profile supported: in-box maximum is 6*9+1 = 55 taps
  * (R/models/model-age-groups2q.R:22-23,656) */
 #define EPI_MAX_TAPS 64
+/* largest padding (= longest delay + 1) supported: age-2q/simple 64, age-2i 80 (its death
+ * latency box reaches 50 + 3*9 = 77 days, R/models/model-age-groups2i.R:580-582) */
+#define EPI_MAX_PADDING 80
 /* InvalidDataOffset, R/models/model-age-groups2q.R:5 */
 #define EPI_INVALID_DATA_OFFSET 10000
 
@@ -72,7 +79,8 @@ extern "C" {
 #define EPI_ST_NA 2
 /* theta lies outside the df_params box (R/models/model-age-groups2q.R:637-663) */
 #define EPI_ST_OUT_OF_BOX 8
-/* a latency profile would need more than EPI_MAX_TAPS taps: result is NaN     */
+/* a latency profile would need more than EPI_MAX_TAPS taps (or a padding beyond the
+ * flavour's limit, see EPI_MAX_PADDING): result is NaN                        */
 #define EPI_ST_UNSUPPORTED 16
 
 /* ---- theta layouts -------------------------------------------------------- */
@@ -117,6 +125,10 @@ typedef struct epi_model_desc {
  *   dmort_last, y_ifr/o_ifr/y_hr/o_hr/g/gtrimp[n_rate], case_nbinom_size1,
  *   case_nbinom_sizey2, case_nbinom_sizeo2, hosp_nbinom_size1, hosp_nbinom_size2,
  *   mort_nbinom_size, hosp_last7
+ * age-2i (R/models/model-age-groups2i.R, analyses/be/age/settings.R:29-33): as age-2q minus
+ *   g, gtrimp, o_wdmorti, d6, d8, d_reliable_hosp, d_hosp_o1/o2, hosp_nbinom_size1/2, hosp_last7;
+ *   the settings' case_nbinom_size2 goes into BOTH case_nbinom_sizey2 and case_nbinom_sizeo2,
+ *   hosp_nbinom_size and mort_nbinom_size are the scalar sizes of :496-523
  */
 typedef struct epi_data {
   double N, y_N, o_N;
@@ -170,8 +182,8 @@ int epi_eval_device(epi_handle *h, const double *d_theta_soa, int64_t n,
 /* Per-evaluation detail for parity checks: offset[n] = state$offset
  * (data_offset or 10000), padding[n] = state$padding, terms[n*8] = the
  * likelihood terms in reference order (age: y.loglC, o.loglC, loglH,
- * loglHRatio, y.loglD, o.loglD; simple: loglLD, loglH, loglD), each EXCLUDING
- * nothing (full dnbinom values).  HOST buffers, any may be NULL.              */
+ * loglHRatio, y.loglD, o.loglD — age-2i has no ratio term, its slot 3 is 0;
+ * simple: loglLD, loglH, loglD), each the full dnbinom sum.  HOST buffers, any may be NULL.              */
 int epi_eval_detail(epi_handle *h, const double *theta, int64_t n, int layout,
                     int32_t *offset, int32_t *padding, double *terms);
 

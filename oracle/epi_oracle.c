@@ -446,6 +446,24 @@ void oracle_derivs_age(const double *parms45, double t, const double *y, double 
   derivs_age(&p, SEG_LITERAL, t, y, ydot);
 }
 
+/* same for the 8-breakpoint schedule of R/models/model-agef.cpp:7-43,66-87 (parms[37]):
+ * segments 0..5 linear towards the next breakpoint, 6 and 7 hold */
+void oracle_derivs_agef(const double *parms37, double t, const double *y, double *ydot) {
+  rhs_t p;
+  memset(&p, 0, sizeof p);
+  p.Ny = parms37[0]; p.No = parms37[1]; p.a1 = parms37[2]; p.a2 = parms37[3]; p.gamma = parms37[4];
+  p.s.nbp = 8;
+  static const int kind[8] = {1, 1, 1, 1, 1, 1, 0, 0};
+  static const int tidx[8] = {5, 6, 7, 17, 21, 25, 29, 33};
+  for (int k = 0; k < 8; ++k) {
+    p.s.kind[k] = kind[k];
+    p.s.t[k] = parms37[tidx[k]];
+    int b = (k < 3) ? 8 + 3 * k : tidx[k] + 1;
+    p.by[k] = parms37[b]; p.bo[k] = parms37[b + 1]; p.byo[k] = parms37[b + 2];
+  }
+  derivs_age(&p, SEG_LITERAL, t, y, ydot);
+}
+
 /* ------------------------------------------------------------ helpers ----- */
 
 static double *vec(int n, double fill) { /* 1-based vector of length n */
@@ -845,6 +863,285 @@ static void age_df_params(const epi_data *D, double *mn, double *mx, double *ini
   for (int i = 0; i < 45; ++i) { mn[i] = mn_[i]; mx[i] = mx_[i]; init[i] = i_[i]; }
 }
 
+/* ------------------------------------------------------------ age-2i ------ */
+
+/* three-slice rate map of R/models/model-age-groups2i.R:214-227 etc.: like rate_map(), but
+ * the InvalidDataOffset branch multiplies by an explicit scalar (`:224`: ycase_rate *
+ * y.died_rate, without the pmin of the valid branch), and a rate vector may carry a scalar
+ * factor applied to s2i FIRST (`:236`: s2i * yhosp_rate * y.hr[...] is left-associative). */
+static void rate_map2i(double *dst, const double *s2i, int pad, int P, int valid, double t1d, double pre,
+                       const double *rate, int nr, double pre_invalid, double rate_invalid) {
+  if (valid) {
+    int t1 = (int)t1d;
+    int t2 = (pad + P < t1 + nr - 1) ? pad + P : t1 + nr - 1;
+    if (t1 > pad && t2 > t1) {
+      for (int t = pad + 1; t <= t1; ++t) dst[t] = s2i[t - pad] * pre * rate[1];
+      for (int t = t1; t <= t2; ++t) dst[t] = s2i[t - pad] * pre * rate[t - t1 + 1];
+      for (int t = t2; t <= pad + P; ++t) dst[t] = s2i[t - pad] * pre * rate[nr];
+    }
+  } else {
+    for (int t = pad + 1; t <= pad + P; ++t) dst[t] = s2i[t - pad] * pre_invalid * rate_invalid;
+  }
+}
+
+/* calculateModel(params, period): R/models/model-age-groups2i.R:50-316 (params 1-based, 36) */
+static int age2i_calculate_model(const epi_data *D, const double *params, int period, int m,
+                                 age_state_t *st) {
+  memset(st, 0, sizeof *st);
+  const double y_N = D->y_N, o_N = D->o_N;
+  const double y_died_rate = D->y_ifr[0], o_died_rate = D->o_ifr[0]; /* :11-12 */
+  const double a1 = 1 / TINC1, a2 = 1 / TINC2, gamma = oracle_age_gamma();
+
+  /* :52-93 */
+  double betay[8], betao[8], betayo[8];
+  betay[0] = params[1]; betao[0] = params[2]; betayo[0] = params[3];
+  betay[1] = params[4]; betao[1] = params[5]; betayo[1] = params[6];
+  betay[2] = params[7]; betao[2] = params[8]; betayo[2] = params[9];
+  const double ycase_rate = params[10], ycase_latency = params[11], yhosp_rate = params[12],
+               yhosp_latency = params[13], ydied_latency = params[14], ocase_rate = params[15],
+               ocase_latency = params[16], ohosp_rate = params[17], ohosp_latency = params[18],
+               odied_latency = params[19], t0_morts = params[20], t0o = params[21], CLsd = params[22],
+               HLsd = params[23], DLsd = params[24], t3o = params[25], t4o = params[26], t6o = params[30];
+  betay[3] = betay[2]; betao[3] = betao[2]; betayo[3] = betayo[2];
+  betay[4] = params[27]; betao[4] = params[28]; betayo[4] = params[29];
+  betay[5] = betay[4]; betao[5] = betao[4]; betayo[5] = betayo[4];
+  betay[6] = params[31]; betao[6] = params[32]; betayo[6] = params[33];
+  betay[7] = params[34] * betay[6]; betayo[7] = params[35] * betayo[6]; betao[7] = params[36] * betao[6];
+
+  /* :96-101 */
+  profile_t ycase, ocase, yhosp, ohosp, ydied, odied;
+  if (calc_gamma_profile(ycase_latency, CLsd, &ycase) || calc_gamma_profile(ocase_latency, CLsd, &ocase) ||
+      calc_gamma_profile(yhosp_latency, HLsd, &yhosp) || calc_gamma_profile(ohosp_latency, HLsd, &ohosp) ||
+      calc_gamma_profile(ydied_latency, DLsd, &ydied) || calc_gamma_profile(odied_latency, DLsd, &odied))
+    return -1;
+
+  /* :103-104 */
+  int padding = -ycase.kbegin;
+  if (-ydied.kbegin > padding) padding = -ydied.kbegin;
+  if (-ocase.kbegin > padding) padding = -ocase.kbegin;
+  if (-odied.kbegin > padding) padding = -odied.kbegin;
+  padding += 1;
+
+  const int P = period, T = padding + period;
+  st->pad = padding; st->T = T; st->P = P;
+  st->yS = vec(T, y_N - INITIAL);   /* :108 */
+  st->oS = vec(T, o_N);             /* :117 */
+  st->ycasei = vec(T, 0); st->ocasei = vec(T, 0);
+  st->yhospi = vec(T, 0); st->ohospi = vec(T, 0);
+  st->ydeadi = vec(T, 0); st->odeadi = vec(T, 0);
+
+  /* :133-143 */
+  rhs_t rp;
+  memset(&rp, 0, sizeof rp);
+  rp.flavour = EPI_FLAVOUR_AGE2I;
+  rp.Ny = y_N; rp.No = o_N; rp.a1 = a1; rp.a2 = a2; rp.gamma = gamma;
+  rp.s.nbp = 8;
+  static const int kind[8] = {1, 1, 1, 1, 1, 1, 0, 0}; /* model-agef.cpp:66-87 */
+  for (int k = 0; k < 8; ++k) {
+    rp.s.kind[k] = kind[k];
+    rp.s.t[k] = 1E10;
+    rp.by[k] = betay[k]; rp.bo[k] = betao[k]; rp.byo[k] = betayo[k];
+  }
+  const double Y[10] = {y_N - INITIAL, INITIAL, 0, 0, 0, o_N, 0, 0, 0, 0};
+
+  /* pass 1 over the WHOLE period, :148-163 */
+  double *out = (double *)malloc(sizeof(double) * 10 * (size_t)P);
+  ode_rk4(&rp, 10, Y, padding + 1, P, m, out);
+  for (int i = 1; i <= P; ++i) {
+    st->yS[padding + i] = out[(i - 1) * 10 + 0];
+    st->oS[padding + i] = out[(i - 1) * 10 + 5];
+  }
+  double *s2 = vec(P, 0), *s2b = vec(P, 0);
+  convolute(st->yS, T, padding + 1, padding + P, &ydied, s2);
+  convolute(st->oS, T, padding + 1, padding + P, &odied, s2b);
+  double data_offset = EPI_INVALID_DATA_OFFSET; /* :165 */
+  int lds1 = 0;
+  for (int i = 1; i <= P; ++i) { /* which(state$died > t0_morts), :167 (NA on 1..padding) */
+    double died = (y_N - s2[i]) * y_died_rate + (o_N - s2b[i]) * o_died_rate;
+    if (died > t0_morts) { lds1 = padding + i; break; }
+  }
+  free(s2b);
+
+  const int lo = D->lockdown_offset, ltp = D->lockdown_transition_period;
+  if (lds1 > 0) { /* :168-197 */
+    data_offset = lds1 - lo;
+    double t2 = data_offset + lo + ltp;
+    double t3 = t2 + t3o;
+    double t4 = t3 + t4o;
+    double t5 = data_offset + D->d5;
+    double t6 = t5 + t6o;
+    double t7 = data_offset + D->d7;
+    rp.s.t[0] = data_offset + lo + t0o;
+    rp.s.t[1] = data_offset + lo + fmax(t0o, 0);
+    rp.s.t[2] = t2; rp.s.t[3] = t3; rp.s.t[4] = t4; rp.s.t[5] = t5; rp.s.t[6] = t6; rp.s.t[7] = t7;
+    ode_rk4(&rp, 10, Y, padding + 1, P, m, out);
+  }
+  /* :199-210 */
+  st->full = (double *)malloc(sizeof(double) * 10 * (size_t)P);
+  memcpy(st->full, out, sizeof(double) * 10 * (size_t)P);
+  for (int i = 1; i <= P; ++i) {
+    st->yS[padding + i] = out[(i - 1) * 10 + 0];
+    st->oS[padding + i] = out[(i - 1) * 10 + 5];
+  }
+  free(out);
+
+  const int nr = D->n_rate;
+  double *ycr = vec(nr, 0), *ocr = vec(nr, 0);
+  for (int i = 1; i <= nr; ++i) {
+    ycr[i] = pmin_(1, ycase_rate * D->y_ifr[i - 1]); /* :219-221 */
+    ocr[i] = pmin_(1, ocase_rate * D->o_ifr[i - 1]); /* :267-269 */
+  }
+  const int valid = data_offset != EPI_INVALID_DATA_OFFSET;
+  double *s2i = vec(P, 0);
+  struct {
+    const double *S; double Ng; const profile_t *prof; double t1; double pre; const double *rate;
+    double pre_inv, rate_inv; double *dst;
+  } ser[6] = {
+      /* :212-226 */ {st->yS, y_N, &ycase, data_offset + nearbyint(-ydied_latency + ycase_latency), 1.0, ycr,
+                      ycase_rate, y_died_rate, st->ycasei},
+      /* :229-242 */ {st->yS, y_N, &yhosp, data_offset + nearbyint(-ydied_latency + yhosp_latency), yhosp_rate,
+                      D->y_hr - 1, yhosp_rate, D->y_hr[0], st->yhospi},
+      /* :245-257 */ {st->yS, y_N, &ydied, data_offset, 1.0, D->y_ifr - 1, 1.0, y_died_rate, st->ydeadi},
+      /* :260-273 */ {st->oS, o_N, &ocase, data_offset + nearbyint(-ydied_latency + ocase_latency), 1.0, ocr,
+                      ocase_rate, o_died_rate, st->ocasei},
+      /* :276-289 */ {st->oS, o_N, &ohosp, data_offset + nearbyint(-ydied_latency + ohosp_latency), ohosp_rate,
+                      D->o_hr - 1, ohosp_rate, D->o_hr[0], st->ohospi},
+      /* :291-304 */ {st->oS, o_N, &odied, data_offset, 1.0, D->o_ifr - 1, 1.0, o_died_rate, st->odeadi},
+  };
+  for (int q = 0; q < 6; ++q) {
+    convolute(ser[q].S, T, padding + 1, padding + P, ser[q].prof, s2);
+    for (int i = 1; i <= P; ++i) s2[i] = ser[q].Ng - s2[i];
+    s2i[1] = s2[1];
+    for (int i = 2; i <= P; ++i) s2i[i] = s2[i] - s2[i - 1];
+    rate_map2i(ser[q].dst, s2i, padding, P, valid, ser[q].t1, ser[q].pre, ser[q].rate, nr, ser[q].pre_inv,
+               ser[q].rate_inv);
+  }
+  free(s2); free(s2i); free(ycr); free(ocr);
+  st->offset = (int)data_offset;
+  return 0;
+}
+
+/* calclogp(params): R/models/model-age-groups2i.R:362-438 (params 1-based) */
+static double age2i_calclogp(const epi_data *D, const double *params) {
+  const double gamma = oracle_age_gamma();
+  const double betay0 = params[1], betao0 = params[2], betayo0 = params[3], betay1 = params[4],
+               betao1 = params[5], betayo1 = params[6], betay2 = params[7], betao2 = params[8],
+               betayo2 = params[9], ydied_latency = params[14], odied_latency = params[19],
+               t0o = params[21], CLsd = params[22], HLsd = params[23], DLsd = params[24],
+               t3o = params[25], t4o = params[26], betay4 = params[27], betao4 = params[28],
+               betayo4 = params[29], t6o = params[30], betay6 = params[31], betao6 = params[32],
+               betayo6 = params[33];
+  const double betay3 = betay2, betao3 = betao2, betayo3 = betayo2;
+  const double betay7 = params[34] * betay6, betayo7 = params[35] * betayo6, betao7 = params[36] * betao6;
+  const double lo = D->lockdown_offset, ltp = D->lockdown_transition_period;
+  double lp = 0;
+  lp = lp + oracle_dnorm_log(t0o, 0, 10);
+  lp = lp + oracle_dnorm_log(lo + ltp + t3o, D->d3, 10);
+  lp = lp + oracle_dnorm_log(lo + ltp + t3o + t4o, D->d4, 10);
+  lp = lp + oracle_dnorm_log(t6o, G_CONST, 3);
+  lp = lp + oracle_dnorm_log(betay0 - betay1, 0, 2 * gamma);
+  lp = lp + oracle_dnorm_log(betao0 - betao1, 0, 2 * gamma);
+  lp = lp + oracle_dnorm_log(betayo0 - betayo1, 0, 2 * gamma);
+  lp = lp + oracle_dnorm_log(betay1 - betay2, 0, 2 * gamma);
+  lp = lp + oracle_dnorm_log(betao1 - betao2, 0, 2 * gamma);
+  lp = lp + oracle_dnorm_log(betayo1 - betayo2, 0, 2 * gamma);
+  lp = lp + oracle_dnorm_log(betay3 - betay4, 0, 0.5 * gamma);
+  lp = lp + oracle_dnorm_log(betao3 - betao4, 0, 0.5 * gamma);
+  lp = lp + oracle_dnorm_log(betayo3 - betayo4, 0, 0.5 * gamma);
+  lp = lp + oracle_dnorm_log(CLsd, 5, 1);
+  lp = lp + oracle_dnorm_log(HLsd, 5, 1);
+  lp = lp + oracle_dnorm_log(DLsd, 5, 1);
+  lp = lp + oracle_dnorm_log(ydied_latency, 21, 4);
+  lp = lp + oracle_dnorm_log(odied_latency, 21, 4);
+  lp = lp + oracle_dnorm_log(betay6, 0.6, 0.2);
+  lp = lp + oracle_dnorm_log(betao6, 0.22, 0.2);
+  lp = lp + oracle_dnorm_log(betayo6, 0.26, 0.2);
+  lp = lp + oracle_dnorm_log(betay7, 0.85, 0.2);
+  lp = lp + oracle_dnorm_log(betao7, 0.19, 0.05);
+  lp = lp + oracle_dnorm_log(betayo7, 0.02, 0.02);
+  return lp;
+}
+
+/* calclogl(params, x): R/models/model-age-groups2i.R:442-536.  terms[0..5] =
+ * y.loglC, o.loglC, loglH, 0 (no ratio term in this generation), y.loglD, o.loglD */
+static double age2i_calclogl(const epi_data *D, const double *params, int period, int m,
+                             double *terms, int *offset_out, int *pad_out, int *status) {
+  age_state_t st;
+  if (age2i_calculate_model(D, params, period, m, &st)) {
+    *status |= EPI_ST_UNSUPPORTED;
+    for (int i = 0; i < 6; ++i) terms[i] = NA_REAL;
+    *offset_out = 0; *pad_out = 0;
+    return NA_REAL;
+  }
+  *offset_out = st.offset;
+  *pad_out = st.pad;
+  int offset = st.offset;
+  if (offset == EPI_INVALID_DATA_OFFSET) { /* :445-446 */
+    offset = 1;
+    *status |= EPI_ST_INVALID_OFFSET;
+  }
+  const int T = st.T;
+  int dstart, dend;
+  const int r = D->d_reliable_cases, nc = D->n_dcasei;
+  double one[2];
+
+  /* cases, :449-478 */
+  window(offset, nc, T, &dstart, &dend);
+  const double *yx = D->y_dcasei - 1, *ox = D->o_dcasei - 1;
+  one[1] = D->case_nbinom_size1;
+  double yC = sum_dnbinom(yx, nc, 1, r - 1, st.ycasei, T, dstart, dstart + r, 0.1, one, 1);
+  double oC = sum_dnbinom(ox, nc, 1, r - 1, st.ocasei, T, dstart, dstart + r, 0.1, one, 1);
+  one[1] = D->case_nbinom_sizey2; /* case_nbinom_size2 */
+  yC = yC + sum_dnbinom(yx, nc, r, nc, st.ycasei, T, dstart + r + 1, dend, 0.1, one, 1);
+  one[1] = D->case_nbinom_sizeo2; /* case_nbinom_size2 */
+  oC = oC + sum_dnbinom(ox, nc, r, nc, st.ocasei, T, dstart + r + 1, dend, 0.1, one, 1);
+
+  /* hosp, :481-498 */
+  const int nh = D->n_dhospi;
+  window(offset, nh, T, &dstart, &dend);
+  double *H = vec(T, 0);
+  for (int t = 1; t <= T; ++t) H[t] = st.yhospi[t] + st.ohospi[t];
+  one[1] = D->hosp_nbinom_size;
+  double lH = sum_dnbinom(D->dhospi - 1, nh, 1, nh, H, T, dstart, dend, 0.001, one, 1);
+  free(H);
+
+  /* deaths, :501-522 */
+  const int nm = D->n_dmorti;
+  window(offset, nm, T, &dstart, &dend);
+  one[1] = D->mort_nbinom_size;
+  double yD = sum_dnbinom(D->y_dmorti - 1, nm, 1, nm, st.ydeadi, T, dstart, dend, 0.001, one, 1);
+  double oD = sum_dnbinom(D->o_dmorti - 1, nm, 1, nm, st.odeadi, T, dstart, dend, 0.001, one, 1);
+
+  terms[0] = yC; terms[1] = oC; terms[2] = lH; terms[3] = 0; terms[4] = yD; terms[5] = oD;
+  double result = yC + oC + lH + yD + oD; /* :526 */
+  if (isnan(result)) *status |= EPI_ST_NA;
+  age_state_free(&st);
+  return result;
+}
+
+/* df_params, R/models/model-age-groups2i.R:552-587 */
+static void age2i_df_params(const epi_data *D, double *mn, double *mx, double *init) {
+  const double g = oracle_age_gamma();
+  const double lo = D->lockdown_offset, ltp = D->lockdown_transition_period;
+  const double i_[36] = {3.6 * g, 3.6 * g, 3.6 * g, 2.0 * g, 2.0 * g, 2.0 * g, 0.8 * g, 0.8 * g, 0.8 * g,
+                         100, 10, 1, 10, 21, 20, 10, 1, 10, 21,
+                         D->total_deaths_at_lockdown, -1, 5, 5, 5,
+                         D->d3 - lo - ltp, D->d4 - D->d3, 0.8 * g, 0.8 * g, 0.8 * g,
+                         G_CONST, 0.8 * g, 0.8 * g, 0.8 * g, 1.2, 1.01, 1.01};
+  const double mn_[36] = {2 * g, 2 * g, 2 * g, 1 * g, 1 * g, 1 * g, 0.05 * g, 0.01 * g, 0.01 * g,
+                          3, 3, 0.5, 3, 10, 3, 3, 0.5, 3, 10,
+                          0, -30, 2, 2, 2, 60,
+                          10, 0.05 * g, 0.01 * g, 0.01 * g,
+                          3, 0.05 * g, 0.01 * g, 0.01 * g, 1, 1, 1};
+  const double mx_[36] = {8 * g, 8 * g, 8 * g, 5 * g, 5 * g, 5 * g, 2 * g, 2 * g, 2 * g,
+                          5000, 25, 2, 25, 50, 100, 25, 2, 25, 50,
+                          fmax(D->dmort_last / 10, D->total_deaths_at_lockdown * 10),
+                          30, 9, 9, 9, 90,
+                          50, 3 * g, 3 * g, 3 * g,
+                          12, 1.5 * g, 1.5 * g, 1.5 * g, 2, 6, 6};
+  for (int i = 0; i < 36; ++i) { mn[i] = mn_[i]; mx[i] = mx_[i]; init[i] = i_[i]; }
+}
+
 /* ------------------------------------------------------- simple / Ne ------ */
 
 typedef struct {
@@ -987,14 +1284,18 @@ static void simple_df_params(const epi_data *D, int flavour, double *mn, double 
 /* ------------------------------------------------------------- public ----- */
 
 int oracle_n_params(int flavour) {
-  return flavour == EPI_FLAVOUR_AGE2Q ? 45 : flavour == EPI_FLAVOUR_NE ? 9 : 8;
+  return flavour == EPI_FLAVOUR_AGE2Q ? 45 : flavour == EPI_FLAVOUR_AGE2I ? 36 : flavour == EPI_FLAVOUR_NE ? 9 : 8;
 }
 
-int oracle_n_series(int flavour) { return flavour == EPI_FLAVOUR_AGE2Q ? 8 : 3; }
+static int is_age(int flavour) { return flavour == EPI_FLAVOUR_AGE2Q || flavour == EPI_FLAVOUR_AGE2I; }
+
+int oracle_n_series(int flavour) { return is_age(flavour) ? 8 : 3; }
 
 int oracle_df_params(const epi_model_desc *desc, const epi_data *D, double *mn, double *mx, double *init) {
   if (desc->flavour == EPI_FLAVOUR_AGE2Q)
     age_df_params(D, mn, mx, init);
+  else if (desc->flavour == EPI_FLAVOUR_AGE2I)
+    age2i_df_params(D, mn, mx, init);
   else
     simple_df_params(D, desc->flavour, mn, mx, init);
   return 0;
@@ -1004,7 +1305,7 @@ int oracle_df_params(const epi_model_desc *desc, const epi_data *D, double *mn, 
  * result[5] = exp(params[5]) (model-simple-ode-drj-cmp.R:136-142) */
 static void transform_params(int flavour, const double *theta0 /*0-based*/, int d, double *params1 /*1-based*/) {
   for (int i = 0; i < d; ++i) params1[i + 1] = theta0[i];
-  if (flavour != EPI_FLAVOUR_AGE2Q) params1[5] = exp(theta0[4]);
+  if (!is_age(flavour)) params1[5] = exp(theta0[4]);
 }
 
 /* One sampler-space theta (0-based, d doubles) -> logl, logp, detail.
@@ -1026,6 +1327,9 @@ void oracle_eval_one(const epi_model_desc *desc, const epi_data *D, const double
   if (desc->flavour == EPI_FLAVOUR_AGE2Q) {
     ll = age_calclogl(D, params, desc->period, desc->substeps, terms, &off, &pad, &st);
     lp = age_calclogp(D, raw);
+  } else if (desc->flavour == EPI_FLAVOUR_AGE2I) {
+    ll = age2i_calclogl(D, params, desc->period, desc->substeps, terms, &off, &pad, &st);
+    lp = age2i_calclogp(D, raw);
   } else {
     ll = simple_calclogl(D, desc->flavour, params, desc->period, desc->substeps, terms, &off, &pad, &st);
     lp = simple_calclogp(raw);
@@ -1089,9 +1393,11 @@ int oracle_trajectory(const epi_model_desc *desc, const epi_data *D, const doubl
   const int d = oracle_n_params(desc->flavour);
   double params[EPI_MAX_PARAMS + 1];
   for (int i = 0; i < d; ++i) params[i + 1] = theta_model[i];
-  if (desc->flavour == EPI_FLAVOUR_AGE2Q) {
+  if (is_age(desc->flavour)) {
     age_state_t st;
-    if (age_calculate_model(D, params, period, desc->substeps, &st)) return -1;
+    if (desc->flavour == EPI_FLAVOUR_AGE2I ? age2i_calculate_model(D, params, period, desc->substeps, &st)
+                                           : age_calculate_model(D, params, period, desc->substeps, &st))
+      return -1;
     const double *src[8] = {st.yS, st.oS, st.ycasei, st.ocasei, st.yhospi, st.ohospi, st.ydeadi, st.odeadi};
     for (int q = 0; q < 8; ++q)
       for (int i = 1; i <= period; ++i) out[(size_t)q * period + i - 1] = src[q][st.pad + i];

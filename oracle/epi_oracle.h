@@ -14,6 +14,7 @@ double oracle_dlnorm_log(double x, double meanlog, double sdlog);
 double oracle_dnbinom_mu_log(double x, double size, double mu);
 double oracle_age_gamma(void);
 void oracle_derivs_age(const double *parms45, double t, const double *y, double *ydot);
+void oracle_derivs_agef(const double *parms37, double t, const double *y, double *ydot);
 int oracle_n_params(int flavour);
 int oracle_n_series(int flavour);
 int oracle_df_params(const epi_model_desc *desc, const epi_data *D, double *mn, double *mx, double *init);

@@ -40,6 +40,7 @@ def lib():
             getattr(L, f).argtypes = [C.c_double] * 3
         L.oracle_age_gamma.restype = C.c_double
         L.oracle_derivs_age.argtypes = [_dp, C.c_double, _dp, _dp]
+        L.oracle_derivs_agef.argtypes = [_dp, C.c_double, _dp, _dp]
         L.oracle_df_params.argtypes = [C.POINTER(_capi.ModelDesc), C.POINTER(_capi.Data), _dp, _dp, _dp]
         L.oracle_eval.argtypes = [C.POINTER(_capi.ModelDesc), C.POINTER(_capi.Data), _dp, C.c_int64,
                                   C.c_int, _dp, _dp, _ip, _ip, _ip, _dp]
@@ -89,7 +90,7 @@ def trajectory(flavour, data: dict, theta_model, period, substeps=4, calc_period
     D, keep = _capi.make_data(data)
     P = calc_period or period
     ns = _capi.N_SERIES[desc.flavour]
-    neq = 10 if desc.flavour == _capi.FLAVOUR_AGE2Q else 4
+    neq = 10 if desc.flavour in _capi.AGE_FLAVOURS else 4
     th = np.ascontiguousarray(np.asarray(theta_model, dtype=np.float64))
     out, states = np.zeros((ns, P)), np.zeros((P, neq))
     off, pad = C.c_int32(0), C.c_int32(0)
@@ -131,6 +132,14 @@ def derivs_age(parms45, t, y):
     yy = np.ascontiguousarray(y, dtype=np.float64)
     out = np.zeros(10)
     lib().oracle_derivs_age(_capi.as_dp(p), t, _capi.as_dp(yy), _capi.as_dp(out))
+    return out
+
+
+def derivs_agef(parms37, t, y):
+    p = np.ascontiguousarray(parms37, dtype=np.float64)
+    yy = np.ascontiguousarray(y, dtype=np.float64)
+    out = np.zeros(10)
+    lib().oracle_derivs_agef(_capi.as_dp(p), t, _capi.as_dp(yy), _capi.as_dp(out))
     return out
 
 

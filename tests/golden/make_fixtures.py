@@ -11,6 +11,8 @@ Workloads:
   S120, S365   synthetic simple SEIR, P = 120 / 365
   NE120        synthetic Ne flavour, P = 120
   A300, A365   synthetic two-age-group (model-age-groups2q), P = 300 / 365
+  I290         synthetic two-age-group, earlier generation (model-age-groups2i,
+               analyses/be/age/settings.R: P = 290, sizes 0.1 / 2 / 20 / 120)
   DE, SE       ECDC daily cases/deaths (R/data/ecdc/ecdc.csv, geoId DE / SE),
                loader logic of R/data/ecdc/data.R:75-105 with the lockdown
                dates fixed by hand (the Google mobility file is not in the tree)
@@ -110,6 +112,41 @@ def age_dataset(P):
     return d
 
 
+def age2i_dataset(P):
+    n = P - 60
+    nr = n + 200
+    vs = np.arange(1, nr + 1, dtype=float)
+    g = glogis(vs, 0, 1, 1, 0.5, 0.1, 200, 0.5)
+    gtrimp = glogis(vs, 0, 1, 1, 0.5, 0.1, 113, 0.5)
+    d = dict(name="I" + str(P), flavour="age2i", period=P, N=11.5e6, y_N=8.55e6, o_N=2.95e6,
+             lockdown_offset=2, lockdown_transition_period=10, total_deaths_at_lockdown=5.0,
+             d3=88, d4=118, d5=139, d6=160, d7=195, d8=220, d_reliable_cases=205,
+             n_dhospi=n, n_dhosp=n, n_dmorti=n, n_dcasei=n, n_rate=nr,
+             # this generation has no fyifr / ifrred parameters: the time dependence lives in the data vectors
+             y_ifr=(3e-4 * (1 - 0.5 * g)).tolist(), o_ifr=(0.04 * (1 - 0.3 * gtrimp)).tolist(),
+             y_hr=[0.01] * nr, o_hr=(0.06 * (1 - 0.2 * g)).tolist(),
+             case_nbinom_size1=0.1, case_nbinom_sizey2=2.0, case_nbinom_sizeo2=2.0,
+             hosp_nbinom_size=20.0, mort_nbinom_size=120.0,
+             dhospi=[0.0] * n, y_dcasei=[0.0] * n, o_dcasei=[0.0] * n, y_dmorti=[0.0] * n,
+             o_dmorti=[0.0] * n, dmort_last=20000.0)
+    _, _, init = oracle.df_params("age2i", d, P)
+    series, _, off, pad = oracle.trajectory("age2i", d, init, P, M_DEFAULT)
+    assert off != 10000, "init does not cross t0_morts"
+    idx = off - 1 - pad + np.arange(n)
+    assert idx.min() >= 0 and idx.max() < P, (off, pad, idx.min(), idx.max())
+    rng = np.random.default_rng(20200310)
+    ycasei, ocasei, yhospi, ohospi, ydeadi, odeadi = (series[q][idx] for q in range(2, 8))
+    d["y_dcasei"] = nb_draw(rng, np.maximum(0.1, ycasei), 2.0).tolist()
+    d["o_dcasei"] = nb_draw(rng, np.maximum(0.1, ocasei), 2.0).tolist()
+    d["dhospi"] = nb_draw(rng, np.maximum(0.001, yhospi + ohospi), 20.0).tolist()
+    d["y_dmorti"] = nb_draw(rng, np.maximum(0.001, ydeadi), 120.0).tolist()
+    d["o_dmorti"] = nb_draw(rng, np.maximum(0.001, odeadi), 120.0).tolist()
+    d["dmort_last"] = float(np.sum(d["y_dmorti"]) + np.sum(d["o_dmorti"]))
+    d["provenance"] = ("synthetic: oracle (RK4 m=4) at model-age-groups2i.R init, NB noise with the "
+                       "analyses/be/age/settings.R sizes, numpy default_rng(20200310)")
+    return d
+
+
 def ecdc_dataset(geo, d1, transition, data_days, flavour):
     rows = [r for r in csv.DictReader(open(ECDC)) if r["geoId"] == geo]
     for r in rows:
@@ -166,7 +203,7 @@ def golden(ds, n_random, seed):
             terms=[[None if np.isnan(v) else v for v in row] for row in r["terms"].tolist()])
     # trajectories at init (model space) for the calculateModel parity test
     model = init.copy()
-    if fl != "age2q":
+    if fl not in ("age2q", "age2i"):
         model[4] = np.exp(init[4])
     series, states, off, pad = oracle.trajectory(fl, ds, model, P, 4)
     out["init_trajectory"] = dict(substeps=4, offset=off, padding=pad,
@@ -177,14 +214,17 @@ def golden(ds, n_random, seed):
 
 def main():
     os.makedirs(DS_DIR, exist_ok=True)
-    sets = [simple_dataset(120), simple_dataset(365), simple_dataset(120, "ne"),
-            age_dataset(300), age_dataset(365),
-            ecdc_dataset("DE", dt.date(2020, 3, 13), 10, 60, "simple"),
-            ecdc_dataset("SE", dt.date(2020, 3, 12), 14, 60, "ne")]
+    makers = {"S120": lambda: simple_dataset(120), "S365": lambda: simple_dataset(365),
+              "NE120": lambda: simple_dataset(120, "ne"), "A300": lambda: age_dataset(300),
+              "A365": lambda: age_dataset(365), "I290": lambda: age2i_dataset(290),
+              "DE": lambda: ecdc_dataset("DE", dt.date(2020, 3, 13), 10, 60, "simple"),
+              "SE_NE": lambda: ecdc_dataset("SE", dt.date(2020, 3, 12), 14, 60, "ne")}
+    only = sys.argv[1:]  # optional: regenerate only the named sets
+    sets = [mk() for name, mk in makers.items() if not only or name in only]
     for ds in sets:
         with open(os.path.join(DS_DIR, ds["name"] + ".json"), "w") as f:
             json.dump(ds, f)
-        nrand = 24 if ds["flavour"] == "age2q" else 32
+        nrand = 24 if ds["flavour"] in ("age2q", "age2i") else 32
         g = golden(ds, nrand, 1234)
         with open(os.path.join(GOLD_DIR, "golden_" + ds["name"] + ".json"), "w") as f:
             json.dump(g, f)

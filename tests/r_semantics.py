@@ -10,6 +10,7 @@ used ONLY by tests to cross-check the oracle:
 
 R vectors are emulated with 1-based helper accessors; NA is NaN.
 Reference: R/models/model-age-groups2q.R, R/models/model-agen.cpp,
+R/models/model-age-groups2i.R, R/models/model-agef.cpp,
 R/models/model-simple-ode-drj-cmp.R.
 """
 import numpy as np
@@ -356,6 +357,174 @@ class Age2q:
         lp += dlnorm_log(p(22), np.log(0.3), np.log(2)) + dlnorm_log(p(23), np.log(0.3), np.log(2))
         lp += dlnorm_log(p(43), np.log(0.35), np.log(1.3))
         lp += dlnorm_log(p(11), 0, lSD) + dlnorm_log(p(15), 0, lSD)
+        return float(lp)
+
+
+# ------------------------------------------------------------------- age2i --
+
+class Age2i(Age2q):
+    """R/models/model-age-groups2i.R + R/models/model-agef.cpp (36 parameters, 8 breakpoints)."""
+    KIND = (1, 1, 1, 1, 1, 1, 0, 0)
+
+    @staticmethod
+    def active(t, T):
+        for k in range(7, -1, -1):
+            if t > T[k]:
+                return k
+        return -1
+
+    # model-agef.cpp:66-87
+    @staticmethod
+    def interpolate(t, T, v):
+        if t > T[7]: return v[7]
+        if t > T[6]: return v[6]
+        elif t > T[5]: return v[5] + (t - T[5]) / (T[6] - T[5]) * (v[6] - v[5])
+        elif t > T[4]: return v[4] + (t - T[4]) / (T[5] - T[4]) * (v[5] - v[4])
+        elif t > T[3]: return v[3] + (t - T[3]) / (T[4] - T[3]) * (v[4] - v[3])
+        elif t > T[2]: return v[2] + (t - T[2]) / (T[3] - T[2]) * (v[3] - v[2])
+        elif t > T[1]: return v[1] + (t - T[1]) / (T[2] - T[1]) * (v[2] - v[1])
+        elif t > T[0]: return v[0] + (t - T[0]) / (T[1] - T[0]) * (v[1] - v[0])
+        return v[0]
+
+    # model-age-groups2i.R:50-316
+    def calculateModel(self, params, period):
+        D = self.D
+        p = lambda i: params[i - 1]
+        y_N, o_N = D["y_N"], D["o_N"]
+        y_ifr, o_ifr, y_hr, o_hr = (np.asarray(D[k], dtype=float) for k in ("y_ifr", "o_ifr", "y_hr", "o_hr"))
+        y_died_rate, o_died_rate = y_ifr[0], o_ifr[0]
+        lockdown_offset, ltp = D["lockdown_offset"], D["lockdown_transition_period"]
+        by = [p(1), p(4), p(7), p(7), p(27), p(27), p(31), p(34) * p(31)]
+        bo = [p(2), p(5), p(8), p(8), p(28), p(28), p(32), p(36) * p(32)]
+        byo = [p(3), p(6), p(9), p(9), p(29), p(29), p(33), p(35) * p(33)]
+        ycase_rate, ycase_latency, yhosp_rate, yhosp_latency, ydied_latency = p(10), p(11), p(12), p(13), p(14)
+        ocase_rate, ocase_latency, ohosp_rate, ohosp_latency, odied_latency = p(15), p(16), p(17), p(18), p(19)
+        t0_morts, t0o, CLsd, HLsd, DLsd, t3o, t4o, t6o = p(20), p(21), p(22), p(23), p(24), p(25), p(26), p(30)
+        prof = dict(ycase=self.calcGammaProfile(ycase_latency, CLsd), ocase=self.calcGammaProfile(ocase_latency, CLsd),
+                    yhosp=self.calcGammaProfile(yhosp_latency, HLsd), ohosp=self.calcGammaProfile(ohosp_latency, HLsd),
+                    ydied=self.calcGammaProfile(ydied_latency, DLsd), odied=self.calcGammaProfile(odied_latency, DLsd))
+        padding = max(-prof["ycase"]["kbegin"], -prof["ydied"]["kbegin"], -prof["ocase"]["kbegin"],
+                      -prof["odied"]["kbegin"]) + 1
+        T = padding + period
+        yS = np.full(T, y_N - Initial, dtype=float)
+        oS = np.full(T, o_N, dtype=float)
+        Y0 = [y_N - Initial, Initial, 0, 0, 0, o_N, 0, 0, 0, 0]
+        Tb = [1e10] * 8
+        times = np.arange(padding + 1, padding + period + 1)
+        out = self._solve(Y0, times, Tb, by, bo, byo)
+        yS[padding:] = out[:, 0]
+        oS[padding:] = out[:, 5]
+        died = np.full(T, np.nan)
+        died[padding:] = ((y_N - self.convolute(yS, padding + 1, padding + period, prof["ydied"])) * y_died_rate
+                          + (o_N - self.convolute(oS, padding + 1, padding + period, prof["odied"])) * o_died_rate)
+        data_offset = InvalidDataOffset
+        with np.errstate(invalid="ignore"):
+            lds = np.nonzero(died > t0_morts)[0] + 1
+        if len(lds) > 0:
+            data_offset = lds[0] - lockdown_offset
+            t2 = data_offset + lockdown_offset + ltp
+            t3 = t2 + t3o
+            t4 = t3 + t4o
+            t5 = data_offset + D["d5"]
+            t6 = t5 + t6o
+            t7 = data_offset + D["d7"]
+            Tb = [data_offset + lockdown_offset + t0o, data_offset + lockdown_offset + max(t0o, 0), t2,
+                  t3, t4, t5, t6, t7]
+            out = self._solve(Y0, times, Tb, by, bo, byo)
+        yS[padding:] = out[:, 0]
+        oS[padding:] = out[:, 5]
+
+        def series(S, Ng, profile, t1, valid_rate, invalid_fun):
+            """valid_rate(s2i_slice, idx0, idx1) applies rate[idx0:idx1] the way the R line does"""
+            dst = np.zeros(T)
+            s2 = Ng - self.convolute(S, padding + 1, padding + period, profile)
+            s2i = np.concatenate([[s2[0]], np.diff(s2)])
+            n_rate = len(y_ifr)
+            if data_offset != InvalidDataOffset:
+                t1 = int(t1)
+                t2 = min(padding + period, t1 + n_rate - 1)
+                if t1 > padding and t2 > t1:
+                    dst[padding:t1] = valid_rate(s2i[0:t1 - padding], 0, 1)
+                    dst[t1 - 1:t2] = valid_rate(s2i[t1 - padding - 1:t2 - padding], 0, t2 - t1 + 1)
+                    dst[t2 - 1:padding + period] = valid_rate(s2i[t2 - padding - 1:period], n_rate - 1, n_rate)
+            else:
+                dst[padding:padding + period] = invalid_fun(s2i)
+            return dst
+
+        st = dict(padding=padding, offset=data_offset, y_S=yS, o_S=oS)
+        st["y_casei"] = series(yS, y_N, prof["ycase"], data_offset + r_round(-ydied_latency + ycase_latency),
+                               lambda x, a, b: x * np.minimum(1, ycase_rate * y_ifr[a:b]),
+                               lambda x: x * ycase_rate * y_died_rate)
+        st["y_hospi"] = series(yS, y_N, prof["yhosp"], data_offset + r_round(-ydied_latency + yhosp_latency),
+                               lambda x, a, b: x * yhosp_rate * y_hr[a:b], lambda x: x * yhosp_rate * y_hr[0])
+        st["y_deadi"] = series(yS, y_N, prof["ydied"], data_offset,
+                               lambda x, a, b: x * y_ifr[a:b], lambda x: x * y_died_rate)
+        st["o_casei"] = series(oS, o_N, prof["ocase"], data_offset + r_round(-ydied_latency + ocase_latency),
+                               lambda x, a, b: x * np.minimum(1, ocase_rate * o_ifr[a:b]),
+                               lambda x: x * ocase_rate * o_died_rate)
+        st["o_hospi"] = series(oS, o_N, prof["ohosp"], data_offset + r_round(-ydied_latency + ohosp_latency),
+                               lambda x, a, b: x * ohosp_rate * o_hr[a:b], lambda x: x * ohosp_rate * o_hr[0])
+        st["o_deadi"] = series(oS, o_N, prof["odied"], data_offset,
+                               lambda x, a, b: x * o_ifr[a:b], lambda x: x * o_died_rate)
+        return st
+
+    # model-age-groups2i.R:442-536
+    def calclogl(self, params):
+        D = self.D
+        state = self.calculateModel(params, self.P)
+        if state["offset"] == InvalidDataOffset:
+            state["offset"] = 1
+        y_dcasei, o_dcasei = np.asarray(D["y_dcasei"], float), np.asarray(D["o_dcasei"], float)
+        dhospi = np.asarray(D["dhospi"], float)
+        y_dmorti, o_dmorti = np.asarray(D["y_dmorti"], float), np.asarray(D["o_dmorti"], float)
+        r = D["d_reliable_cases"]
+        size2 = D["case_nbinom_sizey2"]  # case_nbinom_size2 of analyses/be/age/settings.R:31
+        assert size2 == D["case_nbinom_sizeo2"]
+
+        def window(n, L):
+            dstart = state["offset"]
+            dend = state["offset"] + n - 1
+            if dend > L:
+                dend = L
+                dstart = dend - n + 1
+            if dstart < 1:
+                dstart = 1
+                dend = dstart + n - 1
+            return dstart, dend
+
+        dstart, dend = window(len(y_dcasei), len(state["y_casei"]))
+        y_loglC = (np.sum(dnbinom_log(rslice(y_dcasei, 1, r - 1), pmax(0.1, rslice(state["y_casei"], dstart, dstart + r)), D["case_nbinom_size1"]))
+                   + np.sum(dnbinom_log(rslice(y_dcasei, r, len(y_dcasei)), pmax(0.1, rslice(state["y_casei"], dstart + r + 1, dend)), size2)))
+        o_loglC = (np.sum(dnbinom_log(rslice(o_dcasei, 1, r - 1), pmax(0.1, rslice(state["o_casei"], dstart, dstart + r)), D["case_nbinom_size1"]))
+                   + np.sum(dnbinom_log(rslice(o_dcasei, r, len(o_dcasei)), pmax(0.1, rslice(state["o_casei"], dstart + r + 1, dend)), size2)))
+        dstart, dend = window(len(dhospi), len(state["y_hospi"]))
+        H = state["y_hospi"] + state["o_hospi"]
+        loglH = np.sum(dnbinom_log(dhospi, pmax(0.001, rslice(H, dstart, dend)), D["hosp_nbinom_size"]))
+        dstart, dend = window(len(y_dmorti), len(state["y_deadi"]))
+        y_loglD = np.sum(dnbinom_log(y_dmorti, pmax(0.001, rslice(state["y_deadi"], dstart, dend)), D["mort_nbinom_size"]))
+        o_loglD = np.sum(dnbinom_log(o_dmorti, pmax(0.001, rslice(state["o_deadi"], dstart, dend)), D["mort_nbinom_size"]))
+        terms = [y_loglC, o_loglC, loglH, 0.0, y_loglD, o_loglD]
+        return float(y_loglC + o_loglC + loglH + y_loglD + o_loglD), terms, state
+
+    # model-age-groups2i.R:362-438
+    def calclogp(self, params):
+        D, gamma = self.D, self.gamma
+        p = lambda i: params[i - 1]
+        lo, ltp = D["lockdown_offset"], D["lockdown_transition_period"]
+        betay7, betayo7, betao7 = p(34) * p(31), p(35) * p(33), p(36) * p(32)
+        lp = 0.0
+        lp += dnorm_log(p(21), 0, 10)
+        lp += dnorm_log(lo + ltp + p(25), D["d3"], 10)
+        lp += dnorm_log(lo + ltp + p(25) + p(26), D["d4"], 10)
+        lp += dnorm_log(p(30), self.G, 3)
+        for a, b in ((p(1), p(4)), (p(2), p(5)), (p(3), p(6)), (p(4), p(7)), (p(5), p(8)), (p(6), p(9))):
+            lp += dnorm_log(a - b, 0, 2 * gamma)
+        for a, b in ((p(7), p(27)), (p(8), p(28)), (p(9), p(29))):  # beta3 = beta2
+            lp += dnorm_log(a - b, 0, 0.5 * gamma)
+        lp += dnorm_log(p(22), 5, 1) + dnorm_log(p(23), 5, 1) + dnorm_log(p(24), 5, 1)
+        lp += dnorm_log(p(14), 21, 4) + dnorm_log(p(19), 21, 4)
+        lp += dnorm_log(p(31), 0.6, 0.2) + dnorm_log(p(32), 0.22, 0.2) + dnorm_log(p(33), 0.26, 0.2)
+        lp += dnorm_log(betay7, 0.85, 0.2) + dnorm_log(betao7, 0.19, 0.05) + dnorm_log(betayo7, 0.02, 0.02)
         return float(lp)
 
 

@@ -109,7 +109,34 @@ def test_rhs_matches_reference_binary(oracle):
         assert np.array_equal(a, oracle.derivs_age(parms, t, y))
 
 
-@pytest.mark.parametrize("name", ["A300", "S120", "NE120", "DE"])
+def test_rhs_agef_matches_reference_binary(oracle):
+    """Same for the 8-breakpoint RHS of the secondary age model (model-agef.cpp, parms[37])."""
+    try:
+        ref = oracle.RefRHS("model-agef", 37)
+    except FileNotFoundError:
+        pytest.skip("oracle/_ref not built (reference tree absent)")
+    rng = np.random.default_rng(4)
+    gamma = oracle.lib().oracle_age_gamma()
+    tidx = [5, 6, 7, 17, 21, 25, 29, 33]
+    for trial in range(600):
+        parms = np.zeros(37)
+        parms[:5] = [8.55e6, 2.95e6, 1 / 3, 1, gamma]
+        ts = np.sort(rng.uniform(30, 330, 8)) if trial % 3 else rng.uniform(30, 330, 8)
+        for k, i in enumerate(tidx):
+            parms[i] = ts[k]
+        for i in range(8, 37):
+            if i not in tidx:
+                parms[i] = rng.uniform(0.01, 4)
+        y = np.concatenate([rng.dirichlet(np.ones(5)) * 8.55e6, rng.dirichlet(np.ones(5)) * 2.95e6])
+        if trial % 50 == 0:
+            y[rng.integers(10)] = -1.0
+        t = rng.uniform(0, 360) if trial % 7 else ts[rng.integers(8)]
+        ref.init(parms)
+        a, _ = ref.derivs(t, y)
+        assert np.array_equal(a, oracle.derivs_agef(parms, t, y))
+
+
+@pytest.mark.parametrize("name", ["A300", "I290", "S120", "NE120", "DE"])
 def test_oracle_vs_numpy_transliteration_same_scheme(name, oracle):
     """Index semantics (filter alignment + mirror, two-pass offset, rate-map slices, dnbinom
     recycling, window clamps, NA and invalid-offset branches) against an independent
@@ -120,8 +147,8 @@ def test_oracle_vs_numpy_transliteration_same_scheme(name, oracle):
     idx = list(range(0, len(theta), 3))[:14]
     res = oracle.evaluate(ds["flavour"], ds, theta[idx], ds["period"], 4)
     for k, i in enumerate(idx):
-        if ds["flavour"] == "age2q":
-            M = R.Age2q(ds, ds["period"], "rk4", 4)
+        if ds["flavour"] in ("age2q", "age2i"):
+            M = (R.Age2q if ds["flavour"] == "age2q" else R.Age2i)(ds, ds["period"], "rk4", 4)
             ll, terms, st = M.calclogl(theta[i])
         else:
             M = R.Simple(ds, ds["period"], "rk4", 4, ne=ds["flavour"] == "ne")
@@ -137,7 +164,7 @@ def test_oracle_vs_numpy_transliteration_same_scheme(name, oracle):
         assert rel_err(lp, res["logp"][k]) < 1e-13
 
 
-@pytest.mark.parametrize("name,tol_m4,tol_lsoda", [("A300", 0.02, 0.05), ("S120", 1e-3, 1e-2)])
+@pytest.mark.parametrize("name,tol_m4,tol_lsoda", [("A300", 0.02, 0.05), ("I290", 0.02, 0.05), ("S120", 1e-3, 1e-2)])
 def test_fixed_step_scheme_vs_lsoda(name, tol_m4, tol_lsoda, oracle):
     """The oracle's breakpoint-cut RK4 (m = 4) against scipy LSODA: (a) at deSolve's defaults
     rtol = atol = 1e-6, hmax = 1 (the reference's own solver noise) and (b) tight.  At the model
@@ -146,8 +173,9 @@ def test_fixed_step_scheme_vs_lsoda(name, tol_m4, tol_lsoda, oracle):
     g = load_golden(name)
     th = np.array(g["theta"])[0]
     o4 = oracle.evaluate(ds["flavour"], ds, th[None], ds["period"], 4)["logl"][0]
-    if ds["flavour"] == "age2q":
-        mk = lambda integ: R.Age2q(ds, ds["period"], integ, 4).calclogl(th)[0]
+    if ds["flavour"] in ("age2q", "age2i"):
+        cls = R.Age2q if ds["flavour"] == "age2q" else R.Age2i
+        mk = lambda integ: cls(ds, ds["period"], integ, 4).calclogl(th)[0]
     else:
         p = th.copy()
         p[4] = np.exp(p[4])
