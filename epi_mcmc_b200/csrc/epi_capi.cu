@@ -44,6 +44,8 @@ int epi_fail(epi_handle *h, int rc, const char *fmt, ...) {
   } while (0)
 
 static double age_gamma() { return 1.0 / ((4.7 - (3.0 + 1.0)) * 2.0); }  // model-age-groups2q.R:8-15
+static bool is_age(int flavour) { return flavour == EPI_FLAVOUR_AGE2Q || flavour == EPI_FLAVOUR_AGE2I; }
+static int pad_rows(int flavour) { return flavour == EPI_FLAVOUR_AGE2I ? EPI_MAX_PADDING : kPadMax; }  // Traits<FL>::kPad
 
 // ------------------------------------------------------------- metadata tables
 static const char *kAgeNames[45] = {  // fit.paramnames, model-age-groups2q.R:604-618
@@ -52,6 +54,11 @@ static const char *kAgeNames[45] = {  // fit.paramnames, model-age-groups2q.R:60
     "fyifr", "fyhr", "t3o", "t4o", "betay4", "betao4", "betayo4", "betay5", "betao5", "betayo5",
     "t6o", "betay6", "betao6", "betayo6", "t7o", "betay7", "betao7", "betayo7", "fy9", "fo9", "fyo9",
     "ifrred", "y.CL", "o.CL"};
+static const char *kAge2iNames[36] = {  // fit.paramnames, model-age-groups2i.R:538-549
+    "betay0", "betao0", "betayo0", "betay1", "betao1", "betayo1", "betay2", "betao2", "betayo2",
+    "y.CR", "y.CL", "y.HR", "y.HL", "y.DL", "o.CR", "o.CL", "o.HR", "o.HL", "o.DL", "t0_morts", "t0o",
+    "CRsd", "HLsd", "DLsd", "t3o", "t4o", "betay4", "betao4", "betayo4", "t6o", "betay6", "betao6", "betayo6",
+    "fy7", "fo7", "fyo7"};
 static const char *kSimpleNames[9] = {  // model-simple-ode-drj-cmp.R:259-260 (+ Nef, README.md:91-93)
     "R0", "Rt", "Tinf0", "Tinft", "logHR", "HL", "DL", "lockdownmort", "Nef"};
 
@@ -76,6 +83,26 @@ static void df_params_host(int flavour, const epi_data &D, double *mn, double *m
                             50, 3 * g, 3 * g, 0.5 * g, 50, 3 * g, 3 * g, 0.5 * g,
                             1.1, 1.1, 1.1, 0.7, 14, 14};
     for (int i = 0; i < 45; ++i) { mn[i] = mn_[i]; mx[i] = mx_[i]; init[i] = i_[i]; }
+  } else if (flavour == EPI_FLAVOUR_AGE2I) {  // model-age-groups2i.R:552-587
+    const double g = age_gamma();
+    const double lo = D.lockdown_offset, ltp = D.lockdown_transition_period;
+    const double i_[36] = {3.6 * g, 3.6 * g, 3.6 * g, 2.0 * g, 2.0 * g, 2.0 * g, 0.8 * g, 0.8 * g, 0.8 * g,
+                           100, 10, 1, 10, 21, 20, 10, 1, 10, 21,
+                           D.total_deaths_at_lockdown, -1, 5, 5, 5,
+                           D.d3 - lo - ltp, (double)(D.d4 - D.d3), 0.8 * g, 0.8 * g, 0.8 * g,
+                           4.7, 0.8 * g, 0.8 * g, 0.8 * g, 1.2, 1.01, 1.01};
+    const double mn_[36] = {2 * g, 2 * g, 2 * g, 1 * g, 1 * g, 1 * g, 0.05 * g, 0.01 * g, 0.01 * g,
+                            3, 3, 0.5, 3, 10, 3, 3, 0.5, 3, 10,
+                            0, -30, 2, 2, 2, 60,
+                            10, 0.05 * g, 0.01 * g, 0.01 * g,
+                            3, 0.05 * g, 0.01 * g, 0.01 * g, 1, 1, 1};
+    const double mx_[36] = {8 * g, 8 * g, 8 * g, 5 * g, 5 * g, 5 * g, 2 * g, 2 * g, 2 * g,
+                            5000, 25, 2, 25, 50, 100, 25, 2, 25, 50,
+                            std::fmax(D.dmort_last / 10, D.total_deaths_at_lockdown * 10),
+                            30, 9, 9, 9, 90,
+                            50, 3 * g, 3 * g, 3 * g,
+                            12, 1.5 * g, 1.5 * g, 1.5 * g, 2, 6, 6};
+    for (int i = 0; i < 36; ++i) { mn[i] = mn_[i]; mx[i] = mx_[i]; init[i] = i_[i]; }
   } else {  // model-simple-ode-drj-cmp.R:263-270
     const double tdl = D.total_deaths_at_lockdown;
     const double i_[9] = {2.9, 0.9, 3, 3, std::log(0.02), 10, 20, tdl, 0.7};
@@ -197,6 +224,25 @@ static std::vector<PriorTerm> build_prior(int flavour, const epi_data &D) {
     p.push_back(pt_lnorm(42, std::log(0.35), std::log(1.3)));
     p.push_back(pt_lnorm(10, 0, lSD));
     p.push_back(pt_lnorm(14, 0, lSD));
+  } else if (flavour == EPI_FLAVOUR_AGE2I) {  // calclogp, model-age-groups2i.R:410-435 (0-based theta indices)
+    const double g = age_gamma(), lo_ltp = D.lockdown_offset + D.lockdown_transition_period;
+    p.push_back(pt_norm(20, 0, 10));
+    p.push_back(pt_sum(24, -1, lo_ltp, 1, 0, D.d3, 10));
+    p.push_back(pt_sum(24, 25, lo_ltp, 1, 1, D.d4, 10));
+    p.push_back(pt_norm(29, 4.7, 3));  // dnorm(t6o, mean = G, sd = 3)
+    const int df2[6][2] = {{0, 3}, {1, 4}, {2, 5}, {3, 6}, {4, 7}, {5, 8}};
+    for (auto &r : df2) p.push_back(pt_sum(r[0], r[1], 0, 1, -1, 0, 2 * g));
+    const int df05[3][2] = {{6, 26}, {7, 27}, {8, 28}};  // beta3 = beta2
+    for (auto &r : df05) p.push_back(pt_sum(r[0], r[1], 0, 1, -1, 0, 0.5 * g));
+    for (int i : {21, 22, 23}) p.push_back(pt_norm(i, 5, 1));
+    p.push_back(pt_norm(13, 21, 4));
+    p.push_back(pt_norm(18, 21, 4));
+    p.push_back(pt_norm(30, 0.6, 0.2));
+    p.push_back(pt_norm(31, 0.22, 0.2));
+    p.push_back(pt_norm(32, 0.26, 0.2));
+    p.push_back(PriorTerm{33, 30, 1, 0, 0, 0, 0, 0.85, 0.2});   // betay7 = fy7 * betay6
+    p.push_back(PriorTerm{35, 31, 1, 0, 0, 0, 0, 0.19, 0.05});  // betao7 = params[36] * betao6
+    p.push_back(PriorTerm{34, 32, 1, 0, 0, 0, 0, 0.02, 0.02});  // betayo7 = params[35] * betayo6
   } else {  // calclogp, model-simple-ode-drj-cmp.R:156-179: G0 = Tinc + Tinf0/2, Gt = Tinc + Tinft/2
     p.push_back(pt_norm(6, 21, 4));
     p.push_back(pt_sum(2, -1, 3.0, 0.5, 0, 5, 1));
@@ -266,6 +312,43 @@ static int fill_model(epi_handle *h, const epi_model_desc &desc, const epi_data 
     calls.push_back({4, 5, D.o_dmorti, nm, 1, nm, 0, nm - 1, h->size_vec.data(), nm});
     M.d3 = D.d3; M.d4 = D.d4; M.d5d = D.d5; M.d6 = D.d6; M.d7 = D.d7;
     M.lo_ltp = D.lockdown_offset + D.lockdown_transition_period;
+  } else if (desc.flavour == EPI_FLAVOUR_AGE2I) {
+    M.d = 36;
+    M.P1 = desc.period;  // pass 1 covers the whole period, model-age-groups2i.R:148-152
+    if (!(D.y_N > 1 && D.o_N > 0)) return epi_fail(h, EPI_ERR_ARG, "y_N / o_N missing");
+    if (D.n_rate < 1 || !D.y_ifr || !D.o_ifr || !D.y_hr || !D.o_hr)
+      return epi_fail(h, EPI_ERR_ARG, "rate vectors y_ifr/o_ifr/y_hr/o_hr missing");
+    if (!D.y_dcasei || !D.o_dcasei || !D.dhospi || !D.y_dmorti || !D.o_dmorti)
+      return epi_fail(h, EPI_ERR_ARG, "observed series missing");
+    M.Ny = D.y_N; M.No = D.o_N; M.N = D.y_N + D.o_N;
+    M.a1 = 1.0 / 3.0; M.a2 = 1.0 / 1.0; M.gamma = age_gamma();
+    M.ifr_y1 = D.y_ifr[0]; M.ifr_o1 = D.o_ifr[0];
+    M.d5 = D.d5;
+    M.n_rate = D.n_rate;
+    int rc;
+    if ((rc = upload(h, D.y_ifr, D.n_rate, &M.y_ifr))) return rc;
+    if ((rc = upload(h, D.o_ifr, D.n_rate, &M.o_ifr))) return rc;
+    if ((rc = upload(h, D.y_hr, D.n_rate, &M.y_hr))) return rc;
+    if ((rc = upload(h, D.o_hr, D.n_rate, &M.o_hr))) return rc;
+    M.n_series = 5;
+    const int nc = D.n_dcasei, nh = D.n_dhospi, nm = D.n_dmorti;
+    const int r = D.d_reliable_cases;
+    n_obs[0] = nc; n_obs[1] = nc; n_obs[2] = nh; n_obs[3] = nm; n_obs[4] = nm;
+    const int term_of[5] = {0, 1, 2, 4, 5};
+    const double fl[5] = {0.1, 0.1, 0.001, 0.001, 0.001};  // :471,496,516
+    for (int s = 0; s < 5; ++s) { M.term_of[s] = term_of[s]; M.floor_[s] = fl[s]; }
+    h->sizes = {D.case_nbinom_size1, D.case_nbinom_sizey2, D.case_nbinom_sizeo2, D.hosp_nbinom_size, D.mort_nbinom_size};
+    const double *sz = h->sizes.data();
+    // cases, model-age-groups2i.R:466-478 (same x/mu length mismatch as 2q)
+    calls.push_back({0, 0, D.y_dcasei, nc, 1, r - 1, 0, r, sz + 0, 1});
+    calls.push_back({0, 0, D.y_dcasei, nc, r, nc, r + 1, nc - 1, sz + 1, 1});
+    calls.push_back({1, 1, D.o_dcasei, nc, 1, r - 1, 0, r, sz + 0, 1});
+    calls.push_back({1, 1, D.o_dcasei, nc, r, nc, r + 1, nc - 1, sz + 2, 1});
+    calls.push_back({2, 2, D.dhospi, nh, 1, nh, 0, nh - 1, sz + 3, 1});     // :496-498
+    calls.push_back({3, 4, D.y_dmorti, nm, 1, nm, 0, nm - 1, sz + 4, 1});  // :516-522
+    calls.push_back({4, 5, D.o_dmorti, nm, 1, nm, 0, nm - 1, sz + 4, 1});
+    M.d3 = D.d3; M.d4 = D.d4; M.d5d = D.d5; M.d7 = D.d7;
+    M.lo_ltp = D.lockdown_offset + D.lockdown_transition_period;
   } else if (desc.flavour == EPI_FLAVOUR_SIMPLE || desc.flavour == EPI_FLAVOUR_NE) {
     M.d = desc.flavour == EPI_FLAVOUR_NE ? 9 : 8;
     M.P1 = desc.period;  // pass 1 covers the whole period, model-simple-ode-drj-cmp.R:82-86
@@ -290,7 +373,8 @@ static int fill_model(epi_handle *h, const epi_model_desc &desc, const epi_data 
   } else {
     return epi_fail(h, EPI_ERR_ARG, "unknown flavour %d", desc.flavour);
   }
-  if (desc.period < 2 || desc.period > 4096) return epi_fail(h, EPI_ERR_ARG, "period out of range");
+  if (desc.period < 2 || desc.period > (is_age(desc.flavour) ? 2048 : 4096))
+    return epi_fail(h, EPI_ERR_ARG, "period out of range (2..4096, age flavours 2..2048)");
   if (desc.substeps < 1 || desc.substeps > 64) return epi_fail(h, EPI_ERR_ARG, "substeps out of range");
   for (int s = 0; s < M.n_series; ++s)
     if (n_obs[s] > desc.period) return epi_fail(h, EPI_ERR_ARG, "observed series longer than FitTotalPeriod");
@@ -371,10 +455,10 @@ extern "C" void epi_destroy(epi_handle *h) {
 
 extern "C" const char *epi_last_error(const epi_handle *h) { return h ? h->err.c_str() : g_last_error.c_str(); }
 extern "C" int epi_n_params(const epi_handle *h) { return h ? h->M.d : 0; }
-extern "C" int epi_n_series(const epi_handle *h) { return h ? (h->M.flavour == EPI_FLAVOUR_AGE2Q ? 8 : 3) : 0; }
+extern "C" int epi_n_series(const epi_handle *h) { return h ? (is_age(h->M.flavour) ? 8 : 3) : 0; }
 extern "C" const char *epi_param_name(const epi_handle *h, int i) {
   if (!h || i < 0 || i >= h->M.d) return nullptr;
-  return h->M.flavour == EPI_FLAVOUR_AGE2Q ? kAgeNames[i] : kSimpleNames[i];
+  return h->M.flavour == EPI_FLAVOUR_AGE2Q ? kAgeNames[i] : h->M.flavour == EPI_FLAVOUR_AGE2I ? kAge2iNames[i] : kSimpleNames[i];
 }
 extern "C" int epi_df_params(const epi_handle *h, double *mn, double *mx, double *init) {
   if (!h) return EPI_ERR_ARG;
@@ -389,8 +473,8 @@ extern "C" int64_t epi_launch_count(const epi_handle *h) { return h ? h->launche
 
 // ----------------------------------------------------------------- workspace
 int epi_ensure_workspace(epi_handle *h, Workspace &w, const DevModel &M, int64_t n, bool want_series) {
-  const int NG = M.flavour == EPI_FLAVOUR_AGE2Q ? 2 : 1, NK = M.flavour == EPI_FLAVOUR_AGE2Q ? 6 : 2;
-  const int NS = M.flavour == EPI_FLAVOUR_AGE2Q ? 8 : 3;
+  const int NG = is_age(M.flavour) ? 2 : 1, NK = is_age(M.flavour) ? 6 : 2;
+  const int NS = is_age(M.flavour) ? 8 : 3;
   if (n <= w.cap && M.P <= w.P && (!want_series || w.series)) return EPI_OK;
   cudaStreamSynchronize(h->stream);
   const int64_t cap = std::max<int64_t>(n, w.cap);
@@ -405,10 +489,10 @@ int epi_ensure_workspace(epi_handle *h, Workspace &w, const DevModel &M, int64_t
   CUDA_OK(h, cudaMalloc(&w.hist1, sizeof(double) * (size_t)(ld * NG * ((P1 + 1) & ~1))));
   CUDA_OK(h, cudaMalloc(&w.hist2, sizeof(double) * (size_t)(ld * NG * ((P + 1) & ~1))));
   {
-    const int NEQ = M.flavour == EPI_FLAVOUR_AGE2Q ? 10 : 4;
+    const int NEQ = is_age(M.flavour) ? 10 : 4;
     CUDA_OK(h, cudaMalloc(&w.ckpt, sizeof(double) * (size_t)(ld * NEQ * (P1 < 64 ? P1 : 64))));
   }
-  CUDA_OK(h, cudaMalloc(&w.W, sizeof(double) * (size_t)(ld * NG * EPI_MAX_TAPS * 4)));  // [chain][group][delay][4]
+  CUDA_OK(h, cudaMalloc(&w.W, sizeof(double) * (size_t)(ld * NG * pad_rows(M.flavour) * 4)));  // [chain][group][delay][4]
   CUDA_OK(h, cudaMalloc(&w.pmeta, sizeof(int2) * (size_t)(ld * NK)));
   CUDA_OK(h, cudaMalloc(&w.offset, sizeof(int) * (size_t)ld));
   CUDA_OK(h, cudaMalloc(&w.pad, sizeof(int) * (size_t)ld));
@@ -425,16 +509,16 @@ static EvalArgs make_args(epi_handle *h, Workspace &w, const DevModel &M, const 
                           int64_t first, int model_space, double *d_logl, double *d_logp, int *d_status,
                           double *d_terms, double *d_series, cudaStream_t stream) {
   // the chain range [first, first + n) of a batch; `first` is a multiple of the 32-chain tile
-  const int NG = M.flavour == EPI_FLAVOUR_AGE2Q ? 2 : 1, NK = M.flavour == EPI_FLAVOUR_AGE2Q ? 6 : 2;
-  const int NS = M.flavour == EPI_FLAVOUR_AGE2Q ? 8 : 3;
+  const int NG = is_age(M.flavour) ? 2 : 1, NK = is_age(M.flavour) ? 6 : 2;
+  const int NS = is_age(M.flavour) ? 8 : 3;
   EvalArgs a;
   a.M = &M; a.PT = h->PT; a.n_prior = h->n_prior;
   a.theta = d_theta + first; a.ld = ld; a.n = n; a.model_space = model_space;
   a.hist1 = w.hist1 + first * NG * (int64_t)((M.P1 + 1) & ~1);
   a.hist2 = w.hist2 + first * NG * (int64_t)((M.P + 1) & ~1);
-  a.W = w.W + first * NG * EPI_MAX_TAPS * 4;
+  a.W = w.W + first * NG * pad_rows(M.flavour) * 4;
   // (`first` is a multiple of the 32-chain checkpoint tile)
-  a.ckpt = h->restart ? w.ckpt + first * (M.flavour == EPI_FLAVOUR_AGE2Q ? 10 : 4) * (int64_t)(M.P1 < 64 ? M.P1 : 64) : nullptr;
+  a.ckpt = h->restart ? w.ckpt + first * (is_age(M.flavour) ? 10 : 4) * (int64_t)(M.P1 < 64 ? M.P1 : 64) : nullptr;
   a.pmeta = w.pmeta + first * NK;
   a.offset = w.offset + first; a.pad = w.pad + first;
   a.status = (d_status ? d_status : w.status) + first;
@@ -543,12 +627,12 @@ extern "C" int epi_trajectories(epi_handle *h, const double *theta, int64_t n, i
                                 int32_t *offset, int32_t *padding) {
   if (!h || !theta || !out || n < 0) return epi_fail(h, EPI_ERR_ARG, "bad argument");
   if (n == 0) return EPI_OK;
-  const bool age = h->M.flavour == EPI_FLAVOUR_AGE2Q;
-  if (period < (age ? 60 : 2) || period > 4096) return epi_fail(h, EPI_ERR_ARG, "period out of range");
+  const bool age = is_age(h->M.flavour), fixed_p1 = h->M.flavour == EPI_FLAVOUR_AGE2Q;  // 2q: period1 = 60
+  if (period < (fixed_p1 ? 60 : 2) || period > (age ? 2048 : 4096)) return epi_fail(h, EPI_ERR_ARG, "period out of range");
   CUDA_OK(h, cudaSetDevice(h->device));
   DevModel M = h->M;  // calculateModel(params, period): same data, another horizon
   M.P = period;
-  if (!age) M.P1 = period;
+  if (!fixed_p1) M.P1 = period;
   const int NS = age ? 8 : 3;
   int rc = epi_ensure_workspace(h, h->ws_traj, M, n, true);
   if (rc) return rc;
@@ -566,15 +650,15 @@ extern "C" int epi_quantiles(epi_handle *h, const double *theta, int64_t n, int 
                              int32_t series_a, int32_t series_b, const double *probs, int32_t n_probs, double *out) {
   if (!h || !theta || !probs || !out || n < 1 || n_probs < 1 || period < 1) return epi_fail(h, EPI_ERR_ARG, "bad argument");
   if (n > 8192) return epi_fail(h, EPI_ERR_ARG, "epi_quantiles supports at most 8192 draws (got %lld)", (long long)n);
-  const bool age = h->M.flavour == EPI_FLAVOUR_AGE2Q;
+  const bool age = is_age(h->M.flavour), fixed_p1 = h->M.flavour == EPI_FLAVOUR_AGE2Q;
   const int NS = age ? 8 : 3;
   if (series_a < 0 || series_a >= NS || series_b >= NS) return epi_fail(h, EPI_ERR_ARG, "series index out of range");
   const int simperiod = 3 * period;  // libMCMC.R:153
-  if (simperiod < (age ? 60 : 2) || simperiod > 4096) return epi_fail(h, EPI_ERR_ARG, "period out of range");
+  if (simperiod < (fixed_p1 ? 60 : 2) || simperiod > (age ? 2048 : 4096)) return epi_fail(h, EPI_ERR_ARG, "period out of range");
   CUDA_OK(h, cudaSetDevice(h->device));
   DevModel M = h->M;
   M.P = simperiod;
-  if (!age) M.P1 = simperiod;
+  if (!fixed_p1) M.P1 = simperiod;
   int rc = epi_ensure_workspace(h, h->ws_traj, M, n, true);
   if (rc) return rc;
   Workspace &w = h->ws_traj;

@@ -67,18 +67,39 @@ __device__ __forceinline__ void mbar_wait(uint64_t *mbar, unsigned parity) {
 
 template <int FL>
 struct Traits {
-  static constexpr bool kAge = (FL == EPI_FLAVOUR_AGE2Q);
+  static constexpr bool k2i = (FL == EPI_FLAVOUR_AGE2I);  // model-age-groups2i.R + model-agef.cpp
+  static constexpr bool kAge = (FL == EPI_FLAVOUR_AGE2Q) || k2i;
   static constexpr int NEQ = kAge ? 10 : 4;
   static constexpr int NG = kAge ? 2 : 1;   // S series per chain
   static constexpr int NK = kAge ? 6 : 2;   // latency profiles per chain
+  static constexpr int NBP = k2i ? 8 : (kAge ? 10 : 2);  // schedule breakpoints
+  // prefill slots kept in front of a staged S series == largest padding supported == rows of the
+  // absolute-delay profile table: the 2i box lets the death latency reach 50 + 3*9 = 77 days
+  // (model-age-groups2i.R:580-582), every other flavour stays below 64
+  static constexpr int kPad = k2i ? EPI_MAX_PADDING : kPadMax;
 };
 
 // ------------------------------------------------------------------ theta map
 // beta triple (y, o, yo) of schedule index k for the age flavour,
 // R/models/model-age-groups2q.R:52-99 (0-based theta indices here).
+template <int FL>
 __device__ __forceinline__ void age_beta(const double *__restrict__ th, int64_t ld, int k, double &by,
                                          double &bo, double &byo) {
   auto T = [&](int i) { return th[(int64_t)i * ld]; };
+  if constexpr (Traits<FL>::k2i) {
+    // R/models/model-age-groups2i.R:52-93: beta3 = beta2, beta5 = beta4, beta7 = f7 * beta6
+    switch (k) {
+      case 0: by = T(0); bo = T(1); byo = T(2); break;
+      case 1: by = T(3); bo = T(4); byo = T(5); break;
+      case 2:
+      case 3: by = T(6); bo = T(7); byo = T(8); break;
+      case 4:
+      case 5: by = T(26); bo = T(27); byo = T(28); break;
+      case 6: by = T(30); bo = T(31); byo = T(32); break;
+      default: by = T(33) * T(30); byo = T(34) * T(32); bo = T(35) * T(31); break;  // :91-93 (fy7, fyo7, fo7)
+    }
+    return;
+  }
   switch (k) {
     case 0: by = T(0); bo = T(1); byo = T(2); break;
     case 1: by = T(3); bo = T(4); byo = T(5); break;
@@ -93,8 +114,10 @@ __device__ __forceinline__ void age_beta(const double *__restrict__ th, int64_t 
   }
 }
 
-// segment kinds of model-agen.cpp:78-99: 1 = linear towards k+1, 0 = hold
-__device__ __forceinline__ bool age_linear(int k) { return (0x10F >> k) & 1; }  // k = 0,1,2,3,8
+// segment kinds: 1 = linear towards k+1, 0 = hold.  model-agen.cpp:78-99: k = 0,1,2,3,8 linear;
+// model-agef.cpp:66-87: k = 0..5 linear, 6 and 7 hold
+template <int FL>
+__device__ __forceinline__ bool age_linear(int k) { return ((Traits<FL>::k2i ? 0x03F : 0x10F) >> k) & 1; }
 
 // ---------------------------------------------------------------------- K_ode
 // Fixed-step classical RK4, m sub-steps per day, each sub-step cut again at the
@@ -240,7 +263,19 @@ __device__ __forceinline__ void rk4_piece(const DevModel &M, const Seg &sg, doub
 template <int FL>
 __device__ __forceinline__ int breakpoints(const DevModel &M, const double *__restrict__ th, int64_t ld,
                                            double data_offset, double *bp) {
-  if constexpr (Traits<FL>::kAge) {
+  if constexpr (Traits<FL>::k2i) {
+    // model-age-groups2i.R:169-183
+    auto T = [&](int i) { return th[(int64_t)i * ld]; };
+    const double lo = M.lockdown_offset, t0o = T(20);
+    const double t2 = data_offset + lo + M.ltp;
+    const double t3 = t2 + T(24);
+    const double t4 = t3 + T(25);
+    const double t5 = data_offset + M.d5;
+    bp[0] = data_offset + lo + t0o;
+    bp[1] = data_offset + lo + fmax(t0o, 0.0);
+    bp[2] = t2; bp[3] = t3; bp[4] = t4; bp[5] = t5; bp[6] = t5 + T(29); bp[7] = data_offset + M.d7;
+    return 8;
+  } else if constexpr (Traits<FL>::kAge) {
     auto T = [&](int i) { return th[(int64_t)i * ld]; };
     const double lo = M.lockdown_offset, t0o = T(18);
     const double t2 = data_offset + lo + M.ltp;
@@ -277,13 +312,13 @@ __device__ __noinline__ Seg select_segment(const DevModel &M, const double *__re
   Seg sg;
   if constexpr (Traits<FL>::kAge) {
     double by, bo, byo;
-    age_beta(th, ld, k < 0 ? 0 : k, by, bo, byo);
+    age_beta<FL>(th, ld, k < 0 ? 0 : k, by, bo, byo);
     sg.b0 = by; sg.b1 = bo; sg.b2 = byo;
     sg.s0 = sg.s1 = sg.s2 = 0.0;
     sg.tk = 0.0;
-    if (k >= 0 && age_linear(k)) {
+    if (k >= 0 && age_linear<FL>(k)) {
       double ny, no, nyo;
-      age_beta(th, ld, k + 1, ny, no, nyo);
+      age_beta<FL>(th, ld, k + 1, ny, no, nyo);
       const double len = bp[k + 1] - bp[k];
       sg.tk = bp[k];
       sg.s0 = (ny - by) / len; sg.s1 = (no - bo) / len; sg.s2 = (nyo - byo) / len;
@@ -502,6 +537,7 @@ __device__ __forceinline__ void rk4_piece_age2(double a1, double gamma, const Se
   for (int i = 0; i < 5; ++i) y[i] = yn[i];
 }
 
+template <int FL>
 __device__ __noinline__ Seg2 select_segment_age2(const double *__restrict__ th, int64_t ld, const double *bp, int nbp,
                                                  double pa, int is_o, double *tcut) {
   int k = -1;
@@ -512,14 +548,14 @@ __device__ __noinline__ Seg2 select_segment_age2(const double *__restrict__ th, 
   }
   *tcut = tc;
   double by, bo, byo;
-  age_beta(th, ld, k < 0 ? 0 : k, by, bo, byo);
+  age_beta<FL>(th, ld, k < 0 ? 0 : k, by, bo, byo);
   Seg2 sg;
   sg.tk = 0.0; sg.sA = 0.0; sg.sB = 0.0;
   sg.bA = is_o ? bo : by;
   sg.bB = is_o ? byo : 0.0;
-  if (k >= 0 && age_linear(k)) {
+  if (k >= 0 && age_linear<FL>(k)) {
     double ny, no, nyo;
-    age_beta(th, ld, k + 1, ny, no, nyo);
+    age_beta<FL>(th, ld, k + 1, ny, no, nyo);
     const double len = bp[k + 1] - bp[k];
     sg.tk = bp[k];
     sg.sA = is_o ? (no - bo) / len : (ny - by) / len;
@@ -531,12 +567,11 @@ __device__ __noinline__ Seg2 select_segment_age2(const double *__restrict__ th, 
   return sg;
 }
 
-template <bool PASS2>
+template <int FL, bool PASS2>
 __global__ void __maxnreg__(128)
 k_ode_age2(const DevModel M, const double *__restrict__ theta, int64_t ld, int64_t n, const int *__restrict__ offset,
            const int *__restrict__ padv, const double *__restrict__ hist1, double *__restrict__ hist_out,
            double *__restrict__ ckpt) {
-  constexpr int FL = EPI_FLAVOUR_AGE2Q;
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t i = tid >> 1;  // chain
   if (i >= n) return;
@@ -585,7 +620,7 @@ k_ode_age2(const DevModel M, const double *__restrict__ theta, int64_t ld, int64
       }
     }
   }
-  Seg2 sg = select_segment_age2(th, ld, bp, nbp, (double)(t0 + d0), g, &tcut);
+  Seg2 sg = select_segment_age2<FL>(th, ld, bp, nbp, (double)(t0 + d0), g, &tcut);
 
   const int m = M.m;
   const double h = 1.0 / (double)m, a1 = M.a1, gamma = M.gamma;
@@ -603,11 +638,11 @@ k_ode_age2(const DevModel M, const double *__restrict__ theta, int64_t ld, int64
       const double b = (s == m - 1) ? tday + 1.0 : tday + (double)(s + 1) * h;
       double pa = a;
       if constexpr (PASS2) {
-        if (a >= tcut) sg = select_segment_age2(th, ld, bp, nbp, a, g, &tcut);
+        if (a >= tcut) sg = select_segment_age2<FL>(th, ld, bp, nbp, a, g, &tcut);
         while (tcut < b) {
           rk4_piece_age2(a1, gamma, sg, y, pa, tcut, invN, Ngrp, nb, pairmask, even_lane);
           pa = tcut;
-          sg = select_segment_age2(th, ld, bp, nbp, pa, g, &tcut);
+          sg = select_segment_age2<FL>(th, ld, bp, nbp, pa, g, &tcut);
         }
       }
       rk4_piece_age2(a1, gamma, sg, y, pa, b, invN, Ngrp, nb, pairmask, even_lane);
@@ -630,7 +665,7 @@ struct WarpSmem {
   double *pp;      // NK * 4: per-profile (x0, shape|mean, scale|sd, lgamma(shape))
   double *cdf;     // NK * kCdfStride
   double *W;       // NK * EPI_MAX_TAPS
-  double *S;       // NG * (kPadMax + hist_pitch(ndays))
+  double *S;       // NG * (Traits<FL>::kPad + hist_pitch(ndays))
   uint64_t *mbar;  // completion barrier of the bulk history copy
 };
 
@@ -638,7 +673,7 @@ template <int FL>
 __host__ __device__ constexpr int warp_smem_doubles(int ndays) {
   // even (16-byte aligned sub-regions); the last two doubles hold the warp's mbarrier
   return (EPI_MAX_PARAMS + Traits<FL>::NK * 4 + Traits<FL>::NK * kCdfStride + Traits<FL>::NK * EPI_MAX_TAPS +
-          Traits<FL>::NG * (kPadMax + hist_pitch(ndays)) + 3) & ~1;
+          Traits<FL>::NG * (Traits<FL>::kPad + hist_pitch(ndays)) + 3) & ~1;
 }
 
 template <int FL>
@@ -658,7 +693,18 @@ __device__ __forceinline__ WarpSmem carve(double *base, int ndays) {
 // with the NEGATED latency and sd 5 (model-simple-ode-drj-cmp.R:56-57).
 template <int FL>
 __device__ __forceinline__ void profile_params(const double *th, int q, double &mean, double &sd) {
-  if constexpr (Traits<FL>::kAge) {
+  if constexpr (Traits<FL>::k2i) {
+    // model-age-groups2i.R:62-75,96-101 (CLsd is a parameter in this generation)
+    const double CLsd = th[21], HLsd = th[22], DLsd = th[23];
+    switch (q) {
+      case 0: mean = th[10]; sd = CLsd; break;
+      case 1: mean = th[12]; sd = HLsd; break;
+      case 2: mean = th[13]; sd = DLsd; break;
+      case 3: mean = th[15]; sd = CLsd; break;
+      case 4: mean = th[17]; sd = HLsd; break;
+      default: mean = th[18]; sd = DLsd; break;
+    }
+  } else if constexpr (Traits<FL>::kAge) {
     const double CLsd = 5.0, HLsd = th[19], DLsd = th[20];
     switch (q) {
       case 0: mean = th[43]; sd = CLsd; break;
@@ -765,30 +811,32 @@ __device__ __forceinline__ void build_profiles(const WarpSmem &w, const int *n_,
   __syncwarp();
 }
 
-// stage one chain's S history (ndays values per group) behind kPadMax prefill slots: issue the
+// stage one chain's S history (ndays values per group) behind Traits<FL>::kPad prefill slots: issue the
 // bulk copies (one elected lane), fill the prefill slots meanwhile, then wait for the bytes
 template <int FL>
 __device__ __forceinline__ void stage_history_begin(double *S, uint64_t *mbar, const double *__restrict__ hist,
                                                     int64_t chain, int ndays, int lane) {
   constexpr int NG = Traits<FL>::NG;
-  const int pitch = hist_pitch(ndays), stride = kPadMax + pitch;
+  constexpr int PAD = Traits<FL>::kPad;
+  const int pitch = hist_pitch(ndays), stride = PAD + pitch;
   if (lane == 0) mbar_init(mbar, 1);
   __syncwarp();
   if (lane == 0) {
     const unsigned bytes = (unsigned)pitch * 8u;
     mbar_expect_tx(mbar, bytes * NG);
 #pragma unroll
-    for (int g = 0; g < NG; ++g) bulk_g2s(S + g * stride + kPadMax, hist + (chain * NG + g) * (int64_t)pitch, bytes, mbar);
+    for (int g = 0; g < NG; ++g) bulk_g2s(S + g * stride + PAD, hist + (chain * NG + g) * (int64_t)pitch, bytes, mbar);
   }
 }
 template <int FL>
 __device__ __forceinline__ void stage_history_end(const DevModel &M, double *S, uint64_t *mbar, int ndays, int lane) {
   constexpr int NG = Traits<FL>::NG;
-  const int stride = kPadMax + hist_pitch(ndays);
+  constexpr int PAD = Traits<FL>::kPad;
+  const int stride = PAD + hist_pitch(ndays);
 #pragma unroll
   for (int g = 0; g < NG; ++g) {
     const double s0 = Traits<FL>::kAge ? (g == 0 ? M.Ny - 1.0 : M.No) : M.N - 1.0;
-    for (int j = lane; j < kPadMax; j += 32) S[g * stride + j] = s0;
+    for (int j = lane; j < PAD; j += 32) S[g * stride + j] = s0;
   }
   mbar_wait(mbar, 0);
   __syncwarp();
@@ -796,11 +844,12 @@ __device__ __forceinline__ void stage_history_end(const DevModel &M, double *S, 
 
 // convolute(), model-age-groups2q.R:42-45, at padded day index j (sim time t =
 // pad+1+j): sum_o f[o] * x[t - dmin - o]; NA (NaN) while t - dmin < n.
+template <int PAD>
 __device__ __forceinline__ double conv_at(const double *__restrict__ Sg, const double *__restrict__ f, int pad,
                                           int j, int dmin, int n) {
   const int t = pad + 1 + j;
   if (t - dmin < n) return NAN;
-  const double *x = Sg + kPadMax + j - dmin;  // x[t - dmin]
+  const double *x = Sg + PAD + j - dmin;  // x[t - dmin]
   double z = 0.0;
   for (int o = 0; o < n; ++o) z = fma(f[o], x[-o], z);
   return z;
@@ -856,7 +905,8 @@ k_mid(const DevModel M, const double *__restrict__ theta, int64_t ld, int64_t n,
     if (in_pad && okq) pad = max(pad, dmin + nt - 1);
   }
   pad += 1;
-  if (!ok || pad > kPadMax) {
+  constexpr int PAD = Traits<FL>::kPad;
+  if (!ok || pad > PAD) {
     if (lane == 0) { offset[chain] = EPI_INVALID_DATA_OFFSET; padv[chain] = 0; status[chain] = st | EPI_ST_UNSUPPORTED; }
     mbar_wait(w.mbar, 0);  // never leave with a bulk copy into this block's shared memory in flight
     return;
@@ -864,8 +914,8 @@ k_mid(const DevModel M, const double *__restrict__ theta, int64_t ld, int64_t n,
   __syncwarp();
   build_profiles<FL>(w, n_, lane);
   // profiles to HBM already in the absolute-delay layout k_score convolves with,
-  // Wabs[group][delay 0..63][4] (column = profile within the group, zero outside its support), so
-  // that the reader can take the whole 2 KB per group with one bulk copy
+  // Wabs[group][delay 0..kPad-1][4] (column = profile within the group, zero outside its support), so
+  // that the reader can take the whole 2 KB (2.5 KB for age-2i) per group with one bulk copy
   {
     constexpr int KG = NK / NG;
     int *meta = reinterpret_cast<int *>(w.cdf);  // the CDF scratch is free again: (dmin, n) per profile
@@ -873,9 +923,9 @@ k_mid(const DevModel M, const double *__restrict__ theta, int64_t ld, int64_t n,
     for (int q = 0; q < NK; ++q)
       if (lane == 0) { meta[2 * q] = dmin_[q]; meta[2 * q + 1] = n_[q]; }
     __syncwarp();
-    double *dst = Wg + (int64_t)chain * NG * EPI_MAX_TAPS * 4;
-    for (int i = lane; i < NG * EPI_MAX_TAPS * 4; i += 32) {
-      const int c = i & 3, dly = (i >> 2) & (EPI_MAX_TAPS - 1), q = (i / (EPI_MAX_TAPS * 4)) * KG + c;
+    double *dst = Wg + (int64_t)chain * NG * PAD * 4;
+    for (int i = lane; i < NG * PAD * 4; i += 32) {
+      const int c = i & 3, grp = i / (PAD * 4), dly = (i >> 2) - grp * PAD, q = grp * KG + c;
       double v = 0.0;
       if (c < KG) {
         const unsigned o = (unsigned)(dly - meta[2 * q]);
@@ -890,21 +940,21 @@ k_mid(const DevModel M, const double *__restrict__ theta, int64_t ld, int64_t n,
 
   // pass-1 threshold search (:167-182 / simple :88-95)
   stage_history_end<FL>(M, w.S, w.mbar, P1, lane);
-  const int stride = kPadMax + hist_pitch(P1);
+  const int stride = PAD + hist_pitch(P1);
   int first = -1;
-  double thr;
-  if constexpr (Traits<FL>::kAge) thr = w.theta[17]; else thr = w.theta[7];
+  double thr;  // t0_morts (2q :69, 2i :71) / mort_lockdown_threshold
+  if constexpr (Traits<FL>::k2i) thr = w.theta[19]; else if constexpr (Traits<FL>::kAge) thr = w.theta[17]; else thr = w.theta[7];
   for (int base = 0; base < P1 && first < 0; base += 32) {
     const int j = base + lane;
     bool hit = false;
     if (j < P1) {
       double died;
       if constexpr (Traits<FL>::kAge) {
-        const double cy = conv_at(w.S, w.W + 2 * EPI_MAX_TAPS, pad, j, dmin_[2], n_[2]);
-        const double co = conv_at(w.S + stride, w.W + 5 * EPI_MAX_TAPS, pad, j, dmin_[5], n_[5]);
+        const double cy = conv_at<PAD>(w.S, w.W + 2 * EPI_MAX_TAPS, pad, j, dmin_[2], n_[2]);
+        const double co = conv_at<PAD>(w.S + stride, w.W + 5 * EPI_MAX_TAPS, pad, j, dmin_[5], n_[5]);
         died = (M.Ny - cy) * M.ifr_y1 + (M.No - co) * M.ifr_o1;
       } else {
-        const double c = conv_at(w.S, w.W + 1 * EPI_MAX_TAPS, pad, j, dmin_[1], n_[1]);
+        const double c = conv_at<PAD>(w.S, w.W + 1 * EPI_MAX_TAPS, pad, j, dmin_[1], n_[1]);
         died = (M.N - c) * 0.007;
       }
       hit = died > thr;
@@ -984,14 +1034,14 @@ struct DaySlots {
 };
 
 // ---- shared-memory carve-up of k_score / k_series (per warp) -------------------
-// theta[EPI_MAX_PARAMS] | Wabs[NG][EPI_MAX_TAPS][4] | S[NG][kPadMax + P]
+// theta[EPI_MAX_PARAMS] | Wabs[NG][kPad][4] | S[NG][kPad + P]
 // Wabs holds the KG = NK/NG latency profiles of one S group indexed by ABSOLUTE delay
 // (zero outside a profile's support), so that one sweep over the delay feeds KG
 // independent FMA chains from a single S load.
 template <int FL>
 __host__ __device__ constexpr int score_smem_doubles(int ndays) {
   // even, so that every warp's Wabs stays 16-byte aligned for the double2 weight loads
-  return (EPI_MAX_PARAMS + Traits<FL>::NG * EPI_MAX_TAPS * 4 + Traits<FL>::NG * (kPadMax + hist_pitch(ndays)) + 3) & ~1;
+  return (EPI_MAX_PARAMS + Traits<FL>::NG * Traits<FL>::kPad * 4 + Traits<FL>::NG * (Traits<FL>::kPad + hist_pitch(ndays)) + 3) & ~1;
 }
 
 struct ScoreSmem {
@@ -1004,7 +1054,7 @@ __device__ __forceinline__ ScoreSmem carve_score(double *base, int ndays) {
   ScoreSmem w;
   w.theta = base;
   w.Wabs = base + EPI_MAX_PARAMS;
-  w.S = w.Wabs + Traits<FL>::NG * EPI_MAX_TAPS * 4;
+  w.S = w.Wabs + Traits<FL>::NG * Traits<FL>::kPad * 4;
   w.mbar = reinterpret_cast<uint64_t *>(base + score_smem_doubles<FL>(ndays) - 2);
   return w;
 }
@@ -1017,18 +1067,18 @@ __device__ __forceinline__ void stage_score(const DevModel &M, const ScoreSmem &
                                             const double *__restrict__ hist2, const double *__restrict__ Wg,
                                             const int2 *__restrict__ pmeta, int P, int lane, int *dmin_, int *n_,
                                             int *lo, int *hi) {
-  constexpr int NK = Traits<FL>::NK, NG = Traits<FL>::NG, KG = NK / NG;
+  constexpr int NK = Traits<FL>::NK, NG = Traits<FL>::NG, KG = NK / NG, PAD = Traits<FL>::kPad;
   // asynchronous bulk copies (TMA unit): the S rows and the profiles, one mbarrier
   {
-    const int pitch = hist_pitch(P), stride = kPadMax + pitch;
+    const int pitch = hist_pitch(P), stride = PAD + pitch;
     if (lane == 0) mbar_init(w.mbar, 1);
     __syncwarp();
     if (lane == 0) {
-      const unsigned hb = (unsigned)pitch * 8u, wb = (unsigned)(NG * EPI_MAX_TAPS * 4 * 8);
+      const unsigned hb = (unsigned)pitch * 8u, wb = (unsigned)(NG * PAD * 4 * 8);
       mbar_expect_tx(w.mbar, hb * NG + wb);
 #pragma unroll
-      for (int g = 0; g < NG; ++g) bulk_g2s(w.S + g * stride + kPadMax, hist2 + (chain * NG + g) * (int64_t)pitch, hb, w.mbar);
-      bulk_g2s(w.Wabs, Wg + (int64_t)chain * NG * EPI_MAX_TAPS * 4, wb, w.mbar);
+      for (int g = 0; g < NG; ++g) bulk_g2s(w.S + g * stride + PAD, hist2 + (chain * NG + g) * (int64_t)pitch, hb, w.mbar);
+      bulk_g2s(w.Wabs, Wg + (int64_t)chain * NG * PAD * 4, wb, w.mbar);
     }
   }
   for (int p = lane; p < M.d; p += 32) {
@@ -1038,7 +1088,7 @@ __device__ __forceinline__ void stage_score(const DevModel &M, const ScoreSmem &
   }
   __syncwarp();
 #pragma unroll
-  for (int g = 0; g < NG; ++g) { lo[g] = EPI_MAX_TAPS; hi[g] = 0; }
+  for (int g = 0; g < NG; ++g) { lo[g] = PAD; hi[g] = 0; }
 #pragma unroll
   for (int q = 0; q < NK; ++q) {
     const int2 pm = pmeta[(int64_t)chain * NK + q];
@@ -1055,11 +1105,11 @@ __device__ __forceinline__ void stage_score(const DevModel &M, const ScoreSmem &
 //   conv_q(t) = sum_d Wabs[d][q] * S[t - d]
 // (ncu, profiles/r1_v1: the per-profile serial FMA chain with two LDS per FMA left the
 // FP64 pipe 17 % busy; here every S load feeds KG chains and every weight load 2 days.)
-template <int KG>
+template <int KG, int PAD>
 __device__ __forceinline__ void conv_group2(const double *__restrict__ Sg, const double *__restrict__ Wabs, int lo,
                                             int hi, int ja, int P, double *ca, double *cb) {
   const int j0 = min(max(ja, 0), P - 1), j1 = min(max(ja + 32, 0), P - 1);  // out-of-range days are discarded later
-  const double *xa = Sg + kPadMax + j0, *xb = Sg + kPadMax + j1;
+  const double *xa = Sg + PAD + j0, *xb = Sg + PAD + j1;
 #pragma unroll
   for (int q = 0; q < KG; ++q) { ca[q] = 0.0; cb[q] = 0.0; }
 #pragma unroll 4
@@ -1082,14 +1132,17 @@ __device__ __forceinline__ void conv_group2(const double *__restrict__ Sg, const
 // is skipped (series stays 0) unless t1 > padding && t2 > t1.  The index is computed branch-free so
 // that the eleven base-vector loads of a day are issued back to back (profiles/r1_v7: the serial
 // load -> branch -> load chains were 24 % long-scoreboard stalls).
+template <int FL>
 struct AgeMap {
   int t1[6], t2[6];
   bool on[6];  // t1 > pad && t2 > t1, or invalid offset (then rate[1] everywhere, :250)
   bool valid;
   __device__ __forceinline__ void init(const DevModel &M, const double *th, int off_raw, int pad, int P) {
     valid = off_raw != EPI_INVALID_DATA_OFFSET;
-    const double ydl = th[12];  // y.DL is used for both groups (:290,306)
-    const double lat[6] = {th[43], th[11], 0, th[44], th[15], 0};
+    // y.DL is used for both groups (2q :290,306; 2i :264,280)
+    const double ydl = Traits<FL>::k2i ? th[13] : th[12];
+    const double lat[6] = {Traits<FL>::k2i ? th[10] : th[43], Traits<FL>::k2i ? th[12] : th[11], 0,
+                           Traits<FL>::k2i ? th[15] : th[44], Traits<FL>::k2i ? th[17] : th[15], 0};
 #pragma unroll
     for (int q = 0; q < 6; ++q) {
       const int shift = (q == 2 || q == 5) ? 0 : (int)rint(-ydl + lat[q]);
@@ -1108,6 +1161,28 @@ struct AgeMap {
     int k[6];
 #pragma unroll
     for (int q = 0; q < 6; ++q) k[q] = index(M, q, t);
+    if constexpr (Traits<FL>::k2i) {
+      // model-age-groups2i.R:212-304: the rates are the data vectors themselves; products are
+      // left-associative as written there (s2i * yhosp_rate * y.hr[.]), and the InvalidDataOffset
+      // branch of the case series has no pmin (:224,272)
+      const double yifr0 = __ldg(M.y_ifr + k[0]), yhr1 = __ldg(M.y_hr + k[1]), yifr2 = __ldg(M.y_ifr + k[2]);
+      const double oifr3 = __ldg(M.o_ifr + k[3]), ohr4 = __ldg(M.o_hr + k[4]), oifr5 = __ldg(M.o_ifr + k[5]);
+      double r[6];
+      if (valid) {
+        double c0 = th[9] * yifr0, c3 = th[14] * oifr3;
+        c0 = c0 > 1 ? 1.0 : c0; c3 = c3 > 1 ? 1.0 : c3;
+        r[0] = inc[0] * c0; r[3] = inc[3] * c3;
+      } else {
+        r[0] = inc[0] * th[9] * M.ifr_y1; r[3] = inc[3] * th[14] * M.ifr_o1;
+      }
+      r[1] = inc[1] * th[11] * yhr1;
+      r[2] = inc[2] * yifr2;
+      r[4] = inc[4] * th[16] * ohr4;
+      r[5] = inc[5] * oifr5;
+#pragma unroll
+      for (int q = 0; q < 6; ++q) val[q] = on[q] ? r[q] : 0.0;
+      return;
+    }
     // all loads first (model-age-groups2q.R:229-235)
     const double yifr0 = __ldg(M.y_ifr + k[0]), g0 = __ldg(M.g + k[0]);
     const double yhr1 = __ldg(M.y_hr + k[1]), g1 = __ldg(M.g + k[1]);
@@ -1173,7 +1248,8 @@ k_score(const DevModel M, const PriorTerm *__restrict__ PT, int n_prior, const d
   const int T = pad + P;
   const int off_raw = offset[chain];
   const int off = off_raw != EPI_INVALID_DATA_OFFSET ? off_raw : 1;  // :493-494
-  const int stride = kPadMax + hist_pitch(P);
+  constexpr int PAD = Traits<FL>::kPad;
+  const int stride = PAD + hist_pitch(P);
 
   int dstart[kMaxSeries];
   int tlo = pad + 1;
@@ -1184,13 +1260,13 @@ k_score(const DevModel M, const PriorTerm *__restrict__ PT, int n_prior, const d
   const int jlo = tlo - (pad + 1);  // <= 0: scored days before padding+1 read the 0 prefill
 
   if constexpr (Traits<FL>::kAge) {
-    AgeMap map;
+    AgeMap<FL> map;
     map.init(M, w.theta, off_raw, pad, P);
     double carry[6] = {0, 0, 0, 0, 0, 0};
     for (int base = jlo; base < P; base += 64) {
       double ca[6], cb[6];
-      conv_group2<3>(w.S, w.Wabs, lo[0], hi[0], base + lane, P, ca, cb);
-      conv_group2<3>(w.S + stride, w.Wabs + EPI_MAX_TAPS * 4, lo[1], hi[1], base + lane, P, ca + 3, cb + 3);
+      conv_group2<3, PAD>(w.S, w.Wabs, lo[0], hi[0], base + lane, P, ca, cb);
+      conv_group2<3, PAD>(w.S + stride, w.Wabs + PAD * 4, lo[1], hi[1], base + lane, P, ca + 3, cb + 3);
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         const int j = base + 32 * half + lane;
@@ -1221,7 +1297,8 @@ k_score(const DevModel M, const PriorTerm *__restrict__ PT, int n_prior, const d
           // (profile order: ycase, yhosp, ydied, ocase, ohosp, odied)
           const double v5[5] = {val[0], val[3], val[1] + val[4], val[2], val[5]};
           slots.score(M, ltab, v5, acc);
-          if (t >= dstart[2] + M.d_hosp_o1 && t <= dstart[2] + M.d_hosp_o2) { ysum += val[1]; osum += val[4]; }  // :563-564
+          if constexpr (!Traits<FL>::k2i)
+            if (t >= dstart[2] + M.d_hosp_o1 && t <= dstart[2] + M.d_hosp_o2) { ysum += val[1]; osum += val[4]; }  // :563-564
         }
       }
     }
@@ -1232,7 +1309,7 @@ k_score(const DevModel M, const PriorTerm *__restrict__ PT, int n_prior, const d
     double carry[2] = {0, 0};
     for (int base = jlo; base < P; base += 64) {
       double ca[2], cb[2];
-      conv_group2<2>(w.S, w.Wabs, lo[0], hi[0], base + lane, P, ca, cb);
+      conv_group2<2, PAD>(w.S, w.Wabs, lo[0], hi[0], base + lane, P, ca, cb);
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         const int j = base + 32 * half + lane;
@@ -1258,7 +1335,9 @@ k_score(const DevModel M, const PriorTerm *__restrict__ PT, int n_prior, const d
 
   double tv[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   for (int s = 0; s < M.n_series; ++s) tv[M.term_of[s]] = warp_sum(acc[s]) + M.term_const[M.term_of[s]];
-  if constexpr (Traits<FL>::kAge) {
+  if constexpr (Traits<FL>::k2i) {
+    tv[3] = 0.0;  // no hospital-ratio term in this generation (model-age-groups2i.R:526)
+  } else if constexpr (Traits<FL>::kAge) {
     ysum = warp_sum(ysum);
     osum = warp_sum(osum);
     tv[3] = dev_dlnorm_log(ysum / (ysum + osum), log(56.7 / 100), log(1.05));  // :565
@@ -1268,7 +1347,8 @@ k_score(const DevModel M, const PriorTerm *__restrict__ PT, int n_prior, const d
     tv[0] = M.tdl * log(mu) - (M.tdl + M.mort_size) * log(M.mort_size + mu) + M.term_const[0];
   }
   double ll;
-  if constexpr (Traits<FL>::kAge) ll = tv[0] + tv[1] + tv[2] + tv[3] + tv[4] + tv[5];  // :592
+  if constexpr (Traits<FL>::k2i) ll = tv[0] + tv[1] + tv[2] + tv[4] + tv[5];  // 2i :526
+  else if constexpr (Traits<FL>::kAge) ll = tv[0] + tv[1] + tv[2] + tv[3] + tv[4] + tv[5];  // :592
   else ll = tv[0] + tv[1] + tv[2];
   if (ll != ll) st |= EPI_ST_NA;
   if (lane == 0) {
@@ -1305,22 +1385,23 @@ k_series(const DevModel M, const double *__restrict__ theta, int64_t ld, int64_t
   stage_score<FL>(M, w, theta, ld, chain, false, hist2, Wg, pmeta, P, lane, dmin_, n_, lo, hi);
   const int pad = padv[chain];
   const int off_raw = offset[chain];
-  const int stride = kPadMax + hist_pitch(P);
+  constexpr int PAD = Traits<FL>::kPad;
+  const int stride = PAD + hist_pitch(P);
   if constexpr (Traits<FL>::kAge) {
-    AgeMap map;
+    AgeMap<FL> map;
     map.init(M, w.theta, off_raw, pad, P);
     const int dst[6] = {2, 4, 6, 3, 5, 7};
     double carry[6] = {0, 0, 0, 0, 0, 0};
     for (int base = 0; base < P; base += 64) {
       double ca[6], cb[6];
-      conv_group2<3>(w.S, w.Wabs, lo[0], hi[0], base + lane, P, ca, cb);
-      conv_group2<3>(w.S + stride, w.Wabs + EPI_MAX_TAPS * 4, lo[1], hi[1], base + lane, P, ca + 3, cb + 3);
+      conv_group2<3, PAD>(w.S, w.Wabs, lo[0], hi[0], base + lane, P, ca, cb);
+      conv_group2<3, PAD>(w.S + stride, w.Wabs + PAD * 4, lo[1], hi[1], base + lane, P, ca + 3, cb + 3);
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         const int j = base + 32 * half + lane;
         const int t = pad + 1 + j;
         const bool in = j < P;
-        if (in) { o[0 * P + j] = w.S[kPadMax + j]; o[1 * P + j] = w.S[stride + kPadMax + j]; }
+        if (in) { o[0 * P + j] = w.S[PAD + j]; o[1 * P + j] = w.S[stride + PAD + j]; }
         double inc[6], val[6];
 #pragma unroll
         for (int q = 0; q < 6; ++q) {
@@ -1345,13 +1426,13 @@ k_series(const DevModel M, const double *__restrict__ theta, int64_t ld, int64_t
     double carry[2] = {0, 0};
     for (int base = 0; base < P; base += 64) {
       double ca[2], cb[2];
-      conv_group2<2>(w.S, w.Wabs, lo[0], hi[0], base + lane, P, ca, cb);
+      conv_group2<2, PAD>(w.S, w.Wabs, lo[0], hi[0], base + lane, P, ca, cb);
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         const int j = base + 32 * half + lane;
         const int t = pad + 1 + j;
         const bool in = j < P;
-        if (in) o[j] = w.S[kPadMax + j];
+        if (in) o[j] = w.S[PAD + j];
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
           double c = half ? cb[q] : ca[q];
@@ -1458,6 +1539,7 @@ static cudaError_t launch_eval_fl(const EvalArgs &a) {
   const unsigned warp_blocks = (unsigned)((n + 3) / 4);
   const size_t smem_mid = (size_t)4 * warp_smem_doubles<FL>(M.P1) * sizeof(double);
   const size_t smem_score = ((size_t)4 * score_smem_doubles<FL>(M.P) + 2 * kLogTabN) * sizeof(double);
+  if (smem_mid > 200 * 1024 || smem_score > 200 * 1024) return cudaErrorInvalidConfiguration;  // period too long (checked at create)
   static bool attr_done = false;
   if (!attr_done) {
     cudaFuncSetAttribute(k_mid<FL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -1475,14 +1557,14 @@ static cudaError_t launch_eval_fl(const EvalArgs &a) {
   if (!n_sm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
   const bool use_pair = Traits<FL>::kAge && n <= (int64_t)n_sm * 256;
   if (use_pair) {
-    if constexpr (Traits<FL>::kAge) k_ode_age2<false><<<pair_blocks, 64, 0, s>>>(M, a.theta, a.ld, n, nullptr, nullptr, nullptr, a.hist1, a.ckpt);
+    if constexpr (Traits<FL>::kAge) k_ode_age2<FL, false><<<pair_blocks, 64, 0, s>>>(M, a.theta, a.ld, n, nullptr, nullptr, nullptr, a.hist1, a.ckpt);
   } else k_ode<FL, false><<<ode_blocks, 32, 0, s>>>(M, a.theta, a.ld, n, nullptr, nullptr, nullptr, a.hist1, a.ckpt);
   if (a.ev) cudaEventRecord(a.ev[1], s);
   k_mid<FL><<<warp_blocks, 128, smem_mid, s>>>(M, a.theta, a.ld, n, a.hist1, a.offset, a.pad, a.status, a.W, a.pmeta, a.model_space);
   if (a.ev) cudaEventRecord(a.ev[2], s);
   if (a.ev_after_mid) cudaEventRecord(a.ev_after_mid, s);
   if (use_pair) {
-    if constexpr (Traits<FL>::kAge) k_ode_age2<true><<<pair_blocks, 64, 0, s>>>(M, a.theta, a.ld, n, a.offset, a.pad, a.hist1, a.hist2, a.ckpt);
+    if constexpr (Traits<FL>::kAge) k_ode_age2<FL, true><<<pair_blocks, 64, 0, s>>>(M, a.theta, a.ld, n, a.offset, a.pad, a.hist1, a.hist2, a.ckpt);
   } else k_ode<FL, true><<<ode_blocks, 32, 0, s>>>(M, a.theta, a.ld, n, a.offset, a.pad, a.hist1, a.hist2, a.ckpt);
   if (a.ev) cudaEventRecord(a.ev[3], s);
   if (a.series_out) {
@@ -1500,6 +1582,7 @@ cudaError_t launch_eval(const EvalArgs &a) {
   switch (a.M->flavour) {
     case EPI_FLAVOUR_SIMPLE: return launch_eval_fl<EPI_FLAVOUR_SIMPLE>(a);
     case EPI_FLAVOUR_NE: return launch_eval_fl<EPI_FLAVOUR_NE>(a);
+    case EPI_FLAVOUR_AGE2I: return launch_eval_fl<EPI_FLAVOUR_AGE2I>(a);
     default: return launch_eval_fl<EPI_FLAVOUR_AGE2Q>(a);
   }
 }

@@ -57,9 +57,14 @@ class Model:
         self.init = init
         # df_params: data.frame(name, min, max, init), model-age-groups2q.R:637-663
         self.df_params = {"name": list(self.fit_paramnames), "min": mn, "max": mx, "init": init.copy()}
+        self.is_age = self.flavour in ("age2q", "age2i")
         if self.flavour == "age2q":  # model-age-groups2q.R:619-622
             self.keyparamnames = ["betay6", "betao6", "betayo6", "betay7", "betao7", "betayo7",
                                   "fy9", "fo9", "fyo9", "ifrred"]
+            self.fitkeyparamnames = list(self.keyparamnames)
+            self.series_names = AGE_SERIES
+        elif self.flavour == "age2i":  # model-age-groups2i.R:550-551
+            self.keyparamnames = ["betay6", "betao6", "betayo6", "fy7", "fo7", "fyo7"]
             self.fitkeyparamnames = list(self.keyparamnames)
             self.series_names = AGE_SERIES
         else:  # model-simple-ode-drj-cmp.R:261-262
@@ -83,25 +88,31 @@ class Model:
     def transformParams(self, params):
         """model-age-groups2q.R:339-342 (identity); model-simple-ode-drj-cmp.R:136-142."""
         r = np.array(params, dtype=np.float64, copy=True)
-        if self.flavour != "age2q":
+        if not self.is_age:
             r[..., 4] = np.exp(r[..., 4])
         return r
 
     def _untransform(self, params):
         r = np.array(params, dtype=np.float64, copy=True)
-        if self.flavour != "age2q":
+        if not self.is_age:
             r[..., 4] = np.log(r[..., 4])
         return r
 
     def invTransformParams(self, posterior: dict) -> dict:
         """Derived columns of a posterior table (dict of arrays keyed by parameter name)."""
         p = dict(posterior)
-        if self.flavour == "age2q":  # model-age-groups2q.R:344-365
+        if self.is_age:  # model-age-groups2q.R:344-365, model-age-groups2i.R:318-351
             gamma = 1 / ((4.7 - 4) * 2)
             p["Tinf"] = 1 / gamma
-            for k in ("0", "1", "2", "4"):
+            for k in ("0", "1", "2", "4") + (("6",) if self.flavour == "age2i" else ()):
                 for g, pre in (("y", "betay"), ("o", "betao"), ("yo", "betayo")):
                     p[f"{g}.Rt{k}"] = np.asarray(p[pre + k]) / gamma
+            if self.flavour == "age2i":  # :342-349
+                p["betay7"] = np.asarray(p["betay6"]) * np.asarray(p["fy7"])
+                p["betao7"] = np.asarray(p["betao6"]) * np.asarray(p["fo7"])
+                p["betayo7"] = np.asarray(p["betayo6"]) * np.asarray(p["fyo7"])
+                for g, pre in (("y", "betay"), ("o", "betao"), ("yo", "betayo")):
+                    p[f"{g}.Rt7"] = np.asarray(p[pre + "7"]) / gamma
         else:  # model-simple-ode-drj-cmp.R:144-154
             p["Tinc"] = 3
             p["beta0"] = np.asarray(p["R0"]) / np.asarray(p["Tinf0"])
@@ -191,7 +202,7 @@ class Model:
     def calcNominalState(self, state: dict) -> dict:
         """model-age-groups2q.R:367-376"""
         s = dict(state)
-        if self.flavour == "age2q":
+        if self.is_age:
             s["casei"] = s["y_casei"] + s["o_casei"]
             s["deadi"] = s["y_deadi"] + s["o_deadi"]
             s["hospi"] = s["y_hospi"] + s["o_hospi"]

@@ -47,7 +47,7 @@ def test_golden_vectors(name, m):
     assert logl_within_bar(logl + logp, ref_l + ref_p, cond, TOL_LOGL).all()
     # theta[0] is the model file's init: the strict bar, no conditioning allowance
     assert rel_err(logl[:1] + logp[:1], ref_l[:1] + ref_p[:1]).max() <= TOL_LOGL
-    nt = 6 if g["flavour"] == "age2q" else 3
+    nt = 6 if g["flavour"] in ("age2q", "age2i") else 3
     ref_t = np.array([[np.nan if v is None else v for v in row] for row in res["terms"]])[:, :nt]
     # individual terms can be tiny next to logl: compare them on the scale of the total
     scale = np.where(np.isfinite(ref_l), np.abs(ref_l), np.nanmax(np.abs(np.where(np.isfinite(ref_t), ref_t, 0.0)), axis=1))
@@ -60,7 +60,7 @@ def test_golden_vectors(name, m):
     M.close()
 
 
-@pytest.mark.parametrize("name,n", [("S120", 2048), ("NE120", 2048), ("A300", 1024), ("SE_NE", 1024)])
+@pytest.mark.parametrize("name,n", [("S120", 2048), ("NE120", 2048), ("A300", 1024), ("I290", 1024), ("SE_NE", 1024)])
 def test_oracle_live_random_theta(name, n, oracle):
     from epi_mcmc_b200.model import load_dataset
     ds = load_dataset(name)
@@ -91,7 +91,7 @@ def test_oracle_live_random_theta(name, n, oracle):
     M.close()
 
 
-@pytest.mark.parametrize("name,n", [("S365", 512), ("A300", 512), ("A365", 256)])
+@pytest.mark.parametrize("name,n", [("S365", 512), ("A300", 512), ("A365", 256), ("I290", 512)])
 def test_well_conditioned_strict(name, n, oracle):
     """theta close to the model file's init (where the posterior
     mass of the synthetic data sits; +-0.5 % of the box width: the north_star bar holds as stated, 1e-10 relative on
@@ -164,7 +164,7 @@ def test_edge_statuses():
     M.close()
 
 
-@pytest.mark.parametrize("name", ["A300", "S120", "NE120"])
+@pytest.mark.parametrize("name", ["A300", "I290", "S120", "NE120"])
 def test_trajectories_match_oracle(name, oracle):
     """calculateModel(params, period) series, also for a horizon other than FitTotalPeriod
     (quantileData calls it with 3 * period, libMCMC.R:160-161)."""
@@ -198,7 +198,7 @@ def test_trajectories_match_oracle(name, oracle):
     M.close()
 
 
-@pytest.mark.parametrize("name,fun", [("A300", ("y.hospi", "o.hospi")), ("A300", "y.deadi"), ("S120", "hospi")])
+@pytest.mark.parametrize("name,fun", [("A300", ("y.hospi", "o.hospi")), ("A300", "y.deadi"), ("I290", "o.casei"), ("S120", "hospi")])
 def test_quantile_data_matches_reference_semantics(name, fun, oracle):
     """quantileData (libMCMC.R:151-172) on the device against the oracle + numpy: per posterior draw
     calculateModel(params, 3 * period), takeAndPad by the draw's data_offset, per-day R type-7
@@ -232,7 +232,7 @@ def test_quantile_data_matches_reference_semantics(name, fun, oracle):
     M.close()
 
 
-@pytest.mark.parametrize("name,m", [("A300", 4), ("S365", 2), ("NE120", 1)])
+@pytest.mark.parametrize("name,m", [("A300", 4), ("I290", 4), ("S365", 2), ("NE120", 1)])
 def test_pass2_restart_is_bit_identical(name, m, monkeypatch):
     """Pass 2 resumes from the pass-1 checkpoint after its first floor(min breakpoint) - t0 days
     (both passes share the fixed-step scheme and beta0 until then): switching the restart off must
@@ -256,7 +256,7 @@ def test_pass2_restart_is_bit_identical(name, m, monkeypatch):
     B.close()
 
 
-@pytest.mark.parametrize("name,period", [("A300", 301), ("A300", 333), ("S120", 121), ("NE120", 127)])
+@pytest.mark.parametrize("name,period", [("A300", 301), ("A300", 333), ("I290", 291), ("S120", 121), ("NE120", 127)])
 def test_odd_periods(name, period, oracle):
     """FitTotalPeriod values that are odd (rows of the S history are padded to an even pitch for the
     16-byte aligned bulk copies) and not multiples of the 64-day sweep."""
