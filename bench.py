@@ -69,9 +69,9 @@ def make_theta(ds_name, n, seed, mn, mx, init):
 
 def f_alg(flavour, P, m, taps_mean, n_terms, n_prior):
     """ALGORITHMIC FLOP per evaluation, SURVEY.md §8d"""
-    age = flavour == "age2q"
+    age = flavour in ("age2q", "age2i")
     S, K, C1, C2 = (10, 6, 2, 6) if age else (4, 2, 1, 2)
-    P1 = 60 if age else P
+    P1 = 60 if flavour == "age2q" else P  # pass 1: 60 days in 2q, the whole period in 2i / simple
     F_rhs = 124 if age else 72
     steps = m * (P1 + P)
     ode = steps * (4 * F_rhs + 14 * S)
@@ -86,11 +86,16 @@ def f_alg(flavour, P, m, taps_mean, n_terms, n_prior):
 
 
 def mean_taps(flavour, theta):
-    if flavour != "age2q":
+    if flavour not in ("age2q", "age2i"):
         return 16.0
     t = []
-    for lat, sd in ((theta[:, 43], 5.0), (theta[:, 11], theta[:, 19]), (theta[:, 12], theta[:, 20]),
-                    (theta[:, 44], 5.0), (theta[:, 15], theta[:, 19]), (theta[:, 16], theta[:, 20])):
+    if flavour == "age2q":
+        prof = ((theta[:, 43], 5.0), (theta[:, 11], theta[:, 19]), (theta[:, 12], theta[:, 20]),
+                (theta[:, 44], 5.0), (theta[:, 15], theta[:, 19]), (theta[:, 16], theta[:, 20]))
+    else:
+        prof = ((theta[:, 10], theta[:, 21]), (theta[:, 12], theta[:, 22]), (theta[:, 13], theta[:, 23]),
+                (theta[:, 15], theta[:, 21]), (theta[:, 17], theta[:, 22]), (theta[:, 18], theta[:, 23]))
+    for lat, sd in prof:
         kb = np.maximum(0, np.ceil(lat - 3 * sd))
         ke = np.maximum(kb + 1, np.floor(lat + 3 * sd))
         t.append(ke - kb + 1)
@@ -204,6 +209,7 @@ def run_reference(args):
 
 def workload_name(args, period):
     what = {"A": "age-structured model-age-groups2q (BASELINE.json configs[2])",
+            "I": "age-structured model-age-groups2i (secondary anchor of BASELINE.json configs[2])",
             "S": "simple SEIR model-simple-ode-drj-cmp (BASELINE.json configs[3])",
             "N": "simple SEIR + effective population size Ne (BASELINE.json configs[1])"}.get(args.workload[0], args.workload)
     return f"{args.workload}: {what}, synthetic {period}-day series, {args.chains} chains per GPU, RK4 m={args.substeps}"
@@ -311,7 +317,7 @@ def main():
     # kernel with the largest share of the step
     peak_tf = M.fp64_peak_tflops()
     fa = f_alg(ds["flavour"], ds["period"], args.substeps, mean_taps(ds["flavour"], theta), _n_terms(M),
-               38 if ds["flavour"] == "age2q" else 3)
+               {"age2q": 38, "age2i": 24}.get(ds["flavour"], 3))
     # pass-2 restart: D leading days are taken from the pass-1 checkpoint instead of being integrated
     # again (bit-identical).  SURVEY §8d: report F_alg with the reduced step count too.
     off_s, pad_s, _ = M.eval_detail(theta[:4096])
@@ -319,6 +325,9 @@ def main():
     if ds["flavour"] == "age2q":
         minbp = off_s + lo_ + theta[:4096, 18]
         cap = 59
+    elif ds["flavour"] == "age2i":
+        minbp = off_s + lo_ + theta[:4096, 20]
+        cap = min(ds["period"], 64) - 1
     else:
         minbp = (off_s + lo_).astype(float)
         cap = min(ds["period"], 64) - 1
@@ -392,6 +401,8 @@ def _n_terms(M):
     if ds["flavour"] == "age2q":
         n = ds["n_dcasei"]
         return 2 * (n + 2) + (ds["n_dhospi"] + 10) + 1 + 2 * ds["n_dmorti"]
+    if ds["flavour"] == "age2i":
+        return 2 * (ds["n_dcasei"] + 2) + ds["n_dhospi"] + 2 * ds["n_dmorti"]
     return ds["n_dhospi"] + ds["n_dmorti"] + 1
 
 
@@ -399,6 +410,8 @@ def _ws_mb(ds, n):
     P = ds["period"]
     if ds["flavour"] == "age2q":
         return n * ((P + 60) * 2 * 8 + 6 * 64 * 8) / 1e6
+    if ds["flavour"] == "age2i":
+        return n * (2 * P * 2 * 8 + 2 * 80 * 4 * 8) / 1e6
     return n * (2 * P * 8 + 2 * 64 * 8) / 1e6
 
 

@@ -1,0 +1,102 @@
+## model-age-groups2i-gpu.R — drop-in for R/models/model-age-groups2i.R (analyses/be/age/settings.R).
+##
+## SOURCE ONLY here (no R in the build image).  Use it exactly like the reference model
+## file: set `fitmodel` in settings.R to this file; fitMCMC-drj.R then sources data ->
+## this file -> libfit.R unchanged.  Everything the reference file defines keeps its name
+## and meaning (fit.paramnames, keyparamnames, init, df_params, transformParams,
+## invTransformParams, calcNominalState, calclogp, calclogl, calculateModel); only the
+## bodies of calclogl / calclogp / calculateModel call the GPU through the .Call shim, and
+## the batched entry points the GPU is for are added next to them.
+
+dyn.load("epimcmc_shim.so")            # replaces: system("R CMD SHLIB model-agef.cpp"); dyn.load("model-agef.so")
+
+InvalidDataOffset <- 10000
+G <- 4.7; Tinc1 <- 3; Tinc2 <- 1
+gamma <- 1/((G - (Tinc1 + Tinc2)) * 2)
+
+if (!exists("epi_substeps")) epi_substeps <- 4        # RK4 sub-steps per day of the fixed-step integrator
+if (!exists("epi_device")) epi_device <- 0
+
+epi_globals <- list(
+    y_N = y.N, o_N = o.N, total_deaths_at_lockdown = total_deaths_at_lockdown,
+    dmort_last = dmort[length(dmort)],
+    lockdown_offset = lockdown_offset, lockdown_transition_period = lockdown_transition_period,
+    d3 = d3, d4 = d4, d5 = d5, d7 = d7,
+    d_reliable_cases = d.reliable.cases,
+    dhospi = as.numeric(dhospi), n_dhosp = length(dhosp),
+    y_dcasei = as.numeric(y.dcasei), o_dcasei = as.numeric(o.dcasei),
+    y_dmorti = as.numeric(y.dmorti), o_dmorti = as.numeric(o.dmorti),
+    y_ifr = y.ifr, o_ifr = o.ifr, y_hr = y.hr, o_hr = o.hr,
+    ## this generation has ONE regime-2 case size (analyses/be/age/settings.R:31): it fills both slots
+    case_nbinom_size1 = case_nbinom_size1, case_nbinom_sizey2 = case_nbinom_size2,
+    case_nbinom_sizeo2 = case_nbinom_size2, hosp_nbinom_size = hosp_nbinom_size,
+    mort_nbinom_size = mort_nbinom_size)
+
+## handle creation snapshots every global above (EPI_FLAVOUR_AGE2I = 3)
+epi_handle <- .Call("C_epi_create", 3L, as.integer(FitTotalPeriod), as.integer(epi_substeps), epi_globals,
+                    as.integer(epi_device))
+
+meta <- .Call("C_epi_df_params", epi_handle)
+fit.paramnames <- meta[[1]]
+init <- meta[[4]]
+df_params <- data.frame(name = fit.paramnames, min = meta[[2]], max = meta[[3]], init = init)
+keyparamnames <- c("betay6", "betao6", "betayo6", "fy7", "fo7", "fyo7")
+fitkeyparamnames <- keyparamnames
+
+transformParams <- function(params) params
+
+invTransformParams <- function(posterior) {
+    posterior$Tinf <- 1/gamma
+    ## model-age-groups2i.R:318-351
+    posterior$betay7 <- posterior$betay6 * posterior$fy7
+    posterior$betao7 <- posterior$betao6 * posterior$fo7
+    posterior$betayo7 <- posterior$betayo6 * posterior$fyo7
+    for (k in c("0", "1", "2", "4", "6", "7")) {
+        posterior[[paste0("y.Rt", k)]] <- posterior[[paste0("betay", k)]] / gamma
+        posterior[[paste0("o.Rt", k)]] <- posterior[[paste0("betao", k)]] / gamma
+        posterior[[paste0("yo.Rt", k)]] <- posterior[[paste0("betayo", k)]] / gamma
+    }
+    posterior
+}
+
+## batched: theta is a d x n matrix, one proposal per column
+calclogpost_batch <- function(theta) {
+    r <- .Call("C_epi_logpost", epi_handle, theta)
+    list(logl = r[[1]], logp = r[[2]], status = r[[3]])
+}
+calclogl_batch <- function(theta) calclogpost_batch(theta)$logl
+
+## the reference's scalar API (drjacoby calls these once per proposal: correct, but the GPU idles)
+calclogl <- function(params, x) {
+    it <<- it + 1
+    calclogpost_batch(matrix(params, ncol = 1))$logl
+}
+calclogp <- function(params) calclogpost_batch(matrix(params, ncol = 1))$logp
+
+series.names <- c("y.S", "o.S", "y.casei", "o.casei", "y.hospi", "o.hospi", "y.deadi", "o.deadi")
+calculateModel_batch <- function(params, period) {
+    r <- .Call("C_epi_trajectories", epi_handle, params, as.integer(period))
+    arr <- array(r[[1]], dim = c(period, length(series.names), ncol(params)))
+    list(series = arr, offset = r[[2]], padding = r[[3]])
+}
+calculateModel <- function(params, period) {
+    r <- calculateModel_batch(matrix(params, ncol = 1), period)
+    padding <- r$padding[1]
+    state <- NULL
+    for (k in seq_along(series.names))
+        state[[series.names[k]]] <- c(rep(if (k == 1) y.N - 1 else if (k == 2) o.N else 0, padding), r$series[, k, 1])
+    state$y.died <- cumsum(state$y.deadi); state$o.died <- cumsum(state$o.deadi)
+    state$y.case <- cumsum(state$y.casei); state$o.case <- cumsum(state$o.casei)
+    state$padding <- padding
+    state$offset <- r$offset[1]
+    state
+}
+
+calcNominalState <- function(state) {
+    state$case <- state$y.case + state$o.case
+    state$died <- state$y.died + state$o.died
+    state$casei <- state$y.casei + state$o.casei
+    state$deadi <- state$y.deadi + state$o.deadi
+    state$hospi <- state$y.hospi + state$o.hospi
+    state
+}
