@@ -12,7 +12,8 @@ data-path collective).  Workload = BASELINE.json configs[2]: the age-structured 
 JSON line keys beyond the base contract:
   roofline      dominant kernel (pass-2 ODE) against the FP64 DFMA peak measured live
   cpu_baseline  the CPU oracle ("port": R is not installed) on a bounded sample, all host threads
-  e2e           the same metric through epi_eval() with pinned HOST buffers (H2D + D2H inside)
+  e2e           the same metric through the host-buffer C ABI (epi_eval_submit/wait, and epi_eval beside it)
+                with pinned HOST buffers (H2D + D2H inside)
   kernels       mean device ms of the four launches of one step
   f_alg         algorithmic FLOP per evaluation (SURVEY.md §8d formula) and the whole-step fraction
   sampler       fused propose/accept DE-MC run: evals/s inside the sampler and ESS/s
@@ -288,19 +289,41 @@ def main():
     M.set_timing(False)
     torch.cuda.synchronize(dev)
 
-    # ---- e2e arm: the public C-ABI call with pinned HOST buffers, copies inside the timed region
-    th_host = torch.from_numpy(theta.copy()).pin_memory()
-    ll_host = torch.empty(n, dtype=torch.float64).pin_memory()
-    lp_host = torch.empty(n, dtype=torch.float64).pin_memory()
-    st_host = torch.empty(n, dtype=torch.int32).pin_memory()
+    # ---- e2e arm: the public C-ABI with pinned HOST buffers, copies inside the timed region.
+    # (a) epi_eval: one blocking call per step (H2D -> kernels -> D2H strictly in sequence);
+    # (b) epi_eval_submit / epi_eval_wait: the same step, double-buffered — step k+1 is submitted before
+    #     step k is waited for, so its input copy (copy stream) overlaps the kernels of step k.  Every
+    #     step still moves its own n x d inputs from pinned host memory and its n x 20 B of results back.
+    # `e2e.value` is (b), the API a host-side driver with two independent batches in flight uses;
+    # (a) is reported beside it as e2e.blocking_call_value.
     from epi_mcmc_b200 import _capi
     import ctypes as C
+    th_host = [torch.from_numpy(theta.copy()).pin_memory() for _ in range(2)]
+    ll_host = [torch.empty(n, dtype=torch.float64).pin_memory() for _ in range(2)]
+    lp_host = [torch.empty(n, dtype=torch.float64).pin_memory() for _ in range(2)]
+    st_host = [torch.empty(n, dtype=torch.int32).pin_memory() for _ in range(2)]
+    dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int32)
 
     def e2e_step():
-        _capi.check(M._lib.epi_eval(M._h, C.cast(th_host.data_ptr(), C.POINTER(C.c_double)), n, _capi.LAYOUT_AOS,
-                                    C.cast(ll_host.data_ptr(), C.POINTER(C.c_double)),
-                                    C.cast(lp_host.data_ptr(), C.POINTER(C.c_double)),
-                                    C.cast(st_host.data_ptr(), C.POINTER(C.c_int32))), M._h)
+        _capi.check(M._lib.epi_eval(M._h, C.cast(th_host[0].data_ptr(), dp), n, _capi.LAYOUT_AOS,
+                                    C.cast(ll_host[0].data_ptr(), dp), C.cast(lp_host[0].data_ptr(), dp),
+                                    C.cast(st_host[0].data_ptr(), ip)), M._h)
+
+    def submit(k):
+        b = k & 1
+        _capi.check(M._lib.epi_eval_submit(M._h, b, C.cast(th_host[b].data_ptr(), dp), n, _capi.LAYOUT_AOS,
+                                           C.cast(ll_host[b].data_ptr(), dp), C.cast(lp_host[b].data_ptr(), dp),
+                                           C.cast(st_host[b].data_ptr(), ip)), M._h)
+
+    def wait(k):
+        _capi.check(M._lib.epi_eval_wait(M._h, k & 1), M._h)
+
+    def pipelined(steps):
+        submit(0)
+        for k in range(1, steps):
+            submit(k)
+            wait(k - 1)
+        wait(steps - 1)
 
     for _ in range(max(1, args.warmup)):
         e2e_step()
@@ -308,9 +331,18 @@ def main():
     t0 = time.perf_counter()
     for _ in range(args.steps):
         e2e_step()       # returns after the D2H copies completed (stream synchronised inside)
+    e2e_block_s = comm.max_over_ranks(time.perf_counter() - t0)
+    e2e_block_value = comm.world * n * args.steps / e2e_block_s
+    assert np.allclose(ll_host[0].numpy(), logl.cpu().numpy(), rtol=0, atol=0, equal_nan=True)
+    ll_host[0].zero_(); ll_host[1].zero_()
+    pipelined(max(2, args.warmup))
+    comm.barrier()
+    t0 = time.perf_counter()
+    pipelined(args.steps)
     e2e_s = comm.max_over_ranks(time.perf_counter() - t0)
     e2e_value = comm.world * n * args.steps / e2e_s
-    assert np.allclose(ll_host.numpy(), logl.cpu().numpy(), rtol=0, atol=0, equal_nan=True)
+    for b in range(2):
+        assert np.allclose(ll_host[b].numpy(), logl.cpu().numpy(), rtol=0, atol=0, equal_nan=True)
     clocks.stop()
 
     # ---- rooflines: every launch of the step against the FP64 peak measured live; `roofline` is the
@@ -365,7 +397,9 @@ def main():
                          f"{_ws_mb(ds, n):.0f} MB vs 126 MB L2",
                    "parallelism": f"chains sharded over {comm.world} GPU(s), no data-path collective"},
         "clocks": clocks.summary(),
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n * d * 8), "d2h_bytes_per_step": int(n * 20)},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n * d * 8), "d2h_bytes_per_step": int(n * 20),
+                "api": "epi_eval_submit/epi_eval_wait, two batches in flight (input copy of step k+1 overlaps the kernels of step k)",
+                "blocking_call_value": e2e_block_value, "blocking_call_api": "epi_eval, one blocking call per step"},
         "gpu_launches": int(launches),
         "kernels": {"ode_pass1_ms": float(kms[0]), "profiles_threshold_ms": float(kms[1]), "ode_pass2_ms": float(kms[2]),
                     "score_ms": float(kms[3])},

@@ -450,6 +450,11 @@ extern "C" void epi_destroy(epi_handle *h) {
   if (h->stream2) cudaStreamDestroy(h->stream2);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
+  if (h->ev_stagger) cudaEventDestroy(h->ev_stagger);
+  for (int s = 0; s < 2; ++s) {
+    cudaFree(h->stage[s]);
+    if (h->ev_h2d[s]) { cudaEventDestroy(h->ev_h2d[s]); cudaEventDestroy(h->ev_free[s]); cudaEventDestroy(h->ev_done[s]); }
+  }
   delete h;
 }
 
@@ -603,6 +608,68 @@ extern "C" int epi_eval(epi_handle *h, const double *theta, int64_t n, int layou
   if (logp) CUDA_OK(h, cudaMemcpyAsync(logp, w.logp, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
   if (status) CUDA_OK(h, cudaMemcpyAsync(status, w.status, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
   CUDA_OK(h, cudaStreamSynchronize(h->stream));
+  return EPI_OK;
+}
+
+extern "C" int epi_eval_submit(epi_handle *h, int slot, const double *theta, int64_t n, int layout, double *logl,
+                               double *logp, int32_t *status) {
+  if (!h || !theta || n < 1 || slot < 0 || slot > 1) return epi_fail(h, EPI_ERR_ARG, "bad argument");
+  if (layout != EPI_LAYOUT_AOS && layout != EPI_LAYOUT_SOA) return epi_fail(h, EPI_ERR_ARG, "unknown layout %d", layout);
+  if (h->slot_pending[slot]) return epi_fail(h, EPI_ERR_STATE, "slot %d has a submission that was not waited for", slot);
+  CUDA_OK(h, cudaSetDevice(h->device));
+  if (n > h->ws.cap) {  // growing the workspace frees buffers the other slot's kernels may still use
+    for (int s = 0; s < 2; ++s)
+      if (h->slot_pending[s]) CUDA_OK(h, cudaEventSynchronize(h->ev_done[s]));
+  }
+  int rc = epi_ensure_workspace(h, h->ws, h->M, n, false);
+  if (rc) return rc;
+  Workspace &w = h->ws;
+  const int d = h->M.d;
+  if (!h->ev_h2d[slot]) {
+    cudaEventCreateWithFlags(&h->ev_h2d[slot], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h->ev_free[slot], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h->ev_done[slot], cudaEventDisableTiming);
+  }
+  if (n * d > h->stage_cap[slot]) {
+    if (h->slot_used[slot]) CUDA_OK(h, cudaEventSynchronize(h->ev_free[slot]));
+    cudaFree(h->stage[slot]);
+    h->stage[slot] = nullptr;
+    h->stage_cap[slot] = 0;
+    CUDA_OK(h, cudaMalloc(&h->stage[slot], sizeof(double) * (size_t)(n * d)));
+    h->stage_cap[slot] = n * d;
+  }
+  cudaStream_t cs = h->stream2, ks = h->stream;
+  // copy stream: the staging buffer is free once the previous user's re-layout has read it
+  if (h->slot_used[slot]) CUDA_OK(h, cudaStreamWaitEvent(cs, h->ev_free[slot], 0));
+  CUDA_OK(h, cudaMemcpyAsync(h->stage[slot], theta, sizeof(double) * (size_t)(n * d), cudaMemcpyHostToDevice, cs));
+  CUDA_OK(h, cudaEventRecord(h->ev_h2d[slot], cs));
+  // compute stream: re-layout into the SoA workspace (ordered after the previous batch's kernels), evaluate, return
+  CUDA_OK(h, cudaStreamWaitEvent(ks, h->ev_h2d[slot], 0));
+  if (layout == EPI_LAYOUT_AOS) {
+    cudaError_t e = launch_aos_to_soa(h->stage[slot], w.theta, n, d, w.ld, ks);
+    h->launches += 1;
+    if (e != cudaSuccess) return epi_fail(h, EPI_ERR_CUDA, "transpose: %s", cudaGetErrorString(e));
+  } else {
+    CUDA_OK(h, cudaMemcpy2DAsync(w.theta, sizeof(double) * (size_t)w.ld, h->stage[slot], sizeof(double) * (size_t)n,
+                                 sizeof(double) * (size_t)n, d, cudaMemcpyDeviceToDevice, ks));
+  }
+  CUDA_OK(h, cudaEventRecord(h->ev_free[slot], ks));
+  h->slot_used[slot] = true;
+  if ((rc = epi_launch_eval_ws(h, w, h->M, w.theta, w.ld, n, 0, w.logl, w.logp, nullptr, nullptr, nullptr, ks))) return rc;
+  if (logl) CUDA_OK(h, cudaMemcpyAsync(logl, w.logl, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, ks));
+  if (logp) CUDA_OK(h, cudaMemcpyAsync(logp, w.logp, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, ks));
+  if (status) CUDA_OK(h, cudaMemcpyAsync(status, w.status, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, ks));
+  CUDA_OK(h, cudaEventRecord(h->ev_done[slot], ks));
+  h->slot_pending[slot] = true;
+  return EPI_OK;
+}
+
+extern "C" int epi_eval_wait(epi_handle *h, int slot) {
+  if (!h || slot < 0 || slot > 1) return epi_fail(h, EPI_ERR_ARG, "bad argument");
+  if (!h->slot_pending[slot]) return epi_fail(h, EPI_ERR_STATE, "nothing submitted on slot %d", slot);
+  CUDA_OK(h, cudaSetDevice(h->device));
+  CUDA_OK(h, cudaEventSynchronize(h->ev_done[slot]));
+  h->slot_pending[slot] = false;
   return EPI_OK;
 }
 

@@ -45,6 +45,12 @@ struct epi_handle {
   int split_mode = 1;
   bool restart = true;  // pass 2 resumes from the pass-1 checkpoint (EPI_PASS2_RESTART=0: re-integrate everything)
   bool split = false;  // EPI_SPLIT_STREAMS=1: run the two halves of a large batch on two streams (measured slower: 6.41 vs 6.03 ms)
+  // epi_eval_submit/wait: two staging buffers for the raw host theta and the events that order
+  // copy stream (stream2) and compute stream
+  double *stage[2] = {nullptr, nullptr};
+  int64_t stage_cap[2] = {0, 0};
+  cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+  bool slot_used[2] = {false, false}, slot_pending[2] = {false, false};
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   bool timing = false;
   int64_t launches = 0;

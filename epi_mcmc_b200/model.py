@@ -139,6 +139,30 @@ class Model:
         self.it += n
         return logl, logp, status
 
+    def calclogpost_submit(self, slot: int, theta, layout="aos"):
+        """Asynchronous calclogpost_batch (epi_eval_submit): queue the batch on `slot` (0 or 1) and
+        return; `calclogpost_wait(slot)` hands back (logl, logp, status).  With two slots the input
+        copy of the next batch overlaps the kernels of the current one."""
+        th = np.ascontiguousarray(np.asarray(theta, dtype=np.float64))
+        if th.ndim == 1:
+            th = th[None, :]
+        n = th.shape[0] if layout == "aos" else th.shape[1]
+        assert (th.shape[1] if layout == "aos" else th.shape[0]) == self.d, th.shape
+        logl, logp = np.empty(n), np.empty(n)
+        status = np.empty(n, dtype=np.int32)
+        _capi.check(self._lib.epi_eval_submit(self._h, slot, _capi.as_dp(th), n,
+                                              _capi.LAYOUT_AOS if layout == "aos" else _capi.LAYOUT_SOA,
+                                              _capi.as_dp(logl), _capi.as_dp(logp), _capi.as_ip(status)), self._h)
+        if not hasattr(self, "_pending"):
+            self._pending = {}
+        self._pending[slot] = (th, logl, logp, status)  # keep the host buffers alive until the wait
+        self.it += n
+
+    def calclogpost_wait(self, slot: int):
+        _capi.check(self._lib.epi_eval_wait(self._h, slot), self._h)
+        _, logl, logp, status = self._pending.pop(slot)
+        return logl, logp, status
+
     def calclogl_batch(self, params_model):
         """calclogl over MODEL-space rows (already through transformParams)."""
         return self.calclogpost_batch(self._untransform(np.atleast_2d(params_model)))[0]

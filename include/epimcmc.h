@@ -173,6 +173,17 @@ int epi_df_params(const epi_handle *h, double *min, double *max, double *init);
 int epi_eval(epi_handle *h, const double *theta, int64_t n, int layout,
              double *logl, double *logp, int32_t *status);
 
+/* Asynchronous pair for back-to-back host batches.  epi_eval_submit queues the host->device
+ * copy (on the handle's copy stream), the evaluation and the device->host copies of the results
+ * and returns; epi_eval_wait blocks until that submission's results are in the host buffers.
+ * Two submissions may be in flight (slot 0 and 1): the input copy of batch k+1 then overlaps the
+ * kernels of batch k.  All host buffers must stay valid until the matching epi_eval_wait and
+ * should be page-locked (pageable memory works but serialises the copy).  Same results as
+ * epi_eval, bit for bit.                                                      */
+int epi_eval_submit(epi_handle *h, int slot, const double *theta, int64_t n, int layout,
+                    double *logl, double *logp, int32_t *status);
+int epi_eval_wait(epi_handle *h, int slot);
+
 /* Same, all buffers already resident on the handle's device.  theta_soa is
  * d x n (EPI_LAYOUT_SOA).  Launches on `stream` (a cudaStream_t passed as
  * void*, NULL = the handle's own stream) and does not synchronise.            */
