@@ -234,3 +234,47 @@ def write_max_csv(path: str, theta_best: np.ndarray):
         w.writerow(["", "x"])
         for i, v in enumerate(theta_best):
             w.writerow([str(i + 1), float(v)])
+
+
+def read_max_csv(path: str, d: int) -> np.ndarray:
+    """The warm start of fitMCMC-drj.R:8-13: `r <- read.csv("max.csv"); init <- r$x[2:(length(init) + 1)]`
+    (x[1] is the log-posterior of the stored maximum)."""
+    with open(path, newline="") as f:
+        rows = list(csv.reader(f))
+    col = rows[0].index("x")
+    x = [float(r[col]) for r in rows[1:]]
+    if len(x) < d + 1:
+        raise ValueError(f"{path}: {len(x)} values, need 1 + {d}")
+    return np.array(x[1:d + 1])
+
+
+def read_chain_csv(files, model) -> dict:
+    """readData (libMCMC.R:6-24): read and row-bind one or more sample files, then invTransformParams.
+    Returns a dict of columns (numeric columns as float arrays)."""
+    cols: dict = {}
+    for path in ([files] if isinstance(files, str) else list(files)):
+        with open(path, newline="") as f:
+            rd = csv.reader(f)
+            header = next(rd)
+            data = list(rd)
+        for j, name in enumerate(header):
+            cols.setdefault(name or "X", []).extend(r[j] for r in data)
+    out = {}
+    for name, v in cols.items():
+        try:
+            out[name] = np.array([float(x) for x in v])
+        except ValueError:
+            out[name] = np.array(v)
+    return model.invTransformParams(out)
+
+
+def dic(model, posterior: dict) -> dict:
+    """DIC() of analyzeMCMC.R:26-44 on a posterior table (columns = fit.paramnames + loglikelihood):
+    D.bar = -2 mean(lik), D.hat = -2 calclogl(transformParams(mean theta)) — one evaluation on the GPU."""
+    lik = np.asarray(posterior["loglikelihood"], dtype=np.float64)
+    theta_bar = np.array([np.mean(posterior[nm]) for nm in model.fit_paramnames])
+    d_bar = -2.0 * float(np.mean(lik))
+    d_hat = -2.0 * model.calclogl(model.transformParams(theta_bar))
+    p_d = d_bar - d_hat
+    p_v = float(np.var(-2.0 * lik, ddof=1)) / 2.0
+    return dict(DIC=p_d + d_bar, DIC2=p_v + d_bar, IC=2 * p_d + d_bar, pD=p_d, pV=p_v, Dbar=d_bar, Dhat=d_hat)

@@ -202,3 +202,41 @@ def test_chain_csv_schema(tmp_path):
     assert rows[0] == ["", "chain", "rung", "phase", "iteration"] + M.fit_paramnames + ["logprior", "loglikelihood"]
     assert len(rows) == 11 and rows[1][3] == "sampling"
     M.close()
+
+
+def test_sample_file_round_trip_warm_start_and_dic(tmp_path, oracle):
+    """The files either side of the path: write.csv schema (fitMCMC-drj.R:60-62) -> readData
+    (libMCMC.R:6-24, incl. invTransformParams) -> DIC (analyzeMCMC.R:26-44); max.csv -> warm start
+    (fitMCMC-drj.R:8-13)."""
+    from epi_mcmc_b200.model import load_dataset
+    from epi_mcmc_b200.sampler import (dic, read_chain_csv, read_max_csv, run_mcmc, write_chain_csv, write_max_csv)
+    M = _model("S120", 2)
+    r = run_mcmc(M, burnin=40, samples=30, chains=64, kind="demc", seed=5)
+    draws = r["draws"]
+    k, n, d = draws.shape
+    flat = draws.reshape(k * n, d)
+    ll, lp, _ = M.calclogpost_batch(flat)
+    ll, lp = ll.reshape(k, n), lp.reshape(k, n)
+    files = []
+    for c in (0, 1):
+        path = tmp_path / f"run_{c + 1}"
+        write_chain_csv(str(path), M, draws, c, logprior=lp, loglike=ll)
+        files.append(str(path))
+    post = read_chain_csv(files, M)
+    assert len(post["loglikelihood"]) == 2 * k
+    for j, nm in enumerate(M.fit_paramnames):
+        assert np.array_equal(post[nm], np.concatenate([draws[:, 0, j], draws[:, 1, j]]))
+    assert np.allclose(post["beta0"], post["R0"] / post["Tinf0"]) and np.allclose(post["HR"], np.exp(post["logHR"]))
+    got = dic(M, post)
+    lik = post["loglikelihood"]
+    theta_bar = np.array([post[nm].mean() for nm in M.fit_paramnames])
+    ref_hat = oracle.evaluate("simple", load_dataset("S120"), theta_bar[None], 120, 2)["logl"][0]
+    d_bar = -2 * lik.mean()
+    assert abs(got["Dbar"] - d_bar) < 1e-9 and abs(got["Dhat"] + 2 * ref_hat) <= 1e-9 * abs(ref_hat)
+    assert abs(got["DIC"] - (2 * d_bar + 2 * ref_hat)) <= 1e-8 * abs(d_bar)
+    assert abs(got["pV"] - np.var(-2 * lik, ddof=1) / 2) < 1e-9
+    # warm start: max.csv = c(maxLogP, params)
+    best = np.unravel_index(np.argmax(ll + lp), ll.shape)
+    write_max_csv(str(tmp_path / "max.csv"), np.concatenate([[ll[best] + lp[best]], draws[best]]))
+    assert np.array_equal(read_max_csv(str(tmp_path / "max.csv"), M.d), draws[best])
+    M.close()
