@@ -102,7 +102,7 @@ _lib = None
 SYMBOLS = (
     "epi_create", "epi_destroy", "epi_last_error", "epi_abi_version", "epi_n_params",
     "epi_param_name", "epi_df_params", "epi_eval", "epi_eval_submit", "epi_eval_wait", "epi_eval_device", "epi_eval_detail",
-    "epi_n_series", "epi_trajectories", "epi_quantiles", "epi_sampler_init", "epi_sampler_run",
+    "epi_n_series", "epi_trajectories", "epi_n_series_ext", "epi_trajectories_ext", "epi_quantiles", "epi_sampler_init", "epi_sampler_run",
     "epi_sampler_adapt", "epi_sampler_state_device", "epi_sampler_set_population",
     "epi_sampler_get", "epi_sampler_stats", "epi_sampler_pt_stats", "epi_sampler_record", "epi_sampler_draws", "epi_sampler_draws_subset",
     "epi_fp64_peak", "epi_set_timing", "epi_last_kernel_ms", "epi_launch_count", "epi_philox_probe",
@@ -137,6 +137,8 @@ def load():
     lib.epi_eval_detail.argtypes = [vp, _dp, i64, C.c_int, ip, ip, _dp]
     lib.epi_n_series.argtypes = [vp]
     lib.epi_trajectories.argtypes = [vp, _dp, i64, C.c_int, i32, _dp, ip, ip]
+    lib.epi_n_series_ext.argtypes = [vp]
+    lib.epi_trajectories_ext.argtypes = [vp, _dp, i64, C.c_int, i32, _dp, ip, ip]
     lib.epi_quantiles.argtypes = [vp, _dp, i64, C.c_int, i32, i32, i32, i32, _dp, i32, _dp]
     lib.epi_sampler_init.argtypes = [vp, C.POINTER(SamplerCfg), _dp]
     lib.epi_sampler_run.argtypes = [vp, i32]

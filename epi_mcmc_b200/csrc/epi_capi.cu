@@ -477,14 +477,15 @@ extern "C" int epi_df_params(const epi_handle *h, double *mn, double *mx, double
 extern "C" int64_t epi_launch_count(const epi_handle *h) { return h ? h->launches : 0; }
 
 // ----------------------------------------------------------------- workspace
-int epi_ensure_workspace(epi_handle *h, Workspace &w, const DevModel &M, int64_t n, bool want_series) {
+int epi_ensure_workspace(epi_handle *h, Workspace &w, const DevModel &M, int64_t n, int want_series) {
+  // want_series: 0 = none, else the number of calculateModel series per chain (basic or basic + ext)
   const int NG = is_age(M.flavour) ? 2 : 1, NK = is_age(M.flavour) ? 6 : 2;
-  const int NS = is_age(M.flavour) ? 8 : 3;
-  if (n <= w.cap && M.P <= w.P && (!want_series || w.series)) return EPI_OK;
+  if (n <= w.cap && M.P <= w.P && want_series <= w.ns) return EPI_OK;
   cudaStreamSynchronize(h->stream);
   const int64_t cap = std::max<int64_t>(n, w.cap);
   const int P = std::max(M.P, w.P), P1 = std::max(M.P1, w.P1);
-  const bool series = want_series || w.series;
+  const int NS = std::max(want_series, w.ns);
+  const bool series = NS > 0;
   free_workspace(w);
   const int64_t tiles = (cap + kTile - 1) / kTile;
   const int64_t ld = tiles * kTile;
@@ -506,16 +507,16 @@ int epi_ensure_workspace(epi_handle *h, Workspace &w, const DevModel &M, int64_t
   CUDA_OK(h, cudaMalloc(&w.logp, sizeof(double) * (size_t)ld));
   CUDA_OK(h, cudaMalloc(&w.terms, sizeof(double) * (size_t)ld * 8));
   if (series) CUDA_OK(h, cudaMalloc(&w.series, sizeof(double) * (size_t)ld * NS * P));
-  w.cap = cap; w.ld = ld; w.P = P; w.P1 = P1;
+  w.cap = cap; w.ld = ld; w.P = P; w.P1 = P1; w.ns = NS;
   return EPI_OK;
 }
 
 static EvalArgs make_args(epi_handle *h, Workspace &w, const DevModel &M, const double *d_theta, int64_t ld, int64_t n,
                           int64_t first, int model_space, double *d_logl, double *d_logp, int *d_status,
-                          double *d_terms, double *d_series, cudaStream_t stream) {
+                          double *d_terms, double *d_series, cudaStream_t stream, int ns_total) {
   // the chain range [first, first + n) of a batch; `first` is a multiple of the 32-chain tile
   const int NG = is_age(M.flavour) ? 2 : 1, NK = is_age(M.flavour) ? 6 : 2;
-  const int NS = is_age(M.flavour) ? 8 : 3;
+  const int NS = ns_total > 0 ? ns_total : (is_age(M.flavour) ? 8 : 3);
   EvalArgs a;
   a.M = &M; a.PT = h->PT; a.n_prior = h->n_prior;
   a.theta = d_theta + first; a.ld = ld; a.n = n; a.model_space = model_space;
@@ -531,6 +532,7 @@ static EvalArgs make_args(epi_handle *h, Workspace &w, const DevModel &M, const 
   a.logp = d_logp ? d_logp + first : nullptr;
   a.terms = d_terms ? d_terms + first * 8 : nullptr;
   a.series_out = d_series ? d_series + first * NS * M.P : nullptr;
+  a.ns_total = NS;
   a.stream = stream;
   a.ev = nullptr;
   return a;
@@ -538,7 +540,7 @@ static EvalArgs make_args(epi_handle *h, Workspace &w, const DevModel &M, const 
 
 int epi_launch_eval_ws(epi_handle *h, Workspace &w, const DevModel &M, const double *d_theta, int64_t ld, int64_t n,
                        int model_space, double *d_logl, double *d_logp, int *d_status, double *d_terms,
-                       double *d_series, cudaStream_t stream) {
+                       double *d_series, cudaStream_t stream, int ns_total) {
   cudaError_t e;
   // Large batches are cut in two halves that run on two streams.  Every phase of the pipeline is
   // latency bound on its own (ncu, profiles/r1_v2: FP64 pipe 42-50 % busy in the ODE kernels,
@@ -546,8 +548,8 @@ int epi_launch_eval_ws(epi_handle *h, Workspace &w, const DevModel &M, const dou
   // with the score/profile kernel of the other half fills issue slots neither can use alone.
   const int64_t half = ((n / 2 + 127) / 128) * 128;
   if (h->split && !h->timing && n >= 16384 && half < n) {
-    EvalArgs a0 = make_args(h, w, M, d_theta, ld, half, 0, model_space, d_logl, d_logp, d_status, d_terms, d_series, stream);
-    EvalArgs a1 = make_args(h, w, M, d_theta, ld, n - half, half, model_space, d_logl, d_logp, d_status, d_terms, d_series, h->stream2);
+    EvalArgs a0 = make_args(h, w, M, d_theta, ld, half, 0, model_space, d_logl, d_logp, d_status, d_terms, d_series, stream, ns_total);
+    EvalArgs a1 = make_args(h, w, M, d_theta, ld, n - half, half, model_space, d_logl, d_logp, d_status, d_terms, d_series, h->stream2, ns_total);
     cudaEventRecord(h->ev_fork, stream);
     cudaStreamWaitEvent(h->stream2, h->ev_fork, 0);
     if (h->split_mode == 2) a0.ev_after_mid = h->ev_stagger;  // half B starts when half A has finished k_mid
@@ -558,7 +560,7 @@ int epi_launch_eval_ws(epi_handle *h, Workspace &w, const DevModel &M, const dou
     cudaStreamWaitEvent(stream, h->ev_join, 0);
     h->launches += 8;
   } else {
-    EvalArgs a = make_args(h, w, M, d_theta, ld, n, 0, model_space, d_logl, d_logp, d_status, d_terms, d_series, stream);
+    EvalArgs a = make_args(h, w, M, d_theta, ld, n, 0, model_space, d_logl, d_logp, d_status, d_terms, d_series, stream, ns_total);
     a.ev = h->timing ? h->ev : nullptr;
     e = launch_eval(a);
     h->launches += 4;
@@ -690,8 +692,11 @@ extern "C" int epi_eval_detail(epi_handle *h, const double *theta, int64_t n, in
   return EPI_OK;
 }
 
-extern "C" int epi_trajectories(epi_handle *h, const double *theta, int64_t n, int layout, int32_t period, double *out,
-                                int32_t *offset, int32_t *padding) {
+static int n_series_of(int flavour, bool ext) { return is_age(flavour) ? (ext ? 18 : 8) : (ext ? 8 : 3); }
+extern "C" int epi_n_series_ext(const epi_handle *h) { return h ? n_series_of(h->M.flavour, true) : 0; }
+
+static int trajectories_impl(epi_handle *h, const double *theta, int64_t n, int layout, int32_t period, double *out,
+                             int32_t *offset, int32_t *padding, bool ext) {
   if (!h || !theta || !out || n < 0) return epi_fail(h, EPI_ERR_ARG, "bad argument");
   if (n == 0) return EPI_OK;
   const bool age = is_age(h->M.flavour), fixed_p1 = h->M.flavour == EPI_FLAVOUR_AGE2Q;  // 2q: period1 = 60
@@ -700,12 +705,12 @@ extern "C" int epi_trajectories(epi_handle *h, const double *theta, int64_t n, i
   DevModel M = h->M;  // calculateModel(params, period): same data, another horizon
   M.P = period;
   if (!fixed_p1) M.P1 = period;
-  const int NS = age ? 8 : 3;
-  int rc = epi_ensure_workspace(h, h->ws_traj, M, n, true);
+  const int NS = n_series_of(M.flavour, ext);
+  int rc = epi_ensure_workspace(h, h->ws_traj, M, n, NS);
   if (rc) return rc;
   Workspace &w = h->ws_traj;
   if ((rc = stage_theta(h, w, theta, n, layout, M.d))) return rc;
-  if ((rc = epi_launch_eval_ws(h, w, M, w.theta, w.ld, n, 1, nullptr, nullptr, nullptr, nullptr, w.series, h->stream))) return rc;
+  if ((rc = epi_launch_eval_ws(h, w, M, w.theta, w.ld, n, 1, nullptr, nullptr, nullptr, nullptr, w.series, h->stream, NS))) return rc;
   CUDA_OK(h, cudaMemcpyAsync(out, w.series, sizeof(double) * (size_t)n * NS * period, cudaMemcpyDeviceToHost, h->stream));
   if (offset) CUDA_OK(h, cudaMemcpyAsync(offset, w.offset, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
   if (padding) CUDA_OK(h, cudaMemcpyAsync(padding, w.pad, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
@@ -713,33 +718,45 @@ extern "C" int epi_trajectories(epi_handle *h, const double *theta, int64_t n, i
   return EPI_OK;
 }
 
+extern "C" int epi_trajectories(epi_handle *h, const double *theta, int64_t n, int layout, int32_t period, double *out,
+                                int32_t *offset, int32_t *padding) {
+  return trajectories_impl(h, theta, n, layout, period, out, offset, padding, false);
+}
+extern "C" int epi_trajectories_ext(epi_handle *h, const double *theta, int64_t n, int layout, int32_t period, double *out,
+                                    int32_t *offset, int32_t *padding) {
+  return trajectories_impl(h, theta, n, layout, period, out, offset, padding, true);
+}
+
 extern "C" int epi_quantiles(epi_handle *h, const double *theta, int64_t n, int layout, int32_t period, int32_t startoffset,
                              int32_t series_a, int32_t series_b, const double *probs, int32_t n_probs, double *out) {
   if (!h || !theta || !probs || !out || n < 1 || n_probs < 1 || period < 1) return epi_fail(h, EPI_ERR_ARG, "bad argument");
   if (n > 8192) return epi_fail(h, EPI_ERR_ARG, "epi_quantiles supports at most 8192 draws (got %lld)", (long long)n);
   const bool age = is_age(h->M.flavour), fixed_p1 = h->M.flavour == EPI_FLAVOUR_AGE2Q;
-  const int NS = age ? 8 : 3;
-  if (series_a < 0 || series_a >= NS || series_b >= NS) return epi_fail(h, EPI_ERR_ARG, "series index out of range");
+  const int NSb = n_series_of(h->M.flavour, false), NSx = n_series_of(h->M.flavour, true);
+  if (series_a < 0 || series_a >= NSx || series_b >= NSx) return epi_fail(h, EPI_ERR_ARG, "series index out of range");
+  const int NS = (series_a >= NSb || series_b >= NSb) ? NSx : NSb;  // an ext series asked for: run the ext pass
   const int simperiod = 3 * period;  // libMCMC.R:153
   if (simperiod < (fixed_p1 ? 60 : 2) || simperiod > (age ? 2048 : 4096)) return epi_fail(h, EPI_ERR_ARG, "period out of range");
   CUDA_OK(h, cudaSetDevice(h->device));
   DevModel M = h->M;
   M.P = simperiod;
   if (!fixed_p1) M.P1 = simperiod;
-  int rc = epi_ensure_workspace(h, h->ws_traj, M, n, true);
+  int rc = epi_ensure_workspace(h, h->ws_traj, M, n, NS);
   if (rc) return rc;
   Workspace &w = h->ws_traj;
   if ((rc = stage_theta(h, w, theta, n, layout, M.d))) return rc;
-  if ((rc = epi_launch_eval_ws(h, w, M, w.theta, w.ld, n, 1, nullptr, nullptr, nullptr, nullptr, w.series, h->stream))) return rc;
+  if ((rc = epi_launch_eval_ws(h, w, M, w.theta, w.ld, n, 1, nullptr, nullptr, nullptr, nullptr, w.series, h->stream, NS))) return rc;
   double *d_probs = nullptr, *d_out = nullptr;
   CUDA_OK(h, cudaMalloc(&d_probs, sizeof(double) * (size_t)n_probs));
   CUDA_OK(h, cudaMalloc(&d_out, sizeof(double) * (size_t)period * n_probs));
   CUDA_OK(h, cudaMemcpyAsync(d_probs, probs, sizeof(double) * (size_t)n_probs, cudaMemcpyHostToDevice, h->stream));
   // values before padding+1: the pre-filled state (model-age-groups2q.R:118-134)
+  // (ext: y.E / o.E are first assigned on (padding+1):..., so 1..padding is NA there, :216-223;
+  //  simple E is pre-filled with Initial, model-simple-ode-drj-cmp.R:66)
   auto prefill = [&](int sidx) -> double {
     if (sidx < 0) return 0.0;
-    if (age) return sidx == 0 ? M.Ny - 1.0 : sidx == 1 ? M.No : 0.0;
-    return sidx == 0 ? M.N - 1.0 : 0.0;
+    if (age) return sidx == 0 ? M.Ny - 1.0 : sidx == 1 ? M.No : (sidx == 8 || sidx == 11) ? NAN : 0.0;
+    return sidx == 0 ? M.N - 1.0 : sidx == 3 ? 1.0 : 0.0;
   };
   cudaError_t e = launch_quantiles(w.series, w.offset, w.pad, n, NS, simperiod, period, startoffset, series_a, series_b,
                                    prefill(series_a), prefill(series_b), d_probs, n_probs, d_out, h->stream);

@@ -15,6 +15,7 @@ namespace epi {
 struct Workspace {
   int64_t cap = 0, ld = 0;
   int P = 0, P1 = 0;
+  int ns = 0;  // series per chain `series` was allocated for (0: none)
   double *theta = nullptr, *aos = nullptr;    // staged theta: SoA d x ld, and the AoS landing buffer
   double *hist1 = nullptr, *hist2 = nullptr;  // S histories, [chain][group][pitch]
   double *ckpt = nullptr;                     // pass-1 checkpoints, [chain][state][ckpt days]
@@ -59,7 +60,7 @@ struct epi_handle {
 
 int epi_fail(epi_handle *h, int rc, const char *fmt, ...);
 void epi_sampler_free(epi_handle *h);
-int epi_ensure_workspace(epi_handle *h, epi::Workspace &w, const epi::DevModel &M, int64_t n, bool want_series);
+int epi_ensure_workspace(epi_handle *h, epi::Workspace &w, const epi::DevModel &M, int64_t n, int want_series);
 int epi_launch_eval_ws(epi_handle *h, epi::Workspace &w, const epi::DevModel &M, const double *d_theta, int64_t ld,
                        int64_t n, int model_space, double *d_logl, double *d_logp, int *d_status, double *d_terms,
-                       double *d_series, cudaStream_t stream);
+                       double *d_series, cudaStream_t stream, int ns_total = 0);

@@ -344,11 +344,76 @@ __device__ __noinline__ Seg select_segment(const DevModel &M, const double *__re
   return sg;
 }
 
-template <int FL, bool PASS2>
+// ---- the state fields calculateModel derives from the ode() matrix besides S (epi_trajectories_ext)
+// age (model-age-groups2q.R:216-227): y.E = E1y + E2y, y.I, y.R, o.E, o.I, o.R, Re, Rt, y.Re, o.Re;
+// the 2i file (:199-210) assigns o.E = out[,8] (E1o only) and o.I = out[,9] + out[,10] (E2o + Io):
+// reproduced as written.  simple (model-simple-ode-drj-cmp.R:108-113): E, I, R, Re, Rt.
+// Re..o.Re are derivs()' output variables (model-agen.cpp:159-163): deSolve evaluates them with one
+// derivs() call at the output time, i.e. with the LITERAL `t > tk` schedule; when the bounds guard
+// returns early the reference leaves them stale — NaN here.
+template <int FL>
+__device__ __noinline__ void write_ext(const DevModel &M, const double *__restrict__ th, int64_t ld, const double *bp,
+                                       int nbp, double t, const double *y, double inv1, double *__restrict__ eo, int P,
+                                       int d) {
+  if constexpr (Traits<FL>::kAge) {
+    const double Sy = y[0], E1y = y[1], E2y = y[2], Iy = y[3], Ry = y[4];
+    const double So = y[5], E1o = y[6], E2o = y[7], Io = y[8], Ro = y[9];
+    const double Ny = M.Ny, No = M.No;
+    eo[0 * P + d] = E1y + E2y; eo[1 * P + d] = Iy; eo[2 * P + d] = Ry;
+    eo[3 * P + d] = Traits<FL>::k2i ? E1o : E1o + E2o;
+    eo[4 * P + d] = Traits<FL>::k2i ? E2o + Io : Io;
+    eo[5 * P + d] = Ro;
+    double o0 = NAN, o1 = NAN, o2 = NAN, o3 = NAN;
+    if (!(Sy < 0 || E1y < 0 || E2y < 0 || Iy < 0 || Ry < 0 || Sy > Ny || E1y > Ny || E2y > Ny || Iy > Ny || Ry > Ny ||
+          So < 0 || E1o < 0 || E2o < 0 || Io < 0 || Ro < 0 || So > No || E1o > No || E2o > No || Io > No || Ro > No)) {
+      int k = -1;
+      for (int i = nbp - 1; i >= 0; --i)
+        if (t > bp[i]) { k = i; break; }
+      double by, bo, byo;
+      age_beta<FL>(th, ld, k < 0 ? 0 : k, by, bo, byo);
+      if (k >= 0 && age_linear<FL>(k)) {
+        double ny, no, nyo;
+        age_beta<FL>(th, ld, k + 1, ny, no, nyo);
+        const double f = (t - bp[k]) / (bp[k + 1] - bp[k]);
+        by = by + f * (ny - by); bo = bo + f * (no - bo); byo = byo + f * (nyo - byo);
+      }
+      const double yinf = (by * Iy) / Ny * Sy;
+      const double oinf = ((bo * Io) / No + (byo * Iy) / Ny) * So;
+      const double ig = 1 / M.gamma;
+      o0 = ig * (yinf + oinf) / (Iy + Io);
+      o1 = o0 * (Ny + No) / (Sy + So);
+      o2 = ig * ((by * Iy) / Ny * Sy + (byo * Iy) / Ny * So) / Iy;
+      o3 = ig * (bo * Io) / No * So / Io;
+    }
+    eo[6 * P + d] = o0; eo[7 * P + d] = o1; eo[8 * P + d] = o2; eo[9 * P + d] = o3;
+  } else {
+    const double S = y[0], E = y[1], I = y[2], R = y[3], N = M.N;
+    eo[0 * P + d] = E; eo[1 * P + d] = I; eo[2 * P + d] = R;
+    double re = NAN, rt = NAN;
+    if (!(S < 0 || E < 0 || I < 0 || R < 0 || S > N || E > N || I > N || R > N)) {
+      auto T = [&](int i) { return th[(int64_t)i * ld]; };
+      const double Tinf0 = T(2), Tinft = T(3);
+      const double beta0 = T(0) / Tinf0, betat = T(1) / Tinft;
+      double beta = beta0, Tinf = Tinf0;
+      if (nbp == 2 && t > bp[1]) { beta = betat; Tinf = Tinft; }
+      else if (nbp == 2 && t > bp[0]) {
+        const double f = (t - bp[0]) / (bp[1] - bp[0]);
+        beta = beta0 + f * (betat - beta0); Tinf = Tinf0 + f * (Tinft - Tinf0);
+      }
+      if constexpr (FL == EPI_FLAVOUR_NE) re = Tinf * beta * fmax(0.0, inv1 - (N - S)) / inv1;  // inv1 = Ne
+      else re = Tinf * beta * S / N;
+      rt = beta * Tinf;
+    }
+    eo[3 * P + d] = re; eo[4 * P + d] = rt;
+  }
+}
+
+template <int FL, bool PASS2, bool FULL = false>
 __global__ void __maxnreg__(144)
 k_ode(const DevModel M, const double *__restrict__ theta, int64_t ld, int64_t n,
       const int *__restrict__ offset, const int *__restrict__ padv, const double *__restrict__ hist1,
-      double *__restrict__ hist_out, double *__restrict__ ckpt) {
+      double *__restrict__ hist_out, double *__restrict__ ckpt, double *__restrict__ series = nullptr,
+      int ns_total = 0) {
   constexpr int NEQ = Traits<FL>::NEQ, NG = Traits<FL>::NG;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -377,6 +442,10 @@ k_ode(const DevModel M, const double *__restrict__ theta, int64_t ld, int64_t n,
   int nbp = 0;
   double tcut = INFINITY;
   int t0 = 1;
+  int nint = ndays;  // days integrated here
+  // FULL: the ext series of this chain, [series][P] behind the basic ones (8 age / 3 simple)
+  double *eo = nullptr;
+  if constexpr (FULL) eo = series + ((int64_t)i * ns_total + (Traits<FL>::kAge ? 8 : 3)) * (int64_t)M.P;
   if constexpr (PASS2) {
     const int off = offset[i];
     if (off == EPI_INVALID_DATA_OFFSET) {
@@ -387,10 +456,15 @@ k_ode(const DevModel M, const double *__restrict__ theta, int64_t ld, int64_t n,
       for (int d = 0; d < M.P; ++d)
 #pragma unroll
         for (int g = 0; g < NG; ++g) out[g * pitch + d] = in[g * pitch1 + d % M.P1];
-      return;
+      if constexpr (!FULL) return;
+      // FULL: the other columns of the recycled matrix are not kept by pass 1: integrate its days
+      // again (beta0 forever, bit-identical) and recycle the rows below
+      t0 = padv[i] + 1;
+      nint = min(M.P1, M.P);
+    } else {
+      t0 = padv[i] + 1;
+      nbp = breakpoints<FL>(M, th, ld, (double)off, bp);
     }
-    t0 = padv[i] + 1;
-    nbp = breakpoints<FL>(M, th, ld, (double)off, bp);
   }
   const int cdays = ckpt_days(M.P1);
   // element (d, q) of this chain: ck[(d * NEQ + q) * kTile]
@@ -420,6 +494,7 @@ k_ode(const DevModel M, const double *__restrict__ theta, int64_t ld, int64_t n,
   if (d0 == 0) {
     out[0] = y[0];
     if constexpr (NG == 2) out[pitch] = y[5];
+    if constexpr (FULL) write_ext<FL>(M, th, ld, bp, nbp, (double)t0, y, inv1, eo, M.P, 0);
   }
   if constexpr (!PASS2) {
     if (ck) {
@@ -427,7 +502,7 @@ k_ode(const DevModel M, const double *__restrict__ theta, int64_t ld, int64_t n,
       for (int q = 0; q < NEQ; ++q) ck[q * kTile] = y[q];
     }
   }
-  for (int d = d0 + 1; d < ndays; ++d) {
+  for (int d = d0 + 1; d < nint; ++d) {
     const double tday = (double)(t0 + d - 1);
     for (int s = 0; s < m; ++s) {
       const double a = tday + (double)s * h;
@@ -445,12 +520,20 @@ k_ode(const DevModel M, const double *__restrict__ theta, int64_t ld, int64_t n,
     }
     out[d] = y[0];
     if constexpr (NG == 2) out[pitch + d] = y[5];
+    if constexpr (FULL) write_ext<FL>(M, th, ld, bp, nbp, (double)(t0 + d), y, inv1, eo, M.P, d);
     if constexpr (!PASS2) {
       if (ck && d < cdays) {
 #pragma unroll
         for (int q = 0; q < NEQ; ++q) ck[((int64_t)d * NEQ + q) * kTile] = y[q];
       }
     }
+  }
+  if constexpr (FULL) {
+    // invalid data_offset with a pass 1 shorter than the period: R recycles the short matrix (:216-227)
+    constexpr int NE = Traits<FL>::kAge ? 10 : 5;
+    for (int d = nint; d < ndays; ++d)
+#pragma unroll
+      for (int q = 0; q < NE; ++q) eo[q * M.P + d] = eo[q * M.P + d % nint];
   }
 }
 
@@ -1366,18 +1449,17 @@ template <int FL>
 __global__ void __launch_bounds__(128, 4)
 k_series(const DevModel M, const double *__restrict__ theta, int64_t ld, int64_t n, const double *__restrict__ hist2,
          const int *__restrict__ offset, const int *__restrict__ padv, const double *__restrict__ Wg,
-         const int2 *__restrict__ pmeta, const int *__restrict__ status, double *__restrict__ out) {
+         const int2 *__restrict__ pmeta, const int *__restrict__ status, double *__restrict__ out, int ns_total) {
   constexpr int NK = Traits<FL>::NK, NG = Traits<FL>::NG;
-  constexpr int NS = Traits<FL>::kAge ? 8 : 3;
   extern __shared__ double smem[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int64_t chain = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
   if (chain >= n) return;
   const int P = M.P;
   const ScoreSmem w = carve_score<FL>(smem + (size_t)wib * score_smem_doubles<FL>(P), P);
-  double *o = out + (int64_t)chain * NS * P;
+  double *o = out + (int64_t)chain * ns_total * P;  // basic series first, ext series (if any) behind them
   if (status[chain] & EPI_ST_UNSUPPORTED) {
-    for (int i = lane; i < NS * P; i += 32) o[i] = NAN;
+    for (int i = lane; i < ns_total * P; i += 32) o[i] = NAN;
     return;
   }
   // theta is already in MODEL space here (calculateModel is called with transformed params)
@@ -1563,13 +1645,18 @@ static cudaError_t launch_eval_fl(const EvalArgs &a) {
   k_mid<FL><<<warp_blocks, 128, smem_mid, s>>>(M, a.theta, a.ld, n, a.hist1, a.offset, a.pad, a.status, a.W, a.pmeta, a.model_space);
   if (a.ev) cudaEventRecord(a.ev[2], s);
   if (a.ev_after_mid) cudaEventRecord(a.ev_after_mid, s);
-  if (use_pair) {
+  const bool want_ext = a.series_out && a.ns_total > (Traits<FL>::kAge ? 8 : 3);
+  if (use_pair && !want_ext) {
     if constexpr (Traits<FL>::kAge) k_ode_age2<FL, true><<<pair_blocks, 64, 0, s>>>(M, a.theta, a.ld, n, a.offset, a.pad, a.hist1, a.hist2, a.ckpt);
+  } else if (want_ext) {
+    // trajectories with the ext series: pass 2 also writes E, I, R and the Re/Rt diagnostics (no restart)
+    k_ode<FL, true, true><<<ode_blocks, 32, 0, s>>>(M, a.theta, a.ld, n, a.offset, a.pad, a.hist1, a.hist2, nullptr,
+                                                    a.series_out, a.ns_total);
   } else k_ode<FL, true><<<ode_blocks, 32, 0, s>>>(M, a.theta, a.ld, n, a.offset, a.pad, a.hist1, a.hist2, a.ckpt);
   if (a.ev) cudaEventRecord(a.ev[3], s);
   if (a.series_out) {
     k_series<FL><<<warp_blocks, 128, smem_score, s>>>(M, a.theta, a.ld, n, a.hist2, a.offset, a.pad, a.W, a.pmeta,
-                                                      a.status, a.series_out);
+                                                      a.status, a.series_out, a.ns_total);
   } else {
     k_score<FL><<<warp_blocks, 128, smem_score, s>>>(M, a.PT, a.n_prior, a.theta, a.ld, n, a.hist2, a.offset, a.pad, a.W, a.pmeta,
                                                      a.status, a.logl, a.logp, a.terms);

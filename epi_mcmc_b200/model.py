@@ -25,6 +25,9 @@ DATASET_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "datasets
 
 AGE_SERIES = ("y.S", "o.S", "y.casei", "o.casei", "y.hospi", "o.hospi", "y.deadi", "o.deadi")
 SIMPLE_SERIES = ("S", "hospi", "deadi")
+# the state fields derived from the other columns of the ode() matrix (epi_trajectories_ext)
+AGE_SERIES_EXT = AGE_SERIES + ("y.E", "y.I", "y.R", "o.E", "o.I", "o.R", "Re", "Rt", "y.Re", "o.Re")
+SIMPLE_SERIES_EXT = SIMPLE_SERIES + ("E", "I", "R", "Re", "Rt")
 
 
 def load_dataset(name: str) -> dict:
@@ -58,6 +61,7 @@ class Model:
         # df_params: data.frame(name, min, max, init), model-age-groups2q.R:637-663
         self.df_params = {"name": list(self.fit_paramnames), "min": mn, "max": mx, "init": init.copy()}
         self.is_age = self.flavour in ("age2q", "age2i")
+        self.series_names_ext = AGE_SERIES_EXT if self.is_age else SIMPLE_SERIES_EXT
         if self.flavour == "age2q":  # model-age-groups2q.R:619-622
             self.keyparamnames = ["betay6", "betao6", "betayo6", "betay7", "betao7", "betayo7",
                                   "fy9", "fo9", "fyo9", "ifrred"]
@@ -185,24 +189,26 @@ class Model:
         """calclogp(params): the UNTRANSFORMED sampler vector (fitMCMC-drj.R:51)."""
         return float(self.calclogpost_batch(np.asarray(params, dtype=np.float64)[None, :])[1][0])
 
-    def calculateModel_batch(self, params_model, period: int | None = None):
+    def calculateModel_batch(self, params_model, period: int | None = None, ext: bool = False):
         """calculateModel(params, period) for each MODEL-space row.  Returns
         (series[n, n_series, period], offset[n], padding[n]); series cover days
-        padding+1..padding+period in the order `self.series_names`."""
+        padding+1..padding+period in the order `self.series_names` (`self.series_names_ext` with
+        ext=True: also E, I, R and the Re/Rt diagnostics)."""
         th = np.ascontiguousarray(np.atleast_2d(np.asarray(params_model, dtype=np.float64)))
         n = th.shape[0]
         P = int(period or self.FitTotalPeriod)
-        ns = self._lib.epi_n_series(self._h)
+        ns = self._lib.epi_n_series_ext(self._h) if ext else self._lib.epi_n_series(self._h)
         out = np.empty((n, ns, P))
         off, pad = np.empty(n, dtype=np.int32), np.empty(n, dtype=np.int32)
-        _capi.check(self._lib.epi_trajectories(self._h, _capi.as_dp(th), n, _capi.LAYOUT_AOS, P, _capi.as_dp(out),
-                                               _capi.as_ip(off), _capi.as_ip(pad)), self._h)
+        fn = self._lib.epi_trajectories_ext if ext else self._lib.epi_trajectories
+        _capi.check(fn(self._h, _capi.as_dp(th), n, _capi.LAYOUT_AOS, P, _capi.as_dp(out),
+                       _capi.as_ip(off), _capi.as_ip(pad)), self._h)
         return out, off, pad
 
     def calculateModel(self, params, period: int | None = None) -> dict:
         """state list of the reference (fields used downstream: libMCMC.R:151-172)."""
-        series, off, pad = self.calculateModel_batch(np.asarray(params, dtype=np.float64)[None, :], period)
-        st = {name.replace(".", "_"): series[0, k] for k, name in enumerate(self.series_names)}
+        series, off, pad = self.calculateModel_batch(np.asarray(params, dtype=np.float64)[None, :], period, ext=True)
+        st = {name.replace(".", "_"): series[0, k] for k, name in enumerate(self.series_names_ext)}
         st["padding"] = int(pad[0])
         st["offset"] = int(off[0])
         return st
@@ -210,11 +216,11 @@ class Model:
     def quantileData(self, sample, fun, startoffset: int, period: int, quantiles):
         """libMCMC.R:151-172.  sample: (n, d) posterior draws in SAMPLER space (rows of the
         posterior table; transformParams is applied like the reference does); fun: a series name
-        from `self.series_names` or a tuple of two names whose sum is wanted (the reference passes
+        from `self.series_names_ext` (e.g. "Re", analyzeMCMC.R:265) or a tuple of two names whose sum is wanted (the reference passes
         closures such as `function(state, params) state$y.hospi + state$o.hospi`).  Returns a
         (period, len(quantiles)) array; everything runs on the device."""
         names = (fun,) if isinstance(fun, str) else tuple(fun)
-        idx = [self.series_names.index(nm) for nm in names] + [-1]
+        idx = [self.series_names_ext.index(nm) for nm in names] + [-1]
         th = np.ascontiguousarray(self.transformParams(np.atleast_2d(np.asarray(sample, dtype=np.float64))))
         probs = np.ascontiguousarray(np.asarray(quantiles, dtype=np.float64))
         out = np.empty((int(period), len(probs)))

@@ -208,6 +208,17 @@ int epi_n_series(const epi_handle *h);
 int epi_trajectories(epi_handle *h, const double *theta, int64_t n, int layout,
                      int32_t period, double *out, int32_t *offset, int32_t *padding);
 
+/* Same, plus the state fields calculateModel derives from the other columns of the ode() matrix
+ * (R/models/model-age-groups2q.R:216-227, model-simple-ode-drj-cmp.R:108-113) behind the basic
+ * series: age (18): ... , y.E, y.I, y.R, o.E, o.I, o.R, Re, Rt, y.Re, o.Re; simple (8): ... , E, I,
+ * R, Re, Rt.  Re..o.Re are derivs()' output variables (R/models/model-agen.cpp:159-163) at the
+ * integer output times; where the reference's bounds guard returns before setting them they are
+ * NaN.  epi_quantiles accepts these series indices too (e.g. quantileData(..., state$Re, ...),
+ * R/MCMC/analyzeMCMC.R:265).                                                  */
+int epi_n_series_ext(const epi_handle *h);
+int epi_trajectories_ext(epi_handle *h, const double *theta, int64_t n, int layout,
+                         int32_t period, double *out, int32_t *offset, int32_t *padding);
+
 /* quantileData(sample, fun, startoffset, period, quantiles) of R/lib/libMCMC.R:151-172:
  * calculateModel(params, 3*period) for each of the n posterior draws (theta in
  * MODEL space), v = takeAndPad(fun(state), state$offset - startoffset, 3*period)

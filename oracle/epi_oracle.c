@@ -333,6 +333,66 @@ static void derivs(const rhs_t *p, int neq, int seg, double t, const double *y, 
     derivs_simple(p, seg, t, y, ydot);
 }
 
+/* The nout = 4 output variables Re, Rt, y.Re, o.Re that derivs() fills next to ydot
+ * (R/models/model-agen.cpp:159-163, model-agef.cpp:146-150), evaluated the way deSolve does for
+ * the output matrix: one derivs() call at the output time with the LITERAL `t > tk` schedule.
+ * When the bounds guard returns early the reference leaves yout untouched (stale values of an
+ * earlier call): reported as NA here. */
+static void yout_age(const rhs_t *p, double t, const double *y, double *yout) {
+  const double Sy = y[0], E1y = y[1], E2y = y[2], Iy = y[3], Ry = y[4];
+  const double So = y[5], E1o = y[6], E2o = y[7], Io = y[8], Ro = y[9];
+  const double Ny = p->Ny, No = p->No;
+  if (Sy < 0 || E1y < 0 || E2y < 0 || Iy < 0 || Ry < 0 || Sy > Ny || E1y > Ny || E2y > Ny ||
+      Iy > Ny || Ry > Ny || So < 0 || E1o < 0 || E2o < 0 || Io < 0 || Ro < 0 || So > No ||
+      E1o > No || E2o > No || Io > No || Ro > No) {
+    for (int i = 0; i < 4; ++i) yout[i] = NA_REAL;
+    return;
+  }
+  const double betay = interpolate(&p->s, SEG_LITERAL, t, p->by);
+  const double betao = interpolate(&p->s, SEG_LITERAL, t, p->bo);
+  const double betayo = interpolate(&p->s, SEG_LITERAL, t, p->byo);
+  const double ygot_infected = (betay * Iy) / Ny * Sy;
+  const double ogot_infected = ((betao * Io) / No + (betayo * Iy) / Ny) * So;
+  yout[0] = 1 / p->gamma * (ygot_infected + ogot_infected) / (Iy + Io);
+  yout[1] = yout[0] * (Ny + No) / (Sy + So);
+  yout[2] = 1 / p->gamma * ((betay * Iy) / Ny * Sy + (betayo * Iy) / Ny * So) / Iy;
+  yout[3] = 1 / p->gamma * (betao * Io) / No * So / Io;
+}
+
+/* simple flavour, nout = 2 (Re, Rt).  INFERRED like derivs_simple (the RHS file is absent):
+ * Re = Tinf * beta * S / N, Rt = beta * Tinf; Ne flavour: S/N -> Seff/Ne. */
+static void yout_simple(const rhs_t *p, double t, const double *y, double *yout) {
+  const double S = y[0], E = y[1], I = y[2], R = y[3];
+  const double N = p->N;
+  if (S < 0 || E < 0 || I < 0 || R < 0 || S > N || E > N || I > N || R > N) {
+    yout[0] = yout[1] = NA_REAL;
+    return;
+  }
+  double beta, Tinf;
+  if (t > p->ldte) {
+    beta = p->betat; Tinf = p->Tinft;
+  } else if (t > p->ldts) {
+    double f = (t - p->ldts) / (p->ldte - p->ldts);
+    beta = p->beta0 + f * (p->betat - p->beta0);
+    Tinf = p->Tinf0 + f * (p->Tinft - p->Tinf0);
+  } else {
+    beta = p->beta0; Tinf = p->Tinf0;
+  }
+  if (p->flavour == EPI_FLAVOUR_NE)
+    yout[0] = Tinf * beta * fmax(0.0, p->Ne - (N - S)) / p->Ne;
+  else
+    yout[0] = Tinf * beta * S / N;
+  yout[1] = beta * Tinf;
+}
+
+/* yout rows for an ode() output matrix: out is [nday][neq] at times t0 .. t0+nday-1 */
+static void yout_rows(const rhs_t *p, int neq, const double *out, int t0, int nday, double *yo) {
+  for (int d = 0; d < nday; ++d) {
+    if (neq == 10) yout_age(p, (double)(t0 + d), out + (size_t)d * 10, yo + (size_t)d * 4);
+    else yout_simple(p, (double)(t0 + d), out + (size_t)d * 4, yo + (size_t)d * 2);
+  }
+}
+
 /* Replaces deSolve::ode(Y, times = (t0):(t0+nday-1), ...)
  * (R/models/model-age-groups2q.R:163-165,211-213; LSODA, adaptive) by a
  * deterministic fixed-step scheme, the SAME scheme the CUDA kernels implement:
@@ -446,6 +506,22 @@ void oracle_derivs_age(const double *parms45, double t, const double *y, double 
   derivs_age(&p, SEG_LITERAL, t, y, ydot);
 }
 
+void oracle_yout_age(const double *parms45, double t, const double *y, double *yout) {
+  rhs_t p;
+  memset(&p, 0, sizeof p);
+  p.Ny = parms45[0]; p.No = parms45[1]; p.a1 = parms45[2]; p.a2 = parms45[3]; p.gamma = parms45[4];
+  p.s.nbp = 10;
+  static const int kind[10] = {1, 1, 1, 1, 0, 0, 0, 0, 1, 0};
+  static const int tidx[10] = {5, 6, 7, 17, 21, 25, 29, 33, 37, 41};
+  for (int k = 0; k < 10; ++k) {
+    p.s.kind[k] = kind[k];
+    p.s.t[k] = parms45[tidx[k]];
+    int b = (k < 3) ? 8 + 3 * k : tidx[k] + 1;
+    p.by[k] = parms45[b]; p.bo[k] = parms45[b + 1]; p.byo[k] = parms45[b + 2];
+  }
+  yout_age(&p, t, y, yout);
+}
+
 /* same for the 8-breakpoint schedule of R/models/model-agef.cpp:7-43,66-87 (parms[37]):
  * segments 0..5 linear towards the next breakpoint, 6 and 7 hold */
 void oracle_derivs_agef(const double *parms37, double t, const double *y, double *ydot) {
@@ -462,6 +538,22 @@ void oracle_derivs_agef(const double *parms37, double t, const double *y, double
     p.by[k] = parms37[b]; p.bo[k] = parms37[b + 1]; p.byo[k] = parms37[b + 2];
   }
   derivs_age(&p, SEG_LITERAL, t, y, ydot);
+}
+
+void oracle_yout_agef(const double *parms37, double t, const double *y, double *yout) {
+  rhs_t p;
+  memset(&p, 0, sizeof p);
+  p.Ny = parms37[0]; p.No = parms37[1]; p.a1 = parms37[2]; p.a2 = parms37[3]; p.gamma = parms37[4];
+  p.s.nbp = 8;
+  static const int kind[8] = {1, 1, 1, 1, 1, 1, 0, 0};
+  static const int tidx[8] = {5, 6, 7, 17, 21, 25, 29, 33};
+  for (int k = 0; k < 8; ++k) {
+    p.s.kind[k] = kind[k];
+    p.s.t[k] = parms37[tidx[k]];
+    int b = (k < 3) ? 8 + 3 * k : tidx[k] + 1;
+    p.by[k] = parms37[b]; p.bo[k] = parms37[b + 1]; p.byo[k] = parms37[b + 2];
+  }
+  yout_age(&p, t, y, yout);
 }
 
 /* ------------------------------------------------------------ helpers ----- */
@@ -540,12 +632,13 @@ double oracle_age_gamma(void) { return 1.0 / ((G_CONST - (TINC1 + TINC2)) * 2.0)
 typedef struct {
   int pad, T, P, offset, na_profile;
   double *yS, *oS, *ycasei, *ocasei, *yhospi, *ohospi, *ydeadi, *odeadi;
-  double *full; /* optional [P][10] state rows of the final ode() */
+  double *full; /* [P][10] state rows of the final ode() */
+  double *yout; /* [P][4] Re, Rt, y.Re, o.Re of the final ode() */
 } age_state_t;
 
 static void age_state_free(age_state_t *s) {
   free(s->yS); free(s->oS); free(s->ycasei); free(s->ocasei);
-  free(s->yhospi); free(s->ohospi); free(s->ydeadi); free(s->odeadi); free(s->full);
+  free(s->yhospi); free(s->ohospi); free(s->ydeadi); free(s->odeadi); free(s->full); free(s->yout);
   memset(s, 0, sizeof *s);
 }
 
@@ -658,13 +751,17 @@ static int age_calculate_model(const epi_data *D, const double *params, int peri
   /* :216-223 — when pass 2 was skipped the 60-row `out` is recycled into the
    * P-length slices */
   st->full = (double *)malloc(sizeof(double) * 10 * (size_t)P);
+  st->yout = (double *)malloc(sizeof(double) * 4 * (size_t)P);
+  double *yo = (double *)malloc(sizeof(double) * 4 * (size_t)out_rows);
+  yout_rows(&rp, 10, out, padding + 1, out_rows, yo);
   for (int i = 1; i <= P; ++i) {
     const double *row = out + (size_t)((i - 1) % out_rows) * 10;
     st->yS[padding + i] = row[0];
     st->oS[padding + i] = row[5];
     memcpy(st->full + (size_t)(i - 1) * 10, row, sizeof(double) * 10);
+    memcpy(st->yout + (size_t)(i - 1) * 4, yo + (size_t)((i - 1) % out_rows) * 4, sizeof(double) * 4);
   }
-  free(out);
+  free(out); free(yo);
 
   /* :229-235 */
   const int nr = D->n_rate;
@@ -979,6 +1076,8 @@ static int age2i_calculate_model(const epi_data *D, const double *params, int pe
   /* :199-210 */
   st->full = (double *)malloc(sizeof(double) * 10 * (size_t)P);
   memcpy(st->full, out, sizeof(double) * 10 * (size_t)P);
+  st->yout = (double *)malloc(sizeof(double) * 4 * (size_t)P);
+  yout_rows(&rp, 10, out, padding + 1, P, st->yout);
   for (int i = 1; i <= P; ++i) {
     st->yS[padding + i] = out[(i - 1) * 10 + 0];
     st->oS[padding + i] = out[(i - 1) * 10 + 5];
@@ -1148,10 +1247,11 @@ typedef struct {
   int pad, T, P, offset;
   double *S, *hospi, *deadi;
   double *full; /* [P][4] */
+  double *yout; /* [P][2] Re, Rt */
 } simple_state_t;
 
 static void simple_state_free(simple_state_t *s) {
-  free(s->S); free(s->hospi); free(s->deadi); free(s->full);
+  free(s->S); free(s->hospi); free(s->deadi); free(s->full); free(s->yout);
   memset(s, 0, sizeof *s);
 }
 
@@ -1201,6 +1301,8 @@ static int simple_calculate_model(const epi_data *D, int flavour, const double *
   }
   st->full = (double *)malloc(sizeof(double) * 4 * (size_t)P);
   memcpy(st->full, out, sizeof(double) * 4 * (size_t)P);
+  st->yout = (double *)malloc(sizeof(double) * 2 * (size_t)P);
+  yout_rows(&rp, 4, out, padding + 1, P, st->yout);
   for (int i = 1; i <= P; ++i) st->S[padding + i] = out[(i - 1) * 4];
   free(out);
   convolute(st->S, T, padding + 1, padding + P, &hosp, s); /* :115-116 */
@@ -1389,7 +1491,7 @@ int oracle_eval(const epi_model_desc *desc, const epi_data *D, const double *the
  * y.S,o.S,y.casei,o.casei,y.hospi,o.hospi,y.deadi,o.deadi; simple: S,hospi,deadi.
  * states (optional) receives the final ode() rows [period][neq]. */
 int oracle_trajectory(const epi_model_desc *desc, const epi_data *D, const double *theta_model,
-                      int period, double *out, double *states, int32_t *offset, int32_t *padding) {
+                      int period, double *out, double *states, double *ext, int32_t *offset, int32_t *padding) {
   const int d = oracle_n_params(desc->flavour);
   double params[EPI_MAX_PARAMS + 1];
   for (int i = 0; i < d; ++i) params[i + 1] = theta_model[i];
@@ -1402,6 +1504,21 @@ int oracle_trajectory(const epi_model_desc *desc, const epi_data *D, const doubl
     for (int q = 0; q < 8; ++q)
       for (int i = 1; i <= period; ++i) out[(size_t)q * period + i - 1] = src[q][st.pad + i];
     if (states) memcpy(states, st.full, sizeof(double) * 10 * (size_t)period);
+    if (ext) {
+      /* the state fields calculateModel derives from the ode() matrix (model-age-groups2q.R:216-227;
+       * 2i :199-210, where o.E = out[,8] and o.I = out[,9] + out[,10]): y.E,y.I,y.R,o.E,o.I,o.R,Re,Rt,y.Re,o.Re */
+      const int two_i = desc->flavour == EPI_FLAVOUR_AGE2I;
+      for (int i = 0; i < period; ++i) {
+        const double *y = st.full + (size_t)i * 10, *yo = st.yout + (size_t)i * 4;
+        ext[0 * (size_t)period + i] = y[1] + y[2];
+        ext[1 * (size_t)period + i] = y[3];
+        ext[2 * (size_t)period + i] = y[4];
+        ext[3 * (size_t)period + i] = two_i ? y[6] : y[6] + y[7];
+        ext[4 * (size_t)period + i] = two_i ? y[7] + y[8] : y[8];
+        ext[5 * (size_t)period + i] = y[9];
+        for (int q = 0; q < 4; ++q) ext[(6 + q) * (size_t)period + i] = yo[q];
+      }
+    }
     if (offset) *offset = st.offset;
     if (padding) *padding = st.pad;
     age_state_free(&st);
@@ -1412,6 +1529,13 @@ int oracle_trajectory(const epi_model_desc *desc, const epi_data *D, const doubl
     for (int q = 0; q < 3; ++q)
       for (int i = 1; i <= period; ++i) out[(size_t)q * period + i - 1] = src[q][st.pad + i];
     if (states) memcpy(states, st.full, sizeof(double) * 4 * (size_t)period);
+    if (ext) { /* E, I, R, Re, Rt (model-simple-ode-drj-cmp.R:108-113) */
+      for (int i = 0; i < period; ++i) {
+        for (int q = 0; q < 3; ++q) ext[q * (size_t)period + i] = st.full[(size_t)i * 4 + 1 + q];
+        ext[3 * (size_t)period + i] = st.yout[(size_t)i * 2];
+        ext[4 * (size_t)period + i] = st.yout[(size_t)i * 2 + 1];
+      }
+    }
     if (offset) *offset = st.offset;
     if (padding) *padding = st.pad;
     simple_state_free(&st);

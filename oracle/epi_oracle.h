@@ -24,7 +24,9 @@ int oracle_eval(const epi_model_desc *desc, const epi_data *D, const double *the
                 int n_threads, double *logl, double *logp, int32_t *status, int32_t *offset,
                 int32_t *padding, double *terms8);
 int oracle_trajectory(const epi_model_desc *desc, const epi_data *D, const double *theta_model,
-                      int period, double *out, double *states, int32_t *offset, int32_t *padding);
+                      int period, double *out, double *states, double *ext, int32_t *offset, int32_t *padding);
+void oracle_yout_age(const double *parms45, double t, const double *y, double *yout);
+void oracle_yout_agef(const double *parms37, double t, const double *y, double *yout);
 void oracle_set_jitter(int ulps, unsigned seed);
 int oracle_profile(int kind, double mean, double sd, double *values, int *kbegin, int *kend);
 #ifdef __cplusplus

@@ -45,7 +45,9 @@ def lib():
         L.oracle_eval.argtypes = [C.POINTER(_capi.ModelDesc), C.POINTER(_capi.Data), _dp, C.c_int64,
                                   C.c_int, _dp, _dp, _ip, _ip, _ip, _dp]
         L.oracle_trajectory.argtypes = [C.POINTER(_capi.ModelDesc), C.POINTER(_capi.Data), _dp, C.c_int,
-                                        _dp, _dp, _ip, _ip]
+                                        _dp, _dp, _dp, _ip, _ip]
+        L.oracle_yout_age.argtypes = [_dp, C.c_double, _dp, _dp]
+        L.oracle_yout_agef.argtypes = [_dp, C.c_double, _dp, _dp]
         L.oracle_profile.argtypes = [C.c_int, C.c_double, C.c_double, _dp, _ip, _ip]
         L.oracle_set_jitter.argtypes = [C.c_int, C.c_uint]
         L.oracle_set_jitter.restype = None
@@ -84,8 +86,10 @@ def evaluate(flavour, data: dict, theta, period, substeps=4, n_threads=1):
     return dict(logl=logl, logp=logp, status=status, offset=offset, padding=padding, terms=terms)
 
 
-def trajectory(flavour, data: dict, theta_model, period, substeps=4, calc_period=None):
-    """calculateModel(theta_model, calc_period).  Returns (series[n_series, P], states[P, neq], offset, padding)."""
+def trajectory(flavour, data: dict, theta_model, period, substeps=4, calc_period=None, ext=False):
+    """calculateModel(theta_model, calc_period).  Returns (series[n_series, P], states[P, neq], offset, padding);
+    with ext=True the series also hold the state fields derived from the ode() matrix (age: y.E, y.I, y.R,
+    o.E, o.I, o.R, Re, Rt, y.Re, o.Re; simple: E, I, R, Re, Rt)."""
     desc = _desc(flavour, period, substeps)
     D, keep = _capi.make_data(data)
     P = calc_period or period
@@ -93,11 +97,15 @@ def trajectory(flavour, data: dict, theta_model, period, substeps=4, calc_period
     neq = 10 if desc.flavour in _capi.AGE_FLAVOURS else 4
     th = np.ascontiguousarray(np.asarray(theta_model, dtype=np.float64))
     out, states = np.zeros((ns, P)), np.zeros((P, neq))
+    n_ext = 10 if neq == 10 else 5
+    extra = np.zeros((n_ext, P))
     off, pad = C.c_int32(0), C.c_int32(0)
     rc = lib().oracle_trajectory(C.byref(desc), C.byref(D), _capi.as_dp(th), P, _capi.as_dp(out),
-                                 _capi.as_dp(states), C.byref(off), C.byref(pad))
+                                 _capi.as_dp(states), _capi.as_dp(extra) if ext else None, C.byref(off), C.byref(pad))
     if rc:
         raise ValueError("latency profile too wide")
+    if ext:
+        out = np.vstack([out, extra])
     return out, states, off.value, pad.value
 
 
@@ -132,6 +140,15 @@ def derivs_age(parms45, t, y):
     yy = np.ascontiguousarray(y, dtype=np.float64)
     out = np.zeros(10)
     lib().oracle_derivs_age(_capi.as_dp(p), t, _capi.as_dp(yy), _capi.as_dp(out))
+    return out
+
+
+def yout_age(parms, t, y):
+    """Re, Rt, y.Re, o.Re of the restated RHS; 45 parms = model-agen.cpp, 37 = model-agef.cpp"""
+    p = np.ascontiguousarray(parms, dtype=np.float64)
+    yy = np.ascontiguousarray(y, dtype=np.float64)
+    out = np.zeros(4)
+    (lib().oracle_yout_age if p.size == 45 else lib().oracle_yout_agef)(_capi.as_dp(p), t, _capi.as_dp(yy), _capi.as_dp(out))
     return out
 
 

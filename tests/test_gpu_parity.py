@@ -314,3 +314,65 @@ def test_async_submit_wait_matches_eval():
     M2.calclogpost_wait(1)
     M.close()
     M2.close()
+
+
+@pytest.mark.parametrize("name", ["A300", "I290", "S120", "NE120"])
+def test_ext_trajectories_match_oracle(name, oracle):
+    """epi_trajectories_ext: E, I, R and the Re/Rt output variables of derivs() at the integer output
+    times (model-agen.cpp:159-163) — incl. invalid-offset draws (pass-1 matrix recycled), batches below
+    and above the two-lanes-per-chain launch threshold, and a horizon other than FitTotalPeriod."""
+    from epi_mcmc_b200.model import load_dataset
+    ds = load_dataset(name)
+    M = _model(name, 4)
+    g = load_golden(name)
+    theta = np.array(g["theta"])[:20]
+    model_th = M.transformParams(theta)
+    nb = len(M.series_names)
+    for P in (ds["period"], ds["period"] + 33):
+        series, off, pad = M.calculateModel_batch(model_th, P, ext=True)
+        basic, off_b, _ = M.calculateModel_batch(model_th, P)
+        assert series.shape[1] == len(M.series_names_ext)
+        assert np.array_equal(series[:, :nb], basic, equal_nan=True) and np.array_equal(off, off_b)
+        for i in range(len(theta)):
+            ref, _, roff, rpad = oracle.trajectory(ds["flavour"], ds, model_th[i], ds["period"], 4, calc_period=P, ext=True)
+            assert off[i] == roff and pad[i] == rpad
+            got, want = series[i, nb:], ref[nb:]
+            # states: relative to the population; diagnostics (ratios of states): relative, except where the
+            # denominators are still ~0 persons and the ratio amplifies the integrator's last bits
+            n_state = 6 if M.is_age else 3
+            bar_s = 1e-10 * np.maximum(np.abs(want[:n_state]), 1e-6 * ds["N"])
+            assert (np.abs(got[:n_state] - want[:n_state]) <= bar_s).all()
+            with np.errstate(invalid="ignore"):
+                err = np.abs(got[n_state:] - want[n_state:]) / (1e-9 * np.abs(want[n_state:]) + 1e-12)
+            err = np.where(np.isnan(got[n_state:]) & np.isnan(want[n_state:]), 0.0, err)
+            assert not np.isnan(err).any() and err.max() <= 1.0, (i, err.max())
+    st = M.calculateModel(model_th[0])
+    assert "Re" in st and len(st["Re"]) == ds["period"]
+    M.close()
+
+
+def test_quantile_data_of_re(oracle):
+    """quantileData(data_sample, function(state, params) state$Re, ...) (analyzeMCMC.R:265) on the device"""
+    from epi_mcmc_b200.model import load_dataset
+    ds = load_dataset("A300")
+    M = _model("A300", 4)
+    mn, mx, init = M.df_params["min"], M.df_params["max"], M.df_params["init"]
+    rng = np.random.default_rng(9)
+    n, period, startoffset = 150, 100, 0
+    sample = np.clip(init + (rng.uniform(size=(n, M.d)) - 0.5) * 0.04 * (mx - mn), mn, mx)
+    probs = [0.05, 0.5, 0.95]
+    got = M.quantileData(sample, "Re", startoffset, period, probs)
+    simperiod = 3 * period
+    data = np.full((simperiod, n), np.nan)
+    k = M.series_names_ext.index("Re")
+    for i in range(n):
+        ser, _, off, pad = oracle.trajectory("age2q", ds, sample[i], ds["period"], 4, calc_period=simperiod, ext=True)
+        if off == 10000:
+            continue
+        vec = np.zeros(pad + simperiod)          # state$Re is pre-filled with 0 (model-age-groups2q.R:136)
+        vec[pad:] = ser[k]
+        take = vec[off - startoffset - 1:simperiod]
+        data[:len(take), i] = take
+    ref = np.nanquantile(data[:period], probs, axis=1).T
+    assert np.abs(got - ref).max() <= 1e-9 * np.nanmax(np.abs(ref))
+    M.close()
