@@ -409,7 +409,7 @@ __device__ __noinline__ void write_ext(const DevModel &M, const double *__restri
 }
 
 template <int FL, bool PASS2, bool FULL = false>
-__global__ void __maxnreg__(144)
+__global__ void __maxnreg__(128)
 k_ode(const DevModel M, const double *__restrict__ theta, int64_t ld, int64_t n,
       const int *__restrict__ offset, const int *__restrict__ padv, const double *__restrict__ hist1,
       double *__restrict__ hist_out, double *__restrict__ ckpt, double *__restrict__ series = nullptr,
