@@ -170,6 +170,9 @@ static int build_term_table(epi_handle *h, const std::vector<NbCall> &calls, con
     CUDA_OK(h, cudaMemcpy(d, flat.data(), flat.size() * sizeof(Slot), cudaMemcpyHostToDevice));
     h->M.slots[s] = d;
     h->M.K[s] = (int)K;
+    h->M.multi_begin[s] = n_obs[s];
+    for (int r = n_obs[s] - 1; r >= 0; --r)
+      if (per[s][r].size() > 1) h->M.multi_begin[s] = r;
     h->M.n_obs[s] = n_obs[s];
     h->n_terms += (int)flat.size();
   }
@@ -384,6 +387,7 @@ static int fill_model(epi_handle *h, const epi_model_desc &desc, const epi_data 
   if ((rc = upload(h, h->box_min, M.d, &M.box_min))) return rc;
   if ((rc = upload(h, h->box_max, M.d, &M.box_max))) return rc;
   std::vector<PriorTerm> pr = build_prior(desc.flavour, D);
+  for (PriorTerm &t : pr) t.log_sd = std::log(t.sd);
   PriorTerm *dp = nullptr;
   CUDA_OK(h, cudaMalloc(&dp, pr.size() * sizeof(PriorTerm)));
   h->owned.push_back(dp);

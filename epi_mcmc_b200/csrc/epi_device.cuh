@@ -54,6 +54,7 @@ struct DevModel {
   double d3, d4, d5d, d6, d7, lo_ltp;
   const double *y_ifr, *o_ifr, *y_hr, *o_hr, *g, *gtrimp;  // device, n_rate each
   const Slot *slots[kMaxSeries];                           // device, [n_obs][K]
+  int multi_begin[kMaxSeries];  // first relative day with more than one slot (n_obs when K == 1)
   const double *box_min, *box_max;                         // device, d each (df_params min/max)
 };
 
@@ -62,6 +63,7 @@ struct DevModel {
 struct PriorTerm {
   int ia, ib, mode, is_ln;
   double c0, ca, cb, mean, sd;
+  double log_sd;  // log(sd), filled on the host (data-only)
 };
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -159,6 +161,22 @@ __device__ __forceinline__ void fill_log_table(double2 *tab, int tid, int nthrea
 __device__ __forceinline__ double tlog(double a, const double2 *__restrict__ tab) {
   const int hi = __double2hiint(a);
   if ((unsigned)(hi - 0x00100000) >= 0x7fe00000u) return log(a);
+  const int e = (hi >> 20) - 1023;
+  const double2 t = tab[(hi >> 13) & (kLogTabN - 1)];
+  const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(a));
+  const double r = fma(m, t.x, -1.0);
+  double p = fma(r, -1.0 / 6.0, 0.2);
+  p = fma(p, r, -0.25);
+  p = fma(p, r, 1.0 / 3.0);
+  p = fma(p, r, -0.5);
+  const double l = fma(r * r, p, r);
+  return fma((double)e, 0.693147180559945309417232, t.y + l);
+}
+
+// the same for an argument known to be positive, finite and normal (the negative-binomial means are
+// clamped to a positive floor and screened for NaN/inf once per term by the caller): no range branch
+__device__ __forceinline__ double tlog_pos(double a, const double2 *__restrict__ tab) {
+  const int hi = __double2hiint(a);
   const int e = (hi >> 20) - 1023;
   const double2 t = tab[(hi >> 13) & (kLogTabN - 1)];
   const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(a));

@@ -1061,7 +1061,15 @@ __device__ __forceinline__ double prior_term(const PriorTerm &p, const double *t
   if (p.mode == 0) v = p.c0 + p.ca * A + p.cb * B;
   else if (p.mode == 1) v = A * B;
   else v = A / B;
-  return p.is_ln ? dev_dlnorm_log(v, p.mean, p.sd) : dev_dnorm_log(v, p.mean, p.sd);
+  // dnorm / dlnorm with log(sd) taken from the table: one library log per log-normal term, none per normal term
+  if (!p.is_ln) {
+    const double z = (v - p.mean) / p.sd;
+    return -(kLnSqrt2Pi + 0.5 * z * z + p.log_sd);
+  }
+  if (v != v) return v;
+  if (v <= 0) return -INFINITY;
+  const double lx = log(v), y = (lx - p.mean) / p.sd;
+  return -(kLnSqrt2Pi + 0.5 * y * y + (lx + p.log_sd));
 }
 
 __device__ __forceinline__ void window(int offset, int n, int T, int &dstart) {
@@ -1080,17 +1088,19 @@ __device__ __forceinline__ double score_slots(const DevModel &M, const double2 *
                                               const Slot &first, double v) {
   if (!in_range) return 0.0;
   const double mu = dev_pmax(M.floor_[s], v);
+  if (!(mu < 1e300)) return NAN;  // NA (or overflow) in the model series: the reference's sum is NA
   double acc = 0.0;
   if (first.n != 0.0f) {
     const double x = (double)first.x;
-    acc = x * tlog(mu, ltab) - fma((double)first.n, first.size, x) * tlog(first.size + mu, ltab);
+    acc = x * tlog_pos(mu, ltab) - fma((double)first.n, first.size, x) * tlog_pos(first.size + mu, ltab);
   }
+  if (r < M.multi_begin[s]) return acc;
   const int K = M.K[s];
   for (int k = 1; k < K; ++k) {  // rare: days with terms of several sizes (the last-8-days hospital weight)
     const Slot z = ldg_slot(M.slots[s] + (size_t)r * K + k);
     if (z.n == 0.0f) continue;
     const double x = (double)z.x;
-    acc += x * tlog(mu, ltab) - fma((double)z.n, z.size, x) * tlog(z.size + mu, ltab);
+    acc += x * tlog_pos(mu, ltab) - fma((double)z.n, z.size, x) * tlog_pos(z.size + mu, ltab);
   }
   return acc;
 }
@@ -1219,7 +1229,7 @@ template <int FL>
 struct AgeMap {
   int t1[6], t2[6];
   bool on[6];  // t1 > pad && t2 > t1, or invalid offset (then rate[1] everywhere, :250)
-  bool valid;
+  bool valid, all_on;
   __device__ __forceinline__ void init(const DevModel &M, const double *th, int off_raw, int pad, int P) {
     valid = off_raw != EPI_INVALID_DATA_OFFSET;
     // y.DL is used for both groups (2q :290,306; 2i :264,280)
@@ -1233,6 +1243,7 @@ struct AgeMap {
       t2[q] = min(pad + P, t1[q] + M.n_rate - 1);
       on[q] = !valid || (t1[q] > pad && t2[q] > t1[q]);
     }
+    all_on = on[0] && on[1] && on[2] && on[3] && on[4] && on[5];
   }
   // 0-based index into the rate vectors for profile q at sim day t
   __device__ __forceinline__ int index(const DevModel &M, int q, int t) const {
@@ -1281,8 +1292,13 @@ struct AgeMap {
     r[3] = th[13] * oifr3;                            r[3] = r[3] > 1 ? 1.0 : r[3];  // gocr
     r[4] = th[14] * ohr4;                                                             // gohr
     r[5] = oifr5 * (1 - ifrred * gt5);                                                // goifr
+    if (all_on) {  // per-chain, i.e. warp-uniform; the usual case
 #pragma unroll
-    for (int q = 0; q < 6; ++q) val[q] = on[q] ? inc[q] * r[q] : 0.0;
+      for (int q = 0; q < 6; ++q) val[q] = inc[q] * r[q];
+    } else {
+#pragma unroll
+      for (int q = 0; q < 6; ++q) val[q] = on[q] ? inc[q] * r[q] : 0.0;
+    }
   }
 };
 
@@ -1362,12 +1378,16 @@ k_score(const DevModel M, const PriorTerm *__restrict__ PT, int n_prior, const d
         for (int q = 0; q < 6; ++q) {
           const double Ng = q < 3 ? M.Ny : M.No;
           double c = half ? cb[q] : ca[q];
-          if (t - dmin_[q] < n_[q]) c = NAN;  // stats::filter leaves the first n-1 outputs NA
+          // stats::filter leaves the first n-1 outputs NA: reachable only for the hospital profiles, the
+          // other four define the padding (:113-114), so t - dmin >= n for every t > padding
+          if ((q == 1 || q == 4) && t - dmin_[q] < n_[q]) c = NAN;
           const double s2 = in ? Ng - c : 0.0;
           double prev = __shfl_up_sync(0xffffffffu, s2, 1);
           if (lane == 0) prev = carry[q];
           carry[q] = __shfl_sync(0xffffffffu, s2, 31);
-          inc[q] = (j == 0) ? s2 : s2 - prev;  // c(s2[1], diff(s2)), :239
+          // c(s2[1], diff(s2)), :239: for j == 0 the predecessor (lane - 1 at j = -1, or the initial carry) is
+          // the 0.0 of an out-of-range day, and s2 - 0.0 == s2 exactly
+          inc[q] = s2 - prev;
         }
         if (in) {
           map.values(M, w.theta, t, inc, val);
@@ -1403,8 +1423,7 @@ k_score(const DevModel M, const PriorTerm *__restrict__ PT, int n_prior, const d
         double v2[2];
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
-          double c = half ? cb[q] : ca[q];
-          if (t - dmin_[q] < n_[q]) c = NAN;
+          const double c = half ? cb[q] : ca[q];  // both profiles define the padding (:59): never NA for t > padding
           const double cum = in ? (M.N - c) * rate[q] : 0.0;
           double prev = __shfl_up_sync(0xffffffffu, cum, 1);
           if (lane == 0) prev = carry[q];
