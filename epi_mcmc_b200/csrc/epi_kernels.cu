@@ -882,9 +882,9 @@ __device__ __forceinline__ void build_profiles(const WarpSmem &w, const int *n_,
   for (int q = 0; q < NK; ++q) {
     const int n = n_[q];
     const double *cdf = w.cdf + q * kCdfStride;
-    double part = 0.0;
-    for (int i = lane; i < n; i += 32) part += cdf[i] - cdf[i + 1];
-    const double sum = warp_sum(part);
+    // sum(values) (:36) telescopes to F(kb - .5) - F(ke + .5); the explicit sum differs from it only by the
+    // rounding of the individual differences (<= n ulp/2), well inside the 1e-13 agreement of the weights
+    const double sum = cdf[0] - cdf[n];
     for (int o = lane; o < n; o += 32) {
       // age: values are reversed (rev(), :37): tap o <-> k = ke - o <-> cell n-1-o
       const int cell = Traits<FL>::kAge ? (n - 1 - o) : o;
@@ -934,7 +934,8 @@ __device__ __forceinline__ double conv_at(const double *__restrict__ Sg, const d
   if (t - dmin < n) return NAN;
   const double *x = Sg + PAD + j - dmin;  // x[t - dmin]
   double z = 0.0;
-  for (int o = 0; o < n; ++o) z = fma(f[o], x[-o], z);
+#pragma unroll 4
+  for (int o = 0; o < n; ++o) z = fma(f[o], x[-o], z);  // sequential order as in stats::filter; loads hoisted
   return z;
 }
 
@@ -965,6 +966,16 @@ k_mid(const DevModel M, const double *__restrict__ theta, int64_t ld, int64_t n,
   oob = __any_sync(0xffffffffu, oob);
   __syncwarp();
 
+  // per-profile CDF parameters (x0, shape | mean, scale | sd): one lane per profile, side by side
+  if (lane < NK) {
+    double mean, sd, x0;
+    profile_params<FL>(w.theta, lane, mean, sd);
+    int dmin = 0, nt = 1;
+    profile_extent<FL>(mean, sd, dmin, nt, x0);
+    w.pp[lane * 4 + 0] = x0;
+    if constexpr (Traits<FL>::kAge) { const double scale = sd * sd / mean; w.pp[lane * 4 + 2] = scale; w.pp[lane * 4 + 1] = mean / scale; }
+    else { w.pp[lane * 4 + 1] = mean; w.pp[lane * 4 + 2] = sd; }
+  }
   // profiles + padding (:106-114 / simple :56-59)
   int st = oob ? EPI_ST_OUT_OF_BOX : 0;
   int pad = 0;
@@ -978,11 +989,6 @@ k_mid(const DevModel M, const double *__restrict__ theta, int64_t ld, int64_t n,
     const bool okq = profile_extent<FL>(mean, sd, dmin, nt, x0);
     ok = ok && okq;
     dmin_[q] = dmin; n_[q] = nt;
-    if (lane == 0) {
-      w.pp[q * 4 + 0] = x0;
-      if constexpr (Traits<FL>::kAge) { const double scale = sd * sd / mean; w.pp[q * 4 + 2] = scale; w.pp[q * 4 + 1] = mean / scale; }
-      else { w.pp[q * 4 + 1] = mean; w.pp[q * 4 + 2] = sd; }
-    }
     // padding counts the case & died kernels only (age, :113-114); both kernels for simple (:59)
     const bool in_pad = Traits<FL>::kAge ? (q != 1 && q != 4) : true;
     if (in_pad && okq) pad = max(pad, dmin + nt - 1);
