@@ -37,16 +37,19 @@ for ln in sass:
 src = subprocess.run(["ncu", "-i", rep, "--kernel-name", "regex:" + kre, "--page", "source", "--csv",
                       "--print-source", "sass"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
-hdr, data, started = None, [], 0
+hdr, blocks = None, []
 for r in rows:
     if r and r[0] == "Kernel Name":
-        started += 1
+        blocks.append([])
         continue
     if r and r[0] == "Address":
         hdr = r
         continue
-    if started == 1 and hdr and len(r) > 6:
-        data.append(r)
+    if blocks and hdr and len(r) > 6:
+        blocks[-1].append(r)
+# several launches may match the regex (template instances share the base name): take the one whose
+# instruction count equals the line table's
+data = next((b for b in blocks if len(b) == len(lines)), blocks[0])
 ix, ism = hdr.index("Instructions Executed"), hdr.index("# Samples")
 print(f"# {len(data)} SASS instructions in the report, {len(lines)} in the line table")
 n = min(len(data), len(lines))
