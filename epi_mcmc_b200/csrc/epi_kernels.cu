@@ -1647,21 +1647,27 @@ static cudaError_t launch_eval_fl(const EvalArgs &a) {
   const size_t smem_mid = (size_t)4 * warp_smem_doubles<FL>(M.P1) * sizeof(double);
   const size_t smem_score = ((size_t)4 * score_smem_doubles<FL>(M.P) + 2 * kLogTabN) * sizeof(double);
   if (smem_mid > 200 * 1024 || smem_score > 200 * 1024) return cudaErrorInvalidConfiguration;  // period too long (checked at create)
-  static bool attr_done = false;
-  if (!attr_done) {
+  // function attributes and the SM count are per DEVICE: one process may hold handles on several GPUs
+  constexpr int kMaxDev = 64;
+  static bool attr_done[kMaxDev] = {};
+  static int n_sm_of[kMaxDev] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const int di = dev < kMaxDev ? dev : kMaxDev - 1;
+  if (!attr_done[di] || dev >= kMaxDev) {
     cudaFuncSetAttribute(k_mid<FL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(k_score<FL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(k_series<FL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr_done = true;
+    cudaDeviceGetAttribute(&n_sm_of[di], cudaDevAttrMultiProcessorCount, dev);
+    attr_done[di] = true;
   }
+  const int n_sm = n_sm_of[di];
   cudaStream_t s = a.stream;
   if (a.ev) cudaEventRecord(a.ev[0], s);
   const unsigned pair_blocks = (unsigned)((2 * n + 63) / 64);
   // Two lanes per chain double the resident warps, but need ~124 registers per lane: they win
   // while all 2n lanes fit one wave (n <= 256 chains per SM), thread-per-chain wins above that
   // (measured on B200, 65,536 chains: 2.25 ms vs 2.07 ms for pass 2).
-  static int n_sm = 0;
-  if (!n_sm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
   const bool use_pair = Traits<FL>::kAge && n <= (int64_t)n_sm * 256;
   if (use_pair) {
     if constexpr (Traits<FL>::kAge) k_ode_age2<FL, false><<<pair_blocks, 64, 0, s>>>(M, a.theta, a.ld, n, nullptr, nullptr, nullptr, a.hist1, a.ckpt);

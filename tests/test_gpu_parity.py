@@ -376,3 +376,21 @@ def test_quantile_data_of_re(oracle):
     ref = np.nanquantile(data[:period], probs, axis=1).T
     assert np.abs(got - ref).max() <= 1e-9 * np.nanmax(np.abs(ref))
     M.close()
+
+
+def test_two_devices_in_one_process():
+    """Per-device launch state (opt-in shared-memory attribute, SM count): a second handle on another GPU of the
+    same process must work, also for a period whose shared-memory footprint needs the opt-in."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from epi_mcmc_b200.model import Model, load_dataset
+    ds = load_dataset("A365")
+    th = np.array(load_golden("A365")["theta"])
+    A = Model(ds, substeps=1, device=0)
+    B = Model(ds, substeps=1, device=1)
+    la, pa, sa = A.calclogpost_batch(th)
+    lb, pb, sb = B.calclogpost_batch(th)
+    assert np.array_equal(la, lb, equal_nan=True) and np.array_equal(pa, pb) and np.array_equal(sa, sb)
+    A.close()
+    B.close()

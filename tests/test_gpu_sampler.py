@@ -240,3 +240,21 @@ def test_sample_file_round_trip_warm_start_and_dic(tmp_path, oracle):
     write_max_csv(str(tmp_path / "max.csv"), np.concatenate([[ll[best] + lp[best]], draws[best]]))
     assert np.array_equal(read_max_csv(str(tmp_path / "max.csv"), M.d), draws[best])
     M.close()
+
+
+def test_sampler_runs_on_the_secondary_age_model():
+    """K2 is flavour-agnostic: DE-MC on the 36-parameter age-2i model moves, stays inside the box and its
+    cached log densities are those of a fresh evaluation of the states."""
+    from epi_mcmc_b200.sampler import Sampler
+    M = _model("I290", 2)
+    S = Sampler(M, 1024, kind="demc", seed=21)
+    for _ in range(4):
+        S.run(10)
+        S.refresh_population()
+    th, ll, lp = S.get()
+    assert th.shape == (1024, 36)
+    assert (th >= M.df_params["min"]).all() and (th <= M.df_params["max"]).all()
+    l2, p2, st = M.calclogpost_batch(th)
+    assert np.array_equal(ll, l2) and np.array_equal(lp, p2)
+    assert 0 < S.stats()["accepted"] < 1024 * 40
+    M.close()
