@@ -83,7 +83,7 @@ def f_alg(flavour, P, m, taps_mean, n_terms, n_prior):
         "ode_pass2": m * P * (4 * F_rhs + 14 * S),
         "score": C2 * P * 2 * taps_mean + 6 * C2 * P + 72 * n_terms + 40 * n_prior,
     }
-    return dict(total=total, ode=ode, per_kernel=per_kernel)
+    return dict(total=total, ode=ode, per_kernel=per_kernel, score_per_day=C2 * 2 * taps_mean + 6 * C2)
 
 
 def mean_taps(flavour, theta):
@@ -367,9 +367,30 @@ def main():
     D = np.clip(np.floor(minbp) - (pad_s + 1), 0, cap) if restart_on else np.zeros(len(off_s))
     D = np.where(off_s == 10000, 0, D)
     d_mean = float(D.mean())
-    step_flop = fa["per_kernel"]["ode_pass2"] / ds["period"]          # per integrated day
-    fa["per_kernel_executed"] = dict(fa["per_kernel"], ode_pass2=fa["per_kernel"]["ode_pass2"] - d_mean * step_flop)
-    fa["total_executed"] = fa["total"] - d_mean * step_flop
+    # data windows: calclogl reads the model series only on [dstart, dstart + n - 1] of every scored series
+    # (window clamps of model-age-groups2q.R:497-512), so the scoring path integrates pass 2 up to the last
+    # window day and convolves window days (+ one predecessor) only — "convolving only observed days" of
+    # SURVEY §8d's list of admissible reductions.  Same window arithmetic as the kernels, in numpy.
+    P_ = ds["period"]
+    n_obs = ([ds["n_dcasei"], ds["n_dcasei"], ds["n_dhospi"], ds["n_dmorti"], ds["n_dmorti"]]
+             if ds["flavour"] in ("age2q", "age2i") else [ds["n_dhospi"], ds["n_dmorti"]])
+    off_e = np.where(off_s == 10000, 1, off_s).astype(np.int64)
+    T_ = pad_s.astype(np.int64) + P_
+    tlo, thi = T_.copy(), np.ones_like(T_)
+    for nn in n_obs:
+        de = off_e + nn - 1
+        dsr = np.where(de > T_, T_ - nn + 1, off_e)
+        dsr = np.maximum(dsr, 1)
+        tlo, thi = np.minimum(tlo, dsr), np.maximum(thi, dsr + nn - 1)
+    nint = np.clip(thi - pad_s, 1, P_)                                   # pass-2 days integrated (incl. day 0)
+    swept = np.minimum(thi - (pad_s + 1), P_ - 1) - (tlo - 1 - (pad_s + 1)) + 1  # days the score sweep covers
+    nint = np.where(off_s == 10000, D, nint)                             # invalid offset: pass 2 is skipped altogether
+    days_pass2 = float(np.maximum(nint - D, 0).mean())
+    days_swept = float(np.minimum(swept, P_ + 64).mean())
+    step_flop = fa["per_kernel"]["ode_pass2"] / P_                        # per integrated day
+    fa["per_kernel_executed"] = dict(fa["per_kernel"], ode_pass2=days_pass2 * step_flop,
+                                     score=fa["per_kernel"]["score"] - (P_ - min(days_swept, P_)) * fa["score_per_day"])
+    fa["total_executed"] = sum(fa["per_kernel_executed"].values())
     knames = ["ode_pass1", "profiles_threshold", "ode_pass2", "score"]
     kernel_fn = {"ode_pass1": "k_ode<pass1>", "profiles_threshold": "k_mid", "ode_pass2": "k_ode<pass2>", "score": "k_score"}
     per_kernel = {}
@@ -378,7 +399,7 @@ def main():
         tf = fa["per_kernel_executed"][k] * n / (float(msk) * 1e-3) / 1e12
         per_kernel[k] = {"kernel": kernel_fn[k], "ms": float(msk),
                          "algorithmic_flop_per_launch": fa["per_kernel_executed"][k] * n,
-                         "algorithmic_flop_per_launch_without_restart": fa["per_kernel"][k] * n,
+                         "algorithmic_flop_per_launch_without_reductions": fa["per_kernel"][k] * n,
                          "achieved": tf, "frac": tf / peak_tf if peak_tf else None,
                          "traffic": NCU_TRAFFIC.get(k) if ncu_match else None,
                          "fp64_pipe_pct_ncu": NCU_FP64_PIPE_PCT.get(k) if ncu_match else None}
@@ -412,12 +433,16 @@ def main():
                      "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, "
                                        "profiles/r1_v11_ncu_full.txt (65,536 chains, A300)"},
         "roofline_all": per_kernel,
-        "f_alg": {"per_eval": fa["total"], "per_eval_with_pass2_restart": fa["total_executed"],
-                  "pass2_restart_days_mean": d_mean, "ode_share": fa["ode"] / fa["total"],
+        "f_alg": {"per_eval": fa["total"], "per_eval_executed": fa["total_executed"],
+                  "pass2_restart_days_mean": d_mean, "pass2_days_integrated_mean": days_pass2,
+                  "score_days_swept_mean": days_swept, "period": P_, "ode_share": fa["ode"] / fa["total"],
                   "whole_step_tflops": whole_tf, "whole_step_frac": whole_tf / peak_tf if peak_tf else None,
-                  "note": "fractions use the step count actually integrated (pass 2 resumes from the pass-1 "
-                          "checkpoint after pass2_restart_days_mean bit-identical days); per_eval is the "
-                          "SURVEY 8d figure without that reduction"},
+                  "whole_step_frac_if_counted_without_reductions":
+                      (fa["total"] * n / (step_ms * 1e-3) / 1e12) / peak_tf if peak_tf else None,
+                  "note": "per_eval is the SURVEY 8d figure; per_eval_executed and every frac count only the work "
+                          "actually done: pass 2 resumes from the pass-1 checkpoint after pass2_restart_days_mean "
+                          "bit-identical days and stops at the last data-window day, the score sweep covers the data "
+                          "windows plus one predecessor day (results identical; DESIGN.md section 3)"},
     }
     if comm.rank == 0 and comm.world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(ds, theta, args.substeps)

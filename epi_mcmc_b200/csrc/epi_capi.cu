@@ -420,6 +420,7 @@ extern "C" int epi_create(const epi_model_desc *desc, const epi_data *data, int 
     cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&h->ev_stagger, cudaEventDisableTiming);
     { const char *env = getenv("EPI_PASS2_RESTART"); h->restart = !(env && env[0] == '0'); }
+    { const char *env = getenv("EPI_WINDOW_ONLY"); h->window_only = !(env && env[0] == '0'); }
     { const char *env = getenv("EPI_SPLIT_STREAMS"); h->split = (env && (env[0] == '1' || env[0] == '2')); h->split_mode = (env && env[0] == '2') ? 2 : 1; }
     for (auto &ev : h->ev) cudaEventCreate(&ev);
     rc = fill_model(h, *desc, *data);
@@ -537,6 +538,7 @@ static EvalArgs make_args(epi_handle *h, Workspace &w, const DevModel &M, const 
   a.terms = d_terms ? d_terms + first * 8 : nullptr;
   a.series_out = d_series ? d_series + first * NS * M.P : nullptr;
   a.ns_total = NS;
+  a.window_only = h->window_only ? 1 : 0;
   a.stream = stream;
   a.ev = nullptr;
   return a;

@@ -344,6 +344,22 @@ __device__ __noinline__ Seg select_segment(const DevModel &M, const double *__re
   return sg;
 }
 
+// Last simulation day any data window of calclogl reads (window clamps of model-age-groups2q.R:497-512
+// for every scored series): the scoring path needs S(t) only up to there, so pass 2 stops at that day
+// when it feeds k_score (never when it feeds calculateModel trajectories).
+__device__ __forceinline__ int last_window_day(const DevModel &M, int off_raw, int pad) {
+  const int off = off_raw != EPI_INVALID_DATA_OFFSET ? off_raw : 1, T = pad + M.P;
+  int thi = 1;
+  for (int s = 0; s < M.n_series; ++s) {
+    const int n = M.n_obs[s];
+    int ds = off, de = off + n - 1;
+    if (de > T) { de = T; ds = de - n + 1; }
+    if (ds < 1) ds = 1;
+    thi = max(thi, ds + n - 1);
+  }
+  return thi;
+}
+
 // ---- the state fields calculateModel derives from the ode() matrix besides S (epi_trajectories_ext)
 // age (model-age-groups2q.R:216-227): y.E = E1y + E2y, y.I, y.R, o.E, o.I, o.R, Re, Rt, y.Re, o.Re;
 // the 2i file (:199-210) assigns o.E = out[,8] (E1o only) and o.I = out[,9] + out[,10] (E2o + Io):
@@ -413,7 +429,7 @@ __global__ void __maxnreg__(128)
 k_ode(const DevModel M, const double *__restrict__ theta, int64_t ld, int64_t n,
       const int *__restrict__ offset, const int *__restrict__ padv, const double *__restrict__ hist1,
       double *__restrict__ hist_out, double *__restrict__ ckpt, double *__restrict__ series = nullptr,
-      int ns_total = 0) {
+      int ns_total = 0, int window_only = 0) {
   constexpr int NEQ = Traits<FL>::NEQ, NG = Traits<FL>::NG;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -464,6 +480,7 @@ k_ode(const DevModel M, const double *__restrict__ theta, int64_t ld, int64_t n,
     } else {
       t0 = padv[i] + 1;
       nbp = breakpoints<FL>(M, th, ld, (double)off, bp);
+      if (!FULL && window_only) nint = min(nint, max(last_window_day(M, off, padv[i]) - padv[i], 1));
     }
   }
   const int cdays = ckpt_days(M.P1);
@@ -654,7 +671,7 @@ template <int FL, bool PASS2>
 __global__ void __maxnreg__(128)
 k_ode_age2(const DevModel M, const double *__restrict__ theta, int64_t ld, int64_t n, const int *__restrict__ offset,
            const int *__restrict__ padv, const double *__restrict__ hist1, double *__restrict__ hist_out,
-           double *__restrict__ ckpt) {
+           double *__restrict__ ckpt, int window_only = 0) {
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t i = tid >> 1;  // chain
   if (i >= n) return;
@@ -663,6 +680,7 @@ k_ode_age2(const DevModel M, const double *__restrict__ theta, int64_t ld, int64
   const unsigned pairmask = 3u << even_lane;
   const double *th = theta + i;
   const int ndays = PASS2 ? M.P : M.P1;
+  int nint = ndays;  // days integrated here
   double *out = hist_out + (i * 2 + g) * (int64_t)hist_pitch(ndays);
 
   const double Ngrp = g ? M.No : M.Ny;
@@ -685,6 +703,7 @@ k_ode_age2(const DevModel M, const double *__restrict__ theta, int64_t ld, int64
     }
     t0 = padv[i] + 1;
     nbp = breakpoints<FL>(M, th, ld, (double)off, bp);
+    if (window_only) nint = min(nint, max(last_window_day(M, off, padv[i]) - padv[i], 1));
   }
   const int cdays = ckpt_days(M.P1);
   double *ck = ckpt ? ckpt + ((i / kTile) * (int64_t)cdays * 10 + g * 5) * kTile + (i % kTile) : nullptr;
@@ -714,7 +733,7 @@ k_ode_age2(const DevModel M, const double *__restrict__ theta, int64_t ld, int64
       for (int q = 0; q < 5; ++q) ck[q * kTile] = y[q];
     }
   }
-  for (int d = d0 + 1; d < ndays; ++d) {
+  for (int d = d0 + 1; d < nint; ++d) {
     const double tday = (double)(t0 + d - 1);
     for (int s = 0; s < m; ++s) {
       const double a = tday + (double)s * h;
@@ -1313,7 +1332,7 @@ __global__ void __launch_bounds__(128, 4)
 k_score(const DevModel M, const PriorTerm *__restrict__ PT, int n_prior, const double *__restrict__ theta, int64_t ld, int64_t n,
         const double *__restrict__ hist2, const int *__restrict__ offset, const int *__restrict__ padv,
         const double *__restrict__ Wg, const int2 *__restrict__ pmeta, int *__restrict__ status,
-        double *__restrict__ logl, double *__restrict__ logp, double *__restrict__ terms) {
+        double *__restrict__ logl, double *__restrict__ logp, double *__restrict__ terms, int window_only) {
   constexpr int NK = Traits<FL>::NK, NG = Traits<FL>::NG;
   extern __shared__ double smem[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -1356,19 +1375,28 @@ k_score(const DevModel M, const PriorTerm *__restrict__ PT, int n_prior, const d
   constexpr int PAD = Traits<FL>::kPad;
   const int stride = PAD + hist_pitch(P);
 
+  // calclogl reads the model series only inside the data windows [dstart_s, dstart_s + n_s - 1] (:497-590):
+  // the sweep covers the union of the windows plus ONE day in front of it (the predecessor the first scored
+  // day's increment needs), not the whole period.  Days before padding+1 read the 0 prefill.
   int dstart[kMaxSeries];
-  int tlo = pad + 1;
-  for (int s = 0; s < M.n_series; ++s) { window(off, M.n_obs[s], T, dstart[s]); tlo = min(tlo, dstart[s]); }
+  int tlo = T, thi = 1;
+  for (int s = 0; s < M.n_series; ++s) {
+    window(off, M.n_obs[s], T, dstart[s]);
+    tlo = min(tlo, dstart[s]);
+    thi = max(thi, dstart[s] + M.n_obs[s] - 1);
+  }
 
   double acc[kMaxSeries] = {0, 0, 0, 0, 0};
   double ysum = 0.0, osum = 0.0;
-  const int jlo = tlo - (pad + 1);  // <= 0: scored days before padding+1 read the 0 prefill
+  // (window_only == 0, EPI_WINDOW_ONLY=0: sweep the whole period as the reference does — test switch)
+  const int jlo = window_only ? tlo - 1 - (pad + 1) : min(tlo, pad + 1) - (pad + 1);
+  const int jhi = window_only ? min(thi - (pad + 1), P - 1) : P - 1;
 
   if constexpr (Traits<FL>::kAge) {
     AgeMap<FL> map;
     map.init(M, w.theta, off_raw, pad, P);
     double carry[6] = {0, 0, 0, 0, 0, 0};
-    for (int base = jlo; base < P; base += 64) {
+    for (int base = jlo; base <= jhi; base += 64) {
       double ca[6], cb[6];
       conv_group2<3, PAD>(w.S, w.Wabs, lo[0], hi[0], base + lane, P, ca, cb);
       conv_group2<3, PAD>(w.S + stride, w.Wabs + PAD * 4, lo[1], hi[1], base + lane, P, ca + 3, cb + 3);
@@ -1416,7 +1444,7 @@ k_score(const DevModel M, const PriorTerm *__restrict__ PT, int n_prior, const d
     // hospi/deadi = c(v[1], diff(v)) (model-simple-ode-drj-cmp.R:115-122)
     const double rate[2] = {w.theta[4], 0.007};
     double carry[2] = {0, 0};
-    for (int base = jlo; base < P; base += 64) {
+    for (int base = jlo; base <= jhi; base += 64) {
       double ca[2], cb[2];
       conv_group2<2, PAD>(w.S, w.Wabs, lo[0], hi[0], base + lane, P, ca, cb);
 #pragma unroll
@@ -1677,20 +1705,21 @@ static cudaError_t launch_eval_fl(const EvalArgs &a) {
   if (a.ev) cudaEventRecord(a.ev[2], s);
   if (a.ev_after_mid) cudaEventRecord(a.ev_after_mid, s);
   const bool want_ext = a.series_out && a.ns_total > (Traits<FL>::kAge ? 8 : 3);
+  const int window_only = (a.series_out || !a.window_only) ? 0 : 1;  // scoring reads S(t) only up to the last data-window day
   if (use_pair && !want_ext) {
-    if constexpr (Traits<FL>::kAge) k_ode_age2<FL, true><<<pair_blocks, 64, 0, s>>>(M, a.theta, a.ld, n, a.offset, a.pad, a.hist1, a.hist2, a.ckpt);
+    if constexpr (Traits<FL>::kAge) k_ode_age2<FL, true><<<pair_blocks, 64, 0, s>>>(M, a.theta, a.ld, n, a.offset, a.pad, a.hist1, a.hist2, a.ckpt, window_only);
   } else if (want_ext) {
     // trajectories with the ext series: pass 2 also writes E, I, R and the Re/Rt diagnostics (no restart)
     k_ode<FL, true, true><<<ode_blocks, 32, 0, s>>>(M, a.theta, a.ld, n, a.offset, a.pad, a.hist1, a.hist2, nullptr,
                                                     a.series_out, a.ns_total);
-  } else k_ode<FL, true><<<ode_blocks, 32, 0, s>>>(M, a.theta, a.ld, n, a.offset, a.pad, a.hist1, a.hist2, a.ckpt);
+  } else k_ode<FL, true><<<ode_blocks, 32, 0, s>>>(M, a.theta, a.ld, n, a.offset, a.pad, a.hist1, a.hist2, a.ckpt, nullptr, 0, window_only);
   if (a.ev) cudaEventRecord(a.ev[3], s);
   if (a.series_out) {
     k_series<FL><<<warp_blocks, 128, smem_score, s>>>(M, a.theta, a.ld, n, a.hist2, a.offset, a.pad, a.W, a.pmeta,
                                                       a.status, a.series_out, a.ns_total);
   } else {
     k_score<FL><<<warp_blocks, 128, smem_score, s>>>(M, a.PT, a.n_prior, a.theta, a.ld, n, a.hist2, a.offset, a.pad, a.W, a.pmeta,
-                                                     a.status, a.logl, a.logp, a.terms);
+                                                     a.status, a.logl, a.logp, a.terms, window_only);
   }
   if (a.ev) cudaEventRecord(a.ev[4], s);
   return cudaGetLastError();

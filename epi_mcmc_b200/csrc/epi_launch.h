@@ -21,6 +21,7 @@ struct EvalArgs {
   double *logl, *logp, *terms;  // device, any may be null
   double *series_out;           // non-null: write calculateModel series instead of scoring
   int ns_total = 0;             // series per chain in series_out: 8/3 basic, 18/8 with the ext series
+  int window_only = 1;          // scoring path: integrate / sweep only up to the data windows (EPI_WINDOW_ONLY=0: whole period)
   cudaStream_t stream;
   cudaEvent_t *ev;  // null or 5 events bracketing the 4 launches
   cudaEvent_t ev_after_mid = nullptr;  // optional: recorded after k_mid (stagger point of the two-stream mode)

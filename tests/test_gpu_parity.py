@@ -394,3 +394,25 @@ def test_two_devices_in_one_process():
     assert np.array_equal(la, lb, equal_nan=True) and np.array_equal(pa, pb) and np.array_equal(sa, sb)
     A.close()
     B.close()
+
+
+@pytest.mark.parametrize("name,m", [("A300", 4), ("A365", 1), ("I290", 2), ("S365", 2), ("NE120", 4), ("DE", 4)])
+def test_window_limited_sweep_is_bit_identical(name, m, monkeypatch):
+    """The scoring path integrates pass 2 only up to the last data-window day and sweeps only the window days
+    (+ one predecessor): not a bit of logl, the terms or the statuses may differ from sweeping the whole period
+    (EPI_WINDOW_ONLY=0) — incl. invalid offsets, clamped windows and NA draws of the golden theta sets."""
+    from epi_mcmc_b200.model import Model, load_dataset
+    theta = np.array(load_golden(name)["theta"])
+    ds = load_dataset(name)
+    monkeypatch.setenv("EPI_WINDOW_ONLY", "1")
+    A = Model(ds, substeps=m)
+    monkeypatch.setenv("EPI_WINDOW_ONLY", "0")
+    B = Model(ds, substeps=m)
+    la, pa, sa = A.calclogpost_batch(theta)
+    lb, pb, sb = B.calclogpost_batch(theta)
+    assert np.array_equal(la, lb, equal_nan=True) and np.array_equal(pa, pb) and np.array_equal(sa, sb)
+    oa, _, ta = A.eval_detail(theta)
+    ob, _, tb = B.eval_detail(theta)
+    assert np.array_equal(oa, ob) and np.array_equal(ta, tb, equal_nan=True)
+    A.close()
+    B.close()
