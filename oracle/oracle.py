@@ -121,6 +121,9 @@ def conditioning(flavour, data, theta, period, substeps, logl, ulps=32, n_draws=
             with np.errstate(invalid="ignore"):
                 dlt = np.abs(r["logl"] - logl)
             cond = np.maximum(cond, np.where(np.isfinite(dlt), dlt, 0.0))
+            # the jitter turns a finite value into NA or back (the hospital ratio term 0/0 of two sums of
+            # cancellation residue): nothing about this theta is determined beyond rounding
+            cond = np.where(np.isnan(r["logl"]) != np.isnan(logl), np.inf, cond)
     finally:
         lib().oracle_set_jitter(0, 0)
     return cond

@@ -52,4 +52,4 @@ def logl_within_bar(got, ref, cond, tol=1e-10):
     same = (np.isnan(got) & np.isnan(ref)) | ((got == ref) & ~np.isfinite(got))
     with np.errstate(invalid="ignore"):
         ok = np.abs(got - ref) <= np.maximum(tol * np.abs(ref), 4.0 * np.asarray(cond))
-    return ok | same
+    return ok | same | np.isinf(np.asarray(cond))  # cond = inf: the oracle itself flips NA <-> finite under 32-ulp jitter

@@ -74,7 +74,10 @@ def test_oracle_live_random_theta(name, n, oracle):
     off, pad, _ = M.eval_detail(theta)
     ref = oracle.evaluate(ds["flavour"], ds, theta, ds["period"], 4, n_threads=8)
     # a theta whose died(t) touches the threshold within rounding may legitimately pick the
-    # neighbouring day: allow that for at most 1 in 1000, everything else must match exactly
+    # neighbouring day, and one whose hospital series are pure cancellation residue in the ratio window
+    # (no epidemic: ytotal/(ytotal + ototal) is noise/noise or 0/0, :563-565) may flip NA <-> finite — a wide
+    # sweep (tests/_sweep.py, 10^5 box-uniform draws) sees the latter at ~1e-4, only in that term:
+    # allow at most 1 in 1000, everything else must match exactly
     mism = (off != ref["offset"]) | (status != ref["status"]) | (pad != ref["padding"])
     assert mism.sum() <= max(1, n // 1000), mism.sum()
     ok = ~mism
