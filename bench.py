@@ -388,7 +388,18 @@ def main():
     days_pass2 = float(np.maximum(nint - D, 0).mean())
     days_swept = float(np.minimum(swept, P_ + 64).mean())
     step_flop = fa["per_kernel"]["ode_pass2"] / P_                        # per integrated day
-    fa["per_kernel_executed"] = dict(fa["per_kernel"], ode_pass2=days_pass2 * step_flop,
+    # whole-period pass 1 (simple / Ne / age-2i) in two rounds: 128 days for everybody, all days again for the
+    # chains that did not cross the threshold there (kPass1Chunk in epi_kernels.cu)
+    P1_ = 60 if ds["flavour"] == "age2q" else P_
+    chunk_on = os.environ.get("EPI_PASS1_CHUNK", "1") != "0" and P1_ > 160
+    if chunk_on:
+        first = off_s + lo_ - pad_s - 1
+        retry = (off_s == 10000) | (first >= 128)
+        days_pass1 = float(128 + retry.mean() * P1_)
+    else:
+        days_pass1 = float(P1_)
+    fa["per_kernel_executed"] = dict(fa["per_kernel"], ode_pass1=fa["per_kernel"]["ode_pass1"] * days_pass1 / P1_,
+                                     ode_pass2=days_pass2 * step_flop,
                                      score=fa["per_kernel"]["score"] - (P_ - min(days_swept, P_)) * fa["score_per_day"])
     fa["total_executed"] = sum(fa["per_kernel_executed"].values())
     knames = ["ode_pass1", "profiles_threshold", "ode_pass2", "score"]
@@ -435,7 +446,7 @@ def main():
         "roofline_all": per_kernel,
         "f_alg": {"per_eval": fa["total"], "per_eval_executed": fa["total_executed"],
                   "pass2_restart_days_mean": d_mean, "pass2_days_integrated_mean": days_pass2,
-                  "score_days_swept_mean": days_swept, "period": P_, "ode_share": fa["ode"] / fa["total"],
+                  "score_days_swept_mean": days_swept, "pass1_days_integrated_mean": days_pass1, "period": P_, "ode_share": fa["ode"] / fa["total"],
                   "whole_step_tflops": whole_tf, "whole_step_frac": whole_tf / peak_tf if peak_tf else None,
                   "whole_step_frac_if_counted_without_reductions":
                       (fa["total"] * n / (step_ms * 1e-3) / 1e12) / peak_tf if peak_tf else None,

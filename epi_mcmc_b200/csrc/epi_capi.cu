@@ -421,6 +421,7 @@ extern "C" int epi_create(const epi_model_desc *desc, const epi_data *data, int 
     cudaEventCreateWithFlags(&h->ev_stagger, cudaEventDisableTiming);
     { const char *env = getenv("EPI_PASS2_RESTART"); h->restart = !(env && env[0] == '0'); }
     { const char *env = getenv("EPI_WINDOW_ONLY"); h->window_only = !(env && env[0] == '0'); }
+    { const char *env = getenv("EPI_PASS1_CHUNK"); h->pass1_chunk = !(env && env[0] == '0'); }
     { const char *env = getenv("EPI_SPLIT_STREAMS"); h->split = (env && (env[0] == '1' || env[0] == '2')); h->split_mode = (env && env[0] == '2') ? 2 : 1; }
     for (auto &ev : h->ev) cudaEventCreate(&ev);
     rc = fill_model(h, *desc, *data);
@@ -539,6 +540,7 @@ static EvalArgs make_args(epi_handle *h, Workspace &w, const DevModel &M, const 
   a.series_out = d_series ? d_series + first * NS * M.P : nullptr;
   a.ns_total = NS;
   a.window_only = h->window_only ? 1 : 0;
+  a.pass1_chunk = h->pass1_chunk ? 1 : 0;
   a.stream = stream;
   a.ev = nullptr;
   return a;
@@ -564,12 +566,12 @@ int epi_launch_eval_ws(epi_handle *h, Workspace &w, const DevModel &M, const dou
     if (e == cudaSuccess) e = launch_eval(a1);
     cudaEventRecord(h->ev_join, h->stream2);
     cudaStreamWaitEvent(stream, h->ev_join, 0);
-    h->launches += 8;
+    h->launches += 2 * eval_launch_count(M, h->pass1_chunk);
   } else {
     EvalArgs a = make_args(h, w, M, d_theta, ld, n, 0, model_space, d_logl, d_logp, d_status, d_terms, d_series, stream, ns_total);
     a.ev = h->timing ? h->ev : nullptr;
     e = launch_eval(a);
-    h->launches += 4;
+    h->launches += eval_launch_count(M, h->pass1_chunk);
   }
   if (e != cudaSuccess) return epi_fail(h, EPI_ERR_CUDA, "kernel launch: %s", cudaGetErrorString(e));
   return EPI_OK;

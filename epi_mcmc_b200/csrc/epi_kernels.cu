@@ -36,6 +36,7 @@ __host__ __device__ constexpr int hist_pitch(int ndays) { return (ndays + 1) & ~
 // chain-major layout made pass 1 LSU bound, 0.24 -> 1.14 ms — and pass 2 resumes from day D
 // instead of re-integrating it.
 __host__ __device__ constexpr int ckpt_days(int P1) { return P1 < 64 ? P1 : 64; }
+constexpr int kPass1Chunk = 128;  // first-round days of a whole-period pass 1 (>= the checkpoint window)
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *mbar, unsigned count) {
@@ -64,6 +65,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t *mbar, unsigned parity) {
       "r"(parity)
       : "memory");
 }
+
+// internal status bit: pass 1 was integrated for its first chunk of days only and the threshold was not
+// crossed there — the chain's pass 1 + threshold search are redone over the whole pass-1 period by the retry
+// launches that follow in the same batch (never visible outside the library)
+constexpr int kStRetry = 1 << 30;
 
 template <int FL>
 struct Traits {
@@ -429,7 +435,7 @@ __global__ void __maxnreg__(128)
 k_ode(const DevModel M, const double *__restrict__ theta, int64_t ld, int64_t n,
       const int *__restrict__ offset, const int *__restrict__ padv, const double *__restrict__ hist1,
       double *__restrict__ hist_out, double *__restrict__ ckpt, double *__restrict__ series = nullptr,
-      int ns_total = 0, int window_only = 0) {
+      int ns_total = 0, int window_only = 0, int ndays_limit = 0, const int *__restrict__ retry_status = nullptr) {
   constexpr int NEQ = Traits<FL>::NEQ, NG = Traits<FL>::NG;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -459,6 +465,13 @@ k_ode(const DevModel M, const double *__restrict__ theta, int64_t ld, int64_t n,
   double tcut = INFINITY;
   int t0 = 1;
   int nint = ndays;  // days integrated here
+  if constexpr (!PASS2) {
+    // pass 1 in two rounds when it covers the whole period (simple / age-2i): the first round integrates only
+    // the first ndays_limit days, where the threshold is usually crossed; chains that did not cross there are
+    // flagged by k_mid and integrated over the whole pass-1 period by the retry round
+    if (retry_status && !(retry_status[i] & kStRetry)) return;
+    if (ndays_limit > 0) nint = min(nint, ndays_limit);
+  }
   // FULL: the ext series of this chain, [series][P] behind the basic ones (8 age / 3 simple)
   double *eo = nullptr;
   if constexpr (FULL) eo = series + ((int64_t)i * ns_total + (Traits<FL>::kAge ? 8 : 3)) * (int64_t)M.P;
@@ -671,7 +684,8 @@ template <int FL, bool PASS2>
 __global__ void __maxnreg__(128)
 k_ode_age2(const DevModel M, const double *__restrict__ theta, int64_t ld, int64_t n, const int *__restrict__ offset,
            const int *__restrict__ padv, const double *__restrict__ hist1, double *__restrict__ hist_out,
-           double *__restrict__ ckpt, int window_only = 0) {
+           double *__restrict__ ckpt, int window_only = 0, int ndays_limit = 0,
+           const int *__restrict__ retry_status = nullptr) {
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t i = tid >> 1;  // chain
   if (i >= n) return;
@@ -681,6 +695,10 @@ k_ode_age2(const DevModel M, const double *__restrict__ theta, int64_t ld, int64
   const double *th = theta + i;
   const int ndays = PASS2 ? M.P : M.P1;
   int nint = ndays;  // days integrated here
+  if constexpr (!PASS2) {  // two-round pass 1, see k_ode
+    if (retry_status && !(retry_status[i] & kStRetry)) return;
+    if (ndays_limit > 0) nint = min(nint, ndays_limit);
+  }
   double *out = hist_out + (i * 2 + g) * (int64_t)hist_pitch(ndays);
 
   const double Ngrp = g ? M.No : M.Ny;
@@ -962,13 +980,15 @@ template <int FL>
 __global__ void __launch_bounds__(128)
 k_mid(const DevModel M, const double *__restrict__ theta, int64_t ld, int64_t n, const double *__restrict__ hist1,
       int *__restrict__ offset, int *__restrict__ padv, int *__restrict__ status, double *__restrict__ Wg,
-      int2 *__restrict__ pmeta, int model_space) {
+      int2 *__restrict__ pmeta, int model_space, int ndays_search, int only_flagged) {
   constexpr int NK = Traits<FL>::NK, NG = Traits<FL>::NG;
   extern __shared__ double smem[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int64_t chain = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
   if (chain >= n) return;
+  if (only_flagged && !(status[chain] & kStRetry)) return;  // retry round: only the chains the first round flagged
   const int P1 = M.P1;
+  const int nsearch = ndays_search > 0 ? min(P1, ndays_search) : P1;  // days of pass 1 that exist in this round
   const WarpSmem w = carve<FL>(smem + (size_t)wib * warp_smem_doubles<FL>(P1), P1);
   stage_history_begin<FL>(w.S, w.mbar, hist1, chain, P1, lane);  // asynchronous; consumed after the profiles
 
@@ -1052,10 +1072,10 @@ k_mid(const DevModel M, const double *__restrict__ theta, int64_t ld, int64_t n,
   int first = -1;
   double thr;  // t0_morts (2q :69, 2i :71) / mort_lockdown_threshold
   if constexpr (Traits<FL>::k2i) thr = w.theta[19]; else if constexpr (Traits<FL>::kAge) thr = w.theta[17]; else thr = w.theta[7];
-  for (int base = 0; base < P1 && first < 0; base += 32) {
+  for (int base = 0; base < nsearch && first < 0; base += 32) {
     const int j = base + lane;
     bool hit = false;
-    if (j < P1) {
+    if (j < nsearch) {
       double died;
       if constexpr (Traits<FL>::kAge) {
         const double cy = conv_at<PAD>(w.S, w.W + 2 * EPI_MAX_TAPS, pad, j, dmin_[2], n_[2]);
@@ -1074,6 +1094,7 @@ k_mid(const DevModel M, const double *__restrict__ theta, int64_t ld, int64_t n,
   if (first >= 0) off = pad + 1 + first - M.lockdown_offset;
   if (!Traits<FL>::kAge && thr < 0) off = 1 - M.lockdown_offset;  // died[1] = 0 > threshold (simple prefill is 0, :70)
   if (off == EPI_INVALID_DATA_OFFSET) st |= EPI_ST_INVALID_OFFSET;
+  if (off == EPI_INVALID_DATA_OFFSET && nsearch < P1) st |= kStRetry;  // not crossed in the first chunk: redo over P1 days
   if (lane == 0) { offset[chain] = off; padv[chain] = pad; status[chain] = st; }
   (void)NG;
 }
@@ -1697,11 +1718,21 @@ static cudaError_t launch_eval_fl(const EvalArgs &a) {
   // while all 2n lanes fit one wave (n <= 256 chains per SM), thread-per-chain wins above that
   // (measured on B200, 65,536 chains: 2.25 ms vs 2.07 ms for pass 2).
   const bool use_pair = Traits<FL>::kAge && n <= (int64_t)n_sm * 256;
+  // pass 1 that covers the whole period (simple / age-2i) is integrated for its first kPass1Chunk days first:
+  // the threshold is normally crossed there and everything behind the crossing is never read.  Chains that
+  // did not cross are redone over the whole pass-1 period by a retry round (k_mid flags them).
+  const int chunk = (a.pass1_chunk && M.P1 > kPass1Chunk + kPass1Chunk / 4) ? kPass1Chunk : 0;
   if (use_pair) {
-    if constexpr (Traits<FL>::kAge) k_ode_age2<FL, false><<<pair_blocks, 64, 0, s>>>(M, a.theta, a.ld, n, nullptr, nullptr, nullptr, a.hist1, a.ckpt);
-  } else k_ode<FL, false><<<ode_blocks, 32, 0, s>>>(M, a.theta, a.ld, n, nullptr, nullptr, nullptr, a.hist1, a.ckpt);
+    if constexpr (Traits<FL>::kAge) k_ode_age2<FL, false><<<pair_blocks, 64, 0, s>>>(M, a.theta, a.ld, n, nullptr, nullptr, nullptr, a.hist1, a.ckpt, 0, chunk);
+  } else k_ode<FL, false><<<ode_blocks, 32, 0, s>>>(M, a.theta, a.ld, n, nullptr, nullptr, nullptr, a.hist1, a.ckpt, nullptr, 0, 0, chunk);
   if (a.ev) cudaEventRecord(a.ev[1], s);
-  k_mid<FL><<<warp_blocks, 128, smem_mid, s>>>(M, a.theta, a.ld, n, a.hist1, a.offset, a.pad, a.status, a.W, a.pmeta, a.model_space);
+  k_mid<FL><<<warp_blocks, 128, smem_mid, s>>>(M, a.theta, a.ld, n, a.hist1, a.offset, a.pad, a.status, a.W, a.pmeta, a.model_space, chunk, 0);
+  if (chunk) {
+    if (use_pair) {
+      if constexpr (Traits<FL>::kAge) k_ode_age2<FL, false><<<pair_blocks, 64, 0, s>>>(M, a.theta, a.ld, n, nullptr, nullptr, nullptr, a.hist1, a.ckpt, 0, 0, a.status);
+    } else k_ode<FL, false><<<ode_blocks, 32, 0, s>>>(M, a.theta, a.ld, n, nullptr, nullptr, nullptr, a.hist1, a.ckpt, nullptr, 0, 0, 0, a.status);
+    k_mid<FL><<<warp_blocks, 128, smem_mid, s>>>(M, a.theta, a.ld, n, a.hist1, a.offset, a.pad, a.status, a.W, a.pmeta, a.model_space, 0, 1);
+  }
   if (a.ev) cudaEventRecord(a.ev[2], s);
   if (a.ev_after_mid) cudaEventRecord(a.ev_after_mid, s);
   const bool want_ext = a.series_out && a.ns_total > (Traits<FL>::kAge ? 8 : 3);
@@ -1723,6 +1754,10 @@ static cudaError_t launch_eval_fl(const EvalArgs &a) {
   }
   if (a.ev) cudaEventRecord(a.ev[4], s);
   return cudaGetLastError();
+}
+
+int eval_launch_count(const DevModel &M, int pass1_chunk) {
+  return (pass1_chunk && M.P1 > kPass1Chunk + kPass1Chunk / 4) ? 6 : 4;
 }
 
 cudaError_t launch_eval(const EvalArgs &a) {
