@@ -2,8 +2,10 @@
  * epimcmc_shim.c — R `.Call` shim over libepimcmc.so (include/epimcmc.h).
  *
  * SOURCE ONLY in this repository: R, R.h and Rinternals.h are not installed in the
- * build image, so this file is not compiled or tested here (the same C entry points
- * are driven through Python ctypes by tests/).  On a machine with R:
+ * build image, so this file is not built or run here; it is type-checked against
+ * include/epimcmc.h with a declarations-only stand-in for R's C API (tests/r_stub,
+ * tests/test_capi.py), and the same C entry points are driven through Python ctypes by
+ * tests/.  On a machine with R:
  *
  *   R CMD SHLIB epimcmc_shim.c -I../include -L../epi_mcmc_b200/csrc -lepimcmc -o epimcmc_shim.so
  *
@@ -12,7 +14,8 @@
  * and binds, one to one:
  *   C_epi_create      -> epi_create      handle from the data/settings globals
  *   C_epi_logpost     -> epi_eval        batched calclogl(transformParams(.)) + calclogp(.)
- *   C_epi_trajectories-> epi_trajectories calculateModel(params, period) for many draws
+ *   C_epi_trajectories-> epi_trajectories / epi_trajectories_ext   calculateModel(params, period) for many draws
+ *   C_epi_quantiles   -> epi_quantiles   quantileData (libMCMC.R:151-172)
  *   C_epi_df_params   -> epi_df_params
  * R is single-threaded and drjacoby calls back on the main thread, which is all the
  * handle's "one host thread at a time" rule needs.  Errors: the library never longjmps;
@@ -116,19 +119,43 @@ SEXP C_epi_logpost(SEXP ptr, SEXP theta) {
   return out;
 }
 
-/* .Call(C_epi_trajectories, handle, params, period): params d x n MODEL-space; returns a
- * period x n_series x n array plus offset and padding. */
-SEXP C_epi_trajectories(SEXP ptr, SEXP params, SEXP period) {
+/* .Call(C_epi_trajectories, handle, params, period, ext): params d x n MODEL-space; returns a
+ * period x n_series x n array plus offset and padding.  ext = TRUE adds the state fields derived from the
+ * other columns of the ode() matrix (y.E ... o.R, Re, Rt, y.Re, o.Re; epi_trajectories_ext). */
+SEXP C_epi_trajectories(SEXP ptr, SEXP params, SEXP period, SEXP ext) {
   epi_handle *h = get_handle(ptr);
-  const int d = epi_n_params(h), ns = epi_n_series(h), P = Rf_asInteger(period);
+  const int want_ext = Rf_asLogical(ext) == TRUE;
+  const int d = epi_n_params(h), ns = want_ext ? epi_n_series_ext(h) : epi_n_series(h), P = Rf_asInteger(period);
   const R_xlen_t n = XLENGTH(params) / d;
   SEXP arr = PROTECT(Rf_allocVector(REALSXP, (R_xlen_t)P * ns * n));
   SEXP off = PROTECT(Rf_allocVector(INTSXP, n)), pad = PROTECT(Rf_allocVector(INTSXP, n));
-  int rc = epi_trajectories(h, REAL(params), (int64_t)n, EPI_LAYOUT_AOS, P, REAL(arr), INTEGER(off), INTEGER(pad));
+  int rc = want_ext ? epi_trajectories_ext(h, REAL(params), (int64_t)n, EPI_LAYOUT_AOS, P, REAL(arr), INTEGER(off), INTEGER(pad))
+                    : epi_trajectories(h, REAL(params), (int64_t)n, EPI_LAYOUT_AOS, P, REAL(arr), INTEGER(off), INTEGER(pad));
   SEXP out = PROTECT(Rf_allocVector(VECSXP, 3));
   SET_VECTOR_ELT(out, 0, arr); SET_VECTOR_ELT(out, 1, off); SET_VECTOR_ELT(out, 2, pad);
   UNPROTECT(4);
   if (rc) Rf_error("epi_trajectories failed (%d): %s", rc, epi_last_error(h));
+  return out;
+}
+
+/* .Call(C_epi_quantiles, handle, params, period, startoffset, series_a, series_b, probs): quantileData of
+ * R/lib/libMCMC.R:151-172 on the device.  params d x n MODEL-space (transformParams already applied);
+ * series_a / series_b are 0-based indices into the ext series list (series_b = -1: a single series, else
+ * their sum).  Returns a period x length(probs) matrix. */
+SEXP C_epi_quantiles(SEXP ptr, SEXP params, SEXP period, SEXP startoffset, SEXP series_a, SEXP series_b, SEXP probs) {
+  epi_handle *h = get_handle(ptr);
+  const int d = epi_n_params(h), P = Rf_asInteger(period), nq = (int)XLENGTH(probs);
+  const R_xlen_t n = XLENGTH(params) / d;
+  SEXP out = PROTECT(Rf_allocMatrix(REALSXP, P, nq));
+  /* the library returns period x n_probs row-major; R matrices are column-major */
+  double *tmp = (double *)R_alloc((size_t)P * nq, sizeof(double));
+  int rc = epi_quantiles(h, REAL(params), (int64_t)n, EPI_LAYOUT_AOS, P, Rf_asInteger(startoffset), Rf_asInteger(series_a),
+                         Rf_asInteger(series_b), REAL(probs), nq, tmp);
+  if (!rc)
+    for (int j = 0; j < P; ++j)
+      for (int q = 0; q < nq; ++q) REAL(out)[j + (R_xlen_t)q * P] = tmp[(size_t)j * nq + q];
+  UNPROTECT(1);
+  if (rc) Rf_error("epi_quantiles failed (%d): %s", rc, epi_last_error(h));
   return out;
 }
 
@@ -148,7 +175,8 @@ SEXP C_epi_df_params(SEXP ptr) {
 static const R_CallMethodDef call_methods[] = {
     {"C_epi_create", (DL_FUNC)&C_epi_create, 5},
     {"C_epi_logpost", (DL_FUNC)&C_epi_logpost, 2},
-    {"C_epi_trajectories", (DL_FUNC)&C_epi_trajectories, 3},
+    {"C_epi_trajectories", (DL_FUNC)&C_epi_trajectories, 4},
+    {"C_epi_quantiles", (DL_FUNC)&C_epi_quantiles, 7},
     {"C_epi_df_params", (DL_FUNC)&C_epi_df_params, 1},
     {NULL, NULL, 0}};
 

@@ -69,23 +69,37 @@ calclogl <- function(params, x) {
 }
 calclogp <- function(params) calclogpost_batch(matrix(params, ncol = 1))$logp
 
-series.names <- c("y.S", "o.S", "y.casei", "o.casei", "y.hospi", "o.hospi", "y.deadi", "o.deadi")
-calculateModel_batch <- function(params, period) {
-    r <- .Call("C_epi_trajectories", epi_handle, params, as.integer(period))
-    arr <- array(r[[1]], dim = c(period, length(series.names), ncol(params)))
+series.names <- c("y.S", "o.S", "y.casei", "o.casei", "y.hospi", "o.hospi", "y.deadi", "o.deadi",
+                  "y.E", "y.I", "y.R", "o.E", "o.I", "o.R", "Re", "Rt", "y.Re", "o.Re")
+calculateModel_batch <- function(params, period, ext = TRUE) {
+    r <- .Call("C_epi_trajectories", epi_handle, params, as.integer(period), ext)
+    ns <- if (ext) length(series.names) else 8L
+    arr <- array(r[[1]], dim = c(period, ns, ncol(params)))
     list(series = arr, offset = r[[2]], padding = r[[3]])
 }
+## values of 1..padding as the reference pre-fills them (model-age-groups2q.R:118-141; y.E / o.E are first
+## assigned on (padding+1):..., i.e. NA before)
+series.prefill <- c(y.N - 1, o.N, 0, 0, 0, 0, 0, 0, NA, 0, 0, NA, 0, 0, 0, 0, 0, 0)
 calculateModel <- function(params, period) {
     r <- calculateModel_batch(matrix(params, ncol = 1), period)
     padding <- r$padding[1]
     state <- NULL
     for (k in seq_along(series.names))
-        state[[series.names[k]]] <- c(rep(if (k == 1) y.N - 1 else if (k == 2) o.N else 0, padding), r$series[, k, 1])
+        state[[series.names[k]]] <- c(rep(series.prefill[k], padding), r$series[, k, 1])
     state$y.died <- cumsum(state$y.deadi); state$o.died <- cumsum(state$o.deadi)
     state$y.case <- cumsum(state$y.casei); state$o.case <- cumsum(state$o.casei)
     state$padding <- padding
     state$offset <- r$offset[1]
     state
+}
+
+## quantileData (libMCMC.R:151-172) on the GPU: `series` is a name from series.names or two names to be summed,
+## e.g. quantileData_gpu(data_sample, c("y.hospi", "o.hospi"), 0, 200, c(0.05, 0.5, 0.95)), or "Re" (analyzeMCMC.R:265)
+quantileData_gpu <- function(sample, series, startoffset, period, quantiles) {
+    params <- apply(sample[, fit.paramnames], 1, function(p) transformParams(unlist(p, use.names = FALSE)))
+    idx <- match(series, series.names) - 1L
+    .Call("C_epi_quantiles", epi_handle, params, as.integer(period), as.integer(startoffset), idx[1],
+          if (length(idx) > 1) idx[2] else -1L, as.numeric(quantiles))
 }
 
 calcNominalState <- function(state) {

@@ -64,3 +64,27 @@ def test_struct_layout_matches_header():
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
         sizes = [int(v) for v in subprocess.check_output([exe]).split()]
     assert sizes == [C.sizeof(_capi.ModelDesc), C.sizeof(_capi.Data), C.sizeof(_capi.SamplerCfg)]
+
+
+def test_r_shim_type_checks_against_the_header():
+    """r/epimcmc_shim.c cannot be built here (no R), but it must at least type-check against include/epimcmc.h
+    with a declarations-only stand-in for R's C API (tests/r_stub): every C_* wrapper calls existing entry points
+    with the right argument types, and registers the arity it really has."""
+    import re
+    import subprocess
+    from conftest import ROOT
+    src = os.path.join(ROOT, "r", "epimcmc_shim.c")
+    r = subprocess.run(["gcc", "-fsyntax-only", "-Wall", "-Wextra", "-Werror", "-Wno-cast-function-type",
+                        "-I" + os.path.join(ROOT, "tests", "r_stub"), "-I" + os.path.join(ROOT, "include"), src],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    text = open(src).read()
+    for name, arity in re.findall(r'\{"(C_\w+)", \(DL_FUNC\)&\w+, (\d+)\}', text):
+        m = re.search(r"SEXP " + name + r"\(([^)]*)\)", text)
+        assert m and len(m.group(1).split(",")) == int(arity), name
+    # every .Call in the drop-in model files names a registered routine with that many arguments
+    registered = dict(re.findall(r'\{"(C_\w+)", \(DL_FUNC\)&\w+, (\d+)\}', text))
+    for fn in ("model-age-groups2q-gpu.R", "model-age-groups2i-gpu.R"):
+        rsrc = open(os.path.join(ROOT, "r", fn)).read()
+        for call in re.findall(r'\.Call\("(C_\w+)"', rsrc):
+            assert call in registered, (fn, call)
