@@ -83,7 +83,11 @@ def f_alg(flavour, P, m, taps_mean, n_terms, n_prior):
         "ode_pass2": m * P * (4 * F_rhs + 14 * S),
         "score": C2 * P * 2 * taps_mean + 6 * C2 * P + 72 * n_terms + 40 * n_prior,
     }
-    return dict(total=total, ode=ode, per_kernel=per_kernel, score_per_day=C2 * 2 * taps_mean + 6 * C2)
+    # the removed compartment(s) are not integrated on the hot path (bit-identical): the RK4
+    # update of 2 (age) / 1 (simple) of the S states is not executed
+    n_r = 2 if age else 1
+    return dict(total=total, ode=ode, per_kernel=per_kernel, score_per_day=C2 * 2 * taps_mean + 6 * C2,
+                ode_executed_share=(4 * F_rhs + 14 * (S - n_r)) / (4 * F_rhs + 14 * S))
 
 
 def mean_taps(flavour, theta):
@@ -398,8 +402,9 @@ def main():
         days_pass1 = float(128 + retry.mean() * P1_)
     else:
         days_pass1 = float(P1_)
-    fa["per_kernel_executed"] = dict(fa["per_kernel"], ode_pass1=fa["per_kernel"]["ode_pass1"] * days_pass1 / P1_,
-                                     ode_pass2=days_pass2 * step_flop,
+    r_share = fa["ode_executed_share"] if os.environ.get("EPI_FORCE_R_FALLBACK", "0") != "1" else 1.0
+    fa["per_kernel_executed"] = dict(fa["per_kernel"], ode_pass1=fa["per_kernel"]["ode_pass1"] * days_pass1 / P1_ * r_share,
+                                     ode_pass2=days_pass2 * step_flop * r_share,
                                      score=fa["per_kernel"]["score"] - (P_ - min(days_swept, P_)) * fa["score_per_day"])
     fa["total_executed"] = sum(fa["per_kernel_executed"].values())
     knames = ["ode_pass1", "profiles_threshold", "ode_pass2", "score"]
@@ -453,7 +458,9 @@ def main():
                   "note": "per_eval is the SURVEY 8d figure; per_eval_executed and every frac count only the work "
                           "actually done: pass 2 resumes from the pass-1 checkpoint after pass2_restart_days_mean "
                           "bit-identical days and stops at the last data-window day, the score sweep covers the data "
-                          "windows plus one predecessor day (results identical; DESIGN.md section 3)"},
+                          "windows plus one predecessor day, and the removed compartment R is not integrated (it only "
+                          "enters the reference through a bounds guard that provably cannot fire on it; chains where that "
+                          "is not certain are recomputed with R) — results identical bit for bit; DESIGN.md section 4"},
     }
     if comm.rank == 0 and comm.world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(ds, theta, args.substeps)

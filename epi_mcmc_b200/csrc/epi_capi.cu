@@ -422,6 +422,7 @@ extern "C" int epi_create(const epi_model_desc *desc, const epi_data *data, int 
     { const char *env = getenv("EPI_PASS2_RESTART"); h->restart = !(env && env[0] == '0'); }
     { const char *env = getenv("EPI_WINDOW_ONLY"); h->window_only = !(env && env[0] == '0'); }
     { const char *env = getenv("EPI_PASS1_CHUNK"); h->pass1_chunk = !(env && env[0] == '0'); }
+    { const char *env = getenv("EPI_FORCE_R_FALLBACK"); h->force_need_r = (env && env[0] == '1'); }
     { const char *env = getenv("EPI_SPLIT_STREAMS"); h->split = (env && (env[0] == '1' || env[0] == '2')); h->split_mode = (env && env[0] == '2') ? 2 : 1; }
     for (auto &ev : h->ev) cudaEventCreate(&ev);
     rc = fill_model(h, *desc, *data);
@@ -438,7 +439,7 @@ extern "C" int epi_create(const epi_model_desc *desc, const epi_data *data, int 
 
 static void free_workspace(Workspace &w) {
   cudaFree(w.theta); cudaFree(w.aos); cudaFree(w.hist1); cudaFree(w.hist2); cudaFree(w.ckpt); cudaFree(w.W); cudaFree(w.pmeta);
-  cudaFree(w.offset); cudaFree(w.pad); cudaFree(w.status); cudaFree(w.logl); cudaFree(w.logp); cudaFree(w.terms);
+  cudaFree(w.offset); cudaFree(w.pad); cudaFree(w.status); cudaFree(w.need_r); cudaFree(w.logl); cudaFree(w.logp); cudaFree(w.terms);
   cudaFree(w.series);
   w = Workspace();
 }
@@ -509,6 +510,8 @@ int epi_ensure_workspace(epi_handle *h, Workspace &w, const DevModel &M, int64_t
   CUDA_OK(h, cudaMalloc(&w.offset, sizeof(int) * (size_t)ld));
   CUDA_OK(h, cudaMalloc(&w.pad, sizeof(int) * (size_t)ld));
   CUDA_OK(h, cudaMalloc(&w.status, sizeof(int) * (size_t)ld));
+  CUDA_OK(h, cudaMalloc(&w.need_r, sizeof(int) * (size_t)ld));
+  CUDA_OK(h, cudaMemset(w.need_r, 0, sizeof(int) * (size_t)ld));
   CUDA_OK(h, cudaMalloc(&w.logl, sizeof(double) * (size_t)ld));
   CUDA_OK(h, cudaMalloc(&w.logp, sizeof(double) * (size_t)ld));
   CUDA_OK(h, cudaMalloc(&w.terms, sizeof(double) * (size_t)ld * 8));
@@ -541,6 +544,9 @@ static EvalArgs make_args(epi_handle *h, Workspace &w, const DevModel &M, const 
   a.ns_total = NS;
   a.window_only = h->window_only ? 1 : 0;
   a.pass1_chunk = h->pass1_chunk ? 1 : 0;
+  a.need_r = w.need_r + first;
+  a.force_need_r = h->force_need_r ? 1 : 0;
+  a.n_launches = &h->launches;
   a.stream = stream;
   a.ev = nullptr;
   return a;
@@ -566,12 +572,10 @@ int epi_launch_eval_ws(epi_handle *h, Workspace &w, const DevModel &M, const dou
     if (e == cudaSuccess) e = launch_eval(a1);
     cudaEventRecord(h->ev_join, h->stream2);
     cudaStreamWaitEvent(stream, h->ev_join, 0);
-    h->launches += 2 * eval_launch_count(M, h->pass1_chunk);
   } else {
     EvalArgs a = make_args(h, w, M, d_theta, ld, n, 0, model_space, d_logl, d_logp, d_status, d_terms, d_series, stream, ns_total);
     a.ev = h->timing ? h->ev : nullptr;
     e = launch_eval(a);
-    h->launches += eval_launch_count(M, h->pass1_chunk);
   }
   if (e != cudaSuccess) return epi_fail(h, EPI_ERR_CUDA, "kernel launch: %s", cudaGetErrorString(e));
   return EPI_OK;

@@ -22,6 +22,7 @@ struct Workspace {
   double *W = nullptr;                        // latency profiles, [chain][NK][EPI_MAX_TAPS]
   int2 *pmeta = nullptr;                      // (dmin, n) per profile
   int *offset = nullptr, *pad = nullptr, *status = nullptr;
+  int *need_r = nullptr;  // chains whose ODE passes must be redone with the removed compartment integrated
   double *logl = nullptr, *logp = nullptr, *terms = nullptr, *series = nullptr;
 };
 
@@ -44,6 +45,7 @@ struct epi_handle {
   cudaStream_t stream = nullptr, stream2 = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_stagger = nullptr;
   int split_mode = 1;
+  bool force_need_r = false;  // EPI_FORCE_R_FALLBACK=1: every chain takes the R-tracking instance (bit-identical results)
   bool pass1_chunk = true;  // EPI_PASS1_CHUNK=0: whole-period pass 1 in one round (bit-identical results)
   bool window_only = true;  // EPI_WINDOW_ONLY=0: pass 2 and the score sweep cover the whole period (bit-identical results)
   bool restart = true;  // pass 2 resumes from the pass-1 checkpoint (EPI_PASS2_RESTART=0: re-integrate everything)

@@ -171,13 +171,41 @@ __device__ __forceinline__ unsigned oob_group4(double S, double a, double b, dou
   return (nhi_m1 - mx) | (unsigned)__double2hiint(S);
 }
 
-template <int FL, bool GUARDED>
+// The removed compartment R is not integrated on the hot path.  R only ever enters the reference through
+// the bounds guard (R < 0 || R > N, model-agen.cpp:109-124): it never feeds back into S, E, I.
+//   * R >= 0 always: R starts at 0 and every stage derivative the guard lets through is gamma * (I >= 0), so
+//     fma(c, k, R) >= R by monotone rounding.
+//   * R <= N whenever S >= 1 at that stage input and the other states pass the guard: the stage inputs conserve
+//     the population, S + E(1,2) + I + R = N up to the accumulated rounding (< 1e-5 persons after 10^3 steps of
+//     <= 5 half-ulp(N) errors each), so R <= N - 1 + 1e-5.
+// The fast path therefore tests "S < 1" instead of "S < 0" (same cost class: integer ops on the high word) and
+// sends such steps to the exact path; the exact path, which cannot evaluate the R test without R, raises
+// `need_r` when a stage input has 0 <= S < 1 with the guard otherwise silent — the chain is then recomputed
+// from scratch by the R-tracking instance of the kernel (launched right behind, exits at once otherwise).
+// In other words: results are bit-identical to integrating R, and R is integrated whenever it could matter.
+// bit 31 of the result set <=> S < 1.0 (incl. negative, -0.0, NaN)
+__device__ __forceinline__ unsigned below_one(double S) {
+  const unsigned v = (unsigned)__double2hiint(S) - 0x3ff00000u;  // S in [1, +inf) <=> v in [0, 0x40000000]
+  return v | (0x40000000u - v);
+}
+__device__ __forceinline__ unsigned oob_group4_nor(double S, double a, double b, double c, unsigned nhi_m1) {
+  const unsigned mx = max(max((unsigned)__double2hiint(a), (unsigned)__double2hiint(b)), (unsigned)__double2hiint(c));
+  return (nhi_m1 - mx) | below_one(S);
+}
+__device__ __forceinline__ unsigned oob_group3_nor(double S, double a, double b, unsigned nhi_m1) {
+  const unsigned mx = max((unsigned)__double2hiint(a), (unsigned)__double2hiint(b));
+  return (nhi_m1 - mx) | below_one(S);
+}
+
+// TRACKR = false: y[4], y[9] (age) / y[3] (simple) are not integrated (see below_one); `flag` bit 0 of the
+// GUARDED instance reports a stage where the missing R test could have mattered.
+template <int FL, bool GUARDED, bool TRACKR>
 __device__ __forceinline__ void rhs(const DevModel &M, const Seg &sg, double t, const double *y, double *dy,
                                     double inv0, double inv1, unsigned nb0, unsigned nb1, unsigned &flag) {
   const double dt = t - sg.tk;
   if constexpr (Traits<FL>::kAge) {
-    const double Sy = y[0], E1y = y[1], E2y = y[2], Iy = y[3], Ry = y[4];
-    const double So = y[5], E1o = y[6], E2o = y[7], Io = y[8], Ro = y[9];
+    const double Sy = y[0], E1y = y[1], E2y = y[2], Iy = y[3], Ry = TRACKR ? y[4] : 0.0;
+    const double So = y[5], E1o = y[6], E2o = y[7], Io = y[8], Ro = TRACKR ? y[9] : 0.0;
     if constexpr (GUARDED) {
       const double Ny = M.Ny, No = M.No;
       // bounds guard, model-agen.cpp:109-124: freeze the state
@@ -188,22 +216,34 @@ __device__ __forceinline__ void rhs(const DevModel &M, const Seg &sg, double t, 
         for (int i = 0; i < 10; ++i) dy[i] = 0.0;
         return;
       }
-    } else {
+      if constexpr (!TRACKR) flag |= (Sy < 1.0 || So < 1.0) ? 1u : 0u;  // the R test is undecidable here
+    } else if constexpr (TRACKR) {
       flag |= oob_group5(Sy, E1y, E2y, Iy, Ry, nb0) | oob_group5(So, E1o, E2o, Io, Ro, nb1);
+    } else {
+      flag |= oob_group4_nor(Sy, E1y, E2y, Iy, nb0) | oob_group4_nor(So, E1o, E2o, Io, nb1);
     }
+    // Every multiply-add below is an EXPLICIT fma and every other operation an explicit rounding intrinsic, so
+    // that all instances of this function (fast / exact guard, with / without R) round identically: left to the
+    // compiler, the contraction of a * b - c differed between instances and the R-tracking fallback was not
+    // bit-identical to the hot path.  (a2 = 1/Tinc2 = 1, model-age-groups2q.R:10,14.)
     const double betay = fma(dt, sg.s0, sg.b0);
     const double betao = fma(dt, sg.s1, sg.b1);
     const double betayo = fma(dt, sg.s2, sg.b2);
-    const double fy = Iy * inv0;  // Iy / Ny
-    const double fo = Io * inv1;  // Io / No
-    const double yinf = betay * fy * Sy;
-    const double oinf = fma(betao, fo, betayo * fy) * So;
-    const double yl2 = M.a1 * E1y, yr = M.gamma * Iy;  // a2 = 1/Tinc2 = 1 (model-age-groups2q.R:10,14)
-    const double ol2 = M.a1 * E1o, orr = M.gamma * Io;
-    dy[0] = -yinf; dy[1] = yinf - yl2; dy[2] = yl2 - E2y; dy[3] = E2y - yr; dy[4] = yr;
-    dy[5] = -oinf; dy[6] = oinf - ol2; dy[7] = ol2 - E2o; dy[8] = E2o - orr; dy[9] = orr;
+    const double fy = __dmul_rn(Iy, inv0);  // Iy / Ny
+    const double fo = __dmul_rn(Io, inv1);  // Io / No
+    const double yinf = __dmul_rn(__dmul_rn(betay, fy), Sy);
+    const double oinf = __dmul_rn(fma(betao, fo, __dmul_rn(betayo, fy)), So);
+    dy[0] = -yinf;
+    dy[1] = fma(-M.a1, E1y, yinf);      // got_infected - a1 * E1
+    dy[2] = fma(M.a1, E1y, -E2y);       // a1 * E1 - E2
+    dy[3] = fma(-M.gamma, Iy, E2y);     // E2 - gamma * I
+    dy[5] = -oinf;
+    dy[6] = fma(-M.a1, E1o, oinf);
+    dy[7] = fma(M.a1, E1o, -E2o);
+    dy[8] = fma(-M.gamma, Io, E2o);
+    if constexpr (TRACKR) { dy[4] = __dmul_rn(M.gamma, Iy); dy[9] = __dmul_rn(M.gamma, Io); }
   } else {
-    const double S = y[0], E = y[1], I = y[2], R = y[3];
+    const double S = y[0], E = y[1], I = y[2], R = TRACKR ? y[3] : 0.0;
     const double N = M.N;
     if constexpr (GUARDED) {
       if (S < 0 || E < 0 || I < 0 || R < 0 || S > N || E > N || I > N || R > N) {
@@ -211,54 +251,80 @@ __device__ __forceinline__ void rhs(const DevModel &M, const Seg &sg, double t, 
         for (int i = 0; i < 4; ++i) dy[i] = 0.0;
         return;
       }
-    } else {
+      if constexpr (!TRACKR) flag |= (S < 1.0) ? 1u : 0u;
+    } else if constexpr (TRACKR) {
       flag |= oob_group4(S, E, I, R, nb0);
+    } else {
+      flag |= oob_group3_nor(S, E, I, nb0);
     }
     const double beta = fma(dt, sg.s0, sg.b0);
-    const double rT = (sg.s1 == 0.0) ? sg.b2 : 1.0 / fma(dt, sg.s1, sg.b1);  // b2 caches 1/Tinf on hold segments
+    const double rT = (sg.s1 == 0.0) ? sg.b2 : __ddiv_rn(1.0, fma(dt, sg.s1, sg.b1));  // b2 caches 1/Tinf on hold segments
     double inf;
     if constexpr (FL == EPI_FLAVOUR_NE) {
-      const double Seff = fmax(0.0, inv1 - (N - S));  // inv1 carries Ne = Nef*N
-      inf = beta * I * inv0 * Seff;                  // inv0 = 1/Ne
+      const double Seff = fmax(0.0, __dsub_rn(inv1, __dsub_rn(N, S)));             // inv1 carries Ne = Nef*N
+      inf = __dmul_rn(__dmul_rn(__dmul_rn(beta, I), inv0), Seff);                   // inv0 = 1/Ne
     } else {
-      inf = beta * I * inv0 * S;  // inv0 = 1/N
+      inf = __dmul_rn(__dmul_rn(__dmul_rn(beta, I), inv0), S);  // inv0 = 1/N
     }
-    const double ei = M.a_inc * E, ir = I * rT;
-    dy[0] = -inf; dy[1] = inf - ei; dy[2] = ei - ir; dy[3] = ir;
+    const double ir = __dmul_rn(I, rT);
+    dy[0] = -inf;
+    dy[1] = fma(-M.a_inc, E, inf);  // got_infected - a * E
+    dy[2] = fma(M.a_inc, E, -ir);   // a * E - I / Tinf
+    if constexpr (TRACKR) dy[3] = ir;
   }
 }
 
-template <int FL, bool GUARDED>
+// index i is a removed compartment (not integrated when TRACKR is false)
+template <int FL>
+__device__ __forceinline__ constexpr bool is_r_state(int i) { return Traits<FL>::kAge ? (i == 4 || i == 9) : (i == 3); }
+
+template <int FL, bool GUARDED, bool TRACKR>
 __device__ __forceinline__ bool rk4_try(const DevModel &M, const Seg &sg, const double *y, double *ynew, double pa,
-                                        double pb, double inv0, double inv1, unsigned nb0, unsigned nb1) {
+                                        double pb, double inv0, double inv1, unsigned nb0, unsigned nb1, bool &need_r) {
   constexpr int NEQ = Traits<FL>::NEQ;
   const double hh = pb - pa, hh2 = 0.5 * hh, tm = pa + hh2;
   double k[NEQ], acc[NEQ], yt[NEQ];
   unsigned flag = 0;
-  rhs<FL, GUARDED>(M, sg, pa, y, k, inv0, inv1, nb0, nb1, flag);
+  rhs<FL, GUARDED, TRACKR>(M, sg, pa, y, k, inv0, inv1, nb0, nb1, flag);
 #pragma unroll
-  for (int i = 0; i < NEQ; ++i) { acc[i] = k[i]; yt[i] = fma(hh2, k[i], y[i]); }
-  rhs<FL, GUARDED>(M, sg, tm, yt, k, inv0, inv1, nb0, nb1, flag);
+  for (int i = 0; i < NEQ; ++i) {
+    if (!TRACKR && is_r_state<FL>(i)) continue;
+    acc[i] = k[i]; yt[i] = fma(hh2, k[i], y[i]);
+  }
+  rhs<FL, GUARDED, TRACKR>(M, sg, tm, yt, k, inv0, inv1, nb0, nb1, flag);
 #pragma unroll
-  for (int i = 0; i < NEQ; ++i) { acc[i] = fma(2.0, k[i], acc[i]); yt[i] = fma(hh2, k[i], y[i]); }
-  rhs<FL, GUARDED>(M, sg, tm, yt, k, inv0, inv1, nb0, nb1, flag);
+  for (int i = 0; i < NEQ; ++i) {
+    if (!TRACKR && is_r_state<FL>(i)) continue;
+    acc[i] = fma(2.0, k[i], acc[i]); yt[i] = fma(hh2, k[i], y[i]);
+  }
+  rhs<FL, GUARDED, TRACKR>(M, sg, tm, yt, k, inv0, inv1, nb0, nb1, flag);
 #pragma unroll
-  for (int i = 0; i < NEQ; ++i) { acc[i] = fma(2.0, k[i], acc[i]); yt[i] = fma(hh, k[i], y[i]); }
-  rhs<FL, GUARDED>(M, sg, pb, yt, k, inv0, inv1, nb0, nb1, flag);
+  for (int i = 0; i < NEQ; ++i) {
+    if (!TRACKR && is_r_state<FL>(i)) continue;
+    acc[i] = fma(2.0, k[i], acc[i]); yt[i] = fma(hh, k[i], y[i]);
+  }
+  rhs<FL, GUARDED, TRACKR>(M, sg, pb, yt, k, inv0, inv1, nb0, nb1, flag);
   const double h6 = hh / 6.0;
 #pragma unroll
-  for (int i = 0; i < NEQ; ++i) ynew[i] = fma(h6, acc[i] + k[i], y[i]);
+  for (int i = 0; i < NEQ; ++i) {
+    if (!TRACKR && is_r_state<FL>(i)) { ynew[i] = 0.0; continue; }
+    ynew[i] = fma(h6, __dadd_rn(acc[i], k[i]), y[i]);
+  }
+  if constexpr (GUARDED) {
+    if (!TRACKR && (flag & 1u)) need_r = true;
+    return true;
+  }
   return (int)flag >= 0;  // no stage raised the maybe-out-of-bounds bit
 }
 
-template <int FL>
+template <int FL, bool TRACKR>
 __device__ __forceinline__ void rk4_piece(const DevModel &M, const Seg &sg, double *y, double pa, double pb,
-                                          double inv0, double inv1, unsigned nb0, unsigned nb1) {
+                                          double inv0, double inv1, unsigned nb0, unsigned nb1, bool &need_r) {
   constexpr int NEQ = Traits<FL>::NEQ;
   double yn[NEQ];
-  if (!sg.fast_ok || !rk4_try<FL, false>(M, sg, y, yn, pa, pb, inv0, inv1, nb0, nb1)) {
+  if (!sg.fast_ok || !rk4_try<FL, false, TRACKR>(M, sg, y, yn, pa, pb, inv0, inv1, nb0, nb1, need_r)) {
     // rare: redo the step with the reference's guard evaluated exactly in FP64
-    rk4_try<FL, true>(M, sg, y, yn, pa, pb, inv0, inv1, 0u, 0u);
+    rk4_try<FL, true, TRACKR>(M, sg, y, yn, pa, pb, inv0, inv1, 0u, 0u, need_r);
   }
 #pragma unroll
   for (int i = 0; i < NEQ; ++i) y[i] = yn[i];
@@ -430,15 +496,24 @@ __device__ __noinline__ void write_ext(const DevModel &M, const double *__restri
   }
 }
 
-template <int FL, bool PASS2, bool FULL = false>
+// TRACKR = false (the hot instance): the removed compartment is not integrated (see below_one); a chain where
+// that could have changed a guard decision sets need_r[chain] and is recomputed by the TRACKR = true instance,
+// which is launched right behind and only works on those chains.  FULL (ext trajectories) always tracks R.
+template <int FL, bool PASS2, bool FULL = false, bool TRACKR = false>
 __global__ void __maxnreg__(128)
 k_ode(const DevModel M, const double *__restrict__ theta, int64_t ld, int64_t n,
       const int *__restrict__ offset, const int *__restrict__ padv, const double *__restrict__ hist1,
       double *__restrict__ hist_out, double *__restrict__ ckpt, double *__restrict__ series = nullptr,
-      int ns_total = 0, int window_only = 0, int ndays_limit = 0, const int *__restrict__ retry_status = nullptr) {
+      int ns_total = 0, int window_only = 0, int ndays_limit = 0, const int *__restrict__ retry_status = nullptr,
+      int *__restrict__ need_r_flag = nullptr, int force_need_r = 0) {
   constexpr int NEQ = Traits<FL>::NEQ, NG = Traits<FL>::NG;
+  constexpr bool TR = TRACKR || FULL;  // integrate the removed compartment
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  if constexpr (TRACKR && !FULL) {
+    if (!need_r_flag[i]) return;  // fallback instance: only the chains the hot instance flagged
+  }
+  bool need_r = false;
   const double *th = theta + i;
   const int ndays = PASS2 ? M.P : M.P1;
   const int pitch = hist_pitch(ndays);
@@ -485,7 +560,10 @@ k_ode(const DevModel M, const double *__restrict__ theta, int64_t ld, int64_t n,
       for (int d = 0; d < M.P; ++d)
 #pragma unroll
         for (int g = 0; g < NG; ++g) out[g * pitch + d] = in[g * pitch1 + d % M.P1];
-      if constexpr (!FULL) return;
+      if constexpr (!FULL) {
+        if constexpr (!TR) { if (need_r_flag) need_r_flag[i] = 0; }
+        return;
+      }
       // FULL: the other columns of the recycled matrix are not kept by pass 1: integrate its days
       // again (beta0 forever, bit-identical) and recycle the rows below
       t0 = padv[i] + 1;
@@ -500,7 +578,7 @@ k_ode(const DevModel M, const double *__restrict__ theta, int64_t ld, int64_t n,
   // element (d, q) of this chain: ck[(d * NEQ + q) * kTile]
   double *ck = ckpt ? ckpt + ((i / kTile) * (int64_t)cdays * NEQ) * kTile + (i % kTile) : nullptr;
   int d0 = 0;  // last day already known
-  if constexpr (PASS2) {
+  if constexpr (PASS2 && !TRACKR) {  // (the R-tracking fallback integrates from day 0: the checkpoints hold no R)
     if (ck) {
       double minbp = INFINITY;
       for (int k = 0; k < nbp; ++k) minbp = fmin(minbp, bp[k]);
@@ -513,7 +591,8 @@ k_ode(const DevModel M, const double *__restrict__ theta, int64_t ld, int64_t n,
 #pragma unroll
           for (int g = 0; g < NG; ++g) out[g * pitch + d] = in[g * pitch1 + d];
 #pragma unroll
-        for (int q = 0; q < NEQ; ++q) y[q] = ck[((int64_t)d0 * NEQ + q) * kTile];
+        for (int q = 0; q < NEQ; ++q)
+          if (TR || !is_r_state<FL>(q)) y[q] = ck[((int64_t)d0 * NEQ + q) * kTile];
       }
     }
   }
@@ -529,7 +608,8 @@ k_ode(const DevModel M, const double *__restrict__ theta, int64_t ld, int64_t n,
   if constexpr (!PASS2) {
     if (ck) {
 #pragma unroll
-      for (int q = 0; q < NEQ; ++q) ck[q * kTile] = y[q];
+      for (int q = 0; q < NEQ; ++q)
+        if (TR || !is_r_state<FL>(q)) ck[q * kTile] = y[q];
     }
   }
   for (int d = d0 + 1; d < nint; ++d) {
@@ -541,12 +621,12 @@ k_ode(const DevModel M, const double *__restrict__ theta, int64_t ld, int64_t n,
       if constexpr (PASS2) {
         if (a >= tcut) sg = select_segment<FL>(M, th, ld, bp, nbp, a, &tcut);
         while (tcut < b) {
-          rk4_piece<FL>(M, sg, y, pa, tcut, inv0, inv1, nb0, nb1);
+          rk4_piece<FL, TR>(M, sg, y, pa, tcut, inv0, inv1, nb0, nb1, need_r);
           pa = tcut;
           sg = select_segment<FL>(M, th, ld, bp, nbp, pa, &tcut);
         }
       }
-      rk4_piece<FL>(M, sg, y, pa, b, inv0, inv1, nb0, nb1);
+      rk4_piece<FL, TR>(M, sg, y, pa, b, inv0, inv1, nb0, nb1, need_r);
     }
     out[d] = y[0];
     if constexpr (NG == 2) out[pitch + d] = y[5];
@@ -554,9 +634,13 @@ k_ode(const DevModel M, const double *__restrict__ theta, int64_t ld, int64_t n,
     if constexpr (!PASS2) {
       if (ck && d < cdays) {
 #pragma unroll
-        for (int q = 0; q < NEQ; ++q) ck[((int64_t)d * NEQ + q) * kTile] = y[q];
+        for (int q = 0; q < NEQ; ++q)
+          if (TR || !is_r_state<FL>(q)) ck[((int64_t)d * NEQ + q) * kTile] = y[q];
       }
     }
+  }
+  if constexpr (!TR) {
+    if (need_r_flag) need_r_flag[i] = (need_r || force_need_r) ? 1 : 0;
   }
   if constexpr (FULL) {
     // invalid data_offset with a pass 1 shorter than the period: R recycles the short matrix (:216-227)
@@ -589,27 +673,26 @@ __device__ __forceinline__ void rhs_age2(double a1, double gamma, const Seg2 &sg
                          I > Ngrp || R > Ngrp);
     const int bad = bad_own | __shfl_xor_sync(pairmask, bad_own, 1);
     // (the shuffle below must still be executed by both lanes)
-    const double f_own = I * invN;
+    const double f_own = __dmul_rn(I, invN);
     const double fy = __shfl_sync(pairmask, f_own, even_lane);
     if (bad) {
 #pragma unroll
       for (int i = 0; i < 5; ++i) dy[i] = 0.0;
       return;
     }
+    // the same explicitly rounded operations as rhs<>: both ODE kernels produce the same bits
     const double dt = t - sg.tk;
     const double bA = fma(dt, sg.sA, sg.bA), bB = fma(dt, sg.sB, sg.bB);
-    const double inf = fma(bA, f_own, bB * fy) * S;
-    const double l2 = a1 * E1, rm = gamma * I;
-    dy[0] = -inf; dy[1] = inf - l2; dy[2] = l2 - E2; dy[3] = E2 - rm; dy[4] = rm;
+    const double inf = __dmul_rn(fma(bA, f_own, __dmul_rn(bB, fy)), S);
+    dy[0] = -inf; dy[1] = fma(-a1, E1, inf); dy[2] = fma(a1, E1, -E2); dy[3] = fma(-gamma, I, E2); dy[4] = __dmul_rn(gamma, I);
   } else {
     flag |= oob_group5(S, E1, E2, I, R, nb);
-    const double f_own = I * invN;
+    const double f_own = __dmul_rn(I, invN);
     const double fy = __shfl_sync(pairmask, f_own, even_lane);
     const double dt = t - sg.tk;
     const double bA = fma(dt, sg.sA, sg.bA), bB = fma(dt, sg.sB, sg.bB);
-    const double inf = fma(bA, f_own, bB * fy) * S;  // y: (betay*fy)*Sy; o: (betao*fo + betayo*fy)*So
-    const double l2 = a1 * E1, rm = gamma * I;       // a2 = 1
-    dy[0] = -inf; dy[1] = inf - l2; dy[2] = l2 - E2; dy[3] = E2 - rm; dy[4] = rm;
+    const double inf = __dmul_rn(fma(bA, f_own, __dmul_rn(bB, fy)), S);  // y: (betay*fy)*Sy; o: (betao*fo + betayo*fy)*So
+    dy[0] = -inf; dy[1] = fma(-a1, E1, inf); dy[2] = fma(a1, E1, -E2); dy[3] = fma(-gamma, I, E2); dy[4] = __dmul_rn(gamma, I);
   }
 }
 
@@ -632,7 +715,7 @@ __device__ __forceinline__ bool rk4_try_age2(double a1, double gamma, const Seg2
   rhs_age2<GUARDED>(a1, gamma, sg, pb, yt, k, invN, Ngrp, nb, pairmask, even_lane, flag);
   const double h6 = hh / 6.0;
 #pragma unroll
-  for (int i = 0; i < 5; ++i) ynew[i] = fma(h6, acc[i] + k[i], y[i]);
+  for (int i = 0; i < 5; ++i) ynew[i] = fma(h6, __dadd_rn(acc[i], k[i]), y[i]);
   if constexpr (GUARDED) return true;
   const int own_bad = (int)flag < 0;
   return !(own_bad | __shfl_xor_sync(pairmask, own_bad, 1));
@@ -1722,16 +1805,27 @@ static cudaError_t launch_eval_fl(const EvalArgs &a) {
   // the threshold is normally crossed there and everything behind the crossing is never read.  Chains that
   // did not cross are redone over the whole pass-1 period by a retry round (k_mid flags them).
   const int chunk = (a.pass1_chunk && M.P1 > kPass1Chunk + kPass1Chunk / 4) ? kPass1Chunk : 0;
-  if (use_pair) {
-    if constexpr (Traits<FL>::kAge) k_ode_age2<FL, false><<<pair_blocks, 64, 0, s>>>(M, a.theta, a.ld, n, nullptr, nullptr, nullptr, a.hist1, a.ckpt, 0, chunk);
-  } else k_ode<FL, false><<<ode_blocks, 32, 0, s>>>(M, a.theta, a.ld, n, nullptr, nullptr, nullptr, a.hist1, a.ckpt, nullptr, 0, 0, chunk);
+  int nl = 0;  // kernels enqueued
+  // thread-per-chain pass 1: the hot instance (R not integrated) and, right behind it, the R-tracking instance for
+  // the chains the hot one flagged (exits at once otherwise)
+  auto pass1 = [&](int limit, const int *retry) {
+    if (use_pair) {
+      if constexpr (Traits<FL>::kAge) k_ode_age2<FL, false><<<pair_blocks, 64, 0, s>>>(M, a.theta, a.ld, n, nullptr, nullptr, nullptr, a.hist1, a.ckpt, 0, limit, retry);
+      nl += 1;
+    } else {
+      k_ode<FL, false><<<ode_blocks, 32, 0, s>>>(M, a.theta, a.ld, n, nullptr, nullptr, nullptr, a.hist1, a.ckpt, nullptr, 0, 0, limit, retry, a.need_r, a.force_need_r);
+      k_ode<FL, false, false, true><<<ode_blocks, 32, 0, s>>>(M, a.theta, a.ld, n, nullptr, nullptr, nullptr, a.hist1, a.ckpt, nullptr, 0, 0, 0, nullptr, a.need_r, 0);
+      nl += 2;
+    }
+  };
+  pass1(chunk, nullptr);
   if (a.ev) cudaEventRecord(a.ev[1], s);
   k_mid<FL><<<warp_blocks, 128, smem_mid, s>>>(M, a.theta, a.ld, n, a.hist1, a.offset, a.pad, a.status, a.W, a.pmeta, a.model_space, chunk, 0);
+  nl += 1;
   if (chunk) {
-    if (use_pair) {
-      if constexpr (Traits<FL>::kAge) k_ode_age2<FL, false><<<pair_blocks, 64, 0, s>>>(M, a.theta, a.ld, n, nullptr, nullptr, nullptr, a.hist1, a.ckpt, 0, 0, a.status);
-    } else k_ode<FL, false><<<ode_blocks, 32, 0, s>>>(M, a.theta, a.ld, n, nullptr, nullptr, nullptr, a.hist1, a.ckpt, nullptr, 0, 0, 0, a.status);
+    pass1(0, a.status);
     k_mid<FL><<<warp_blocks, 128, smem_mid, s>>>(M, a.theta, a.ld, n, a.hist1, a.offset, a.pad, a.status, a.W, a.pmeta, a.model_space, 0, 1);
+    nl += 1;
   }
   if (a.ev) cudaEventRecord(a.ev[2], s);
   if (a.ev_after_mid) cudaEventRecord(a.ev_after_mid, s);
@@ -1739,11 +1833,17 @@ static cudaError_t launch_eval_fl(const EvalArgs &a) {
   const int window_only = (a.series_out || !a.window_only) ? 0 : 1;  // scoring reads S(t) only up to the last data-window day
   if (use_pair && !want_ext) {
     if constexpr (Traits<FL>::kAge) k_ode_age2<FL, true><<<pair_blocks, 64, 0, s>>>(M, a.theta, a.ld, n, a.offset, a.pad, a.hist1, a.hist2, a.ckpt, window_only);
+    nl += 1;
   } else if (want_ext) {
     // trajectories with the ext series: pass 2 also writes E, I, R and the Re/Rt diagnostics (no restart)
     k_ode<FL, true, true><<<ode_blocks, 32, 0, s>>>(M, a.theta, a.ld, n, a.offset, a.pad, a.hist1, a.hist2, nullptr,
                                                     a.series_out, a.ns_total);
-  } else k_ode<FL, true><<<ode_blocks, 32, 0, s>>>(M, a.theta, a.ld, n, a.offset, a.pad, a.hist1, a.hist2, a.ckpt, nullptr, 0, window_only);
+    nl += 1;
+  } else {
+    k_ode<FL, true><<<ode_blocks, 32, 0, s>>>(M, a.theta, a.ld, n, a.offset, a.pad, a.hist1, a.hist2, a.ckpt, nullptr, 0, window_only, 0, nullptr, a.need_r, a.force_need_r);
+    k_ode<FL, true, false, true><<<ode_blocks, 32, 0, s>>>(M, a.theta, a.ld, n, a.offset, a.pad, a.hist1, a.hist2, a.ckpt, nullptr, 0, window_only, 0, nullptr, a.need_r, 0);
+    nl += 2;
+  }
   if (a.ev) cudaEventRecord(a.ev[3], s);
   if (a.series_out) {
     k_series<FL><<<warp_blocks, 128, smem_score, s>>>(M, a.theta, a.ld, n, a.hist2, a.offset, a.pad, a.W, a.pmeta,
@@ -1752,12 +1852,10 @@ static cudaError_t launch_eval_fl(const EvalArgs &a) {
     k_score<FL><<<warp_blocks, 128, smem_score, s>>>(M, a.PT, a.n_prior, a.theta, a.ld, n, a.hist2, a.offset, a.pad, a.W, a.pmeta,
                                                      a.status, a.logl, a.logp, a.terms, window_only);
   }
+  nl += 1;
+  if (a.n_launches) *a.n_launches += nl;
   if (a.ev) cudaEventRecord(a.ev[4], s);
   return cudaGetLastError();
-}
-
-int eval_launch_count(const DevModel &M, int pass1_chunk) {
-  return (pass1_chunk && M.P1 > kPass1Chunk + kPass1Chunk / 4) ? 6 : 4;
 }
 
 cudaError_t launch_eval(const EvalArgs &a) {

@@ -21,6 +21,9 @@ struct EvalArgs {
   double *logl, *logp, *terms;  // device, any may be null
   double *series_out;           // non-null: write calculateModel series instead of scoring
   int ns_total = 0;             // series per chain in series_out: 8/3 basic, 18/8 with the ext series
+  int *need_r = nullptr;        // per chain: the hot ODE instance could not decide the R part of the bounds guard
+  int force_need_r = 0;         // EPI_FORCE_R_FALLBACK=1 (tests): flag every chain
+  int64_t *n_launches = nullptr;  // incremented by the number of kernels enqueued
   int pass1_chunk = 1;          // whole-period pass 1 in two rounds (EPI_PASS1_CHUNK=0: one round over all days)
   int window_only = 1;          // scoring path: integrate / sweep only up to the data windows (EPI_WINDOW_ONLY=0: whole period)
   cudaStream_t stream;
@@ -29,7 +32,6 @@ struct EvalArgs {
 };
 
 cudaError_t launch_eval(const EvalArgs &a);
-int eval_launch_count(const DevModel &M, int pass1_chunk);  // kernels one launch_eval enqueues
 cudaError_t launch_aos_to_soa(const double *aos, double *soa, int64_t n, int d, int64_t ld, cudaStream_t s);
 cudaError_t launch_quantiles(const double *series, const int *offset, const int *pad, int64_t n, int NS, int simperiod,
                              int period, int startoffset, int sa, int sb, double prefill_a, double prefill_b,

@@ -455,3 +455,45 @@ def test_two_round_pass1_is_bit_identical(name, m, period, monkeypatch, oracle):
     assert np.array_equal(ta, tb, equal_nan=True)
     A.close()
     B.close()
+
+
+@pytest.mark.parametrize("name,m", [("A300", 4), ("I290", 2), ("S365", 2), ("NE120", 4), ("DE", 1)])
+def test_removed_compartment_fallback_is_bit_identical(name, m, monkeypatch):
+    """The hot ODE kernels do not integrate the removed compartment R (it only enters the reference through the
+    bounds guard, which cannot fire on R while S >= 1 at every stage input); chains where that is not certain
+    are recomputed by the R-tracking instance.  Forcing EVERY chain through that instance
+    (EPI_FORCE_R_FALLBACK=1) must not change a bit of logl, the terms, offsets, statuses or trajectories."""
+    from epi_mcmc_b200.model import Model, load_dataset
+    theta = np.array(load_golden(name)["theta"])
+    ds = load_dataset(name)
+    monkeypatch.setenv("EPI_FORCE_R_FALLBACK", "0")
+    A = Model(ds, substeps=m)
+    monkeypatch.setenv("EPI_FORCE_R_FALLBACK", "1")
+    B = Model(ds, substeps=m)
+    la, pa, sa = A.calclogpost_batch(theta)
+    lb, pb, sb = B.calclogpost_batch(theta)
+    assert np.array_equal(la, lb, equal_nan=True) and np.array_equal(pa, pb) and np.array_equal(sa, sb)
+    oa, qa, ta = A.eval_detail(theta)
+    ob, qb, tb = B.eval_detail(theta)
+    assert np.array_equal(oa, ob) and np.array_equal(qa, qb) and np.array_equal(ta, tb, equal_nan=True)
+    xa, _, _ = A.calculateModel_batch(A.transformParams(theta[:32]), ds["period"] + 25)
+    xb, _, _ = B.calculateModel_batch(B.transformParams(theta[:32]), ds["period"] + 25)
+    assert np.array_equal(xa, xb, equal_nan=True)
+    assert B.launch_count() > 0
+    A.close()
+    B.close()
+
+
+@pytest.mark.parametrize("name", ["A300", "I290"])
+def test_both_ode_kernels_produce_the_same_bits(name):
+    """Small batches of the age flavours use two lanes per chain (k_ode_age2, always integrates R), large ones a
+    thread per chain (k_ode, R-free hot path): the same theta must give the same bits through either."""
+    M = _model(name, 4)
+    theta = np.array(load_golden(name)["theta"])
+    small = M.calclogpost_batch(theta)
+    reps = 45000 // len(theta) + 1          # > 256 chains per SM: thread-per-chain launch
+    big = M.calclogpost_batch(np.tile(theta, (reps, 1)))
+    for a, b in zip(small, big):
+        assert np.array_equal(a, b[:len(theta)], equal_nan=True)
+        assert np.array_equal(a, b[-len(theta):], equal_nan=True)
+    M.close()
