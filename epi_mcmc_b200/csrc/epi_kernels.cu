@@ -229,10 +229,9 @@ __device__ __forceinline__ void rhs(const DevModel &M, const Seg &sg, double t, 
     const double betay = fma(dt, sg.s0, sg.b0);
     const double betao = fma(dt, sg.s1, sg.b1);
     const double betayo = fma(dt, sg.s2, sg.b2);
-    const double fy = __dmul_rn(Iy, inv0);  // Iy / Ny
-    const double fo = __dmul_rn(Io, inv1);  // Io / No
-    const double yinf = __dmul_rn(__dmul_rn(betay, fy), Sy);
-    const double oinf = __dmul_rn(fma(betao, fo, __dmul_rn(betayo, fy)), So);
+    // (betay, betao, betayo are beta_y / N_y, beta_o / N_o, beta_yo / N_y here, see select_segment)
+    const double yinf = __dmul_rn(__dmul_rn(betay, Iy), Sy);
+    const double oinf = __dmul_rn(fma(betao, Io, __dmul_rn(betayo, Iy)), So);
     dy[0] = -yinf;
     dy[1] = fma(-M.a1, E1y, yinf);      // got_infected - a1 * E1
     dy[2] = fma(M.a1, E1y, -E2y);       // a1 * E1 - E2
@@ -262,9 +261,9 @@ __device__ __forceinline__ void rhs(const DevModel &M, const Seg &sg, double t, 
     double inf;
     if constexpr (FL == EPI_FLAVOUR_NE) {
       const double Seff = fmax(0.0, __dsub_rn(inv1, __dsub_rn(N, S)));             // inv1 carries Ne = Nef*N
-      inf = __dmul_rn(__dmul_rn(__dmul_rn(beta, I), inv0), Seff);                   // inv0 = 1/Ne
+      inf = __dmul_rn(__dmul_rn(beta, I), Seff);  // beta is beta / Ne here, see select_segment
     } else {
-      inf = __dmul_rn(__dmul_rn(__dmul_rn(beta, I), inv0), S);  // inv0 = 1/N
+      inf = __dmul_rn(__dmul_rn(beta, I), S);     // beta is beta / N here
     }
     const double ir = __dmul_rn(I, rT);
     dy[0] = -inf;
@@ -372,8 +371,11 @@ __device__ __forceinline__ int breakpoints(const DevModel &M, const double *__re
 // highest k with t_k <= pa (== the highest k with tm > t_k for a piece without
 // interior breakpoints), and the next cut.
 template <int FL>
+// The curves are stored already divided by the population they multiply (beta_y / N_y, beta_o / N_o,
+// beta_yo / N_y; simple: beta / N or beta / Ne), so that the RHS needs no I / N products.
 __device__ __noinline__ Seg select_segment(const DevModel &M, const double *__restrict__ th, int64_t ld,
-                                           const double *bp, int nbp, double pa, double *tcut) {
+                                           const double *bp, int nbp, double pa, double *tcut, double inv0,
+                                           double inv1) {
   int k = -1;
   double tc = INFINITY;
   for (int i = 0; i < nbp; ++i) {
@@ -398,6 +400,9 @@ __device__ __noinline__ Seg select_segment(const DevModel &M, const double *__re
     } else {
       sg.fast_ok = by >= 0 && bo >= 0 && byo >= 0;
     }
+    sg.b0 = __dmul_rn(sg.b0, inv0); sg.s0 = __dmul_rn(sg.s0, inv0);
+    sg.b1 = __dmul_rn(sg.b1, inv1); sg.s1 = __dmul_rn(sg.s1, inv1);
+    sg.b2 = __dmul_rn(sg.b2, inv0); sg.s2 = __dmul_rn(sg.s2, inv0);
   } else {
     auto T = [&](int i) { return th[(int64_t)i * ld]; };
     const double Tinf0 = T(2), Tinft = T(3);
@@ -412,6 +417,7 @@ __device__ __noinline__ Seg select_segment(const DevModel &M, const double *__re
       if (sg.s1 == 0.0) sg.b2 = 1.0 / Tinf0;
     }
     sg.fast_ok = beta0 >= 0 && betat >= 0 && bp[1] > bp[0];
+    sg.b0 = __dmul_rn(sg.b0, inv0); sg.s0 = __dmul_rn(sg.s0, inv0);  // beta / N (Ne flavour: beta / Ne)
   }
   return sg;
 }
@@ -596,7 +602,7 @@ k_ode(const DevModel M, const double *__restrict__ theta, int64_t ld, int64_t n,
       }
     }
   }
-  Seg sg = select_segment<FL>(M, th, ld, bp, nbp, (double)(t0 + d0), &tcut);
+  Seg sg = select_segment<FL>(M, th, ld, bp, nbp, (double)(t0 + d0), &tcut, inv0, inv1);
 
   const int m = M.m;
   const double h = 1.0 / (double)m;
@@ -619,11 +625,11 @@ k_ode(const DevModel M, const double *__restrict__ theta, int64_t ld, int64_t n,
       const double b = (s == m - 1) ? tday + 1.0 : tday + (double)(s + 1) * h;
       double pa = a;
       if constexpr (PASS2) {
-        if (a >= tcut) sg = select_segment<FL>(M, th, ld, bp, nbp, a, &tcut);
+        if (a >= tcut) sg = select_segment<FL>(M, th, ld, bp, nbp, a, &tcut, inv0, inv1);
         while (tcut < b) {
           rk4_piece<FL, TR>(M, sg, y, pa, tcut, inv0, inv1, nb0, nb1, need_r);
           pa = tcut;
-          sg = select_segment<FL>(M, th, ld, bp, nbp, pa, &tcut);
+          sg = select_segment<FL>(M, th, ld, bp, nbp, pa, &tcut, inv0, inv1);
         }
       }
       rk4_piece<FL, TR>(M, sg, y, pa, b, inv0, inv1, nb0, nb1, need_r);
@@ -673,8 +679,7 @@ __device__ __forceinline__ void rhs_age2(double a1, double gamma, const Seg2 &sg
                          I > Ngrp || R > Ngrp);
     const int bad = bad_own | __shfl_xor_sync(pairmask, bad_own, 1);
     // (the shuffle below must still be executed by both lanes)
-    const double f_own = __dmul_rn(I, invN);
-    const double fy = __shfl_sync(pairmask, f_own, even_lane);
+    const double fy = __shfl_sync(pairmask, I, even_lane);  // I of the younger group
     if (bad) {
 #pragma unroll
       for (int i = 0; i < 5; ++i) dy[i] = 0.0;
@@ -683,15 +688,14 @@ __device__ __forceinline__ void rhs_age2(double a1, double gamma, const Seg2 &sg
     // the same explicitly rounded operations as rhs<>: both ODE kernels produce the same bits
     const double dt = t - sg.tk;
     const double bA = fma(dt, sg.sA, sg.bA), bB = fma(dt, sg.sB, sg.bB);
-    const double inf = __dmul_rn(fma(bA, f_own, __dmul_rn(bB, fy)), S);
+    const double inf = __dmul_rn(fma(bA, I, __dmul_rn(bB, fy)), S);
     dy[0] = -inf; dy[1] = fma(-a1, E1, inf); dy[2] = fma(a1, E1, -E2); dy[3] = fma(-gamma, I, E2); dy[4] = __dmul_rn(gamma, I);
   } else {
     flag |= oob_group5(S, E1, E2, I, R, nb);
-    const double f_own = __dmul_rn(I, invN);
-    const double fy = __shfl_sync(pairmask, f_own, even_lane);
+    const double fy = __shfl_sync(pairmask, I, even_lane);  // I of the younger group
     const double dt = t - sg.tk;
     const double bA = fma(dt, sg.sA, sg.bA), bB = fma(dt, sg.sB, sg.bB);
-    const double inf = __dmul_rn(fma(bA, f_own, __dmul_rn(bB, fy)), S);  // y: (betay*fy)*Sy; o: (betao*fo + betayo*fy)*So
+    const double inf = __dmul_rn(fma(bA, I, __dmul_rn(bB, fy)), S);  // y: (betay/Ny*Iy)*Sy; o: (betao/No*Io + betayo/Ny*Iy)*So
     dy[0] = -inf; dy[1] = fma(-a1, E1, inf); dy[2] = fma(a1, E1, -E2); dy[3] = fma(-gamma, I, E2); dy[4] = __dmul_rn(gamma, I);
   }
 }
@@ -735,7 +739,7 @@ __device__ __forceinline__ void rk4_piece_age2(double a1, double gamma, const Se
 
 template <int FL>
 __device__ __noinline__ Seg2 select_segment_age2(const double *__restrict__ th, int64_t ld, const double *bp, int nbp,
-                                                 double pa, int is_o, double *tcut) {
+                                                 double pa, int is_o, double *tcut, double invy, double invo) {
   int k = -1;
   double tc = INFINITY;
   for (int i = 0; i < nbp; ++i) {
@@ -760,6 +764,10 @@ __device__ __noinline__ Seg2 select_segment_age2(const double *__restrict__ th, 
   } else {
     sg.fast_ok = by >= 0 && bo >= 0 && byo >= 0;
   }
+  // the same normalisation (and the same roundings) as select_segment
+  const double invA = is_o ? invo : invy;
+  sg.bA = __dmul_rn(sg.bA, invA); sg.sA = __dmul_rn(sg.sA, invA);
+  sg.bB = __dmul_rn(sg.bB, invy); sg.sB = __dmul_rn(sg.sB, invy);
   return sg;
 }
 
@@ -823,7 +831,7 @@ k_ode_age2(const DevModel M, const double *__restrict__ theta, int64_t ld, int64
       }
     }
   }
-  Seg2 sg = select_segment_age2<FL>(th, ld, bp, nbp, (double)(t0 + d0), g, &tcut);
+  Seg2 sg = select_segment_age2<FL>(th, ld, bp, nbp, (double)(t0 + d0), g, &tcut, 1.0 / M.Ny, 1.0 / M.No);
 
   const int m = M.m;
   const double h = 1.0 / (double)m, a1 = M.a1, gamma = M.gamma;
@@ -841,11 +849,11 @@ k_ode_age2(const DevModel M, const double *__restrict__ theta, int64_t ld, int64
       const double b = (s == m - 1) ? tday + 1.0 : tday + (double)(s + 1) * h;
       double pa = a;
       if constexpr (PASS2) {
-        if (a >= tcut) sg = select_segment_age2<FL>(th, ld, bp, nbp, a, g, &tcut);
+        if (a >= tcut) sg = select_segment_age2<FL>(th, ld, bp, nbp, a, g, &tcut, 1.0 / M.Ny, 1.0 / M.No);
         while (tcut < b) {
           rk4_piece_age2(a1, gamma, sg, y, pa, tcut, invN, Ngrp, nb, pairmask, even_lane);
           pa = tcut;
-          sg = select_segment_age2<FL>(th, ld, bp, nbp, pa, g, &tcut);
+          sg = select_segment_age2<FL>(th, ld, bp, nbp, pa, g, &tcut, 1.0 / M.Ny, 1.0 / M.No);
         }
       }
       rk4_piece_age2(a1, gamma, sg, y, pa, b, invN, Ngrp, nb, pairmask, even_lane);
