@@ -143,6 +143,7 @@ __device__ __forceinline__ bool age_linear(int k) { return ((Traits<FL>::k2i ? 0
 struct Seg {
   double tk, b0, b1, b2, s0, s1, s2;  // age: betay/betao/betayo; simple: beta, Tinf, 1/Tinf cache
   bool fast_ok;                       // beta(t) >= 0 on the whole segment (premise of the fast guard)
+  bool hold;                          // every slope is 0: the curves are constants (fma(dt, 0, b) == b exactly)
 };
 
 // y > N or y < 0 or NaN  =>  bit 63 of (bits(N) - bits(y)) | bits(y) is set (conservative: it is
@@ -199,10 +200,12 @@ __device__ __forceinline__ unsigned oob_group3_nor(double S, double a, double b,
 
 // TRACKR = false: y[4], y[9] (age) / y[3] (simple) are not integrated (see below_one); `flag` bit 0 of the
 // GUARDED instance reports a stage where the missing R test could have mattered.
-template <int FL, bool GUARDED, bool TRACKR>
+// HOLD = true: the segment's curves are constants (pass 1 and the step segments of the schedule, i.e. most of the
+// integration): no t - tk and no fma per curve and stage; same bits, since fma(dt, 0, b) == b.
+template <int FL, bool GUARDED, bool TRACKR, bool HOLD = false>
 __device__ __forceinline__ void rhs(const DevModel &M, const Seg &sg, double t, const double *y, double *dy,
                                     double inv0, double inv1, unsigned nb0, unsigned nb1, unsigned &flag) {
-  const double dt = t - sg.tk;
+  const double dt = HOLD ? 0.0 : t - sg.tk;
   if constexpr (Traits<FL>::kAge) {
     const double Sy = y[0], E1y = y[1], E2y = y[2], Iy = y[3], Ry = TRACKR ? y[4] : 0.0;
     const double So = y[5], E1o = y[6], E2o = y[7], Io = y[8], Ro = TRACKR ? y[9] : 0.0;
@@ -226,9 +229,9 @@ __device__ __forceinline__ void rhs(const DevModel &M, const Seg &sg, double t, 
     // that all instances of this function (fast / exact guard, with / without R) round identically: left to the
     // compiler, the contraction of a * b - c differed between instances and the R-tracking fallback was not
     // bit-identical to the hot path.  (a2 = 1/Tinc2 = 1, model-age-groups2q.R:10,14.)
-    const double betay = fma(dt, sg.s0, sg.b0);
-    const double betao = fma(dt, sg.s1, sg.b1);
-    const double betayo = fma(dt, sg.s2, sg.b2);
+    const double betay = HOLD ? sg.b0 : fma(dt, sg.s0, sg.b0);
+    const double betao = HOLD ? sg.b1 : fma(dt, sg.s1, sg.b1);
+    const double betayo = HOLD ? sg.b2 : fma(dt, sg.s2, sg.b2);
     // (betay, betao, betayo are beta_y / N_y, beta_o / N_o, beta_yo / N_y here, see select_segment)
     const double yinf = __dmul_rn(__dmul_rn(betay, Iy), Sy);
     const double oinf = __dmul_rn(fma(betao, Io, __dmul_rn(betayo, Iy)), So);
@@ -256,8 +259,8 @@ __device__ __forceinline__ void rhs(const DevModel &M, const Seg &sg, double t, 
     } else {
       flag |= oob_group3_nor(S, E, I, nb0);
     }
-    const double beta = fma(dt, sg.s0, sg.b0);
-    const double rT = (sg.s1 == 0.0) ? sg.b2 : __ddiv_rn(1.0, fma(dt, sg.s1, sg.b1));  // b2 caches 1/Tinf on hold segments
+    const double beta = HOLD ? sg.b0 : fma(dt, sg.s0, sg.b0);
+    const double rT = (HOLD || sg.s1 == 0.0) ? sg.b2 : __ddiv_rn(1.0, fma(dt, sg.s1, sg.b1));  // b2 caches 1/Tinf on hold segments
     double inf;
     if constexpr (FL == EPI_FLAVOUR_NE) {
       const double Seff = fmax(0.0, __dsub_rn(inv1, __dsub_rn(N, S)));             // inv1 carries Ne = Nef*N
@@ -277,32 +280,32 @@ __device__ __forceinline__ void rhs(const DevModel &M, const Seg &sg, double t, 
 template <int FL>
 __device__ __forceinline__ constexpr bool is_r_state(int i) { return Traits<FL>::kAge ? (i == 4 || i == 9) : (i == 3); }
 
-template <int FL, bool GUARDED, bool TRACKR>
+template <int FL, bool GUARDED, bool TRACKR, bool HOLD = false>
 __device__ __forceinline__ bool rk4_try(const DevModel &M, const Seg &sg, const double *y, double *ynew, double pa,
                                         double pb, double inv0, double inv1, unsigned nb0, unsigned nb1, bool &need_r) {
   constexpr int NEQ = Traits<FL>::NEQ;
   const double hh = pb - pa, hh2 = 0.5 * hh, tm = pa + hh2;
   double k[NEQ], acc[NEQ], yt[NEQ];
   unsigned flag = 0;
-  rhs<FL, GUARDED, TRACKR>(M, sg, pa, y, k, inv0, inv1, nb0, nb1, flag);
+  rhs<FL, GUARDED, TRACKR, HOLD>(M, sg, pa, y, k, inv0, inv1, nb0, nb1, flag);
 #pragma unroll
   for (int i = 0; i < NEQ; ++i) {
     if (!TRACKR && is_r_state<FL>(i)) continue;
     acc[i] = k[i]; yt[i] = fma(hh2, k[i], y[i]);
   }
-  rhs<FL, GUARDED, TRACKR>(M, sg, tm, yt, k, inv0, inv1, nb0, nb1, flag);
+  rhs<FL, GUARDED, TRACKR, HOLD>(M, sg, tm, yt, k, inv0, inv1, nb0, nb1, flag);
 #pragma unroll
   for (int i = 0; i < NEQ; ++i) {
     if (!TRACKR && is_r_state<FL>(i)) continue;
     acc[i] = fma(2.0, k[i], acc[i]); yt[i] = fma(hh2, k[i], y[i]);
   }
-  rhs<FL, GUARDED, TRACKR>(M, sg, tm, yt, k, inv0, inv1, nb0, nb1, flag);
+  rhs<FL, GUARDED, TRACKR, HOLD>(M, sg, tm, yt, k, inv0, inv1, nb0, nb1, flag);
 #pragma unroll
   for (int i = 0; i < NEQ; ++i) {
     if (!TRACKR && is_r_state<FL>(i)) continue;
     acc[i] = fma(2.0, k[i], acc[i]); yt[i] = fma(hh, k[i], y[i]);
   }
-  rhs<FL, GUARDED, TRACKR>(M, sg, pb, yt, k, inv0, inv1, nb0, nb1, flag);
+  rhs<FL, GUARDED, TRACKR, HOLD>(M, sg, pb, yt, k, inv0, inv1, nb0, nb1, flag);
   const double h6 = hh / 6.0;
 #pragma unroll
   for (int i = 0; i < NEQ; ++i) {
@@ -321,7 +324,11 @@ __device__ __forceinline__ void rk4_piece(const DevModel &M, const Seg &sg, doub
                                           double inv0, double inv1, unsigned nb0, unsigned nb1, bool &need_r) {
   constexpr int NEQ = Traits<FL>::NEQ;
   double yn[NEQ];
-  if (!sg.fast_ok || !rk4_try<FL, false, TRACKR>(M, sg, y, yn, pa, pb, inv0, inv1, nb0, nb1, need_r)) {
+  bool ok = false;
+  if (sg.fast_ok)
+    ok = sg.hold ? rk4_try<FL, false, TRACKR, true>(M, sg, y, yn, pa, pb, inv0, inv1, nb0, nb1, need_r)
+                 : rk4_try<FL, false, TRACKR, false>(M, sg, y, yn, pa, pb, inv0, inv1, nb0, nb1, need_r);
+  if (!ok) {
     // rare: redo the step with the reference's guard evaluated exactly in FP64
     rk4_try<FL, true, TRACKR>(M, sg, y, yn, pa, pb, inv0, inv1, 0u, 0u, need_r);
   }
@@ -403,6 +410,7 @@ __device__ __noinline__ Seg select_segment(const DevModel &M, const double *__re
     sg.b0 = __dmul_rn(sg.b0, inv0); sg.s0 = __dmul_rn(sg.s0, inv0);
     sg.b1 = __dmul_rn(sg.b1, inv1); sg.s1 = __dmul_rn(sg.s1, inv1);
     sg.b2 = __dmul_rn(sg.b2, inv0); sg.s2 = __dmul_rn(sg.s2, inv0);
+    sg.hold = sg.s0 == 0.0 && sg.s1 == 0.0 && sg.s2 == 0.0;
   } else {
     auto T = [&](int i) { return th[(int64_t)i * ld]; };
     const double Tinf0 = T(2), Tinft = T(3);
@@ -418,6 +426,7 @@ __device__ __noinline__ Seg select_segment(const DevModel &M, const double *__re
     }
     sg.fast_ok = beta0 >= 0 && betat >= 0 && bp[1] > bp[0];
     sg.b0 = __dmul_rn(sg.b0, inv0); sg.s0 = __dmul_rn(sg.s0, inv0);  // beta / N (Ne flavour: beta / Ne)
+    sg.hold = sg.s0 == 0.0 && sg.s1 == 0.0;  // (then b2 = 1 / Tinf is set)
   }
   return sg;
 }
