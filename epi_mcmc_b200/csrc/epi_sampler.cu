@@ -89,12 +89,12 @@ __device__ inline double reflect(double x, double lo, double hi) {
   return lo + y;
 }
 
-enum { USE_ACCEPT = 0, USE_PARTNER = 1, USE_SWAP = 2, USE_NORMAL = 16 };
+enum { USE_ACCEPT = 0, USE_PARTNER = 1, USE_SWAP = 2, USE_NORMAL = 16, USE_CROSS = 64 };
 
 // Accept/reject iteration `iter` (when do_accept) and write the proposal of iteration iter+1.
 __global__ void __launch_bounds__(128)
 k_accept_propose(int d, int64_t n, int64_t ld, int kind, uint64_t seed, int64_t chain_id0, int64_t iter, int do_accept,
-                 double beta0, const double *__restrict__ beta_rung, int cpr, double scale, double de_eps, const double *__restrict__ box_min,
+                 double beta0, const double *__restrict__ beta_rung, int cpr, double scale, double de_eps, int flags, const double *__restrict__ box_min,
                  const double *__restrict__ box_max, double *__restrict__ cur, double *__restrict__ prop,
                  double *__restrict__ logl, double *__restrict__ logp, const double *__restrict__ logl_p,
                  const double *__restrict__ logp_p, const int *__restrict__ status_p, double *__restrict__ lscale,
@@ -156,9 +156,36 @@ k_accept_propose(int d, int64_t n, int64_t ld, int kind, uint64_t seed, int64_t 
     if (b >= a) b += 1;  // two distinct members of the snapshot
     z1 = pop + ((int64_t)(a / per_rank) * d) * pop_ld + first + (a % per_rank);
     z2 = pop + ((int64_t)(b / per_rank) * d) * pop_ld + first + (b % per_rank);
-    // ter Braak (2006): gamma = 2.38/sqrt(2d), every 10th proposal gamma = 1 (mode hopping)
-    gam = ((it1 % 10u) == 0u) ? 1.0 : umix * step * 2.38 / sqrt(2.0 * d);
   }
+  // Subspace (crossover) updates, as in DREAM (Vrugt et al. 2009): a DE-MC proposal moves only a random subset
+  // of the coordinates, each chosen with probability CR in {0.1, 0.25, 0.5, 1} (one of the four per proposal,
+  // independent of the state: the kernel stays symmetric), with gamma = 2.38 / sqrt(2 d') for the d' chosen ones.
+  // On this target a handful of parameters (latencies, kernel sds, the death threshold) make logl jump at
+  // ceil/floor and integer-offset boundaries; full-dimensional moves cross such a boundary almost always and
+  // the integrated autocorrelation time was ~1,500 iterations, see profiles/r1_summary.md.
+  unsigned long long sel = ~0ull;  // bit p: coordinate p moves
+  int dsel = d;
+  const bool hop = (it1 % 10u) == 0u;  // ter Braak (2006): every 10th proposal gamma = 1, all coordinates
+  if (z1 && !hop && !(flags & EPI_SAMPLER_FLAG_FULLDIM)) {
+    const uint32_t crsel = r[3] & 3u;
+    const double CR = crsel == 0 ? 0.1 : crsel == 1 ? 0.25 : crsel == 2 ? 0.5 : 1.0;
+    if (CR < 1.0) {
+      sel = 0ull;
+      dsel = 0;
+      uint32_t c[4];
+      for (int p0 = 0; p0 < d; p0 += 4) {
+        philox4x32_10((uint32_t)cid, (uint32_t)(cid >> 32), it1, USE_CROSS + (uint32_t)(p0 >> 2), k0, k1, c);
+        for (int q = 0; q < 4 && p0 + q < d; ++q)
+          if (u01(c[q]) < CR) { sel |= 1ull << (p0 + q); ++dsel; }
+      }
+      if (dsel == 0) {  // at least one coordinate
+        const int p = (int)(((uint64_t)r[2] * (uint32_t)d) >> 32);
+        sel = 1ull << p;
+        dsel = 1;
+      }
+    }
+  }
+  if (z1) gam = hop ? 1.0 : umix * step * 2.38 / sqrt(2.0 * dsel);
   double zn[EPI_MAX_PARAMS];
   for (int p0 = 0; p0 < d; p0 += 4) {
     philox4x32_10((uint32_t)cid, (uint32_t)(cid >> 32), it1, USE_NORMAL + (uint32_t)(p0 >> 2), k0, k1, r);
@@ -171,9 +198,9 @@ k_accept_propose(int d, int64_t n, int64_t ld, int kind, uint64_t seed, int64_t 
     const double x = cur[(int64_t)p * ld + i];
     double y;
     if (z1) {
-      // DE-MC: x + gamma (z1 - z2) + e, e ~ N(0, (de_eps * population sd)^2)
+      // DE-MC: x + gamma (z1 - z2) + e, e ~ N(0, (de_eps * population sd)^2), on the chosen coordinates
       const double w = psd ? psd[p] : (hi - lo);
-      y = x + gam * (z1[(int64_t)p * pop_ld] - z2[(int64_t)p * pop_ld]) + de_eps * w * zn[p];
+      y = ((sel >> p) & 1ull) ? x + gam * (z1[(int64_t)p * pop_ld] - z2[(int64_t)p * pop_ld]) + de_eps * w * zn[p] : x;
     } else if (chol) {
       // RWM with the population covariance: x + step * 2.38/sqrt(d) * L z  (adaptive Metropolis shape,
       // measured during burn-in only)
@@ -333,7 +360,7 @@ static int launch_ap(epi_handle *h, SamplerState *s, int do_accept, double *draw
   k_accept_propose<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(
       h->M.d, n, s->ld, s->cfg.kind, s->cfg.seed, s->cfg.chain_id0, s->iter, do_accept, s->cfg.beta,
       s->n_rungs > 1 ? s->beta_rung : nullptr, s->cpr, s->cfg.scale,
-      s->cfg.de_eps, h->M.box_min, h->M.box_max, s->cur, s->prop, s->logl, s->logp, s->logl_p, s->logp_p, s->status_p,
+      s->cfg.de_eps, s->cfg.reserved, h->M.box_min, h->M.box_max, s->cur, s->prop, s->logl, s->logp, s->logl_p, s->logp_p, s->status_p,
       s->lscale, s->adapt, s->adapt_target, s->acc, s->pop, s->pop_ranks, s->pop_per_rank, s->pop_ld,
       s->psd_ready ? s->psd : nullptr, (s->psd_ready && s->cfg.kind == EPI_SAMPLER_RWM) ? s->chol : nullptr, draw_out, draw_lp);
   h->launches += 1;

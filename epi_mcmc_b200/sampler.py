@@ -24,7 +24,7 @@ KINDS = {"rwm": _capi.SAMPLER_RWM, "demc": _capi.SAMPLER_DEMC}
 class Sampler:
     def __init__(self, model, n_chains: int, kind: str = "demc", seed: int = 42, scale: float | None = None,
                  de_eps: float = 1e-4, beta: float = 1.0, chain_id0: int = 0, theta0=None, rungs: int = 1,
-                 GTI_pow: float = 1.0):
+                 GTI_pow: float = 1.0, subspace: bool = True):
         """n_chains is the total on this device; with `rungs` > 1 (parallel tempering, the
         reference driver uses rungs = 20, GTI_pow = 1: fitMCMC-drj.R:53-56) chain i sits on rung
         i // (n_chains // rungs) and the LAST rung is the cold one."""
@@ -41,7 +41,8 @@ class Sampler:
             # (before that: of 2 % of the box width / sqrt(d))
             scale = 1.0
         cfg = _capi.SamplerCfg(KINDS[kind], self.n_chains, int(chain_id0), int(seed), float(scale), float(de_eps),
-                               float(beta), self.rungs, 0, float(GTI_pow))
+                               float(beta), self.rungs, 0 if subspace else 1, float(GTI_pow))  # flags: EPI_SAMPLER_FLAG_FULLDIM
+        # subspace: DE-MC proposals move a random subset of the coordinates (DREAM-style crossover)
         t0 = None
         if theta0 is not None:
             t0 = np.ascontiguousarray(np.asarray(theta0, dtype=np.float64))

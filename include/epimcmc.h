@@ -93,6 +93,9 @@ extern "C" {
 /* ---- sampler kinds -------------------------------------------------------- */
 #define EPI_SAMPLER_RWM 0 /* random-walk Metropolis, per-parameter Gaussian scale */
 #define EPI_SAMPLER_DEMC 1 /* differential evolution MC (ter Braak 2006) on a population snapshot */
+/* epi_sampler_cfg.reserved carries flags.  By default a DE-MC proposal moves a random subset of the coordinates
+ * (DREAM-style crossover, CR drawn from {0.1, 0.25, 0.5, 1}); this flag restores full-dimensional moves.        */
+#define EPI_SAMPLER_FLAG_FULLDIM 1
 
 typedef struct epi_handle epi_handle;
 
@@ -243,7 +246,7 @@ typedef struct epi_sampler_cfg {
   int32_t n_rungs;     /* parallel tempering: temperature rungs (<= 1: none).  n_chains must be a
                           multiple; chain i sits on rung i / (n_chains / n_rungs); the LAST rung is the
                           cold one (beta = 1), as in drjacoby (fitMCMC-drj.R:53,62)                     */
-  int32_t reserved;
+  int32_t reserved;    /* flags: EPI_SAMPLER_FLAG_* (0 = defaults) */
   double gti_pow;      /* beta_r = ((r) / (n_rungs - 1)) ^ gti_pow, r = 0 .. n_rungs-1 (GTI_pow, :56)   */
 } epi_sampler_cfg;
 
