@@ -103,7 +103,7 @@ SYMBOLS = (
     "epi_create", "epi_destroy", "epi_last_error", "epi_abi_version", "epi_n_params",
     "epi_param_name", "epi_df_params", "epi_eval", "epi_eval_submit", "epi_eval_wait", "epi_eval_device", "epi_eval_detail",
     "epi_n_series", "epi_trajectories", "epi_n_series_ext", "epi_trajectories_ext", "epi_quantiles", "epi_sampler_init", "epi_sampler_run",
-    "epi_sampler_adapt", "epi_sampler_state_device", "epi_sampler_set_population",
+    "epi_sampler_adapt", "epi_sampler_set_scale", "epi_sampler_state_device", "epi_sampler_set_population",
     "epi_sampler_get", "epi_sampler_stats", "epi_sampler_pt_stats", "epi_sampler_record", "epi_sampler_draws", "epi_sampler_draws_subset",
     "epi_fp64_peak", "epi_set_timing", "epi_last_kernel_ms", "epi_launch_count", "epi_philox_probe",
 )
@@ -143,6 +143,7 @@ def load():
     lib.epi_sampler_init.argtypes = [vp, C.POINTER(SamplerCfg), _dp]
     lib.epi_sampler_run.argtypes = [vp, i32]
     lib.epi_sampler_adapt.argtypes = [vp, C.c_int, C.c_double]
+    lib.epi_sampler_set_scale.argtypes = [vp, C.c_double]
     lib.epi_sampler_state_device.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(i64)]
     lib.epi_sampler_set_population.argtypes = [vp, vp, i32, i32, i64]
     lib.epi_philox_probe.argtypes = [vp, C.c_uint64, C.c_uint32, C.c_uint32, i32, C.POINTER(C.c_uint32)]

@@ -493,6 +493,19 @@ extern "C" int epi_sampler_run(epi_handle *h, int32_t n_iter) {
   return EPI_OK;
 }
 
+extern "C" int epi_sampler_set_scale(epi_handle *h, double scale) {
+  if (!h || !h->sampler) return epi_fail(h, EPI_ERR_STATE, "sampler not initialised");
+  if (!(scale > 0) || !std::isfinite(scale)) return epi_fail(h, EPI_ERR_ARG, "scale must be positive and finite");
+  SamplerState *s = h->sampler;
+  CUDA_OK(h, cudaSetDevice(h->device));
+  s->cfg.scale = scale;
+  // the pending proposal (iteration iter + 1) was drawn with the old scale: redraw it (same Philox counters)
+  int rc = launch_ap(h, s, 0, nullptr, nullptr);
+  if (rc) return rc;
+  CUDA_OK(h, cudaStreamSynchronize(h->stream));
+  return EPI_OK;
+}
+
 extern "C" int epi_sampler_pt_stats(epi_handle *h, int64_t *proposed, int64_t *accepted) {
   if (!h || !h->sampler) return epi_fail(h, EPI_ERR_STATE, "sampler not initialised");
   unsigned long long c[2] = {0, 0};

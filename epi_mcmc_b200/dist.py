@@ -68,6 +68,17 @@ class Comm:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def allreduce_sum(self, values):
+        """element-wise sum of a small float64 vector over the ranks (returns a numpy array)"""
+        import numpy as np
+        v = np.asarray(values, dtype=np.float64)
+        if self.world == 1:
+            return v
+        dev = torch.device("cuda", self.local_rank) if self.backend == "nccl" else torch.device("cpu")
+        t = torch.tensor(v, dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return t.cpu().numpy()
+
     def barrier(self):
         if self.world > 1:
             if self.backend == "nccl":

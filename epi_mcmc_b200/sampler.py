@@ -49,9 +49,35 @@ class Sampler:
             assert t0.shape == (self.n_chains, model.d)
         _capi.check(self._lib.epi_sampler_init(self._h, C.byref(cfg), _capi.as_dp(t0) if t0 is not None else None),
                     self._h)
+        self.scale = float(scale)
+        self._tune_acc, self._tune_it, self._tune_k = 0, 0, 0
 
     def run(self, n_iter: int):
         _capi.check(self._lib.epi_sampler_run(self._h, int(n_iter)), self._h)
+
+    def set_scale(self, scale: float):
+        _capi.check(self._lib.epi_sampler_set_scale(self._h, float(scale)), self._h)
+        self.scale = float(scale)
+
+    def tune_scale(self, comm=None, target: float = 0.2, lo: float = 0.05, hi: float = 20.0):
+        """Burn-in only: one Robbins-Monro step of the GLOBAL step multiplier towards `target` acceptance,
+        using the acceptances of ALL chains (all ranks when `comm` is given, so the result does not depend on
+        the sharding) since the previous call.  A population that starts too tight is accepted too often and
+        grows its steps, one that starts too wide shrinks them; the multiplier is frozen afterwards."""
+        st = self.stats()
+        acc, its = st["accepted"] - self._tune_acc, st["iterations"] - self._tune_it
+        self._tune_acc, self._tune_it = st["accepted"], st["iterations"]
+        if its <= 0:
+            return self.scale
+        tot = np.array([float(acc), float(its) * self.n_chains])
+        if comm is not None and comm.world > 1:
+            tot = comm.allreduce_sum(tot)
+        rate = tot[0] / max(1.0, tot[1])
+        self._tune_k += 1
+        gain = max(0.15, 1.0 / np.sqrt(self._tune_k))
+        new = float(np.clip(self.scale * np.exp(gain * (rate - target) / max(target, 1e-3)), lo, hi))
+        self.set_scale(new)
+        return new
 
     def adapt(self, enable: bool, target: float = 0.0):
         _capi.check(self._lib.epi_sampler_adapt(self._h, int(enable), float(target)), self._h)

@@ -261,6 +261,11 @@ int epi_sampler_run(epi_handle *h, int32_t n_iter);
  * the classical step sizes (2.38/sqrt(d), 2.38/sqrt(2d)) alone — preferable on
  * this rugged target (ceil/floor kernel extents, integer data_offset).        */
 int epi_sampler_adapt(epi_handle *h, int enable, double target_accept);
+/* Replace the global step multiplier (epi_sampler_cfg.scale) between epi_sampler_run calls and redraw the
+ * pending proposal with it.  The host front end uses it during burn-in to steer the POPULATION acceptance
+ * rate (all ranks' chains together, so that results do not depend on the sharding) towards a target; it is
+ * frozen for the sampling phase.                                                */
+int epi_sampler_set_scale(epi_handle *h, double scale);
 /* device pointers of the current chain states (d x ld SOA, ld >= n_chains) for
  * the NCCL all-gather of the DE-MC population; the pointers stay valid until
  * the next epi_sampler_init / epi_destroy                                      */
