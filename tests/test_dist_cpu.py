@@ -31,6 +31,8 @@ def _worker(rank, world, port, q):
         for p in range(d):
             ok &= flat[partner_address(z, n, d, ld, p)] == 1000 * z + p
     mx = comm.max_over_ranks(1.0 + rank)
+    tot = comm.allreduce_sum([10.0 + rank, 100.0])     # the acceptance totals Sampler.tune_scale reduces
+    ok &= bool(tot[0] == 21.0 and tot[1] == 200.0)
     comm.barrier()
     q.put((rank, bool(ok), mx, first, cnt))
     comm.close()
