@@ -13,14 +13,11 @@ def report(tag, S, it):
     lpost = ll + lp
     print(tag, it, "acc %.3f" % S.stats()["accept_rate"], "mean %.2f med %.2f p05 %.2f max %.2f" % (np.mean(lpost), np.median(lpost), np.percentile(lpost, 5), np.max(lpost)),
           "sd/box", np.round(sd[keys], 4), flush=True)
-for jit, tune in ((0.02, False), (0.02, True), (0.10, True)):
-    rng = np.random.default_rng(3)
-    th0 = np.clip(init + (rng.uniform(size=(n, M.d)) - 0.5) * jit * (mx - mn), mn, mx)
-    S = Sampler(M, n, kind="demc", seed=1, theta0=th0)
+for kind in ("rwm",):
+    S = Sampler(M, n, kind=kind, seed=1)
     S.adapt(True)
     for blk in range(1, 41):
         for _ in range(10):
-            S.run(10); S.refresh_population()
-            if tune and blk <= 20: S.tune_scale(target=0.2)
+            S.run(10)
         if blk == 20: S.adapt(False)
-        if blk in (1, 2, 5, 10, 15, 20, 30, 40): report("jitter %.2f tune %d scale %.2f" % (jit, tune, S.scale), S, blk * 100)
+        if blk in (1, 2, 5, 10, 15, 20, 30, 40): report(kind, S, blk * 100)
