@@ -677,11 +677,12 @@ struct Seg2 {
   bool fast_ok;               // all three beta curves >= 0 on the segment (premise of the fast guard)
 };
 
-template <bool GUARDED>
+// TRACKR = false: R (y[4]) is not integrated, exactly as in rhs<> (see below_one)
+template <bool GUARDED, bool TRACKR>
 __device__ __forceinline__ void rhs_age2(double a1, double gamma, const Seg2 &sg, double t, const double *y, double *dy,
                                          double invN, double Ngrp, unsigned nb, unsigned pairmask, int even_lane,
                                          unsigned &flag) {
-  const double S = y[0], E1 = y[1], E2 = y[2], I = y[3], R = y[4];
+  const double S = y[0], E1 = y[1], E2 = y[2], I = y[3], R = TRACKR ? y[4] : 0.0;
   if constexpr (GUARDED) {
     // bounds guard over all ten states of the chain, model-agen.cpp:109-124
     const int bad_own = (S < 0 || E1 < 0 || E2 < 0 || I < 0 || R < 0 || S > Ngrp || E1 > Ngrp || E2 > Ngrp ||
@@ -694,53 +695,63 @@ __device__ __forceinline__ void rhs_age2(double a1, double gamma, const Seg2 &sg
       for (int i = 0; i < 5; ++i) dy[i] = 0.0;
       return;
     }
+    if constexpr (!TRACKR) flag |= (S < 1.0) ? 1u : 0u;  // the R test is undecidable here
     // the same explicitly rounded operations as rhs<>: both ODE kernels produce the same bits
     const double dt = t - sg.tk;
     const double bA = fma(dt, sg.sA, sg.bA), bB = fma(dt, sg.sB, sg.bB);
     const double inf = __dmul_rn(fma(bA, I, __dmul_rn(bB, fy)), S);
-    dy[0] = -inf; dy[1] = fma(-a1, E1, inf); dy[2] = fma(a1, E1, -E2); dy[3] = fma(-gamma, I, E2); dy[4] = __dmul_rn(gamma, I);
+    dy[0] = -inf; dy[1] = fma(-a1, E1, inf); dy[2] = fma(a1, E1, -E2); dy[3] = fma(-gamma, I, E2);
+    if constexpr (TRACKR) dy[4] = __dmul_rn(gamma, I);
   } else {
-    flag |= oob_group5(S, E1, E2, I, R, nb);
+    if constexpr (TRACKR) flag |= oob_group5(S, E1, E2, I, R, nb);
+    else flag |= oob_group4_nor(S, E1, E2, I, nb);
     const double fy = __shfl_sync(pairmask, I, even_lane);  // I of the younger group
     const double dt = t - sg.tk;
     const double bA = fma(dt, sg.sA, sg.bA), bB = fma(dt, sg.sB, sg.bB);
     const double inf = __dmul_rn(fma(bA, I, __dmul_rn(bB, fy)), S);  // y: (betay/Ny*Iy)*Sy; o: (betao/No*Io + betayo/Ny*Iy)*So
-    dy[0] = -inf; dy[1] = fma(-a1, E1, inf); dy[2] = fma(a1, E1, -E2); dy[3] = fma(-gamma, I, E2); dy[4] = __dmul_rn(gamma, I);
+    dy[0] = -inf; dy[1] = fma(-a1, E1, inf); dy[2] = fma(a1, E1, -E2); dy[3] = fma(-gamma, I, E2);
+    if constexpr (TRACKR) dy[4] = __dmul_rn(gamma, I);
   }
 }
 
-template <bool GUARDED>
+template <bool GUARDED, bool TRACKR>
 __device__ __forceinline__ bool rk4_try_age2(double a1, double gamma, const Seg2 &sg, const double *y, double *ynew,
                                              double pa, double pb, double invN, double Ngrp, unsigned nb,
-                                             unsigned pairmask, int even_lane) {
+                                             unsigned pairmask, int even_lane, bool &need_r) {
+  constexpr int NS = TRACKR ? 5 : 4;
   const double hh = pb - pa, hh2 = 0.5 * hh, tm = pa + hh2;
   double k[5], acc[5], yt[5];
   unsigned flag = 0;
-  rhs_age2<GUARDED>(a1, gamma, sg, pa, y, k, invN, Ngrp, nb, pairmask, even_lane, flag);
+  rhs_age2<GUARDED, TRACKR>(a1, gamma, sg, pa, y, k, invN, Ngrp, nb, pairmask, even_lane, flag);
 #pragma unroll
-  for (int i = 0; i < 5; ++i) { acc[i] = k[i]; yt[i] = fma(hh2, k[i], y[i]); }
-  rhs_age2<GUARDED>(a1, gamma, sg, tm, yt, k, invN, Ngrp, nb, pairmask, even_lane, flag);
+  for (int i = 0; i < NS; ++i) { acc[i] = k[i]; yt[i] = fma(hh2, k[i], y[i]); }
+  rhs_age2<GUARDED, TRACKR>(a1, gamma, sg, tm, yt, k, invN, Ngrp, nb, pairmask, even_lane, flag);
 #pragma unroll
-  for (int i = 0; i < 5; ++i) { acc[i] = fma(2.0, k[i], acc[i]); yt[i] = fma(hh2, k[i], y[i]); }
-  rhs_age2<GUARDED>(a1, gamma, sg, tm, yt, k, invN, Ngrp, nb, pairmask, even_lane, flag);
+  for (int i = 0; i < NS; ++i) { acc[i] = fma(2.0, k[i], acc[i]); yt[i] = fma(hh2, k[i], y[i]); }
+  rhs_age2<GUARDED, TRACKR>(a1, gamma, sg, tm, yt, k, invN, Ngrp, nb, pairmask, even_lane, flag);
 #pragma unroll
-  for (int i = 0; i < 5; ++i) { acc[i] = fma(2.0, k[i], acc[i]); yt[i] = fma(hh, k[i], y[i]); }
-  rhs_age2<GUARDED>(a1, gamma, sg, pb, yt, k, invN, Ngrp, nb, pairmask, even_lane, flag);
+  for (int i = 0; i < NS; ++i) { acc[i] = fma(2.0, k[i], acc[i]); yt[i] = fma(hh, k[i], y[i]); }
+  rhs_age2<GUARDED, TRACKR>(a1, gamma, sg, pb, yt, k, invN, Ngrp, nb, pairmask, even_lane, flag);
   const double h6 = hh / 6.0;
 #pragma unroll
-  for (int i = 0; i < 5; ++i) ynew[i] = fma(h6, __dadd_rn(acc[i], k[i]), y[i]);
-  if constexpr (GUARDED) return true;
+  for (int i = 0; i < NS; ++i) ynew[i] = fma(h6, __dadd_rn(acc[i], k[i]), y[i]);
+  if constexpr (!TRACKR) ynew[4] = 0.0;
+  if constexpr (GUARDED) {
+    if (!TRACKR && (flag & 1u)) need_r = true;
+    return true;
+  }
   const int own_bad = (int)flag < 0;
   return !(own_bad | __shfl_xor_sync(pairmask, own_bad, 1));
 }
 
+template <bool TRACKR>
 __device__ __forceinline__ void rk4_piece_age2(double a1, double gamma, const Seg2 &sg, double *y, double pa, double pb,
                                                double invN, double Ngrp, unsigned nb, unsigned pairmask,
-                                               int even_lane) {
+                                               int even_lane, bool &need_r) {
   double yn[5];
-  if (!sg.fast_ok || !rk4_try_age2<false>(a1, gamma, sg, y, yn, pa, pb, invN, Ngrp, nb, pairmask, even_lane)) {
+  if (!sg.fast_ok || !rk4_try_age2<false, TRACKR>(a1, gamma, sg, y, yn, pa, pb, invN, Ngrp, nb, pairmask, even_lane, need_r)) {
     // rare: redo the step with the reference's guard evaluated exactly in FP64
-    rk4_try_age2<true>(a1, gamma, sg, y, yn, pa, pb, invN, Ngrp, nb, pairmask, even_lane);
+    rk4_try_age2<true, TRACKR>(a1, gamma, sg, y, yn, pa, pb, invN, Ngrp, nb, pairmask, even_lane, need_r);
   }
 #pragma unroll
   for (int i = 0; i < 5; ++i) y[i] = yn[i];
@@ -780,12 +791,20 @@ __device__ __noinline__ Seg2 select_segment_age2(const double *__restrict__ th, 
   return sg;
 }
 
+// Like k_ode, this instance does not integrate R (4 states per lane); chains it flags are redone by the R-tracking
+// instance of the thread-per-chain kernel, which computes the same bits.  (Capped at 72 registers so that all
+// 2 x 65,536 lanes of a full batch are resident at once it spills and takes 1.71 ms for pass 2 against 1.00 ms
+// thread-per-chain: the two-lane form stays a small-batch kernel.)
+constexpr int kPairRegs = 128;
 template <int FL, bool PASS2>
-__global__ void __maxnreg__(128)
+__global__ void __maxnreg__(kPairRegs)
 k_ode_age2(const DevModel M, const double *__restrict__ theta, int64_t ld, int64_t n, const int *__restrict__ offset,
            const int *__restrict__ padv, const double *__restrict__ hist1, double *__restrict__ hist_out,
            double *__restrict__ ckpt, int window_only = 0, int ndays_limit = 0,
-           const int *__restrict__ retry_status = nullptr) {
+           const int *__restrict__ retry_status = nullptr, int *__restrict__ need_r_flag = nullptr,
+           int force_need_r = 0) {
+  constexpr bool TR = false;
+  bool need_r = false;
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t i = tid >> 1;  // chain
   if (i >= n) return;
@@ -817,6 +836,7 @@ k_ode_age2(const DevModel M, const double *__restrict__ theta, int64_t ld, int64
       // pass 2 skipped: the pass-1 rows are recycled into the P-length slices (:216-223)
       const double *in = hist1 + (i * 2 + g) * (int64_t)hist_pitch(M.P1);
       for (int d = 0; d < M.P; ++d) out[d] = in[d % M.P1];
+      if (g == 0 && need_r_flag) need_r_flag[i] = 0;
       return;
     }
     t0 = padv[i] + 1;
@@ -836,7 +856,7 @@ k_ode_age2(const DevModel M, const double *__restrict__ theta, int64_t ld, int64
         const double *in = hist1 + (i * 2 + g) * (int64_t)hist_pitch(M.P1);
         for (int d = 0; d <= d0; ++d) out[d] = in[d];
 #pragma unroll
-        for (int q = 0; q < 5; ++q) y[q] = ck[((int64_t)d0 * 10 + q) * kTile];
+        for (int q = 0; q < (TR ? 5 : 4); ++q) y[q] = ck[((int64_t)d0 * 10 + q) * kTile];
       }
     }
   }
@@ -848,7 +868,7 @@ k_ode_age2(const DevModel M, const double *__restrict__ theta, int64_t ld, int64
   if constexpr (!PASS2) {
     if (ck) {
 #pragma unroll
-      for (int q = 0; q < 5; ++q) ck[q * kTile] = y[q];
+      for (int q = 0; q < (TR ? 5 : 4); ++q) ck[q * kTile] = y[q];
     }
   }
   for (int d = d0 + 1; d < nint; ++d) {
@@ -860,21 +880,24 @@ k_ode_age2(const DevModel M, const double *__restrict__ theta, int64_t ld, int64
       if constexpr (PASS2) {
         if (a >= tcut) sg = select_segment_age2<FL>(th, ld, bp, nbp, a, g, &tcut, 1.0 / M.Ny, 1.0 / M.No);
         while (tcut < b) {
-          rk4_piece_age2(a1, gamma, sg, y, pa, tcut, invN, Ngrp, nb, pairmask, even_lane);
+          rk4_piece_age2<TR>(a1, gamma, sg, y, pa, tcut, invN, Ngrp, nb, pairmask, even_lane, need_r);
           pa = tcut;
           sg = select_segment_age2<FL>(th, ld, bp, nbp, pa, g, &tcut, 1.0 / M.Ny, 1.0 / M.No);
         }
       }
-      rk4_piece_age2(a1, gamma, sg, y, pa, b, invN, Ngrp, nb, pairmask, even_lane);
+      rk4_piece_age2<TR>(a1, gamma, sg, y, pa, b, invN, Ngrp, nb, pairmask, even_lane, need_r);
     }
     out[d] = y[0];
     if constexpr (!PASS2) {
       if (ck && d < cdays) {
 #pragma unroll
-        for (int q = 0; q < 5; ++q) ck[((int64_t)d * 10 + q) * kTile] = y[q];
+        for (int q = 0; q < (TR ? 5 : 4); ++q) ck[((int64_t)d * 10 + q) * kTile] = y[q];
       }
     }
   }
+  // either lane may have met an undecidable R test: the chain is flagged if one of them did
+  const int nr = (need_r ? 1 : 0) | __shfl_xor_sync(pairmask, need_r ? 1 : 0, 1);
+  if (g == 0 && need_r_flag) need_r_flag[i] = (nr || force_need_r) ? 1 : 0;
 }
 
 // ---------------------------------------------------------------------- K_mid
@@ -1827,13 +1850,12 @@ static cudaError_t launch_eval_fl(const EvalArgs &a) {
   // the chains the hot one flagged (exits at once otherwise)
   auto pass1 = [&](int limit, const int *retry) {
     if (use_pair) {
-      if constexpr (Traits<FL>::kAge) k_ode_age2<FL, false><<<pair_blocks, 64, 0, s>>>(M, a.theta, a.ld, n, nullptr, nullptr, nullptr, a.hist1, a.ckpt, 0, limit, retry);
-      nl += 1;
+      if constexpr (Traits<FL>::kAge) k_ode_age2<FL, false><<<pair_blocks, 64, 0, s>>>(M, a.theta, a.ld, n, nullptr, nullptr, nullptr, a.hist1, a.ckpt, 0, limit, retry, a.need_r, a.force_need_r);
     } else {
       k_ode<FL, false><<<ode_blocks, 32, 0, s>>>(M, a.theta, a.ld, n, nullptr, nullptr, nullptr, a.hist1, a.ckpt, nullptr, 0, 0, limit, retry, a.need_r, a.force_need_r);
-      k_ode<FL, false, false, true><<<ode_blocks, 32, 0, s>>>(M, a.theta, a.ld, n, nullptr, nullptr, nullptr, a.hist1, a.ckpt, nullptr, 0, 0, 0, nullptr, a.need_r, 0);
-      nl += 2;
     }
+    k_ode<FL, false, false, true><<<ode_blocks, 32, 0, s>>>(M, a.theta, a.ld, n, nullptr, nullptr, nullptr, a.hist1, a.ckpt, nullptr, 0, 0, 0, nullptr, a.need_r, 0);
+    nl += 2;
   };
   pass1(chunk, nullptr);
   if (a.ev) cudaEventRecord(a.ev[1], s);
@@ -1849,8 +1871,9 @@ static cudaError_t launch_eval_fl(const EvalArgs &a) {
   const bool want_ext = a.series_out && a.ns_total > (Traits<FL>::kAge ? 8 : 3);
   const int window_only = (a.series_out || !a.window_only) ? 0 : 1;  // scoring reads S(t) only up to the last data-window day
   if (use_pair && !want_ext) {
-    if constexpr (Traits<FL>::kAge) k_ode_age2<FL, true><<<pair_blocks, 64, 0, s>>>(M, a.theta, a.ld, n, a.offset, a.pad, a.hist1, a.hist2, a.ckpt, window_only);
-    nl += 1;
+    if constexpr (Traits<FL>::kAge) k_ode_age2<FL, true><<<pair_blocks, 64, 0, s>>>(M, a.theta, a.ld, n, a.offset, a.pad, a.hist1, a.hist2, a.ckpt, window_only, 0, nullptr, a.need_r, a.force_need_r);
+    k_ode<FL, true, false, true><<<ode_blocks, 32, 0, s>>>(M, a.theta, a.ld, n, a.offset, a.pad, a.hist1, a.hist2, a.ckpt, nullptr, 0, window_only, 0, nullptr, a.need_r, 0);
+    nl += 2;
   } else if (want_ext) {
     // trajectories with the ext series: pass 2 also writes E, I, R and the Re/Rt diagnostics (no restart)
     k_ode<FL, true, true><<<ode_blocks, 32, 0, s>>>(M, a.theta, a.ld, n, a.offset, a.pad, a.hist1, a.hist2, nullptr,
