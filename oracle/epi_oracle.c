@@ -106,9 +106,19 @@ double oracle_dnbinom_mu_log(double x, double size, double mu) {
   if (x == 0)
     return size * (size < mu ? log(size / (size + mu)) : log1p(-mu / (size + mu)));
   /* the data-only lgamma part cancels heavily for large x: long double keeps it
-   * at the accuracy R's saddle-point dbinom_raw() has */
-  const double lg = (double)(lgammal((long double)x + size) - lgammal((long double)size) -
-                             lgammal((long double)x + 1.0L));
+   * at the accuracy R's saddle-point dbinom_raw() has.  It depends on (x, size) only, i.e. on the data: a small
+   * per-thread direct-mapped cache keeps the CPU baseline from paying three lgammal() per term and evaluation
+   * (the GPU path folds the same constants into its term table once, at handle creation). */
+  static __thread struct { double x, size, lg; int used; } cache[4096];
+  union { double d; uint64_t u; } kx = {x}, ks = {size};
+  const unsigned slot = (unsigned)((kx.u * 0x9E3779B97F4A7C15ull ^ ks.u * 0xC2B2AE3D27D4EB4Full) >> 52);
+  double lg;
+  if (cache[slot].used && cache[slot].x == x && cache[slot].size == size) {
+    lg = cache[slot].lg;
+  } else {
+    lg = (double)(lgammal((long double)x + size) - lgammal((long double)size) - lgammal((long double)x + 1.0L));
+    cache[slot].x = x; cache[slot].size = size; cache[slot].lg = lg; cache[slot].used = 1;
+  }
   return lg + size * log(size / (size + mu)) + x * log(mu / (size + mu));
 }
 
