@@ -105,7 +105,7 @@ SYMBOLS = (
     "epi_n_series", "epi_trajectories", "epi_n_series_ext", "epi_trajectories_ext", "epi_quantiles", "epi_sampler_init", "epi_sampler_run",
     "epi_sampler_adapt", "epi_sampler_set_scale", "epi_sampler_state_device", "epi_sampler_set_population",
     "epi_sampler_get", "epi_sampler_stats", "epi_sampler_pt_stats", "epi_sampler_record", "epi_sampler_draws", "epi_sampler_draws_subset",
-    "epi_fp64_peak", "epi_set_timing", "epi_last_kernel_ms", "epi_launch_count", "epi_philox_probe",
+    "epi_fp64_peak", "epi_set_timing", "epi_last_kernel_ms", "epi_launch_count", "epi_fallback_count", "epi_philox_probe",
 )
 
 
@@ -158,6 +158,8 @@ def load():
     lib.epi_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
     lib.epi_launch_count.argtypes = [vp]
     lib.epi_launch_count.restype = i64
+    lib.epi_fallback_count.argtypes = [vp]
+    lib.epi_fallback_count.restype = i64
     _lib = lib
     return lib
 

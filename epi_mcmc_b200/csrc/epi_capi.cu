@@ -483,6 +483,17 @@ extern "C" int epi_df_params(const epi_handle *h, double *mn, double *mx, double
 }
 extern "C" int64_t epi_launch_count(const epi_handle *h) { return h ? h->launches : 0; }
 
+extern "C" int64_t epi_fallback_count(epi_handle *h) {
+  if (!h || !h->ws.need_r || h->ws.ld <= 0) return h ? 0 : -1;
+  if (cudaSetDevice(h->device) != cudaSuccess) return -1;
+  std::vector<int> host((size_t)h->ws.ld);
+  if (cudaStreamSynchronize(h->stream) != cudaSuccess) return -1;
+  if (cudaMemcpy(host.data(), h->ws.need_r, sizeof(int) * host.size(), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  int64_t c = 0;
+  for (int v : host) c += v != 0;
+  return c;
+}
+
 // ----------------------------------------------------------------- workspace
 int epi_ensure_workspace(epi_handle *h, Workspace &w, const DevModel &M, int64_t n, int want_series) {
   // want_series: 0 = none, else the number of calculateModel series per chain (basic or basic + ext)

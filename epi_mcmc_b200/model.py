@@ -249,6 +249,10 @@ class Model:
     def launch_count(self) -> int:
         return int(self._lib.epi_launch_count(self._h))
 
+    def fallback_count(self) -> int:
+        """chains of the last batch whose ODE passes were redone with the removed compartment integrated"""
+        return int(self._lib.epi_fallback_count(self._h))
+
     def eval_device(self, d_theta_ptr: int, n: int, d_logl: int, d_logp: int, d_status: int, stream: int = 0):
         """epi_eval_device on raw device pointers (theta SoA d x n)."""
         _capi.check(self._lib.epi_eval_device(self._h, d_theta_ptr, n, d_logl, d_logp, d_status, stream), self._h)

@@ -303,6 +303,9 @@ int epi_set_timing(epi_handle *h, int enable);
 int epi_last_kernel_ms(epi_handle *h, float ms[4]);
 /* number of kernel launches issued by this handle since creation             */
 int64_t epi_launch_count(const epi_handle *h);
+/* diagnostic: how many chains of the most recent evaluation batch (epi_eval* / sampler) had their ODE passes
+ * recomputed by the R-tracking kernel instance (0 in any realistic regime); < 0 on error */
+int64_t epi_fallback_count(epi_handle *h);
 /* test hook: raw Philox4x32-10 words generated on the device,
  * out[4*j..4*j+3] = philox(counter = (j, 0, iter, use), key = seed)           */
 int epi_philox_probe(epi_handle *h, uint64_t seed, uint32_t iter, uint32_t use, int32_t n, uint32_t *out);

@@ -18,6 +18,7 @@ for name, n, m in (("A300", 24576, 4), ("A300", 8192, 1), ("I290", 16384, 4), ("
     theta = np.vstack([box, near])
     t0 = time.time()
     logl, logp, status = M.calclogpost_batch(theta)
+    n_fallback = M.fallback_count()
     off, pad, terms = M.eval_detail(theta)
     ref = oracle.evaluate(ds["flavour"], ds, theta, ds["period"], m, n_threads=16)
     cond = oracle.conditioning(ds["flavour"], ds, theta, ds["period"], m, ref["logl"], n_threads=16)
@@ -27,7 +28,7 @@ for name, n, m in (("A300", 24576, 4), ("A300", 8192, 1), ("I290", 16384, 4), ("
     lp_ok = rel_err(logp, ref["logp"]).max()
     nanmis = int((np.isnan(logl) != np.isnan(ref["logl"])).sum())
     print(f"{name} m={m} n={n}: ints_equal={ok_int} within_bar={within.mean():.5f} strict_1e-10={np.mean(strict):.4f} "
-          f"logp_max_rel={lp_ok:.2e} nan_mismatch={nanmis} status0={np.mean(status==0):.3f} t={time.time()-t0:.1f}s", flush=True)
+          f"logp_max_rel={lp_ok:.2e} nan_mismatch={nanmis} status0={np.mean(status==0):.3f} r_fallback={n_fallback} t={time.time()-t0:.1f}s", flush=True)
     if not ok_int:
         bad = np.nonzero((status != ref["status"]) | (off != ref["offset"]) | (pad != ref["padding"]))[0]
         print("  int mismatches:", len(bad), [(int(i), int(status[i]), int(ref["status"][i]), int(off[i]), int(ref["offset"][i])) for i in bad[:5]])

@@ -497,3 +497,35 @@ def test_both_ode_kernels_produce_the_same_bits(name):
         assert np.array_equal(a, b[:len(theta)], equal_nan=True)
         assert np.array_equal(a, b[-len(theta):], equal_nan=True)
     M.close()
+
+
+def test_tiny_population_exercises_the_r_fallback(oracle, monkeypatch):
+    """With a population of a few hundred the epidemic burns through everybody: S falls below 1, the hot ODE path
+    can no longer rule out the R part of the bounds guard, and the chains are recomputed by the R-tracking instance.
+    Results must still match the oracle (which integrates R and evaluates the full guard) and the forced-fallback run."""
+    from epi_mcmc_b200.model import Model, load_dataset
+    ds = dict(load_dataset("A300"))
+    ds["y_N"], ds["o_N"], ds["N"] = 300.0, 120.0, 420.0
+    mn, mx, init = (np.array(v) for v in oracle.df_params("age2q", ds, 300))
+    rng = np.random.default_rng(2)
+    theta = np.clip(init + (rng.uniform(size=(256, 45)) - 0.5) * 0.3 * (mx - mn), mn, mx)
+    theta[:, 17] = rng.uniform(0.0, 0.5, size=256)   # t0_morts: a threshold such a small epidemic can cross
+    M = Model(ds, substeps=4)
+    logl, logp, status = M.calclogpost_batch(theta)
+    n_fb = M.fallback_count()
+    assert n_fb > 0, "the scenario no longer reaches S < 1: pick a smaller population"
+    off, pad, _ = M.eval_detail(theta)
+    ref = oracle.evaluate("age2q", ds, theta, 300, 4, n_threads=8)
+    mism = (off != ref["offset"]) | (pad != ref["padding"]) | (status != ref["status"])
+    assert mism.sum() <= 2, int(mism.sum())
+    ok = ~mism
+    cond = oracle_conditioning(oracle, "age2q", ds, theta, 300, 4, ref["logl"])
+    within = logl_within_bar(logl[ok], ref["logl"][ok], cond[ok], TOL_LOGL)
+    assert within.mean() >= 0.98, (int((~within).sum()), int(ok.sum()))
+    monkeypatch.setenv("EPI_FORCE_R_FALLBACK", "1")
+    B = Model(ds, substeps=4)
+    lb, pb, sb = B.calclogpost_batch(theta)
+    assert B.fallback_count() == len(theta)
+    assert np.array_equal(logl, lb, equal_nan=True) and np.array_equal(status, sb)
+    M.close()
+    B.close()
