@@ -84,7 +84,7 @@ def test_r_shim_type_checks_against_the_header():
         assert m and len(m.group(1).split(",")) == int(arity), name
     # every .Call in the drop-in model files names a registered routine with that many arguments
     registered = dict(re.findall(r'\{"(C_\w+)", \(DL_FUNC\)&\w+, (\d+)\}', text))
-    for fn in ("model-age-groups2q-gpu.R", "model-age-groups2i-gpu.R"):
+    for fn in ("model-age-groups2q-gpu.R", "model-age-groups2i-gpu.R", "model-simple-ode-drj-cmp-gpu.R"):
         rsrc = open(os.path.join(ROOT, "r", fn)).read()
         for call in re.findall(r'\.Call\("(C_\w+)"', rsrc):
             assert call in registered, (fn, call)
