@@ -529,3 +529,26 @@ def test_tiny_population_exercises_the_r_fallback(oracle, monkeypatch):
     assert np.array_equal(logl, lb, equal_nan=True) and np.array_equal(status, sb)
     M.close()
     B.close()
+
+
+@pytest.mark.parametrize("name,m", [("A300", 3), ("A300", 8), ("I290", 3), ("S120", 3), ("NE120", 7), ("S365", 8)])
+def test_other_substep_counts(name, m, oracle):
+    """sub-step counts whose step 1/m is not a power of two (m = 3, 7: the sub-step boundaries are rounded) and a
+    finer grid (m = 8): same bar as the golden test — integer outputs exact, logl within the conditioning bar,
+    the model file's init strictly."""
+    from epi_mcmc_b200.model import Model, load_dataset
+    ds = load_dataset(name)
+    M = Model(ds, substeps=m)
+    theta = np.array(load_golden(name)["theta"])
+    logl, logp, status = M.calclogpost_batch(theta)
+    off, pad, _ = M.eval_detail(theta)
+    ref = oracle.evaluate(ds["flavour"], ds, theta, ds["period"], m, n_threads=8)
+    mism = (off != ref["offset"]) | (pad != ref["padding"]) | (status != ref["status"])
+    assert mism.sum() <= 1, int(mism.sum())
+    ok = ~mism
+    cond = oracle_conditioning(oracle, ds["flavour"], ds, theta, ds["period"], m, ref["logl"])
+    within = logl_within_bar(logl[ok], ref["logl"][ok], cond[ok], TOL_LOGL)
+    assert (~within).sum() <= 1, [(i, logl[ok][i], ref["logl"][ok][i], cond[ok][i]) for i in np.nonzero(~within)[0]]
+    assert rel_err(logp, ref["logp"]).max() <= TOL_LOGP
+    assert rel_err(logl[:1] + logp[:1], ref["logl"][:1] + ref["logp"][:1]).max() <= TOL_LOGL
+    M.close()
