@@ -282,9 +282,10 @@ __device__ __forceinline__ constexpr bool is_r_state(int i) { return Traits<FL>:
 
 template <int FL, bool GUARDED, bool TRACKR, bool HOLD = false>
 __device__ __forceinline__ bool rk4_try(const DevModel &M, const Seg &sg, const double *y, double *ynew, double pa,
-                                        double pb, double inv0, double inv1, unsigned nb0, unsigned nb1, bool &need_r) {
+                                        double pb, double hh, double hh2, double h6, double inv0, double inv1,
+                                        unsigned nb0, unsigned nb1, bool &need_r) {
   constexpr int NEQ = Traits<FL>::NEQ;
-  const double hh = pb - pa, hh2 = 0.5 * hh, tm = pa + hh2;
+  const double tm = pa + hh2;
   double k[NEQ], acc[NEQ], yt[NEQ];
   unsigned flag = 0;
   rhs<FL, GUARDED, TRACKR, HOLD>(M, sg, pa, y, k, inv0, inv1, nb0, nb1, flag);
@@ -306,7 +307,6 @@ __device__ __forceinline__ bool rk4_try(const DevModel &M, const Seg &sg, const 
     acc[i] = fma(2.0, k[i], acc[i]); yt[i] = fma(hh, k[i], y[i]);
   }
   rhs<FL, GUARDED, TRACKR, HOLD>(M, sg, pb, yt, k, inv0, inv1, nb0, nb1, flag);
-  const double h6 = hh / 6.0;
 #pragma unroll
   for (int i = 0; i < NEQ; ++i) {
     if (!TRACKR && is_r_state<FL>(i)) { ynew[i] = 0.0; continue; }
@@ -321,16 +321,19 @@ __device__ __forceinline__ bool rk4_try(const DevModel &M, const Seg &sg, const 
 
 template <int FL, bool TRACKR>
 __device__ __forceinline__ void rk4_piece(const DevModel &M, const Seg &sg, double *y, double pa, double pb,
-                                          double inv0, double inv1, unsigned nb0, unsigned nb1, bool &need_r) {
+                                          double hh, double hh2, double h6, double inv0, double inv1, unsigned nb0,
+                                          unsigned nb1, bool &need_r) {
+  // hh = pb - pa, hh2 = hh / 2, h6 = hh / 6: constants of the kernel for a regular sub-step, computed by the caller
+  // for a piece that a breakpoint cut
   constexpr int NEQ = Traits<FL>::NEQ;
   double yn[NEQ];
   bool ok = false;
   if (sg.fast_ok)
-    ok = sg.hold ? rk4_try<FL, false, TRACKR, true>(M, sg, y, yn, pa, pb, inv0, inv1, nb0, nb1, need_r)
-                 : rk4_try<FL, false, TRACKR, false>(M, sg, y, yn, pa, pb, inv0, inv1, nb0, nb1, need_r);
+    ok = sg.hold ? rk4_try<FL, false, TRACKR, true>(M, sg, y, yn, pa, pb, hh, hh2, h6, inv0, inv1, nb0, nb1, need_r)
+                 : rk4_try<FL, false, TRACKR, false>(M, sg, y, yn, pa, pb, hh, hh2, h6, inv0, inv1, nb0, nb1, need_r);
   if (!ok) {
     // rare: redo the step with the reference's guard evaluated exactly in FP64
-    rk4_try<FL, true, TRACKR>(M, sg, y, yn, pa, pb, inv0, inv1, 0u, 0u, need_r);
+    rk4_try<FL, true, TRACKR>(M, sg, y, yn, pa, pb, hh, hh2, h6, inv0, inv1, 0u, 0u, need_r);
   }
 #pragma unroll
   for (int i = 0; i < NEQ; ++i) y[i] = yn[i];
@@ -627,21 +630,35 @@ k_ode(const DevModel M, const double *__restrict__ theta, int64_t ld, int64_t n,
         if (TR || !is_r_state<FL>(q)) ck[q * kTile] = y[q];
     }
   }
+  // a regular sub-step has hh = h exactly when 1/m is a power of two (m = 1, 2, 4, 8, ...: tday + s*h is then exact
+  // too): its hh, hh/2 and hh/6 are constants of the kernel and the sub-step boundaries follow by addition.  A day
+  // takes that route when no breakpoint falls inside it; otherwise (and for other m) every piece computes them.
+  const bool pow2 = (m & (m - 1)) == 0;
+  const double hh2reg = 0.5 * h, h6reg = h / 6.0;
   for (int d = d0 + 1; d < nint; ++d) {
     const double tday = (double)(t0 + d - 1);
-    for (int s = 0; s < m; ++s) {
-      const double a = tday + (double)s * h;
-      const double b = (s == m - 1) ? tday + 1.0 : tday + (double)(s + 1) * h;
-      double pa = a;
-      if constexpr (PASS2) {
-        if (a >= tcut) sg = select_segment<FL>(M, th, ld, bp, nbp, a, &tcut, inv0, inv1);
-        while (tcut < b) {
-          rk4_piece<FL, TR>(M, sg, y, pa, tcut, inv0, inv1, nb0, nb1, need_r);
-          pa = tcut;
-          sg = select_segment<FL>(M, th, ld, bp, nbp, pa, &tcut, inv0, inv1);
+    const bool regular = pow2 && tcut >= tday + 1.0;
+    double pa = tday;
+    int s = 0;
+    while (s < m) {
+      double pb, hh, hh2, h6;
+      bool step_done = true;
+      if (regular) {
+        pb = pa + h; hh = h; hh2 = hh2reg; h6 = h6reg;
+      } else {
+        const double b = (s == m - 1) ? tday + 1.0 : tday + (double)(s + 1) * h;
+        if constexpr (PASS2) {
+          if (pa >= tcut) sg = select_segment<FL>(M, th, ld, bp, nbp, pa, &tcut, inv0, inv1);
         }
+        pb = b;
+        if constexpr (PASS2) {
+          if (tcut < b) { pb = tcut; step_done = false; }  // a breakpoint strictly inside (pa, b): cut there
+        }
+        hh = pb - pa; hh2 = 0.5 * hh; h6 = hh / 6.0;
       }
-      rk4_piece<FL, TR>(M, sg, y, pa, b, inv0, inv1, nb0, nb1, need_r);
+      rk4_piece<FL, TR>(M, sg, y, pa, pb, hh, hh2, h6, inv0, inv1, nb0, nb1, need_r);
+      pa = pb;
+      if (step_done) ++s;
     }
     out[d] = y[0];
     if constexpr (NG == 2) out[pitch + d] = y[5];
