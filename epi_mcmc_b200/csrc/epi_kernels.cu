@@ -319,14 +319,12 @@ __device__ __forceinline__ bool rk4_try(const DevModel &M, const Seg &sg, const 
   return (int)flag >= 0;  // no stage raised the maybe-out-of-bounds bit
 }
 
+// one RK4 step from y to yn (distinct arrays).  hh = pb - pa, hh2 = hh / 2, h6 = hh / 6: constants of the kernel for a
+// regular sub-step, computed by the caller for a piece that a breakpoint cut
 template <int FL, bool TRACKR>
-__device__ __forceinline__ void rk4_piece(const DevModel &M, const Seg &sg, double *y, double pa, double pb,
-                                          double hh, double hh2, double h6, double inv0, double inv1, unsigned nb0,
-                                          unsigned nb1, bool &need_r) {
-  // hh = pb - pa, hh2 = hh / 2, h6 = hh / 6: constants of the kernel for a regular sub-step, computed by the caller
-  // for a piece that a breakpoint cut
-  constexpr int NEQ = Traits<FL>::NEQ;
-  double yn[NEQ];
+__device__ __forceinline__ void rk4_step(const DevModel &M, const Seg &sg, const double *y, double *yn, double pa,
+                                         double pb, double hh, double hh2, double h6, double inv0, double inv1,
+                                         unsigned nb0, unsigned nb1, bool &need_r) {
   bool ok = false;
   if (sg.fast_ok)
     ok = sg.hold ? rk4_try<FL, false, TRACKR, true>(M, sg, y, yn, pa, pb, hh, hh2, h6, inv0, inv1, nb0, nb1, need_r)
@@ -335,6 +333,15 @@ __device__ __forceinline__ void rk4_piece(const DevModel &M, const Seg &sg, doub
     // rare: redo the step with the reference's guard evaluated exactly in FP64
     rk4_try<FL, true, TRACKR>(M, sg, y, yn, pa, pb, hh, hh2, h6, inv0, inv1, 0u, 0u, need_r);
   }
+}
+
+template <int FL, bool TRACKR>
+__device__ __forceinline__ void rk4_piece(const DevModel &M, const Seg &sg, double *y, double pa, double pb,
+                                          double hh, double hh2, double h6, double inv0, double inv1, unsigned nb0,
+                                          unsigned nb1, bool &need_r) {
+  constexpr int NEQ = Traits<FL>::NEQ;
+  double yn[NEQ];
+  rk4_step<FL, TRACKR>(M, sg, y, yn, pa, pb, hh, hh2, h6, inv0, inv1, nb0, nb1, need_r);
 #pragma unroll
   for (int i = 0; i < NEQ; ++i) y[i] = yn[i];
 }
@@ -640,6 +647,16 @@ k_ode(const DevModel M, const double *__restrict__ theta, int64_t ld, int64_t n,
     const bool regular = pow2 && tcut >= tday + 1.0;
     double pa = tday;
     int s = 0;
+    if (regular && (m & 1) == 0) {
+      // sub-steps in pairs, ping-pong between two state arrays: no copy of the new state back into the old one
+      double z[NEQ];
+      for (; s < m; s += 2) {
+        const double pm = pa + h, pb = pm + h;
+        rk4_step<FL, TR>(M, sg, y, z, pa, pm, h, hh2reg, h6reg, inv0, inv1, nb0, nb1, need_r);
+        rk4_step<FL, TR>(M, sg, z, y, pm, pb, h, hh2reg, h6reg, inv0, inv1, nb0, nb1, need_r);
+        pa = pb;
+      }
+    }
     while (s < m) {
       double pb, hh, hh2, h6;
       bool step_done = true;
