@@ -32,10 +32,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 # DRAM bytes per launch of each kernel (read + write) from the committed ncu --set full capture of
-# this exact workload (profiles/r1_v13_ncu_full.txt); only reported when the run matches that workload
-NCU_TRAFFIC = {"ode_pass1": 291.5e6, "profiles_threshold": 301.0e6, "ode_pass2": 478.2e6, "score": 616.8e6}
+# this exact workload (profiles/r1_v14_ncu_full.txt); only reported when the run matches that workload
+NCU_TRAFFIC = {"ode_pass1": 293.5e6, "profiles_threshold": 301.3e6, "ode_pass2": 459.1e6, "score": 619.0e6}
 # sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active of the same capture
-NCU_FP64_PIPE_PCT = {"ode_pass1": 51.8, "profiles_threshold": 62.5, "ode_pass2": 47.2, "score": 29.8}
+NCU_FP64_PIPE_PCT = {"ode_pass1": 51.6, "profiles_threshold": 62.5, "ode_pass2": 49.5, "score": 29.9}
 NCU_WORKLOAD = ("A300", 65536, 4)
 
 METRIC = "log_posterior_evals_per_s"
@@ -452,7 +452,7 @@ def main():
                                     "nominal 37.2 TFLOP/s = 148 SM x 64 DFMA/clk x 2 x 1.965 GHz)",
                      "algorithmic_flop_per_launch": per_kernel[dom]["algorithmic_flop_per_launch"],
                      "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, "
-                                       "profiles/r1_v13_ncu_full.txt (65,536 chains, A300)"},
+                                       "profiles/r1_v14_ncu_full.txt (65,536 chains, A300)"},
         "roofline_all": per_kernel,
         "f_alg": {"per_eval": fa["total"], "per_eval_executed": fa["total_executed"],
                   "pass2_restart_days_mean": d_mean, "pass2_days_integrated_mean": days_pass2,
