@@ -40,11 +40,15 @@ for r in rows[2:]:
     print("   stall samples: " + ", ".join(f"{n} {100 * v / tot:.1f}%" for v, n in sorted(items, reverse=True)[:8] if tot))
     print()
 rows = list(csv.reader(io.StringIO(src)))
-kern, data, h2 = None, collections.OrderedDict(), None
+kern, data, h2, nsec = None, collections.OrderedDict(), None, 0
 for r in rows:
     if r and r[0] == "Kernel Name":
-        kern = r[1]
-        data.setdefault(kern, [])
+        # the page prints every launch twice (two views of the same table): keep the first of each pair, so the
+        # totals equal smsp__inst_executed.sum above
+        kern = r[1] if nsec % 2 == 0 else None
+        nsec += 1
+        if kern:
+            data.setdefault(kern, [])
         continue
     if r and r[0] == "Address":
         h2 = r
