@@ -552,3 +552,41 @@ def test_other_substep_counts(name, m, oracle):
     assert rel_err(logp, ref["logp"]).max() <= TOL_LOGP
     assert rel_err(logl[:1] + logp[:1], ref["logl"][:1] + ref["logp"][:1]).max() <= TOL_LOGL
     M.close()
+
+
+def _box_jitter(M, n, seed, width):
+    rng = np.random.default_rng(seed)
+    mn, mx, init = M.df_params["min"], M.df_params["max"], M.df_params["init"]
+    return np.clip(init + (rng.uniform(size=(n, M.d)) - 0.5) * width * (mx - mn), mn, mx)
+
+
+@pytest.mark.parametrize("name,n,m", [("A300", 65536, 4), ("S365", 1 << 20, 4), ("NE120", 4096, 4)])
+def test_full_size_properties(name, n, m, oracle):
+    """BASELINE.json's full sizes (65,536 age chains; 2^20 simple proposals over 365 days; 4,096 Ne chains), checked
+    through size-independent properties: (1) a proposal's result does not depend on where in the batch it sits or
+    how big the batch is — the whole batch reversed, and slices of 4,099 (not a multiple of any tile), reproduce the
+    same bits; (2) duplicated proposals give duplicated bits; (3) a seeded sample of 192 chains of the big batch
+    meets the oracle bar."""
+    M = _model(name, m)
+    theta = _box_jitter(M, n, 11, 0.2)
+    theta[n // 2:n // 2 + 64] = theta[:64]                         # (2)
+    l, p, s = M.calclogpost_batch(theta)
+    assert np.array_equal(l[n // 2:n // 2 + 64], l[:64], equal_nan=True) and np.array_equal(p[n // 2:n // 2 + 64], p[:64])
+    lr, pr, sr = M.calclogpost_batch(theta[::-1].copy())           # (1) position
+    assert np.array_equal(lr[::-1], l, equal_nan=True) and np.array_equal(pr[::-1], p) and np.array_equal(sr[::-1], s)
+    step = 4099
+    for a in range(0, min(n, 8 * step), step):                     # (1) batch size: the pair kernel / thread kernel switch
+        ls, ps, ss = M.calclogpost_batch(theta[a:a + step])
+        assert np.array_equal(ls, l[a:a + step], equal_nan=True) and np.array_equal(ps, p[a:a + step])
+        assert np.array_equal(ss, s[a:a + step])
+    pick = np.random.default_rng(5).choice(n, 192, replace=False)  # (3)
+    ds, P = M.data, M.data["period"]
+    o = oracle.evaluate(M.flavour, ds, theta[pick], P, m, n_threads=8)
+    same = s[pick] == o["status"]                                  # a threshold touched within rounding: <= 1 (see above)
+    assert (~same).sum() <= 1
+    assert np.all(rel_err(p[pick], o["logp"]) <= TOL_LOGP)
+    cond = oracle_conditioning(oracle, M.flavour, ds, theta[pick], P, m, o["logl"])
+    ok = logl_within_bar(l[pick], o["logl"], cond, TOL_LOGL) | ~same
+    assert ok.all(), (np.flatnonzero(~ok), l[pick][~ok], o["logl"][~ok])
+    assert (s[pick] == 0).sum() > 96
+    M.close()
