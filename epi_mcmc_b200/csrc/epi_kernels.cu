@@ -326,9 +326,14 @@ __device__ __forceinline__ void rk4_step(const DevModel &M, const Seg &sg, const
                                          double pb, double hh, double hh2, double h6, double inv0, double inv1,
                                          unsigned nb0, unsigned nb1, bool &need_r) {
   bool ok = false;
-  if (sg.fast_ok)
-    ok = sg.hold ? rk4_try<FL, false, TRACKR, true>(M, sg, y, yn, pa, pb, hh, hh2, h6, inv0, inv1, nb0, nb1, need_r)
+  // the hold instance only saves the three beta(t) fmas (fma(dt, 0, b) == b exactly), so a warp whose lanes sit in
+  // segments of both kinds — chains of a sampler cross their breakpoints on different days — takes the general
+  // instance together instead of running the two one after the other
+  if (sg.fast_ok) {
+    const bool hold = __all_sync(__activemask(), sg.hold);
+    ok = hold ? rk4_try<FL, false, TRACKR, true>(M, sg, y, yn, pa, pb, hh, hh2, h6, inv0, inv1, nb0, nb1, need_r)
                  : rk4_try<FL, false, TRACKR, false>(M, sg, y, yn, pa, pb, hh, hh2, h6, inv0, inv1, nb0, nb1, need_r);
+  }
   if (!ok) {
     // rare: redo the step with the reference's guard evaluated exactly in FP64
     rk4_try<FL, true, TRACKR>(M, sg, y, yn, pa, pb, hh, hh2, h6, inv0, inv1, 0u, 0u, need_r);
@@ -640,11 +645,15 @@ k_ode(const DevModel M, const double *__restrict__ theta, int64_t ld, int64_t n,
   // a regular sub-step has hh = h exactly when 1/m is a power of two (m = 1, 2, 4, 8, ...: tday + s*h is then exact
   // too): its hh, hh/2 and hh/6 are constants of the kernel and the sub-step boundaries follow by addition.  A day
   // takes that route when no breakpoint falls inside it; otherwise (and for other m) every piece computes them.
+  // Both routes give a regular day the same bits, so the choice is made per WARP: a day that a breakpoint cuts in
+  // one lane takes every converged lane through the general loop (4 or 5 pieces) instead of serialising the two
+  // routes (4 + 5) — chains of a running sampler have their breakpoints on different days (tests/_samp_overhead.py:
+  // pass 2 on a DE-MC population 1.29 ms against 0.91 ms on the bench's narrow theta cloud before this vote).
   const bool pow2 = (m & (m - 1)) == 0;
   const double hh2reg = 0.5 * h, h6reg = h / 6.0;
   for (int d = d0 + 1; d < nint; ++d) {
     const double tday = (double)(t0 + d - 1);
-    const bool regular = pow2 && tcut >= tday + 1.0;
+    const bool regular = pow2 && __all_sync(__activemask(), tcut >= tday + 1.0);
     double pa = tday;
     int s = 0;
     if (regular && (m & 1) == 0) {
