@@ -303,6 +303,49 @@ def main():
     M.set_timing(False)
     torch.cuda.synchronize(dev)
 
+    # ---- the same step on a posterior-spread cloud (secondary figure).  The headline cloud is narrow (+-0.5 % of the
+    # box around init), so the chains of a warp cross every schedule breakpoint on the same day; the population of a
+    # running sampler does not (its breakpoints are spread over days), which costs the ODE warps lock-step.  theta ~
+    # N(mean, cov) of a 65,536-chain DE-MC population after 4,000 iterations (tests/_pop_dump.py), clipped to the box.
+    cloud = None
+    gpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "epi_mcmc_b200", "datasets",
+                         f"{args.workload}_posterior_gauss.json")
+    if os.path.exists(gpath):
+        with open(gpath) as f:
+            g = json.load(f)
+        rng = np.random.default_rng(4321 + comm.rank)
+        th_c = np.clip(rng.multivariate_normal(np.array(g["mean"]), np.array(g["cov"]), size=n), mn, mx)
+        th_dev_head = th_dev
+        th_dev = torch.from_numpy(np.ascontiguousarray(th_c.T)).to(f"cuda:{dev}")
+        for _ in range(args.warmup):
+            step()
+        torch.cuda.synchronize(dev)
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record(stream)
+        for _ in range(args.steps):
+            step()
+        c1.record(stream)
+        torch.cuda.synchronize(dev)
+        ms_c = comm.max_over_ranks(c0.elapsed_time(c1))
+        M.set_timing(True)
+        kc = np.zeros(4)
+        for _ in range(reps):
+            step()
+            kc += np.array(M.last_kernel_ms())
+        kc /= reps
+        M.set_timing(False)
+        torch.cuda.synchronize(dev)
+        cloud = {"value": comm.world * n * args.steps / (ms_c * 1e-3), "unit": UNIT, "ms_per_step": ms_c / args.steps,
+                 "kernels": {"ode_pass1_ms": float(kc[0]), "profiles_threshold_ms": float(kc[1]),
+                             "ode_pass2_ms": float(kc[2]), "score_ms": float(kc[3])},
+                 "status_nonzero": int((status != 0).sum().item()),
+                 "theta": "N(mean, cov) of a 65,536-chain DE-MC population after 4,000 iterations, clipped to the box "
+                          "(epi_mcmc_b200/datasets/%s_posterior_gauss.json): breakpoints differ by days between the "
+                          "chains of a warp" % args.workload}
+        th_dev = th_dev_head
+        step()                      # logl / logp / status hold the headline batch again for the checks below
+        torch.cuda.synchronize(dev)
+
     # ---- e2e arm: the public C-ABI with pinned HOST buffers, copies inside the timed region.
     # (a) epi_eval: one blocking call per step (H2D -> kernels -> D2H strictly in sequence);
     # (b) epi_eval_submit / epi_eval_wait: the same step, double-buffered — step k+1 is submitted before
@@ -462,6 +505,7 @@ def main():
                      "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, "
                                        "profiles/r1_v14_ncu_full.txt (65,536 chains, A300)"},
         "roofline_all": per_kernel,
+        "posterior_cloud": cloud,
         "f_alg": {"per_eval": fa["total"], "per_eval_executed": fa["total_executed"],
                   "pass2_restart_days_mean": d_mean, "pass2_days_integrated_mean": days_pass2,
                   "score_days_swept_mean": days_swept, "pass1_days_integrated_mean": days_pass1, "period": P_, "ode_share": fa["ode"] / fa["total"],
