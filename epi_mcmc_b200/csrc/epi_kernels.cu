@@ -397,13 +397,22 @@ template <int FL>
 // beta_yo / N_y; simple: beta / N or beta / Ne), so that the RHS needs no I / N products.
 __device__ __noinline__ Seg select_segment(const DevModel &M, const double *__restrict__ th, int64_t ld,
                                            const double *bp, int nbp, double pa, double *tcut, double inv0,
-                                           double inv1) {
+                                           double inv1, int *kcur, bool sorted) {
   int k = -1;
   double tc = INFINITY;
-  for (int i = 0; i < nbp; ++i) {
-    if (bp[i] <= pa) k = i;
-    if (bp[i] > pa && bp[i] < tc) tc = bp[i];
+  if (sorted && *kcur >= -1) {
+    // breakpoints in index order are in time order (the usual case, checked once per chain) and the segment
+    // before this cut is known: the scan below reduces to stepping over the breakpoints just passed
+    k = *kcur;
+    while (k + 1 < nbp && bp[k + 1] <= pa) ++k;
+    if (k + 1 < nbp) tc = bp[k + 1];
+  } else {
+    for (int i = 0; i < nbp; ++i) {
+      if (bp[i] <= pa) k = i;
+      if (bp[i] > pa && bp[i] < tc) tc = bp[i];
+    }
   }
+  *kcur = k;
   *tcut = tc;
   Seg sg;
   if constexpr (Traits<FL>::kAge) {
@@ -626,7 +635,10 @@ k_ode(const DevModel M, const double *__restrict__ theta, int64_t ld, int64_t n,
       }
     }
   }
-  Seg sg = select_segment<FL>(M, th, ld, bp, nbp, (double)(t0 + d0), &tcut, inv0, inv1);
+  bool bp_sorted = true;  // (NaN breakpoints compare false: the full scan handles them as before)
+  for (int k = 1; k < nbp; ++k) bp_sorted = bp_sorted && bp[k - 1] <= bp[k];
+  int kseg = -2;          // segment index not known yet
+  Seg sg = select_segment<FL>(M, th, ld, bp, nbp, (double)(t0 + d0), &tcut, inv0, inv1, &kseg, bp_sorted);
 
   const int m = M.m;
   const double h = 1.0 / (double)m;
@@ -674,7 +686,7 @@ k_ode(const DevModel M, const double *__restrict__ theta, int64_t ld, int64_t n,
       } else {
         const double b = (s == m - 1) ? tday + 1.0 : tday + (double)(s + 1) * h;
         if constexpr (PASS2) {
-          if (pa >= tcut) sg = select_segment<FL>(M, th, ld, bp, nbp, pa, &tcut, inv0, inv1);
+          if (pa >= tcut) sg = select_segment<FL>(M, th, ld, bp, nbp, pa, &tcut, inv0, inv1, &kseg, bp_sorted);
         }
         pb = b;
         if constexpr (PASS2) {
