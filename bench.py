@@ -32,15 +32,15 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 # DRAM bytes per launch of each kernel (read + write) from the committed ncu --set full capture of
-# this exact workload (profiles/r1_v14_ncu_full.txt); only reported when the run matches that workload
-NCU_TRAFFIC = {"ode_pass1": 293.5e6, "profiles_threshold": 301.3e6, "ode_pass2": 459.1e6, "score": 619.0e6}
+# this exact workload (profiles/r1_v15_ncu_full.txt); only reported when the run matches that workload
+NCU_TRAFFIC = {"ode_pass1": 296.4e6, "profiles_threshold": 301.0e6, "ode_pass2": 467.4e6, "score": 617.1e6}
 # sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active of the same capture
-NCU_FP64_PIPE_PCT = {"ode_pass1": 51.6, "profiles_threshold": 62.5, "ode_pass2": 49.5, "score": 29.9}
+NCU_FP64_PIPE_PCT = {"ode_pass1": 50.6, "profiles_threshold": 62.5, "ode_pass2": 47.9, "score": 29.9}
 # FP64 flop actually EXECUTED per launch in the same capture: thread-level predicated-on DFMA x 2 + DMUL + DADD from the
 # report's SASS table.  SURVEY 8d counts the reference's arithmetic (bounds-guard comparisons, the output variables
 # Re/Rt, the removed compartment, per-call segment selection ...): the ODE kernels execute about a third of that, which
 # is why their algorithmic `frac` exceeds 1 — the pipe utilisation above and this figure are the honest bound for them
-NCU_EXECUTED_FLOP = {"ode_pass1": 2.749e9, "profiles_threshold": 4.985e9, "ode_pass2": 12.443e9, "score": 11.311e9}
+NCU_EXECUTED_FLOP = {"ode_pass1": 2.749e9, "profiles_threshold": 4.985e9, "ode_pass2": 12.512e9, "score": 11.311e9}
 NCU_WORKLOAD = ("A300", 65536, 4)
 
 METRIC = "log_posterior_evals_per_s"
@@ -503,7 +503,7 @@ def main():
                                     "nominal 37.2 TFLOP/s = 148 SM x 64 DFMA/clk x 2 x 1.965 GHz)",
                      "algorithmic_flop_per_launch": per_kernel[dom]["algorithmic_flop_per_launch"],
                      "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, "
-                                       "profiles/r1_v14_ncu_full.txt (65,536 chains, A300)"},
+                                       "profiles/r1_v15_ncu_full.txt (65,536 chains, A300)"},
         "roofline_all": per_kernel,
         "posterior_cloud": cloud,
         "f_alg": {"per_eval": fa["total"], "per_eval_executed": fa["total_executed"],

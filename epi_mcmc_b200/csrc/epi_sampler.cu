@@ -83,6 +83,7 @@ __device__ inline void box_muller(uint32_t a, uint32_t b, double &z0, double &z1
 __device__ inline double reflect(double x, double lo, double hi) {
   const double w = hi - lo;
   if (!(w > 0)) return lo;
+  if (x >= lo && x <= hi) return x;  // the usual case: nothing to fold (and no fmod)
   double y = fmod(x - lo, 2.0 * w);
   if (y < 0) y += 2.0 * w;
   if (y > w) y = 2.0 * w - y;
@@ -186,6 +187,33 @@ k_accept_propose(int d, int64_t n, int64_t ld, int kind, uint64_t seed, int64_t 
     }
   }
   if (z1) gam = hop ? 1.0 : umix * step * 2.38 / sqrt(2.0 * dsel);
+  if (z1) {
+    // DE-MC: x + gamma (z1 - z2) + e, e ~ N(0, (de_eps * population sd)^2), on the chosen coordinates; the others
+    // keep their value bit for bit.  The normals of a group of four coordinates (one Philox call, as in the RWM
+    // branch below) are only generated when one of the four moves: with CR = 0.1 most groups do not.
+    for (int p0 = 0; p0 < d; p0 += 4) {
+      double z[4] = {0.0, 0.0, 0.0, 0.0};
+      if ((unsigned)(sel >> p0) & 0xFu) {
+        philox4x32_10((uint32_t)cid, (uint32_t)(cid >> 32), it1, USE_NORMAL + (uint32_t)(p0 >> 2), k0, k1, r);
+        box_muller(r[0], r[1], z[0], z[1]);
+        box_muller(r[2], r[3], z[2], z[3]);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int p = p0 + q;
+        if (p >= d) break;
+        const double x = cur[(int64_t)p * ld + i];
+        double y = x;
+        if ((sel >> p) & 1ull) {
+          const double lo = box_min[p], hi = box_max[p];
+          const double w = psd ? psd[p] : (hi - lo);
+          y = reflect(x + gam * (z1[(int64_t)p * pop_ld] - z2[(int64_t)p * pop_ld]) + de_eps * w * z[q], lo, hi);
+        }
+        prop[(int64_t)p * ld + i] = y;
+      }
+    }
+    return;
+  }
   double zn[EPI_MAX_PARAMS];
   for (int p0 = 0; p0 < d; p0 += 4) {
     philox4x32_10((uint32_t)cid, (uint32_t)(cid >> 32), it1, USE_NORMAL + (uint32_t)(p0 >> 2), k0, k1, r);
@@ -197,11 +225,7 @@ k_accept_propose(int d, int64_t n, int64_t ld, int kind, uint64_t seed, int64_t 
     const double lo = box_min[p], hi = box_max[p];
     const double x = cur[(int64_t)p * ld + i];
     double y;
-    if (z1) {
-      // DE-MC: x + gamma (z1 - z2) + e, e ~ N(0, (de_eps * population sd)^2), on the chosen coordinates
-      const double w = psd ? psd[p] : (hi - lo);
-      y = ((sel >> p) & 1ull) ? x + gam * (z1[(int64_t)p * pop_ld] - z2[(int64_t)p * pop_ld]) + de_eps * w * zn[p] : x;
-    } else if (chol) {
+    if (chol) {
       // RWM with the population covariance: x + step * 2.38/sqrt(d) * L z  (adaptive Metropolis shape,
       // measured during burn-in only)
       double a = 0.0;
