@@ -8,5 +8,5 @@ for f in epi_kernels epi_capi epi_sampler; do
   $NVCC $FLAGS -c $f.cu -o $f.o &
 done
 wait
-$NVCC -shared -o libepimcmc.so epi_kernels.o epi_capi.o epi_sampler.o -cudart static
+$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o libepimcmc.so epi_kernels.o epi_capi.o epi_sampler.o -cudart static
 echo "built $(pwd)/libepimcmc.so"
