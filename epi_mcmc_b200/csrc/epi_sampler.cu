@@ -119,6 +119,9 @@ k_accept_propose(int d, int64_t n, int64_t ld, int kind, uint64_t seed, int64_t 
     const bool cur_ok = isfinite(cur_post);
     accepted = new_ok && (!cur_ok || log(u01(r[0])) < new_post - cur_post);
     if (accepted) {
+      // (unrolled: with a run-time trip count every load -> store pair waited out its own L2 round trip; ncu,
+      // prof_ap: 71 % of this kernel's stall samples were long-scoreboard at 3.5 warps per scheduler)
+#pragma unroll 8
       for (int p = 0; p < d; ++p) cur[(int64_t)p * ld + i] = prop[(int64_t)p * ld + i];
       logl[i] = ll1;
       logp[i] = lp1;
@@ -133,6 +136,7 @@ k_accept_propose(int d, int64_t n, int64_t ld, int kind, uint64_t seed, int64_t 
   }
   if (!live) return;
   if (draw_out) {
+#pragma unroll 8
     for (int p = 0; p < d; ++p) draw_out[(int64_t)p * ld + i] = cur[(int64_t)p * ld + i];
     draw_lp[i] = logl[i] + logp[i];
   }
@@ -192,8 +196,20 @@ k_accept_propose(int d, int64_t n, int64_t ld, int kind, uint64_t seed, int64_t 
     // keep their value bit for bit.  The normals of a group of four coordinates (one Philox call, as in the RWM
     // branch below) are only generated when one of the four moves: with CR = 0.1 most groups do not.
     for (int p0 = 0; p0 < d; p0 += 4) {
+      // the loads of the group first (current values, and the two partners' values of the moving coordinates), so
+      // that they are in flight together while the normals are generated
+      const unsigned g = (unsigned)(sel >> p0) & 0xFu;
+      double x[4], dz[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) x[q] = (p0 + q < d) ? cur[(int64_t)(p0 + q) * ld + i] : 0.0;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const bool mv = ((g >> q) & 1u) && p0 + q < d;
+        const double a = mv ? z1[(int64_t)(p0 + q) * pop_ld] : 0.0, b = mv ? z2[(int64_t)(p0 + q) * pop_ld] : 0.0;
+        dz[q] = a - b;
+      }
       double z[4] = {0.0, 0.0, 0.0, 0.0};
-      if ((unsigned)(sel >> p0) & 0xFu) {
+      if (g) {
         philox4x32_10((uint32_t)cid, (uint32_t)(cid >> 32), it1, USE_NORMAL + (uint32_t)(p0 >> 2), k0, k1, r);
         box_muller(r[0], r[1], z[0], z[1]);
         box_muller(r[2], r[3], z[2], z[3]);
@@ -202,12 +218,11 @@ k_accept_propose(int d, int64_t n, int64_t ld, int kind, uint64_t seed, int64_t 
       for (int q = 0; q < 4; ++q) {
         const int p = p0 + q;
         if (p >= d) break;
-        const double x = cur[(int64_t)p * ld + i];
-        double y = x;
-        if ((sel >> p) & 1ull) {
+        double y = x[q];
+        if ((g >> q) & 1u) {
           const double lo = box_min[p], hi = box_max[p];
           const double w = psd ? psd[p] : (hi - lo);
-          y = reflect(x + gam * (z1[(int64_t)p * pop_ld] - z2[(int64_t)p * pop_ld]) + de_eps * w * z[q], lo, hi);
+          y = reflect(x[q] + gam * dz[q] + de_eps * w * z[q], lo, hi);
         }
         prop[(int64_t)p * ld + i] = y;
       }
