@@ -230,19 +230,25 @@ def workload_name(args, period):
     return f"{args.workload}: {what}, synthetic {period}-day series, {args.chains} chains per GPU, RK4 m={args.substeps}"
 
 
+_REAL_STDOUT = 1
+
+
 def emit(line: dict):
     """the ONE JSON line of the contract, on the real stdout"""
     os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
 
 
-# Everything else any library prints to fd 1 (NCCL's version banner, for one) goes to stderr, so
-# that stdout carries exactly one JSON line.
-_REAL_STDOUT = os.dup(1)
-os.dup2(2, 1)
+def _claim_stdout():
+    """Everything else any library prints to fd 1 (NCCL's version banner, for one) goes to stderr, so that stdout
+    carries exactly one JSON line.  Done when the script RUNS, not on import (tests import this module)."""
+    global _REAL_STDOUT
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
 
 
 def main():
     args = parse()
+    _claim_stdout()
     if args.impl == "reference":
         run_reference(args)
         return
