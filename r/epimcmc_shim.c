@@ -17,6 +17,8 @@
  *   C_epi_trajectories-> epi_trajectories / epi_trajectories_ext   calculateModel(params, period) for many draws
  *   C_epi_quantiles   -> epi_quantiles   quantileData (libMCMC.R:151-172)
  *   C_epi_df_params   -> epi_df_params
+ *   C_epi_run_mcmc    -> epi_sampler_*   drjacoby::run_mcmc (fitMCMC-drj.R:48-57) for a population of chains
+ *                                        that stays on the GPU: burn-in, then recorded sampling draws
  * R is single-threaded and drjacoby calls back on the main thread, which is all the
  * handle's "one host thread at a time" rule needs.  Errors: the library never longjmps;
  * a nonzero return code is turned into Rf_error() AFTER every temporary is released.
@@ -172,12 +174,79 @@ SEXP C_epi_df_params(SEXP ptr) {
   return out;
 }
 
+/* .Call(C_epi_run_mcmc, handle, theta0, chains, burnin, samples, thin, rungs, GTI_pow, seed, kind): what
+ * fitMCMC-drj.R:48-57 asks of drjacoby::run_mcmc, for `chains` chains per rung on the device.
+ *   theta0: NULL (start at init + jitter) or a d x (chains * rungs) numeric matrix of starting points;
+ *   kind:   1 = DE-MC (population proposals), 0 = adaptive random-walk Metropolis;
+ *   rungs / GTI_pow: drjacoby's tempering ladder (1 = no tempering); draws are the COLD rung's.
+ * Burn-in adapts the proposal shape from the population and refreshes the DE-MC partner snapshot every 10
+ * iterations; both are frozen for the sampling phase.  Returns list(draws = d x chains x kept array,
+ * logpost = chains x kept matrix, accept_rate, evals). */
+SEXP C_epi_run_mcmc(SEXP ptr, SEXP theta0, SEXP chains, SEXP burnin, SEXP samples, SEXP thin, SEXP rungs, SEXP gti_pow,
+                    SEXP seed, SEXP kind) {
+  epi_handle *h = get_handle(ptr);
+  const int d = epi_n_params(h), cpr = Rf_asInteger(chains), nr = Rf_asInteger(rungs) > 1 ? Rf_asInteger(rungs) : 1;
+  const int n = cpr * nr, nburn = Rf_asInteger(burnin), nsamp = Rf_asInteger(samples);
+  const int th = Rf_asInteger(thin) > 0 ? Rf_asInteger(thin) : 1, keep = nsamp / th > 0 ? nsamp / th : 1;
+  if (cpr < 1 || nburn < 0 || nsamp < 1) Rf_error("epimcmc: chains >= 1, burnin >= 0, samples >= 1");
+  if (theta0 != R_NilValue && (!Rf_isReal(theta0) || XLENGTH(theta0) != (R_xlen_t)d * n))
+    Rf_error("epimcmc: theta0 must be NULL or a numeric %d x %d matrix", d, n);
+  epi_sampler_cfg cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.kind = Rf_asInteger(kind) ? EPI_SAMPLER_DEMC : EPI_SAMPLER_RWM;
+  cfg.n_chains = n;
+  cfg.seed = (uint64_t)Rf_asReal(seed);
+  cfg.scale = 1.0;
+  cfg.de_eps = 1e-4;
+  cfg.beta = 1.0;
+  cfg.n_rungs = nr;
+  cfg.gti_pow = Rf_asReal(gti_pow);
+  int rc = epi_sampler_init(h, &cfg, theta0 == R_NilValue ? NULL : REAL(theta0));
+  const int is_de = cfg.kind == EPI_SAMPLER_DEMC;
+  if (!rc) rc = epi_sampler_adapt(h, 1, 0.0);
+  for (int done = 0; !rc && done < nburn; done += 10) {
+    rc = epi_sampler_run(h, nburn - done < 10 ? nburn - done : 10);
+    if (!rc && is_de) rc = epi_sampler_set_population(h, NULL, 1, n, 0);
+    R_CheckUserInterrupt();
+  }
+  if (!rc) rc = epi_sampler_adapt(h, 0, 0.0);
+  if (!rc) rc = epi_sampler_record(h, th, keep);
+  for (int done = 0; !rc && done < nsamp; done += 10) {
+    rc = epi_sampler_run(h, nsamp - done < 10 ? nsamp - done : 10);
+    if (!rc && is_de) rc = epi_sampler_set_population(h, NULL, 1, n, 0);
+    R_CheckUserInterrupt();
+  }
+  if (rc) Rf_error("epi_sampler failed (%d): %s", rc, epi_last_error(h));
+  /* recorded draws of the cold rung = the LAST cpr chains, device layout kept x d x cpr */
+  int32_t kept = 0;
+  double *dr = (double *)R_alloc((size_t)keep * d * cpr, sizeof(double));
+  double *lp = (double *)R_alloc((size_t)keep * cpr, sizeof(double));
+  rc = epi_sampler_draws_subset(h, n - cpr, cpr, dr, lp, &kept);
+  int64_t it = 0, acc = 0, ev = 0;
+  if (!rc) rc = epi_sampler_stats(h, &it, &acc, &ev);
+  if (rc) Rf_error("epi_sampler_draws failed (%d): %s", rc, epi_last_error(h));
+  SEXP draws = PROTECT(Rf_alloc3DArray(REALSXP, d, cpr, kept)), logpost = PROTECT(Rf_allocMatrix(REALSXP, cpr, kept));
+  for (int k = 0; k < kept; ++k)
+    for (int p = 0; p < d; ++p)
+      for (int c = 0; c < cpr; ++c)
+        REAL(draws)[p + (R_xlen_t)d * (c + (R_xlen_t)cpr * k)] = dr[((size_t)k * d + p) * cpr + c];
+  memcpy(REAL(logpost), lp, sizeof(double) * (size_t)kept * cpr);
+  SEXP out = PROTECT(Rf_allocVector(VECSXP, 4));
+  SET_VECTOR_ELT(out, 0, draws);
+  SET_VECTOR_ELT(out, 1, logpost);
+  SET_VECTOR_ELT(out, 2, Rf_ScalarReal(it > 0 ? (double)acc / ((double)it * n) : 0.0));
+  SET_VECTOR_ELT(out, 3, Rf_ScalarReal((double)ev));
+  UNPROTECT(3);
+  return out;
+}
+
 static const R_CallMethodDef call_methods[] = {
     {"C_epi_create", (DL_FUNC)&C_epi_create, 5},
     {"C_epi_logpost", (DL_FUNC)&C_epi_logpost, 2},
     {"C_epi_trajectories", (DL_FUNC)&C_epi_trajectories, 4},
     {"C_epi_quantiles", (DL_FUNC)&C_epi_quantiles, 7},
     {"C_epi_df_params", (DL_FUNC)&C_epi_df_params, 1},
+    {"C_epi_run_mcmc", (DL_FUNC)&C_epi_run_mcmc, 10},
     {NULL, NULL, 0}};
 
 void R_init_epimcmc_shim(DllInfo *dll) {

@@ -6,4 +6,5 @@
 #include <stddef.h>
 void Rf_error(const char *, ...) __attribute__((noreturn));
 char *R_alloc(size_t, int);
+void R_CheckUserInterrupt(void);
 #endif

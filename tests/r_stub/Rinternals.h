@@ -23,6 +23,8 @@ void SET_STRING_ELT(SEXP, R_xlen_t, SEXP);
 SEXP SET_VECTOR_ELT(SEXP, R_xlen_t, SEXP);
 SEXP Rf_allocVector(unsigned int, R_xlen_t);
 SEXP Rf_allocMatrix(unsigned int, int, int);
+SEXP Rf_alloc3DArray(unsigned int, int, int, int);
+SEXP Rf_ScalarReal(double);
 SEXP Rf_getAttrib(SEXP, SEXP);
 SEXP Rf_mkChar(const char *);
 int Rf_asInteger(SEXP);
