@@ -230,3 +230,86 @@ def test_invalid_offset_and_na_branches(oracle):
     assert r["offset"][0] == 10000 and r["status"][0] & 1 and np.isfinite(r["logl"][0])
     assert r["status"][1] & 2 and np.isnan(r["logl"][1])
     assert r["status"][2] & 16 and np.isnan(r["logl"][2])
+
+
+def test_ode_path_through_the_reference_binary(oracle):
+    """The whole pass-2 ODE path pinned to the reference's compiled code: the parms vector built the way
+    model-age-groups2q.R:193-207 builds it (position-coupled to the #defines of model-agen.cpp:7-51) is handed to
+    the reference's own derivs() (oracle/_ref/model-agen.so) and integrated with scipy LSODA at tight tolerances
+    from the R file's initial state; the oracle's calculateModel states (breakpoint-cut RK4, m = 8 and 16) must converge
+    to it at fourth order on every compartment and every day.  A wrong slot in parms, a wrong segment
+    kind or a wrong initial state shows up as an O(1) difference."""
+    from scipy import integrate
+    try:
+        ref = oracle.RefRHS()
+    except FileNotFoundError:
+        pytest.skip("oracle/_ref not built (reference tree absent)")
+    ds = ds_load("A300")
+    P = ds["period"]
+    for th in np.array(load_golden("A300")["theta"])[[0, 3, 5]]:
+        series, states, off, pad = oracle.trajectory("age2q", ds, th, P, 8)
+        states16 = oracle.trajectory("age2q", ds, th, P, 16)[1]
+        if off == 10000:
+            continue
+        p = lambda i: th[i - 1]   # 1-based like the R file (:52-99)
+        lo, ltp = ds["lockdown_offset"], ds["lockdown_transition_period"]
+        t2 = off + lo + ltp; t3 = t2 + p(24); t4 = t3 + p(25); t5 = off + ds["d5"]; t6 = t5 + p(32); t7 = t6 + p(36)
+        t8 = off + ds["d8"]; t9 = t8 + 7
+        gamma = oracle.lib().oracle_age_gamma()
+        b = {0: (p(1), p(2), p(3)), 1: (p(4), p(5), p(6)), 2: (p(7), p(8), p(9)), 3: (p(7), p(27), p(28)),
+             4: (p(26), p(27), p(28)), 5: (p(29), p(30), p(31)), 6: (p(33), p(34), p(35)), 7: (p(37), p(38), p(39)),
+             8: (p(37), p(38), p(39)), 9: (p(40) * p(37), p(41) * p(38), p(42) * p(39))}
+        parms = [ds["y_N"], ds["o_N"], 1 / 3, 1.0, gamma, off + lo + p(19), off + lo + max(p(19), 0), t2,
+                 *b[0], *b[1], *b[2]]
+        for k, tk in zip(range(3, 10), (t3, t4, t5, t6, t7, t8, t9)):
+            parms += [tk, *b[k]]
+        ref.init(np.array(parms))
+        Y0 = [ds["y_N"] - 1, 1, 0, 0, 0, ds["o_N"], 0, 0, 0, 0]
+        times = np.arange(pad + 1, pad + P + 1, dtype=float)
+        sol = integrate.solve_ivp(lambda t, y: ref.derivs(t, y)[0], (times[0], times[-1]), Y0, method="LSODA",
+                                  t_eval=times, rtol=1e-12, atol=1e-9, max_step=0.1)
+        assert sol.success and sol.y.shape[1] == P
+        got = sol.y.T
+        # states: [day][Sy, E1y, E2y, Iy, Ry, So, E1o, E2o, Io, Ro]; persons below 1 compared absolutely
+        scale = np.maximum(np.abs(got), 1.0)
+        e8, e16 = ((np.abs(st - got) / scale).max() for st in (states, states16))
+        # fourth-order convergence TOWARDS the reference binary's solution: 16x per halving of the step
+        assert e8 < 1e-4 and e16 < 1e-5 and e16 < e8 / 8, (e8, e16)
+
+
+def test_ode_path_2i_through_the_reference_binary(oracle):
+    """Same for the secondary age model: parms as model-age-groups2i.R:176-191 builds them from params[1..36]
+    (:52-93), the reference's model-agef.so, fourth-order convergence of the oracle's states towards it."""
+    from scipy import integrate
+    try:
+        ref = oracle.RefRHS("model-agef", 37)
+    except FileNotFoundError:
+        pytest.skip("oracle/_ref not built (reference tree absent)")
+    ds = ds_load("I290")
+    P = ds["period"]
+    checked = 0
+    for th in np.array(load_golden("I290")["theta"])[:6]:
+        series, states, off, pad = oracle.trajectory("age2i", ds, th, P, 8)
+        if off == 10000:
+            continue
+        states16 = oracle.trajectory("age2i", ds, th, P, 16)[1]
+        p = lambda i: th[i - 1]
+        lo, ltp = ds["lockdown_offset"], ds["lockdown_transition_period"]
+        t2 = off + lo + ltp; t3 = t2 + p(25); t4 = t3 + p(26); t5 = off + ds["d5"]; t6 = t5 + p(30); t7 = off + ds["d7"]
+        b2, b4, b6 = (p(7), p(8), p(9)), (p(27), p(28), p(29)), (p(31), p(32), p(33))
+        b7 = (p(34) * p(31), p(36) * p(32), p(35) * p(33))     # (betay7, betao7, betayo7): note fo7 = params[36]
+        parms = [ds["y_N"], ds["o_N"], 1 / 3, 1.0, oracle.lib().oracle_age_gamma(), off + lo + p(21),
+                 off + lo + max(p(21), 0), t2, p(1), p(2), p(3), p(4), p(5), p(6), *b2,
+                 t3, *b2, t4, *b4, t5, *b4, t6, *b6, t7, *b7]
+        ref.init(np.array(parms))
+        Y0 = [ds["y_N"] - 1, 1, 0, 0, 0, ds["o_N"], 0, 0, 0, 0]
+        times = np.arange(pad + 1, pad + P + 1, dtype=float)
+        sol = integrate.solve_ivp(lambda t, y: ref.derivs(t, y)[0], (times[0], times[-1]), Y0, method="LSODA",
+                                  t_eval=times, rtol=1e-12, atol=1e-9, max_step=0.1)
+        assert sol.success and sol.y.shape[1] == P
+        got = sol.y.T
+        scale = np.maximum(np.abs(got), 1.0)
+        e8, e16 = ((np.abs(st - got) / scale).max() for st in (states, states16))
+        assert e8 < 1e-4 and e16 < 1e-5 and e16 < e8 / 8, (e8, e16)
+        checked += 1
+    assert checked >= 2
