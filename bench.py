@@ -483,6 +483,28 @@ def main():
                                            if ncu_match and peak_tf else None)}
     dom = knames[int(np.argmax(kms))]
     step_ms = ms / args.steps
+    # the HBM view of the same launches (why the bound is FP64 and not memory): ALGORITHMIC bytes per launch — what
+    # each kernel has to read and write once — against the measured copy bandwidth of MEASURED_PEAKS.json
+    hbm_peak, hbm_src = 6650.0, "fallback of B200_PROFILING.md (MEASURED_PEAKS.json absent)"
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "MEASURED_PEAKS.json")) as f:
+            hbm_peak, hbm_src = float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+    except (OSError, KeyError, ValueError):
+        pass
+    age = ds["flavour"] in ("age2q", "age2i")
+    NGb, NEQb, padb = (2, 8, 80 if ds["flavour"] == "age2i" else 64) if age else (1, 3, 64)
+    ck_days = min(P1_, 64)
+    row = lambda days: NGb * ((days + 1) & ~1) * 8
+    bytes_alg = {
+        "ode_pass1": d * 8 + row(P1_) + NEQb * ck_days * 8,                       # theta in; S rows + checkpoints out
+        "profiles_threshold": d * 8 + row(P1_) + NGb * padb * 4 * 8 + 6 * 8 + 12,  # theta, pass-1 S in; profile table, meta out
+        "ode_pass2": d * 8 + NEQb * 8 + row(min(int(d_mean) + 1, P1_)) + row(P_),  # theta, one checkpoint, head of pass-1 S in; S rows out
+        "score": d * 8 + row(P_) + NGb * padb * 4 * 8 + 20,                       # theta, S rows, profile table in; logl, logp, status out
+    }
+    for k, msk in zip(knames, kms):
+        gbs = bytes_alg[k] * n / (float(msk) * 1e-3) / 1e9
+        per_kernel[k]["hbm"] = {"algorithmic_bytes_per_launch": bytes_alg[k] * n, "achieved": gbs, "peak": hbm_peak,
+                                "unit": "GB/s", "frac": gbs / hbm_peak}
     whole_tf = fa["total_executed"] * n / (step_ms * 1e-3) / 1e12
 
     line = {
@@ -508,6 +530,7 @@ def main():
                      "peak_source": "measured live: DFMA-chain microbenchmark epi_fp64_peak (MEASURED_PEAKS.json has no FP64 entry; "
                                     "nominal 37.2 TFLOP/s = 148 SM x 64 DFMA/clk x 2 x 1.965 GHz)",
                      "algorithmic_flop_per_launch": per_kernel[dom]["algorithmic_flop_per_launch"],
+                     "hbm": dict(per_kernel[dom]["hbm"], peak_source=hbm_src),
                      "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, "
                                        "profiles/r1_v15_ncu_full.txt (65,536 chains, A300)"},
         "roofline_all": per_kernel,
