@@ -292,3 +292,44 @@ def test_global_scale_control():
         out.append(T.get()[0])
     assert np.array_equal(out[0], out[1])
     M.close()
+
+
+def test_the_r_shim_call_sequence():
+    """The exact C-ABI sequence r/epimcmc_shim.c::C_epi_run_mcmc issues (the shim cannot be built here: no R) —
+    init from a zeroed cfg with the shim's defaults, burn-in in chunks of 10 with the single-rank population
+    refresh, record, sampling, draws of the cold rung by epi_sampler_draws_subset — driven through ctypes."""
+    import ctypes as C
+    from epi_mcmc_b200 import _capi
+    from epi_mcmc_b200.model import Model, load_dataset
+    M = Model(load_dataset("S120"), substeps=2)
+    lib, h, d = M._lib, M._h, M.d
+    cpr, rungs, nburn, nsamp, thin = 96, 2, 35, 45, 3
+    n, keep = cpr * rungs, nsamp // thin
+    cfg = _capi.SamplerCfg()                                   # memset(&cfg, 0, sizeof cfg)
+    cfg.kind, cfg.n_chains, cfg.seed, cfg.scale, cfg.de_eps, cfg.beta = 1, n, 42, 1.0, 1e-4, 1.0
+    cfg.n_rungs, cfg.gti_pow = rungs, 1.0
+    ck = lambda rc: _capi.check(rc, h)
+    ck(lib.epi_sampler_init(h, C.byref(cfg), None))
+    ck(lib.epi_sampler_adapt(h, 1, C.c_double(0.0)))
+    for phase, total in (("burnin", nburn), ("sampling", nsamp)):
+        if phase == "sampling":
+            ck(lib.epi_sampler_adapt(h, 0, C.c_double(0.0)))
+            ck(lib.epi_sampler_record(h, thin, keep))
+        done = 0
+        while done < total:
+            ck(lib.epi_sampler_run(h, min(10, total - done)))
+            ck(lib.epi_sampler_set_population(h, None, 1, n, 0))
+            done += 10
+    kept = C.c_int32()
+    dr, lp = np.empty((keep, d, cpr)), np.empty((keep, cpr))
+    ck(lib.epi_sampler_draws_subset(h, n - cpr, cpr, _capi.as_dp(dr), _capi.as_dp(lp), C.byref(kept)))
+    it, acc, ev = C.c_int64(), C.c_int64(), C.c_int64()
+    ck(lib.epi_sampler_stats(h, C.byref(it), C.byref(acc), C.byref(ev)))
+    assert kept.value == keep and it.value == nburn + nsamp and ev.value == (nburn + nsamp + 1) * n
+    mn, mx = M.df_params["min"], M.df_params["max"]
+    assert np.isfinite(dr).all() and (dr >= mn[None, :, None]).all() and (dr <= mx[None, :, None]).all()
+    # logpost of a recorded draw == one batched evaluation of it (cold rung: beta = 1)
+    last = np.ascontiguousarray(dr[-1].T)                      # cpr x d
+    l, p, s = M.calclogpost_batch(last)
+    assert np.array_equal(l + p, lp[-1])
+    M.close()
