@@ -88,3 +88,52 @@ def test_r_shim_type_checks_against_the_header():
         rsrc = open(os.path.join(ROOT, "r", fn)).read()
         for call in re.findall(r'\.Call\("(C_\w+)"', rsrc):
             assert call in registered, (fn, call)
+
+
+def test_r_files_call_only_registered_shim_routines_with_the_right_arity():
+    """r/*.R are source-only here (no R): at least every .Call("C_...", ...) they make must name a routine that
+    r/epimcmc_shim.c registers, with the registered number of arguments, and every registered routine must be
+    defined with that many SEXP parameters."""
+    import re
+    rdir = os.path.join(ROOT, "r")
+    shim = open(os.path.join(rdir, "epimcmc_shim.c")).read()
+    registered = {m.group(1): int(m.group(2)) for m in re.finditer(r'\{"(C_\w+)",\s*\(DL_FUNC\)&\1,\s*(\d+)\}', shim)}
+    assert {"C_epi_create", "C_epi_logpost", "C_epi_trajectories", "C_epi_quantiles", "C_epi_df_params",
+            "C_epi_run_mcmc"} <= set(registered)
+    for name, arity in registered.items():
+        m = re.search(r"^SEXP %s\(([^)]*)\)" % name, shim, re.M | re.S)
+        assert m, name
+        assert len(re.findall(r"\bSEXP\b", m.group(1))) == arity, name
+
+    def call_args(text, start):
+        """number of top-level arguments of the call whose '(' is at text[start]"""
+        depth, n, i, seen = 0, 0, start, False
+        while i < len(text):
+            c = text[i]
+            if c in "([{":
+                depth += 1
+            elif c in ")]}":
+                depth -= 1
+                if depth == 0:
+                    return n + (1 if seen else 0)
+            elif c == "," and depth == 1:
+                n += 1
+            elif c == '"':
+                i = text.index('"', i + 1)
+                seen = True
+            elif not c.isspace() and depth >= 1:
+                seen = True
+            i += 1
+        raise AssertionError("unbalanced call")
+
+    n_calls = 0
+    for fn in sorted(os.listdir(rdir)):
+        if not fn.endswith(".R"):
+            continue
+        text = re.sub(r"#[^\n]*", "", open(os.path.join(rdir, fn)).read())   # strip comments
+        for m in re.finditer(r'\.Call\(\s*"(C_\w+)"', text):
+            name = m.group(1)
+            assert name in registered, (fn, name)
+            assert call_args(text, m.start() + len(".Call")) - 1 == registered[name], (fn, name)
+            n_calls += 1
+    assert n_calls >= 10
