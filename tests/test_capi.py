@@ -137,3 +137,42 @@ def test_r_files_call_only_registered_shim_routines_with_the_right_arity():
             assert call_args(text, m.start() + len(".Call")) - 1 == registered[name], (fn, name)
             n_calls += 1
     assert n_calls >= 10
+
+
+def test_r_model_files_pass_only_globals_the_shim_reads():
+    """A misspelt name in a model file's epi_globals list would be ignored silently (the shim's lookup falls back
+    to 0): every name passed must be one C_epi_create looks up, and the per-flavour essentials must be there."""
+    import re
+    rdir = os.path.join(ROOT, "r")
+    shim = open(os.path.join(rdir, "epimcmc_shim.c")).read()
+    looked_up = set(re.findall(r'\b(?:num|vec)\(g, "(\w+)"', shim))
+    assert len(looked_up) > 30
+    need = {"model-age-groups2q-gpu.R": {"y_N", "o_N", "y_ifr", "o_wdmorti", "d8", "hosp_last7", "g", "gtrimp"},
+            "model-age-groups2i-gpu.R": {"y_N", "o_N", "y_ifr", "d7", "hosp_nbinom_size"},
+            "model-simple-ode-drj-cmp-gpu.R": {"N", "dhospi", "dmorti", "mort_nbinom_size"}}
+    for fn, essentials in need.items():
+        text = re.sub(r"#[^\n]*", "", open(os.path.join(rdir, fn)).read())
+        start = text.index("epi_globals <- list(") + len("epi_globals <- list")
+        depth, i = 0, start
+        while True:
+            depth += text[i] == "("
+            depth -= text[i] == ")"
+            i += 1
+            if depth == 0:
+                break
+        body = text[start + 1:i - 1]
+        # top-level `name = value` pairs
+        keys, depth, tok = [], 0, ""
+        for c in body + ",":
+            if c in "([":
+                depth += 1
+            elif c in ")]":
+                depth -= 1
+            if c == "," and depth == 0:
+                keys.append(tok.split("=")[0].strip())
+                tok = ""
+            else:
+                tok += c
+        keys = {k for k in keys if k}
+        assert keys <= looked_up, (fn, sorted(keys - looked_up))
+        assert essentials <= keys, (fn, sorted(essentials - keys))
