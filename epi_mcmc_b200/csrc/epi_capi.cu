@@ -423,6 +423,8 @@ extern "C" int epi_create(const epi_model_desc *desc, const epi_data *data, int 
     { const char *env = getenv("EPI_WINDOW_ONLY"); h->window_only = !(env && env[0] == '0'); }
     { const char *env = getenv("EPI_PASS1_CHUNK"); h->pass1_chunk = !(env && env[0] == '0'); }
     { const char *env = getenv("EPI_FORCE_R_FALLBACK"); h->force_need_r = (env && env[0] == '1'); }
+    { const char *env = getenv("EPI_ODE_LANES"); h->ode_lanes = (env && (env[0] == '1' || env[0] == '2' || env[0] == '4')) ? env[0] - '0' : 0; }
+    { const char *env = getenv("EPI_SCORE_STRIPS"); h->score_strips = (env && env[0] == '2') ? 2 : 4; }
     { const char *env = getenv("EPI_SPLIT_STREAMS"); h->split = (env && (env[0] == '1' || env[0] == '2')); h->split_mode = (env && env[0] == '2') ? 2 : 1; }
     for (auto &ev : h->ev) cudaEventCreate(&ev);
     rc = fill_model(h, *desc, *data);
@@ -555,6 +557,8 @@ static EvalArgs make_args(epi_handle *h, Workspace &w, const DevModel &M, const 
   a.ns_total = NS;
   a.window_only = h->window_only ? 1 : 0;
   a.pass1_chunk = h->pass1_chunk ? 1 : 0;
+  a.ode_lanes = h->ode_lanes;
+  a.score_strips = h->score_strips;
   a.need_r = w.need_r + first;
   a.force_need_r = h->force_need_r ? 1 : 0;
   a.n_launches = &h->launches;

@@ -48,6 +48,8 @@ struct epi_handle {
   bool force_need_r = false;  // EPI_FORCE_R_FALLBACK=1: every chain takes the R-tracking instance (bit-identical results)
   bool pass1_chunk = true;  // EPI_PASS1_CHUNK=0: whole-period pass 1 in one round (bit-identical results)
   bool window_only = true;  // EPI_WINDOW_ONLY=0: pass 2 and the score sweep cover the whole period (bit-identical results)
+  int ode_lanes = 0;  // EPI_ODE_LANES=1|2|4: force the lanes-per-chain mapping of the age ODE kernels (0: by batch size)
+  int score_strips = 4;  // EPI_SCORE_STRIPS=2|4
   bool restart = true;  // pass 2 resumes from the pass-1 checkpoint (EPI_PASS2_RESTART=0: re-integrate everything)
   bool split = false;  // EPI_SPLIT_STREAMS=1: run the two halves of a large batch on two streams (measured slower: 6.41 vs 6.03 ms)
   // epi_eval_submit/wait: two staging buffers for the raw host theta and the events that order

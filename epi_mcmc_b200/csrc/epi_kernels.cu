@@ -955,6 +955,298 @@ k_ode_age2(const DevModel M, const double *__restrict__ theta, int64_t ld, int64
   if (g == 0 && need_r_flag) need_r_flag[i] = (nr || force_need_r) ? 1 : 0;
 }
 
+// ------------------------------------------------ K_ode, four lanes per chain
+// Small batches (the 8,192-chain shards of the strong-scaled BASELINE config, 65,536 chains over 8 GPUs) leave a
+// thread-per-chain launch at ~2 warps per SM: every RK4 stage is then one long dependent FP64 chain per warp and the
+// pipe idles (round 1: pass 2 0.71 ms thread-per-chain, 0.56 ms with two lanes per chain, for 1/8 of the work that
+// takes 0.86 ms at full batch).  Here a chain is spread over FOUR lanes, two per age group:
+//     lane (g, 0) holds (S_g, E1_g),   lane (g, 1) holds (E2_g, I_g)
+// and a stage costs each lane two shuffles (its partner's second value: I_g resp. E1_g; and I_y, the only coupling
+// between the groups, model-agen.cpp:136-144) and ONE instruction stream for both lane kinds:
+//     inf = ((bA * I_g) + bB * I_y) * S_g        (bA = bB = 0 on the (E2, I) lanes)
+//     w   = half ? u : inf
+//     dv  = fma(c, v, w)        c = -a1 | -gamma     ->  inf - a1 E1   |  E2 - gamma I
+//     du  = fma(a1h, pv, -w)    a1h = 0 | a1         ->  -inf          |  a1 E1 - E2
+// Every operation is the explicitly rounded one of rhs<> (the y group's beta_yo = 0 term adds an exact +0), so the
+// results are bit-identical to the thread-per-chain kernel (tests/test_gpu_parity.py).  R is not integrated; a
+// chain whose guard decision could have depended on it is flagged for the R-tracking instance of k_ode, as there.
+struct Seg4 {
+  double tk, bA, sA, bB, sB;
+  bool fast_ok, hold;
+};
+
+template <int FL>
+__device__ __noinline__ Seg4 select_segment4(const double *__restrict__ th, int64_t ld, const double *bp, int nbp,
+                                             double pa, int is_o, int half, double *tcut, double invy, double invo,
+                                             int *kcur, bool sorted) {
+  int k = -1;
+  double tc = INFINITY;
+  if (sorted && *kcur >= -1) {
+    k = *kcur;
+    while (k + 1 < nbp && bp[k + 1] <= pa) ++k;
+    if (k + 1 < nbp) tc = bp[k + 1];
+  } else {
+    for (int i = 0; i < nbp; ++i) {
+      if (bp[i] <= pa) k = i;
+      if (bp[i] > pa && bp[i] < tc) tc = bp[i];
+    }
+  }
+  *kcur = k;
+  *tcut = tc;
+  double by, bo, byo;
+  age_beta<FL>(th, ld, k < 0 ? 0 : k, by, bo, byo);
+  Seg4 sg;
+  sg.tk = 0.0; sg.sA = 0.0; sg.sB = 0.0;
+  sg.bA = is_o ? bo : by;
+  sg.bB = is_o ? byo : 0.0;
+  if (k >= 0 && age_linear<FL>(k)) {
+    double ny, no, nyo;
+    age_beta<FL>(th, ld, k + 1, ny, no, nyo);
+    const double len = bp[k + 1] - bp[k];
+    sg.tk = bp[k];
+    sg.sA = is_o ? (no - bo) / len : (ny - by) / len;
+    sg.sB = is_o ? (nyo - byo) / len : 0.0;
+    sg.fast_ok = by >= 0 && bo >= 0 && byo >= 0 && ny >= 0 && no >= 0 && nyo >= 0 && len > 0;
+    // hold <=> all three slopes of the chain are zero (the same test as select_segment, on the same roundings)
+    sg.hold = __dmul_rn((ny - by) / len, invy) == 0.0 && __dmul_rn((no - bo) / len, invo) == 0.0 &&
+              __dmul_rn((nyo - byo) / len, invy) == 0.0;
+  } else {
+    sg.fast_ok = by >= 0 && bo >= 0 && byo >= 0;
+    sg.hold = true;
+  }
+  // the same normalisation (and the same roundings) as select_segment
+  const double invA = is_o ? invo : invy;
+  sg.bA = __dmul_rn(sg.bA, invA); sg.sA = __dmul_rn(sg.sA, invA);
+  sg.bB = __dmul_rn(sg.bB, invy); sg.sB = __dmul_rn(sg.sB, invy);
+  if (half) { sg.bA = 0.0; sg.sA = 0.0; sg.bB = 0.0; sg.sB = 0.0; }  // the (E2, I) lanes have no infection term
+  return sg;
+}
+
+// per-lane constants of the four-lane kernel
+struct Lane4 {
+  double a1h, c, Ngrp;  // du = fma(a1h, pv, -w), dv = fma(c, v, w)
+  int shift;            // first lane of this chain's quad
+  int src_partner, src_iy, half;
+  unsigned nb, lo_u, r_u;  // fast guard: v in [0, N) via nb = hi(N) - 1; u in [1, +inf) (S) or [0, N) via (lo_u, r_u)
+};
+
+// The kernel is WARP-SYNCHRONOUS: all 32 lanes (8 chains) execute every stage together and every shuffle / vote
+// names the full warp.  (First version, profiles/r2_summary.md: shuffles over per-quad masks made ptxas emit
+// MATCH.ANY + REDUX.OR + a divergence check in front of every RK4 step — 400 cycles per stage at 8,192 chains,
+// twice the thread-per-chain kernel.)  Chains that have nothing to do in a piece — finished, not started, fewer
+// pieces on a day a breakpoint cuts for a neighbour — run it with their state frozen (`commit` false).
+constexpr unsigned kFull = 0xffffffffu;
+
+template <bool GUARDED, bool HOLD>
+__device__ __forceinline__ void rhs4(const Lane4 &L, const Seg4 &sg, double t, double u, double v, double &du,
+                                     double &dv, unsigned &flag) {
+  const double pv = __shfl_sync(kFull, v, L.src_partner);  // (S,E1) lane: I_g;  (E2,I) lane: E1_g
+  const double iy = __shfl_sync(kFull, v, L.src_iy);       // I of the younger group
+  bool bad = false;
+  if constexpr (GUARDED) {
+    // bounds guard over the chain's states, model-agen.cpp:109-124 (R is not integrated here: see below_one)
+    const int bad_own = (u < 0 || v < 0 || u > L.Ngrp || v > L.Ngrp);
+    bad = ((__ballot_sync(kFull, bad_own) >> L.shift) & 0xFu) != 0u;
+    flag |= (!bad && !L.half && u < 1.0) ? 1u : 0u;  // the R test is undecidable here
+  } else {
+    const unsigned hu = (unsigned)__double2hiint(u) - L.lo_u, hv = (unsigned)__double2hiint(v);
+    flag |= ((L.r_u - hu) | hu) | ((L.nb - hv) | hv);  // bit 31 set <=> maybe out of bounds
+  }
+  const double dt = HOLD ? 0.0 : t - sg.tk;
+  const double bA = HOLD ? sg.bA : fma(dt, sg.sA, sg.bA), bB = HOLD ? sg.bB : fma(dt, sg.sB, sg.bB);
+  const double inf = __dmul_rn(fma(bA, pv, __dmul_rn(bB, iy)), u);
+  const double w = L.half ? u : inf;
+  dv = fma(L.c, v, w);
+  du = fma(L.a1h, pv, -w);
+  if constexpr (GUARDED) {
+    if (bad) { du = 0.0; dv = 0.0; }  // the guard freezes the whole state
+  }
+}
+
+// returns (fast instance) whether no lane of the chain raised the maybe-out-of-bounds bit
+template <bool GUARDED, bool HOLD>
+__device__ __forceinline__ bool rk4_try4(const Lane4 &L, const Seg4 &sg, double u, double v, double &un, double &vn,
+                                         double pa, double pb, double hh, double hh2, double h6, bool &need_r) {
+  const double tm = pa + hh2;
+  double ku, kv, au, av, ut, vt;
+  unsigned flag = 0;
+  rhs4<GUARDED, HOLD>(L, sg, pa, u, v, ku, kv, flag);
+  au = ku; av = kv; ut = fma(hh2, ku, u); vt = fma(hh2, kv, v);
+  rhs4<GUARDED, HOLD>(L, sg, tm, ut, vt, ku, kv, flag);
+  au = fma(2.0, ku, au); av = fma(2.0, kv, av); ut = fma(hh2, ku, u); vt = fma(hh2, kv, v);
+  rhs4<GUARDED, HOLD>(L, sg, tm, ut, vt, ku, kv, flag);
+  au = fma(2.0, ku, au); av = fma(2.0, kv, av); ut = fma(hh, ku, u); vt = fma(hh, kv, v);
+  rhs4<GUARDED, HOLD>(L, sg, pb, ut, vt, ku, kv, flag);
+  un = fma(h6, __dadd_rn(au, ku), u);
+  vn = fma(h6, __dadd_rn(av, kv), v);
+  if constexpr (GUARDED) {
+    need_r = (flag & 1u) != 0u;
+    return true;
+  }
+  return ((__ballot_sync(kFull, (int)flag < 0) >> L.shift) & 0xFu) == 0u;
+}
+
+// one RK4 piece for all eight chains of the warp; a chain takes the result only when `commit`
+__device__ __forceinline__ void rk4_step4(const Lane4 &L, const Seg4 &sg, double &u, double &v, bool commit, double pa,
+                                          double pb, double hh, double hh2, double h6, bool &need_r) {
+  double un, vn;
+  bool nr = false;
+  const bool hold = __all_sync(kFull, sg.hold);
+  bool ok = hold ? rk4_try4<false, true>(L, sg, u, v, un, vn, pa, pb, hh, hh2, h6, nr)
+                 : rk4_try4<false, false>(L, sg, u, v, un, vn, pa, pb, hh, hh2, h6, nr);
+  ok = ok && sg.fast_ok;
+  if (__any_sync(kFull, commit && !ok)) {
+    // rare: the reference's guard evaluated exactly in FP64, by the whole warp; taken by the chains that need it
+    double gu, gv;
+    bool gnr = false;
+    rk4_try4<true, false>(L, sg, u, v, gu, gv, pa, pb, hh, hh2, h6, gnr);
+    if (!ok) { un = gu; vn = gv; nr = gnr; }
+  }
+  if (commit) { u = un; v = vn; need_r = need_r || nr; }
+}
+
+// MINB = resident blocks per SM the register allocation must allow: 4 (<= 128 registers, nothing spilled) while the
+// whole batch fits at that occupancy anyway, 7 (<= 72 registers) above it
+template <int FL, bool PASS2, int MINB>
+__global__ void __launch_bounds__(128, MINB)
+k_ode_age4(const DevModel M, const double *__restrict__ theta, int64_t ld, int64_t n, const int *__restrict__ offset,
+           const int *__restrict__ padv, const double *__restrict__ hist1, double *__restrict__ hist_out,
+           double *__restrict__ ckpt, int window_only = 0, int ndays_limit = 0,
+           const int *__restrict__ retry_status = nullptr, int *__restrict__ need_r_flag = nullptr,
+           int force_need_r = 0) {
+  bool need_r = false;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool exists = (tid >> 2) < n;
+  const int64_t i = exists ? (tid >> 2) : n - 1;  // lanes behind the batch shadow its last chain and never store
+  const int lane = threadIdx.x & 31;
+  const int g = (lane >> 1) & 1;  // 0 = younger group, 1 = older group
+  Lane4 L;
+  L.half = lane & 1;              // 0: (S, E1), 1: (E2, I)
+  L.shift = lane & ~3;
+  L.src_partner = lane ^ 1;
+  L.src_iy = L.shift | 1;
+  L.Ngrp = g ? M.No : M.Ny;
+  L.nb = (unsigned)__double2hiint(L.Ngrp) - 1u;
+  L.lo_u = L.half ? 0u : 0x3ff00000u;
+  L.r_u = L.half ? L.nb : 0x40000000u;
+  L.a1h = L.half ? M.a1 : 0.0;
+  L.c = L.half ? -M.gamma : -M.a1;
+  const double *th = theta + i;
+  const int ndays = PASS2 ? M.P : M.P1;
+  int nint = ndays;  // days integrated here
+  bool alive = exists;
+  if constexpr (!PASS2) {  // two-round pass 1, see k_ode
+    if (retry_status && !(retry_status[i] & kStRetry)) alive = false;
+    if (ndays_limit > 0) nint = min(nint, ndays_limit);
+  }
+  double *out = hist_out + (i * 2 + g) * (int64_t)hist_pitch(ndays);
+  const bool writes_s = !L.half;
+  // model-age-groups2q.R:157-158
+  double u = L.half ? 0.0 : (g ? M.No : M.Ny - 1.0);
+  double v = (L.half || g) ? 0.0 : 1.0;
+
+  double bp[kMaxBp];
+  int nbp = 0;
+  double tcut = INFINITY;
+  int t0 = 1;
+  if constexpr (PASS2) {
+    const int off = offset[i];
+    if (off == EPI_INVALID_DATA_OFFSET) {
+      // pass 2 skipped: the pass-1 rows are recycled into the P-length slices (:216-223)
+      if (alive && writes_s) {
+        const double *in = hist1 + (i * 2 + g) * (int64_t)hist_pitch(M.P1);
+        for (int d = 0; d < M.P; ++d) out[d] = in[d % M.P1];
+      }
+      if (alive && (lane & 3) == 0 && need_r_flag) need_r_flag[i] = 0;
+      alive = false;
+    } else {
+      t0 = padv[i] + 1;
+      nbp = breakpoints<FL>(M, th, ld, (double)off, bp);
+      if (window_only) nint = min(nint, max(last_window_day(M, off, padv[i]) - padv[i], 1));
+    }
+  }
+  const bool flags_r = alive;  // this chain reports need_r at the end
+  const int cdays = ckpt_days(M.P1);
+  // states of this lane in the checkpoint tile: q = g * 5 + half * 2 (+1)
+  double *ck = ckpt ? ckpt + ((i / kTile) * (int64_t)cdays * 10 + g * 5 + L.half * 2) * kTile + (i % kTile) : nullptr;
+  int d0 = 0;
+  if constexpr (PASS2) {
+    if (ck && alive) {
+      double minbp = INFINITY;
+      for (int k = 0; k < nbp; ++k) minbp = fmin(minbp, bp[k]);
+      const double dd = floor(minbp) - (double)t0;
+      d0 = dd > 0 ? (int)fmin(dd, (double)min(cdays - 1, ndays - 1)) : 0;
+      if (d0 > 0) {
+        if (writes_s) {
+          const double *in = hist1 + (i * 2 + g) * (int64_t)hist_pitch(M.P1);
+          for (int d = 0; d <= d0; ++d) out[d] = in[d];
+        }
+        u = ck[((int64_t)d0 * 10) * kTile];
+        v = ck[((int64_t)d0 * 10 + 1) * kTile];
+      }
+    }
+  }
+  bool bp_sorted = true;
+  for (int k = 1; k < nbp; ++k) bp_sorted = bp_sorted && bp[k - 1] <= bp[k];
+  int kseg = -2;
+  const double invy = 1.0 / M.Ny, invo = 1.0 / M.No;
+  Seg4 sg = select_segment4<FL>(th, ld, bp, nbp, (double)(t0 + d0), g, L.half, &tcut, invy, invo, &kseg, bp_sorted);
+
+  const int m = M.m;
+  const double h = 1.0 / (double)m;
+  if (alive && d0 == 0 && writes_s) out[0] = u;
+  if constexpr (!PASS2) {
+    if (ck && alive) { ck[0] = u; ck[kTile] = v; }
+  }
+  // day range of the warp: every chain walks it, live only inside its own (d0, nint)
+  const int d_first = __reduce_min_sync(kFull, alive ? d0 + 1 : 0x7fffffff);
+  const int d_end = __reduce_max_sync(kFull, alive ? nint : 0);
+  // the same route choices as k_ode (all of them give the same bits): a day without a breakpoint in any live lane
+  // takes the constant-step loop, the others the general piece loop
+  const bool pow2 = (m & (m - 1)) == 0;
+  const double hh2reg = 0.5 * h, h6reg = h / 6.0;
+  for (int d = d_first; d < d_end; ++d) {
+    const bool live = alive && d > d0 && d < nint;
+    const double tday = (double)(t0 + d - 1);
+    const bool regular = pow2 && __all_sync(kFull, !live || tcut >= tday + 1.0);
+    double pa = tday;
+    if (regular) {
+      for (int s = 0; s < m; ++s) {
+        const double pb = pa + h;
+        rk4_step4(L, sg, u, v, live, pa, pb, h, hh2reg, h6reg, need_r);
+        pa = pb;
+      }
+    } else {
+      int s = 0;
+      for (;;) {
+        const bool pending = live && s < m;
+        if (!__any_sync(kFull, pending)) break;
+        const double b = (s == m - 1) ? tday + 1.0 : tday + (double)(s + 1) * h;
+        bool step_done = true;
+        double pb = b;
+        if constexpr (PASS2) {
+          if (pending && pa >= tcut)
+            sg = select_segment4<FL>(th, ld, bp, nbp, pa, g, L.half, &tcut, invy, invo, &kseg, bp_sorted);
+          if (tcut < b) { pb = tcut; step_done = false; }  // a breakpoint strictly inside (pa, b): cut there
+        }
+        const double hh = pending ? pb - pa : 0.0, hh2 = 0.5 * hh, h6 = hh / 6.0;
+        rk4_step4(L, sg, u, v, pending, pa, pending ? pb : pa, hh, hh2, h6, need_r);
+        if (pending) {
+          pa = pb;
+          if (step_done) ++s;
+        }
+      }
+    }
+    if (live && writes_s) out[d] = u;
+    if constexpr (!PASS2) {
+      if (ck && live && d < cdays) { ck[((int64_t)d * 10) * kTile] = u; ck[((int64_t)d * 10 + 1) * kTile] = v; }
+    }
+  }
+  // any lane may have met an undecidable R test: the chain is flagged if one of them did
+  const unsigned nr = (__ballot_sync(kFull, need_r) >> L.shift) & 0xFu;
+  if (flags_r && (lane & 3) == 0 && need_r_flag) need_r_flag[i] = (nr || force_need_r) ? 1 : 0;
+}
+
 // ---------------------------------------------------------------------- K_mid
 // Per-warp shared-memory carve-up shared by k_mid and k_score.
 constexpr int kCdfStride = EPI_MAX_TAPS + 1;  // n + 1 cell edges per profile
@@ -1422,22 +1714,28 @@ __device__ __forceinline__ void stage_score(const DevModel &M, const ScoreSmem &
 //   conv_q(t) = sum_d Wabs[d][q] * S[t - d]
 // (ncu, profiles/r1_v1: the per-profile serial FMA chain with two LDS per FMA left the
 // FP64 pipe 17 % busy; here every S load feeds KG chains and every weight load 2 days.)
-template <int KG, int PAD>
-__device__ __forceinline__ void conv_group2(const double *__restrict__ Sg, const double *__restrict__ Wabs, int lo,
-                                            int hi, int ja, int P, double *ca, double *cb) {
-  const int j0 = min(max(ja, 0), P - 1), j1 = min(max(ja + 32, 0), P - 1);  // out-of-range days are discarded later
-  const double *xa = Sg + PAD + j0, *xb = Sg + PAD + j1;
+// NS day strips per lane (days ja, ja + 32, ..., ja + 32 (NS - 1)): every weight load feeds NS days.
+// c[s * KG + q] = conv_q(day ja + 32 s).  The FMA chain of one (day, profile) runs over the delays in ascending
+// order whatever NS is, so the result does not depend on it.
+template <int KG, int PAD, int NS>
+__device__ __forceinline__ void conv_group(const double *__restrict__ Sg, const double *__restrict__ Wabs, int lo,
+                                           int hi, int ja, int P, double *c) {
+  const double *x[NS];
 #pragma unroll
-  for (int q = 0; q < KG; ++q) { ca[q] = 0.0; cb[q] = 0.0; }
-#pragma unroll 4
+  for (int s = 0; s < NS; ++s) x[s] = Sg + PAD + min(max(ja + 32 * s, 0), P - 1);  // out-of-range days are discarded later
+#pragma unroll
+  for (int i = 0; i < NS * KG; ++i) c[i] = 0.0;
+#pragma unroll 2
   for (int d = lo; d <= hi; ++d) {
-    const double x0 = xa[-d], x1 = xb[-d];
     const double2 w01 = *reinterpret_cast<const double2 *>(Wabs + d * 4);
-    ca[0] = fma(w01.x, x0, ca[0]); cb[0] = fma(w01.x, x1, cb[0]);
-    ca[1] = fma(w01.y, x0, ca[1]); cb[1] = fma(w01.y, x1, cb[1]);
-    if constexpr (KG == 3) {
-      const double w2 = Wabs[d * 4 + 2];
-      ca[2] = fma(w2, x0, ca[2]); cb[2] = fma(w2, x1, cb[2]);
+    double w2 = 0.0;
+    if constexpr (KG == 3) w2 = Wabs[d * 4 + 2];
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      const double xs = x[s][-d];
+      c[s * KG + 0] = fma(w01.x, xs, c[s * KG + 0]);
+      c[s * KG + 1] = fma(w01.y, xs, c[s * KG + 1]);
+      if constexpr (KG == 3) c[s * KG + 2] = fma(w2, xs, c[s * KG + 2]);
     }
   }
 }
@@ -1526,7 +1824,8 @@ struct AgeMap {
   }
 };
 
-template <int FL>
+// NS = day strips per lane and sweep (32 NS days per sweep): every profile-weight load of the convolution feeds NS days
+template <int FL, int NS>
 __global__ void __launch_bounds__(128, 4)
 k_score(const DevModel M, const PriorTerm *__restrict__ PT, int n_prior, const double *__restrict__ theta, int64_t ld, int64_t n,
         const double *__restrict__ hist2, const int *__restrict__ offset, const int *__restrict__ padv,
@@ -1595,13 +1894,14 @@ k_score(const DevModel M, const PriorTerm *__restrict__ PT, int n_prior, const d
     AgeMap<FL> map;
     map.init(M, w.theta, off_raw, pad, P);
     double carry[6] = {0, 0, 0, 0, 0, 0};
-    for (int base = jlo; base <= jhi; base += 64) {
-      double ca[6], cb[6];
-      conv_group2<3, PAD>(w.S, w.Wabs, lo[0], hi[0], base + lane, P, ca, cb);
-      conv_group2<3, PAD>(w.S + stride, w.Wabs + PAD * 4, lo[1], hi[1], base + lane, P, ca + 3, cb + 3);
+    for (int base = jlo; base <= jhi; base += 32 * NS) {
+      double cy[NS * 3], co[NS * 3];
+      conv_group<3, PAD, NS>(w.S, w.Wabs, lo[0], hi[0], base + lane, P, cy);
+      conv_group<3, PAD, NS>(w.S + stride, w.Wabs + PAD * 4, lo[1], hi[1], base + lane, P, co);
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
+      for (int half = 0; half < NS; ++half) {
         const int j = base + 32 * half + lane;
+        if (base + 32 * half > jhi) break;  // (warp-uniform) strips behind the last swept day
         const int t = pad + 1 + j;
         const bool in = j >= 0 && j < P;
         DaySlots<5> slots;
@@ -1610,7 +1910,7 @@ k_score(const DevModel M, const PriorTerm *__restrict__ PT, int n_prior, const d
 #pragma unroll
         for (int q = 0; q < 6; ++q) {
           const double Ng = q < 3 ? M.Ny : M.No;
-          double c = half ? cb[q] : ca[q];
+          double c = q < 3 ? cy[half * 3 + q] : co[half * 3 + q - 3];
           // stats::filter leaves the first n-1 outputs NA: reachable only for the hospital profiles, the
           // other four define the padding (:113-114), so t - dmin >= n for every t > padding
           if ((q == 1 || q == 4) && t - dmin_[q] < n_[q]) c = NAN;
@@ -1643,12 +1943,13 @@ k_score(const DevModel M, const PriorTerm *__restrict__ PT, int n_prior, const d
     // hospi/deadi = c(v[1], diff(v)) (model-simple-ode-drj-cmp.R:115-122)
     const double rate[2] = {w.theta[4], 0.007};
     double carry[2] = {0, 0};
-    for (int base = jlo; base <= jhi; base += 64) {
-      double ca[2], cb[2];
-      conv_group2<2, PAD>(w.S, w.Wabs, lo[0], hi[0], base + lane, P, ca, cb);
+    for (int base = jlo; base <= jhi; base += 32 * NS) {
+      double cc[NS * 2];
+      conv_group<2, PAD, NS>(w.S, w.Wabs, lo[0], hi[0], base + lane, P, cc);
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
+      for (int half = 0; half < NS; ++half) {
         const int j = base + 32 * half + lane;
+        if (base + 32 * half > jhi) break;  // (warp-uniform) strips behind the last swept day
         const int t = pad + 1 + j;
         const bool in = j >= 0 && j < P;
         DaySlots<2> slots;
@@ -1656,7 +1957,7 @@ k_score(const DevModel M, const PriorTerm *__restrict__ PT, int n_prior, const d
         double v2[2];
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
-          const double c = half ? cb[q] : ca[q];  // both profiles define the padding (:59): never NA for t > padding
+          const double c = cc[half * 2 + q];  // both profiles define the padding (:59): never NA for t > padding
           const double cum = in ? (M.N - c) * rate[q] : 0.0;
           double prev = __shfl_up_sync(0xffffffffu, cum, 1);
           if (lane == 0) prev = carry[q];
@@ -1726,12 +2027,13 @@ k_series(const DevModel M, const double *__restrict__ theta, int64_t ld, int64_t
     map.init(M, w.theta, off_raw, pad, P);
     const int dst[6] = {2, 4, 6, 3, 5, 7};
     double carry[6] = {0, 0, 0, 0, 0, 0};
-    for (int base = 0; base < P; base += 64) {
-      double ca[6], cb[6];
-      conv_group2<3, PAD>(w.S, w.Wabs, lo[0], hi[0], base + lane, P, ca, cb);
-      conv_group2<3, PAD>(w.S + stride, w.Wabs + PAD * 4, lo[1], hi[1], base + lane, P, ca + 3, cb + 3);
+    constexpr int NS = 2;
+    for (int base = 0; base < P; base += 32 * NS) {
+      double cy[NS * 3], co[NS * 3];
+      conv_group<3, PAD, NS>(w.S, w.Wabs, lo[0], hi[0], base + lane, P, cy);
+      conv_group<3, PAD, NS>(w.S + stride, w.Wabs + PAD * 4, lo[1], hi[1], base + lane, P, co);
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
+      for (int half = 0; half < NS; ++half) {
         const int j = base + 32 * half + lane;
         const int t = pad + 1 + j;
         const bool in = j < P;
@@ -1740,7 +2042,7 @@ k_series(const DevModel M, const double *__restrict__ theta, int64_t ld, int64_t
 #pragma unroll
         for (int q = 0; q < 6; ++q) {
           const double Ng = q < 3 ? M.Ny : M.No;
-          double c = half ? cb[q] : ca[q];
+          double c = q < 3 ? cy[half * 3 + q] : co[half * 3 + q - 3];
           if (t - dmin_[q] < n_[q]) c = NAN;
           const double s2 = in ? Ng - c : 0.0;
           double prev = __shfl_up_sync(0xffffffffu, s2, 1);
@@ -1758,18 +2060,19 @@ k_series(const DevModel M, const double *__restrict__ theta, int64_t ld, int64_t
   } else {
     const double rate[2] = {w.theta[4], 0.007};
     double carry[2] = {0, 0};
-    for (int base = 0; base < P; base += 64) {
-      double ca[2], cb[2];
-      conv_group2<2, PAD>(w.S, w.Wabs, lo[0], hi[0], base + lane, P, ca, cb);
+    constexpr int NS = 2;
+    for (int base = 0; base < P; base += 32 * NS) {
+      double cc[NS * 2];
+      conv_group<2, PAD, NS>(w.S, w.Wabs, lo[0], hi[0], base + lane, P, cc);
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
+      for (int half = 0; half < NS; ++half) {
         const int j = base + 32 * half + lane;
         const int t = pad + 1 + j;
         const bool in = j < P;
         if (in) o[j] = w.S[PAD + j];
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
-          double c = half ? cb[q] : ca[q];
+          double c = cc[half * 2 + q];
           if (t - dmin_[q] < n_[q]) c = NAN;
           const double cum = in ? (M.N - c) * rate[q] : 0.0;
           double prev = __shfl_up_sync(0xffffffffu, cum, 1);
@@ -1883,7 +2186,8 @@ static cudaError_t launch_eval_fl(const EvalArgs &a) {
   const int di = dev < kMaxDev ? dev : kMaxDev - 1;
   if (!attr_done[di] || dev >= kMaxDev) {
     cudaFuncSetAttribute(k_mid<FL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(k_score<FL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(k_score<FL, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(k_score<FL, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(k_series<FL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaDeviceGetAttribute(&n_sm_of[di], cudaDevAttrMultiProcessorCount, dev);
     attr_done[di] = true;
@@ -1895,7 +2199,15 @@ static cudaError_t launch_eval_fl(const EvalArgs &a) {
   // Two lanes per chain double the resident warps, but need ~124 registers per lane: they win
   // while all 2n lanes fit one wave (n <= 256 chains per SM), thread-per-chain wins above that
   // (measured on B200, 65,536 chains: 2.25 ms vs 2.07 ms for pass 2).
-  const bool use_pair = Traits<FL>::kAge && n <= (int64_t)n_sm * 256;
+  // Four lanes per chain (k_ode_age4) while a thread-per-chain launch would leave the SMs short of warps; the
+  // thresholds are measured (profiles/r2_summary.md).  EPI_ODE_LANES = 1 | 2 | 4 forces one mapping (tests, bench).
+  int lanes = 1;
+  if constexpr (Traits<FL>::kAge) {
+    lanes = a.ode_lanes ? a.ode_lanes : (n <= (int64_t)n_sm * 256 ? 4 : 1);
+  }
+  const bool use_pair = lanes == 2, use_quad = lanes == 4;
+  const unsigned quad_blocks = (unsigned)((4 * n + 127) / 128);
+  const bool quad_roomy = (int64_t)quad_blocks <= (int64_t)n_sm * 4;  // all blocks resident at 128 registers
   // pass 1 that covers the whole period (simple / age-2i) is integrated for its first kPass1Chunk days first:
   // the threshold is normally crossed there and everything behind the crossing is never read.  Chains that
   // did not cross are redone over the whole pass-1 period by a retry round (k_mid flags them).
@@ -1904,7 +2216,12 @@ static cudaError_t launch_eval_fl(const EvalArgs &a) {
   // thread-per-chain pass 1: the hot instance (R not integrated) and, right behind it, the R-tracking instance for
   // the chains the hot one flagged (exits at once otherwise)
   auto pass1 = [&](int limit, const int *retry) {
-    if (use_pair) {
+    if (use_quad) {
+      if constexpr (Traits<FL>::kAge) {
+        if (quad_roomy) k_ode_age4<FL, false, 4><<<quad_blocks, 128, 0, s>>>(M, a.theta, a.ld, n, nullptr, nullptr, nullptr, a.hist1, a.ckpt, 0, limit, retry, a.need_r, a.force_need_r);
+        else k_ode_age4<FL, false, 7><<<quad_blocks, 128, 0, s>>>(M, a.theta, a.ld, n, nullptr, nullptr, nullptr, a.hist1, a.ckpt, 0, limit, retry, a.need_r, a.force_need_r);
+      }
+    } else if (use_pair) {
       if constexpr (Traits<FL>::kAge) k_ode_age2<FL, false><<<pair_blocks, 64, 0, s>>>(M, a.theta, a.ld, n, nullptr, nullptr, nullptr, a.hist1, a.ckpt, 0, limit, retry, a.need_r, a.force_need_r);
     } else {
       k_ode<FL, false><<<ode_blocks, 32, 0, s>>>(M, a.theta, a.ld, n, nullptr, nullptr, nullptr, a.hist1, a.ckpt, nullptr, 0, 0, limit, retry, a.need_r, a.force_need_r);
@@ -1925,8 +2242,12 @@ static cudaError_t launch_eval_fl(const EvalArgs &a) {
   if (a.ev_after_mid) cudaEventRecord(a.ev_after_mid, s);
   const bool want_ext = a.series_out && a.ns_total > (Traits<FL>::kAge ? 8 : 3);
   const int window_only = (a.series_out || !a.window_only) ? 0 : 1;  // scoring reads S(t) only up to the last data-window day
-  if (use_pair && !want_ext) {
-    if constexpr (Traits<FL>::kAge) k_ode_age2<FL, true><<<pair_blocks, 64, 0, s>>>(M, a.theta, a.ld, n, a.offset, a.pad, a.hist1, a.hist2, a.ckpt, window_only, 0, nullptr, a.need_r, a.force_need_r);
+  if ((use_pair || use_quad) && !want_ext) {
+    if constexpr (Traits<FL>::kAge) {
+      if (use_quad && quad_roomy) k_ode_age4<FL, true, 4><<<quad_blocks, 128, 0, s>>>(M, a.theta, a.ld, n, a.offset, a.pad, a.hist1, a.hist2, a.ckpt, window_only, 0, nullptr, a.need_r, a.force_need_r);
+      else if (use_quad) k_ode_age4<FL, true, 7><<<quad_blocks, 128, 0, s>>>(M, a.theta, a.ld, n, a.offset, a.pad, a.hist1, a.hist2, a.ckpt, window_only, 0, nullptr, a.need_r, a.force_need_r);
+      else k_ode_age2<FL, true><<<pair_blocks, 64, 0, s>>>(M, a.theta, a.ld, n, a.offset, a.pad, a.hist1, a.hist2, a.ckpt, window_only, 0, nullptr, a.need_r, a.force_need_r);
+    }
     k_ode<FL, true, false, true><<<ode_blocks, 32, 0, s>>>(M, a.theta, a.ld, n, a.offset, a.pad, a.hist1, a.hist2, a.ckpt, nullptr, 0, window_only, 0, nullptr, a.need_r, 0);
     nl += 2;
   } else if (want_ext) {
@@ -1944,8 +2265,12 @@ static cudaError_t launch_eval_fl(const EvalArgs &a) {
     k_series<FL><<<warp_blocks, 128, smem_score, s>>>(M, a.theta, a.ld, n, a.hist2, a.offset, a.pad, a.W, a.pmeta,
                                                       a.status, a.series_out, a.ns_total);
   } else {
-    k_score<FL><<<warp_blocks, 128, smem_score, s>>>(M, a.PT, a.n_prior, a.theta, a.ld, n, a.hist2, a.offset, a.pad, a.W, a.pmeta,
-                                                     a.status, a.logl, a.logp, a.terms, window_only);
+    if (a.score_strips == 2)
+      k_score<FL, 2><<<warp_blocks, 128, smem_score, s>>>(M, a.PT, a.n_prior, a.theta, a.ld, n, a.hist2, a.offset, a.pad, a.W, a.pmeta,
+                                                          a.status, a.logl, a.logp, a.terms, window_only);
+    else
+      k_score<FL, 4><<<warp_blocks, 128, smem_score, s>>>(M, a.PT, a.n_prior, a.theta, a.ld, n, a.hist2, a.offset, a.pad, a.W, a.pmeta,
+                                                          a.status, a.logl, a.logp, a.terms, window_only);
   }
   nl += 1;
   if (a.n_launches) *a.n_launches += nl;

@@ -486,8 +486,8 @@ def test_removed_compartment_fallback_is_bit_identical(name, m, monkeypatch):
 
 @pytest.mark.parametrize("name", ["A300", "I290"])
 def test_both_ode_kernels_produce_the_same_bits(name):
-    """Small batches of the age flavours use two lanes per chain (k_ode_age2, always integrates R), large ones a
-    thread per chain (k_ode, R-free hot path): the same theta must give the same bits through either."""
+    """Small batches of the age flavours use four lanes per chain (k_ode_age4), large ones a thread per chain
+    (k_ode): the same theta must give the same bits through either."""
     M = _model(name, 4)
     theta = np.array(load_golden(name)["theta"])
     small = M.calclogpost_batch(theta)
@@ -497,6 +497,53 @@ def test_both_ode_kernels_produce_the_same_bits(name):
         assert np.array_equal(a, b[:len(theta)], equal_nan=True)
         assert np.array_equal(a, b[-len(theta):], equal_nan=True)
     M.close()
+
+
+@pytest.mark.parametrize("name,m", [("A300", 4), ("A300", 1), ("A300", 3), ("I290", 4), ("A365", 2)])
+def test_ode_lane_mappings_produce_the_same_bits(name, m, monkeypatch):
+    """EPI_ODE_LANES forces one, two or four lanes per chain for the ODE passes of the age flavours (k_ode,
+    k_ode_age2, k_ode_age4).  Golden theta, box-uniform theta (guard slow path, invalid offsets, unsorted
+    breakpoints) and a ragged batch size must give identical bits, offsets and statuses through all three."""
+    from epi_mcmc_b200.model import Model, load_dataset
+    ds = load_dataset(name)
+    theta = np.array(load_golden(name)["theta"])
+    rng = np.random.default_rng(11)
+    outs = {}
+    for lanes in (1, 2, 4):
+        monkeypatch.setenv("EPI_ODE_LANES", str(lanes))
+        M = Model(ds, substeps=m)
+        mn, mx = M.df_params["min"], M.df_params["max"]
+        if lanes == 1:
+            box = mn + rng.uniform(size=(1003, M.d)) * (mx - mn)
+            th = np.vstack([theta, box])
+        logl, logp, status = M.calclogpost_batch(th)
+        off, pad, terms = M.eval_detail(th)
+        outs[lanes] = (logl, logp, status, off, pad, terms)
+        M.close()
+    for lanes in (2, 4):
+        for a, b in zip(outs[1], outs[lanes]):
+            assert np.array_equal(a, b, equal_nan=True), lanes
+
+
+def test_four_lane_kernel_through_the_r_fallback(monkeypatch):
+    """Tiny population: S falls below 1, the four-lane kernel flags the chains and the R-tracking thread-per-chain
+    instance recomputes them — same bits as the thread-per-chain hot path followed by the same fallback."""
+    from epi_mcmc_b200.model import Model, load_dataset
+    ds = dict(load_dataset("A300"))
+    ds["y_N"], ds["o_N"], ds["N"] = 300.0, 120.0, 420.0
+    outs = {}
+    for lanes in (1, 4):
+        monkeypatch.setenv("EPI_ODE_LANES", str(lanes))
+        M = Model(ds, substeps=4)
+        mn, mx, init = M.df_params["min"], M.df_params["max"], M.df_params["init"]
+        rng = np.random.default_rng(2)
+        theta = np.clip(init + (rng.uniform(size=(256, 45)) - 0.5) * 0.3 * (mx - mn), mn, mx)
+        theta[:, 17] = rng.uniform(0.0, 0.5, size=256)
+        outs[lanes] = M.calclogpost_batch(theta) + (M.fallback_count(),)
+        M.close()
+    assert outs[1][3] > 0 and outs[1][3] == outs[4][3]
+    for a, b in zip(outs[1][:3], outs[4][:3]):
+        assert np.array_equal(a, b, equal_nan=True)
 
 
 def test_tiny_population_exercises_the_r_fallback(oracle, monkeypatch):
