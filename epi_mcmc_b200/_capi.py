@@ -101,7 +101,7 @@ _lib = None
 # every symbol include/epimcmc.h declares (tests check the library exports them all)
 SYMBOLS = (
     "epi_create", "epi_destroy", "epi_last_error", "epi_abi_version", "epi_n_params",
-    "epi_param_name", "epi_df_params", "epi_eval", "epi_eval_submit", "epi_eval_wait", "epi_eval_device", "epi_eval_detail",
+    "epi_param_name", "epi_df_params", "epi_eval", "epi_eval_submit", "epi_eval_wait", "epi_eval_device", "epi_eval_device_range", "epi_reserve", "epi_eval_detail",
     "epi_n_series", "epi_trajectories", "epi_n_series_ext", "epi_trajectories_ext", "epi_quantiles", "epi_sampler_init", "epi_sampler_run",
     "epi_sampler_adapt", "epi_sampler_set_scale", "epi_sampler_state_device", "epi_sampler_set_population",
     "epi_sampler_get", "epi_sampler_stats", "epi_sampler_pt_stats", "epi_sampler_record", "epi_sampler_draws", "epi_sampler_draws_subset",
@@ -134,6 +134,8 @@ def load():
     lib.epi_eval_submit.argtypes = [vp, C.c_int, _dp, i64, C.c_int, _dp, _dp, ip]
     lib.epi_eval_wait.argtypes = [vp, C.c_int]
     lib.epi_eval_device.argtypes = [vp, vp, i64, vp, vp, vp, vp]
+    lib.epi_eval_device_range.argtypes = [vp, vp, i64, i64, i64, i64, vp, vp, vp, vp]
+    lib.epi_reserve.argtypes = [vp, i64]
     lib.epi_eval_detail.argtypes = [vp, _dp, i64, C.c_int, ip, ip, _dp]
     lib.epi_n_series.argtypes = [vp]
     lib.epi_trajectories.argtypes = [vp, _dp, i64, C.c_int, i32, _dp, ip, ip]

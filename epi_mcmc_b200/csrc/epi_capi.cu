@@ -417,15 +417,17 @@ extern "C" int epi_create(const epi_model_desc *desc, const epi_data *data, int 
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { rc = epi_fail(h, EPI_ERR_CUDA, "stream"); break; }
     if (cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking) != cudaSuccess) { rc = epi_fail(h, EPI_ERR_CUDA, "stream"); break; }
     cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&h->ev_stagger, cudaEventDisableTiming);
+    for (int k = 0; k < epi_handle::kMaxWays - 1; ++k) {
+      if (cudaStreamCreateWithFlags(&h->split_stream[k], cudaStreamNonBlocking) != cudaSuccess) { rc = epi_fail(h, EPI_ERR_CUDA, "stream"); break; }
+      cudaEventCreateWithFlags(&h->ev_join[k], cudaEventDisableTiming);
+    }
+    if (rc) break;
     { const char *env = getenv("EPI_PASS2_RESTART"); h->restart = !(env && env[0] == '0'); }
     { const char *env = getenv("EPI_WINDOW_ONLY"); h->window_only = !(env && env[0] == '0'); }
     { const char *env = getenv("EPI_PASS1_CHUNK"); h->pass1_chunk = !(env && env[0] == '0'); }
     { const char *env = getenv("EPI_FORCE_R_FALLBACK"); h->force_need_r = (env && env[0] == '1'); }
     { const char *env = getenv("EPI_ODE_LANES"); h->ode_lanes = (env && (env[0] == '1' || env[0] == '2' || env[0] == '4')) ? env[0] - '0' : 0; }
-    { const char *env = getenv("EPI_SCORE_STRIPS"); h->score_strips = (env && env[0] == '2') ? 2 : 4; }
-    { const char *env = getenv("EPI_SPLIT_STREAMS"); h->split = (env && (env[0] == '1' || env[0] == '2')); h->split_mode = (env && env[0] == '2') ? 2 : 1; }
+    { const char *env = getenv("EPI_SPLIT_WAYS"); h->split_ways = (env && env[0] >= '1' && env[0] <= '8') ? env[0] - '0' : 0; }
     for (auto &ev : h->ev) cudaEventCreate(&ev);
     rc = fill_model(h, *desc, *data);
   } while (0);
@@ -458,8 +460,10 @@ extern "C" void epi_destroy(epi_handle *h) {
   if (h->stream) cudaStreamDestroy(h->stream);
   if (h->stream2) cudaStreamDestroy(h->stream2);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
-  if (h->ev_join) cudaEventDestroy(h->ev_join);
-  if (h->ev_stagger) cudaEventDestroy(h->ev_stagger);
+  for (int k = 0; k < epi_handle::kMaxWays - 1; ++k) {
+    if (h->split_stream[k]) { cudaStreamSynchronize(h->split_stream[k]); cudaStreamDestroy(h->split_stream[k]); }
+    if (h->ev_join[k]) cudaEventDestroy(h->ev_join[k]);
+  }
   for (int s = 0; s < 2; ++s) {
     cudaFree(h->stage[s]);
     if (h->ev_h2d[s]) { cudaEventDestroy(h->ev_h2d[s]); cudaEventDestroy(h->ev_free[s]); cudaEventDestroy(h->ev_done[s]); }
@@ -513,12 +517,12 @@ int epi_ensure_workspace(epi_handle *h, Workspace &w, const DevModel &M, int64_t
   CUDA_OK(h, cudaMalloc(&w.aos, sizeof(double) * (size_t)(M.d * ld)));
   // S histories: [chain][group][pitch], pitch = days rounded up to even (16-byte aligned rows for the bulk copies)
   CUDA_OK(h, cudaMalloc(&w.hist1, sizeof(double) * (size_t)(ld * NG * ((P1 + 1) & ~1))));
-  CUDA_OK(h, cudaMalloc(&w.hist2, sizeof(double) * (size_t)(ld * NG * ((P + 1) & ~1))));
+  CUDA_OK(h, cudaMalloc(&w.hist2, sizeof(double) * (size_t)(ld * NG * ((P + 7) & ~7))));  // four phase rows, hist_pitch2
   {
     const int NEQ = is_age(M.flavour) ? 10 : 4;
     CUDA_OK(h, cudaMalloc(&w.ckpt, sizeof(double) * (size_t)(ld * NEQ * (P1 < 64 ? P1 : 64))));
   }
-  CUDA_OK(h, cudaMalloc(&w.W, sizeof(double) * (size_t)(ld * NG * pad_rows(M.flavour) * 4)));  // [chain][group][delay][4]
+  CUDA_OK(h, cudaMalloc(&w.W, sizeof(double) * (size_t)(ld * NG * pad_rows(M.flavour) * (is_age(M.flavour) ? 3 : 2))));  // [chain][group][delay][KG]
   CUDA_OK(h, cudaMalloc(&w.pmeta, sizeof(int2) * (size_t)(ld * NK)));
   CUDA_OK(h, cudaMalloc(&w.offset, sizeof(int) * (size_t)ld));
   CUDA_OK(h, cudaMalloc(&w.pad, sizeof(int) * (size_t)ld));
@@ -543,8 +547,8 @@ static EvalArgs make_args(epi_handle *h, Workspace &w, const DevModel &M, const 
   a.M = &M; a.PT = h->PT; a.n_prior = h->n_prior;
   a.theta = d_theta + first; a.ld = ld; a.n = n; a.model_space = model_space;
   a.hist1 = w.hist1 + first * NG * (int64_t)((M.P1 + 1) & ~1);
-  a.hist2 = w.hist2 + first * NG * (int64_t)((M.P + 1) & ~1);
-  a.W = w.W + first * NG * pad_rows(M.flavour) * 4;
+  a.hist2 = w.hist2 + first * NG * (int64_t)((M.P + 7) & ~7);
+  a.W = w.W + first * NG * pad_rows(M.flavour) * (is_age(M.flavour) ? 3 : 2);
   // (`first` is a multiple of the 32-chain checkpoint tile)
   a.ckpt = h->restart ? w.ckpt + first * (is_age(M.flavour) ? 10 : 4) * (int64_t)(M.P1 < 64 ? M.P1 : 64) : nullptr;
   a.pmeta = w.pmeta + first * NK;
@@ -558,7 +562,6 @@ static EvalArgs make_args(epi_handle *h, Workspace &w, const DevModel &M, const 
   a.window_only = h->window_only ? 1 : 0;
   a.pass1_chunk = h->pass1_chunk ? 1 : 0;
   a.ode_lanes = h->ode_lanes;
-  a.score_strips = h->score_strips;
   a.need_r = w.need_r + first;
   a.force_need_r = h->force_need_r ? 1 : 0;
   a.n_launches = &h->launches;
@@ -570,30 +573,43 @@ static EvalArgs make_args(epi_handle *h, Workspace &w, const DevModel &M, const 
 int epi_launch_eval_ws(epi_handle *h, Workspace &w, const DevModel &M, const double *d_theta, int64_t ld, int64_t n,
                        int model_space, double *d_logl, double *d_logp, int *d_status, double *d_terms,
                        double *d_series, cudaStream_t stream, int ns_total) {
-  cudaError_t e;
-  // Large batches are cut in two halves that run on two streams.  Every phase of the pipeline is
-  // latency bound on its own (ncu, profiles/r1_v2: FP64 pipe 42-50 % busy in the ODE kernels,
-  // 26 % in the LDS/log-heavy score kernel), so letting the ODE kernel of one half share the SMs
-  // with the score/profile kernel of the other half fills issue slots neither can use alone.
-  const int64_t half = ((n / 2 + 127) / 128) * 128;
-  if (h->split && !h->timing && n >= 16384 && half < n) {
-    EvalArgs a0 = make_args(h, w, M, d_theta, ld, half, 0, model_space, d_logl, d_logp, d_status, d_terms, d_series, stream, ns_total);
-    EvalArgs a1 = make_args(h, w, M, d_theta, ld, n - half, half, model_space, d_logl, d_logp, d_status, d_terms, d_series, h->stream2, ns_total);
-    cudaEventRecord(h->ev_fork, stream);
-    cudaStreamWaitEvent(h->stream2, h->ev_fork, 0);
-    if (h->split_mode == 2) a0.ev_after_mid = h->ev_stagger;  // half B starts when half A has finished k_mid
-    e = launch_eval(a0);
-    if (h->split_mode == 2) cudaStreamWaitEvent(h->stream2, h->ev_stagger, 0);
-    if (e == cudaSuccess) e = launch_eval(a1);
-    cudaEventRecord(h->ev_join, h->stream2);
-    cudaStreamWaitEvent(stream, h->ev_join, 0);
-  } else {
-    EvalArgs a = make_args(h, w, M, d_theta, ld, n, 0, model_space, d_logl, d_logp, d_status, d_terms, d_series, stream, ns_total);
-    a.ev = h->timing ? h->ev : nullptr;
-    e = launch_eval(a);
-  }
+  EvalArgs a = make_args(h, w, M, d_theta, ld, n, 0, model_space, d_logl, d_logp, d_status, d_terms, d_series, stream, ns_total);
+  a.ev = h->timing ? h->ev : nullptr;
+  const cudaError_t e = launch_eval(a);
   if (e != cudaSuccess) return epi_fail(h, EPI_ERR_CUDA, "kernel launch: %s", cudaGetErrorString(e));
   return EPI_OK;
+}
+
+// The chains [first, first + n) of a batch, with the workspace rows of that range: ranges of one batch that do not
+// overlap may be in flight on different streams at the same time (the caller orders them against whatever produced
+// theta and consumes the results).  `first` must be a multiple of 128.
+int epi_launch_eval_range(epi_handle *h, Workspace &w, const DevModel &M, const double *d_theta, int64_t ld, int64_t first,
+                          int64_t n, double *d_logl, double *d_logp, int *d_status, cudaStream_t stream) {
+  EvalArgs a = make_args(h, w, M, d_theta, ld, n, first, 0, d_logl, d_logp, d_status, nullptr, nullptr, stream, 0);
+  const cudaError_t e = launch_eval(a);
+  if (e != cudaSuccess) return epi_fail(h, EPI_ERR_CUDA, "kernel launch: %s", cudaGetErrorString(e));
+  return EPI_OK;
+}
+
+extern "C" int epi_eval_device_range(epi_handle *h, const double *d_theta_soa, int64_t ld, int64_t n_total, int64_t first,
+                                     int64_t n, double *d_logl, double *d_logp, int32_t *d_status, void *stream) {
+  if (!h || !d_theta_soa || n < 0 || first < 0 || first + n > n_total || ld < n_total || (first & 127))
+    return epi_fail(h, EPI_ERR_ARG, "bad argument (first must be a multiple of 128, first + n <= n_total <= ld)");
+  if (n == 0) return EPI_OK;
+  CUDA_OK(h, cudaSetDevice(h->device));
+  if (n_total > h->ws.cap) {
+    // growing the workspace frees what other ranges may still be using: the caller sizes it first (epi_reserve)
+    return epi_fail(h, EPI_ERR_STATE, "workspace holds %lld chains, the batch has %lld: call epi_reserve first",
+                    (long long)h->ws.cap, (long long)n_total);
+  }
+  return epi_launch_eval_range(h, h->ws, h->M, d_theta_soa, ld, first, n, d_logl, d_logp, d_status,
+                               stream ? (cudaStream_t)stream : h->stream);
+}
+
+extern "C" int epi_reserve(epi_handle *h, int64_t n) {
+  if (!h || n < 1) return epi_fail(h, EPI_ERR_ARG, "bad argument");
+  CUDA_OK(h, cudaSetDevice(h->device));
+  return epi_ensure_workspace(h, h->ws, h->M, n, false);
 }
 
 // ---------------------------------------------------------------------- eval

@@ -43,15 +43,17 @@ struct epi_handle {
   epi::Workspace ws, ws_traj;
   epi::SamplerState *sampler = nullptr;
   cudaStream_t stream = nullptr, stream2 = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_stagger = nullptr;
-  int split_mode = 1;
+  // the sampler runs a small population as `ways` slices, each a free-running pipeline on its own stream
+  // (epi_sampler_run); split_stream[k] serves slice k + 1, the handle's stream slice 0
+  static constexpr int kMaxWays = 8;
+  cudaStream_t split_stream[kMaxWays - 1] = {};
+  cudaEvent_t ev_fork = nullptr, ev_join[kMaxWays - 1] = {};
+  int split_ways = 0;  // EPI_SPLIT_WAYS=1..8: force the number of slices (0: by population size)
   bool force_need_r = false;  // EPI_FORCE_R_FALLBACK=1: every chain takes the R-tracking instance (bit-identical results)
   bool pass1_chunk = true;  // EPI_PASS1_CHUNK=0: whole-period pass 1 in one round (bit-identical results)
   bool window_only = true;  // EPI_WINDOW_ONLY=0: pass 2 and the score sweep cover the whole period (bit-identical results)
   int ode_lanes = 0;  // EPI_ODE_LANES=1|2|4: force the lanes-per-chain mapping of the age ODE kernels (0: by batch size)
-  int score_strips = 4;  // EPI_SCORE_STRIPS=2|4
   bool restart = true;  // pass 2 resumes from the pass-1 checkpoint (EPI_PASS2_RESTART=0: re-integrate everything)
-  bool split = false;  // EPI_SPLIT_STREAMS=1: run the two halves of a large batch on two streams (measured slower: 6.41 vs 6.03 ms)
   // epi_eval_submit/wait: two staging buffers for the raw host theta and the events that order
   // copy stream (stream2) and compute stream
   double *stage[2] = {nullptr, nullptr};
@@ -67,6 +69,8 @@ struct epi_handle {
 int epi_fail(epi_handle *h, int rc, const char *fmt, ...);
 void epi_sampler_free(epi_handle *h);
 int epi_ensure_workspace(epi_handle *h, epi::Workspace &w, const epi::DevModel &M, int64_t n, int want_series);
+int epi_launch_eval_range(epi_handle *h, epi::Workspace &w, const epi::DevModel &M, const double *d_theta, int64_t ld,
+                          int64_t first, int64_t n, double *d_logl, double *d_logp, int *d_status, cudaStream_t stream);
 int epi_launch_eval_ws(epi_handle *h, epi::Workspace &w, const epi::DevModel &M, const double *d_theta, int64_t ld,
                        int64_t n, int model_space, double *d_logl, double *d_logp, int *d_status, double *d_terms,
                        double *d_series, cudaStream_t stream, int ns_total = 0);

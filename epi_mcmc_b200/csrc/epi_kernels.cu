@@ -28,6 +28,18 @@ namespace epi {
 // of the score kernel's stall samples).
 __host__ __device__ constexpr int hist_pitch(int ndays) { return (ndays + 1) & ~1; }
 
+// The PASS-2 history (hist2, read by k_score / k_series) is stored in four PHASES per (chain, group):
+//   day d  ->  row (d & 3) of length Q = hist_pitch2(ndays) / 4, element d >> 2.
+// k_score's convolution gives every lane four CONSECUTIVE days and slides a register window of S over the delay
+// (one new S value per delay and lane instead of one per day and delay): the lanes of a warp then read S at a
+// stride of four days, which in a day-major row would be an eight-way shared-memory bank conflict and in the phase
+// rows is one conflict-free load (round 1, profiles/r1_v15_ncu_full.txt: 192 M shared wavefronts per launch, 4 LDS
+// per 6 DFMA, the FP64 pipe 30 % busy).  The thread-per-chain writer scatters 8 bytes per day either way.
+__host__ __device__ constexpr int hist_pitch2(int ndays) { return (ndays + 7) & ~7; }
+// index of day d in a history row: phase layout for pass 2 (Q = hist_pitch2 / 4), day-major for pass 1
+template <bool PASS2>
+__device__ __forceinline__ int hist_index(int d, int Q) { return PASS2 ? (d & 3) * Q + (d >> 2) : d; }
+
 // Pass-2 restart.  Both passes use the same fixed-step scheme and pass 2 has beta0 until its first
 // breakpoint, so its first D = floor(min breakpoint) - t0 days are BIT-identical to pass 1
 // (SURVEY.md §8d allows the restart provided the reduced step count is reported: bench.py does).
@@ -555,7 +567,8 @@ k_ode(const DevModel M, const double *__restrict__ theta, int64_t ld, int64_t n,
   bool need_r = false;
   const double *th = theta + i;
   const int ndays = PASS2 ? M.P : M.P1;
-  const int pitch = hist_pitch(ndays);
+  const int pitch = PASS2 ? hist_pitch2(ndays) : hist_pitch(ndays);
+  const int Q = pitch >> 2;  // phase-row length of the pass-2 history (hist_index)
   double *out = hist_out + (i * NG) * (int64_t)pitch;
 
   double y[NEQ];
@@ -598,7 +611,7 @@ k_ode(const DevModel M, const double *__restrict__ theta, int64_t ld, int64_t n,
       const double *in = hist1 + (i * NG) * (int64_t)pitch1;
       for (int d = 0; d < M.P; ++d)
 #pragma unroll
-        for (int g = 0; g < NG; ++g) out[g * pitch + d] = in[g * pitch1 + d % M.P1];
+        for (int g = 0; g < NG; ++g) out[g * pitch + hist_index<PASS2>(d, Q)] = in[g * pitch1 + d % M.P1];
       if constexpr (!FULL) {
         if constexpr (!TR) { if (need_r_flag) need_r_flag[i] = 0; }
         return;
@@ -628,7 +641,7 @@ k_ode(const DevModel M, const double *__restrict__ theta, int64_t ld, int64_t n,
         const double *in = hist1 + (i * NG) * (int64_t)pitch1;
         for (int d = 0; d <= d0; ++d)
 #pragma unroll
-          for (int g = 0; g < NG; ++g) out[g * pitch + d] = in[g * pitch1 + d];
+          for (int g = 0; g < NG; ++g) out[g * pitch + hist_index<PASS2>(d, Q)] = in[g * pitch1 + d];
 #pragma unroll
         for (int q = 0; q < NEQ; ++q)
           if (TR || !is_r_state<FL>(q)) y[q] = ck[((int64_t)d0 * NEQ + q) * kTile];
@@ -698,8 +711,8 @@ k_ode(const DevModel M, const double *__restrict__ theta, int64_t ld, int64_t n,
       pa = pb;
       if (step_done) ++s;
     }
-    out[d] = y[0];
-    if constexpr (NG == 2) out[pitch + d] = y[5];
+    out[hist_index<PASS2>(d, Q)] = y[0];
+    if constexpr (NG == 2) out[pitch + hist_index<PASS2>(d, Q)] = y[5];
     if constexpr (FULL) write_ext<FL>(M, th, ld, bp, nbp, (double)(t0 + d), y, inv1, eo, M.P, d);
     if constexpr (!PASS2) {
       if (ck && d < cdays) {
@@ -873,7 +886,8 @@ k_ode_age2(const DevModel M, const double *__restrict__ theta, int64_t ld, int64
     if (retry_status && !(retry_status[i] & kStRetry)) return;
     if (ndays_limit > 0) nint = min(nint, ndays_limit);
   }
-  double *out = hist_out + (i * 2 + g) * (int64_t)hist_pitch(ndays);
+  const int pitch = PASS2 ? hist_pitch2(ndays) : hist_pitch(ndays), Q = pitch >> 2;
+  double *out = hist_out + (i * 2 + g) * (int64_t)pitch;
 
   const double Ngrp = g ? M.No : M.Ny;
   const double invN = 1.0 / Ngrp;
@@ -890,7 +904,7 @@ k_ode_age2(const DevModel M, const double *__restrict__ theta, int64_t ld, int64
     if (off == EPI_INVALID_DATA_OFFSET) {
       // pass 2 skipped: the pass-1 rows are recycled into the P-length slices (:216-223)
       const double *in = hist1 + (i * 2 + g) * (int64_t)hist_pitch(M.P1);
-      for (int d = 0; d < M.P; ++d) out[d] = in[d % M.P1];
+      for (int d = 0; d < M.P; ++d) out[hist_index<PASS2>(d, Q)] = in[d % M.P1];
       if (g == 0 && need_r_flag) need_r_flag[i] = 0;
       return;
     }
@@ -909,7 +923,7 @@ k_ode_age2(const DevModel M, const double *__restrict__ theta, int64_t ld, int64
       d0 = dd > 0 ? (int)fmin(dd, (double)min(cdays - 1, ndays - 1)) : 0;
       if (d0 > 0) {
         const double *in = hist1 + (i * 2 + g) * (int64_t)hist_pitch(M.P1);
-        for (int d = 0; d <= d0; ++d) out[d] = in[d];
+        for (int d = 0; d <= d0; ++d) out[hist_index<PASS2>(d, Q)] = in[d];
 #pragma unroll
         for (int q = 0; q < (TR ? 5 : 4); ++q) y[q] = ck[((int64_t)d0 * 10 + q) * kTile];
       }
@@ -942,7 +956,7 @@ k_ode_age2(const DevModel M, const double *__restrict__ theta, int64_t ld, int64
       }
       rk4_piece_age2<TR>(a1, gamma, sg, y, pa, b, invN, Ngrp, nb, pairmask, even_lane, need_r);
     }
-    out[d] = y[0];
+    out[hist_index<PASS2>(d, Q)] = y[0];
     if constexpr (!PASS2) {
       if (ck && d < cdays) {
 #pragma unroll
@@ -1139,7 +1153,8 @@ k_ode_age4(const DevModel M, const double *__restrict__ theta, int64_t ld, int64
     if (retry_status && !(retry_status[i] & kStRetry)) alive = false;
     if (ndays_limit > 0) nint = min(nint, ndays_limit);
   }
-  double *out = hist_out + (i * 2 + g) * (int64_t)hist_pitch(ndays);
+  const int pitch = PASS2 ? hist_pitch2(ndays) : hist_pitch(ndays), Q = pitch >> 2;
+  double *out = hist_out + (i * 2 + g) * (int64_t)pitch;
   const bool writes_s = !L.half;
   // model-age-groups2q.R:157-158
   double u = L.half ? 0.0 : (g ? M.No : M.Ny - 1.0);
@@ -1155,7 +1170,7 @@ k_ode_age4(const DevModel M, const double *__restrict__ theta, int64_t ld, int64
       // pass 2 skipped: the pass-1 rows are recycled into the P-length slices (:216-223)
       if (alive && writes_s) {
         const double *in = hist1 + (i * 2 + g) * (int64_t)hist_pitch(M.P1);
-        for (int d = 0; d < M.P; ++d) out[d] = in[d % M.P1];
+        for (int d = 0; d < M.P; ++d) out[hist_index<PASS2>(d, Q)] = in[d % M.P1];
       }
       if (alive && (lane & 3) == 0 && need_r_flag) need_r_flag[i] = 0;
       alive = false;
@@ -1179,7 +1194,7 @@ k_ode_age4(const DevModel M, const double *__restrict__ theta, int64_t ld, int64
       if (d0 > 0) {
         if (writes_s) {
           const double *in = hist1 + (i * 2 + g) * (int64_t)hist_pitch(M.P1);
-          for (int d = 0; d <= d0; ++d) out[d] = in[d];
+          for (int d = 0; d <= d0; ++d) out[hist_index<PASS2>(d, Q)] = in[d];
         }
         u = ck[((int64_t)d0 * 10) * kTile];
         v = ck[((int64_t)d0 * 10 + 1) * kTile];
@@ -1237,7 +1252,7 @@ k_ode_age4(const DevModel M, const double *__restrict__ theta, int64_t ld, int64
         }
       }
     }
-    if (live && writes_s) out[d] = u;
+    if (live && writes_s) out[hist_index<PASS2>(d, Q)] = u;
     if constexpr (!PASS2) {
       if (ck && live && d < cdays) { ck[((int64_t)d * 10) * kTile] = u; ck[((int64_t)d * 10 + 1) * kTile] = v; }
     }
@@ -1512,8 +1527,9 @@ k_mid(const DevModel M, const double *__restrict__ theta, int64_t ld, int64_t n,
   __syncwarp();
   build_profiles<FL>(w, n_, lane);
   // profiles to HBM already in the absolute-delay layout k_score convolves with,
-  // Wabs[group][delay 0..kPad-1][4] (column = profile within the group, zero outside its support), so
-  // that the reader can take the whole 2 KB (2.5 KB for age-2i) per group with one bulk copy
+  // Wabs[group][delay 0..kPad-1][KG] (column = profile within the group, zero outside its support; a block of
+  // four delays is 4 KG consecutive doubles), so that the reader can take the whole table of a chain with one
+  // bulk copy
   {
     constexpr int KG = NK / NG;
     int *meta = reinterpret_cast<int *>(w.cdf);  // the CDF scratch is free again: (dmin, n) per profile
@@ -1521,15 +1537,11 @@ k_mid(const DevModel M, const double *__restrict__ theta, int64_t ld, int64_t n,
     for (int q = 0; q < NK; ++q)
       if (lane == 0) { meta[2 * q] = dmin_[q]; meta[2 * q + 1] = n_[q]; }
     __syncwarp();
-    double *dst = Wg + (int64_t)chain * NG * PAD * 4;
-    for (int i = lane; i < NG * PAD * 4; i += 32) {
-      const int c = i & 3, grp = i / (PAD * 4), dly = (i >> 2) - grp * PAD, q = grp * KG + c;
-      double v = 0.0;
-      if (c < KG) {
-        const unsigned o = (unsigned)(dly - meta[2 * q]);
-        if (o < (unsigned)meta[2 * q + 1]) v = w.W[q * EPI_MAX_TAPS + o];
-      }
-      dst[i] = v;
+    double *dst = Wg + (int64_t)chain * NG * PAD * KG;
+    for (int i = lane; i < NG * PAD * KG; i += 32) {
+      const int grp = i / (PAD * KG), rem = i - grp * (PAD * KG), dly = rem / KG, c = rem - dly * KG, q = grp * KG + c;
+      const unsigned o = (unsigned)(dly - meta[2 * q]);
+      dst[i] = (o < (unsigned)meta[2 * q + 1]) ? w.W[q * EPI_MAX_TAPS + o] : 0.0;
     }
 #pragma unroll
     for (int q = 0; q < NK; ++q)
@@ -1596,6 +1608,20 @@ __device__ __forceinline__ void window(int offset, int n, int T, int &dstart) {
   dstart = ds;
 }
 
+// rare: a day with terms of several sizes (the last-8-days hospital weight, :552-554): slots 1..K-1 of that day.
+// Kept out of line: inlined into every series of every day it was most of k_score's code (instruction cache).
+__device__ __noinline__ double score_more_slots(const Slot *__restrict__ day, int K, const double2 *__restrict__ ltab, double mu) {
+  double acc = 0.0;
+  const double lmu = tlog_pos(mu, ltab);
+  for (int k = 1; k < K; ++k) {
+    const Slot z = ldg_slot(day + k);
+    if (z.n == 0.0f) continue;
+    const double x = (double)z.x;
+    acc += x * lmu - fma((double)z.n, z.size, x) * tlog_pos(z.size + mu, ltab);
+  }
+  return acc;
+}
+
 // score the slots of scored series s that read model day t (value v)
 // One scored series at model day t: x*log(mu) - (x + n*size)*log(size + mu) summed over the slots of
 // that day (= size*log(size/(size+mu)) + x*log(mu/(size+mu)) minus its data-only part size*log(size)).
@@ -1611,14 +1637,7 @@ __device__ __forceinline__ double score_slots(const DevModel &M, const double2 *
     acc = x * tlog_pos(mu, ltab) - fma((double)first.n, first.size, x) * tlog_pos(first.size + mu, ltab);
   }
   if (r < M.multi_begin[s]) return acc;
-  const int K = M.K[s];
-  for (int k = 1; k < K; ++k) {  // rare: days with terms of several sizes (the last-8-days hospital weight)
-    const Slot z = ldg_slot(M.slots[s] + (size_t)r * K + k);
-    if (z.n == 0.0f) continue;
-    const double x = (double)z.x;
-    acc += x * tlog_pos(mu, ltab) - fma((double)z.n, z.size, x) * tlog_pos(z.size + mu, ltab);
-  }
-  return acc;
+  return acc + score_more_slots(M.slots[s] + (size_t)r * M.K[s], M.K[s], ltab, mu);
 }
 
 // all scored series of one model day: slot 0 of every series is fetched (DaySlots::load, issued
@@ -1643,14 +1662,17 @@ struct DaySlots {
 };
 
 // ---- shared-memory carve-up of k_score / k_series (per warp) -------------------
-// theta[EPI_MAX_PARAMS] | Wabs[NG][kPad][4] | S[NG][kPad + P]
+// theta[EPI_MAX_PARAMS] | Wabs[NG][kPad][KG] | S[NG][4 phases][kPad/4 + Q]
 // Wabs holds the KG = NK/NG latency profiles of one S group indexed by ABSOLUTE delay
 // (zero outside a profile's support), so that one sweep over the delay feeds KG
-// independent FMA chains from a single S load.
+// independent FMA chains per day from a single S value.
+// S is kept in the four-phase layout of hist2 (hist_index): phase row r of a group holds the padded-index
+// elements e = 4 a + r, a = 0 .. kPad/4 + Q - 1 (the first kPad/4 entries are the prefill x[1..padding], :118,127).
 template <int FL>
 __host__ __device__ constexpr int score_smem_doubles(int ndays) {
-  // even, so that every warp's Wabs stays 16-byte aligned for the double2 weight loads
-  return (EPI_MAX_PARAMS + Traits<FL>::NG * Traits<FL>::kPad * 4 + Traits<FL>::NG * (Traits<FL>::kPad + hist_pitch(ndays)) + 3) & ~1;
+  // even, so that every warp's regions stay 16-byte aligned for the double2 weight loads and the bulk copies
+  return (EPI_MAX_PARAMS + Traits<FL>::NG * Traits<FL>::kPad * (Traits<FL>::NK / Traits<FL>::NG) +
+          Traits<FL>::NG * (Traits<FL>::kPad + hist_pitch2(ndays)) + 3) & ~1;
 }
 
 struct ScoreSmem {
@@ -1663,7 +1685,7 @@ __device__ __forceinline__ ScoreSmem carve_score(double *base, int ndays) {
   ScoreSmem w;
   w.theta = base;
   w.Wabs = base + EPI_MAX_PARAMS;
-  w.S = w.Wabs + Traits<FL>::NG * Traits<FL>::kPad * 4;
+  w.S = w.Wabs + Traits<FL>::NG * Traits<FL>::kPad * (Traits<FL>::NK / Traits<FL>::NG);
   w.mbar = reinterpret_cast<uint64_t *>(base + score_smem_doubles<FL>(ndays) - 2);
   return w;
 }
@@ -1676,18 +1698,19 @@ __device__ __forceinline__ void stage_score(const DevModel &M, const ScoreSmem &
                                             const double *__restrict__ hist2, const double *__restrict__ Wg,
                                             const int2 *__restrict__ pmeta, int P, int lane, int *dmin_, int *n_,
                                             int *lo, int *hi) {
-  constexpr int NK = Traits<FL>::NK, NG = Traits<FL>::NG, KG = NK / NG, PAD = Traits<FL>::kPad;
-  // asynchronous bulk copies (TMA unit): the S rows and the profiles, one mbarrier
+  constexpr int NK = Traits<FL>::NK, NG = Traits<FL>::NG, KG = NK / NG, PAD = Traits<FL>::kPad, PADQ = PAD / 4;
+  const int pitch = hist_pitch2(P), Q = pitch >> 2, AS = PADQ + Q;  // AS: phase-row stride in shared memory
+  // asynchronous bulk copies (TMA unit): the four phase rows of every S group and the profile table, one mbarrier
   {
-    const int pitch = hist_pitch(P), stride = PAD + pitch;
     if (lane == 0) mbar_init(w.mbar, 1);
     __syncwarp();
     if (lane == 0) {
-      const unsigned hb = (unsigned)pitch * 8u, wb = (unsigned)(NG * PAD * 4 * 8);
-      mbar_expect_tx(w.mbar, hb * NG + wb);
+      const unsigned rb = (unsigned)Q * 8u, wb = (unsigned)(NG * PAD * KG * 8);
+      mbar_expect_tx(w.mbar, rb * 4 * NG + wb);
 #pragma unroll
-      for (int g = 0; g < NG; ++g) bulk_g2s(w.S + g * stride + PAD, hist2 + (chain * NG + g) * (int64_t)pitch, hb, w.mbar);
-      bulk_g2s(w.Wabs, Wg + (int64_t)chain * NG * PAD * 4, wb, w.mbar);
+      for (int r = 0; r < 4 * NG; ++r)  // r = group * 4 + phase: rows are consecutive in HBM and AS apart here
+        bulk_g2s(w.S + r * AS + PADQ, hist2 + chain * NG * (int64_t)pitch + (int64_t)r * Q, rb, w.mbar);
+      bulk_g2s(w.Wabs, Wg + (int64_t)chain * NG * PAD * KG, wb, w.mbar);
     }
   }
   for (int p = lane; p < M.d; p += 32) {
@@ -1706,37 +1729,69 @@ __device__ __forceinline__ void stage_score(const DevModel &M, const ScoreSmem &
     lo[g] = min(lo[g], pm.x);
     hi[g] = max(hi[g], pm.x + pm.y - 1);
   }
-  stage_history_end<FL>(M, w.S, w.mbar, P, lane);
+  // prefill slots x[1..padding] = N - Initial (:118,127) in front of every phase row
+#pragma unroll
+  for (int g = 0; g < NG; ++g) {
+    const double s0 = Traits<FL>::kAge ? (g == 0 ? M.Ny - 1.0 : M.No) : M.N - 1.0;
+    for (int j = lane; j < PAD; j += 32) w.S[(g * 4 + (j & 3)) * AS + (j >> 2)] = s0;
+  }
+  mbar_wait(w.mbar, 0);
+  __syncwarp();
 }
 
-// convolute() (model-age-groups2q.R:42-45) of the KG profiles of one S group at the two
-// padded day indices ja and ja + 32 in ONE sweep over the delay d:
-//   conv_q(t) = sum_d Wabs[d][q] * S[t - d]
-// (ncu, profiles/r1_v1: the per-profile serial FMA chain with two LDS per FMA left the
-// FP64 pipe 17 % busy; here every S load feeds KG chains and every weight load 2 days.)
-// NS day strips per lane (days ja, ja + 32, ..., ja + 32 (NS - 1)): every weight load feeds NS days.
-// c[s * KG + q] = conv_q(day ja + 32 s).  The FMA chain of one (day, profile) runs over the delays in ascending
-// order whatever NS is, so the result does not depend on it.
-template <int KG, int PAD, int NS>
-__device__ __forceinline__ void conv_group(const double *__restrict__ Sg, const double *__restrict__ Wabs, int lo,
-                                           int hi, int ja, int P, double *c) {
-  const double *x[NS];
+// S at padded day index j (sim time padding + 1 + j) of group g in the staged phase layout
+template <int PAD>
+__device__ __forceinline__ double staged_s(const double *__restrict__ S, int g, int AS, int j) {
+  return S[(g * 4 + (j & 3)) * AS + PAD / 4 + (j >> 2)];
+}
+
+// convolute() (model-age-groups2q.R:42-45) of the KG profiles of one S group for the FOUR consecutive padded day
+// indices 4 G .. 4 G + 3 of this lane, in one sweep over the delay:
+//   conv_q(j) = sum_d Wabs[d][q] * S[j - d]          acc[r * KG + q] = conv_q(4 G + r)
+// The delays run in blocks of four (blk_lo .. blk_hi, delay = 4 blk + u; the table is zero outside a profile's
+// support, and fma(+0, x, acc) == acc).  Within a block the sixteen (day, delay) pairs of a lane read only SEVEN
+// distinct S values  v[k] = S[4 G + 3 - 4 blk - k], k = 0..6,  three of which are the previous block's last three:
+// four new S loads (one per phase row, consecutive lanes -> consecutive addresses, no bank conflict) and 4 KG
+// broadcast weights feed 16 KG DFMA — against 4 loads per 6 DFMA when a lane's days were 32 apart.
+// The FMA chain of one (day, profile) still runs over the delays in ascending order.
+template <int KG, int PAD>
+__device__ __forceinline__ void conv_tile4(const double *__restrict__ Sg, int AS, const double *__restrict__ Wabs,
+                                           int blk_lo, int blk_hi, int G, double *acc) {
 #pragma unroll
-  for (int s = 0; s < NS; ++s) x[s] = Sg + PAD + min(max(ja + 32 * s, 0), P - 1);  // out-of-range days are discarded later
+  for (int i = 0; i < 4 * KG; ++i) acc[i] = 0.0;
+  const double *p = Sg + PAD / 4 + G - blk_lo;  // phase-0 row, element a0 = PAD/4 + G - blk
+  const double *wp = Wabs + blk_lo * 4 * KG;
+  double v0 = p[3 * AS], v1 = p[2 * AS], v2 = p[AS];
+  auto block = [&](const double *pb, const double *wb, double a0, double a1, double a2, double &b4, double &b5, double &b6) {
+    const double v3 = pb[0];
+    b4 = pb[3 * AS - 1]; b5 = pb[2 * AS - 1]; b6 = pb[AS - 1];
+    double w[4 * KG];
 #pragma unroll
-  for (int i = 0; i < NS * KG; ++i) c[i] = 0.0;
-#pragma unroll 2
-  for (int d = lo; d <= hi; ++d) {
-    const double2 w01 = *reinterpret_cast<const double2 *>(Wabs + d * 4);
-    double w2 = 0.0;
-    if constexpr (KG == 3) w2 = Wabs[d * 4 + 2];
-#pragma unroll
-    for (int s = 0; s < NS; ++s) {
-      const double xs = x[s][-d];
-      c[s * KG + 0] = fma(w01.x, xs, c[s * KG + 0]);
-      c[s * KG + 1] = fma(w01.y, xs, c[s * KG + 1]);
-      if constexpr (KG == 3) c[s * KG + 2] = fma(w2, xs, c[s * KG + 2]);
+    for (int i = 0; i < 2 * KG; ++i) {
+      const double2 t = *reinterpret_cast<const double2 *>(wb + 2 * i);
+      w[2 * i] = t.x; w[2 * i + 1] = t.y;
     }
+    const double v[7] = {a0, a1, a2, v3, b4, b5, b6};
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int q = 0; q < KG; ++q) acc[r * KG + q] = fma(w[u * KG + q], v[3 - r + u], acc[r * KG + q]);
+  };
+  int blk = blk_lo;
+  // two blocks per trip: the second one continues from the first one's window, no register moves in between
+#pragma unroll 1
+  for (; blk + 1 <= blk_hi; blk += 2) {
+    double t4, t5, t6;
+    block(p, wp, v0, v1, v2, t4, t5, t6);
+    block(p - 1, wp + 4 * KG, t4, t5, t6, v0, v1, v2);
+    p -= 2;
+    wp += 8 * KG;
+  }
+  if (blk <= blk_hi) {
+    double t4, t5, t6;
+    block(p, wp, v0, v1, v2, t4, t5, t6);
   }
 }
 
@@ -1822,21 +1877,89 @@ struct AgeMap {
       for (int q = 0; q < 6; ++q) val[q] = on[q] ? inc[q] * r[q] : 0.0;
     }
   }
+  // the same for the three profiles of ONE group (G = 0: ycase, yhosp, ydied; G = 1: ocase, ohosp, odied):
+  // val[c] = inc[c] * rate_{3 G + c}(t), the same operations in the same order as values()
+  template <int G>
+  __device__ __forceinline__ void values3(const DevModel &M, const double *th, int t, const double *inc, double *val) const {
+    int k[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) k[c] = index(M, 3 * G + c, t);
+    double r[3];
+    if constexpr (Traits<FL>::k2i) {
+      if constexpr (G == 0) {
+        const double yifr0 = __ldg(M.y_ifr + k[0]), yhr1 = __ldg(M.y_hr + k[1]), yifr2 = __ldg(M.y_ifr + k[2]);
+        if (valid) { double c0 = th[9] * yifr0; c0 = c0 > 1 ? 1.0 : c0; r[0] = inc[0] * c0; }
+        else r[0] = inc[0] * th[9] * M.ifr_y1;
+        r[1] = inc[1] * th[11] * yhr1;
+        r[2] = inc[2] * yifr2;
+      } else {
+        const double oifr3 = __ldg(M.o_ifr + k[0]), ohr4 = __ldg(M.o_hr + k[1]), oifr5 = __ldg(M.o_ifr + k[2]);
+        if (valid) { double c3 = th[14] * oifr3; c3 = c3 > 1 ? 1.0 : c3; r[0] = inc[0] * c3; }
+        else r[0] = inc[0] * th[14] * M.ifr_o1;
+        r[1] = inc[1] * th[16] * ohr4;
+        r[2] = inc[2] * oifr5;
+      }
+#pragma unroll
+      for (int c = 0; c < 3; ++c) val[c] = on[3 * G + c] ? r[c] : 0.0;
+      return;
+    }
+    if constexpr (G == 0) {
+      const double yifr0 = __ldg(M.y_ifr + k[0]), g0 = __ldg(M.g + k[0]);
+      const double yhr1 = __ldg(M.y_hr + k[1]), g1 = __ldg(M.g + k[1]);
+      const double yifr2 = __ldg(M.y_ifr + k[2]), g2 = __ldg(M.g + k[2]), gt2 = __ldg(M.gtrimp + k[2]);
+      r[0] = th[9] * yifr0 * (1 + (th[21] - 1) * g0);   r[0] = r[0] > 1 ? 1.0 : r[0];  // gycr = pmin(1, .)
+      r[1] = th[10] * yhr1 * (1 + (th[22] - 1) * g1);                                   // gyhr
+      r[2] = yifr2 * (1 + (th[21] - 1) * g2) * (1 - th[42] * gt2);                      // gyifr
+    } else {
+      const double oifr3 = __ldg(M.o_ifr + k[0]);
+      const double ohr4 = __ldg(M.o_hr + k[1]);
+      const double oifr5 = __ldg(M.o_ifr + k[2]), gt5 = __ldg(M.gtrimp + k[2]);
+      r[0] = th[13] * oifr3;                            r[0] = r[0] > 1 ? 1.0 : r[0];  // gocr
+      r[1] = th[14] * ohr4;                                                             // gohr
+      r[2] = oifr5 * (1 - th[42] * gt5);                                                // goifr
+    }
+    if (all_on) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) val[c] = inc[c] * r[c];
+    } else {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) val[c] = on[3 * G + c] ? inc[c] * r[c] : 0.0;
+    }
+  }
 };
 
-// NS = day strips per lane and sweep (32 NS days per sweep): every profile-weight load of the convolution feeds NS days
-template <int FL, int NS>
+// one scored series at one model day: the slot fetch (issued before the day's model value is computed) and its score
+struct SeriesSlot {
+  Slot first;
+  int r;
+  bool ok;
+  __device__ __forceinline__ void load(const DevModel &M, int s, int t, int dstart_s) {
+    r = t - dstart_s;
+    ok = r >= 0 && r < M.n_obs[s];
+    first = ok ? ldg_slot(M.slots[s] + (size_t)r * M.K[s]) : Slot{0.0, 0.0f, 0.0f};
+  }
+  __device__ __forceinline__ double score(const DevModel &M, const double2 *__restrict__ ltab, int s, double v) const {
+    return score_slots(M, ltab, s, r, ok, first, v);
+  }
+};
+
+// the table of tlog(): computed once per device by k_fill_log_table (first launch), copied into shared memory
+// by every k_score block (round 1 recomputed its 128 divisions and logarithms in every block: 1 % of the kernel)
+__device__ double2 g_log_table[kLogTabN];
+__global__ void k_fill_log_table() { fill_log_table(g_log_table, threadIdx.x, blockDim.x); }
+
+template <int FL>
 __global__ void __launch_bounds__(128, 4)
 k_score(const DevModel M, const PriorTerm *__restrict__ PT, int n_prior, const double *__restrict__ theta, int64_t ld, int64_t n,
         const double *__restrict__ hist2, const int *__restrict__ offset, const int *__restrict__ padv,
         const double *__restrict__ Wg, const int2 *__restrict__ pmeta, int *__restrict__ status,
         double *__restrict__ logl, double *__restrict__ logp, double *__restrict__ terms, int window_only) {
-  constexpr int NK = Traits<FL>::NK, NG = Traits<FL>::NG;
+  constexpr int NK = Traits<FL>::NK, NG = Traits<FL>::NG, KG = NK / NG;
   extern __shared__ double smem[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int64_t chain = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
   double2 *ltab = reinterpret_cast<double2 *>(smem);  // block-shared log table, then the per-warp regions
-  fill_log_table(ltab, threadIdx.x, blockDim.x);
+  for (int i = threadIdx.x; i < kLogTabN; i += blockDim.x) ltab[i] = g_log_table[i];  // (filled once per device)
   __syncthreads();
   if (chain >= n) return;
   const int P = M.P;
@@ -1871,14 +1994,16 @@ k_score(const DevModel M, const PriorTerm *__restrict__ PT, int n_prior, const d
   const int off_raw = offset[chain];
   const int off = off_raw != EPI_INVALID_DATA_OFFSET ? off_raw : 1;  // :493-494
   constexpr int PAD = Traits<FL>::kPad;
-  const int stride = PAD + hist_pitch(P);
+  const int AS = PAD / 4 + (hist_pitch2(P) >> 2);  // phase-row stride of the staged S
 
   // calclogl reads the model series only inside the data windows [dstart_s, dstart_s + n_s - 1] (:497-590):
   // the sweep covers the union of the windows plus ONE day in front of it (the predecessor the first scored
   // day's increment needs), not the whole period.  Days before padding+1 read the 0 prefill.
   int dstart[kMaxSeries];
   int tlo = T, thi = 1;
-  for (int s = 0; s < M.n_series; ++s) {
+  constexpr int NSER = Traits<FL>::kAge ? 5 : 2;  // == M.n_series (static trip counts keep dstart[] in registers)
+#pragma unroll
+  for (int s = 0; s < NSER; ++s) {
     window(off, M.n_obs[s], T, dstart[s]);
     tlo = min(tlo, dstart[s]);
     thi = max(thi, dstart[s] + M.n_obs[s] - 1);
@@ -1890,51 +2015,91 @@ k_score(const DevModel M, const PriorTerm *__restrict__ PT, int n_prior, const d
   const int jlo = window_only ? tlo - 1 - (pad + 1) : min(tlo, pad + 1) - (pad + 1);
   const int jhi = window_only ? min(thi - (pad + 1), P - 1) : P - 1;
 
+  // days in front of padding+1 (j < 0) hold the 0 prefill of every model series (:118-136): scored with the value 0
+  for (int j = jlo + lane; j < 0; j += 32) {
+    const int t = pad + 1 + j;
+    if constexpr (Traits<FL>::kAge) {
+      DaySlots<5> slots;
+      slots.load(M, t, dstart, true);
+      const double v5[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+      slots.score(M, ltab, v5, acc);
+    } else {
+      DaySlots<2> slots;
+      slots.load(M, t, dstart, true);
+      const double v2[2] = {0.0, 0.0};
+      slots.score(M, ltab, v2, acc);
+    }
+  }
+
+  // Sweeps of 128 days: lane L owns the four consecutive days 4 G .. 4 G + 3, G = base / 4 + L (conv_tile4).  Lanes
+  // whose days lie behind the period convolve the last in-range quad again (their results are discarded).
+  const int Gmax = (P - 1) >> 2;
+  const int blo[2] = {lo[0] >> 2, lo[NG - 1] >> 2}, bhi[2] = {hi[0] >> 2, hi[NG - 1] >> 2};
   if constexpr (Traits<FL>::kAge) {
     AgeMap<FL> map;
     map.init(M, w.theta, off_raw, pad, P);
-    double carry[6] = {0, 0, 0, 0, 0, 0};
-    for (int base = jlo; base <= jhi; base += 32 * NS) {
-      double cy[NS * 3], co[NS * 3];
-      conv_group<3, PAD, NS>(w.S, w.Wabs, lo[0], hi[0], base + lane, P, cy);
-      conv_group<3, PAD, NS>(w.S + stride, w.Wabs + PAD * 4, lo[1], hi[1], base + lane, P, co);
+    double carry[6] = {0, 0, 0, 0, 0, 0};  // s2 of the day in front of the sweep (0 in front of day 0)
+    // One S group at a time, so that only twelve convolution results are live while a group's days are scored
+    // (with all 24 the day loop spilled: profiles/r2_summary.md): the y group scores y.casei and y.deadi and
+    // parks its hospital series, the o group scores o.casei, o.deadi and hospi = y.hospi + o.hospi (:552) and the
+    // sums of the ratio term (:563-565).  Per series the days still arrive in the same order as before.
+    for (int base = max(jlo, 0) & ~3; base <= jhi; base += 128) {
+      const int G = (base >> 2) + lane, Gc = min(G, Gmax);
+      const int j0 = 4 * G, t0 = pad + 1 + j0;
+      const bool mine = j0 + 3 >= jlo && j0 <= jhi;  // some day of this lane lies inside the swept range
+      double yhosp[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-      for (int half = 0; half < NS; ++half) {
-        const int j = base + 32 * half + lane;
-        if (base + 32 * half > jhi) break;  // (warp-uniform) strips behind the last swept day
-        const int t = pad + 1 + j;
-        const bool in = j >= 0 && j < P;
-        DaySlots<5> slots;
-        slots.load(M, t, dstart, j < P);
-        double val[6], inc[6];
+      for (int g = 0; g < 2; ++g) {
+        double c[12];  // c[r * 3 + q]
+        conv_tile4<3, PAD>(w.S + g * 4 * AS, AS, w.Wabs + g * PAD * 3, blo[g], bhi[g], Gc, c);
+        // s2 = N - conv (NA while stats::filter has no full window: reachable only for the hospital profiles, the
+        // other four define the padding (:113-114), so t - dmin >= n for every t > padding); 0 behind the period
 #pragma unroll
-        for (int q = 0; q < 6; ++q) {
-          const double Ng = q < 3 ? M.Ny : M.No;
-          double c = q < 3 ? cy[half * 3 + q] : co[half * 3 + q - 3];
-          // stats::filter leaves the first n-1 outputs NA: reachable only for the hospital profiles, the
-          // other four define the padding (:113-114), so t - dmin >= n for every t > padding
-          if ((q == 1 || q == 4) && t - dmin_[q] < n_[q]) c = NAN;
-          const double s2 = in ? Ng - c : 0.0;
-          double prev = __shfl_up_sync(0xffffffffu, s2, 1);
-          if (lane == 0) prev = carry[q];
-          carry[q] = __shfl_sync(0xffffffffu, s2, 31);
-          // c(s2[1], diff(s2)), :239: for j == 0 the predecessor (lane - 1 at j = -1, or the initial carry) is
-          // the 0.0 of an out-of-range day, and s2 - 0.0 == s2 exactly
-          inc[q] = s2 - prev;
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int q = 0; q < 3; ++q) {
+            double &x = c[r * 3 + q];
+            if (q == 1 && t0 + r - dmin_[g * 3 + 1] < n_[g * 3 + 1]) x = NAN;
+            x = (j0 + r < P) ? (g ? M.No : M.Ny) - x : 0.0;
+          }
+        // c(s2[1], diff(s2)), :239: the predecessor of the lane's first day is the last day of the lane below (the
+        // carry of the previous sweep for lane 0; the 0.0 in front of day 0, and s2 - 0.0 == s2 exactly)
+        double prev[3];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+          prev[q] = __shfl_up_sync(0xffffffffu, c[9 + q], 1);
+          if (lane == 0) prev[q] = carry[g * 3 + q];
+          carry[g * 3 + q] = __shfl_sync(0xffffffffu, c[9 + q], 31);
         }
-        if (in) {
-          map.values(M, w.theta, t, inc, val);
-        } else {
+        if (mine) {
 #pragma unroll
-          for (int q = 0; q < 6; ++q) val[q] = 0.0;  // days before padding+1 hold the 0 prefill
-        }
-        if (j < P) {
-          // scored series: y.casei, o.casei, hospi = y.hospi + o.hospi, y.deadi, o.deadi
-          // (profile order: ycase, yhosp, ydied, ocase, ohosp, odied)
-          const double v5[5] = {val[0], val[3], val[1] + val[4], val[2], val[5]};
-          slots.score(M, ltab, v5, acc);
-          if constexpr (!Traits<FL>::k2i)
-            if (t >= dstart[2] + M.d_hosp_o1 && t <= dstart[2] + M.d_hosp_o2) { ysum += val[1]; osum += val[4]; }  // :563-564
+          for (int r = 0; r < 4; ++r) {
+            const int j = j0 + r, t = t0 + r;
+            if (j >= P) break;
+            // scored series (profile order within a group: case, hosp, died):
+            //   0 y.casei, 1 o.casei, 2 hospi = y.hospi + o.hospi, 3 y.deadi, 4 o.deadi
+            SeriesSlot sc, sd, sh;
+            sc.load(M, g, t, dstart[g]);
+            sd.load(M, 3 + g, t, dstart[3 + g]);
+            if (g == 1) sh.load(M, 2, t, dstart[2]);
+            double inc[3], val[3];
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+              inc[q] = c[r * 3 + q] - prev[q];
+              prev[q] = c[r * 3 + q];
+            }
+            if (g == 0) map.template values3<0>(M, w.theta, t, inc, val);
+            else map.template values3<1>(M, w.theta, t, inc, val);
+            acc[g] += sc.score(M, ltab, g, val[0]);
+            acc[3 + g] += sd.score(M, ltab, 3 + g, val[2]);
+            if (g == 0) {
+              yhosp[r] = val[1];
+            } else {
+              acc[2] += sh.score(M, ltab, 2, yhosp[r] + val[1]);
+              if constexpr (!Traits<FL>::k2i)
+                if (t >= dstart[2] + M.d_hosp_o1 && t <= dstart[2] + M.d_hosp_o2) { ysum += yhosp[r]; osum += val[1]; }  // :563-564
+            }
+          }
         }
       }
     }
@@ -1943,34 +2108,48 @@ k_score(const DevModel M, const PriorTerm *__restrict__ PT, int n_prior, const d
     // hospi/deadi = c(v[1], diff(v)) (model-simple-ode-drj-cmp.R:115-122)
     const double rate[2] = {w.theta[4], 0.007};
     double carry[2] = {0, 0};
-    for (int base = jlo; base <= jhi; base += 32 * NS) {
-      double cc[NS * 2];
-      conv_group<2, PAD, NS>(w.S, w.Wabs, lo[0], hi[0], base + lane, P, cc);
+    for (int base = max(jlo, 0) & ~3; base <= jhi; base += 128) {
+      const int G = (base >> 2) + lane, Gc = min(G, Gmax);
+      double c[8];  // c[r * 2 + q]
+      conv_tile4<2, PAD>(w.S, AS, w.Wabs, blo[0], bhi[0], Gc, c);
+      const int j0 = 4 * G, t0 = pad + 1 + j0;
 #pragma unroll
-      for (int half = 0; half < NS; ++half) {
-        const int j = base + 32 * half + lane;
-        if (base + 32 * half > jhi) break;  // (warp-uniform) strips behind the last swept day
-        const int t = pad + 1 + j;
-        const bool in = j >= 0 && j < P;
-        DaySlots<2> slots;
-        slots.load(M, t, dstart, j < P);
-        double v2[2];
+      for (int i = 0; i < 8; ++i)  // both profiles define the padding (:59): never NA for t > padding
+        c[i] = (j0 + (i >> 1) < P) ? (M.N - c[i]) * rate[i & 1] : 0.0;
+      double prev[2];
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          const double c = cc[half * 2 + q];  // both profiles define the padding (:59): never NA for t > padding
-          const double cum = in ? (M.N - c) * rate[q] : 0.0;
-          double prev = __shfl_up_sync(0xffffffffu, cum, 1);
-          if (lane == 0) prev = carry[q];
-          carry[q] = __shfl_sync(0xffffffffu, cum, 31);
-          v2[q] = (j >= 0) ? cum - prev : 0.0;  // prev is 0 for t = pad+1 (prefill)
+      for (int q = 0; q < 2; ++q) {
+        prev[q] = __shfl_up_sync(0xffffffffu, c[6 + q], 1);
+        if (lane == 0) prev[q] = carry[q];  // 0 in front of day 0 (prefill)
+        carry[q] = __shfl_sync(0xffffffffu, c[6 + q], 31);
+      }
+      if (j0 + 3 >= jlo && j0 <= jhi) {
+#pragma unroll 1
+        for (int r = 0; r < 4; ++r) {
+          const int j = j0 + r, t = t0 + r;
+          if (j >= P) break;
+          DaySlots<2> slots;
+          slots.load(M, t, dstart, true);
+          const double v2[2] = {c[0] - prev[0], c[1] - prev[1]};
+          prev[0] = c[0]; prev[1] = c[1];
+#pragma unroll
+          for (int i = 0; i < 6; ++i) c[i] = c[i + 2];
+          slots.score(M, ltab, v2, acc);
         }
-        if (j < P) slots.score(M, ltab, v2, acc);
       }
     }
   }
+  (void)KG;
 
   double tv[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  for (int s = 0; s < M.n_series; ++s) tv[M.term_of[s]] = warp_sum(acc[s]) + M.term_const[M.term_of[s]];
+  // (static indices only: a dynamically indexed acc[] / tv[] lives in local memory for the whole kernel)
+#pragma unroll
+  for (int s = 0; s < NSER; ++s) {
+    const int term = M.term_of[s];
+    const double v = warp_sum(acc[s]) + M.term_const[term];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) tv[k] = (k == term) ? v : tv[k];
+  }
   if constexpr (Traits<FL>::k2i) {
     tv[3] = 0.0;  // no hospital-ratio term in this generation (model-age-groups2i.R:526)
   } else if constexpr (Traits<FL>::kAge) {
@@ -2021,64 +2200,84 @@ k_series(const DevModel M, const double *__restrict__ theta, int64_t ld, int64_t
   const int pad = padv[chain];
   const int off_raw = offset[chain];
   constexpr int PAD = Traits<FL>::kPad;
-  const int stride = PAD + hist_pitch(P);
+  const int AS = PAD / 4 + (hist_pitch2(P) >> 2);
+  const int Gmax = (P - 1) >> 2;
+  const int blo[2] = {lo[0] >> 2, lo[NG - 1] >> 2}, bhi[2] = {hi[0] >> 2, hi[NG - 1] >> 2};
+  // the same sweep as k_score (four consecutive days per lane, conv_tile4) over the whole period
   if constexpr (Traits<FL>::kAge) {
     AgeMap<FL> map;
     map.init(M, w.theta, off_raw, pad, P);
     const int dst[6] = {2, 4, 6, 3, 5, 7};
     double carry[6] = {0, 0, 0, 0, 0, 0};
-    constexpr int NS = 2;
-    for (int base = 0; base < P; base += 32 * NS) {
-      double cy[NS * 3], co[NS * 3];
-      conv_group<3, PAD, NS>(w.S, w.Wabs, lo[0], hi[0], base + lane, P, cy);
-      conv_group<3, PAD, NS>(w.S + stride, w.Wabs + PAD * 4, lo[1], hi[1], base + lane, P, co);
+    for (int base = 0; base < P; base += 128) {
+      const int G = (base >> 2) + lane, Gc = min(G, Gmax);
+      double c[2][12];
+      conv_tile4<3, PAD>(w.S, AS, w.Wabs, blo[0], bhi[0], Gc, c[0]);
+      conv_tile4<3, PAD>(w.S + 4 * AS, AS, w.Wabs + PAD * 3, blo[1], bhi[1], Gc, c[1]);
+      const int j0 = 4 * G, t0 = pad + 1 + j0;
 #pragma unroll
-      for (int half = 0; half < NS; ++half) {
-        const int j = base + 32 * half + lane;
-        const int t = pad + 1 + j;
-        const bool in = j < P;
-        if (in) { o[0 * P + j] = w.S[PAD + j]; o[1 * P + j] = w.S[stride + PAD + j]; }
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+          double &x = c[q / 3][r * 3 + q % 3];
+          if (t0 + r - dmin_[q] < n_[q]) x = NAN;
+          x = (j0 + r < P) ? (q < 3 ? M.Ny : M.No) - x : 0.0;
+        }
+      double prev[6];
+#pragma unroll
+      for (int q = 0; q < 6; ++q) {
+        const double last = c[q / 3][9 + q % 3];
+        prev[q] = __shfl_up_sync(0xffffffffu, last, 1);
+        if (lane == 0) prev[q] = carry[q];
+        carry[q] = __shfl_sync(0xffffffffu, last, 31);
+      }
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int j = j0 + r, t = t0 + r;
+        if (j >= P) break;
+        o[0 * P + j] = staged_s<PAD>(w.S, 0, AS, j);
+        o[1 * P + j] = staged_s<PAD>(w.S, 1, AS, j);
         double inc[6], val[6];
 #pragma unroll
         for (int q = 0; q < 6; ++q) {
-          const double Ng = q < 3 ? M.Ny : M.No;
-          double c = q < 3 ? cy[half * 3 + q] : co[half * 3 + q - 3];
-          if (t - dmin_[q] < n_[q]) c = NAN;
-          const double s2 = in ? Ng - c : 0.0;
-          double prev = __shfl_up_sync(0xffffffffu, s2, 1);
-          if (lane == 0) prev = carry[q];
-          carry[q] = __shfl_sync(0xffffffffu, s2, 31);
-          inc[q] = (j == 0) ? s2 : s2 - prev;
+          const double s2 = c[q / 3][r * 3 + q % 3];
+          inc[q] = (j == 0) ? s2 : s2 - prev[q];
+          prev[q] = s2;
         }
-        if (in) {
-          map.values(M, w.theta, t, inc, val);
+        map.values(M, w.theta, t, inc, val);
 #pragma unroll
-          for (int q = 0; q < 6; ++q) o[dst[q] * P + j] = val[q];
-        }
+        for (int q = 0; q < 6; ++q) o[dst[q] * P + j] = val[q];
       }
     }
   } else {
     const double rate[2] = {w.theta[4], 0.007};
     double carry[2] = {0, 0};
-    constexpr int NS = 2;
-    for (int base = 0; base < P; base += 32 * NS) {
-      double cc[NS * 2];
-      conv_group<2, PAD, NS>(w.S, w.Wabs, lo[0], hi[0], base + lane, P, cc);
+    for (int base = 0; base < P; base += 128) {
+      const int G = (base >> 2) + lane, Gc = min(G, Gmax);
+      double c[8];
+      conv_tile4<2, PAD>(w.S, AS, w.Wabs, blo[0], bhi[0], Gc, c);
+      const int j0 = 4 * G, t0 = pad + 1 + j0;
 #pragma unroll
-      for (int half = 0; half < NS; ++half) {
-        const int j = base + 32 * half + lane;
-        const int t = pad + 1 + j;
-        const bool in = j < P;
-        if (in) o[j] = w.S[PAD + j];
+      for (int i = 0; i < 8; ++i) {
+        if (t0 + (i >> 1) - dmin_[i & 1] < n_[i & 1]) c[i] = NAN;
+        c[i] = (j0 + (i >> 1) < P) ? (M.N - c[i]) * rate[i & 1] : 0.0;
+      }
+      double prev[2];
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        prev[q] = __shfl_up_sync(0xffffffffu, c[6 + q], 1);
+        if (lane == 0) prev[q] = carry[q];
+        carry[q] = __shfl_sync(0xffffffffu, c[6 + q], 31);
+      }
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int j = j0 + r;
+        if (j >= P) break;
+        o[j] = staged_s<PAD>(w.S, 0, AS, j);
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
-          double c = cc[half * 2 + q];
-          if (t - dmin_[q] < n_[q]) c = NAN;
-          const double cum = in ? (M.N - c) * rate[q] : 0.0;
-          double prev = __shfl_up_sync(0xffffffffu, cum, 1);
-          if (lane == 0) prev = carry[q];
-          carry[q] = __shfl_sync(0xffffffffu, cum, 31);
-          if (in) o[(1 + q) * P + j] = cum - prev;
+          o[(1 + q) * P + j] = c[r * 2 + q] - prev[q];
+          prev[q] = c[r * 2 + q];
         }
       }
     }
@@ -2186,10 +2385,11 @@ static cudaError_t launch_eval_fl(const EvalArgs &a) {
   const int di = dev < kMaxDev ? dev : kMaxDev - 1;
   if (!attr_done[di] || dev >= kMaxDev) {
     cudaFuncSetAttribute(k_mid<FL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(k_score<FL, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(k_score<FL, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(k_score<FL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(k_series<FL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaDeviceGetAttribute(&n_sm_of[di], cudaDevAttrMultiProcessorCount, dev);
+    k_fill_log_table<<<1, kLogTabN, 0, a.stream>>>();
+    cudaStreamSynchronize(a.stream);  // once per device and process: other streams may launch k_score next
     attr_done[di] = true;
   }
   const int n_sm = n_sm_of[di];
@@ -2265,12 +2465,8 @@ static cudaError_t launch_eval_fl(const EvalArgs &a) {
     k_series<FL><<<warp_blocks, 128, smem_score, s>>>(M, a.theta, a.ld, n, a.hist2, a.offset, a.pad, a.W, a.pmeta,
                                                       a.status, a.series_out, a.ns_total);
   } else {
-    if (a.score_strips == 2)
-      k_score<FL, 2><<<warp_blocks, 128, smem_score, s>>>(M, a.PT, a.n_prior, a.theta, a.ld, n, a.hist2, a.offset, a.pad, a.W, a.pmeta,
-                                                          a.status, a.logl, a.logp, a.terms, window_only);
-    else
-      k_score<FL, 4><<<warp_blocks, 128, smem_score, s>>>(M, a.PT, a.n_prior, a.theta, a.ld, n, a.hist2, a.offset, a.pad, a.W, a.pmeta,
-                                                          a.status, a.logl, a.logp, a.terms, window_only);
+    k_score<FL><<<warp_blocks, 128, smem_score, s>>>(M, a.PT, a.n_prior, a.theta, a.ld, n, a.hist2, a.offset, a.pad, a.W, a.pmeta,
+                                                     a.status, a.logl, a.logp, a.terms, window_only);
   }
   nl += 1;
   if (a.n_launches) *a.n_launches += nl;

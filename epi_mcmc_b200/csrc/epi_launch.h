@@ -26,7 +26,6 @@ struct EvalArgs {
   int64_t *n_launches = nullptr;  // incremented by the number of kernels enqueued
   int pass1_chunk = 1;          // whole-period pass 1 in two rounds (EPI_PASS1_CHUNK=0: one round over all days)
   int ode_lanes = 0;            // lanes per chain of the age-flavour ODE kernels: 0 = by batch size, 1 | 2 | 4 forced (EPI_ODE_LANES)
-  int score_strips = 4;         // day strips per lane and sweep in k_score (EPI_SCORE_STRIPS=2: the round-1 mapping; same bits)
   int window_only = 1;          // scoring path: integrate / sweep only up to the data windows (EPI_WINDOW_ONLY=0: whole period)
   cudaStream_t stream;
   cudaEvent_t *ev;  // null or 5 events bracketing the 4 launches

@@ -394,14 +394,22 @@ static int update_shape(epi_handle *h, SamplerState *s) {
   return EPI_OK;
 }
 
-static int launch_ap(epi_handle *h, SamplerState *s, int do_accept, double *draw_out, double *draw_lp) {
-  const int64_t n = s->cfg.n_chains;
-  k_accept_propose<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(
-      h->M.d, n, s->ld, s->cfg.kind, s->cfg.seed, s->cfg.chain_id0, s->iter, do_accept, s->cfg.beta,
+// accept / propose for the chains [first, first + cnt) at iteration `iter` on `stream` (cnt < 0: all chains, the
+// sampler's current iteration, the handle's stream).  The Philox counters carry the chain id, so a slice draws what
+// the whole population would have drawn for its chains.
+static int launch_ap(epi_handle *h, SamplerState *s, int do_accept, double *draw_out, double *draw_lp, int64_t first = 0,
+                     int64_t cnt = -1, int64_t iter = -1, cudaStream_t stream = nullptr) {
+  const int64_t n = cnt < 0 ? s->cfg.n_chains : cnt;
+  if (iter < 0) iter = s->iter;
+  if (!stream) stream = h->stream;
+  k_accept_propose<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(
+      h->M.d, n, s->ld, s->cfg.kind, s->cfg.seed, s->cfg.chain_id0 + first, iter, do_accept, s->cfg.beta,
       s->n_rungs > 1 ? s->beta_rung : nullptr, s->cpr, s->cfg.scale,
-      s->cfg.de_eps, s->cfg.reserved, h->M.box_min, h->M.box_max, s->cur, s->prop, s->logl, s->logp, s->logl_p, s->logp_p, s->status_p,
-      s->lscale, s->adapt, s->adapt_target, s->acc, s->pop, s->pop_ranks, s->pop_per_rank, s->pop_ld,
-      s->psd_ready ? s->psd : nullptr, (s->psd_ready && s->cfg.kind == EPI_SAMPLER_RWM) ? s->chol : nullptr, draw_out, draw_lp);
+      s->cfg.de_eps, s->cfg.reserved, h->M.box_min, h->M.box_max, s->cur + first, s->prop + first, s->logl + first, s->logp + first,
+      s->logl_p + first, s->logp_p + first, s->status_p + first,
+      s->lscale + first, s->adapt, s->adapt_target, s->acc, s->pop, s->pop_ranks, s->pop_per_rank, s->pop_ld,
+      s->psd_ready ? s->psd : nullptr, (s->psd_ready && s->cfg.kind == EPI_SAMPLER_RWM) ? s->chol : nullptr,
+      draw_out ? draw_out + first : nullptr, draw_lp ? draw_lp + first : nullptr);
   h->launches += 1;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return epi_fail(h, EPI_ERR_CUDA, "k_accept_propose: %s", cudaGetErrorString(e));
@@ -501,6 +509,46 @@ extern "C" int epi_sampler_run(epi_handle *h, int32_t n_iter) {
     // frozen when adaptation is switched off, so the sampling phase is a fixed-kernel Markov chain.)
     int rc = update_shape(h, s);
     if (rc) return rc;
+  }
+  // A small population without tempering runs as `ways` slices, each a free-running pipeline on its own stream for
+  // the whole call: nothing couples two chains inside a run (DE-MC partners come from the fixed snapshot, the
+  // proposal shape is fixed), the ODE passes of <= 16 k chains are latency bound (0.43 ms whatever the batch), so
+  // the slices drift apart and the score kernel of one fills the issue slots the ODE warps of the others leave
+  // idle.  Same draws as one slice: the Philox counters carry (chain id, iteration).  (Slices launched together
+  // and joined after every evaluation stay in phase and gain nothing: profiles/r2_summary.md.)
+  int ways = h->split_ways;
+  if (ways == 0) ways = n <= 3072 ? 1 : n <= 24576 ? 4 : n <= 40960 ? 2 : 1;
+  if (s->n_rungs > 1 || h->timing) ways = 1;
+  ways = (int)std::min<int64_t>(ways, std::max<int64_t>(1, n / 512));
+  if (ways > 1) {
+    const int64_t slice = (((n + ways - 1) / ways + 127) / 128) * 128;
+    cudaEventRecord(h->ev_fork, h->stream);
+    int used = 0;
+    for (int k = 1; k < ways && (int64_t)k * slice < n; ++k) { cudaStreamWaitEvent(h->split_stream[k - 1], h->ev_fork, 0); used = k; }
+    for (int it = 0; it < n_iter; ++it) {
+      double *dout = nullptr, *dlp = nullptr;
+      const int64_t iter = s->iter + 1;
+      if (s->draws && s->thin > 0 && (iter % s->thin) == 0 && s->kept < s->capacity) {
+        dout = s->draws + (size_t)s->kept * h->M.d * s->ld;
+        dlp = s->draws_lp + (size_t)s->kept * s->ld;
+        s->kept += 1;
+      }
+      for (int k = 0; k <= used; ++k) {
+        const int64_t first = k * slice, cnt = std::min(slice, n - first);
+        cudaStream_t sk = k == 0 ? h->stream : h->split_stream[k - 1];
+        int rc = epi_launch_eval_range(h, h->ws, h->M, s->prop, s->ld, first, cnt, s->logl_p, s->logp_p, s->status_p, sk);
+        if (rc) return rc;
+        if ((rc = launch_ap(h, s, 1, dout, dlp, first, cnt, iter, sk))) return rc;
+      }
+      s->evals += n;
+      s->iter = iter;
+    }
+    for (int k = 1; k <= used; ++k) {
+      cudaEventRecord(h->ev_join[k - 1], h->split_stream[k - 1]);
+      cudaStreamWaitEvent(h->stream, h->ev_join[k - 1], 0);
+    }
+    CUDA_OK(h, cudaStreamSynchronize(h->stream));
+    return EPI_OK;
   }
   for (int it = 0; it < n_iter; ++it) {
     int rc = epi_launch_eval_ws(h, h->ws, h->M, s->prop, s->ld, n, 0, s->logl_p, s->logp_p, s->status_p, nullptr, nullptr,

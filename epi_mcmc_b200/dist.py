@@ -88,22 +88,49 @@ class Comm:
 
     # -- DE-MC population exchange on the library's device buffers
     def attach(self, sampler):
+        """Two population buffers and a side stream: the all-gather started by exchange() k
+        fills buffer k % 2 while the chains already run their next iterations against the snapshot of exchange k - 1."""
         th_ptr, _, _, ld = sampler.state_device()
         d = sampler.model.d
         dev = torch.device("cuda", sampler.model.device)
         self._state = torch.as_tensor(_DevPtr(th_ptr, d * ld), device=dev)
-        self._pop = torch.empty(self.world * d * ld, dtype=torch.float64, device=dev)
+        self._stage = torch.empty(d * ld, dtype=torch.float64, device=dev)
+        self._pops = [torch.empty(self.world * d * ld, dtype=torch.float64, device=dev) for _ in range(2)]
+        self._pop = self._pops[0]
+        self._side = torch.cuda.Stream(device=dev)
+        self._done = [None, None]
+        self._k = 0
         self._ld = ld
-        self.exchange(sampler)
+        self.exchange(sampler, wait=True)
 
-    def exchange(self, sampler):
-        """all-gather every rank's d x ld state block into [rank][d][ld] and hand it to the
-        proposal kernel as the new population snapshot"""
-        if self.world == 1:
-            self._pop.copy_(self._state)
+    def exchange(self, sampler, wait: bool = False):
+        """Start the all-gather of every rank's d x ld state block into [rank][d][ld] on the side stream and hand
+        the proposal kernel the newest COMPLETED snapshot.  The chains' state is first copied aside (a device copy
+        of d x ld doubles, the only thing the host waits for: the kernels of the next iterations overwrite the state
+        while the collective is still reading), so the collective overlaps the next K1 launches; its result is
+        picked up by the following call.  wait=True (first call, tests): block until this very snapshot is in."""
+        dev = self._stage.device
+        k = self._k
+        with torch.cuda.stream(self._side):
+            self._stage.copy_(self._state)
+            staged = torch.cuda.Event()
+            staged.record(self._side)
+            if self.world == 1:
+                self._pops[k % 2].copy_(self._stage)
+            else:
+                dist.all_gather_into_tensor(self._pops[k % 2], self._stage)
+            ev = torch.cuda.Event()
+            ev.record(self._side)
+        self._done[k % 2] = ev
+        self._k += 1
+        if wait or k == 0:
+            ev.synchronize()
+            use = k % 2
         else:
-            dist.all_gather_into_tensor(self._pop, self._state)
-        torch.cuda.current_stream(self._pop.device).synchronize()
+            staged.synchronize()                 # the state may be overwritten from here on
+            use = (k - 1) % 2
+            self._done[use].synchronize()        # started a whole exchange period ago: normally long complete
+        self._pop = self._pops[use]
         sampler.set_population(self._pop.data_ptr(), self.world, sampler.n_chains, self._ld)
 
     def close(self):

@@ -253,6 +253,17 @@ class Model:
         """chains of the last batch whose ODE passes were redone with the removed compartment integrated"""
         return int(self._lib.epi_fallback_count(self._h))
 
+    def reserve(self, n: int):
+        """epi_reserve: size the device workspace for n chains (before the first eval_device_range call)."""
+        _capi.check(self._lib.epi_reserve(self._h, n), self._h)
+
+    def eval_device_range(self, d_theta_ptr: int, ld: int, n_total: int, first: int, n: int, d_logl: int, d_logp: int,
+                          d_status: int, stream: int = 0):
+        """epi_eval_device_range: the chains [first, first + n) of a device-resident batch; ranges that do not overlap
+        may be in flight on different streams."""
+        _capi.check(self._lib.epi_eval_device_range(self._h, d_theta_ptr, ld, n_total, first, n, d_logl, d_logp,
+                                                    d_status, stream), self._h)
+
     def eval_device(self, d_theta_ptr: int, n: int, d_logl: int, d_logp: int, d_status: int, stream: int = 0):
         """epi_eval_device on raw device pointers (theta SoA d x n)."""
         _capi.check(self._lib.epi_eval_device(self._h, d_theta_ptr, n, d_logl, d_logp, d_status, stream), self._h)

@@ -213,21 +213,28 @@ def run_mcmc(model, burnin: int = 1000, samples: int = 500, chains: int = 4096, 
     if comm is not None and kind == "demc":
         comm.attach(S)
 
-    def advance(n):
+    def advance(n, refresh):
         done = 0
         while done < n:
             step = min(exchange_every, n - done)
             S.run(step)
             done += step
-            if kind == "demc":
+            if kind == "demc" and refresh:
                 comm.exchange(S) if comm is not None else S.refresh_population()
 
+    # Burn-in adapts: the partner snapshot follows the population (all-gathered over the ranks every
+    # `exchange_every` iterations) and the proposal shape is re-measured.  For the recorded phase BOTH are frozen:
+    # partners then come from a fixed archive of past states, the kernel is a fixed symmetric Metropolis kernel and
+    # every chain is a Markov chain with the posterior as its invariant law (a snapshot that keeps following the
+    # moving chains is an adaptive scheme that needs a growing archive to be valid: ter Braak & Vrugt 2008).
     S.adapt(True)
-    advance(burnin)
+    advance(burnin, True)
     S.adapt(False)
+    if kind == "demc" and comm is not None:
+        comm.exchange(S, wait=True)   # the archive of the sampling phase: the population at the end of burn-in
     keep = max(1, samples // thin)
     S.record(thin, keep)
-    advance(samples)
+    advance(samples, False)
     draws, logpost = S.draws()
     if rungs > 1 and len(draws):
         draws, logpost = S.cold(draws), S.cold(logpost)

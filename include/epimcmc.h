@@ -193,6 +193,20 @@ int epi_eval_wait(epi_handle *h, int slot);
 int epi_eval_device(epi_handle *h, const double *d_theta_soa, int64_t n,
                     double *d_logl, double *d_logp, int32_t *d_status, void *stream);
 
+/* The chains [first, first + n) of a device-resident batch of n_total chains
+ * (theta_soa d x ld, outputs indexed by chain like epi_eval_device's).  Ranges
+ * that do not overlap may be in flight on different streams at the same time —
+ * how a small batch keeps the GPU busy: the ODE passes of <= 16 k chains are
+ * latency bound, so K ranges on K streams, each a free-running pipeline, overlap
+ * the score kernel of one range with the ODE passes of the others (bench.py's
+ * strong-scaled runs, 65,536 chains over 8 GPUs).  `first` must be a multiple
+ * of 128; epi_reserve(h, n_total) must have sized the workspace before the first
+ * range call (growing it would free buffers other ranges are using).          */
+int epi_eval_device_range(epi_handle *h, const double *d_theta_soa, int64_t ld, int64_t n_total,
+                          int64_t first, int64_t n, double *d_logl, double *d_logp, int32_t *d_status,
+                          void *stream);
+int epi_reserve(epi_handle *h, int64_t n);
+
 /* Per-evaluation detail for parity checks: offset[n] = state$offset
  * (data_offset or 10000), padding[n] = state$padding, terms[n*8] = the
  * likelihood terms in reference order (age: y.loglC, o.loglC, loglH,

@@ -46,6 +46,7 @@ static epi_handle *get_handle(SEXP ptr) {
 
 static double num(SEXP lst, const char *name, double dflt) {
   SEXP names = Rf_getAttrib(lst, R_NamesSymbol);
+  if (names == R_NilValue) return dflt;  /* an unnamed list has nothing to look up */
   for (R_xlen_t i = 0; i < XLENGTH(lst); ++i)
     if (strcmp(CHAR(STRING_ELT(names, i)), name) == 0) return Rf_asReal(VECTOR_ELT(lst, i));
   return dflt;
@@ -53,6 +54,7 @@ static double num(SEXP lst, const char *name, double dflt) {
 
 static const double *vec(SEXP lst, const char *name, int *n) {
   SEXP names = Rf_getAttrib(lst, R_NamesSymbol);
+  if (names == R_NilValue) { if (n) *n = 0; return NULL; }
   for (R_xlen_t i = 0; i < XLENGTH(lst); ++i)
     if (strcmp(CHAR(STRING_ELT(names, i)), name) == 0) {
       SEXP v = VECTOR_ELT(lst, i);
@@ -128,6 +130,8 @@ SEXP C_epi_trajectories(SEXP ptr, SEXP params, SEXP period, SEXP ext) {
   epi_handle *h = get_handle(ptr);
   const int want_ext = Rf_asLogical(ext) == TRUE;
   const int d = epi_n_params(h), ns = want_ext ? epi_n_series_ext(h) : epi_n_series(h), P = Rf_asInteger(period);
+  if (!Rf_isReal(params) || XLENGTH(params) == 0 || XLENGTH(params) % d)
+    Rf_error("epimcmc: params must be a numeric (double) matrix with %d rows", d);
   const R_xlen_t n = XLENGTH(params) / d;
   SEXP arr = PROTECT(Rf_allocVector(REALSXP, (R_xlen_t)P * ns * n));
   SEXP off = PROTECT(Rf_allocVector(INTSXP, n)), pad = PROTECT(Rf_allocVector(INTSXP, n));
@@ -147,6 +151,9 @@ SEXP C_epi_trajectories(SEXP ptr, SEXP params, SEXP period, SEXP ext) {
 SEXP C_epi_quantiles(SEXP ptr, SEXP params, SEXP period, SEXP startoffset, SEXP series_a, SEXP series_b, SEXP probs) {
   epi_handle *h = get_handle(ptr);
   const int d = epi_n_params(h), P = Rf_asInteger(period), nq = (int)XLENGTH(probs);
+  if (!Rf_isReal(params) || XLENGTH(params) == 0 || XLENGTH(params) % d)
+    Rf_error("epimcmc: params must be a numeric (double) matrix with %d rows", d);
+  if (!Rf_isReal(probs) || nq < 1) Rf_error("epimcmc: probs must be a non-empty numeric (double) vector");
   const R_xlen_t n = XLENGTH(params) / d;
   SEXP out = PROTECT(Rf_allocMatrix(REALSXP, P, nq));
   /* the library returns period x n_probs row-major; R matrices are column-major */
@@ -211,9 +218,12 @@ SEXP C_epi_run_mcmc(SEXP ptr, SEXP theta0, SEXP chains, SEXP burnin, SEXP sample
   }
   if (!rc) rc = epi_sampler_adapt(h, 0, 0.0);
   if (!rc) rc = epi_sampler_record(h, th, keep);
+  /* sampling phase: the partner snapshot taken at the end of burn-in stays FIXED (a fixed symmetric proposal
+   * kernel; refreshing it from the moving chains would be an adaptive scheme without a valid archive) */
+  int64_t it0 = 0, acc0 = 0, ev0 = 0;
+  if (!rc) rc = epi_sampler_stats(h, &it0, &acc0, &ev0);
   for (int done = 0; !rc && done < nsamp; done += 10) {
     rc = epi_sampler_run(h, nsamp - done < 10 ? nsamp - done : 10);
-    if (!rc && is_de) rc = epi_sampler_set_population(h, NULL, 1, n, 0);
     R_CheckUserInterrupt();
   }
   if (rc) Rf_error("epi_sampler failed (%d): %s", rc, epi_last_error(h));
@@ -234,7 +244,8 @@ SEXP C_epi_run_mcmc(SEXP ptr, SEXP theta0, SEXP chains, SEXP burnin, SEXP sample
   SEXP out = PROTECT(Rf_allocVector(VECSXP, 4));
   SET_VECTOR_ELT(out, 0, draws);
   SET_VECTOR_ELT(out, 1, logpost);
-  SET_VECTOR_ELT(out, 2, Rf_ScalarReal(it > 0 ? (double)acc / ((double)it * n) : 0.0));
+  /* acceptance of the SAMPLING phase (all rungs pooled; drjacoby reports it per phase too) */
+  SET_VECTOR_ELT(out, 2, Rf_ScalarReal(it > it0 ? (double)(acc - acc0) / ((double)(it - it0) * n) : 0.0));
   SET_VECTOR_ELT(out, 3, Rf_ScalarReal((double)ev));
   UNPROTECT(3);
   return out;

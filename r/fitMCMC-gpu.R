@@ -8,23 +8,24 @@
 ## parameter of one chain at a time (a batch of 1 per GPU call); here a population of `gpu_chains` chains per
 ## rung advances together, one batched log-posterior evaluation per iteration.
 
+## the same sequence the reference driver runs before it samples (R/MCMC/fitMCMC-drj.R:3-24): settings, data file,
+## model file, the optional warm start, libfit.R, then settings.R a second time so that it can override anything
+## the model file set
 source("settings.R")
+source(data, chdir = TRUE)
+source(fitmodel, chdir = TRUE)
 
-source(data, chdir=T)
-source(fitmodel, chdir=T)
-
-if (file.exists("max.csv")) {
-    print("Loading initial state from max.csv")
-    r <- read.csv("max.csv")
-    init <- r$x[2:(length(init) + 1)]
+warm_start <- file.exists("max.csv")
+if (warm_start) {
+    ## max.csv: x[1] is the log-posterior of the best point of the previous run, x[2..] the point itself
+    best_prev <- read.csv("max.csv")$x
+    init <- best_prev[1 + seq_along(init)]
     df_params$init <- init
+    print("initial state taken from max.csv")
 }
 
-source(paste(Rdir, "lib/libfit.R", sep=""))
-
-options(scipen=999)
-
-## source it again so that you can override things
+source(paste(Rdir, "lib/libfit.R", sep = ""))
+options(scipen = 999)
 source("settings.R")
 
 if (!exists("gpu_chains")) gpu_chains <- 4096     # chains per rung on the device
@@ -37,13 +38,21 @@ print(fit.paramnames)
 r0 <- calclogpost_batch(matrix(init, ncol = 1))
 print(c("initial logl: ", r0$logl, " logl prior: ", r0$logp))
 
-## start every chain at init + 2 % box jitter (NULL lets the library do exactly that), or warm-start them all
-## around the max.csv point the same way
-out <- .Call("C_epi_run_mcmc", epi_handle, NULL, as.integer(gpu_chains), as.integer(1e3), as.integer(0.5e3), 1L,
+## every chain starts at `init` — the model file's, or the max.csv point loaded above — plus 2 % of the box width of
+## jitter, clamped to the df_params box (the handle only knows the model file's compiled-in init, so the starting
+## cloud is built here and passed in: a warm start really moves the whole population)
+n_start <- as.integer(gpu_chains) * max(1L, as.integer(gpu_rungs))
+set.seed(gpu_seed)
+box_w <- df_params$max - df_params$min
+theta0 <- matrix(init, nrow = length(init), ncol = n_start) +
+    0.02 * box_w * (matrix(runif(length(init) * n_start), nrow = length(init)) - 0.5)
+theta0 <- pmin(pmax(theta0, df_params$min), df_params$max)       # (recycled down the columns: one bound per row)
+storage.mode(theta0) <- "double"
+out <- .Call("C_epi_run_mcmc", epi_handle, theta0, as.integer(gpu_chains), as.integer(1e3), as.integer(0.5e3), 1L,
              as.integer(gpu_rungs), 1.0, as.numeric(gpu_seed), as.integer(gpu_kind))
 draws <- out[[1]]                 # d x chains x kept
 logpost <- out[[2]]               # chains x kept
-print(c("acceptance rate: ", out[[3]], " evaluations: ", out[[4]]))
+print(c("acceptance rate (sampling phase): ", out[[3]], " evaluations: ", out[[4]]))
 
 ## effective sample size per parameter, pooled over a subset of chains (what drjacoby prints, :58)
 if (requireNamespace("coda", quietly = TRUE)) {

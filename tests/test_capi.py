@@ -176,3 +176,19 @@ def test_r_model_files_pass_only_globals_the_shim_reads():
         keys = {k for k in keys if k}
         assert keys <= looked_up, (fn, sorted(keys - looked_up))
         assert essentials <= keys, (fn, sorted(essentials - keys))
+
+
+def test_r_driver_passes_its_warm_start_to_the_sampler():
+    """the GPU driver read max.csv into `init` but started every chain from the library's compiled-in
+    init (theta0 = NULL).  Static check (no R here): the starting cloud is built from `init` in R and handed to
+    C_epi_run_mcmc, and the sampling phase of the shim no longer refreshes the DE-MC snapshot."""
+    with open(os.path.join(ROOT, "r", "fitMCMC-gpu.R")) as f:
+        src = f.read()
+    call = re.search(r'\.Call\("C_epi_run_mcmc",\s*epi_handle,\s*(\w+),', src)
+    assert call and call.group(1) == "theta0"
+    assert re.search(r"theta0 <- matrix\(init,", src) and "df_params$min" in src and 'read.csv("max.csv")' in src
+    with open(os.path.join(ROOT, "r", "epimcmc_shim.c")) as f:
+        shim = f.read()
+    body = shim[shim.index("SEXP C_epi_run_mcmc"):]
+    burn, samp = body.split("epi_sampler_record", 1)
+    assert "epi_sampler_set_population" in burn and "epi_sampler_set_population" not in samp

@@ -74,47 +74,16 @@ def test_state_is_consistent_and_inside_the_box():
 
 
 def _start(mn, mx, init, n, seed):
-    """start inside the main mode: the target is rugged (HL, DL enter through ceil/floor kernel
-    extents, the threshold through an integer data_offset) and has shallow local modes that trap
-    ~10 % of widely dispersed starts for any local sampler — which is what the reference's
-    20-rung parallel tempering is for (fitMCMC-drj.R:53)"""
-    rng = np.random.default_rng(seed)
-    return np.clip(init + 0.02 * (mx - mn) * (rng.uniform(size=(n, len(init))) - 0.5), mn, mx)
+    from oracle import cpu_mcmc
+    return cpu_mcmc.start_cloud(mn, mx, init, n, seed)
 
 
 def _cpu_reference_sampler(oracle, ds, m, n_chains, burnin, samples, thin, seed):
-    """An independent CPU sampler on the ORACLE density: population-adaptive Metropolis in numpy
-    (proposal covariance = 2.38^2/d x pooled covariance, refreshed during burn-in only)."""
-    rng = np.random.default_rng(seed)
-    mn, mx, init = oracle.df_params(ds["flavour"], ds, ds["period"])
-    d = len(init)
-    x = _start(mn, mx, init, n_chains, seed + 100)
-
-    def post(th):
-        r = oracle.evaluate(ds["flavour"], ds, th, ds["period"], m, n_threads=16)
-        lp = r["logl"] + r["logp"]
-        return np.where(np.isfinite(lp), lp, -np.inf)
-
-    def reflect(y):
-        w = mx - mn
-        z = np.mod(y - mn, 2 * w)
-        z = np.where(z > w, 2 * w - z, z)
-        return mn + z
-
-    lp = post(x)
-    L = np.diag(0.02 * (mx - mn) / np.sqrt(d))
-    keep = []
-    for it in range(burnin + samples):
-        if it < burnin and it % 50 == 0 and it > 0:
-            C = np.cov(x.T) + 1e-12 * np.diag((mx - mn) ** 2)
-            L = np.linalg.cholesky(C) * 2.38 / np.sqrt(d)
-        y = reflect(x + rng.standard_normal((n_chains, d)) @ L.T)
-        lq = post(y)
-        acc = np.log(rng.uniform(size=n_chains)) < lq - lp
-        x[acc], lp[acc] = y[acc], lq[acc]
-        if it >= burnin and (it - burnin) % thin == 0:
-            keep.append(x.copy())
-    return np.array(keep).reshape(-1, d)
+    """An independent CPU sampler on the ORACLE density (oracle/cpu_mcmc.py): population-adaptive Metropolis in
+    numpy (proposal covariance = 2.38^2/d x pooled covariance, refreshed during burn-in only)."""
+    from oracle import cpu_mcmc
+    draws, _ = cpu_mcmc.run(oracle, ds, m, n_chains, burnin, samples, thin, seed)
+    return draws.reshape(-1, draws.shape[-1])
 
 
 def test_samplers_agree_on_the_posterior(oracle):
