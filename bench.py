@@ -4,19 +4,28 @@
   python bench.py --gpus N --steps K --warmup W          (N > 1: launched under torchrun)
   python bench.py --impl reference --gpus N --steps K --warmup W
 
-One "step" = one pass of the hot path (calclogl(transformParams(theta)) + calclogp(theta))
-over one batch of `--chains` proposals PER GPU (weak scaling; chains are independent, no
-data-path collective).  Workload = BASELINE.json configs[2]: the age-structured model
-(model-age-groups2q) on the synthetic A300 series, 65,536 chains per GPU, RK4 m = 4.
+One "step" = one pass of the hot path (calclogl(transformParams(theta)) + calclogp(theta)) over one batch of
+proposals.  Workload = BASELINE.json configs[2]: the age-structured model (model-age-groups2q) on the synthetic A300
+series, RK4 m = 4, `--chains` = 65,536 chains IN TOTAL: under `--scaling strong` (default, the configuration
+BASELINE.json quotes: "65,536 chains at 1/2/4/8 B200") every GPU evaluates 65,536 / N of them; `--scaling weak` gives
+every GPU all 65,536 (also reported as the `weak` object of a strong run).  Chains are independent: no data-path
+collective.  The headline theta are draws from the posterior cloud of a running sampler (what the kernels see in
+production: breakpoints differ by days between the chains of a warp); the narrow cloud of round 1 is `narrow_cloud`.
 
 JSON line keys beyond the base contract:
-  roofline      dominant kernel (pass-2 ODE) against the FP64 DFMA peak measured live
-  cpu_baseline  the CPU oracle ("port": R is not installed) on a bounded sample, all host threads
+  roofline      the longest kernel of the step: EXECUTED FP64 flop (ncu SASS counts of this workload,
+                profiles/ncu_constants.json) / launch time / the DFMA peak measured live — never above 1; the SURVEY 8d
+                formula figure is `survey_formula_frac`; `hbm` is the HBM view of the same launch
+  cpu_baseline  the CPU oracle ("port": R is probed for and not installed) on a bounded sample, all host threads,
+                and a CPU Metropolis sampler on it for ESS/s
   e2e           the same metric through the host-buffer C ABI (epi_eval_submit/wait, and epi_eval beside it)
                 with pinned HOST buffers (H2D + D2H inside)
+  sustained     the same step for >= 1 s
   kernels       mean device ms of the four launches of one step
-  f_alg         algorithmic FLOP per evaluation (SURVEY.md §8d formula) and the whole-step fraction
-  sampler       fused propose/accept DE-MC run: evals/s inside the sampler and ESS/s
+  secondary     one short timed leg per other BASELINE config (S120 / S365 at 2^20 proposals, A365, NE120 at 4,096,
+                A300 on the daily grid m = 1, I290)
+  sampler       fused propose/accept DE-MC run: evals/s inside the sampler, ESS/s from independent replicate
+                populations, split R-hat, and `k2`: the fused kernel alone against the HBM peak (65,536 and 2^22 chains)
 """
 import argparse
 import json
@@ -31,17 +40,18 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-# DRAM bytes per launch of each kernel (read + write) from the committed ncu --set full capture of
-# this exact workload (profiles/r1_v15_ncu_full.txt); only reported when the run matches that workload
-NCU_TRAFFIC = {"ode_pass1": 296.4e6, "profiles_threshold": 301.0e6, "ode_pass2": 467.4e6, "score": 617.1e6}
-# sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active of the same capture
-NCU_FP64_PIPE_PCT = {"ode_pass1": 50.6, "profiles_threshold": 62.5, "ode_pass2": 47.9, "score": 29.9}
-# FP64 flop actually EXECUTED per launch in the same capture: thread-level predicated-on DFMA x 2 + DMUL + DADD from the
-# report's SASS table.  SURVEY 8d counts the reference's arithmetic (bounds-guard comparisons, the output variables
-# Re/Rt, the removed compartment, per-call segment selection ...): the ODE kernels execute about a third of that, which
-# is why their algorithmic `frac` exceeds 1 — the pipe utilisation above and this figure are the honest bound for them
-NCU_EXECUTED_FLOP = {"ode_pass1": 2.749e9, "profiles_threshold": 4.985e9, "ode_pass2": 12.512e9, "score": 11.311e9}
-NCU_WORKLOAD = ("A300", 65536, 4)
+# ncu constants of bench.py's own workloads (profiles/extract_ncu_constants.py writes the file from a
+# `ncu --set full` capture): DRAM bytes per launch, FP64 pipe utilisation, FP64 flop actually EXECUTED per launch
+# (thread-level predicated-on DFMA x 2 + DMUL + DADD of the report's SASS table).  SURVEY 8d counts the reference's
+# arithmetic (bounds-guard comparisons, the output variables Re/Rt, the removed compartment, per-call segment
+# selection ...): the ODE kernels execute about a third of that, so the executed count is the honest numerator.
+def load_ncu_constants():
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_constants.json")) as f:
+            return json.load(f)
+    except (OSError, ValueError):
+        return {}
+
 
 METRIC = "log_posterior_evals_per_s"
 UNIT = "evals/s"
@@ -50,28 +60,76 @@ UNIT = "evals/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=300)   # ~1 s of timed region at 3 ms per step
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="A300")
-    ap.add_argument("--chains", type=int, default=65536)
+    ap.add_argument("--chains", type=int, default=65536, help="chains of the configuration IN TOTAL (BASELINE.json: 65,536)")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="strong: every GPU takes chains / N (BASELINE.json configs[2]); weak: every GPU takes all of them")
     ap.add_argument("--substeps", type=int, default=4)
+    ap.add_argument("--theta", default="auto", choices=["auto", "posterior", "narrow"],
+                    help="headline proposals: posterior cloud of a running sampler (auto: when the workload has one) or init +- 0.5 %% of the box")
     ap.add_argument("--no-sampler", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true")
     ap.add_argument("--sampler-iters", type=int, default=3000)
-    ap.add_argument("--sampler-burnin", type=int, default=1000)
+    ap.add_argument("--sampler-burnin", type=int, default=4000)
     ap.add_argument("--sampler-fulldim", action="store_true", help="DE-MC without subspace (crossover) updates")
     return ap.parse_args()
 
 
 def make_theta(ds_name, n, seed, mn, mx, init):
-    """proposals where a running sampler spends its time: +-0.5 % of the box width around the
-    model file's init (= the mode of the synthetic data), so every chain does the full work
-    (valid data_offset, pass 2 integrated).  Box-uniform draws would let ~1/3 of the chains skip
-    pass 2 and flatter the number."""
+    """narrow cloud: +-0.5 % of the box width around the model file's init (= the mode of the synthetic data), so
+    every chain does the full work (valid data_offset, pass 2 integrated).  Box-uniform draws would let ~1/3 of the
+    chains skip pass 2 and flatter the number."""
     rng = np.random.default_rng(seed)
     th = init + (rng.uniform(size=(n, len(init))) - 0.5) * 0.01 * (mx - mn)
     return np.clip(th, mn, mx)
+
+
+def posterior_gauss(workload):
+    """mean and covariance of a 65,536-chain DE-MC population after 4,000 iterations (tests/_pop_dump.py), or None"""
+    path = os.path.join(ROOT, "epi_mcmc_b200", "datasets", f"{workload}_posterior_gauss.json")
+    if not os.path.exists(path):
+        return None
+    with open(path) as f:
+        g = json.load(f)
+    return np.array(g["mean"]), np.array(g["cov"])
+
+
+def make_cloud(workload, n, seed, mn, mx):
+    """posterior cloud: theta ~ N(mean, cov) of a running sampler's population, clipped to the box.  The breakpoints
+    of the chains of a warp then differ by days, which costs the ODE warps their lock-step."""
+    g = posterior_gauss(workload)
+    rng = np.random.default_rng(seed)
+    return np.clip(rng.multivariate_normal(g[0], g[1], size=n), mn, mx)
+
+
+THETA_LABEL = {"posterior": "N(mean, cov) of a 65,536-chain DE-MC population after 4,000 iterations, clipped to the box "
+                            "(epi_mcmc_b200/datasets/<workload>_posterior_gauss.json): what a running sampler evaluates",
+               "narrow": "init +- 0.5% of the df_params box (every chain integrates both passes, warps in lock-step)"}
+
+
+def batch_theta(kind, workload, total, mn, mx, init):
+    """the configuration's whole batch of `total` proposals — the same on every rank, whatever the sharding"""
+    return make_cloud(workload, total, 4321, mn, mx) if kind == "posterior" else make_theta(workload, total, 1234, mn, mx, init)
+
+
+def r_probe():
+    """BASELINE.md step 1 / SURVEY 8d: is the reference's own runtime here?  The reference arm can only be R when
+    Rscript, deSolve AND the reference tree are all present (the tree never travels to the GPU box)."""
+    import shutil
+    rs = shutil.which("Rscript")
+    have_ds = None
+    if rs:
+        try:
+            have_ds = subprocess.run([rs, "-e", "quit(status = !requireNamespace('deSolve', quietly = TRUE))"],
+                                     capture_output=True, timeout=60).returncode == 0
+        except Exception:
+            have_ds = False
+    return {"Rscript": rs, "deSolve": have_ds, "reference_tree": os.path.isdir("/root/reference"),
+            "usable": bool(rs and have_ds and os.path.isdir("/root/reference"))}
 
 
 def f_alg(flavour, P, m, taps_mean, n_terms, n_prior):
@@ -159,9 +217,10 @@ class ClockSampler(threading.Thread):
                 "power_w_max": max(pw) if pw else None, "reasons": reasons, "samples": len(rows)}
 
 
-def cpu_baseline(ds, theta, substeps, budget_s=15.0):
-    """the CPU oracle (kind 'port': R/deSolve are not installed) on a bounded sample of the
-    same theta batch with every host thread"""
+def cpu_baseline(ds, theta, substeps, budget_s=15.0, ess_budget_s=20.0, workload=None):
+    """the CPU oracle (kind 'port': R/deSolve are probed for and not installed) on a bounded sample of the
+    same theta batch with every host thread; then a CPU Metropolis sampler on the same density (oracle/cpu_mcmc.py,
+    one chain per host thread, proposal shape = the posterior covariance) for ESS/s"""
     from oracle import oracle
     oracle.build()
     cores = os.cpu_count() or 1
@@ -176,31 +235,70 @@ def cpu_baseline(ds, theta, substeps, budget_s=15.0):
     for _ in range(reps):
         oracle.evaluate(ds["flavour"], ds, theta[:n], ds["period"], substeps, n_threads=cores)
     dt = time.perf_counter() - t0
-    return {"value": n * reps / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"first {n} proposals of the step's batch x {reps} passes, oracle/epi_oracle.c (RK4 m={substeps}), "
-                      f"{cores} pthreads, {dt:.1f} s"}
+    out = {"value": n * reps / dt, "unit": UNIT, "cores": cores, "kind": "port", "r_probe": r_probe(),
+           "sample": f"first {n} proposals of the step's batch x {reps} passes, oracle/epi_oracle.c (RK4 m={substeps}), "
+                     f"{cores} pthreads, {dt:.1f} s"}
+    g = posterior_gauss(workload) if workload else None
+    if g is not None and ess_budget_s > 0:
+        from oracle import cpu_mcmc
+        from epi_mcmc_b200.sampler import effective_size
+        mn, mx, _ = (np.asarray(v) for v in oracle.df_params(ds["flavour"], ds, ds["period"]))
+        nc = max(4, cores)
+        x0 = np.clip(np.random.default_rng(11).multivariate_normal(g[0], g[1], size=nc), mn, mx)
+        draws, info = cpu_mcmc.run(oracle, ds, substeps, nc, 100, 10 ** 9, 1, 5, n_threads=cores, cov0=g[1], x0=x0,
+                                   budget_s=ess_budget_s)
+        # independent chains started in the stationary law: coda's spectral ESS per chain, summed over the chains
+        ess = np.array([sum(effective_size(draws[:, c, p]) for c in range(nc)) for p in range(draws.shape[2])])
+        out["ess_per_s_median"] = float(np.median(ess)) / info["sampling_s"]
+        out["ess_per_s_min"] = float(ess.min()) / info["sampling_s"]
+        out["ess_sample"] = (f"{nc} independent random-walk Metropolis chains on the oracle density, started from draws of the "
+                             f"posterior's Gaussian summary with its covariance x 2.38^2/d as the proposal shape, "
+                             f"{info['sampling_iterations']} iterations each in {info['sampling_s']:.1f} s "
+                             f"({info['evals_sampling'] / info['sampling_s']:.0f} evals/s, acceptance {info['accept_rate']:.3f}); "
+                             f"ESS = coda spectral ESS per chain, summed; median / min over all {draws.shape[2]} parameters")
+    return out
+
+
+def make_config(args, period, n_per_gpu, world, d, theta_kind, ws_mb=None):
+    """the `config` object — the SAME keys and values in both arms, so that the driver can compare them"""
+    return {"workload": workload_name(args, period), "chains_total": args.chains, "chains_per_gpu": n_per_gpu,
+            "params": d, "period": period, "substeps": args.substeps, "theta": THETA_LABEL[theta_kind],
+            "l2": "inputs larger than L2: the S-history/profile working set of one step is "
+                  f"{ws_mb:.0f} MB vs 126 MB L2" if ws_mb is not None else "n/a",
+            "parallelism": f"{args.scaling} scaling: {args.chains} chains "
+                           + ("sharded over" if args.scaling == "strong" else "on each of") + f" {world} GPU(s), no data-path collective"}
+
+
+def theta_kind_of(args):
+    if args.theta == "auto":
+        return "posterior" if posterior_gauss(args.workload) is not None else "narrow"
+    return args.theta
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU implementation of the path is R + deSolve, absent
-    from this image; its restatement (oracle/) is timed instead, all host threads, on a bounded
-    sample of the same config.  Rank 0 only."""
+    """--impl reference: the reference's CPU implementation of the path is R + deSolve (probed for, absent from
+    this image); its restatement (oracle/) is timed instead, all host threads, on a bounded sample of the same
+    config.  Rank 0 only."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
     from epi_mcmc_b200.model import load_dataset
     from oracle import oracle
     oracle.build()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     ds = load_dataset(args.workload)
     mn, mx, init = oracle.df_params(ds["flavour"], ds, ds["period"])
     cores = os.cpu_count() or 1
-    probe = make_theta(args.workload, 4 * cores, 7, mn, mx, init)
+    kind = theta_kind_of(args)
+    n_per_gpu = (args.chains + world - 1) // world if args.scaling == "strong" else args.chains
+    batch = batch_theta(kind, args.workload, min(args.chains, 16384), mn, mx, init)
+    probe = batch[: 4 * cores]
     t0 = time.perf_counter()
     oracle.evaluate(ds["flavour"], ds, probe, ds["period"], args.substeps, n_threads=cores)
     rate = len(probe) / (time.perf_counter() - t0)
     total_budget = 120.0
     per_step = max(4 * cores, int(rate * total_budget / max(1, args.steps + args.warmup)))
-    per_step = min(per_step, args.chains)
-    theta = make_theta(args.workload, per_step, 1234, mn, mx, init)
+    per_step = min(per_step, len(batch))
+    theta = batch[:per_step]
     for _ in range(args.warmup):
         oracle.evaluate(ds["flavour"], ds, theta, ds["period"], args.substeps, n_threads=cores)
     t0 = time.perf_counter()
@@ -209,14 +307,13 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     value = per_step * args.steps / dt
     sample = f"{per_step} proposals per step (bounded sample of the {args.chains}-chain batch), {cores} pthreads"
+    ws = _ws_mb(ds, n_per_gpu)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(args, ds["period"]), "chains_per_gpu": args.chains,
-                       "params": len(init), "period": ds["period"], "substeps": args.substeps,
-                       "theta": "init +- 0.5% of the df_params box (every chain integrates both passes)",
-                       "reference_arm": "CPU restatement oracle/epi_oracle.c (R + deSolve + drjacoby are not installed)"},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "config": make_config(args, ds["period"], n_per_gpu, world, len(init), kind, ws),
+            "reference_arm": "CPU restatement oracle/epi_oracle.c (R + deSolve + drjacoby are not installed: r_probe)",
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "r_probe": r_probe()},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     emit(line)
@@ -227,7 +324,7 @@ def workload_name(args, period):
             "I": "age-structured model-age-groups2i (secondary anchor of BASELINE.json configs[2])",
             "S": "simple SEIR model-simple-ode-drj-cmp (BASELINE.json configs[3])",
             "N": "simple SEIR + effective population size Ne (BASELINE.json configs[1])"}.get(args.workload[0], args.workload)
-    return f"{args.workload}: {what}, synthetic {period}-day series, {args.chains} chains per GPU, RK4 m={args.substeps}"
+    return f"{args.workload}: {what}, synthetic {period}-day series, {args.chains} chains in total, RK4 m={args.substeps}"
 
 
 _REAL_STDOUT = 1
@@ -246,182 +343,89 @@ def _claim_stdout():
     os.dup2(2, 1)
 
 
-def main():
-    args = parse()
-    _claim_stdout()
-    if args.impl == "reference":
-        run_reference(args)
-        return
+class DeviceBatch:
+    """one device-resident batch of this rank: theta SoA in HBM, result buffers, the launching stream"""
+
+    def __init__(self, M, theta, dev, stream):
+        import torch
+        self.M, self.n, self.stream = M, len(theta), stream
+        self.th = torch.from_numpy(np.ascontiguousarray(theta.T)).to(f"cuda:{dev}")
+        self.logl = torch.empty(self.n, dtype=torch.float64, device=f"cuda:{dev}")
+        self.logp = torch.empty_like(self.logl)
+        self.status = torch.empty(self.n, dtype=torch.int32, device=f"cuda:{dev}")
+
+    def step(self):
+        self.M.eval_device(self.th.data_ptr(), self.n, self.logl.data_ptr(), self.logp.data_ptr(), self.status.data_ptr(),
+                           self.stream.cuda_stream)
+
+
+def timed(batch, steps, warmup, comm, dev):
+    """W untimed steps, then EXACTLY `steps` steps between CUDA events recorded on the launching stream, bracketed
+    by a barrier + synchronize on both sides; max over ranks.  Returns (ms total, launches)."""
     import torch
-    from epi_mcmc_b200.dist import Comm
-    from epi_mcmc_b200.model import Model, load_dataset
-
-    comm = Comm()
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the evaluation path has no CPU fallback")
-    dev = comm.local_rank
-    torch.cuda.set_device(dev)
-    ds = load_dataset(args.workload)
-    M = Model(ds, substeps=args.substeps, device=dev)
-    n, d = args.chains, M.d
-    mn, mx, init = M.df_params["min"], M.df_params["max"], M.df_params["init"]
-    theta = make_theta(args.workload, n, 1234 + comm.rank, mn, mx, init)
-
-    # ---- device-resident arm: theta SoA already in HBM when the timed region starts
-    th_dev = torch.from_numpy(np.ascontiguousarray(theta.T)).to(f"cuda:{dev}")
-    logl = torch.empty(n, dtype=torch.float64, device=f"cuda:{dev}")
-    logp = torch.empty_like(logl)
-    status = torch.empty(n, dtype=torch.int32, device=f"cuda:{dev}")
-    stream = torch.cuda.Stream(device=dev)   # the kernels are launched on THIS stream; so are the timing events
-    stream.wait_stream(torch.cuda.current_stream(dev))
-
-    def step():
-        M.eval_device(th_dev.data_ptr(), n, logl.data_ptr(), logp.data_ptr(), status.data_ptr(), stream.cuda_stream)
-
-    for _ in range(args.warmup):
-        step()
+    for _ in range(warmup):
+        batch.step()
     torch.cuda.synchronize(dev)
-    clocks = ClockSampler(dev)
-    clocks.start()
-    time.sleep(0.3)   # let nvidia-smi start streaming before the timed region
     comm.barrier()
     torch.cuda.synchronize(dev)
-    launches0 = M.launch_count()
+    l0 = batch.M.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(args.steps):
-        step()
-    e1.record(stream)
+    e0.record(batch.stream)
+    for _ in range(steps):
+        batch.step()
+    e1.record(batch.stream)
     torch.cuda.synchronize(dev)
     comm.barrier()
-    ms = comm.max_over_ranks(e0.elapsed_time(e1))
-    launches = M.launch_count() - launches0
-    value = comm.world * n * args.steps / (ms * 1e-3)
+    return comm.max_over_ranks(e0.elapsed_time(e1)), batch.M.launch_count() - l0
 
-    # ---- per-kernel device times (CUDA events on the launching stream, same timed loop shape)
+
+def kernel_ms(batch, reps, dev):
+    """mean device time of the four launches of a step (CUDA events on the launching stream)"""
+    import torch
+    M = batch.M
     M.set_timing(True)
-    kms = np.zeros(4)
-    reps = max(3, min(args.steps, 10))
+    k = np.zeros(4)
     for _ in range(reps):
-        step()
-        kms += np.array(M.last_kernel_ms())
-    kms /= reps
+        batch.step()
+        k += np.array(M.last_kernel_ms())
     M.set_timing(False)
     torch.cuda.synchronize(dev)
+    return k / reps
 
-    # ---- the same step on a posterior-spread cloud (secondary figure).  The headline cloud is narrow (+-0.5 % of the
-    # box around init), so the chains of a warp cross every schedule breakpoint on the same day; the population of a
-    # running sampler does not (its breakpoints are spread over days), which costs the ODE warps lock-step.  theta ~
-    # N(mean, cov) of a 65,536-chain DE-MC population after 4,000 iterations (tests/_pop_dump.py), clipped to the box.
-    cloud = None
-    gpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "epi_mcmc_b200", "datasets",
-                         f"{args.workload}_posterior_gauss.json")
-    if os.path.exists(gpath):
-        with open(gpath) as f:
-            g = json.load(f)
-        rng = np.random.default_rng(4321 + comm.rank)
-        th_c = np.clip(rng.multivariate_normal(np.array(g["mean"]), np.array(g["cov"]), size=n), mn, mx)
-        th_dev_head = th_dev
-        th_dev = torch.from_numpy(np.ascontiguousarray(th_c.T)).to(f"cuda:{dev}")
-        for _ in range(args.warmup):
-            step()
-        torch.cuda.synchronize(dev)
-        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        c0.record(stream)
-        for _ in range(args.steps):
-            step()
-        c1.record(stream)
-        torch.cuda.synchronize(dev)
-        ms_c = comm.max_over_ranks(c0.elapsed_time(c1))
-        M.set_timing(True)
-        kc = np.zeros(4)
-        for _ in range(reps):
-            step()
-            kc += np.array(M.last_kernel_ms())
-        kc /= reps
-        M.set_timing(False)
-        torch.cuda.synchronize(dev)
-        cloud = {"value": comm.world * n * args.steps / (ms_c * 1e-3), "unit": UNIT, "ms_per_step": ms_c / args.steps,
-                 "kernels": {"ode_pass1_ms": float(kc[0]), "profiles_threshold_ms": float(kc[1]),
-                             "ode_pass2_ms": float(kc[2]), "score_ms": float(kc[3])},
-                 "status_nonzero": int((status != 0).sum().item()),
-                 "theta": "N(mean, cov) of a 65,536-chain DE-MC population after 4,000 iterations, clipped to the box "
-                          "(epi_mcmc_b200/datasets/%s_posterior_gauss.json): breakpoints differ by days between the "
-                          "chains of a warp" % args.workload}
-        th_dev = th_dev_head
-        step()                      # logl / logp / status hold the headline batch again for the checks below
-        torch.cuda.synchronize(dev)
 
-    # ---- e2e arm: the public C-ABI with pinned HOST buffers, copies inside the timed region.
-    # (a) epi_eval: one blocking call per step (H2D -> kernels -> D2H strictly in sequence);
-    # (b) epi_eval_submit / epi_eval_wait: the same step, double-buffered — step k+1 is submitted before
-    #     step k is waited for, so its input copy (copy stream) overlaps the kernels of step k.  Every
-    #     step still moves its own n x d inputs from pinned host memory and its n x 20 B of results back.
-    # `e2e.value` is (b), the API a host-side driver with two independent batches in flight uses;
-    # (a) is reported beside it as e2e.blocking_call_value.
-    from epi_mcmc_b200 import _capi
-    import ctypes as C
-    th_host = [torch.from_numpy(theta.copy()).pin_memory() for _ in range(2)]
-    ll_host = [torch.empty(n, dtype=torch.float64).pin_memory() for _ in range(2)]
-    lp_host = [torch.empty(n, dtype=torch.float64).pin_memory() for _ in range(2)]
-    st_host = [torch.empty(n, dtype=torch.int32).pin_memory() for _ in range(2)]
-    dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int32)
+KNAMES = ["ode_pass1", "profiles_threshold", "ode_pass2", "score"]
+KERNEL_FN = {"ode_pass1": "k_ode<pass1>", "profiles_threshold": "k_mid", "ode_pass2": "k_ode<pass2>", "score": "k_score"}
 
-    def e2e_step():
-        _capi.check(M._lib.epi_eval(M._h, C.cast(th_host[0].data_ptr(), dp), n, _capi.LAYOUT_AOS,
-                                    C.cast(ll_host[0].data_ptr(), dp), C.cast(lp_host[0].data_ptr(), dp),
-                                    C.cast(st_host[0].data_ptr(), ip)), M._h)
 
-    def submit(k):
-        b = k & 1
-        _capi.check(M._lib.epi_eval_submit(M._h, b, C.cast(th_host[b].data_ptr(), dp), n, _capi.LAYOUT_AOS,
-                                           C.cast(ll_host[b].data_ptr(), dp), C.cast(lp_host[b].data_ptr(), dp),
-                                           C.cast(st_host[b].data_ptr(), ip)), M._h)
+def kdict(k):
+    return {"ode_pass1_ms": float(k[0]), "profiles_threshold_ms": float(k[1]), "ode_pass2_ms": float(k[2]), "score_ms": float(k[3])}
 
-    def wait(k):
-        _capi.check(M._lib.epi_eval_wait(M._h, k & 1), M._h)
 
-    def pipelined(steps):
-        submit(0)
-        for k in range(1, steps):
-            submit(k)
-            wait(k - 1)
-        wait(steps - 1)
+def hbm_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+    except (OSError, KeyError, ValueError):
+        return 6650.0, "fallback of B200_PROFILING.md (MEASURED_PEAKS.json absent)"
 
-    for _ in range(max(1, args.warmup)):
-        e2e_step()
-    comm.barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        e2e_step()       # returns after the D2H copies completed (stream synchronised inside)
-    e2e_block_s = comm.max_over_ranks(time.perf_counter() - t0)
-    e2e_block_value = comm.world * n * args.steps / e2e_block_s
-    assert np.allclose(ll_host[0].numpy(), logl.cpu().numpy(), rtol=0, atol=0, equal_nan=True)
-    ll_host[0].zero_(); ll_host[1].zero_()
-    pipelined(max(2, args.warmup))
-    comm.barrier()
-    t0 = time.perf_counter()
-    pipelined(args.steps)
-    e2e_s = comm.max_over_ranks(time.perf_counter() - t0)
-    e2e_value = comm.world * n * args.steps / e2e_s
-    for b in range(2):
-        assert np.allclose(ll_host[b].numpy(), logl.cpu().numpy(), rtol=0, atol=0, equal_nan=True)
-    clocks.stop()
 
-    # ---- rooflines: every launch of the step against the FP64 peak measured live; `roofline` is the
-    # kernel with the largest share of the step
-    peak_tf = M.fp64_peak_tflops()
-    fa = f_alg(ds["flavour"], ds["period"], args.substeps, mean_taps(ds["flavour"], theta), _n_terms(M),
+def rooflines(M, ds, args_substeps, theta, n, kms, step_ms, peak_tf, ncu):
+    """FP64 and HBM view of every launch of the step.  `frac` is EXECUTED flop (ncu SASS count per chain of this
+    workload, when profiles/ncu_constants.json has it) / time / DFMA peak; `survey_formula_frac` prices the launch
+    with SURVEY 8d's formula (the reference's arithmetic, reductions applied) and can exceed 1 for the ODE launches."""
+    d = M.d
+    fa = f_alg(ds["flavour"], ds["period"], args_substeps, mean_taps(ds["flavour"], theta), _n_terms(M),
                {"age2q": 38, "age2i": 24}.get(ds["flavour"], 3))
     # pass-2 restart: D leading days are taken from the pass-1 checkpoint instead of being integrated
     # again (bit-identical, DESIGN.md §3).  SURVEY §8d: report F_alg with the reduced step count too.
     off_s, pad_s, _ = M.eval_detail(theta[:4096])
+    th = theta[:4096]
     lo_ = ds["lockdown_offset"]
     if ds["flavour"] == "age2q":
-        minbp = off_s + lo_ + theta[:4096, 18]
+        minbp = off_s + lo_ + th[:, 18]
         cap = 59
     elif ds["flavour"] == "age2i":
-        minbp = off_s + lo_ + theta[:4096, 20]
+        minbp = off_s + lo_ + th[:, 20]
         cap = min(ds["period"], 64) - 1
     else:
         minbp = (off_s + lo_).astype(float)
@@ -466,31 +470,7 @@ def main():
                                      ode_pass2=days_pass2 * step_flop * r_share,
                                      score=fa["per_kernel"]["score"] - (P_ - min(days_swept, P_)) * fa["score_per_day"])
     fa["total_executed"] = sum(fa["per_kernel_executed"].values())
-    knames = ["ode_pass1", "profiles_threshold", "ode_pass2", "score"]
-    kernel_fn = {"ode_pass1": "k_ode<pass1>", "profiles_threshold": "k_mid", "ode_pass2": "k_ode<pass2>", "score": "k_score"}
-    per_kernel = {}
-    ncu_match = (args.workload, n, args.substeps) == NCU_WORKLOAD
-    for k, msk in zip(knames, kms):
-        tf = fa["per_kernel_executed"][k] * n / (float(msk) * 1e-3) / 1e12
-        per_kernel[k] = {"kernel": kernel_fn[k], "ms": float(msk),
-                         "algorithmic_flop_per_launch": fa["per_kernel_executed"][k] * n,
-                         "algorithmic_flop_per_launch_without_reductions": fa["per_kernel"][k] * n,
-                         "achieved": tf, "frac": tf / peak_tf if peak_tf else None,
-                         "traffic": NCU_TRAFFIC.get(k) if ncu_match else None,
-                         "fp64_pipe_pct_ncu": NCU_FP64_PIPE_PCT.get(k) if ncu_match else None,
-                         "executed_fp64_flop_per_launch_ncu": NCU_EXECUTED_FLOP.get(k) if ncu_match else None,
-                         "executed_frac": (NCU_EXECUTED_FLOP[k] / (float(msk) * 1e-3) / 1e12 / peak_tf
-                                           if ncu_match and peak_tf else None)}
-    dom = knames[int(np.argmax(kms))]
-    step_ms = ms / args.steps
-    # the HBM view of the same launches (why the bound is FP64 and not memory): ALGORITHMIC bytes per launch — what
-    # each kernel has to read and write once — against the measured copy bandwidth of MEASURED_PEAKS.json
-    hbm_peak, hbm_src = 6650.0, "fallback of B200_PROFILING.md (MEASURED_PEAKS.json absent)"
-    try:
-        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "MEASURED_PEAKS.json")) as f:
-            hbm_peak, hbm_src = float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
-    except (OSError, KeyError, ValueError):
-        pass
+    hbm, hbm_src = hbm_peak()
     age = ds["flavour"] in ("age2q", "age2i")
     NGb, NEQb, padb = (2, 8, 80 if ds["flavour"] == "age2i" else 64) if age else (1, 3, 64)
     ck_days = min(P1_, 64)
@@ -501,61 +481,264 @@ def main():
         "ode_pass2": d * 8 + NEQb * 8 + row(min(int(d_mean) + 1, P1_)) + row(P_),  # theta, one checkpoint, head of pass-1 S in; S rows out
         "score": d * 8 + row(P_) + NGb * padb * 4 * 8 + 20,                       # theta, S rows, profile table in; logl, logp, status out
     }
-    for k, msk in zip(knames, kms):
-        gbs = bytes_alg[k] * n / (float(msk) * 1e-3) / 1e9
-        per_kernel[k]["hbm"] = {"algorithmic_bytes_per_launch": bytes_alg[k] * n, "achieved": gbs, "peak": hbm_peak,
-                                "unit": "GB/s", "frac": gbs / hbm_peak}
+    per_kernel = {}
+    kc = (ncu or {}).get("kernels", {})
+    n_cap = (ncu or {}).get("chains", 0)
+    for k, msk in zip(KNAMES, kms):
+        t = float(msk) * 1e-3
+        tf_formula = fa["per_kernel_executed"][k] * n / t / 1e12
+        c = kc.get(k)
+        # executed flop per chain from the capture of this workload (the count per chain does not depend on the batch)
+        ex = c["executed_fp64_flop"] / n_cap * n if c and n_cap else None
+        tf = ex / t / 1e12 if ex else None
+        gbs = bytes_alg[k] * n / t / 1e9
+        per_kernel[k] = {"kernel": KERNEL_FN[k], "ms": float(msk),
+                         "executed_fp64_flop_per_launch": ex, "achieved": tf, "frac": (tf / peak_tf if tf and peak_tf else None),
+                         "fp64_pipe_pct_ncu": c["fp64_pipe_pct"] if c and n == n_cap else None,
+                         "traffic": c["traffic_bytes"] if c and n == n_cap else None,
+                         "survey_formula_flop_per_launch": fa["per_kernel_executed"][k] * n,
+                         "survey_formula_flop_per_launch_without_reductions": fa["per_kernel"][k] * n,
+                         "survey_formula_tflops": tf_formula,
+                         "survey_formula_frac": tf_formula / peak_tf if peak_tf else None,
+                         "hbm": {"algorithmic_bytes_per_launch": bytes_alg[k] * n, "achieved": gbs, "peak": hbm, "unit": "GB/s",
+                                 "frac": gbs / hbm, "peak_source": hbm_src}}
+    ex_tot = sum(v["executed_fp64_flop_per_launch"] for v in per_kernel.values()) if all(
+        v["executed_fp64_flop_per_launch"] for v in per_kernel.values()) else None
     whole_tf = fa["total_executed"] * n / (step_ms * 1e-3) / 1e12
+    fsum = {"per_eval_survey_formula": fa["total"], "per_eval_survey_formula_with_reductions": fa["total_executed"],
+            "per_eval_executed_ncu": ex_tot / n if ex_tot else None,
+            "pass2_restart_days_mean": d_mean, "pass2_days_integrated_mean": days_pass2,
+            "score_days_swept_mean": days_swept, "pass1_days_integrated_mean": days_pass1, "period": P_,
+            "whole_step_executed_tflops": ex_tot / (step_ms * 1e-3) / 1e12 if ex_tot else None,
+            "whole_step_executed_frac": ex_tot / (step_ms * 1e-3) / 1e12 / peak_tf if ex_tot and peak_tf else None,
+            "whole_step_survey_formula_frac": whole_tf / peak_tf if peak_tf else None,
+            "whole_step_survey_formula_frac_without_reductions":
+                (fa["total"] * n / (step_ms * 1e-3) / 1e12) / peak_tf if peak_tf else None,
+            "note": "executed = FP64 flop the kernels actually execute (ncu SASS counts, profiles/ncu_constants.json); the "
+                    "survey formula prices the reference's arithmetic (124 flop per RHS call incl. guard comparisons, output "
+                    "variables, the removed compartment), about three times what the ODE kernels execute, so its fractions "
+                    "are NOT roofline fractions.  Reductions (all bit-identical, DESIGN.md section 4): pass 2 resumes from the "
+                    "pass-1 checkpoint and stops at the last data-window day, the score sweep covers the data windows, the "
+                    "removed compartment R is not integrated"}
+    return per_kernel, fsum
 
+
+def device_leg(M, ds, theta, args, comm, dev, stream, steps, warmup, peak_tf, ncu, world_chains):
+    """device-resident arm on one theta batch: value, per-kernel times, rooflines"""
+    b = DeviceBatch(M, theta, dev, stream)
+    ms, launches = timed(b, steps, warmup, comm, dev)
+    kms = kernel_ms(b, max(3, min(steps, 10)), dev)
+    step_ms = ms / steps
+    pk, fsum = rooflines(M, ds, args.substeps, theta, len(theta), kms, step_ms, peak_tf, ncu)
+    return {"value": world_chains * steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": step_ms, "steps": steps,
+            "kernels": kdict(kms), "status_nonzero": int((b.status != 0).sum().item())}, b, kms, launches, pk, fsum
+
+
+def secondary_legs(args, comm, dev, stream, peak_tf, ncu_all):
+    """one short timed leg per other BASELINE config, sharded like the headline (strong: total / N per GPU)"""
+    from epi_mcmc_b200.model import Model, load_dataset
+    import torch
+    legs = [("S120", 1 << 20, 4, "configs[0]/[3]: simple SEIR, 120-day horizon, 2^20 proposals"),
+            ("S365", 1 << 20, 4, "configs[3]: simple SEIR, 365-day horizon, 2^20 proposals"),
+            ("NE120", 4096, 4, "configs[1]: model-Ne, 4,096 chains"),
+            ("A365", 65536, 4, "configs[2] at the 365-day horizon"),
+            ("A300", 65536, 1, "configs[2] on the daily grid (m = 1, the north_star's wording)"),
+            ("I290", 65536, 4, "configs[2], secondary anchor model-age-groups2i")]
+    out = []
+    for wl, total, m, what in legs:
+        try:
+            ds = load_dataset(wl)
+        except OSError:
+            continue
+        n = (total + comm.world - 1) // comm.world if args.scaling == "strong" else total
+        M = Model(ds, substeps=m, device=dev)
+        mn, mx, init = M.df_params["min"], M.df_params["max"], M.df_params["init"]
+        kind = "posterior" if (posterior_gauss(wl) is not None and args.theta != "narrow") else "narrow"
+        whole = batch_theta(kind, wl, total, mn, mx, init)
+        theta = whole[comm.rank * n:(comm.rank + 1) * n] if args.scaling == "strong" else whole
+        b = DeviceBatch(M, theta, dev, stream)
+        for _ in range(3):
+            b.step()
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter(); b.step(); torch.cuda.synchronize(dev)
+        est = max(1e-4, time.perf_counter() - t0)
+        steps = int(min(200, max(5, 0.25 / est)))
+        ms, _ = timed(b, steps, 3, comm, dev)
+        kms = kernel_ms(b, 3, dev)
+        ncu = ncu_all.get(f"{wl}/m{m}/{kind}")
+        pk, fsum = rooflines(M, ds, m, theta, len(theta), kms, ms / steps, peak_tf, ncu)
+        tot_chains = total if args.scaling == "strong" else total * comm.world
+        out.append({"workload": wl, "what": what, "chains_total": tot_chains, "chains_per_gpu": len(theta), "substeps": m,
+                    "period": ds["period"], "params": M.d, "theta": kind, "steps": steps, "ms_per_step": ms / steps,
+                    "value": tot_chains * steps / (ms * 1e-3), "unit": UNIT, "kernels": kdict(kms),
+                    "executed_fp64_frac": fsum["whole_step_executed_frac"],
+                    "survey_formula_frac": fsum["whole_step_survey_formula_frac"],
+                    "fp64_pipe_pct_ncu": {k: v["fp64_pipe_pct_ncu"] for k, v in pk.items()} if ncu else None})
+        del b
+        M.close()
+        torch.cuda.empty_cache()
+    return out
+
+
+def main():
+    args = parse()
+    _claim_stdout()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    import torch
+    from epi_mcmc_b200.dist import Comm
+    from epi_mcmc_b200.model import Model, load_dataset
+
+    comm = Comm()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the evaluation path has no CPU fallback")
+    dev = comm.local_rank
+    torch.cuda.set_device(dev)
+    ds = load_dataset(args.workload)
+    M = Model(ds, substeps=args.substeps, device=dev)
+    d = M.d
+    mn, mx, init = M.df_params["min"], M.df_params["max"], M.df_params["init"]
+    world = comm.world
+    n = (args.chains + world - 1) // world if args.scaling == "strong" else args.chains
+    total_chains = args.chains if args.scaling == "strong" else args.chains * world
+    kind = theta_kind_of(args)
+    # the configuration's batch is the same whatever N; a strong-scaled rank takes its slice of it
+    whole = batch_theta(kind, args.workload, args.chains, mn, mx, init)
+    theta = whole[comm.rank * n:(comm.rank + 1) * n] if args.scaling == "strong" else whole
+    n = len(theta)
+    ncu_all = load_ncu_constants()
+    ncu = ncu_all.get(f"{args.workload}/m{args.substeps}/{kind}")
+    peak_tf = M.fp64_peak_tflops()
+    stream = torch.cuda.Stream(device=dev)   # the kernels are launched on THIS stream; so are the timing events
+    stream.wait_stream(torch.cuda.current_stream(dev))
+
+    clocks = ClockSampler(dev)
+    clocks.start()
+    time.sleep(0.3)   # let nvidia-smi start streaming before the timed region
+    # ---- device-resident arm (headline): theta SoA already in HBM when the timed region starts
+    head, hb, kms, launches, per_kernel, fsum = device_leg(M, ds, theta, args, comm, dev, stream, args.steps, args.warmup,
+                                                           peak_tf, ncu, total_chains)
+    value, step_ms = head["value"], head["ms_per_step"]
+    # ---- the same step for >= 1 s (the contract's K steps last ~60 ms at K = 20)
+    sus_steps = int(max(args.steps, np.ceil(1000.0 / step_ms)))
+    ms_s, _ = timed(hb, sus_steps, 1, comm, dev)
+    sustained = {"steps": sus_steps, "ms_per_step": ms_s / sus_steps, "value": total_chains * sus_steps / (ms_s * 1e-3), "unit": UNIT}
+    ref_logl = hb.logl.cpu().numpy().copy()
+
+    # ---- e2e arm: the public C-ABI with pinned HOST buffers, copies inside the timed region.
+    # (a) epi_eval: one blocking call per step (H2D -> kernels -> D2H strictly in sequence);
+    # (b) epi_eval_submit / epi_eval_wait: the same step, double-buffered — step k+1 is submitted before
+    #     step k is waited for, so its input copy (copy stream) overlaps the kernels of step k.  Every
+    #     step still moves its own n x d inputs from pinned host memory and its n x 20 B of results back.
+    # `e2e.value` is (b), the API a host-side driver with two independent batches in flight uses;
+    # (a) is reported beside it as e2e.blocking_call_value.
+    from epi_mcmc_b200 import _capi
+    import ctypes as C
+    th_host = [torch.from_numpy(theta.copy()).pin_memory() for _ in range(2)]
+    ll_host = [torch.empty(n, dtype=torch.float64).pin_memory() for _ in range(2)]
+    lp_host = [torch.empty(n, dtype=torch.float64).pin_memory() for _ in range(2)]
+    st_host = [torch.empty(n, dtype=torch.int32).pin_memory() for _ in range(2)]
+    dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int32)
+
+    def e2e_step():
+        _capi.check(M._lib.epi_eval(M._h, C.cast(th_host[0].data_ptr(), dp), n, _capi.LAYOUT_AOS,
+                                    C.cast(ll_host[0].data_ptr(), dp), C.cast(lp_host[0].data_ptr(), dp),
+                                    C.cast(st_host[0].data_ptr(), ip)), M._h)
+
+    def submit(k):
+        b = k & 1
+        _capi.check(M._lib.epi_eval_submit(M._h, b, C.cast(th_host[b].data_ptr(), dp), n, _capi.LAYOUT_AOS,
+                                           C.cast(ll_host[b].data_ptr(), dp), C.cast(lp_host[b].data_ptr(), dp),
+                                           C.cast(st_host[b].data_ptr(), ip)), M._h)
+
+    def wait(k):
+        _capi.check(M._lib.epi_eval_wait(M._h, k & 1), M._h)
+
+    def pipelined(steps):
+        submit(0)
+        for k in range(1, steps):
+            submit(k)
+            wait(k - 1)
+        wait(steps - 1)
+
+    for _ in range(max(1, args.warmup)):
+        e2e_step()
+    comm.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()       # returns after the D2H copies completed (stream synchronised inside)
+    e2e_block_s = comm.max_over_ranks(time.perf_counter() - t0)
+    e2e_block_value = total_chains * args.steps / e2e_block_s
+    assert np.allclose(ll_host[0].numpy(), ref_logl, rtol=0, atol=0, equal_nan=True)
+    ll_host[0].zero_(); ll_host[1].zero_()
+    pipelined(max(2, args.warmup))
+    comm.barrier()
+    t0 = time.perf_counter()
+    pipelined(args.steps)
+    e2e_s = comm.max_over_ranks(time.perf_counter() - t0)
+    e2e_value = total_chains * args.steps / e2e_s
+    for b in range(2):
+        assert np.allclose(ll_host[b].numpy(), ref_logl, rtol=0, atol=0, equal_nan=True)
+    clocks.stop()
+
+    # ---- the narrow cloud of round 1 (warps in lock-step) beside the headline
+    narrow = None
+    if kind == "posterior":
+        wn = batch_theta("narrow", args.workload, args.chains, mn, mx, init)
+        tn = wn[comm.rank * n:(comm.rank + 1) * n] if args.scaling == "strong" else wn
+        narrow, _, _, _, _, _ = device_leg(M, ds, tn, args, comm, dev, stream, args.steps, args.warmup, peak_tf, None, total_chains)
+        narrow["theta"] = THETA_LABEL["narrow"]
+    # ---- weak-scaling figure of a strong run: every GPU evaluates the whole configuration's batch
+    weak = None
+    if args.scaling == "strong" and world > 1:
+        weak, _, _, _, _, _ = device_leg(M, ds, whole, args, comm, dev, stream, args.steps, args.warmup, peak_tf, None,
+                                         args.chains * world)
+        weak["chains_per_gpu"] = args.chains
+
+    dom = KNAMES[int(np.argmax(kms))]
+    r = per_kernel[dom]
+    # frac: executed flop of the capture when there is one for this workload; otherwise the survey formula, capped
+    # so that no fraction above 1 is ever printed as a roofline fraction
+    frac_src = "executed FP64 flop per chain of profiles/ncu_constants.json (ncu SASS counts of this workload) x chains / launch time"
+    ach, frac = r["achieved"], r["frac"]
+    if ach is None:
+        ach, frac = r["survey_formula_tflops"], r["survey_formula_frac"]
+        frac_src = "SURVEY 8d formula with the reductions applied (no ncu capture of this workload)"
+        if frac and frac > 1:
+            ach, frac = None, None
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": comm.world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": step_ms, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": workload_name(args, ds["period"]),
-                   "chains_per_gpu": n, "params": d, "period": ds["period"], "substeps": args.substeps,
-                   "theta": "init +- 0.5% of the df_params box (every chain integrates both passes)",
-                   "l2": "inputs larger than L2: the S-history/profile working set of one step is "
-                         f"{_ws_mb(ds, n):.0f} MB vs 126 MB L2",
-                   "parallelism": f"chains sharded over {comm.world} GPU(s), no data-path collective"},
+        "config": make_config(args, ds["period"], n, world, d, kind, _ws_mb(ds, n)),
         "clocks": clocks.summary(),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n * d * 8), "d2h_bytes_per_step": int(n * 20),
+                "bytes_are": "per GPU",
                 "api": "epi_eval_submit/epi_eval_wait, two batches in flight (input copy of step k+1 overlaps the kernels of step k)",
                 "blocking_call_value": e2e_block_value, "blocking_call_api": "epi_eval, one blocking call per step"},
         "gpu_launches": int(launches),
-        "kernels": {"ode_pass1_ms": float(kms[0]), "profiles_threshold_ms": float(kms[1]), "ode_pass2_ms": float(kms[2]),
-                    "score_ms": float(kms[3])},
-        "roofline": {"bound": "fp64", "kernel": per_kernel[dom]["kernel"], "achieved": per_kernel[dom]["achieved"],
-                     "peak": peak_tf, "unit": "TFLOP/s", "frac": per_kernel[dom]["frac"],
-                     "traffic": per_kernel[dom]["traffic"],
+        "kernels": head["kernels"],
+        "sustained": sustained,
+        "roofline": {"bound": "fp64", "kernel": r["kernel"], "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": frac,
+                     "traffic": r["traffic"], "frac_source": frac_src, "fp64_pipe_pct_ncu": r["fp64_pipe_pct_ncu"],
+                     "survey_formula_frac": r["survey_formula_frac"],
                      "peak_source": "measured live: DFMA-chain microbenchmark epi_fp64_peak (MEASURED_PEAKS.json has no FP64 entry; "
                                     "nominal 37.2 TFLOP/s = 148 SM x 64 DFMA/clk x 2 x 1.965 GHz)",
-                     "algorithmic_flop_per_launch": per_kernel[dom]["algorithmic_flop_per_launch"],
-                     "hbm": dict(per_kernel[dom]["hbm"], peak_source=hbm_src),
-                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, "
-                                       "profiles/r1_v15_ncu_full.txt (65,536 chains, A300)"},
+                     "hbm": r["hbm"],
+                     "traffic_source": ("dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, profiles/"
+                                        + str((ncu or {}).get("source"))) if r["traffic"] else None},
         "roofline_all": per_kernel,
-        "posterior_cloud": cloud,
-        "f_alg": {"per_eval": fa["total"], "per_eval_executed": fa["total_executed"],
-                  "pass2_restart_days_mean": d_mean, "pass2_days_integrated_mean": days_pass2,
-                  "score_days_swept_mean": days_swept, "pass1_days_integrated_mean": days_pass1, "period": P_, "ode_share": fa["ode"] / fa["total"],
-                  "whole_step_tflops": whole_tf, "whole_step_frac": whole_tf / peak_tf if peak_tf else None,
-                  "whole_step_frac_if_counted_without_reductions":
-                      (fa["total"] * n / (step_ms * 1e-3) / 1e12) / peak_tf if peak_tf else None,
-                  "whole_step_executed_frac_ncu": (sum(NCU_EXECUTED_FLOP.values()) / (step_ms * 1e-3) / 1e12 / peak_tf
-                                                   if ncu_match and peak_tf else None),
-                  "note": "per_eval is the SURVEY 8d figure (the reference's arithmetic; the ODE kernels execute about a "
-                          "third of it, so their algorithmic frac exceeds 1 — executed_frac / fp64_pipe_pct_ncu in "
-                          "roofline_all are counted from the ncu SASS table instead); per_eval_executed and every frac count only the work "
-                          "actually done: pass 2 resumes from the pass-1 checkpoint after pass2_restart_days_mean "
-                          "bit-identical days and stops at the last data-window day, the score sweep covers the data "
-                          "windows plus one predecessor day, and the removed compartment R is not integrated (it only "
-                          "enters the reference through a bounds guard that provably cannot fire on it; chains where that "
-                          "is not certain are recomputed with R) — results identical bit for bit; DESIGN.md section 4"},
+        "f_alg": fsum,
+        "narrow_cloud": narrow,
+        "weak": weak,
     }
-    if comm.rank == 0 and comm.world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(ds, theta, args.substeps)
+    if not args.no_secondary:
+        line["secondary"] = secondary_legs(args, comm, dev, stream, peak_tf, ncu_all)
+    if comm.rank == 0 and world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(ds, theta, args.substeps, workload=args.workload)
     if not args.no_sampler:
-        line["sampler"] = sampler_leg(M, comm, args)
+        line["sampler"] = sampler_leg(M, comm, args, n)
     if comm.rank == 0:
         emit(line)
     M.close()
@@ -582,17 +765,38 @@ def _ws_mb(ds, n):
     return n * (2 * P * 8 + 2 * 64 * 8) / 1e6
 
 
-def sampler_leg(M, comm, args):
-    """DE-MC with the fused propose/accept kernel: chain state stays on the GPU; the population
-    is all-gathered over NCCL every 10 iterations.  evals/s inside the sampler, and ESS/s over the
-    recorded sampling phase (coda spectral ESS of `fitkeyparamnames`, measured on 64 chains of this
-    rank and scaled to the whole population; min and median over the parameters)."""
+def k2_roofline(M, chains_list=(65536, 1 << 22)):
+    """the fused accept/propose kernel alone (epi_k2_bench): device time per launch, algorithmic bytes, GB/s against
+    the measured HBM copy bandwidth.  65,536 chains x 45 parameters live in L2; 2^22 chains do not."""
+    import ctypes as C
+    from epi_mcmc_b200 import _capi
+    hbm, src = hbm_peak()
+    out = []
+    for nc in chains_list:
+        us, by, ar = C.c_double(), C.c_double(), C.c_double()
+        _capi.check(M._lib.epi_k2_bench(M._h, _capi.SAMPLER_DEMC, int(nc), 50, C.byref(us), C.byref(by), C.byref(ar)), M._h)
+        gbs = by.value / (us.value * 1e-6) / 1e9
+        out.append({"chains": int(nc), "kernel": "k_accept_propose (DE-MC, subspace updates)", "us_per_iter": us.value,
+                    "algorithmic_bytes": by.value, "achieved_GBs": gbs, "peak_GBs": hbm, "frac": gbs / hbm,
+                    "accept_rate": ar.value, "population_MB": nc * M.d * 8 / 1e6, "peak_source": src})
+    return out
+
+
+def sampler_leg(M, comm, args, n):
+    """DE-MC with the fused propose/accept kernel: chain state stays on the GPU; the population is all-gathered over
+    NCCL every 10 iterations (side stream, double-buffered).  The population runs as B independent replicate
+    populations (EPI_SAMPLER_FLAG_REPLICATES; a replicate spans all ranks): ESS of the whole run for a posterior mean
+    = B var_posterior / var(replicate means), which needs no assumption about the dependence of the chains inside a
+    population.  Reported for the whole recorded phase and for its first half (a stationary run gives the same
+    ESS/s for both), with split R-hat over one chain per replicate."""
     import torch
-    from epi_mcmc_b200.sampler import Sampler, pooled_ess
-    n = args.chains
-    S = Sampler(M, n, kind="demc", seed=42, chain_id0=comm.rank * n, subspace=not args.sampler_fulldim)
+    from epi_mcmc_b200.sampler import Sampler
+    B = 64 if n % 64 == 0 and n // 64 >= 8 else (8 if n % 8 == 0 else 1)
+    S = Sampler(M, n, kind="demc", seed=42, chain_id0=comm.rank * n, subspace=not args.sampler_fulldim, rungs=B,
+                replicates=B > 1)
     comm.attach(S)
     burn, iters = args.sampler_burnin, args.sampler_iters
+    thin = 10
     S.adapt(True)
     torch.cuda.synchronize()
     comm.barrier()
@@ -601,31 +805,68 @@ def sampler_leg(M, comm, args):
         S.run(10)
         comm.exchange(S)
     S.adapt(False)
-    S.record(1, iters)
+    comm.exchange(S, wait=True)   # the archive of the recorded phase: the population at the end of burn-in
+    S.record(thin, iters // thin)
     torch.cuda.synchronize()
     comm.barrier()
     burn_s = comm.max_over_ranks(time.perf_counter() - tb)
     ev0 = S.stats()["evals"]
+    acc0 = S.stats()["accepted"]
     t0 = time.perf_counter()
     for _ in range(iters // 10):
         S.run(10)
-        comm.exchange(S)
     torch.cuda.synchronize()
     dt = comm.max_over_ranks(time.perf_counter() - t0)
     st = S.stats()
-    n_sub = min(64, n)
-    draws, _ = S.draws_subset(0, n_sub)
+    # the evaluation kernels alone on the sampler's OWN population (its chains have drifted apart further than the
+    # Gaussian summary the headline cloud is drawn from): what an iteration costs beyond that is K2 + sequencing
+    th_ptr, ll_ptr, lp_ptr, ld = S.state_device()
+    scr = [torch.empty(n, dtype=torch.float64, device=f"cuda:{M.device}") for _ in range(2)]
+    scr_st = torch.empty(n, dtype=torch.int32, device=f"cuda:{M.device}")
+    pstream = torch.cuda.Stream(device=M.device)
+    def pop_step():
+        M.eval_device_range(th_ptr, ld, n, 0, n, scr[0].data_ptr(), scr[1].data_ptr(), scr_st.data_ptr(), pstream.cuda_stream)
+    for _ in range(3):
+        pop_step()
+    torch.cuda.synchronize()
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record(pstream)
+    for _ in range(20):
+        pop_step()
+    p1.record(pstream)
+    torch.cuda.synchronize()
+    pop_ms = comm.max_over_ranks(p0.elapsed_time(p1)) / 20
     keys = [M.fit_paramnames.index(k) for k in M.fitkeyparamnames if k in M.fit_paramnames]
-    ess = pooled_ess(draws[:, :, keys]) * (n / n_sub)
-    return {"kind": "DE-MC (scale mixture, subspace updates), population snapshot all-gathered every 10 iterations",
-            "chains_per_gpu": n, "burnin_iterations": burn, "burnin_s": burn_s, "sampling_iterations": iters,
-            "sampling_s": dt, "evals_per_s": comm.world * (st["evals"] - ev0) / dt, "accept_rate": st["accept_rate"],
-            "ess_per_s_min": comm.world * float(ess.min()) / dt, "ess_per_s_median": comm.world * float(np.median(ess)) / dt,
-            "ess_per_eval_median": float(np.median(ess)) / max(1, st["evals"] - ev0),
-            "note": "ESS of 64 chains of rank 0 scaled to all chains and ranks; sampling phase only; chains start "
-                    "at the model file's init + 2% box jitter.  The spectral ESS of a chain shorter than a few "
-                    "integrated autocorrelation times is biased upwards: on this target 200 + 400 iterations report "
-                    "~158 k ESS/s per GPU, 1000 + 3000 ~25 k, 2000 + 6000 ~12 k (profiles/r1_summary.md)"}
+    full = S.replicate_stats(keys, comm) if B > 1 else None
+    half = S.replicate_stats(keys, comm, last=(iters // thin) // 2) if B > 1 else None
+    evals = comm.world * (st["evals"] - ev0)
+    out = {"kind": "DE-MC (scale mixture, subspace updates); burn-in: population snapshot all-gathered every 10 iterations "
+                   "(side stream, double-buffered) and proposal shape re-measured; recorded phase: both frozen",
+           "chains_per_gpu": n, "replicate_populations": B * 1, "chains_per_replicate": (n // B) * comm.world,
+           "burnin_iterations": burn, "burnin_s": burn_s, "burnin_evals_per_s": comm.world * n * burn / burn_s,
+           "sampling_iterations": iters, "sampling_s": dt, "thin": thin,
+           "evals_per_s": evals / dt, "accept_rate": (st["accepted"] - acc0) / max(1, (st["evals"] - ev0)),
+           "ms_per_iteration": 1e3 * dt / iters, "eval_kernels_on_this_population_ms": pop_ms,
+           "evals_per_s_vs_bare_eval_of_this_population": (1e3 * dt / iters and pop_ms / (1e3 * dt / iters))}
+    if full is not None:
+        e_full, e_half = float(np.median(full["ess"])), float(np.median(half["ess"]))
+        out.update({"ess_median": e_full, "ess_median_first_half": e_half,
+                    "ess_per_s_median": e_full / dt, "ess_per_s_min": float(full["ess"].min()) / dt,
+                    "ess_per_s_median_first_half": e_half / (dt / 2),
+                    "ess_growth_per_s": (e_full - e_half) / (dt / 2),
+                    "ess_per_eval_median": e_full / max(1, evals),
+                    "ess_note": "ESS of the posterior-mean estimator over ALL chains and recorded iterations.  When the recorded "
+                                "window is shorter than a chain's integrated autocorrelation time, the ESS is carried by the "
+                                "spread of the population at the start of the window and barely grows with it (ess_median vs "
+                                "ess_median_first_half, split R-hat well above 1): ESS / window is then NOT an asymptotic "
+                                "rate — ess_growth_per_s is the rate at which the window adds information",
+                    "split_rhat_max": float(full["rhat"].max()), "split_rhat_median": float(np.median(full["rhat"])),
+                    "ess_method": f"between-replicate variance of the posterior-mean estimator over {full['n_replicates']} independent "
+                                  f"replicate populations (relative sd of the estimate ~ sqrt(2 / {full['n_replicates'] - 1})), "
+                                  f"{len(keys)} key parameters; split R-hat over one chain per replicate"})
+    if comm.rank == 0:
+        out["k2"] = k2_roofline(M)
+    return out
 
 
 if __name__ == "__main__":

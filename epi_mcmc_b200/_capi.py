@@ -24,7 +24,8 @@ INVALID_DATA_OFFSET = 10000
 
 ST_INVALID_OFFSET, ST_NA, ST_OUT_OF_BOX, ST_UNSUPPORTED = 1, 2, 8, 16
 LAYOUT_AOS, LAYOUT_SOA = 0, 1
-SAMPLER_RWM, SAMPLER_DEMC = 0, 1
+SAMPLER_RWM, SAMPLER_DEMC, SAMPLER_DRJ = 0, 1, 2
+SAMPLER_FLAG_FULLDIM, SAMPLER_FLAG_REPLICATES = 1, 2
 
 ERR_NAMES = {0: "EPI_OK", 1: "EPI_ERR_ARG", 2: "EPI_ERR_NO_DEVICE", 3: "EPI_ERR_CUDA",
              4: "EPI_ERR_NOMEM", 5: "EPI_ERR_STATE"}
@@ -105,6 +106,7 @@ SYMBOLS = (
     "epi_n_series", "epi_trajectories", "epi_n_series_ext", "epi_trajectories_ext", "epi_quantiles", "epi_sampler_init", "epi_sampler_run",
     "epi_sampler_adapt", "epi_sampler_set_scale", "epi_sampler_state_device", "epi_sampler_set_population",
     "epi_sampler_get", "epi_sampler_stats", "epi_sampler_pt_stats", "epi_sampler_record", "epi_sampler_draws", "epi_sampler_draws_subset",
+    "epi_sampler_draws_device", "epi_sampler_bandwidths", "epi_k2_bench",
     "epi_fp64_peak", "epi_set_timing", "epi_last_kernel_ms", "epi_launch_count", "epi_fallback_count", "epi_philox_probe",
 )
 
@@ -142,6 +144,9 @@ def load():
     lib.epi_n_series_ext.argtypes = [vp]
     lib.epi_trajectories_ext.argtypes = [vp, _dp, i64, C.c_int, i32, _dp, ip, ip]
     lib.epi_quantiles.argtypes = [vp, _dp, i64, C.c_int, i32, i32, i32, i32, _dp, i32, _dp]
+    lib.epi_sampler_draws_device.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), ip, C.POINTER(i64)]
+    lib.epi_sampler_bandwidths.argtypes = [vp, _dp]
+    lib.epi_k2_bench.argtypes = [vp, i32, i64, i32, _dp, _dp, _dp]
     lib.epi_sampler_init.argtypes = [vp, C.POINTER(SamplerCfg), _dp]
     lib.epi_sampler_run.argtypes = [vp, i32]
     lib.epi_sampler_adapt.argtypes = [vp, C.c_int, C.c_double]

@@ -50,6 +50,13 @@ struct SamplerState {
   int adapt = 0;
   double adapt_target = 0.0;  // <= 0: shape adaptation only (classical AM / DE-MC step sizes)
   int64_t iter = 0, evals = 0;
+  // EPI_SAMPLER_DRJ: per-chain, per-parameter bandwidths on the phi scale (d x ld), the parameters with a
+  // non-degenerate box (the sweep order), sub-iteration counter (the Philox "iteration" of a single-parameter
+  // update) and the number of sweeps adaptation has seen (Robbins-Monro gain 1/sqrt(k))
+  double *bw = nullptr;
+  std::vector<int> free_params;
+  int64_t sub = 0, adapt_sweeps = 0;
+  bool replicates = false;
 };
 
 // ----------------------------------------------------------------- Philox4x32
@@ -254,6 +261,102 @@ k_accept_propose(int d, int64_t n, int64_t ld, int kind, uint64_t seed, int64_t 
   }
 }
 
+// drjacoby's update, one parameter per launch (R/MCMC/fitMCMC-drj.R:48-57 drives drjacoby::run_mcmc; the
+// algorithm restated here is the published one of the package, which is not part of the reference tree):
+//   phi = log((theta - a) / (b - theta));  phi' ~ N(phi, bw);  theta' = (b e^phi' + a) / (1 + e^phi')
+//   MH  = beta (logl' - logl) + (logp' - logp) + log((theta' - a)(b - theta')) - log((theta - a)(b - theta))
+//   Robbins-Monro while adapting: log bw += gain ((accepted ? 1 : 0) - target), gain = 1 / sqrt(sweep)
+// `prop` equals `cur` in every coordinate but the one being proposed, so a launch touches two coordinates:
+// it decides the pending move of p_acc (restoring prop[p_acc] on reject) and writes the move of p_new.
+// After a rung swap (full_sync) the whole proposal row is rewritten from the current state.
+__global__ void __launch_bounds__(128)
+k_drj_step(int d, int64_t n, int64_t ld, uint64_t seed, int64_t chain_id0, int64_t sub_acc, int p_acc, int p_new,
+           int full_sync, const double *__restrict__ beta_rung, int cpr, const double *__restrict__ box_min,
+           const double *__restrict__ box_max, double *__restrict__ cur, double *__restrict__ prop,
+           double *__restrict__ logl, double *__restrict__ logp, const double *__restrict__ logl_p,
+           const double *__restrict__ logp_p, const int *__restrict__ status_p, double *__restrict__ bw, int adapt,
+           double gain, double target, unsigned long long *__restrict__ acc_total, double *__restrict__ draw_out,
+           double *__restrict__ draw_lp) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = i < n;
+  const uint64_t cid = (uint64_t)(chain_id0 + i);
+  const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+  uint32_t r[4];
+  bool accepted = false;
+  if (live && p_acc >= 0) {
+    const double beta = beta_rung ? beta_rung[i / cpr] : 1.0;
+    philox4x32_10((uint32_t)cid, (uint32_t)(cid >> 32), (uint32_t)sub_acc, USE_ACCEPT, k0, k1, r);
+    const double a = box_min[p_acc], b = box_max[p_acc];
+    const double x = cur[(int64_t)p_acc * ld + i], y = prop[(int64_t)p_acc * ld + i];
+    const double ll0 = logl[i], lp0 = logp[i], ll1 = logl_p[i], lp1 = logp_p[i];
+    const double adj = log((y - a) * (b - y)) - log((x - a) * (b - x));
+    const double mh = beta * (ll1 - ll0) + (lp1 - lp0) + adj;
+    const bool new_ok = isfinite(beta * ll1 + lp1) && !(status_p[i] & (EPI_ST_NA | EPI_ST_UNSUPPORTED)) && y > a && y < b;
+    const bool cur_ok = isfinite(beta * ll0 + lp0);
+    accepted = new_ok && (!cur_ok || log(u01(r[0])) < mh);
+    if (accepted) {
+      cur[(int64_t)p_acc * ld + i] = y;
+      logl[i] = ll1;
+      logp[i] = lp1;
+    } else if (!full_sync) {
+      prop[(int64_t)p_acc * ld + i] = x;
+    }
+    if (adapt) bw[(int64_t)p_acc * ld + i] *= exp(gain * ((accepted ? 1.0 : 0.0) - target));
+  }
+  if (p_acc >= 0) {
+    const unsigned bal = __ballot_sync(0xffffffffu, accepted);
+    if ((threadIdx.x & 31) == 0 && bal) atomicAdd(acc_total, (unsigned long long)__popc(bal));
+  }
+  if (!live) return;
+  if (draw_out) {
+#pragma unroll 8
+    for (int p = 0; p < d; ++p) draw_out[(int64_t)p * ld + i] = cur[(int64_t)p * ld + i];
+    draw_lp[i] = logl[i] + logp[i];
+  }
+  if (full_sync) {
+#pragma unroll 8
+    for (int p = 0; p < d; ++p) prop[(int64_t)p * ld + i] = cur[(int64_t)p * ld + i];
+  }
+  if (p_new >= 0) {
+    philox4x32_10((uint32_t)cid, (uint32_t)(cid >> 32), (uint32_t)(sub_acc + 1), USE_NORMAL, k0, k1, r);
+    double z0, z1;
+    box_muller(r[0], r[1], z0, z1);
+    const double a = box_min[p_new], b = box_max[p_new], w = b - a;
+    const double x = cur[(int64_t)p_new * ld + i];
+    // a state exactly on the boundary has phi = +-inf: step from just inside (the Jacobian term of the true
+    // state is +inf, so whatever is proposed from there is accepted and the chain leaves the boundary)
+    const double xi = fmin(fmax(x, a + 1e-12 * w), b - 1e-12 * w);
+    const double phi = log((xi - a) / (b - xi)) + bw[(int64_t)p_new * ld + i] * z0;
+    prop[(int64_t)p_new * ld + i] = a + w / (1.0 + exp(-phi));
+  }
+}
+
+// synthetic population for epi_k2_bench: uniform in the box, Philox keyed like the sampler
+__global__ void k_fill_uniform(int d, int64_t n, int64_t ld, uint64_t seed, const double *__restrict__ box_min,
+                               const double *__restrict__ box_max, double *__restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t r[4];
+  for (int p0 = 0; p0 < d; p0 += 4) {
+    philox4x32_10((uint32_t)i, (uint32_t)(i >> 32), 0xFFFFFFFEu, (uint32_t)p0, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+    for (int q = 0; q < 4 && p0 + q < d; ++q)
+      out[(int64_t)(p0 + q) * ld + i] = box_min[p0 + q] + (box_max[p0 + q] - box_min[p0 + q]) * u01(r[q]);
+  }
+}
+// log density of the proposals of epi_k2_bench: a fixed, hashed fraction of the chains accepts every proposal
+// (+1e6 on the first one, equal densities afterwards), the others none (-inf)
+__global__ void k_fill_accept_pattern(int64_t n, uint64_t seed, double frac, double *__restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t r[4];
+  philox4x32_10((uint32_t)i, (uint32_t)(i >> 32), 0xFFFFFFFDu, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+  out[i] = u01(r[0]) < frac ? 1e6 : -INFINITY;
+}
+__global__ void k_fill_const(int64_t n, double v, double *__restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = v;
+}
+
 // population covariance of the chains of this rank: one block per (p, q), q <= p
 __global__ void __launch_bounds__(256) k_cov(const double *__restrict__ cur_all, int64_t n, int64_t ld, int d,
                                              double *__restrict__ cov_all) {
@@ -345,7 +448,7 @@ void epi_sampler_free(epi_handle *h) {
   SamplerState *s = h->sampler;
   if (!s) return;
   cudaFree(s->cur); cudaFree(s->prop); cudaFree(s->logl); cudaFree(s->logp); cudaFree(s->logl_p); cudaFree(s->logp_p);
-  cudaFree(s->status_p); cudaFree(s->lscale); cudaFree(s->psd); cudaFree(s->cov); cudaFree(s->chol); cudaFree(s->beta_rung); cudaFree(s->swaps); cudaFree(s->acc); cudaFree(s->pop_own); cudaFree(s->draws); cudaFree(s->draws_lp);
+  cudaFree(s->status_p); cudaFree(s->lscale); cudaFree(s->psd); cudaFree(s->cov); cudaFree(s->chol); cudaFree(s->beta_rung); cudaFree(s->swaps); cudaFree(s->acc); cudaFree(s->pop_own); cudaFree(s->draws); cudaFree(s->draws_lp); cudaFree(s->bw);
   delete s;
   h->sampler = nullptr;
 }
@@ -416,51 +519,84 @@ static int launch_ap(epi_handle *h, SamplerState *s, int do_accept, double *draw
   return EPI_OK;
 }
 
+// one k_drj_step launch for all chains on the handle's stream
+static int launch_drj(epi_handle *h, SamplerState *s, int64_t sub_acc, int p_acc, int p_new, int full_sync, double *draw_out,
+                      double *draw_lp) {
+  const int64_t n = s->cfg.n_chains;
+  const double gain = 1.0 / std::sqrt((double)(s->adapt_sweeps + 1));
+  const double target = s->adapt_target > 0 ? s->adapt_target : 0.44;
+  k_drj_step<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(
+      h->M.d, n, s->ld, s->cfg.seed, s->cfg.chain_id0, sub_acc, p_acc, p_new, full_sync,
+      s->n_rungs > 1 ? s->beta_rung : nullptr, s->cpr, h->M.box_min, h->M.box_max, s->cur, s->prop, s->logl, s->logp,
+      s->logl_p, s->logp_p, s->status_p, s->bw, s->adapt, gain, target, s->acc, draw_out, draw_lp);
+  h->launches += 1;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return epi_fail(h, EPI_ERR_CUDA, "k_drj_step: %s", cudaGetErrorString(e));
+  return EPI_OK;
+}
+
+// every failure path of init releases the half-built sampler: a later epi_sampler_* call then reports
+// EPI_ERR_STATE instead of running on garbage
+#define INIT_OK(h, call)                                                                              \
+  do {                                                                                                \
+    cudaError_t e_ = (call);                                                                          \
+    if (e_ != cudaSuccess) {                                                                          \
+      epi_sampler_free(h);                                                                            \
+      return epi_fail(h, EPI_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_));                      \
+    }                                                                                                 \
+  } while (0)
+
 extern "C" int epi_sampler_init(epi_handle *h, const epi_sampler_cfg *cfg, const double *theta0) {
   if (!h || !cfg || cfg->n_chains < 1) return epi_fail(h, EPI_ERR_ARG, "bad sampler config");
-  if (cfg->kind != EPI_SAMPLER_RWM && cfg->kind != EPI_SAMPLER_DEMC) return epi_fail(h, EPI_ERR_ARG, "unknown sampler kind");
+  if (cfg->kind != EPI_SAMPLER_RWM && cfg->kind != EPI_SAMPLER_DEMC && cfg->kind != EPI_SAMPLER_DRJ)
+    return epi_fail(h, EPI_ERR_ARG, "unknown sampler kind");
+  // the whole configuration is checked before anything is allocated or installed
+  const int n_rungs = cfg->n_rungs > 1 ? cfg->n_rungs : 1;
+  if (cfg->n_chains % n_rungs) return epi_fail(h, EPI_ERR_ARG, "n_chains must be a multiple of n_rungs");
+  if (cfg->kind == EPI_SAMPLER_DEMC && cfg->n_chains / n_rungs < 3)
+    return epi_fail(h, EPI_ERR_ARG, "DE-MC needs at least 3 chains per rung");
   CUDA_OK(h, cudaSetDevice(h->device));
   epi_sampler_free(h);
   SamplerState *s = new SamplerState();
   h->sampler = s;
   s->cfg = *cfg;
   if (!(s->cfg.beta > 0)) s->cfg.beta = 1.0;
+  s->replicates = (cfg->reserved & EPI_SAMPLER_FLAG_REPLICATES) != 0;
   const int d = h->M.d;
   const int64_t n = cfg->n_chains;
   s->ld = (n + kTile - 1) / kTile * kTile;
+  s->n_rungs = n_rungs;
+  s->cpr = cfg->n_chains / n_rungs;
   const size_t mat = sizeof(double) * (size_t)(d * s->ld), vec = sizeof(double) * (size_t)s->ld;
-  CUDA_OK(h, cudaMalloc(&s->cur, mat));
-  CUDA_OK(h, cudaMalloc(&s->prop, mat));
-  CUDA_OK(h, cudaMalloc(&s->logl, vec));
-  CUDA_OK(h, cudaMalloc(&s->logp, vec));
-  CUDA_OK(h, cudaMalloc(&s->logl_p, vec));
-  CUDA_OK(h, cudaMalloc(&s->logp_p, vec));
-  CUDA_OK(h, cudaMalloc(&s->status_p, sizeof(int) * (size_t)s->ld));
-  CUDA_OK(h, cudaMalloc(&s->lscale, vec));
-  CUDA_OK(h, cudaMalloc(&s->acc, sizeof(unsigned long long)));
-  CUDA_OK(h, cudaMalloc(&s->psd, sizeof(double) * (size_t)d));
-  s->n_rungs = cfg->n_rungs > 1 ? cfg->n_rungs : 1;
-  if (cfg->n_chains % s->n_rungs) return epi_fail(h, EPI_ERR_ARG, "n_chains must be a multiple of n_rungs");
-  s->cpr = cfg->n_chains / s->n_rungs;
-  CUDA_OK(h, cudaMalloc(&s->cov, sizeof(double) * (size_t)s->n_rungs * d * d));
-  CUDA_OK(h, cudaMalloc(&s->chol, sizeof(double) * (size_t)s->n_rungs * d * d));
-  CUDA_OK(h, cudaMalloc(&s->swaps, 2 * sizeof(unsigned long long)));
-  CUDA_OK(h, cudaMemsetAsync(s->swaps, 0, 2 * sizeof(unsigned long long), h->stream));
+  INIT_OK(h, cudaMalloc(&s->cur, mat));
+  INIT_OK(h, cudaMalloc(&s->prop, mat));
+  INIT_OK(h, cudaMalloc(&s->logl, vec));
+  INIT_OK(h, cudaMalloc(&s->logp, vec));
+  INIT_OK(h, cudaMalloc(&s->logl_p, vec));
+  INIT_OK(h, cudaMalloc(&s->logp_p, vec));
+  INIT_OK(h, cudaMalloc(&s->status_p, sizeof(int) * (size_t)s->ld));
+  INIT_OK(h, cudaMalloc(&s->lscale, vec));
+  INIT_OK(h, cudaMalloc(&s->acc, sizeof(unsigned long long)));
+  INIT_OK(h, cudaMalloc(&s->psd, sizeof(double) * (size_t)d));
+  INIT_OK(h, cudaMalloc(&s->cov, sizeof(double) * (size_t)s->n_rungs * d * d));
+  INIT_OK(h, cudaMalloc(&s->chol, sizeof(double) * (size_t)s->n_rungs * d * d));
+  INIT_OK(h, cudaMalloc(&s->swaps, 2 * sizeof(unsigned long long)));
+  INIT_OK(h, cudaMemsetAsync(s->swaps, 0, 2 * sizeof(unsigned long long), h->stream));
   {
     std::vector<double> br(s->n_rungs, 1.0);
     const double pw = cfg->gti_pow > 0 ? cfg->gti_pow : 1.0;
     for (int r = 0; r < s->n_rungs; ++r)
-      br[r] = s->n_rungs > 1 ? std::pow((double)r / (double)(s->n_rungs - 1), pw) : 1.0;
-    CUDA_OK(h, cudaMalloc(&s->beta_rung, sizeof(double) * (size_t)s->n_rungs));
-    CUDA_OK(h, cudaMemcpyAsync(s->beta_rung, br.data(), sizeof(double) * br.size(), cudaMemcpyHostToDevice, h->stream));
-    CUDA_OK(h, cudaStreamSynchronize(h->stream));
+      br[r] = (s->n_rungs > 1 && !s->replicates) ? std::pow((double)r / (double)(s->n_rungs - 1), pw) : 1.0;
+    INIT_OK(h, cudaMalloc(&s->beta_rung, sizeof(double) * (size_t)s->n_rungs));
+    INIT_OK(h, cudaMemcpyAsync(s->beta_rung, br.data(), sizeof(double) * br.size(), cudaMemcpyHostToDevice, h->stream));
+    INIT_OK(h, cudaStreamSynchronize(h->stream));
   }
-  CUDA_OK(h, cudaMemsetAsync(s->lscale, 0, vec, h->stream));
-  CUDA_OK(h, cudaMemsetAsync(s->acc, 0, sizeof(unsigned long long), h->stream));
-  CUDA_OK(h, cudaMemsetAsync(s->cur, 0, mat, h->stream));
-  CUDA_OK(h, cudaMemsetAsync(s->prop, 0, mat, h->stream));
+  INIT_OK(h, cudaMemsetAsync(s->lscale, 0, vec, h->stream));
+  INIT_OK(h, cudaMemsetAsync(s->acc, 0, sizeof(unsigned long long), h->stream));
+  INIT_OK(h, cudaMemsetAsync(s->cur, 0, mat, h->stream));
+  INIT_OK(h, cudaMemsetAsync(s->prop, 0, mat, h->stream));
   int rc = epi_ensure_workspace(h, h->ws, h->M, n, false);
-  if (rc) return rc;
+  if (rc) { epi_sampler_free(h); return rc; }
   // initial state: theta0 (n x d AoS) or the model file's init with a small Philox jitter
   std::vector<double> host((size_t)d * s->ld, 0.0);
   for (int64_t i = 0; i < n; ++i) {
@@ -480,21 +616,75 @@ extern "C" int epi_sampler_init(epi_handle *h, const epi_sampler_cfg *cfg, const
       host[(size_t)p * s->ld + i] = v;
     }
   }
-  CUDA_OK(h, cudaMemcpyAsync(s->cur, host.data(), mat, cudaMemcpyHostToDevice, h->stream));
-  CUDA_OK(h, cudaStreamSynchronize(h->stream));
+  INIT_OK(h, cudaMemcpyAsync(s->cur, host.data(), mat, cudaMemcpyHostToDevice, h->stream));
+  INIT_OK(h, cudaStreamSynchronize(h->stream));
   // log posterior of the initial state
   rc = epi_launch_eval_ws(h, h->ws, h->M, s->cur, s->ld, n, 0, s->logl, s->logp, s->status_p, nullptr, nullptr, h->stream);
-  if (rc) return rc;
+  if (rc) { epi_sampler_free(h); return rc; }
   s->evals += n;
   if (cfg->kind == EPI_SAMPLER_DEMC) {  // default population: a snapshot of this rank's own chains
-    CUDA_OK(h, cudaMalloc(&s->pop_own, mat));
-    CUDA_OK(h, cudaMemcpyAsync(s->pop_own, s->cur, mat, cudaMemcpyDeviceToDevice, h->stream));
+    INIT_OK(h, cudaMalloc(&s->pop_own, mat));
+    INIT_OK(h, cudaMemcpyAsync(s->pop_own, s->cur, mat, cudaMemcpyDeviceToDevice, h->stream));
     s->pop = s->pop_own; s->pop_ranks = 1; s->pop_per_rank = (int)n; s->pop_ld = s->ld;
-    if (s->cpr < 3) return epi_fail(h, EPI_ERR_ARG, "DE-MC needs at least 3 chains per rung");
   }
   s->iter = 0;
-  rc = launch_ap(h, s, /*do_accept=*/0, nullptr, nullptr);  // proposal of iteration 1
-  if (rc) return rc;
+  if (cfg->kind == EPI_SAMPLER_DRJ) {
+    for (int p = 0; p < d; ++p)
+      if (h->box_max[p] > h->box_min[p]) s->free_params.push_back(p);
+    if (s->free_params.empty()) { epi_sampler_free(h); return epi_fail(h, EPI_ERR_ARG, "no free parameter"); }
+    INIT_OK(h, cudaMalloc(&s->bw, mat));
+    k_fill_const<<<(unsigned)(((int64_t)d * s->ld + 255) / 256), 256, 0, h->stream>>>((int64_t)d * s->ld, 1.0, s->bw);  // drjacoby starts every bandwidth at 1
+    h->launches += 1;
+    rc = launch_drj(h, s, /*sub_acc=*/0, /*p_acc=*/-1, s->free_params[0], /*full_sync=*/1, nullptr, nullptr);
+  } else {
+    rc = launch_ap(h, s, /*do_accept=*/0, nullptr, nullptr);  // proposal of iteration 1
+  }
+  if (rc) { epi_sampler_free(h); return rc; }
+  INIT_OK(h, cudaStreamSynchronize(h->stream));
+  return EPI_OK;
+}
+
+// EPI_SAMPLER_DRJ: n_iter sweeps over the free parameters, d' evaluations each
+static int run_drj(epi_handle *h, SamplerState *s, int32_t n_iter) {
+  const int64_t n = s->cfg.n_chains;
+  const int nf = (int)s->free_params.size();
+  const bool coupled = s->n_rungs > 1 && !s->replicates;
+  for (int it = 0; it < n_iter; ++it) {
+    for (int j = 0; j < nf; ++j) {
+      int rc = epi_launch_eval_ws(h, h->ws, h->M, s->prop, s->ld, n, 0, s->logl_p, s->logp_p, s->status_p, nullptr, nullptr,
+                                  h->stream);
+      if (rc) return rc;
+      s->evals += n;
+      s->sub += 1;
+      if (j + 1 < nf) {
+        if ((rc = launch_drj(h, s, s->sub, s->free_params[j], s->free_params[j + 1], 0, nullptr, nullptr))) return rc;
+        continue;
+      }
+      // end of the sweep: record, couple adjacent rungs, start the next sweep
+      s->iter += 1;
+      double *dout = nullptr, *dlp = nullptr;
+      if (s->draws && s->thin > 0 && (s->iter % s->thin) == 0 && s->kept < s->capacity) {
+        dout = s->draws + (size_t)s->kept * h->M.d * s->ld;
+        dlp = s->draws_lp + (size_t)s->kept * s->ld;
+        s->kept += 1;
+      }
+      if (!coupled) {
+        if ((rc = launch_drj(h, s, s->sub, s->free_params[j], s->free_params[0], 0, dout, dlp))) return rc;
+      } else {
+        if ((rc = launch_drj(h, s, s->sub, s->free_params[j], -1, 0, nullptr, nullptr))) return rc;
+        const int parity = (int)(s->iter & 1);
+        const int64_t pairs = (int64_t)((s->n_rungs - parity) / 2) * s->cpr;
+        if (pairs > 0) {
+          k_pt_swap<<<(unsigned)((pairs + 127) / 128), 128, 0, h->stream>>>(h->M.d, s->cpr, s->n_rungs, s->ld, parity,
+                                                                           s->cfg.seed, s->cfg.chain_id0, s->sub, s->beta_rung,
+                                                                           s->cur, s->logl, s->logp, s->swaps);
+          h->launches += 1;
+        }
+        if ((rc = launch_drj(h, s, s->sub, -1, s->free_params[0], 1, dout, dlp))) return rc;
+      }
+      if (s->adapt) s->adapt_sweeps += 1;
+    }
+  }
   CUDA_OK(h, cudaStreamSynchronize(h->stream));
   return EPI_OK;
 }
@@ -504,6 +694,7 @@ extern "C" int epi_sampler_run(epi_handle *h, int32_t n_iter) {
   SamplerState *s = h->sampler;
   CUDA_OK(h, cudaSetDevice(h->device));
   const int64_t n = s->cfg.n_chains;
+  if (s->cfg.kind == EPI_SAMPLER_DRJ) return run_drj(h, s, n_iter);
   if (s->adapt && s->cpr >= 2 * h->M.d) {
     // burn-in only: re-measure the population covariance that shapes the proposals.  (It is
     // frozen when adaptation is switched off, so the sampling phase is a fixed-kernel Markov chain.)
@@ -563,7 +754,7 @@ extern "C" int epi_sampler_run(epi_handle *h, int32_t n_iter) {
       s->kept += 1;
     }
     if ((rc = launch_ap(h, s, 1, dout, dlp))) return rc;
-    if (s->n_rungs > 1) {
+    if (s->n_rungs > 1 && !s->replicates) {
       const int parity = (int)(s->iter & 1);
       const int64_t pairs = (int64_t)((s->n_rungs - parity) / 2) * s->cpr;
       if (pairs > 0) {
@@ -585,6 +776,7 @@ extern "C" int epi_sampler_set_scale(epi_handle *h, double scale) {
   if (!(scale > 0) || !std::isfinite(scale)) return epi_fail(h, EPI_ERR_ARG, "scale must be positive and finite");
   SamplerState *s = h->sampler;
   CUDA_OK(h, cudaSetDevice(h->device));
+  if (s->cfg.kind == EPI_SAMPLER_DRJ) return epi_fail(h, EPI_ERR_STATE, "the drjacoby-style sampler has per-parameter bandwidths, no global scale");
   s->cfg.scale = scale;
   // the pending proposal (iteration iter + 1) was drawn with the old scale: redraw it (same Philox counters)
   int rc = launch_ap(h, s, 0, nullptr, nullptr);
@@ -726,6 +918,127 @@ extern "C" int epi_sampler_draws_subset(epi_handle *h, int32_t first, int32_t n_
                                  sizeof(double) * (size_t)n_sub, (size_t)s->kept, cudaMemcpyDeviceToHost, h->stream));
   CUDA_OK(h, cudaStreamSynchronize(h->stream));
   return EPI_OK;
+}
+
+extern "C" int epi_sampler_draws_device(epi_handle *h, double **d_draws, double **d_logpost, int32_t *n_kept, int64_t *ld) {
+  if (!h || !h->sampler) return epi_fail(h, EPI_ERR_STATE, "sampler not initialised");
+  SamplerState *s = h->sampler;
+  if (d_draws) *d_draws = s->draws;
+  if (d_logpost) *d_logpost = s->draws_lp;
+  if (n_kept) *n_kept = s->kept;
+  if (ld) *ld = s->ld;
+  return EPI_OK;
+}
+
+extern "C" int epi_sampler_bandwidths(epi_handle *h, double *bw) {
+  if (!h || !h->sampler) return epi_fail(h, EPI_ERR_STATE, "sampler not initialised");
+  SamplerState *s = h->sampler;
+  if (!s->bw || !bw) return epi_fail(h, EPI_ERR_STATE, "no bandwidths (sampler kind is not EPI_SAMPLER_DRJ)");
+  CUDA_OK(h, cudaSetDevice(h->device));
+  const int d = h->M.d;
+  const int64_t n = s->cfg.n_chains;
+  std::vector<double> host((size_t)d * s->ld);
+  CUDA_OK(h, cudaMemcpyAsync(host.data(), s->bw, sizeof(double) * host.size(), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_OK(h, cudaStreamSynchronize(h->stream));
+  for (int64_t i = 0; i < n; ++i)
+    for (int p = 0; p < d; ++p) bw[i * d + p] = host[(size_t)p * s->ld + i];
+  return EPI_OK;
+}
+
+// K2 alone on a synthetic population (see include/epimcmc.h)
+extern "C" int epi_k2_bench(epi_handle *h, int32_t kind, int64_t n_chains, int32_t iters, double *us_per_iter,
+                            double *bytes_per_iter, double *accept_rate) {
+  if (!h || n_chains < 128 || iters < 1) return epi_fail(h, EPI_ERR_ARG, "bad argument");
+  if (kind != EPI_SAMPLER_DEMC && kind != EPI_SAMPLER_DRJ) return epi_fail(h, EPI_ERR_ARG, "epi_k2_bench: DE-MC or DRJ");
+  CUDA_OK(h, cudaSetDevice(h->device));
+  const int d = h->M.d;
+  const int64_t n = n_chains, ld = (n + kTile - 1) / kTile * kTile;
+  const size_t mat = sizeof(double) * (size_t)d * ld, vec = sizeof(double) * (size_t)ld;
+  double *cur = nullptr, *prop = nullptr, *pop = nullptr, *v[5] = {nullptr, nullptr, nullptr, nullptr, nullptr}, *psd = nullptr, *bw = nullptr;
+  int *st = nullptr;
+  unsigned long long *acc = nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  int rc = EPI_OK;
+  auto cleanup = [&]() {
+    cudaFree(cur); cudaFree(prop); cudaFree(pop); for (double *q : v) cudaFree(q); cudaFree(psd); cudaFree(bw); cudaFree(st); cudaFree(acc);
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+  };
+#define K2_OK(call)                                                                                      \
+  do {                                                                                                   \
+    cudaError_t e_ = (call);                                                                             \
+    if (e_ != cudaSuccess) { cleanup(); return epi_fail(h, EPI_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); } \
+  } while (0)
+  K2_OK(cudaMalloc(&cur, mat));
+  K2_OK(cudaMalloc(&prop, mat));
+  if (kind == EPI_SAMPLER_DEMC) K2_OK(cudaMalloc(&pop, mat));
+  if (kind == EPI_SAMPLER_DRJ) K2_OK(cudaMalloc(&bw, mat));
+  for (double *&q : v) K2_OK(cudaMalloc(&q, vec));  // logl, logp, logl', logp', lscale
+  K2_OK(cudaMalloc(&st, sizeof(int) * (size_t)ld));
+  K2_OK(cudaMalloc(&acc, sizeof(unsigned long long)));
+  K2_OK(cudaMalloc(&psd, sizeof(double) * d));
+  K2_OK(cudaMemsetAsync(st, 0, sizeof(int) * (size_t)ld, h->stream));
+  K2_OK(cudaMemsetAsync(acc, 0, sizeof(unsigned long long), h->stream));
+  const unsigned gv = (unsigned)((ld + 255) / 256);
+  k_fill_uniform<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(d, n, ld, 99, h->M.box_min, h->M.box_max, cur);
+  K2_OK(cudaMemcpyAsync(prop, cur, mat, cudaMemcpyDeviceToDevice, h->stream));
+  if (pop) K2_OK(cudaMemcpyAsync(pop, cur, mat, cudaMemcpyDeviceToDevice, h->stream));
+  if (bw) k_fill_const<<<(unsigned)(((int64_t)d * ld + 255) / 256), 256, 0, h->stream>>>((int64_t)d * ld, 0.05, bw);
+  k_fill_const<<<gv, 256, 0, h->stream>>>(ld, 0.0, v[0]);
+  k_fill_const<<<gv, 256, 0, h->stream>>>(ld, 0.0, v[1]);
+  k_fill_accept_pattern<<<gv, 256, 0, h->stream>>>(ld, 7, 0.25, v[2]);  // a quarter of the chains accepts, every iteration
+  k_fill_const<<<gv, 256, 0, h->stream>>>(ld, 0.0, v[3]);
+  k_fill_const<<<gv, 256, 0, h->stream>>>(ld, 0.0, v[4]);
+  {
+    std::vector<double> sd(d);
+    for (int p = 0; p < d; ++p) sd[p] = 0.1 * (h->box_max[p] - h->box_min[p]);
+    K2_OK(cudaMemcpyAsync(psd, sd.data(), sizeof(double) * d, cudaMemcpyHostToDevice, h->stream));
+    K2_OK(cudaStreamSynchronize(h->stream));
+  }
+  std::vector<int> freep;
+  for (int p = 0; p < d; ++p)
+    if (h->box_max[p] > h->box_min[p]) freep.push_back(p);
+  const int nf = (int)freep.size();
+  auto one = [&](int64_t it, int do_accept) {
+    if (kind == EPI_SAMPLER_DEMC)
+      k_accept_propose<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(
+          d, n, ld, EPI_SAMPLER_DEMC, 42, 0, it, do_accept, 1.0, nullptr, (int)n, 1.0, 1e-4, 0, h->M.box_min, h->M.box_max, cur,
+          prop, v[0], v[1], v[2], v[3], st, v[4], 0, 0.0, acc, pop, 1, (int)n, ld, psd, nullptr, nullptr, nullptr);
+    else
+      k_drj_step<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(
+          d, n, ld, 42, 0, it, do_accept ? freep[(it + nf - 1) % nf] : -1, freep[it % nf], do_accept ? 0 : 1, nullptr, (int)n,
+          h->M.box_min, h->M.box_max, cur, prop, v[0], v[1], v[2], v[3], st, bw, 0, 0.0, 0.44, acc, nullptr, nullptr);
+    h->launches += 1;
+  };
+  one(0, 0);
+  for (int it = 1; it <= 3; ++it) one(it, 1);  // warm-up
+  K2_OK(cudaMemsetAsync(acc, 0, sizeof(unsigned long long), h->stream));
+  K2_OK(cudaEventCreate(&e0));
+  K2_OK(cudaEventCreate(&e1));
+  K2_OK(cudaEventRecord(e0, h->stream));
+  for (int it = 0; it < iters; ++it) one(4 + it, 1);
+  K2_OK(cudaEventRecord(e1, h->stream));
+  K2_OK(cudaEventSynchronize(e1));
+  float ms = 0.f;
+  K2_OK(cudaEventElapsedTime(&ms, e0, e1));
+  unsigned long long a = 0;
+  K2_OK(cudaMemcpy(&a, acc, sizeof a, cudaMemcpyDeviceToHost));
+  const double ar = (double)a / ((double)n * iters);
+  if (us_per_iter) *us_per_iter = 1e3 * ms / iters;
+  if (accept_rate) *accept_rate = ar;
+  if (bytes_per_iter) {
+    if (kind == EPI_SAMPLER_DEMC) {
+      // moving coordinates per proposal: every tenth proposal all d; otherwise CR in {0.1, 0.25, 0.5, 1} with equal odds
+      const double dmove = 0.1 * d + 0.9 * 0.25 * (0.1 + 0.25 + 0.5 + 1.0) * d;
+      *bytes_per_iter = (double)n * (8.0 * d /*theta read*/ + 8.0 * d /*proposal written*/ + 16.0 * dmove /*two partners*/ +
+                                     ar * (16.0 * d + 16.0) /*accepted rows copied*/ + 36.0 /*log densities, status*/ + 8.0 /*step size*/);
+    } else {
+      *bytes_per_iter = (double)n * (16.0 /*theta_p, theta'_p*/ + 36.0 + 8.0 /*bandwidth*/ + ar * 24.0 + (1 - ar) * 8.0 + 16.0 /*next coordinate*/ + 8.0);
+    }
+  }
+#undef K2_OK
+  cleanup();
+  return rc;
 }
 
 // test hook: raw Philox4x32-10 words from the device

@@ -79,6 +79,18 @@ class Comm:
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return t.cpu().numpy()
 
+    def allgather_np(self, a):
+        """the same-shaped float64 numpy array of every rank, as a list ordered by rank"""
+        import numpy as np
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        if self.world == 1:
+            return [a]
+        dev = torch.device("cuda", self.local_rank) if self.backend == "nccl" else torch.device("cpu")
+        t = torch.from_numpy(a.reshape(-1)).to(dev)
+        out = torch.empty(self.world * t.numel(), dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(out, t)
+        return [o.reshape(a.shape) for o in out.cpu().numpy().reshape(self.world, -1)]
+
     def barrier(self):
         if self.world > 1:
             if self.backend == "nccl":

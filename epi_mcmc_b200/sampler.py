@@ -18,16 +18,23 @@ import numpy as np
 
 from . import _capi
 
-KINDS = {"rwm": _capi.SAMPLER_RWM, "demc": _capi.SAMPLER_DEMC}
+KINDS = {"rwm": _capi.SAMPLER_RWM, "demc": _capi.SAMPLER_DEMC, "drj": _capi.SAMPLER_DRJ}
 
 
 class Sampler:
     def __init__(self, model, n_chains: int, kind: str = "demc", seed: int = 42, scale: float | None = None,
                  de_eps: float = 1e-4, beta: float = 1.0, chain_id0: int = 0, theta0=None, rungs: int = 1,
-                 GTI_pow: float = 1.0, subspace: bool = True):
+                 GTI_pow: float = 1.0, subspace: bool = True, replicates: bool = False):
         """n_chains is the total on this device; with `rungs` > 1 (parallel tempering, the
         reference driver uses rungs = 20, GTI_pow = 1: fitMCMC-drj.R:53-56) chain i sits on rung
-        i // (n_chains // rungs) and the LAST rung is the cold one."""
+        i // (n_chains // rungs) and the LAST rung is the cold one.
+
+        kind "drj" is drjacoby's own update (one parameter at a time on the logit-reparameterised box,
+        per-parameter Robbins-Monro bandwidths towards 0.44 acceptance during burn-in, Metropolis coupling of
+        adjacent rungs after every sweep): one `run` iteration is one sweep = d evaluations per chain.
+
+        replicates=True turns the `rungs` into independent replicate populations at beta = 1 (no swaps): the
+        spread of their means measures the Monte-Carlo error of the run (`replicate_stats`)."""
         self.model = model
         self._lib = model._lib
         self._h = model._h
@@ -41,7 +48,9 @@ class Sampler:
             # (before that: of 2 % of the box width / sqrt(d))
             scale = 1.0
         cfg = _capi.SamplerCfg(KINDS[kind], self.n_chains, int(chain_id0), int(seed), float(scale), float(de_eps),
-                               float(beta), self.rungs, 0 if subspace else 1, float(GTI_pow))  # flags: EPI_SAMPLER_FLAG_FULLDIM
+                               float(beta), self.rungs,
+                               (0 if subspace else _capi.SAMPLER_FLAG_FULLDIM) | (_capi.SAMPLER_FLAG_REPLICATES if replicates else 0),
+                               float(GTI_pow))
         # subspace: DE-MC proposals move a random subset of the coordinates (DREAM-style crossover)
         t0 = None
         if theta0 is not None:
@@ -50,6 +59,7 @@ class Sampler:
         _capi.check(self._lib.epi_sampler_init(self._h, C.byref(cfg), _capi.as_dp(t0) if t0 is not None else None),
                     self._h)
         self.scale = float(scale)
+        self.replicates = bool(replicates)
         self._tune_acc, self._tune_it, self._tune_k = 0, 0, 0
 
     def run(self, n_iter: int):
@@ -109,6 +119,9 @@ class Sampler:
         it, acc, ev = C.c_int64(), C.c_int64(), C.c_int64()
         _capi.check(self._lib.epi_sampler_stats(self._h, C.byref(it), C.byref(acc), C.byref(ev)), self._h)
         n = max(1, it.value * self.n_chains)
+        if self.kind == "drj":  # one iteration = one sweep over the free parameters, each its own accept / reject
+            dp = self.model.df_params
+            n *= max(1, int((np.asarray(dp["max"]) > np.asarray(dp["min"])).sum()))
         return dict(iterations=it.value, accepted=acc.value, evals=ev.value, accept_rate=acc.value / n)
 
     def pt_stats(self) -> dict:
@@ -134,6 +147,80 @@ class Sampler:
             _capi.check(self._lib.epi_sampler_draws_subset(self._h, int(first), int(n_sub), _capi.as_dp(out),
                                                            _capi.as_dp(lp), C.byref(kept)), self._h)
         return np.ascontiguousarray(out.transpose(0, 2, 1)), lp
+
+    def bandwidths(self):
+        """kind "drj": the current proposal bandwidths (n_chains, d) on the phi scale"""
+        bw = np.empty((self.n_chains, self.model.d))
+        _capi.check(self._lib.epi_sampler_bandwidths(self._h, _capi.as_dp(bw)), self._h)
+        return bw
+
+    def draws_device(self):
+        """the recorded draws where they lie: a torch view [kept, d, ld] on the device (no copy) and logpost [kept, ld]"""
+        import torch
+        dp, lp = C.c_void_p(), C.c_void_p()
+        kept, ld = C.c_int32(), C.c_int64()
+        _capi.check(self._lib.epi_sampler_draws_device(self._h, C.byref(dp), C.byref(lp), C.byref(kept), C.byref(ld)), self._h)
+        if not kept.value:
+            return None, None
+        from .dist import _DevPtr
+        d, k, L = self.model.d, kept.value, ld.value
+        dev = f"cuda:{self.model.device}"
+        dr = torch.as_tensor(_DevPtr(dp.value, k * d * L), device=dev).view(k, d, L)
+        lg = torch.as_tensor(_DevPtr(lp.value, k * L), device=dev).view(k, L)
+        return dr, lg
+
+    def replicate_stats(self, params=None, comm=None, last=None):
+        """Monte-Carlo error of the recorded phase from INDEPENDENT replicate populations (replicates=True): the
+        chains of one replicate share partners, so they are not independent draws, but replicates never interact —
+        the variance of the replicate means (each the mean over its chains and recorded iterations) IS the variance
+        of that estimator.  ESS of the whole run for a posterior mean = B * var_posterior / var(replicate means),
+        B replicates (all ranks together when `comm` is given).  Also split-R-hat over one chain per replicate.
+        `last`: use only the first `last` recorded draws (ESS of half the window, to check stationarity).
+        Returns dict(ess[p], rhat[p], post_sd[p], n_replicates); everything is reduced on the device."""
+        import torch
+        dr, _ = self.draws_device()
+        if last is not None:
+            dr = dr[:int(last)]
+        n, cpr, B = self.n_chains, self.chains_per_rung, self.rungs
+        idx = torch.as_tensor(list(range(self.model.d)) if params is None else list(params), device=dr.device)
+        x = dr[:, idx, :n].reshape(dr.shape[0], len(idx), B, cpr)            # [k, p, B, cpr]
+        k = x.shape[0]
+        rep_mean = x.mean(dim=(0, 3))                                        # [p, B]
+        tot_mean = rep_mean.mean(dim=1)                                      # local
+        ss_tot = ((x - tot_mean[None, :, None, None]) ** 2).sum(dim=(0, 2, 3))
+        cnt = float(k * B * cpr)
+        # one chain per replicate for split R-hat: first chain of each replicate, halves of the recorded phase
+        c = x[:, :, :, 0]                                                    # [k, p, B]
+        h = k // 2
+        halves = torch.stack([c[:h], c[h:2 * h]], dim=0)                     # [2, h, p, B]
+        hm = halves.mean(dim=1)                                              # [2, p, B]
+        hv = halves.var(dim=1, unbiased=True)                                # [2, p, B]
+        rep_mean_np, hm_np, hv_np = rep_mean.cpu().numpy(), hm.cpu().numpy(), hv.cpu().numpy()
+        sums = np.concatenate([[cnt], (tot_mean * cnt).cpu().numpy(), ss_tot.cpu().numpy()])
+        if comm is not None and comm.world > 1:
+            rep_mean_np = np.concatenate(comm.allgather_np(rep_mean_np), axis=1)
+            hm_np = np.concatenate(comm.allgather_np(hm_np), axis=2)
+            hv_np = np.concatenate(comm.allgather_np(hv_np), axis=2)
+            # pooled variance across ranks: combine (count, sum, sum of squares about the LOCAL mean)
+            parts = comm.allgather_np(sums)
+            P = len(idx)
+            cnts = np.array([q[0] for q in parts]); s1 = np.array([q[1:1 + P] for q in parts]); s2 = np.array([q[1 + P:] for q in parts])
+            gmean = s1.sum(0) / cnts.sum()
+            lmean = s1 / cnts[:, None]
+            ss = (s2 + cnts[:, None] * (lmean - gmean) ** 2).sum(0)
+            var_post = ss / (cnts.sum() - 1)
+        else:
+            var_post = sums[1 + len(idx):] / (cnt - 1)
+        Bt = rep_mean_np.shape[1]
+        var_rep = rep_mean_np.var(axis=1, ddof=1)
+        ess = Bt * var_post / np.maximum(var_rep, 1e-300)
+        # split R-hat (Gelman et al. 2013): chains = 2 * Bt half-chains of length h
+        m_ = np.concatenate([hm_np[0], hm_np[1]], axis=1)   # [p, 2 Bt]
+        v_ = np.concatenate([hv_np[0], hv_np[1]], axis=1)
+        W = v_.mean(axis=1)
+        Bv = h * m_.var(axis=1, ddof=1)
+        rhat = np.sqrt(((h - 1) / h * W + Bv / h) / np.maximum(W, 1e-300))
+        return dict(ess=ess, rhat=rhat, post_sd=np.sqrt(var_post), n_replicates=Bt, kept=k)
 
     def draws(self):
         """(draws[k, chain, d], logpost[k, chain]) of the recorded thinned states"""

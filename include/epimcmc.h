@@ -96,6 +96,17 @@ extern "C" {
 /* epi_sampler_cfg.reserved carries flags.  By default a DE-MC proposal moves a random subset of the coordinates
  * (DREAM-style crossover, CR drawn from {0.1, 0.25, 0.5, 1}); this flag restores full-dimensional moves.        */
 #define EPI_SAMPLER_FLAG_FULLDIM 1
+/* drjacoby's own update (the sampler R/MCMC/fitMCMC-drj.R:48-57 drives): one parameter at a time, a Gaussian step
+ * of per-chain, per-parameter bandwidth on the logit-reparameterised box phi = log((theta - min) / (max - theta))
+ * with the Jacobian term in the acceptance ratio, the bandwidths steered by Robbins-Monro towards a target
+ * acceptance (0.44) while adaptation is on, n_rungs temperature rungs with beta_r = (r / (R-1))^GTI_pow and
+ * Metropolis coupling of adjacent rungs after every sweep.  One epi_sampler_run iteration is one SWEEP over the
+ * d parameters (d evaluations per chain), as one drjacoby iteration is; draws are recorded per sweep.           */
+#define EPI_SAMPLER_DRJ 2
+/* The n_rungs "rungs" are independent replicate populations, all at beta = 1 and never swapped: chains of one
+ * replicate draw their DE-MC partners from that replicate only.  The spread of the replicate means is an honest
+ * estimate of the Monte-Carlo error of the whole run (bench.py's ESS figure).                                   */
+#define EPI_SAMPLER_FLAG_REPLICATES 2
 
 typedef struct epi_handle epi_handle;
 
@@ -304,6 +315,11 @@ int epi_sampler_draws(epi_handle *h, double *draws, double *logpost, int32_t *n_
 /* the recorded draws of chains [first, first + n_sub) only, in the device layout:
  * draws HOST n_kept x d x n_sub, logpost HOST n_kept x n_sub (either may be NULL) */
 int epi_sampler_draws_subset(epi_handle *h, int32_t first, int32_t n_sub, double *draws, double *logpost, int32_t *n_kept);
+/* the recorded draws where they lie: DEVICE pointers to [n_kept][d][ld] and [n_kept][ld] (valid until the next
+ * epi_sampler_record / epi_sampler_init), for reductions over the whole population without a host copy         */
+int epi_sampler_draws_device(epi_handle *h, double **d_draws, double **d_logpost, int32_t *n_kept, int64_t *ld);
+/* EPI_SAMPLER_DRJ: the current proposal bandwidths (HOST, n_chains x d, phi scale) */
+int epi_sampler_bandwidths(epi_handle *h, double *bw);
 
 /* ---- measurement helpers --------------------------------------------------- */
 /* DFMA-chain microbenchmark on the handle's device: measured FP64 TFLOP/s, the
@@ -315,6 +331,16 @@ int epi_fp64_peak(epi_handle *h, double *tflops);
  * ODE, [3]=score.                                                             */
 int epi_set_timing(epi_handle *h, int enable);
 int epi_last_kernel_ms(epi_handle *h, float ms[4]);
+/* The fused accept/propose kernel (K2) alone: `iters` launches on a synthetic population of n_chains chains
+ * (uniform states in the box, log densities set so that a fixed quarter of the chains accepts every proposal, own-population
+ * snapshot for DE-MC), timed with CUDA events on the handle's stream.  No evaluation kernels run and no K1
+ * workspace is allocated, so n_chains may be far beyond what a sampler would hold (the HBM roofline of K2 needs
+ * a population outside L2: 2^22 chains).  us_per_iter: mean device time of one launch; bytes_per_iter: the
+ * ALGORITHMIC bytes of one launch (each chain: theta read and proposal written once, the partner values of the
+ * moving coordinates, the accepted rows copied, 36 B of log densities and status) at the acceptance rate the
+ * launches actually had (accept_rate) and the expected number of moving coordinates of the crossover scheme.   */
+int epi_k2_bench(epi_handle *h, int32_t kind, int64_t n_chains, int32_t iters, double *us_per_iter, double *bytes_per_iter,
+                 double *accept_rate);
 /* number of kernel launches issued by this handle since creation             */
 int64_t epi_launch_count(const epi_handle *h);
 /* diagnostic: how many chains of the most recent evaluation batch (epi_eval* / sampler) had their ODE passes

@@ -30,9 +30,11 @@ def reflect(y, mn, mx):
     return mn + z
 
 
-def run(oracle, ds, m, n_chains, burnin, samples, thin, seed, n_threads=16, cov0=None, x0=None, budget_s=None):
+def run(oracle, ds, m, n_chains, burnin, samples, thin, seed, n_threads=16, cov0=None, x0=None, budget_s=None, beta=1.0):
     """Returns (draws[k, chain, d], info).  cov0: proposal covariance to start from (e.g. the posterior covariance
-    of a previous run; None: 2 % of the box).  budget_s: stop the SAMPLING phase after that many seconds."""
+    of a previous run; None: 2 % of the box).  budget_s: stop the SAMPLING phase after that many seconds.
+    beta: likelihood tempering exponent (0: the prior, restricted to where the likelihood is finite — what the
+    beta = 0 rung of the GPU sampler targets)."""
     rng = np.random.default_rng(seed)
     mn, mx, init = (np.asarray(v) for v in oracle.df_params(ds["flavour"], ds, ds["period"]))
     d = len(init)
@@ -40,8 +42,8 @@ def run(oracle, ds, m, n_chains, burnin, samples, thin, seed, n_threads=16, cov0
 
     def post(th):
         r = oracle.evaluate(ds["flavour"], ds, th, ds["period"], m, n_threads=n_threads)
-        lp = r["logl"] + r["logp"]
-        return np.where(np.isfinite(lp), lp, -np.inf)
+        lp = (beta * r["logl"] if beta != 0 else 0.0) + r["logp"]
+        return np.where(np.isfinite(lp) & np.isfinite(r["logl"]) & ((r["status"] & (2 | 16)) == 0), lp, -np.inf)
 
     lp = post(x)
     evals = n_chains

@@ -1,0 +1,3 @@
+set -x
+python -m pytest tests/test_gpu_sampler.py -m gpu -q -s -k "age_model_stat" 2>&1 | grep -v "^$" | tail -12
+bash scripts/_r2_ncu_all.sh

@@ -1,6 +1,5 @@
-"""The bench line contract, checked on the committed lines of the final kernels (profiles/r1_bench_*_v15.json were
-written by `python bench.py` / `bench.py --impl reference` / torchrun on the B200 box) and on bench.py's own
-arithmetic helpers.  CPU only."""
+"""The bench line contract, checked on committed lines (profiles/r2_bench_*.json were written by `python bench.py` /
+`bench.py --impl reference` / torchrun on the B200 box) and on bench.py's own arithmetic helpers.  CPU only."""
 import json
 import os
 
@@ -21,48 +20,73 @@ BASE_KEYS = ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_ste
              "vs_baseline", "dtype", "data", "config", "e2e")
 
 
-@pytest.mark.parametrize("name,n_gpus", [("r1_bench_n1_v15.json", 1), ("r1_bench_n8_v15.json", 8)])
+OWN_LINES = [("r2_bench_n1_b.json", 1)]
+
+
+@pytest.mark.parametrize("name,n_gpus", OWN_LINES)
 def test_own_arm_line(name, n_gpus):
     j = _line(name)
-    for k in BASE_KEYS + ("clocks", "gpu_launches", "roofline"):
+    for k in BASE_KEYS + ("clocks", "gpu_launches", "roofline", "sustained", "secondary"):
         assert k in j, k
     assert j["metric"] == "log_posterior_evals_per_s" and j["unit"] == "evals/s" and j["higher_is_better"] is True
-    assert j["n_gpus"] == n_gpus and j["scaling"] == "weak" and j["dtype"] == "f64" and j["data"] == "synthetic"
+    assert j["n_gpus"] == n_gpus and j["scaling"] == "strong" and j["dtype"] == "f64" and j["data"] == "synthetic"
     assert j["vs_baseline"] is None                       # BASELINE.md publishes no number for this metric
-    assert "workload" in j["config"] and "model" not in j["config"]
+    c = j["config"]
+    assert "workload" in c and "model" not in c
+    # strong scaling: the configuration's 65,536 chains are sharded, value counts every one of them once per step
+    assert c["chains_total"] == 65536 and c["chains_per_gpu"] * n_gpus == c["chains_total"]
     assert j["warmup"] >= 3 and j["gpu_launches"] >= 4 * j["steps"]
-    # value and ms_per_step describe the same timed region
-    chains = j["config"]["chains_per_gpu"] * n_gpus
-    assert j["value"] == pytest.approx(chains / (j["ms_per_step"] * 1e-3), rel=1e-6)
+    assert j["value"] == pytest.approx(c["chains_total"] / (j["ms_per_step"] * 1e-3), rel=1e-6)
     e = j["e2e"]
-    assert e["unit"] == j["unit"] and e["h2d_bytes_per_step"] == j["config"]["chains_per_gpu"] * j["config"]["params"] * 8
-    assert e["d2h_bytes_per_step"] == j["config"]["chains_per_gpu"] * 20
+    assert e["unit"] == j["unit"] and e["h2d_bytes_per_step"] == c["chains_per_gpu"] * c["params"] * 8
+    assert e["d2h_bytes_per_step"] == c["chains_per_gpu"] * 20
     assert 0 < e["value"] < j["value"]                    # copies inside the timed region cost something
     r = j["roofline"]
     for k in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
         assert k in r, k
     assert r["frac"] == pytest.approx(r["achieved"] / r["peak"], rel=1e-9) and 0 < r["frac"] < 1
-    c = j["clocks"]
-    assert c["sm_mhz"] > 0.9 * c["sm_max_mhz"]
-    assert not set(c["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    # no launch is ever given a roofline fraction above 1 (the survey-formula figures are labelled as such)
+    for k, v in j["roofline_all"].items():
+        assert v["frac"] is None or 0 < v["frac"] < 1, (k, v["frac"])
+    s = j["sustained"]
+    assert s["steps"] * s["ms_per_step"] >= 999.0 and s["value"] == pytest.approx(j["value"], rel=0.05)
+    cl = j["clocks"]
+    assert cl["sm_mhz"] > 0.9 * cl["sm_max_mhz"]
+    assert not set(cl["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
     if n_gpus == 1:
         b = j["cpu_baseline"]
-        for k in ("value", "unit", "cores", "kind", "sample"):
+        for k in ("value", "unit", "cores", "kind", "sample", "r_probe", "ess_per_s_median"):
             assert k in b, k
-        assert b["kind"] in ("port", "reference") and b["cores"] >= 1
+        assert b["kind"] in ("port", "reference", "r") and b["cores"] >= 1
+    else:
+        assert j["weak"]["chains_per_gpu"] == 65536 and j["weak"]["value"] > j["value"]
     # the per-kernel event times add up to the step (launch gaps and the two idle fallback launches are the rest)
     assert sum(j["kernels"].values()) == pytest.approx(j["ms_per_step"], rel=0.03)
+    # every other BASELINE config is observed by the same run
+    got = {(x["workload"], x["substeps"]) for x in j["secondary"]}
+    assert {("S120", 4), ("S365", 4), ("NE120", 4), ("A365", 4), ("A300", 1), ("I290", 4)} <= got
+    for x in j["secondary"]:
+        assert x["value"] == pytest.approx(x["chains_total"] / (x["ms_per_step"] * 1e-3), rel=1e-6)
+    if "sampler" in j:
+        sm = j["sampler"]
+        assert 0 < sm["evals_per_s"] <= j["value"] * 1.05 and sm["replicate_populations"] >= 8
+        k2 = {x["chains"]: x for x in sm["k2"]}
+        assert set(k2) == {65536, 1 << 22}
+        for x in k2.values():
+            assert x["achieved_GBs"] == pytest.approx(x["algorithmic_bytes"] / (x["us_per_iter"] * 1e-6) / 1e9, rel=1e-9)
+            assert 0 < x["frac"] < 1
 
 
 def test_reference_arm_line():
-    j = _line("r1_bench_ref_v15.json")
+    j = _line("r2_bench_ref_b.json")
     for k in BASE_KEYS + ("impl", "cpu_baseline"):
         assert k in j, k
     assert j["impl"] == "reference" and j["metric"] == "log_posterior_evals_per_s"
-    own = _line("r1_bench_n1_v15.json")
-    assert j["config"]["workload"] == own["config"]["workload"] and j["unit"] == own["unit"]
+    own = _line("r2_bench_n1_b.json")
+    assert j["config"] == own["config"] and j["unit"] == own["unit"] and j["scaling"] == own["scaling"]
     assert j["e2e"]["value"] == j["value"] and j["e2e"]["h2d_bytes_per_step"] == 0 and j["e2e"]["d2h_bytes_per_step"] == 0
     assert j["cpu_baseline"]["value"] == j["value"] and j["cpu_baseline"]["cores"] >= 1
+    assert "r_probe" in j["cpu_baseline"] and j["cpu_baseline"]["kind"] == ("r" if j["cpu_baseline"]["r_probe"]["usable"] else "port")
 
 
 def test_f_alg_matches_the_survey_formula():
