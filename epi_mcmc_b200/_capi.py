@@ -14,12 +14,13 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "csrc", "libepimcmc.so")
 
-FLAVOUR_SIMPLE, FLAVOUR_NE, FLAVOUR_AGE2Q, FLAVOUR_AGE2I = 0, 1, 2, 3
-FLAVOURS = {"simple": FLAVOUR_SIMPLE, "ne": FLAVOUR_NE, "age2q": FLAVOUR_AGE2Q, "age2i": FLAVOUR_AGE2I}
-AGE_FLAVOURS = (FLAVOUR_AGE2Q, FLAVOUR_AGE2I)
-N_PARAMS = {FLAVOUR_SIMPLE: 8, FLAVOUR_NE: 9, FLAVOUR_AGE2Q: 45, FLAVOUR_AGE2I: 36}
-N_SERIES = {FLAVOUR_SIMPLE: 3, FLAVOUR_NE: 3, FLAVOUR_AGE2Q: 8, FLAVOUR_AGE2I: 8}
-MAX_PARAMS = 48
+FLAVOUR_SIMPLE, FLAVOUR_NE, FLAVOUR_AGE2Q, FLAVOUR_AGE2I, FLAVOUR_AGE2X = 0, 1, 2, 3, 4
+FLAVOURS = {"simple": FLAVOUR_SIMPLE, "ne": FLAVOUR_NE, "age2q": FLAVOUR_AGE2Q, "age2i": FLAVOUR_AGE2I,
+            "age2x": FLAVOUR_AGE2X}
+AGE_FLAVOURS = (FLAVOUR_AGE2Q, FLAVOUR_AGE2I, FLAVOUR_AGE2X)
+N_PARAMS = {FLAVOUR_SIMPLE: 8, FLAVOUR_NE: 9, FLAVOUR_AGE2Q: 45, FLAVOUR_AGE2I: 36, FLAVOUR_AGE2X: 52}
+N_SERIES = {FLAVOUR_SIMPLE: 3, FLAVOUR_NE: 3, FLAVOUR_AGE2Q: 8, FLAVOUR_AGE2I: 8, FLAVOUR_AGE2X: 8}
+MAX_PARAMS = 56
 INVALID_DATA_OFFSET = 10000
 
 ST_INVALID_OFFSET, ST_NA, ST_OUT_OF_BOX, ST_UNSUPPORTED = 1, 2, 8, 16
@@ -57,6 +58,8 @@ class Data(C.Structure):
         ("case_nbinom_size1", C.c_double), ("case_nbinom_sizey2", C.c_double),
         ("case_nbinom_sizeo2", C.c_double), ("hosp_nbinom_size1", C.c_double),
         ("hosp_nbinom_size2", C.c_double), ("hosp_last7", C.c_double),
+        ("d9", C.c_int32), ("d10", C.c_int32), ("d12", C.c_int32), ("duncertain", C.c_int32),
+        ("d_symp_cases", C.c_int32), ("d_all_cases", C.c_int32), ("symp_cases_factor", C.c_double),
     ]
 
 

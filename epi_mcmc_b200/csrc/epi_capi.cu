@@ -44,7 +44,8 @@ int epi_fail(epi_handle *h, int rc, const char *fmt, ...) {
   } while (0)
 
 static double age_gamma() { return 1.0 / ((4.7 - (3.0 + 1.0)) * 2.0); }  // model-age-groups2q.R:8-15
-static bool is_age(int flavour) { return flavour == EPI_FLAVOUR_AGE2Q || flavour == EPI_FLAVOUR_AGE2I; }
+static bool is_age(int flavour) { return flavour == EPI_FLAVOUR_AGE2Q || flavour == EPI_FLAVOUR_AGE2I || flavour == EPI_FLAVOUR_AGE2X; }
+static bool fixed_pass1(int flavour) { return flavour == EPI_FLAVOUR_AGE2Q || flavour == EPI_FLAVOUR_AGE2X; }  // period1 = 60
 static int pad_rows(int flavour) { return flavour == EPI_FLAVOUR_AGE2I ? EPI_MAX_PADDING : kPadMax; }  // Traits<FL>::kPad
 
 // ------------------------------------------------------------- metadata tables
@@ -59,6 +60,12 @@ static const char *kAge2iNames[36] = {  // fit.paramnames, model-age-groups2i.R:
     "y.CR", "y.CL", "y.HR", "y.HL", "y.DL", "o.CR", "o.CL", "o.HR", "o.HL", "o.DL", "t0_morts", "t0o",
     "CRsd", "HLsd", "DLsd", "t3o", "t4o", "betay4", "betao4", "betayo4", "t6o", "betay6", "betao6", "betayo6",
     "fy7", "fo7", "fyo7"};
+static const char *kAge2xNames[52] = {  // fit.paramnames, model-age-groups2x.R:683-698
+    "betay0", "betao0", "betayo0", "betay1", "betao1", "betayo1", "betay2", "betao2", "betayo2",
+    "y.CR", "y.HR", "y.HL", "y.DL", "o.CR", "o.HR", "o.HL", "o.DL", "t0_morts", "t0o", "HLsd", "DLsd",
+    "fyifr", "fyhr", "t3o", "betay3", "betao3", "betayo3", "t4o", "betay4", "betao4", "betayo4",
+    "betay5", "betao5", "betayo5", "t6o", "betay6", "betao6", "betayo6", "t7o", "betay7", "betao7", "betayo7",
+    "betay9", "betao9", "betayo9", "ifrred", "y.CL", "o.CL", "t10o", "betay11", "betao11", "betayo11"};
 static const char *kSimpleNames[9] = {  // model-simple-ode-drj-cmp.R:259-260 (+ Nef, README.md:91-93)
     "R0", "Rt", "Tinf0", "Tinft", "logHR", "HL", "DL", "lockdownmort", "Nef"};
 
@@ -83,6 +90,25 @@ static void df_params_host(int flavour, const epi_data &D, double *mn, double *m
                             50, 3 * g, 3 * g, 0.5 * g, 50, 3 * g, 3 * g, 0.5 * g,
                             1.1, 1.1, 1.1, 0.7, 14, 14};
     for (int i = 0; i < 45; ++i) { mn[i] = mn_[i]; mx[i] = mx_[i]; init[i] = i_[i]; }
+  } else if (flavour == EPI_FLAVOUR_AGE2X) {  // model-age-groups2x.R:705-751
+    const double g = age_gamma();
+    const double i_[52] = {3.1, 0.52, 0.50, 1.5, 0.50, 0.44, 0.8, 0.35, 0.09, 550, 0.75, 14, 21, 11, 1.5, 14, 21,
+                           14, -8, 5.2, 5.8, 0.49, 0.30, 92, 1.0, 0.18, 0.02, 29, 1.4, 0.4, 0.04, 0.96, 0.27, 0.007,
+                           28, 1.2, 0.9, 0.02, 32, 2.0, 0.6, 0.10, 1.3, 0.3, 0.05, 0.34, 6, 11, 245, 1.9, 0.3, 0.04};
+    const double mn_[52] = {2 * g, 0.5 * g, 0.5 * g, 1 * g, 0.5 * g, 0.5 * g, 0.1 * g, 0.1 * g, 0.01 * g,
+                            500, 0.5, 9, 14, 3, 0.5, 9, 14, 0, -20, 2, 2, 0.05, 0.05,
+                            60, 0.5 * g, 0.01 * g, 0.002 * g, 10, 0.5 * g, 0.01 * g, 0.002 * g,
+                            0.1 * g, 0.01 * g, 0.002 * g, 10, 0.2 * g, 0.01 * g, 0.002 * g,
+                            10, 0.2 * g, 0.01 * g, 0.002 * g, 0.2 * g, 0.01 * g, 0.002 * g, 0.1, 4, 4,
+                            (double)D.d10 - 10, 0.2 * g, 0.01 * g, 0.002 * g};
+    const double tdl = D.total_deaths_at_lockdown * 10, dml = D.dmort_last / 10;
+    const double mx_[52] = {8 * g, 5 * g, 5 * g, 5 * g, 3 * g, 3 * g, 2 * g, 2 * g, 2 * g,
+                            5000, 2, 18, 25, 100, 6, 18, 25, dml > tdl ? dml : tdl, 10, 9, 9, 1, 1,
+                            100, 3 * g, 1 * g, 0.5 * g, 50, 3 * g, 1 * g, 0.5 * g,
+                            2 * g, 1 * g, 0.5 * g, 50, 4 * g, 3 * g, 0.5 * g,
+                            50, 4 * g, 3 * g, 0.5 * g, 3 * g, 3 * g, 0.5 * g, 0.7, 14, 17,
+                            (double)D.duncertain - 2, 3 * g, 3 * g, 0.5 * g};
+    for (int i = 0; i < 52; ++i) { mn[i] = mn_[i]; mx[i] = mx_[i]; init[i] = i_[i]; }
   } else if (flavour == EPI_FLAVOUR_AGE2I) {  // model-age-groups2i.R:552-587
     const double g = age_gamma();
     const double lo = D.lockdown_offset, ltp = D.lockdown_transition_period;
@@ -227,6 +253,34 @@ static std::vector<PriorTerm> build_prior(int flavour, const epi_data &D) {
     p.push_back(pt_lnorm(42, std::log(0.35), std::log(1.3)));
     p.push_back(pt_lnorm(10, 0, lSD));
     p.push_back(pt_lnorm(14, 0, lSD));
+  } else if (flavour == EPI_FLAVOUR_AGE2X) {  // calclogp, model-age-groups2x.R:485-543 (0-based theta indices)
+    const double lo_ltp = D.lockdown_offset + D.lockdown_transition_period;
+    const double SD = std::log(2.0), lSD = std::log(1.3), llSD = std::log(1.2);
+    p.push_back(pt_norm(18, 0, 10));
+    p.push_back(pt_sum(23, -1, lo_ltp, 1, 0, D.d3, 10));
+    p.push_back(pt_sum(23, 27, lo_ltp, 1, 1, D.d4, 10));
+    p.push_back(pt_sum(34, -1, D.d5, 1, 0, D.d6, 5));
+    p.push_back(pt_sum(34, 38, D.d5, 1, 1, (double)D.d7 - D.lockdown_offset, 2));
+    p.push_back(pt_norm(48, D.d10, 3));
+    // beta triples (0-based first index): 0: 0, 1: 3, 2: 6, 3: 24, 4: 28, 5: 31, 6: 35, 7: 39, 9: 42, 11: 49
+    for (int c = 0; c < 3; ++c) p.push_back(pt_lratio(0 + c, 3 + c, llSD));
+    const int pr[5][2] = {{3, 6}, {6, 24}, {24, 28}, {31, 35}, {35, 39}};
+    for (auto &r : pr)
+      for (int c = 0; c < 3; ++c) p.push_back(pt_lratio(r[0] + c, r[1] + c, SD));
+    for (int c = 0; c < 3; ++c) p.push_back(PriorTerm{39 + c, 42 + c, 2, 1, 0, 0, 0, std::log(1.3), lSD});
+    for (int c = 0; c < 3; ++c) p.push_back(pt_lratio(42 + c, 49 + c, lSD));
+    p.push_back(pt_norm(19, 4, 1));
+    p.push_back(pt_norm(20, 5, 1));
+    p.push_back(pt_norm(46, 7, 3));
+    p.push_back(pt_norm(47, 7, 3));
+    p.push_back(pt_norm(11, 13, 1));
+    p.push_back(pt_norm(15, 13, 1));
+    p.push_back(pt_norm(12, 21, 0.5));
+    p.push_back(pt_norm(16, 21, 0.5));
+    p.push_back(pt_lnorm(21, std::log(0.6), std::log(1.5)));
+    p.push_back(pt_lnorm(45, std::log(0.35), std::log(1.3)));
+    p.push_back(pt_lnorm(10, 0, lSD));
+    p.push_back(pt_lnorm(14, 0, lSD));
   } else if (flavour == EPI_FLAVOUR_AGE2I) {  // calclogp, model-age-groups2i.R:410-435 (0-based theta indices)
     const double g = age_gamma(), lo_ltp = D.lockdown_offset + D.lockdown_transition_period;
     p.push_back(pt_norm(20, 0, 10));
@@ -313,6 +367,63 @@ static int fill_model(epi_handle *h, const epi_model_desc &desc, const epi_data 
     // deaths, :584-590
     calls.push_back({3, 4, D.y_dmorti, nm, 1, nm, 0, nm - 1, sz + 6, 1});
     calls.push_back({4, 5, D.o_dmorti, nm, 1, nm, 0, nm - 1, h->size_vec.data(), nm});
+    M.d3 = D.d3; M.d4 = D.d4; M.d5d = D.d5; M.d6 = D.d6; M.d7 = D.d7;
+    M.lo_ltp = D.lockdown_offset + D.lockdown_transition_period;
+  } else if (desc.flavour == EPI_FLAVOUR_AGE2X) {
+    M.d = 52;
+    M.P1 = 60;  // period1, model-age-groups2x.R:183
+    if (desc.period < 60) return epi_fail(h, EPI_ERR_ARG, "age-2x needs period >= 60 (pass 1 integrates 60 days)");
+    if (!(D.y_N > 1 && D.o_N > 0)) return epi_fail(h, EPI_ERR_ARG, "y_N / o_N missing");
+    if (D.n_rate < 1 || !D.y_ifr || !D.o_ifr || !D.y_hr || !D.o_hr || !D.g || !D.gtrimp)
+      return epi_fail(h, EPI_ERR_ARG, "rate vectors y_ifr/o_ifr/y_hr/o_hr/g/gtrimp missing");
+    if (!D.y_dcasei || !D.o_dcasei || !D.dhospi || !D.y_dmorti || !D.o_dmorti || !D.o_wdmorti)
+      return epi_fail(h, EPI_ERR_ARG, "observed series missing");
+    if (!(D.symp_cases_factor > 0) || D.d_symp_cases < 1 || D.d_all_cases < 1 || D.d9 < 1 || D.d10 < 1 || D.d12 < 1 || D.duncertain < 1)
+      return epi_fail(h, EPI_ERR_ARG, "age-2x globals missing (d9, d10, d12, duncertain, d_symp_cases, d_all_cases, symp_cases_factor)");
+    M.Ny = D.y_N; M.No = D.o_N; M.N = D.y_N + D.o_N;
+    M.a1 = 1.0 / 3.0; M.a2 = 1.0 / 1.0; M.gamma = age_gamma();
+    M.eta = 1.0 / (0.75 * 356);  // model-age-groups2x.R:19 (sic)
+    M.ifr_y1 = D.y_ifr[0]; M.ifr_o1 = D.o_ifr[0];
+    M.d5 = D.d5; M.d8 = D.d8; M.d9 = D.d9; M.d12 = D.d12;
+    M.d_symp = D.d_symp_cases; M.d_all = D.d_all_cases; M.symp_factor = D.symp_cases_factor;
+    M.n_rate = D.n_rate;
+    M.d_hosp_o1 = D.d_hosp_o1; M.d_hosp_o2 = D.d_hosp_o2;
+    int rc;
+    if ((rc = upload(h, D.y_ifr, D.n_rate, &M.y_ifr))) return rc;
+    if ((rc = upload(h, D.o_ifr, D.n_rate, &M.o_ifr))) return rc;
+    if ((rc = upload(h, D.y_hr, D.n_rate, &M.y_hr))) return rc;
+    if ((rc = upload(h, D.o_hr, D.n_rate, &M.o_hr))) return rc;
+    if ((rc = upload(h, D.g, D.n_rate, &M.g))) return rc;
+    if ((rc = upload(h, D.gtrimp, D.n_rate, &M.gtrimp))) return rc;
+    M.n_series = 5;
+    const int nc = D.n_dcasei, nh = D.n_dhospi, nhh = D.n_dhosp, nm = D.n_dmorti;
+    const int r = D.d_reliable_cases, rh = D.d_reliable_hosp;
+    if (D.d_hosp_o1 < 0 || D.d_hosp_o2 < D.d_hosp_o1 || D.d_hosp_o2 >= nh)
+      return epi_fail(h, EPI_ERR_ARG, "d_hosp_o1/o2 outside the hospital series");
+    n_obs[0] = nc; n_obs[1] = nc; n_obs[2] = nh; n_obs[3] = nm; n_obs[4] = nm;
+    const int term_of[5] = {0, 1, 2, 4, 5};
+    const double fl[5] = {0.1, 0.1, 0.1, 0.001, 0.001};
+    for (int s = 0; s < 5; ++s) { M.term_of[s] = term_of[s]; M.floor_[s] = fl[s]; }
+    h->sizes = {D.case_nbinom_size1, D.case_nbinom_sizey2, D.case_nbinom_sizeo2, D.hosp_nbinom_size1,
+                D.hosp_nbinom_size2, D.hosp_nbinom_size2 * D.hosp_last7, D.mort_nbinom_size * 5,
+                D.case_nbinom_sizeo2 * D.hosp_last7, D.mort_nbinom_size * D.hosp_last7};
+    h->size_vec.resize(nm);
+    for (int i = 0; i < nm; ++i) h->size_vec[i] = D.o_wdmorti[i] * D.mort_nbinom_size;
+    const double *sz = h->sizes.data();
+    // cases, model-age-groups2x.R:572-588 (the x/mu length mismatch of 2q, plus the last eight days of o.dcasei again)
+    calls.push_back({0, 0, D.y_dcasei, nc, 1, r - 1, 0, r, sz + 0, 1});
+    calls.push_back({0, 0, D.y_dcasei, nc, r, nc, r + 1, nc - 1, sz + 1, 1});
+    calls.push_back({1, 1, D.o_dcasei, nc, 1, r - 1, 0, r, sz + 0, 1});
+    calls.push_back({1, 1, D.o_dcasei, nc, r, nc, r + 1, nc - 1, sz + 2, 1});
+    calls.push_back({1, 1, D.o_dcasei, nc, nc - 7, nc, nc - 1 - 7, nc - 1, sz + 7, 1});
+    // hosp, :606-617
+    calls.push_back({2, 2, D.dhospi, nh, 1, rh - 1, 0, rh, sz + 3, 1});
+    calls.push_back({2, 2, D.dhospi, nh, rh, nhh, rh + 1, nh - 1, sz + 4, 1});
+    calls.push_back({2, 2, D.dhospi, nh, nhh - 7, nhh, nh - 1 - 7, nh - 1, sz + 5, 1});
+    // deaths, :646-655
+    calls.push_back({3, 4, D.y_dmorti, nm, 1, nm, 0, nm - 1, sz + 6, 1});
+    calls.push_back({4, 5, D.o_dmorti, nm, 1, nm, 0, nm - 1, h->size_vec.data(), nm});
+    calls.push_back({4, 5, D.o_dmorti, nm, nm - 7, nm, nm - 1 - 7, nm - 1, sz + 8, 1});
     M.d3 = D.d3; M.d4 = D.d4; M.d5d = D.d5; M.d6 = D.d6; M.d7 = D.d7;
     M.lo_ltp = D.lockdown_offset + D.lockdown_transition_period;
   } else if (desc.flavour == EPI_FLAVOUR_AGE2I) {
@@ -476,7 +587,8 @@ extern "C" int epi_n_params(const epi_handle *h) { return h ? h->M.d : 0; }
 extern "C" int epi_n_series(const epi_handle *h) { return h ? (is_age(h->M.flavour) ? 8 : 3) : 0; }
 extern "C" const char *epi_param_name(const epi_handle *h, int i) {
   if (!h || i < 0 || i >= h->M.d) return nullptr;
-  return h->M.flavour == EPI_FLAVOUR_AGE2Q ? kAgeNames[i] : h->M.flavour == EPI_FLAVOUR_AGE2I ? kAge2iNames[i] : kSimpleNames[i];
+  return h->M.flavour == EPI_FLAVOUR_AGE2Q ? kAgeNames[i] : h->M.flavour == EPI_FLAVOUR_AGE2I ? kAge2iNames[i]
+         : h->M.flavour == EPI_FLAVOUR_AGE2X ? kAge2xNames[i] : kSimpleNames[i];
 }
 extern "C" int epi_df_params(const epi_handle *h, double *mn, double *mx, double *init) {
   if (!h) return EPI_ERR_ARG;
@@ -742,19 +854,25 @@ static int trajectories_impl(epi_handle *h, const double *theta, int64_t n, int 
                              int32_t *offset, int32_t *padding, bool ext) {
   if (!h || !theta || !out || n < 0) return epi_fail(h, EPI_ERR_ARG, "bad argument");
   if (n == 0) return EPI_OK;
-  const bool age = is_age(h->M.flavour), fixed_p1 = h->M.flavour == EPI_FLAVOUR_AGE2Q;  // 2q: period1 = 60
+  const bool age = is_age(h->M.flavour), fixed_p1 = fixed_pass1(h->M.flavour);  // 2q / 2x: period1 = 60
   if (period < (fixed_p1 ? 60 : 2) || period > (age ? 2048 : 4096)) return epi_fail(h, EPI_ERR_ARG, "period out of range");
   CUDA_OK(h, cudaSetDevice(h->device));
   DevModel M = h->M;  // calculateModel(params, period): same data, another horizon
   M.P = period;
   if (!fixed_p1) M.P1 = period;
-  const int NS = n_series_of(M.flavour, ext);
-  int rc = epi_ensure_workspace(h, h->ws_traj, M, n, NS);
+  // age-2x: the histories between the kernels hold the infection incidence, S comes from the ext instance of the
+  // ODE kernel — the ext pass always runs and the basic call copies its first eight series out
+  const int NS = n_series_of(M.flavour, ext), NSrun = M.flavour == EPI_FLAVOUR_AGE2X ? n_series_of(M.flavour, true) : NS;
+  int rc = epi_ensure_workspace(h, h->ws_traj, M, n, NSrun);
   if (rc) return rc;
   Workspace &w = h->ws_traj;
   if ((rc = stage_theta(h, w, theta, n, layout, M.d))) return rc;
-  if ((rc = epi_launch_eval_ws(h, w, M, w.theta, w.ld, n, 1, nullptr, nullptr, nullptr, nullptr, w.series, h->stream, NS))) return rc;
-  CUDA_OK(h, cudaMemcpyAsync(out, w.series, sizeof(double) * (size_t)n * NS * period, cudaMemcpyDeviceToHost, h->stream));
+  if ((rc = epi_launch_eval_ws(h, w, M, w.theta, w.ld, n, 1, nullptr, nullptr, nullptr, nullptr, w.series, h->stream, NSrun))) return rc;
+  if (NSrun == NS)
+    CUDA_OK(h, cudaMemcpyAsync(out, w.series, sizeof(double) * (size_t)n * NS * period, cudaMemcpyDeviceToHost, h->stream));
+  else
+    CUDA_OK(h, cudaMemcpy2DAsync(out, sizeof(double) * (size_t)NS * period, w.series, sizeof(double) * (size_t)NSrun * period,
+                                 sizeof(double) * (size_t)NS * period, (size_t)n, cudaMemcpyDeviceToHost, h->stream));
   if (offset) CUDA_OK(h, cudaMemcpyAsync(offset, w.offset, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
   if (padding) CUDA_OK(h, cudaMemcpyAsync(padding, w.pad, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
   CUDA_OK(h, cudaStreamSynchronize(h->stream));
@@ -774,10 +892,10 @@ extern "C" int epi_quantiles(epi_handle *h, const double *theta, int64_t n, int 
                              int32_t series_a, int32_t series_b, const double *probs, int32_t n_probs, double *out) {
   if (!h || !theta || !probs || !out || n < 1 || n_probs < 1 || period < 1) return epi_fail(h, EPI_ERR_ARG, "bad argument");
   if (n > 8192) return epi_fail(h, EPI_ERR_ARG, "epi_quantiles supports at most 8192 draws (got %lld)", (long long)n);
-  const bool age = is_age(h->M.flavour), fixed_p1 = h->M.flavour == EPI_FLAVOUR_AGE2Q;
+  const bool age = is_age(h->M.flavour), fixed_p1 = fixed_pass1(h->M.flavour);
   const int NSb = n_series_of(h->M.flavour, false), NSx = n_series_of(h->M.flavour, true);
   if (series_a < 0 || series_a >= NSx || series_b >= NSx) return epi_fail(h, EPI_ERR_ARG, "series index out of range");
-  const int NS = (series_a >= NSb || series_b >= NSb) ? NSx : NSb;  // an ext series asked for: run the ext pass
+  const int NS = (series_a >= NSb || series_b >= NSb || h->M.flavour == EPI_FLAVOUR_AGE2X) ? NSx : NSb;  // an ext series asked for (age-2x: always): run the ext pass
   const int simperiod = 3 * period;  // libMCMC.R:153
   if (simperiod < (fixed_p1 ? 60 : 2) || simperiod > (age ? 2048 : 4096)) return epi_fail(h, EPI_ERR_ARG, "period out of range");
   CUDA_OK(h, cudaSetDevice(h->device));

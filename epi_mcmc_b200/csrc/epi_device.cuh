@@ -14,7 +14,7 @@ namespace epi {
 constexpr int kTile = 32;      // chains per history tile == warp width
 constexpr int kPadMax = 64;    // prefill slots kept in front of a staged S series
 constexpr int kMaxSeries = 5;  // scored series: age y.casei,o.casei,hospi,y.deadi,o.deadi; simple hospi,deadi
-constexpr int kMaxBp = 10;     // schedule breakpoints (model-agen.cpp:73-100)
+constexpr int kMaxBp = 13;     // schedule breakpoints (model-agen.cpp:73-100: 10; model-ager.cpp:88-124: 13)
 constexpr int kNaFlagTerms = 8;
 
 // One slot of the day-major likelihood term table: the data-only part of one
@@ -52,6 +52,10 @@ struct DevModel {
   double term_const[8];  // data-only constants per reference term (lgamma parts + size*log(size))
   double tdl, mort_size;  // simple: loglLD = dnbinom(total_deaths_at_lockdown, mu = max(.1, thr), size)
   double d3, d4, d5d, d6, d7, lo_ltp;
+  // age-2x (model-age-groups2x.R + model-ager.cpp): waning rate, the fixed breakpoint days d9 / d12, the
+  // symptomatic-testing factor window of the case series (:278-279,293-294)
+  double eta, symp_factor;
+  int d9, d12, d_symp, d_all;
   const double *y_ifr, *o_ifr, *y_hr, *o_hr, *g, *gtrimp;  // device, n_rate each
   const Slot *slots[kMaxSeries];                           // device, [n_obs][K]
   int multi_begin[kMaxSeries];  // first relative day with more than one slot (n_obs when K == 1)

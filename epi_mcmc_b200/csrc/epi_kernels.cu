@@ -86,11 +86,16 @@ constexpr int kStRetry = 1 << 30;
 template <int FL>
 struct Traits {
   static constexpr bool k2i = (FL == EPI_FLAVOUR_AGE2I);  // model-age-groups2i.R + model-agef.cpp
-  static constexpr bool kAge = (FL == EPI_FLAVOUR_AGE2Q) || k2i;
+  // model-age-groups2x.R + model-ager.cpp: waning immunity (R flows back into S, so R is ALWAYS integrated), the
+  // younger group's effective-susceptible cap, 13 breakpoints, and the histories between the kernels hold the
+  // infection INCIDENCE (derivs() output variables y.i / o.i) instead of S: the observation series are plain
+  // convolutions of it, no N - x and no diff
+  static constexpr bool k2x = (FL == EPI_FLAVOUR_AGE2X);
+  static constexpr bool kAge = (FL == EPI_FLAVOUR_AGE2Q) || k2i || k2x;
   static constexpr int NEQ = kAge ? 10 : 4;
   static constexpr int NG = kAge ? 2 : 1;   // S series per chain
   static constexpr int NK = kAge ? 6 : 2;   // latency profiles per chain
-  static constexpr int NBP = k2i ? 8 : (kAge ? 10 : 2);  // schedule breakpoints
+  static constexpr int NBP = k2i ? 8 : k2x ? 13 : (kAge ? 10 : 2);  // schedule breakpoints
   // prefill slots kept in front of a staged S series == largest padding supported == rows of the
   // absolute-delay profile table: the 2i box lets the death latency reach 50 + 3*9 = 77 days
   // (model-age-groups2i.R:580-582), every other flavour stays below 64
@@ -118,6 +123,25 @@ __device__ __forceinline__ void age_beta(const double *__restrict__ th, int64_t 
     }
     return;
   }
+  if constexpr (Traits<FL>::k2x) {
+    // R/models/model-age-groups2x.R:56-119: beta8 = beta7, beta10 = beta12 = beta9
+    int b;
+    switch (k) {
+      case 0: b = 0; break;
+      case 1: b = 3; break;
+      case 2: b = 6; break;
+      case 3: b = 24; break;
+      case 4: b = 28; break;
+      case 5: b = 31; break;
+      case 6: b = 35; break;
+      case 7:
+      case 8: b = 39; break;
+      case 11: b = 49; break;
+      default: b = 42; break;  // 9, 10, 12
+    }
+    by = T(b); bo = T(b + 1); byo = T(b + 2);
+    return;
+  }
   switch (k) {
     case 0: by = T(0); bo = T(1); byo = T(2); break;
     case 1: by = T(3); bo = T(4); byo = T(5); break;
@@ -133,9 +157,9 @@ __device__ __forceinline__ void age_beta(const double *__restrict__ th, int64_t 
 }
 
 // segment kinds: 1 = linear towards k+1, 0 = hold.  model-agen.cpp:78-99: k = 0,1,2,3,8 linear;
-// model-agef.cpp:66-87: k = 0..5 linear, 6 and 7 hold
+// model-agef.cpp:66-87: k = 0..5 linear, 6 and 7 hold; model-ager.cpp:88-124: k = 0,1,2,3,8,10,11 linear
 template <int FL>
-__device__ __forceinline__ bool age_linear(int k) { return ((Traits<FL>::k2i ? 0x03F : 0x10F) >> k) & 1; }
+__device__ __forceinline__ bool age_linear(int k) { return ((Traits<FL>::k2i ? 0x03F : Traits<FL>::k2x ? 0xD0F : 0x10F) >> k) & 1; }
 
 // ---------------------------------------------------------------------- K_ode
 // Fixed-step classical RK4, m sub-steps per day, each sub-step cut again at the
@@ -234,6 +258,8 @@ __device__ __forceinline__ void rhs(const DevModel &M, const Seg &sg, double t, 
       if constexpr (!TRACKR) flag |= (Sy < 1.0 || So < 1.0) ? 1u : 0u;  // the R test is undecidable here
     } else if constexpr (TRACKR) {
       flag |= oob_group5(Sy, E1y, E2y, Iy, Ry, nb0) | oob_group5(So, E1o, E2o, Io, Ro, nb1);
+      // with waning immunity S is no longer monotone: "S > N" gets its own (exact) test
+      if constexpr (Traits<FL>::k2x) flag |= (Sy > M.Ny || So > M.No) ? 0x80000000u : 0u;
     } else {
       flag |= oob_group4_nor(Sy, E1y, E2y, Iy, nb0) | oob_group4_nor(So, E1o, E2o, Io, nb1);
     }
@@ -245,6 +271,25 @@ __device__ __forceinline__ void rhs(const DevModel &M, const Seg &sg, double t, 
     const double betao = HOLD ? sg.b1 : fma(dt, sg.s1, sg.b1);
     const double betayo = HOLD ? sg.b2 : fma(dt, sg.s2, sg.b2);
     // (betay, betao, betayo are beta_y / N_y, beta_o / N_o, beta_yo / N_y here, see select_segment)
+    if constexpr (Traits<FL>::k2x) {
+      // model-ager.cpp:176-200 (uncertain() multiplies by funcertain = 1, model-age-groups2x.R:221: exact identity)
+      static_assert(TRACKR, "the waning-immunity flavour always integrates R");
+      const double Syeff = fmax(0.0, __dsub_rn(__dmul_rn(M.Ny, 0.8), __dsub_rn(M.Ny, Sy)));
+      const double yinf = __dmul_rn(__dmul_rn(betay, Iy), Syeff);
+      const double oinf = __dmul_rn(fma(betao, Io, __dmul_rn(betayo, Iy)), So);
+      const double yrev = __dmul_rn(M.eta, Ry), orev = __dmul_rn(M.eta, Ro);
+      dy[0] = __dsub_rn(yrev, yinf);
+      dy[1] = fma(-M.a1, E1y, yinf);
+      dy[2] = fma(M.a1, E1y, -E2y);
+      dy[3] = fma(-M.gamma, Iy, E2y);
+      dy[4] = fma(M.gamma, Iy, -yrev);
+      dy[5] = __dsub_rn(orev, oinf);
+      dy[6] = fma(-M.a1, E1o, oinf);
+      dy[7] = fma(M.a1, E1o, -E2o);
+      dy[8] = fma(-M.gamma, Io, E2o);
+      dy[9] = fma(M.gamma, Io, -orev);
+      return;
+    }
     const double yinf = __dmul_rn(__dmul_rn(betay, Iy), Sy);
     const double oinf = __dmul_rn(fma(betao, Io, __dmul_rn(betayo, Iy)), So);
     dy[0] = -yinf;
@@ -380,6 +425,22 @@ __device__ __forceinline__ int breakpoints(const DevModel &M, const double *__re
     bp[1] = data_offset + lo + fmax(t0o, 0.0);
     bp[2] = t2; bp[3] = t3; bp[4] = t4; bp[5] = t5; bp[6] = t5 + T(29); bp[7] = data_offset + M.d7;
     return 8;
+  } else if constexpr (Traits<FL>::k2x) {
+    // model-age-groups2x.R:206-219
+    auto T = [&](int i) { return th[(int64_t)i * ld]; };
+    const double lo = M.lockdown_offset, t0o = T(18);
+    const double t2 = data_offset + lo + M.ltp;
+    const double t3 = t2 + T(23);
+    const double t4 = t3 + T(27);
+    const double t5 = data_offset + M.d5;
+    const double t6 = t5 + T(34);
+    const double t7 = t6 + T(38);
+    const double t10 = data_offset + T(48);
+    bp[0] = data_offset + lo + t0o;
+    bp[1] = data_offset + lo + fmax(t0o, 0.0);
+    bp[2] = t2; bp[3] = t3; bp[4] = t4; bp[5] = t5; bp[6] = t6; bp[7] = t7;
+    bp[8] = data_offset + M.d8; bp[9] = data_offset + M.d9; bp[10] = t10; bp[11] = t10 + 3; bp[12] = data_offset + M.d12;
+    return 13;
   } else if constexpr (Traits<FL>::kAge) {
     auto T = [&](int i) { return th[(int64_t)i * ld]; };
     const double lo = M.lockdown_offset, t0o = T(18);
@@ -516,7 +577,9 @@ __device__ __noinline__ void write_ext(const DevModel &M, const double *__restri
         const double f = (t - bp[k]) / (bp[k + 1] - bp[k]);
         by = by + f * (ny - by); bo = bo + f * (no - bo); byo = byo + f * (nyo - byo);
       }
-      const double yinf = (by * Iy) / Ny * Sy;
+      // (model-ager.cpp:176-178: the younger group's infections run on the effective susceptibles)
+      const double Syx = Traits<FL>::k2x ? fmax(0.0, Ny * 0.8 - (Ny - Sy)) : Sy;
+      const double yinf = (by * Iy) / Ny * Syx;
       const double oinf = ((bo * Io) / No + (byo * Iy) / Ny) * So;
       const double ig = 1 / M.gamma;
       o0 = ig * (yinf + oinf) / (Iy + Io);
@@ -547,6 +610,39 @@ __device__ __noinline__ void write_ext(const DevModel &M, const double *__restri
   }
 }
 
+// What the history rows between the kernels hold at simulation day t: S of each group — or, for the age-2x
+// flavour, the infection incidences y.i / o.i, i.e. derivs()' output variables 5 and 6 (model-ager.cpp:206-207) as
+// deSolve evaluates them for the output matrix: one derivs() call at the output time with the LITERAL `t > tk`
+// schedule, in the reference's own operation order (explicit roundings: bit-identical to the oracle's restatement
+// for the same state).  When the bounds guard returns early the reference leaves them stale: NaN here.
+template <int FL>
+__device__ __noinline__ void incidence_out(const DevModel &M, const double *__restrict__ th, int64_t ld, const double *bp,
+                                           int nbp, double t, const double *y, double &yi, double &oi) {
+  const double Sy = y[0], E1y = y[1], E2y = y[2], Iy = y[3], Ry = y[4];
+  const double So = y[5], E1o = y[6], E2o = y[7], Io = y[8], Ro = y[9];
+  const double Ny = M.Ny, No = M.No;
+  yi = NAN; oi = NAN;
+  if (Sy < 0 || E1y < 0 || E2y < 0 || Iy < 0 || Ry < 0 || Sy > Ny || E1y > Ny || E2y > Ny || Iy > Ny || Ry > Ny ||
+      So < 0 || E1o < 0 || E2o < 0 || Io < 0 || Ro < 0 || So > No || E1o > No || E2o > No || Io > No || Ro > No)
+    return;
+  int k = -1;
+  for (int i = nbp - 1; i >= 0; --i)
+    if (t > bp[i]) { k = i; break; }
+  double by, bo, byo;
+  age_beta<FL>(th, ld, k < 0 ? 0 : k, by, bo, byo);
+  if (k >= 0 && age_linear<FL>(k)) {
+    double ny, no, nyo;
+    age_beta<FL>(th, ld, k + 1, ny, no, nyo);
+    const double f = __ddiv_rn(__dsub_rn(t, bp[k]), __dsub_rn(bp[k + 1], bp[k]));
+    by = __dadd_rn(by, __dmul_rn(f, __dsub_rn(ny, by)));
+    bo = __dadd_rn(bo, __dmul_rn(f, __dsub_rn(no, bo)));
+    byo = __dadd_rn(byo, __dmul_rn(f, __dsub_rn(nyo, byo)));
+  }
+  const double Syeff = fmax(0.0, __dsub_rn(__dmul_rn(Ny, 0.8), __dsub_rn(Ny, Sy)));
+  yi = __dmul_rn(__ddiv_rn(__dmul_rn(by, Iy), Ny), Syeff);
+  oi = __dmul_rn(__dadd_rn(__ddiv_rn(__dmul_rn(bo, Io), No), __ddiv_rn(__dmul_rn(byo, Iy), Ny)), So);
+}
+
 // TRACKR = false (the hot instance): the removed compartment is not integrated (see below_one); a chain where
 // that could have changed a guard decision sets need_r[chain] and is recomputed by the TRACKR = true instance,
 // which is launched right behind and only works on those chains.  FULL (ext trajectories) always tracks R.
@@ -558,7 +654,7 @@ k_ode(const DevModel M, const double *__restrict__ theta, int64_t ld, int64_t n,
       int ns_total = 0, int window_only = 0, int ndays_limit = 0, const int *__restrict__ retry_status = nullptr,
       int *__restrict__ need_r_flag = nullptr, int force_need_r = 0) {
   constexpr int NEQ = Traits<FL>::NEQ, NG = Traits<FL>::NG;
-  constexpr bool TR = TRACKR || FULL;  // integrate the removed compartment
+  constexpr bool TR = TRACKR || FULL || Traits<FL>::k2x;  // integrate the removed compartment
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   if constexpr (TRACKR && !FULL) {
@@ -656,8 +752,15 @@ k_ode(const DevModel M, const double *__restrict__ theta, int64_t ld, int64_t n,
   const int m = M.m;
   const double h = 1.0 / (double)m;
   if (d0 == 0) {
-    out[0] = y[0];
-    if constexpr (NG == 2) out[pitch] = y[5];
+    if constexpr (Traits<FL>::k2x) {
+      double yi, oi;
+      incidence_out<FL>(M, th, ld, bp, nbp, (double)t0, y, yi, oi);
+      out[0] = yi; out[pitch] = oi;
+      if constexpr (FULL) { eo[-8 * (int64_t)M.P] = y[0]; eo[-7 * (int64_t)M.P] = y[5]; }  // series 0, 1: y.S, o.S
+    } else {
+      out[0] = y[0];
+      if constexpr (NG == 2) out[pitch] = y[5];
+    }
     if constexpr (FULL) write_ext<FL>(M, th, ld, bp, nbp, (double)t0, y, inv1, eo, M.P, 0);
   }
   if constexpr (!PASS2) {
@@ -711,8 +814,15 @@ k_ode(const DevModel M, const double *__restrict__ theta, int64_t ld, int64_t n,
       pa = pb;
       if (step_done) ++s;
     }
-    out[hist_index<PASS2>(d, Q)] = y[0];
-    if constexpr (NG == 2) out[pitch + hist_index<PASS2>(d, Q)] = y[5];
+    if constexpr (Traits<FL>::k2x) {
+      double yi, oi;
+      incidence_out<FL>(M, th, ld, bp, nbp, (double)(t0 + d), y, yi, oi);
+      out[hist_index<PASS2>(d, Q)] = yi; out[pitch + hist_index<PASS2>(d, Q)] = oi;
+      if constexpr (FULL) { eo[-8 * (int64_t)M.P + d] = y[0]; eo[-7 * (int64_t)M.P + d] = y[5]; }
+    } else {
+      out[hist_index<PASS2>(d, Q)] = y[0];
+      if constexpr (NG == 2) out[pitch + hist_index<PASS2>(d, Q)] = y[5];
+    }
     if constexpr (FULL) write_ext<FL>(M, th, ld, bp, nbp, (double)(t0 + d), y, inv1, eo, M.P, d);
     if constexpr (!PASS2) {
       if (ck && d < cdays) {
@@ -728,9 +838,14 @@ k_ode(const DevModel M, const double *__restrict__ theta, int64_t ld, int64_t n,
   if constexpr (FULL) {
     // invalid data_offset with a pass 1 shorter than the period: R recycles the short matrix (:216-227)
     constexpr int NE = Traits<FL>::kAge ? 10 : 5;
-    for (int d = nint; d < ndays; ++d)
+    for (int d = nint; d < ndays; ++d) {
 #pragma unroll
       for (int q = 0; q < NE; ++q) eo[q * M.P + d] = eo[q * M.P + d % nint];
+      if constexpr (Traits<FL>::k2x) {
+        eo[-8 * (int64_t)M.P + d] = eo[-8 * (int64_t)M.P + d % nint];
+        eo[-7 * (int64_t)M.P + d] = eo[-7 * (int64_t)M.P + d % nint];
+      }
+    }
   }
 }
 
@@ -1310,12 +1425,14 @@ __device__ __forceinline__ void profile_params(const double *th, int q, double &
       default: mean = th[18]; sd = DLsd; break;
     }
   } else if constexpr (Traits<FL>::kAge) {
-    const double CLsd = 5.0, HLsd = th[19], DLsd = th[20];
+    // CLsd: 5 in model-age-groups2q.R:103, 2.5 in model-age-groups2x.R:20; y.CL / o.CL are parameters 45, 46 resp. 47, 48
+    const double CLsd = Traits<FL>::k2x ? 2.5 : 5.0, HLsd = th[19], DLsd = th[20];
+    constexpr int iycl = Traits<FL>::k2x ? 46 : 43, iocl = Traits<FL>::k2x ? 47 : 44;
     switch (q) {
-      case 0: mean = th[43]; sd = CLsd; break;
+      case 0: mean = th[iycl]; sd = CLsd; break;
       case 1: mean = th[11]; sd = HLsd; break;
       case 2: mean = th[12]; sd = DLsd; break;
-      case 3: mean = th[44]; sd = CLsd; break;
+      case 3: mean = th[iocl]; sd = CLsd; break;
       case 4: mean = th[15]; sd = HLsd; break;
       default: mean = th[16]; sd = DLsd; break;
     }
@@ -1440,7 +1557,8 @@ __device__ __forceinline__ void stage_history_end(const DevModel &M, double *S, 
   const int stride = PAD + hist_pitch(ndays);
 #pragma unroll
   for (int g = 0; g < NG; ++g) {
-    const double s0 = Traits<FL>::kAge ? (g == 0 ? M.Ny - 1.0 : M.No) : M.N - 1.0;
+    // (age-2x: the staged rows hold the incidence, pre-filled with 0, model-age-groups2x.R:156-157)
+    const double s0 = Traits<FL>::k2x ? 0.0 : Traits<FL>::kAge ? (g == 0 ? M.Ny - 1.0 : M.No) : M.N - 1.0;
     for (int j = lane; j < PAD; j += 32) S[g * stride + j] = s0;
   }
   mbar_wait(mbar, 0);
@@ -1554,7 +1672,28 @@ k_mid(const DevModel M, const double *__restrict__ theta, int64_t ld, int64_t n,
   int first = -1;
   double thr;  // t0_morts (2q :69, 2i :71) / mort_lockdown_threshold
   if constexpr (Traits<FL>::k2i) thr = w.theta[19]; else if constexpr (Traits<FL>::kAge) thr = w.theta[17]; else thr = w.theta[7];
-  for (int base = 0; base < nsearch && first < 0; base += 32) {
+  if constexpr (Traits<FL>::k2x) {
+    // model-age-groups2x.R:194-204: died = cumsum(conv(y.i) * y.died_rate) + cumsum(conv(o.i) * o.died_rate), first day
+    // above t0_morts.  The daily terms are computed lane-parallel into the (free) CDF scratch, the two running sums
+    // then sequentially in double-double (R's cumsum accumulates in long double and rounds every partial sum to
+    // double; a NaN term makes every later sum NaN: no crossing)
+    double *dy_ = w.cdf, *do_ = w.cdf + 64;
+    for (int j = lane; j < nsearch; j += 32) {
+      dy_[j] = conv_at<PAD>(w.S, w.W + 2 * EPI_MAX_TAPS, pad, j, dmin_[2], n_[2]) * M.ifr_y1;
+      do_[j] = conv_at<PAD>(w.S + stride, w.W + 5 * EPI_MAX_TAPS, pad, j, dmin_[5], n_[5]) * M.ifr_o1;
+    }
+    __syncwarp();
+    double hy = 0.0, ly = 0.0, ho = 0.0, lo_ = 0.0;
+    for (int j = 0; j < nsearch && first < 0; ++j) {
+      // two-sum of the running (hi, lo) pair with the next term
+      double x = dy_[j], s1 = hy + x, bb = s1 - hy, e = (hy - (s1 - bb)) + (x - bb);
+      e += ly; hy = s1 + e; ly = e - (hy - s1);
+      x = do_[j]; s1 = ho + x; bb = s1 - ho; e = (ho - (s1 - bb)) + (x - bb);
+      e += lo_; ho = s1 + e; lo_ = e - (ho - s1);
+      if (hy + ho > thr) first = j;
+    }
+  }
+  for (int base = 0; !Traits<FL>::k2x && base < nsearch && first < 0; base += 32) {
     const int j = base + lane;
     bool hit = false;
     if (j < nsearch) {
@@ -1732,7 +1871,7 @@ __device__ __forceinline__ void stage_score(const DevModel &M, const ScoreSmem &
   // prefill slots x[1..padding] = N - Initial (:118,127) in front of every phase row
 #pragma unroll
   for (int g = 0; g < NG; ++g) {
-    const double s0 = Traits<FL>::kAge ? (g == 0 ? M.Ny - 1.0 : M.No) : M.N - 1.0;
+    const double s0 = Traits<FL>::k2x ? 0.0 : Traits<FL>::kAge ? (g == 0 ? M.Ny - 1.0 : M.No) : M.N - 1.0;
     for (int j = lane; j < PAD; j += 32) w.S[(g * 4 + (j & 3)) * AS + (j >> 2)] = s0;
   }
   mbar_wait(w.mbar, 0);
@@ -1804,15 +1943,24 @@ __device__ __forceinline__ void conv_tile4(const double *__restrict__ Sg, int AS
 // load -> branch -> load chains were 24 % long-scoreboard stalls).
 template <int FL>
 struct AgeMap {
+  static constexpr int kIfrred = Traits<FL>::k2x ? 45 : 42;  // ifrred: parameter 43 of 2q, 46 of 2x
   int t1[6], t2[6];
+  // age-2x: the case series are multiplied by symp.cases.factor on the days between t.symp and min(t.all, T)
+  // (model-age-groups2x.R:278-279,293-294,340-341; R's a:b runs downwards when a > b); valid offsets only
+  int symp_lo, symp_hi;
+  __device__ __forceinline__ double case_factor(const DevModel &M, int t) const {
+    if constexpr (Traits<FL>::k2x) return (valid && t >= symp_lo && t <= symp_hi) ? M.symp_factor : 1.0;
+    return 1.0;
+  }
   bool on[6];  // t1 > pad && t2 > t1, or invalid offset (then rate[1] everywhere, :250)
   bool valid, all_on;
   __device__ __forceinline__ void init(const DevModel &M, const double *th, int off_raw, int pad, int P) {
     valid = off_raw != EPI_INVALID_DATA_OFFSET;
     // y.DL is used for both groups (2q :290,306; 2i :264,280)
     const double ydl = Traits<FL>::k2i ? th[13] : th[12];
-    const double lat[6] = {Traits<FL>::k2i ? th[10] : th[43], Traits<FL>::k2i ? th[12] : th[11], 0,
-                           Traits<FL>::k2i ? th[15] : th[44], Traits<FL>::k2i ? th[17] : th[15], 0};
+    // (y.CL, o.CL: parameters 44, 45 of 2q, 47, 48 of 2x)
+    const double lat[6] = {Traits<FL>::k2i ? th[10] : Traits<FL>::k2x ? th[46] : th[43], Traits<FL>::k2i ? th[12] : th[11], 0,
+                           Traits<FL>::k2i ? th[15] : Traits<FL>::k2x ? th[47] : th[44], Traits<FL>::k2i ? th[17] : th[15], 0};
 #pragma unroll
     for (int q = 0; q < 6; ++q) {
       const int shift = (q == 2 || q == 5) ? 0 : (int)rint(-ydl + lat[q]);
@@ -1821,6 +1969,20 @@ struct AgeMap {
       on[q] = !valid || (t1[q] > pad && t2[q] > t1[q]);
     }
     all_on = on[0] && on[1] && on[2] && on[3] && on[4] && on[5];
+    symp_lo = 1; symp_hi = 0;
+    if constexpr (Traits<FL>::k2x) {
+      const int a = off_raw + M.d_symp, b = min(off_raw + M.d_all - 1, pad + P);
+      symp_lo = min(a, b); symp_hi = max(a, b);
+    }
+  }
+  // age-2x: a window that would start beyond the vector grows it in R (and moves calclogl's windows): unsupported
+  __device__ __forceinline__ bool symp_unsupported(const DevModel &M, int off_raw, int pad, int P) const {
+    if constexpr (Traits<FL>::k2x) {
+      if (!valid) return false;
+      const int a = off_raw + M.d_symp, b = min(off_raw + M.d_all - 1, pad + P);
+      return a > pad + P || a < 1 || b < 1;
+    }
+    return false;
   }
   // 0-based index into the rate vectors for profile q at sim day t
   __device__ __forceinline__ int index(const DevModel &M, int q, int t) const {
@@ -1861,7 +2023,7 @@ struct AgeMap {
     const double oifr3 = __ldg(M.o_ifr + k[3]);
     const double ohr4 = __ldg(M.o_hr + k[4]);
     const double oifr5 = __ldg(M.o_ifr + k[5]), gt5 = __ldg(M.gtrimp + k[5]);
-    const double ifrred = th[42];
+    const double ifrred = th[kIfrred];
     double r[6];
     r[0] = th[9] * yifr0 * (1 + (th[21] - 1) * g0);   r[0] = r[0] > 1 ? 1.0 : r[0];  // gycr = pmin(1, .)
     r[1] = th[10] * yhr1 * (1 + (th[22] - 1) * g1);                                   // gyhr
@@ -1909,14 +2071,14 @@ struct AgeMap {
       const double yifr2 = __ldg(M.y_ifr + k[2]), g2 = __ldg(M.g + k[2]), gt2 = __ldg(M.gtrimp + k[2]);
       r[0] = th[9] * yifr0 * (1 + (th[21] - 1) * g0);   r[0] = r[0] > 1 ? 1.0 : r[0];  // gycr = pmin(1, .)
       r[1] = th[10] * yhr1 * (1 + (th[22] - 1) * g1);                                   // gyhr
-      r[2] = yifr2 * (1 + (th[21] - 1) * g2) * (1 - th[42] * gt2);                      // gyifr
+      r[2] = yifr2 * (1 + (th[21] - 1) * g2) * (1 - th[kIfrred] * gt2);                 // gyifr
     } else {
       const double oifr3 = __ldg(M.o_ifr + k[0]);
       const double ohr4 = __ldg(M.o_hr + k[1]);
       const double oifr5 = __ldg(M.o_ifr + k[2]), gt5 = __ldg(M.gtrimp + k[2]);
       r[0] = th[13] * oifr3;                            r[0] = r[0] > 1 ? 1.0 : r[0];  // gocr
       r[1] = th[14] * ohr4;                                                             // gohr
-      r[2] = oifr5 * (1 - th[42] * gt5);                                                // goifr
+      r[2] = oifr5 * (1 - th[kIfrred] * gt5);                                           // goifr
     }
     if (all_on) {
 #pragma unroll
@@ -2038,6 +2200,15 @@ k_score(const DevModel M, const PriorTerm *__restrict__ PT, int n_prior, const d
   if constexpr (Traits<FL>::kAge) {
     AgeMap<FL> map;
     map.init(M, w.theta, off_raw, pad, P);
+    if (map.symp_unsupported(M, off_raw, pad, P)) {
+      if (lane == 0) {
+        if (logl) logl[chain] = NAN;
+        if (logp) logp[chain] = lp;
+        status[chain] = st | EPI_ST_UNSUPPORTED;
+        if (terms) for (int k = 0; k < 8; ++k) terms[chain * 8 + k] = NAN;
+      }
+      return;
+    }
     double carry[6] = {0, 0, 0, 0, 0, 0};  // s2 of the day in front of the sweep (0 in front of day 0)
     // One S group at a time, so that only twelve convolution results are live while a group's days are scored
     // (with all 24 the day loop spilled: profiles/r2_summary.md): the y group scores y.casei and y.deadi and
@@ -2060,7 +2231,9 @@ k_score(const DevModel M, const PriorTerm *__restrict__ PT, int n_prior, const d
           for (int q = 0; q < 3; ++q) {
             double &x = c[r * 3 + q];
             if (q == 1 && t0 + r - dmin_[g * 3 + 1] < n_[g * 3 + 1]) x = NAN;
-            x = (j0 + r < P) ? (g ? M.No : M.Ny) - x : 0.0;
+            // (age-2x: the convolution of the incidence IS the series, model-age-groups2x.R:282,301,315)
+            if constexpr (Traits<FL>::k2x) x = (j0 + r < P) ? x : 0.0;
+            else x = (j0 + r < P) ? (g ? M.No : M.Ny) - x : 0.0;
           }
         // c(s2[1], diff(s2)), :239: the predecessor of the lane's first day is the last day of the lane below (the
         // carry of the previous sweep for lane 0; the 0.0 in front of day 0, and s2 - 0.0 == s2 exactly)
@@ -2085,11 +2258,12 @@ k_score(const DevModel M, const PriorTerm *__restrict__ PT, int n_prior, const d
             double inc[3], val[3];
 #pragma unroll
             for (int q = 0; q < 3; ++q) {
-              inc[q] = c[r * 3 + q] - prev[q];
+              inc[q] = Traits<FL>::k2x ? c[r * 3 + q] : c[r * 3 + q] - prev[q];
               prev[q] = c[r * 3 + q];
             }
             if (g == 0) map.template values3<0>(M, w.theta, t, inc, val);
             else map.template values3<1>(M, w.theta, t, inc, val);
+            if constexpr (Traits<FL>::k2x) val[0] = val[0] * map.case_factor(M, t);
             acc[g] += sc.score(M, ltab, g, val[0]);
             acc[3 + g] += sd.score(M, ltab, 3 + g, val[2]);
             if (g == 0) {
@@ -2221,7 +2395,8 @@ k_series(const DevModel M, const double *__restrict__ theta, int64_t ld, int64_t
         for (int q = 0; q < 6; ++q) {
           double &x = c[q / 3][r * 3 + q % 3];
           if (t0 + r - dmin_[q] < n_[q]) x = NAN;
-          x = (j0 + r < P) ? (q < 3 ? M.Ny : M.No) - x : 0.0;
+          if constexpr (Traits<FL>::k2x) x = (j0 + r < P) ? x : 0.0;
+          else x = (j0 + r < P) ? (q < 3 ? M.Ny : M.No) - x : 0.0;
         }
       double prev[6];
 #pragma unroll
@@ -2235,16 +2410,22 @@ k_series(const DevModel M, const double *__restrict__ theta, int64_t ld, int64_t
       for (int r = 0; r < 4; ++r) {
         const int j = j0 + r, t = t0 + r;
         if (j >= P) break;
-        o[0 * P + j] = staged_s<PAD>(w.S, 0, AS, j);
-        o[1 * P + j] = staged_s<PAD>(w.S, 1, AS, j);
+        if constexpr (!Traits<FL>::k2x) {  // (age-2x: the staged rows hold the incidence; S is written by the ext ODE instance)
+          o[0 * P + j] = staged_s<PAD>(w.S, 0, AS, j);
+          o[1 * P + j] = staged_s<PAD>(w.S, 1, AS, j);
+        }
         double inc[6], val[6];
 #pragma unroll
         for (int q = 0; q < 6; ++q) {
           const double s2 = c[q / 3][r * 3 + q % 3];
-          inc[q] = (j == 0) ? s2 : s2 - prev[q];
+          inc[q] = (Traits<FL>::k2x || j == 0) ? s2 : s2 - prev[q];
           prev[q] = s2;
         }
         map.values(M, w.theta, t, inc, val);
+        if constexpr (Traits<FL>::k2x) {
+          const double f = map.case_factor(M, t);
+          val[0] = val[0] * f; val[3] = val[3] * f;
+        }
 #pragma unroll
         for (int q = 0; q < 6; ++q) o[dst[q] * P + j] = val[q];
       }
@@ -2402,9 +2583,10 @@ static cudaError_t launch_eval_fl(const EvalArgs &a) {
   // Four lanes per chain (k_ode_age4) while a thread-per-chain launch would leave the SMs short of warps; the
   // thresholds are measured (profiles/r2_summary.md).  EPI_ODE_LANES = 1 | 2 | 4 forces one mapping (tests, bench).
   int lanes = 1;
-  if constexpr (Traits<FL>::kAge) {
+  if constexpr (Traits<FL>::kAge && !Traits<FL>::k2x) {  // (age-2x: thread per chain only)
     lanes = a.ode_lanes ? a.ode_lanes : (n <= (int64_t)n_sm * 256 ? 4 : 1);
   }
+  constexpr bool kFallback = !Traits<FL>::k2x;  // the R-tracking fallback instance exists where the hot one does not integrate R
   const bool use_pair = lanes == 2, use_quad = lanes == 4;
   const unsigned quad_blocks = (unsigned)((4 * n + 127) / 128);
   const bool quad_roomy = (int64_t)quad_blocks <= (int64_t)n_sm * 4;  // all blocks resident at 128 registers
@@ -2426,8 +2608,8 @@ static cudaError_t launch_eval_fl(const EvalArgs &a) {
     } else {
       k_ode<FL, false><<<ode_blocks, 32, 0, s>>>(M, a.theta, a.ld, n, nullptr, nullptr, nullptr, a.hist1, a.ckpt, nullptr, 0, 0, limit, retry, a.need_r, a.force_need_r);
     }
-    k_ode<FL, false, false, true><<<ode_blocks, 32, 0, s>>>(M, a.theta, a.ld, n, nullptr, nullptr, nullptr, a.hist1, a.ckpt, nullptr, 0, 0, 0, nullptr, a.need_r, 0);
-    nl += 2;
+    if constexpr (kFallback) k_ode<FL, false, false, true><<<ode_blocks, 32, 0, s>>>(M, a.theta, a.ld, n, nullptr, nullptr, nullptr, a.hist1, a.ckpt, nullptr, 0, 0, 0, nullptr, a.need_r, 0);
+    nl += kFallback ? 2 : 1;
   };
   pass1(chunk, nullptr);
   if (a.ev) cudaEventRecord(a.ev[1], s);
@@ -2440,7 +2622,7 @@ static cudaError_t launch_eval_fl(const EvalArgs &a) {
   }
   if (a.ev) cudaEventRecord(a.ev[2], s);
   if (a.ev_after_mid) cudaEventRecord(a.ev_after_mid, s);
-  const bool want_ext = a.series_out && a.ns_total > (Traits<FL>::kAge ? 8 : 3);
+  const bool want_ext = a.series_out && (a.ns_total > (Traits<FL>::kAge ? 8 : 3));  // (age-2x trajectories always ask for it)
   const int window_only = (a.series_out || !a.window_only) ? 0 : 1;  // scoring reads S(t) only up to the last data-window day
   if ((use_pair || use_quad) && !want_ext) {
     if constexpr (Traits<FL>::kAge) {
@@ -2457,8 +2639,8 @@ static cudaError_t launch_eval_fl(const EvalArgs &a) {
     nl += 1;
   } else {
     k_ode<FL, true><<<ode_blocks, 32, 0, s>>>(M, a.theta, a.ld, n, a.offset, a.pad, a.hist1, a.hist2, a.ckpt, nullptr, 0, window_only, 0, nullptr, a.need_r, a.force_need_r);
-    k_ode<FL, true, false, true><<<ode_blocks, 32, 0, s>>>(M, a.theta, a.ld, n, a.offset, a.pad, a.hist1, a.hist2, a.ckpt, nullptr, 0, window_only, 0, nullptr, a.need_r, 0);
-    nl += 2;
+    if constexpr (kFallback) k_ode<FL, true, false, true><<<ode_blocks, 32, 0, s>>>(M, a.theta, a.ld, n, a.offset, a.pad, a.hist1, a.hist2, a.ckpt, nullptr, 0, window_only, 0, nullptr, a.need_r, 0);
+    nl += kFallback ? 2 : 1;
   }
   if (a.ev) cudaEventRecord(a.ev[3], s);
   if (a.series_out) {
@@ -2479,6 +2661,7 @@ cudaError_t launch_eval(const EvalArgs &a) {
     case EPI_FLAVOUR_SIMPLE: return launch_eval_fl<EPI_FLAVOUR_SIMPLE>(a);
     case EPI_FLAVOUR_NE: return launch_eval_fl<EPI_FLAVOUR_NE>(a);
     case EPI_FLAVOUR_AGE2I: return launch_eval_fl<EPI_FLAVOUR_AGE2I>(a);
+    case EPI_FLAVOUR_AGE2X: return launch_eval_fl<EPI_FLAVOUR_AGE2X>(a);
     default: return launch_eval_fl<EPI_FLAVOUR_AGE2Q>(a);
   }
 }

@@ -42,9 +42,15 @@ struct SamplerState {
   bool psd_ready = false;
   unsigned long long *acc = nullptr;         // accepted moves, device scalar
   double *pop_own = nullptr;                 // own snapshot (1 rank)
-  const double *pop = nullptr;               // population snapshot [rank][d][ld_rank]
+  const double *pop = nullptr;               // population snapshot [rank][d][ld_rank] as gathered
   int pop_ranks = 0, pop_per_rank = 0;
   int64_t pop_ld = 0;
+  // the snapshot the proposal kernel reads: one contiguous d-vector per member, [rank * per_rank + i][d].  A DE-MC
+  // proposal gathers ~d/2 coordinates of two random members: in the gathered SoA block every one of them is its own
+  // DRAM access (ncu, profiles/r2_ncu_k2.txt: 28 GB moved for 5.5 GB of algorithmic bytes at 2^22 chains, the
+  // DRAM pipe 75 % busy), in a member-major row they share three 128-byte lines
+  double *pop_aos = nullptr;
+  int64_t pop_aos_cap = 0;
   double *draws = nullptr, *draws_lp = nullptr;  // [capacity][d][ld], [capacity][ld]
   int thin = 0, capacity = 0, kept = 0;
   int adapt = 0;
@@ -166,8 +172,9 @@ k_accept_propose(int d, int64_t n, int64_t ld, int kind, uint64_t seed, int64_t 
     uint32_t a = (uint32_t)(((uint64_t)r[0] * tot) >> 32);
     uint32_t b = (uint32_t)(((uint64_t)r[1] * (tot - 1)) >> 32);
     if (b >= a) b += 1;  // two distinct members of the snapshot
-    z1 = pop + ((int64_t)(a / per_rank) * d) * pop_ld + first + (a % per_rank);
-    z2 = pop + ((int64_t)(b / per_rank) * d) * pop_ld + first + (b % per_rank);
+    // member-major snapshot (k_pop_to_aos): member = rank * pop_per_rank + chain within the rank
+    z1 = pop + ((int64_t)(a / per_rank) * pop_per_rank + first + (a % per_rank)) * d;
+    z2 = pop + ((int64_t)(b / per_rank) * pop_per_rank + first + (b % per_rank)) * d;
   }
   // Subspace (crossover) updates, as in DREAM (Vrugt et al. 2009): a DE-MC proposal moves only a random subset
   // of the coordinates, each chosen with probability CR in {0.1, 0.25, 0.5, 1} (one of the four per proposal,
@@ -212,7 +219,7 @@ k_accept_propose(int d, int64_t n, int64_t ld, int kind, uint64_t seed, int64_t 
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const bool mv = ((g >> q) & 1u) && p0 + q < d;
-        const double a = mv ? z1[(int64_t)(p0 + q) * pop_ld] : 0.0, b = mv ? z2[(int64_t)(p0 + q) * pop_ld] : 0.0;
+        const double a = mv ? z1[p0 + q] : 0.0, b = mv ? z2[p0 + q] : 0.0;
         dz[q] = a - b;
       }
       double z[4] = {0.0, 0.0, 0.0, 0.0};
@@ -357,6 +364,22 @@ __global__ void k_fill_const(int64_t n, double v, double *__restrict__ out) {
   if (i < n) out[i] = v;
 }
 
+// snapshot [rank][d][ld] -> member-major [rank * per_rank + i][d]: 32 members per block through a shared-memory tile
+// (coalesced reads along the chains, coalesced writes along the parameters)
+__global__ void __launch_bounds__(256) k_pop_to_aos(const double *__restrict__ pop, int per_rank, int64_t ld, int d,
+                                                    double *__restrict__ out) {
+  __shared__ double tile[EPI_MAX_PARAMS][33];
+  const int rank = blockIdx.y, lane = threadIdx.x & 31, row = threadIdx.x >> 5;  // 8 rows of 32 lanes
+  const int i0 = blockIdx.x * 32;
+  const double *src = pop + (int64_t)rank * d * ld;
+  for (int p = row; p < d; p += 8)
+    if (i0 + lane < per_rank) tile[p][lane] = src[(int64_t)p * ld + i0 + lane];
+  __syncthreads();
+  const int nm = min(32, per_rank - i0);
+  double *dst = out + ((int64_t)rank * per_rank + i0) * d;
+  for (int k = threadIdx.x; k < nm * d; k += 256) dst[k] = tile[k % d][k / d];
+}
+
 // population covariance of the chains of this rank: one block per (p, q), q <= p
 __global__ void __launch_bounds__(256) k_cov(const double *__restrict__ cur_all, int64_t n, int64_t ld, int d,
                                              double *__restrict__ cov_all) {
@@ -448,7 +471,7 @@ void epi_sampler_free(epi_handle *h) {
   SamplerState *s = h->sampler;
   if (!s) return;
   cudaFree(s->cur); cudaFree(s->prop); cudaFree(s->logl); cudaFree(s->logp); cudaFree(s->logl_p); cudaFree(s->logp_p);
-  cudaFree(s->status_p); cudaFree(s->lscale); cudaFree(s->psd); cudaFree(s->cov); cudaFree(s->chol); cudaFree(s->beta_rung); cudaFree(s->swaps); cudaFree(s->acc); cudaFree(s->pop_own); cudaFree(s->draws); cudaFree(s->draws_lp); cudaFree(s->bw);
+  cudaFree(s->status_p); cudaFree(s->lscale); cudaFree(s->psd); cudaFree(s->cov); cudaFree(s->chol); cudaFree(s->beta_rung); cudaFree(s->swaps); cudaFree(s->acc); cudaFree(s->pop_own); cudaFree(s->pop_aos); cudaFree(s->draws); cudaFree(s->draws_lp); cudaFree(s->bw);
   delete s;
   h->sampler = nullptr;
 }
@@ -497,6 +520,25 @@ static int update_shape(epi_handle *h, SamplerState *s) {
   return EPI_OK;
 }
 
+// (re)build the member-major snapshot the proposal kernel reads from the gathered one (s->pop)
+static int install_population(epi_handle *h, SamplerState *s) {
+  const int d = h->M.d;
+  const int64_t need = (int64_t)s->pop_ranks * s->pop_per_rank * d;
+  if (need > s->pop_aos_cap) {
+    CUDA_OK(h, cudaStreamSynchronize(h->stream));
+    cudaFree(s->pop_aos);
+    s->pop_aos = nullptr; s->pop_aos_cap = 0;
+    CUDA_OK(h, cudaMalloc(&s->pop_aos, sizeof(double) * (size_t)need));
+    s->pop_aos_cap = need;
+  }
+  k_pop_to_aos<<<dim3((unsigned)((s->pop_per_rank + 31) / 32), (unsigned)s->pop_ranks), 256, 0, h->stream>>>(
+      s->pop, s->pop_per_rank, s->pop_ld, d, s->pop_aos);
+  h->launches += 1;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return epi_fail(h, EPI_ERR_CUDA, "k_pop_to_aos: %s", cudaGetErrorString(e));
+  return EPI_OK;
+}
+
 // accept / propose for the chains [first, first + cnt) at iteration `iter` on `stream` (cnt < 0: all chains, the
 // sampler's current iteration, the handle's stream).  The Philox counters carry the chain id, so a slice draws what
 // the whole population would have drawn for its chains.
@@ -510,7 +552,7 @@ static int launch_ap(epi_handle *h, SamplerState *s, int do_accept, double *draw
       s->n_rungs > 1 ? s->beta_rung : nullptr, s->cpr, s->cfg.scale,
       s->cfg.de_eps, s->cfg.reserved, h->M.box_min, h->M.box_max, s->cur + first, s->prop + first, s->logl + first, s->logp + first,
       s->logl_p + first, s->logp_p + first, s->status_p + first,
-      s->lscale + first, s->adapt, s->adapt_target, s->acc, s->pop, s->pop_ranks, s->pop_per_rank, s->pop_ld,
+      s->lscale + first, s->adapt, s->adapt_target, s->acc, s->pop ? s->pop_aos : nullptr, s->pop_ranks, s->pop_per_rank, s->pop_ld,
       s->psd_ready ? s->psd : nullptr, (s->psd_ready && s->cfg.kind == EPI_SAMPLER_RWM) ? s->chol : nullptr,
       draw_out ? draw_out + first : nullptr, draw_lp ? draw_lp + first : nullptr);
   h->launches += 1;
@@ -626,6 +668,7 @@ extern "C" int epi_sampler_init(epi_handle *h, const epi_sampler_cfg *cfg, const
     INIT_OK(h, cudaMalloc(&s->pop_own, mat));
     INIT_OK(h, cudaMemcpyAsync(s->pop_own, s->cur, mat, cudaMemcpyDeviceToDevice, h->stream));
     s->pop = s->pop_own; s->pop_ranks = 1; s->pop_per_rank = (int)n; s->pop_ld = s->ld;
+    if ((rc = install_population(h, s))) { epi_sampler_free(h); return rc; }
   }
   s->iter = 0;
   if (cfg->kind == EPI_SAMPLER_DRJ) {
@@ -821,12 +864,13 @@ extern "C" int epi_sampler_set_population(epi_handle *h, const double *d_pop, in
     CUDA_OK(h, cudaSetDevice(h->device));
     CUDA_OK(h, cudaMemcpyAsync(s->pop_own, s->cur, sizeof(double) * (size_t)(h->M.d * s->ld), cudaMemcpyDeviceToDevice, h->stream));
     s->pop = s->pop_own; s->pop_ranks = 1; s->pop_per_rank = s->cfg.n_chains; s->pop_ld = s->ld;
-    return EPI_OK;
+    return install_population(h, s);
   }
   if (n_ranks < 1 || chains_per_rank < 1 || (int64_t)n_ranks * chains_per_rank < 3 || ld_rank < chains_per_rank)
     return epi_fail(h, EPI_ERR_ARG, "bad population shape");
   s->pop = d_pop; s->pop_ranks = n_ranks; s->pop_per_rank = chains_per_rank; s->pop_ld = ld_rank;
-  return EPI_OK;
+  CUDA_OK(h, cudaSetDevice(h->device));
+  return install_population(h, s);
 }
 
 extern "C" int epi_sampler_get(epi_handle *h, double *theta, double *logl, double *logp) {
@@ -982,7 +1026,7 @@ extern "C" int epi_k2_bench(epi_handle *h, int32_t kind, int64_t n_chains, int32
   const unsigned gv = (unsigned)((ld + 255) / 256);
   k_fill_uniform<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(d, n, ld, 99, h->M.box_min, h->M.box_max, cur);
   K2_OK(cudaMemcpyAsync(prop, cur, mat, cudaMemcpyDeviceToDevice, h->stream));
-  if (pop) K2_OK(cudaMemcpyAsync(pop, cur, mat, cudaMemcpyDeviceToDevice, h->stream));
+  if (pop) k_pop_to_aos<<<dim3((unsigned)((n + 31) / 32), 1), 256, 0, h->stream>>>(cur, (int)n, ld, d, pop);  // member-major snapshot
   if (bw) k_fill_const<<<(unsigned)(((int64_t)d * ld + 255) / 256), 256, 0, h->stream>>>((int64_t)d * ld, 0.05, bw);
   k_fill_const<<<gv, 256, 0, h->stream>>>(ld, 0.0, v[0]);
   k_fill_const<<<gv, 256, 0, h->stream>>>(ld, 0.0, v[1]);

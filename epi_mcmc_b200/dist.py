@@ -29,7 +29,8 @@ def shard(n_total: int, rank: int, world: int):
 
 def partner_address(z: int, chains_per_rank: int, d: int, ld_rank: int, p: int) -> int:
     """offset (in doubles) of parameter p of population member z inside the gathered buffer
-    [rank][d][ld_rank] — the addressing k_accept_propose uses (csrc/epi_sampler.cu)."""
+    [rank][d][ld_rank] — the addressing k_pop_to_aos reads when it turns the gathered block into the member-major
+    snapshot the proposal kernel draws partners from (csrc/epi_sampler.cu)."""
     return ((z // chains_per_rank) * d + p) * ld_rank + (z % chains_per_rank)
 
 

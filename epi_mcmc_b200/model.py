@@ -60,11 +60,16 @@ class Model:
         self.init = init
         # df_params: data.frame(name, min, max, init), model-age-groups2q.R:637-663
         self.df_params = {"name": list(self.fit_paramnames), "min": mn, "max": mx, "init": init.copy()}
-        self.is_age = self.flavour in ("age2q", "age2i")
+        self.is_age = self.flavour in ("age2q", "age2i", "age2x")
         self.series_names_ext = AGE_SERIES_EXT if self.is_age else SIMPLE_SERIES_EXT
         if self.flavour == "age2q":  # model-age-groups2q.R:619-622
             self.keyparamnames = ["betay6", "betao6", "betayo6", "betay7", "betao7", "betayo7",
                                   "fy9", "fo9", "fyo9", "ifrred"]
+            self.fitkeyparamnames = list(self.keyparamnames)
+            self.series_names = AGE_SERIES
+        elif self.flavour == "age2x":  # model-age-groups2x.R:699-703
+            self.keyparamnames = ["betay6", "betao6", "betayo6", "betay7", "betao7", "betayo7",
+                                  "betay9", "betao9", "betayo9", "ifrred"]
             self.fitkeyparamnames = list(self.keyparamnames)
             self.series_names = AGE_SERIES
         elif self.flavour == "age2i":  # model-age-groups2i.R:550-551
@@ -111,6 +116,10 @@ class Model:
             for k in ("0", "1", "2", "4") + (("6",) if self.flavour == "age2i" else ()):
                 for g, pre in (("y", "betay"), ("o", "betao"), ("yo", "betayo")):
                     p[f"{g}.Rt{k}"] = np.asarray(p[pre + k]) / gamma
+            if self.flavour == "age2x":  # model-age-groups2x.R:407-409
+                p["y.ld2"] = np.asarray(p["betay11"]) / np.asarray(p["betay9"])
+                p["o.ld2"] = np.asarray(p["betao11"]) / np.asarray(p["betao9"])
+                p["yo.ld2"] = np.asarray(p["betayo11"]) / np.asarray(p["betayo9"])
             if self.flavour == "age2i":  # :342-349
                 p["betay7"] = np.asarray(p["betay6"]) * np.asarray(p["fy7"])
                 p["betao7"] = np.asarray(p["betao6"]) * np.asarray(p["fo7"])

@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define EPI_ABI_VERSION 1
+#define EPI_ABI_VERSION 2
 
 /* ---- model flavours ------------------------------------------------------- */
 /* simple 1-population SEIR, 8 parameters (R/models/model-simple-ode-drj-cmp.R) */
@@ -50,8 +50,14 @@ extern "C" {
  * pass 1 over the whole period (R/models/model-age-groups2i.R + model-agef.cpp,
  * analyses/be/age/settings.R)                                                 */
 #define EPI_FLAVOUR_AGE2I 3
+/* two-age-group SEEIRS, later generation: 52 parameters, waning immunity (eta), effective-susceptible cap of the
+ * younger group, 13-breakpoint schedule, the observation series are convolutions of the infection INCIDENCE that
+ * derivs() reports as an output variable (not differences of N - filter(S)), a symptomatic-testing factor window
+ * on the case series and two more "last 8 days" likelihood terms (R/models/model-age-groups2x.R + model-ager.cpp;
+ * no analyses/ settings file of the snapshot points at this generation: its extra globals are epi_data members) */
+#define EPI_FLAVOUR_AGE2X 4
 
-#define EPI_MAX_PARAMS 48
+#define EPI_MAX_PARAMS 56
 /* widest latency profile supported: in-box maximum is 6*9+1 = 55 taps
  * (R/models/model-age-groups2q.R:22-23,656) */
 #define EPI_MAX_TAPS 64
@@ -143,6 +149,8 @@ typedef struct epi_model_desc {
  *   g, gtrimp, o_wdmorti, d6, d8, d_reliable_hosp, d_hosp_o1/o2, hosp_nbinom_size1/2, hosp_last7;
  *   the settings' case_nbinom_size2 goes into BOTH case_nbinom_sizey2 and case_nbinom_sizeo2,
  *   hosp_nbinom_size and mort_nbinom_size are the scalar sizes of :496-523
+ * age-2x (R/models/model-age-groups2x.R): as age-2q plus d9, d10, d12, duncertain, d_symp_cases, d_all_cases,
+ *   symp_cases_factor (its settings file is not in the snapshot)
  */
 typedef struct epi_data {
   double N, y_N, o_N;
@@ -161,6 +169,10 @@ typedef struct epi_data {
   double hosp_nbinom_size, mort_nbinom_size;
   double case_nbinom_size1, case_nbinom_sizey2, case_nbinom_sizeo2;
   double hosp_nbinom_size1, hosp_nbinom_size2, hosp_last7;
+  /* age-2x only (R/models/model-age-groups2x.R:216-221,278-279,734,749): d9, d10, d12, duncertain,
+   * d.symp.cases, d.all.cases, symp.cases.factor */
+  int32_t d9, d10, d12, duncertain, d_symp_cases, d_all_cases;
+  double symp_cases_factor;
 } epi_data;
 
 /* ---- lifecycle ------------------------------------------------------------ */

@@ -222,8 +222,8 @@ static void convolute(const double *x, int T, int i1, int i2, const profile_t *p
  * (R/models/model-agen.cpp:73-100).  kind[k]: 1 = linear towards k+1, 0 = hold. */
 typedef struct {
   int nbp;
-  double t[12];
-  int kind[12];
+  double t[16];
+  int kind[16];
 } sched_t;
 
 #define SEG_LITERAL (-2) /* choose the segment from t itself, exactly as the reference RHS does */
@@ -245,8 +245,9 @@ static double interpolate(const sched_t *s, int seg, double t, const double *v) 
 typedef struct {
   /* age flavour, R/models/model-agen.cpp:7-51 */
   double Ny, No, a1, a2, gamma;
+  double eta, tuncertain, funcertain; /* model-ager.cpp:12-14 (age-2x only) */
   sched_t s;
-  double by[12], bo[12], byo[12];
+  double by[16], bo[16], byo[16];
   /* simple / Ne flavour (inferred RHS; model-simple-ode-cmp.cpp is absent —
    * parameters from R/models/model-simple-ode-drj-cmp.R:75-78,98-102) */
   double N, a, ldts, ldte, beta0, Tinf0, betat, Tinft;
@@ -289,6 +290,66 @@ static void derivs_age(const rhs_t *p, int seg, double t, const double *y, doubl
   ydot[7] = ogot_latent2 - ogot_infectious;
   ydot[8] = ogot_infectious - ogot_removed;
   ydot[9] = ogot_removed;
+}
+
+/* derivs() of R/models/model-ager.cpp:135-214: waning immunity (eta * R flows back into S), the younger group's
+ * infections run on the effective susceptibles Syeff = max(0, 0.8 Ny - (Ny - Sy)), the three beta curves pass
+ * through uncertain() (:126-132).  yout (optional, 9 values): Re, Rt, y.Re, o.Re, y.i, o.i, betay, betao, betayo. */
+static void derivs_ager(const rhs_t *p, int seg, double t, const double *y, double *ydot, double *yout) {
+  const double Sy = y[0], E1y = y[1], E2y = y[2], Iy = y[3], Ry = y[4];
+  const double So = y[5], E1o = y[6], E2o = y[7], Io = y[8], Ro = y[9];
+  const double Ny = p->Ny, No = p->No;
+  if (Sy < 0 || E1y < 0 || E2y < 0 || Iy < 0 || Ry < 0 || Sy > Ny || E1y > Ny || E2y > Ny ||
+      Iy > Ny || Ry > Ny || So < 0 || E1o < 0 || E2o < 0 || Io < 0 || Ro < 0 || So > No ||
+      E1o > No || E2o > No || Io > No || Ro > No) {
+    if (ydot) for (int i = 0; i < 10; ++i) ydot[i] = 0;
+    if (yout) for (int i = 0; i < 9; ++i) yout[i] = NA_REAL; /* left stale by the reference: reported as NA */
+    return;
+  }
+  const double mbetay = interpolate(&p->s, seg, t, p->by);
+  const double mbetao = interpolate(&p->s, seg, t, p->bo);
+  const double mbetayo = interpolate(&p->s, seg, t, p->byo);
+  const double betay = t > p->tuncertain ? mbetay * p->funcertain : mbetay;
+  const double betao = t > p->tuncertain ? mbetao * p->funcertain : mbetao;
+  const double betayo = t > p->tuncertain ? mbetayo * p->funcertain : mbetayo;
+
+  const double Syeff = fmax(0.0, Ny * 0.8 - (Ny - Sy));
+
+  const double ygot_infected = (betay * Iy) / Ny * Syeff;
+  const double ygot_latent2 = p->a1 * E1y;
+  const double ygot_infectious = p->a2 * E2y;
+  const double ygot_removed = p->gamma * Iy;
+  const double ygot_reverted = p->eta * Ry;
+
+  const double ogot_infected = ((betao * Io) / No + (betayo * Iy) / Ny) * So;
+  const double ogot_latent2 = p->a1 * E1o;
+  const double ogot_infectious = p->a2 * E2o;
+  const double ogot_removed = p->gamma * Io;
+  const double ogot_reverted = p->eta * Ro;
+
+  if (ydot) {
+    ydot[0] = -ygot_infected + ygot_reverted;
+    ydot[1] = ygot_infected - ygot_latent2;
+    ydot[2] = ygot_latent2 - ygot_infectious;
+    ydot[3] = ygot_infectious - ygot_removed;
+    ydot[4] = ygot_removed - ygot_reverted;
+    ydot[5] = -ogot_infected + ogot_reverted;
+    ydot[6] = ogot_infected - ogot_latent2;
+    ydot[7] = ogot_latent2 - ogot_infectious;
+    ydot[8] = ogot_infectious - ogot_removed;
+    ydot[9] = ogot_removed - ogot_reverted;
+  }
+  if (yout) {
+    yout[0] = 1 / p->gamma * (ygot_infected + ogot_infected) / (Iy + Io);
+    yout[1] = yout[0] * (Ny + No) / (Sy + So);
+    yout[2] = 1 / p->gamma * ((betay * Iy) / Ny * Sy + (betayo * Iy) / Ny * So) / Iy;
+    yout[3] = 1 / p->gamma * (betao * Io) / No * So / Io;
+    yout[4] = ygot_infected;
+    yout[5] = ogot_infected;
+    yout[6] = betay;
+    yout[7] = betao;
+    yout[8] = betayo;
+  }
 }
 
 /* Simple-flavour derivs.  INFERRED: model-simple-ode-cmp.cpp is not in the
@@ -337,7 +398,9 @@ static void derivs_simple(const rhs_t *p, int seg, double t, const double *y, do
 static void jitter_rows(double *out, int nday, int neq);
 
 static void derivs(const rhs_t *p, int neq, int seg, double t, const double *y, double *ydot) {
-  if (neq == 10)
+  if (neq == 10 && p->flavour == EPI_FLAVOUR_AGE2X)
+    derivs_ager(p, seg, t, y, ydot, 0);
+  else if (neq == 10)
     derivs_age(p, seg, t, y, ydot);
   else
     derivs_simple(p, seg, t, y, ydot);
@@ -420,10 +483,139 @@ static void yout_rows(const rhs_t *p, int neq, const double *out, int t0, int nd
  *
  * State is reported at the integer times.  out is row-major [nday][neq], row
  * 0 = Y0 at t = t0. */
+/* ---- mirrored arithmetic (tests only) -------------------------------------------------------------
+ * oracle_set_mirror(1) makes ode_rk4 evaluate the SAME scheme with the operation order and the explicit fused
+ * multiply-adds of the CUDA kernels (epi_mcmc_b200/csrc/epi_kernels.cu: rhs<>, rk4_try<>, select_segment<>):
+ * curves pre-divided by the population they multiply, beta(t) = fma(t - tk, slope, b), every product-sum a
+ * written-out fma, acc = k1 + 2 k2 + 2 k3 accumulated by fma, y' = fma(h/6, acc + k4, y).  Every operation is
+ * correctly rounded IEEE on both sides, so the ODE states then agree BIT FOR BIT with the GPU and what is left of
+ * a GPU <-> oracle difference comes from the latency profiles and the table-driven logarithms only.  The default
+ * (mirror off) keeps the reference's own operation order, (beta * I) / N * S, which differs from the mirrored one by
+ * a few ulp per stage — amplified by the cancellation in diff(N - filter(S)) where the epidemic has burnt out. */
+static int g_mirror = 0;
+void oracle_set_mirror(int on) { g_mirror = on; }
+
+typedef struct { double tk, b0, b1, b2, s0, s1, s2; } mseg_t;
+
+static int guard_hits(const rhs_t *p, int neq, const double *y) {
+  if (neq == 10) {
+    for (int i = 0; i < 5; ++i) if (y[i] < 0 || y[i] > p->Ny) return 1;
+    for (int i = 5; i < 10; ++i) if (y[i] < 0 || y[i] > p->No) return 1;
+    return 0;
+  }
+  for (int i = 0; i < 4; ++i) if (y[i] < 0 || y[i] > p->N) return 1;
+  return 0;
+}
+
+/* select_segment<> of the kernels: segment k (highest breakpoint <= pa), curves divided by their population */
+static mseg_t mirror_segment(const rhs_t *p, int neq, int k) {
+  mseg_t g;
+  memset(&g, 0, sizeof g);
+  if (neq == 10) {
+    const double inv0 = 1.0 / p->Ny, inv1 = 1.0 / p->No;
+    const int kk = k < 0 ? 0 : k;
+    g.b0 = p->by[kk]; g.b1 = p->bo[kk]; g.b2 = p->byo[kk];
+    if (k >= 0 && p->s.kind[k]) {
+      const double len = p->s.t[k + 1] - p->s.t[k];
+      g.tk = p->s.t[k];
+      g.s0 = (p->by[k + 1] - p->by[k]) / len; g.s1 = (p->bo[k + 1] - p->bo[k]) / len; g.s2 = (p->byo[k + 1] - p->byo[k]) / len;
+    }
+    g.b0 = g.b0 * inv0; g.s0 = g.s0 * inv0;
+    g.b1 = g.b1 * inv1; g.s1 = g.s1 * inv1;
+    g.b2 = g.b2 * inv0; g.s2 = g.s2 * inv0;
+  } else {
+    const double inv0 = 1.0 / (p->flavour == EPI_FLAVOUR_NE ? p->Ne : p->N);
+    if (k < 0) { g.b0 = p->beta0; g.b1 = p->Tinf0; g.b2 = 1.0 / p->Tinf0; }
+    else if (k == 1) { g.b0 = p->betat; g.b1 = p->Tinft; g.b2 = 1.0 / p->Tinft; }
+    else {
+      const double len = p->ldte - p->ldts;
+      g.tk = p->ldts; g.b0 = p->beta0; g.b1 = p->Tinf0; g.b2 = 0.0;
+      g.s0 = (p->betat - p->beta0) / len; g.s1 = (p->Tinft - p->Tinf0) / len;
+      if (g.s1 == 0.0) g.b2 = 1.0 / p->Tinf0;
+    }
+    g.b0 = g.b0 * inv0; g.s0 = g.s0 * inv0;
+  }
+  return g;
+}
+
+static void derivs_mirror(const rhs_t *p, int neq, const mseg_t *g, double t, const double *y, double *dy) {
+  if (guard_hits(p, neq, y)) { /* the reference's guard, model-agen.cpp:109-124 */
+    for (int i = 0; i < neq; ++i) dy[i] = 0;
+    return;
+  }
+  const double dt = t - g->tk;
+  if (neq == 10 && p->flavour == EPI_FLAVOUR_AGE2X) { /* rhs<> of the kernels, ager branch */
+    const double Sy = y[0], E1y = y[1], E2y = y[2], Iy = y[3], Ry = y[4], So = y[5], E1o = y[6], E2o = y[7], Io = y[8], Ro = y[9];
+    const double betay = fma(dt, g->s0, g->b0), betao = fma(dt, g->s1, g->b1), betayo = fma(dt, g->s2, g->b2);
+    const double Syeff = fmax(0.0, p->Ny * 0.8 - (p->Ny - Sy));
+    const double yinf = (betay * Iy) * Syeff;
+    const double oinf = fma(betao, Io, betayo * Iy) * So;
+    const double yrev = p->eta * Ry, orev = p->eta * Ro;
+    dy[0] = yrev - yinf;
+    dy[1] = fma(-p->a1, E1y, yinf);
+    dy[2] = fma(p->a1, E1y, -E2y);
+    dy[3] = fma(-p->gamma, Iy, E2y);
+    dy[4] = fma(p->gamma, Iy, -yrev);
+    dy[5] = orev - oinf;
+    dy[6] = fma(-p->a1, E1o, oinf);
+    dy[7] = fma(p->a1, E1o, -E2o);
+    dy[8] = fma(-p->gamma, Io, E2o);
+    dy[9] = fma(p->gamma, Io, -orev);
+  } else if (neq == 10) {
+    const double Sy = y[0], E1y = y[1], E2y = y[2], Iy = y[3], So = y[5], E1o = y[6], E2o = y[7], Io = y[8];
+    const double betay = fma(dt, g->s0, g->b0), betao = fma(dt, g->s1, g->b1), betayo = fma(dt, g->s2, g->b2);
+    const double yinf = (betay * Iy) * Sy;
+    const double oinf = fma(betao, Io, betayo * Iy) * So;
+    dy[0] = -yinf;
+    dy[1] = fma(-p->a1, E1y, yinf);
+    dy[2] = fma(p->a1, E1y, -E2y);
+    dy[3] = fma(-p->gamma, Iy, E2y);
+    dy[4] = p->gamma * Iy;
+    dy[5] = -oinf;
+    dy[6] = fma(-p->a1, E1o, oinf);
+    dy[7] = fma(p->a1, E1o, -E2o);
+    dy[8] = fma(-p->gamma, Io, E2o);
+    dy[9] = p->gamma * Io;
+  } else {
+    const double S = y[0], E = y[1], I = y[2];
+    const double beta = fma(dt, g->s0, g->b0);
+    const double rT = g->s1 == 0.0 ? g->b2 : 1.0 / fma(dt, g->s1, g->b1);
+    double inf;
+    if (p->flavour == EPI_FLAVOUR_NE) {
+      const double Seff = fmax(0.0, p->Ne - (p->N - S));
+      inf = (beta * I) * Seff;
+    } else {
+      inf = (beta * I) * S;
+    }
+    const double ir = I * rT;
+    dy[0] = -inf;
+    dy[1] = fma(-p->a, E, inf);
+    dy[2] = fma(p->a, E, -ir);
+    dy[3] = ir;
+  }
+}
+
+/* one RK4 piece [pa, pb] in the kernels' arithmetic (rk4_try<>); hh2 / h6 are passed in because a regular sub-step
+ * uses the kernel constants 0.5 * h and h / 6 */
+static void rk4_piece_mirror(const rhs_t *p, int neq, int seg, double *y, double pa, double pb, double hh, double hh2,
+                             double h6) {
+  const mseg_t g = mirror_segment(p, neq, seg);
+  const double tm = pa + hh2;
+  double k[10], acc[10], yt[10];
+  derivs_mirror(p, neq, &g, pa, y, k);
+  for (int i = 0; i < neq; ++i) { acc[i] = k[i]; yt[i] = fma(hh2, k[i], y[i]); }
+  derivs_mirror(p, neq, &g, tm, yt, k);
+  for (int i = 0; i < neq; ++i) { acc[i] = fma(2.0, k[i], acc[i]); yt[i] = fma(hh2, k[i], y[i]); }
+  derivs_mirror(p, neq, &g, tm, yt, k);
+  for (int i = 0; i < neq; ++i) { acc[i] = fma(2.0, k[i], acc[i]); yt[i] = fma(hh, k[i], y[i]); }
+  derivs_mirror(p, neq, &g, pb, yt, k);
+  for (int i = 0; i < neq; ++i) y[i] = fma(h6, acc[i] + k[i], y[i]);
+}
+
 static void ode_rk4(const rhs_t *p, int neq, const double *Y0, int t0, int nday, int m, double *out) {
   double y[10], k1[10], k2[10], k3[10], k4[10], yt[10];
   const double h = 1.0 / (double)m;
-  double brk[12];
+  double brk[16];
   int nb;
   if (neq == 10) {
     nb = p->s.nbp;
@@ -449,6 +641,12 @@ static void ode_rk4(const rhs_t *p, int neq, const double *Y0, int t0, int nday,
         const double hh = pb - pa;
         const double tm = pa + 0.5 * hh;
         const int seg = neq == 10 ? active_segment(&p->s, tm) : (tm > p->ldte ? 1 : tm > p->ldts ? 0 : -1);
+        if (g_mirror) {
+          rk4_piece_mirror(p, neq, seg, y, pa, pb, hh, 0.5 * hh, hh / 6.0);
+          if (pb >= b) break;
+          pa = pb;
+          continue;
+        }
         derivs(p, neq, seg, pa, y, k1);
         for (int i = 0; i < neq; ++i) yt[i] = y[i] + 0.5 * hh * k1[i];
         derivs(p, neq, seg, tm, yt, k2);
@@ -530,6 +728,26 @@ void oracle_yout_age(const double *parms45, double t, const double *y, double *y
     p.by[k] = parms45[b]; p.bo[k] = parms45[b + 1]; p.byo[k] = parms45[b + 2];
   }
   yout_age(&p, t, y, yout);
+}
+
+/* the restated ager RHS on the reference's own 60-element parms vector (R/models/model-ager.cpp:4-66): ydot[10] and
+ * the nout = 9 output variables */
+void oracle_derivs_ager(const double *parms60, double t, const double *y, double *ydot, double *yout9) {
+  rhs_t p;
+  memset(&p, 0, sizeof p);
+  p.flavour = EPI_FLAVOUR_AGE2X;
+  p.Ny = parms60[0]; p.No = parms60[1]; p.a1 = parms60[2]; p.a2 = parms60[3]; p.gamma = parms60[4];
+  p.eta = parms60[5]; p.tuncertain = parms60[6]; p.funcertain = parms60[7];
+  p.s.nbp = 13;
+  static const int kind[13] = {1, 1, 1, 1, 0, 0, 0, 0, 1, 0, 1, 1, 0};
+  for (int k = 0; k < 13; ++k) {
+    p.s.kind[k] = kind[k];
+    const int ti = k < 3 ? 8 + k : 20 + 4 * (k - 3);
+    const int b = k < 3 ? 11 + 3 * k : ti + 1;
+    p.s.t[k] = parms60[ti];
+    p.by[k] = parms60[b]; p.bo[k] = parms60[b + 1]; p.byo[k] = parms60[b + 2];
+  }
+  derivs_ager(&p, SEG_LITERAL, t, y, ydot, yout9);
 }
 
 /* same for the 8-breakpoint schedule of R/models/model-agef.cpp:7-43,66-87 (parms[37]):
@@ -1251,6 +1469,371 @@ static void age2i_df_params(const epi_data *D, double *mn, double *mx, double *i
   for (int i = 0; i < 36; ++i) { mn[i] = mn_[i]; mx[i] = mx_[i]; init[i] = i_[i]; }
 }
 
+/* ------------------------------------------------------------ age-2x ------ */
+/* R/models/model-age-groups2x.R + model-ager.cpp: the later generation of the two-group model (params 1-based, 52).
+ * State series: yS/oS keep S (for calculateModel's fields), yI/oI hold the infection incidence y.i / o.i that
+ * derivs() reports as output variables 5 and 6 — the series every observation model convolves here. */
+typedef struct {
+  age_state_t a;
+  double *yi, *oi; /* length T, 0 before padding + 1 (:156-157) */
+  int unsupported;  /* the symptomatic-testing window would start beyond the simulated period (vector growth in R) */
+} age2x_state_t;
+
+static void age2x_state_free(age2x_state_t *s) {
+  free(s->yi); free(s->oi);
+  age_state_free(&s->a);
+  memset(s, 0, sizeof *s);
+}
+
+static void age2x_betas(const double *params, double *by, double *bo, double *byo) {
+  /* :56-119 */
+  by[0] = params[1]; bo[0] = params[2]; byo[0] = params[3];
+  by[1] = params[4]; bo[1] = params[5]; byo[1] = params[6];
+  by[2] = params[7]; bo[2] = params[8]; byo[2] = params[9];
+  by[3] = params[25]; bo[3] = params[26]; byo[3] = params[27];
+  by[4] = params[29]; bo[4] = params[30]; byo[4] = params[31];
+  by[5] = params[32]; bo[5] = params[33]; byo[5] = params[34];
+  by[6] = params[36]; bo[6] = params[37]; byo[6] = params[38];
+  by[7] = params[40]; bo[7] = params[41]; byo[7] = params[42];
+  by[8] = by[7]; bo[8] = bo[7]; byo[8] = byo[7];
+  by[9] = params[43]; bo[9] = params[44]; byo[9] = params[45];
+  by[10] = by[9]; bo[10] = bo[9]; byo[10] = byo[9];
+  by[11] = params[50]; bo[11] = params[51]; byo[11] = params[52];
+  by[12] = by[9]; bo[12] = bo[9]; byo[12] = byo[9];
+}
+
+/* R's cumsum: LDOUBLE accumulator, NA propagates from the first NA on */
+static void cumsum_r(const double *x, int n, double *out /*1-based*/) {
+  long double acc = 0;
+  for (int i = 1; i <= n; ++i) {
+    acc += x[i];
+    out[i] = (double)acc;
+  }
+}
+
+static int age2x_calculate_model(const epi_data *D, const double *params, int period, int m, age2x_state_t *sx) {
+  memset(sx, 0, sizeof *sx);
+  age_state_t *st = &sx->a;
+  const double y_N = D->y_N, o_N = D->o_N;
+  const double y_died_rate = D->y_ifr[0], o_died_rate = D->o_ifr[0]; /* :14-15 */
+  const double a1 = 1 / TINC1, a2 = 1 / TINC2, gamma = oracle_age_gamma();
+  const double eta = 1 / (0.75 * 356); /* :19 (sic: 356) */
+  const double CLsd = 2.5;             /* :20 */
+
+  double betay[14], betao[14], betayo[14];
+  age2x_betas(params, betay, betao, betayo);
+  const double ycase_rate = params[10], yhosp_rate = params[11], yhosp_latency = params[12],
+               ydied_latency = params[13], ocase_rate = params[14], ohosp_rate = params[15],
+               ohosp_latency = params[16], odied_latency = params[17], t0_morts = params[18],
+               t0o = params[19], HLsd = params[20], DLsd = params[21], fyifr = params[22],
+               fyhr = params[23], t3o = params[24], t4o = params[28], t6o = params[35], t7o = params[39],
+               ifrred = params[46], ycase_latency = params[47], ocase_latency = params[48], t10o = params[49];
+
+  /* :123-128 */
+  profile_t ycase, ocase, yhosp, ohosp, ydied, odied;
+  if (calc_gamma_profile(ycase_latency, CLsd, &ycase) || calc_gamma_profile(ocase_latency, CLsd, &ocase) ||
+      calc_gamma_profile(yhosp_latency, HLsd, &yhosp) || calc_gamma_profile(ohosp_latency, HLsd, &ohosp) ||
+      calc_gamma_profile(ydied_latency, DLsd, &ydied) || calc_gamma_profile(odied_latency, DLsd, &odied))
+    return -1;
+  /* :130-131 */
+  int padding = -ycase.kbegin;
+  if (-ydied.kbegin > padding) padding = -ydied.kbegin;
+  if (-ocase.kbegin > padding) padding = -ocase.kbegin;
+  if (-odied.kbegin > padding) padding = -odied.kbegin;
+  padding += 1;
+
+  const int P = period, T = padding + period;
+  st->pad = padding; st->T = T; st->P = P;
+  st->yS = vec(T, y_N - INITIAL); st->oS = vec(T, o_N);
+  st->ycasei = vec(T, 0); st->ocasei = vec(T, 0);
+  st->yhospi = vec(T, 0); st->ohospi = vec(T, 0);
+  st->ydeadi = vec(T, 0); st->odeadi = vec(T, 0);
+  sx->yi = vec(T, 0); sx->oi = vec(T, 0); /* :156-157 */
+
+  /* :162-181 */
+  rhs_t rp;
+  memset(&rp, 0, sizeof rp);
+  rp.flavour = EPI_FLAVOUR_AGE2X;
+  rp.Ny = y_N; rp.No = o_N; rp.a1 = a1; rp.a2 = a2; rp.gamma = gamma; rp.eta = eta;
+  rp.tuncertain = 1E10; rp.funcertain = 1;
+  rp.s.nbp = 13;
+  static const int kind[13] = {1, 1, 1, 1, 0, 0, 0, 0, 1, 0, 1, 1, 0}; /* model-ager.cpp:88-124 */
+  for (int k = 0; k < 13; ++k) {
+    rp.s.kind[k] = kind[k];
+    rp.s.t[k] = 1E10;
+    rp.by[k] = betay[k]; rp.bo[k] = betao[k]; rp.byo[k] = betayo[k];
+  }
+  const double Y[10] = {y_N - INITIAL, INITIAL, 0, 0, 0, o_N, 0, 0, 0, 0};
+
+  /* pass 1, :183-203 */
+  const int period1 = 60;
+  const int rows_max = P > period1 ? P : period1;
+  double *out = (double *)malloc(sizeof(double) * 10 * (size_t)rows_max);
+  double *yo9 = (double *)malloc(sizeof(double) * 9 * (size_t)rows_max);
+  int out_rows = period1;
+  ode_rk4(&rp, 10, Y, padding + 1, period1, m, out);
+  for (int i = 0; i < period1; ++i) derivs_ager(&rp, SEG_LITERAL, (double)(padding + 1 + i), out + (size_t)i * 10, 0, yo9 + (size_t)i * 9);
+  const int T1 = (T > padding + period1) ? T : padding + period1; /* assignment may grow the vector */
+  double *yi1 = vec(T1, 0), *oi1 = vec(T1, 0);
+  for (int i = 1; i <= period1; ++i) {
+    yi1[padding + i] = yo9[(size_t)(i - 1) * 9 + 4];
+    oi1[padding + i] = yo9[(size_t)(i - 1) * 9 + 5];
+  }
+  double *s2 = vec(rows_max, 0), *s2b = vec(period1, 0), *cy = vec(period1, 0), *co = vec(period1, 0);
+  convolute(yi1, T1, padding + 1, padding + period1, &ydied, s2);
+  convolute(oi1, T1, padding + 1, padding + period1, &odied, s2b);
+  for (int i = 1; i <= period1; ++i) { s2[i] = s2[i] * y_died_rate; s2b[i] = s2b[i] * o_died_rate; }
+  cumsum_r(s2, period1, cy);  /* :194-195 */
+  cumsum_r(s2b, period1, co); /* :197-198 */
+  double data_offset = EPI_INVALID_DATA_OFFSET; /* :202 */
+  int lds1 = 0;
+  for (int i = 1; i <= period1; ++i) { /* which(state$died > t0_morts), :204 (NA before padding + 1) */
+    const double died = cy[i] + co[i];
+    if (died > t0_morts) { lds1 = padding + i; break; }
+  }
+  free(yi1); free(oi1); free(s2b); free(cy); free(co);
+
+  const int lo = D->lockdown_offset, ltp = D->lockdown_transition_period;
+  if (lds1 > 0) { /* :205-250 */
+    data_offset = lds1 - lo;
+    const double t2 = data_offset + lo + ltp;
+    const double t3 = t2 + t3o;
+    const double t4 = t3 + t4o;
+    const double t5 = data_offset + D->d5;
+    const double t6 = t5 + t6o;
+    const double t7 = t6 + t7o;
+    const double t8 = data_offset + D->d8;
+    const double t9 = data_offset + D->d9;
+    const double t10 = data_offset + t10o;
+    const double t11 = t10 + 3;
+    const double t12 = data_offset + D->d12;
+    rp.tuncertain = data_offset + D->duncertain; /* :220 */
+    rp.funcertain = 1;                           /* :221 */
+    rp.s.t[0] = data_offset + lo + t0o;
+    rp.s.t[1] = data_offset + lo + fmax(t0o, 0);
+    rp.s.t[2] = t2; rp.s.t[3] = t3; rp.s.t[4] = t4; rp.s.t[5] = t5; rp.s.t[6] = t6; rp.s.t[7] = t7;
+    rp.s.t[8] = t8; rp.s.t[9] = t9; rp.s.t[10] = t10; rp.s.t[11] = t11; rp.s.t[12] = t12;
+    ode_rk4(&rp, 10, Y, padding + 1, P, m, out);
+    out_rows = P;
+    for (int i = 0; i < P; ++i) derivs_ager(&rp, SEG_LITERAL, (double)(padding + 1 + i), out + (size_t)i * 10, 0, yo9 + (size_t)i * 9);
+  }
+  /* :253-268 — when pass 2 was skipped the 60-row `out` is recycled into the P-length slices */
+  st->full = (double *)malloc(sizeof(double) * 10 * (size_t)P);
+  st->yout = (double *)malloc(sizeof(double) * 4 * (size_t)P);
+  for (int i = 1; i <= P; ++i) {
+    const size_t r = (size_t)((i - 1) % out_rows);
+    const double *row = out + r * 10;
+    st->yS[padding + i] = row[0];
+    st->oS[padding + i] = row[5];
+    sx->yi[padding + i] = yo9[r * 9 + 4];
+    sx->oi[padding + i] = yo9[r * 9 + 5];
+    memcpy(st->full + (size_t)(i - 1) * 10, row, sizeof(double) * 10);
+    memcpy(st->yout + (size_t)(i - 1) * 4, yo9 + r * 9, sizeof(double) * 4);
+  }
+  free(out); free(yo9);
+
+  /* :270-276 */
+  const int nr = D->n_rate;
+  double *gycr = vec(nr, 0), *gyifr = vec(nr, 0), *gyhr = vec(nr, 0), *gocr = vec(nr, 0),
+         *goifr = vec(nr, 0), *gohr = vec(nr, 0);
+  for (int i = 1; i <= nr; ++i) {
+    const double yifr = D->y_ifr[i - 1], oifr = D->o_ifr[i - 1], yhr = D->y_hr[i - 1],
+                 ohr = D->o_hr[i - 1], g = D->g[i - 1], gt = D->gtrimp[i - 1];
+    gycr[i] = pmin_(1, ycase_rate * yifr * (1 + (fyifr - 1) * g));
+    gyifr[i] = yifr * (1 + (fyifr - 1) * g) * (1 - ifrred * gt);
+    gyhr[i] = yhosp_rate * yhr * (1 + (fyhr - 1) * g);
+    gocr[i] = pmin_(1, ocase_rate * oifr);
+    goifr[i] = oifr * (1 - ifrred * gt);
+    gohr[i] = ohosp_rate * ohr;
+  }
+
+  const int valid = data_offset != EPI_INVALID_DATA_OFFSET;
+  struct {
+    const double *I; const profile_t *prof; double t1; const double *rate; double *dst; int cases;
+  } ser[6] = {
+      /* :281-297 */ {sx->yi, &ycase, data_offset + nearbyint(-ydied_latency + ycase_latency), gycr, st->ycasei, 1},
+      /* :300-312 */ {sx->yi, &yhosp, data_offset + nearbyint(-ydied_latency + yhosp_latency), gyhr, st->yhospi, 0},
+      /* :314-326 */ {sx->yi, &ydied, data_offset, gyifr, st->ydeadi, 0},
+      /* :329-343 */ {sx->oi, &ocase, data_offset + nearbyint(-ydied_latency + ocase_latency), gocr, st->ocasei, 1},
+      /* :346-357 */ {sx->oi, &ohosp, data_offset + nearbyint(-ydied_latency + ohosp_latency), gohr, st->ohospi, 0},
+      /* :359-371 */ {sx->oi, &odied, data_offset, goifr, st->odeadi, 0},
+  };
+  /* :278-279 */
+  const int t_symp = (int)data_offset + D->d_symp_cases, t_all = (int)data_offset + D->d_all_cases - 1;
+  for (int q = 0; q < 6; ++q) {
+    convolute(ser[q].I, T, padding + 1, padding + P, ser[q].prof, s2);
+    rate_map(ser[q].dst, s2, padding, P, valid, ser[q].t1, ser[q].rate, nr);
+    if (valid && ser[q].cases) {
+      /* state$y.casei[t.symp:min(t.all, length)] *= symp.cases.factor (:293-294,340-341); R's a:b counts down when
+       * a > b.  A window that starts beyond the vector would GROW it in R (and move calclogl's windows): flagged
+       * unsupported — the symptomatic-testing window then begins after the simulated period */
+      int a = t_symp, b = t_all < T ? t_all : T;
+      if (a > T || a < 1 || b < 1) { sx->unsupported = 1; continue; }
+      const int lo_ = a < b ? a : b, hi_ = a < b ? b : a;
+      for (int t = lo_; t <= hi_; ++t) ser[q].dst[t] = ser[q].dst[t] * D->symp_cases_factor;
+    }
+  }
+  free(s2);
+  free(gycr); free(gyifr); free(gyhr); free(gocr); free(goifr); free(gohr);
+  st->offset = (int)data_offset;
+  return 0;
+}
+
+/* calclogp(params): R/models/model-age-groups2x.R:427-545 (params 1-based) */
+static double age2x_calclogp(const epi_data *D, const double *params) {
+  double by[14], bo[14], byo[14];
+  age2x_betas(params, by, bo, byo);
+  const double yhosp_rate = params[11], yhosp_latency = params[12], ydied_latency = params[13],
+               ohosp_rate = params[15], ohosp_latency = params[16], odied_latency = params[17],
+               t0o = params[19], HLsd = params[20], DLsd = params[21], fyifr = params[22],
+               t3o = params[24], t4o = params[28], t6o = params[35], t7o = params[39], ifrred = params[46],
+               ycase_latency = params[47], ocase_latency = params[48], t10o = params[49];
+  const double lo = D->lockdown_offset, ltp = D->lockdown_transition_period;
+  double lp = 0;
+  lp = lp + oracle_dnorm_log(t0o, 0, 10);
+  lp = lp + oracle_dnorm_log(lo + ltp + t3o, D->d3, 10);
+  lp = lp + oracle_dnorm_log(lo + ltp + t3o + t4o, D->d4, 10);
+  lp = lp + oracle_dnorm_log(D->d5 + t6o, D->d6, 5);
+  lp = lp + oracle_dnorm_log(D->d5 + t6o + t7o, D->d7 - lo, 2);
+  lp = lp + oracle_dnorm_log(t10o, D->d10, 3);
+  const double SD = log(2), lSD = log(1.3), llSD = log(1.2);
+  lp = lp + oracle_dlnorm_log(by[0] / by[1], 0, llSD);
+  lp = lp + oracle_dlnorm_log(bo[0] / bo[1], 0, llSD);
+  lp = lp + oracle_dlnorm_log(byo[0] / byo[1], 0, llSD);
+  static const int pairs[5][2] = {{1, 2}, {2, 3}, {3, 4}, {5, 6}, {6, 7}};
+  for (int q = 0; q < 5; ++q) {
+    lp = lp + oracle_dlnorm_log(by[pairs[q][0]] / by[pairs[q][1]], 0, SD);
+    lp = lp + oracle_dlnorm_log(bo[pairs[q][0]] / bo[pairs[q][1]], 0, SD);
+    lp = lp + oracle_dlnorm_log(byo[pairs[q][0]] / byo[pairs[q][1]], 0, SD);
+  }
+  lp = lp + oracle_dlnorm_log(by[7] / by[9], log(1.3), lSD);
+  lp = lp + oracle_dlnorm_log(bo[7] / bo[9], log(1.3), lSD);
+  lp = lp + oracle_dlnorm_log(byo[7] / byo[9], log(1.3), lSD);
+  lp = lp + oracle_dlnorm_log(by[9] / by[11], 0, lSD);
+  lp = lp + oracle_dlnorm_log(bo[9] / bo[11], 0, lSD);
+  lp = lp + oracle_dlnorm_log(byo[9] / byo[11], 0, lSD);
+  lp = lp + oracle_dnorm_log(HLsd, 4, 1);
+  lp = lp + oracle_dnorm_log(DLsd, 5, 1);
+  lp = lp + oracle_dnorm_log(ycase_latency, 7, 3);
+  lp = lp + oracle_dnorm_log(ocase_latency, 7, 3);
+  lp = lp + oracle_dnorm_log(yhosp_latency, 13, 1);
+  lp = lp + oracle_dnorm_log(ohosp_latency, 13, 1);
+  lp = lp + oracle_dnorm_log(ydied_latency, 21, 0.5);
+  lp = lp + oracle_dnorm_log(odied_latency, 21, 0.5);
+  lp = lp + oracle_dlnorm_log(fyifr, log(0.6), log(1.5));
+  lp = lp + oracle_dlnorm_log(ifrred, log(0.35), log(1.3));
+  lp = lp + oracle_dlnorm_log(yhosp_rate, 0, lSD);
+  lp = lp + oracle_dlnorm_log(ohosp_rate, 0, lSD);
+  return lp;
+}
+
+/* calclogl(params, x): R/models/model-age-groups2x.R:547-681.  terms[0..5] = y.loglC, o.loglC, loglH, loglHRatio,
+ * y.loglD, o.loglD */
+static double age2x_calclogl(const epi_data *D, const double *params, int period, int m,
+                             double *terms, int *offset_out, int *pad_out, int *status) {
+  age2x_state_t sx;
+  if (age2x_calculate_model(D, params, period, m, &sx)) {
+    *status |= EPI_ST_UNSUPPORTED;
+    for (int i = 0; i < 6; ++i) terms[i] = NA_REAL;
+    *offset_out = 0; *pad_out = 0;
+    return NA_REAL;
+  }
+  const age_state_t *st = &sx.a;
+  *offset_out = st->offset;
+  *pad_out = st->pad;
+  if (sx.unsupported) {
+    *status |= EPI_ST_UNSUPPORTED;
+    for (int i = 0; i < 6; ++i) terms[i] = NA_REAL;
+    age2x_state_free(&sx);
+    return NA_REAL;
+  }
+  int offset = st->offset;
+  if (offset == EPI_INVALID_DATA_OFFSET) { /* :552-553 */
+    offset = 1;
+    *status |= EPI_ST_INVALID_OFFSET;
+  }
+  const int T = st->T;
+  int dstart, dend;
+  const int r = D->d_reliable_cases, rh = D->d_reliable_hosp, nc = D->n_dcasei;
+  double one[2];
+
+  /* cases, :555-590 */
+  window(offset, nc, T, &dstart, &dend);
+  const double *yx = D->y_dcasei - 1, *ox = D->o_dcasei - 1;
+  one[1] = D->case_nbinom_size1;
+  double yC = sum_dnbinom(yx, nc, 1, r - 1, st->ycasei, T, dstart, dstart + r, 0.1, one, 1);
+  double oC = sum_dnbinom(ox, nc, 1, r - 1, st->ocasei, T, dstart, dstart + r, 0.1, one, 1);
+  one[1] = D->case_nbinom_sizey2;
+  yC = yC + sum_dnbinom(yx, nc, r, nc, st->ycasei, T, dstart + r + 1, dend, 0.1, one, 1);
+  one[1] = D->case_nbinom_sizeo2;
+  oC = oC + sum_dnbinom(ox, nc, r, nc, st->ocasei, T, dstart + r + 1, dend, 0.1, one, 1);
+  one[1] = D->case_nbinom_sizeo2 * D->hosp_last7;
+  oC = oC + sum_dnbinom(ox, nc, nc - 7, nc, st->ocasei, T, dend - 7, dend, 0.1, one, 1); /* :586-588 */
+
+  /* hosp, :592-619 */
+  const int nh = D->n_dhospi, nhh = D->n_dhosp;
+  window(offset, nh, T, &dstart, &dend);
+  double *H = vec(T, 0);
+  for (int t = 1; t <= T; ++t) H[t] = st->yhospi[t] + st->ohospi[t];
+  const double *hx = D->dhospi - 1;
+  one[1] = D->hosp_nbinom_size1;
+  double lH = sum_dnbinom(hx, nh, 1, rh - 1, H, T, dstart, dstart + rh, 0.1, one, 1);
+  one[1] = D->hosp_nbinom_size2;
+  lH = lH + sum_dnbinom(hx, nh, rh, nhh, H, T, dstart + rh + 1, dend, 0.1, one, 1);
+  one[1] = D->hosp_nbinom_size2 * D->hosp_last7;
+  lH = lH + sum_dnbinom(hx, nh, nhh - 7, nhh, H, T, dend - 7, dend, 0.1, one, 1);
+  free(H);
+
+  /* :627-630 */
+  long double yt = 0, ot = 0;
+  for (int t = dstart + D->d_hosp_o1; t <= dstart + D->d_hosp_o2; ++t) {
+    yt += at(st->yhospi, T, t);
+    ot += at(st->ohospi, T, t);
+  }
+  const double ytotal = (double)yt, ototal = (double)ot;
+  const double lHR = oracle_dlnorm_log(ytotal / (ytotal + ototal), log(56.7 / 100), log(1.05));
+
+  /* deaths, :633-657 */
+  const int nm = D->n_dmorti;
+  window(offset, nm, T, &dstart, &dend);
+  one[1] = D->mort_nbinom_size * 5;
+  double yD = sum_dnbinom(D->y_dmorti - 1, nm, 1, nm, st->ydeadi, T, dstart, dend, 0.001, one, 1);
+  double *sz = vec(nm, 0);
+  for (int i = 1; i <= nm; ++i) sz[i] = D->o_wdmorti[i - 1] * D->mort_nbinom_size;
+  double oD = sum_dnbinom(D->o_dmorti - 1, nm, 1, nm, st->odeadi, T, dstart, dend, 0.001, sz, nm);
+  free(sz);
+  one[1] = D->mort_nbinom_size * D->hosp_last7;
+  oD = oD + sum_dnbinom(D->o_dmorti - 1, nm, nm - 7, nm, st->odeadi, T, dend - 7, dend, 0.001, one, 1); /* :653-655 */
+
+  terms[0] = yC; terms[1] = oC; terms[2] = lH; terms[3] = lHR; terms[4] = yD; terms[5] = oD;
+  double result = yC + oC + lH + lHR + yD + oD; /* :658 */
+  if (isnan(result)) *status |= EPI_ST_NA;
+  age2x_state_free(&sx);
+  return result;
+}
+
+/* df_params, R/models/model-age-groups2x.R:683-751 */
+static void age2x_df_params(const epi_data *D, double *mn, double *mx, double *init) {
+  const double g = oracle_age_gamma();
+  const double i_[52] = {3.1, 0.52, 0.50, 1.5, 0.50, 0.44, 0.8, 0.35, 0.09, 550, 0.75, 14, 21, 11, 1.5, 14, 21,
+                         14, -8, 5.2, 5.8, 0.49, 0.30, 92, 1.0, 0.18, 0.02, 29, 1.4, 0.4, 0.04, 0.96, 0.27, 0.007,
+                         28, 1.2, 0.9, 0.02, 32, 2.0, 0.6, 0.10, 1.3, 0.3, 0.05, 0.34, 6, 11, 245, 1.9, 0.3, 0.04};
+  const double mn_[52] = {2 * g, 0.5 * g, 0.5 * g, 1 * g, 0.5 * g, 0.5 * g, 0.1 * g, 0.1 * g, 0.01 * g,
+                          500, 0.5, 9, 14, 3, 0.5, 9, 14, 0, -20, 2, 2, 0.05, 0.05,
+                          60, 0.5 * g, 0.01 * g, 0.002 * g, 10, 0.5 * g, 0.01 * g, 0.002 * g,
+                          0.1 * g, 0.01 * g, 0.002 * g, 10, 0.2 * g, 0.01 * g, 0.002 * g,
+                          10, 0.2 * g, 0.01 * g, 0.002 * g, 0.2 * g, 0.01 * g, 0.002 * g, 0.1, 4, 4,
+                          (double)D->d10 - 10, 0.2 * g, 0.01 * g, 0.002 * g};
+  const double tdl = D->total_deaths_at_lockdown * 10, dml = D->dmort_last / 10;
+  const double mx_[52] = {8 * g, 5 * g, 5 * g, 5 * g, 3 * g, 3 * g, 2 * g, 2 * g, 2 * g,
+                          5000, 2, 18, 25, 100, 6, 18, 25, dml > tdl ? dml : tdl, 10, 9, 9, 1, 1,
+                          100, 3 * g, 1 * g, 0.5 * g, 50, 3 * g, 1 * g, 0.5 * g,
+                          2 * g, 1 * g, 0.5 * g, 50, 4 * g, 3 * g, 0.5 * g,
+                          50, 4 * g, 3 * g, 0.5 * g, 3 * g, 3 * g, 0.5 * g, 0.7, 14, 17,
+                          (double)D->duncertain - 2, 3 * g, 3 * g, 0.5 * g};
+  for (int i = 0; i < 52; ++i) { mn[i] = mn_[i]; mx[i] = mx_[i]; init[i] = i_[i]; }
+}
+
 /* ------------------------------------------------------- simple / Ne ------ */
 
 typedef struct {
@@ -1396,10 +1979,10 @@ static void simple_df_params(const epi_data *D, int flavour, double *mn, double 
 /* ------------------------------------------------------------- public ----- */
 
 int oracle_n_params(int flavour) {
-  return flavour == EPI_FLAVOUR_AGE2Q ? 45 : flavour == EPI_FLAVOUR_AGE2I ? 36 : flavour == EPI_FLAVOUR_NE ? 9 : 8;
+  return flavour == EPI_FLAVOUR_AGE2X ? 52 : flavour == EPI_FLAVOUR_AGE2Q ? 45 : flavour == EPI_FLAVOUR_AGE2I ? 36 : flavour == EPI_FLAVOUR_NE ? 9 : 8;
 }
 
-static int is_age(int flavour) { return flavour == EPI_FLAVOUR_AGE2Q || flavour == EPI_FLAVOUR_AGE2I; }
+static int is_age(int flavour) { return flavour == EPI_FLAVOUR_AGE2Q || flavour == EPI_FLAVOUR_AGE2I || flavour == EPI_FLAVOUR_AGE2X; }
 
 int oracle_n_series(int flavour) { return is_age(flavour) ? 8 : 3; }
 
@@ -1408,6 +1991,8 @@ int oracle_df_params(const epi_model_desc *desc, const epi_data *D, double *mn, 
     age_df_params(D, mn, mx, init);
   else if (desc->flavour == EPI_FLAVOUR_AGE2I)
     age2i_df_params(D, mn, mx, init);
+  else if (desc->flavour == EPI_FLAVOUR_AGE2X)
+    age2x_df_params(D, mn, mx, init);
   else
     simple_df_params(D, desc->flavour, mn, mx, init);
   return 0;
@@ -1442,6 +2027,9 @@ void oracle_eval_one(const epi_model_desc *desc, const epi_data *D, const double
   } else if (desc->flavour == EPI_FLAVOUR_AGE2I) {
     ll = age2i_calclogl(D, params, desc->period, desc->substeps, terms, &off, &pad, &st);
     lp = age2i_calclogp(D, raw);
+  } else if (desc->flavour == EPI_FLAVOUR_AGE2X) {
+    ll = age2x_calclogl(D, params, desc->period, desc->substeps, terms, &off, &pad, &st);
+    lp = age2x_calclogp(D, raw);
   } else {
     ll = simple_calclogl(D, desc->flavour, params, desc->period, desc->substeps, terms, &off, &pad, &st);
     lp = simple_calclogp(raw);
@@ -1507,8 +2095,15 @@ int oracle_trajectory(const epi_model_desc *desc, const epi_data *D, const doubl
   for (int i = 0; i < d; ++i) params[i + 1] = theta_model[i];
   if (is_age(desc->flavour)) {
     age_state_t st;
-    if (desc->flavour == EPI_FLAVOUR_AGE2I ? age2i_calculate_model(D, params, period, desc->substeps, &st)
-                                           : age_calculate_model(D, params, period, desc->substeps, &st))
+    age2x_state_t sx;
+    memset(&sx, 0, sizeof sx);
+    if (desc->flavour == EPI_FLAVOUR_AGE2X) {
+      if (age2x_calculate_model(D, params, period, desc->substeps, &sx)) return -1;
+      st = sx.a;
+      memset(&sx.a, 0, sizeof sx.a); /* st owns the series now */
+      age2x_state_free(&sx);
+    } else if (desc->flavour == EPI_FLAVOUR_AGE2I ? age2i_calculate_model(D, params, period, desc->substeps, &st)
+                                                  : age_calculate_model(D, params, period, desc->substeps, &st))
       return -1;
     const double *src[8] = {st.yS, st.oS, st.ycasei, st.ocasei, st.yhospi, st.ohospi, st.ydeadi, st.odeadi};
     for (int q = 0; q < 8; ++q)

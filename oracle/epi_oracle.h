@@ -15,6 +15,7 @@ double oracle_dnbinom_mu_log(double x, double size, double mu);
 double oracle_age_gamma(void);
 void oracle_derivs_age(const double *parms45, double t, const double *y, double *ydot);
 void oracle_derivs_agef(const double *parms37, double t, const double *y, double *ydot);
+void oracle_derivs_ager(const double *parms60, double t, const double *y, double *ydot, double *yout9);
 int oracle_n_params(int flavour);
 int oracle_n_series(int flavour);
 int oracle_df_params(const epi_model_desc *desc, const epi_data *D, double *mn, double *mx, double *init);
@@ -28,6 +29,8 @@ int oracle_trajectory(const epi_model_desc *desc, const epi_data *D, const doubl
 void oracle_yout_age(const double *parms45, double t, const double *y, double *yout);
 void oracle_yout_agef(const double *parms37, double t, const double *y, double *yout);
 void oracle_set_jitter(int ulps, unsigned seed);
+/* tests only: evaluate the ODE scheme in the CUDA kernels' operation order (explicit fma), see epi_oracle.c */
+void oracle_set_mirror(int on);
 int oracle_profile(int kind, double mean, double sd, double *values, int *kbegin, int *kend);
 #ifdef __cplusplus
 }

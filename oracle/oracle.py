@@ -41,6 +41,8 @@ def lib():
         L.oracle_age_gamma.restype = C.c_double
         L.oracle_derivs_age.argtypes = [_dp, C.c_double, _dp, _dp]
         L.oracle_derivs_agef.argtypes = [_dp, C.c_double, _dp, _dp]
+        L.oracle_derivs_ager.argtypes = [_dp, C.c_double, _dp, _dp, _dp]
+        L.oracle_derivs_ager.restype = None
         L.oracle_df_params.argtypes = [C.POINTER(_capi.ModelDesc), C.POINTER(_capi.Data), _dp, _dp, _dp]
         L.oracle_eval.argtypes = [C.POINTER(_capi.ModelDesc), C.POINTER(_capi.Data), _dp, C.c_int64,
                                   C.c_int, _dp, _dp, _ip, _ip, _ip, _dp]
@@ -51,6 +53,8 @@ def lib():
         L.oracle_profile.argtypes = [C.c_int, C.c_double, C.c_double, _dp, _ip, _ip]
         L.oracle_set_jitter.argtypes = [C.c_int, C.c_uint]
         L.oracle_set_jitter.restype = None
+        L.oracle_set_mirror.argtypes = [C.c_int]
+        L.oracle_set_mirror.restype = None
         _lib = L
     return _lib
 
@@ -129,6 +133,12 @@ def conditioning(flavour, data, theta, period, substeps, logl, ulps=32, n_draws=
     return cond
 
 
+def set_mirror(on: bool):
+    """tests only: the ODE scheme in the CUDA kernels' operation order (explicit fma) — the ODE states are then
+    bit-identical to the GPU's, see epi_oracle.c"""
+    lib().oracle_set_mirror(1 if on else 0)
+
+
 def profile(kind, mean, sd):
     v = np.zeros(_capi.MAX_PARAMS + 32)
     kb, ke = C.c_int32(0), C.c_int32(0)
@@ -161,6 +171,15 @@ def derivs_agef(parms37, t, y):
     out = np.zeros(10)
     lib().oracle_derivs_agef(_capi.as_dp(p), t, _capi.as_dp(yy), _capi.as_dp(out))
     return out
+
+
+def derivs_ager(parms60, t, y):
+    """(ydot[10], yout[9]) of the restated model-ager.cpp RHS"""
+    p = np.ascontiguousarray(parms60, dtype=np.float64)
+    yy = np.ascontiguousarray(y, dtype=np.float64)
+    out, yo = np.zeros(10), np.zeros(9)
+    lib().oracle_derivs_ager(_capi.as_dp(p), t, _capi.as_dp(yy), _capi.as_dp(out), _capi.as_dp(yo))
+    return out, yo
 
 
 class RefRHS:

@@ -9,7 +9,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
-DATASETS = ("S120", "S365", "NE120", "A300", "A365", "I290", "DE", "SE_NE")
+DATASETS = ("S120", "S365", "NE120", "A300", "A365", "I290", "X300", "DE", "SE_NE")
 
 
 def pytest_configure(config):

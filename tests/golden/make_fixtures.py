@@ -147,6 +147,47 @@ def age2i_dataset(P):
     return d
 
 
+def age2x_dataset(P):
+    """the later generation (model-age-groups2x.R + model-ager.cpp).  No settings.R of the snapshot points at it, so
+    its extra globals (d9, d10, d12, duncertain, d.symp.cases, d.all.cases, symp.cases.factor) are chosen here to be
+    consistent with the file's own init vector (t3o = 92, t4o = 29, t6o = 28, t7o = 32, t10o = 245)."""
+    n = P - 60
+    nr = n + 200
+    vs = np.arange(1, nr + 1, dtype=float)
+    g = glogis(vs, 0, 1, 1, 0.5, 0.1, 200, 0.5)
+    gtrimp = glogis(vs, 0, 1, 1, 0.5, 0.1, 113, 0.5)
+    d = dict(name="X" + str(P), flavour="age2x", period=P, N=11.5e6, y_N=8.55e6, o_N=2.95e6,
+             lockdown_offset=2, lockdown_transition_period=10, total_deaths_at_lockdown=5.0,
+             d3=104, d4=133, d5=154, d6=182, d7=216, d8=225, d9=232, d10=245, d12=262, duncertain=280,
+             d_symp_cases=228, d_all_cases=250, symp_cases_factor=0.8,
+             d_reliable_cases=205, d_reliable_hosp=83, d_hosp_o1=104, d_hosp_o2=188,
+             n_dhospi=n, n_dhosp=n, n_dmorti=n, n_dcasei=n, n_rate=nr,
+             y_ifr=(3e-4 * (1 - 0.5 * g)).tolist(), o_ifr=[0.04] * nr, y_hr=[0.01] * nr, o_hr=[0.06] * nr,
+             g=g.tolist(), gtrimp=gtrimp.tolist(), o_wdmorti=[1.0] * n,
+             case_nbinom_size1=0.01, case_nbinom_sizey2=1.0, case_nbinom_sizeo2=1.0,
+             hosp_nbinom_size1=20.0, hosp_nbinom_size2=40.0, mort_nbinom_size=120.0, hosp_last7=3.0,
+             dhospi=[0.0] * n, y_dcasei=[0.0] * n, o_dcasei=[0.0] * n, y_dmorti=[0.0] * n,
+             o_dmorti=[0.0] * n, dmort_last=20000.0)
+    _, _, init = oracle.df_params("age2x", d, P)
+    series, _, off, pad = oracle.trajectory("age2x", d, init, P, M_DEFAULT)
+    assert off != 10000, "init does not cross t0_morts within 60 days"
+    idx = off - 1 - pad + np.arange(n)
+    assert idx.min() >= 0 and idx.max() < P, (off, pad, idx.min(), idx.max())
+    rng = np.random.default_rng(20200310)
+    ycasei, ocasei, yhospi, ohospi, ydeadi, odeadi = (series[q][idx] for q in range(2, 8))
+    d["y_dcasei"] = nb_draw(rng, np.maximum(0.1, ycasei), 1.0).tolist()
+    d["o_dcasei"] = nb_draw(rng, np.maximum(0.1, ocasei), 1.0).tolist()
+    rh = d["d_reliable_hosp"]
+    sz_h = np.where(np.arange(1, n + 1) < rh, 20.0, 40.0)
+    d["dhospi"] = nb_draw(rng, np.maximum(0.1, yhospi + ohospi), sz_h).tolist()
+    d["y_dmorti"] = nb_draw(rng, np.maximum(0.001, ydeadi), 600.0).tolist()
+    d["o_dmorti"] = nb_draw(rng, np.maximum(0.001, odeadi), 120.0).tolist()
+    d["dmort_last"] = float(np.sum(d["y_dmorti"]) + np.sum(d["o_dmorti"]))
+    d["provenance"] = ("synthetic: oracle (RK4 m=4) at model-age-groups2x.R init, NB noise with the age2q settings' sizes, "
+                       "numpy default_rng(20200310); the generation's extra globals are chosen to match its init vector")
+    return d
+
+
 def ecdc_dataset(geo, d1, transition, data_days, flavour):
     rows = [r for r in csv.DictReader(open(ECDC)) if r["geoId"] == geo]
     for r in rows:
@@ -203,7 +244,7 @@ def golden(ds, n_random, seed):
             terms=[[None if np.isnan(v) else v for v in row] for row in r["terms"].tolist()])
     # trajectories at init (model space) for the calculateModel parity test
     model = init.copy()
-    if fl not in ("age2q", "age2i"):
+    if fl not in ("age2q", "age2i", "age2x"):
         model[4] = np.exp(init[4])
     series, states, off, pad = oracle.trajectory(fl, ds, model, P, 4)
     out["init_trajectory"] = dict(substeps=4, offset=off, padding=pad,
@@ -216,7 +257,7 @@ def main():
     os.makedirs(DS_DIR, exist_ok=True)
     makers = {"S120": lambda: simple_dataset(120), "S365": lambda: simple_dataset(365),
               "NE120": lambda: simple_dataset(120, "ne"), "A300": lambda: age_dataset(300),
-              "A365": lambda: age_dataset(365), "I290": lambda: age2i_dataset(290),
+              "A365": lambda: age_dataset(365), "I290": lambda: age2i_dataset(290), "X300": lambda: age2x_dataset(300),
               "DE": lambda: ecdc_dataset("DE", dt.date(2020, 3, 13), 10, 60, "simple"),
               "SE_NE": lambda: ecdc_dataset("SE", dt.date(2020, 3, 12), 14, 60, "ne")}
     only = sys.argv[1:]  # optional: regenerate only the named sets
@@ -224,7 +265,7 @@ def main():
     for ds in sets:
         with open(os.path.join(DS_DIR, ds["name"] + ".json"), "w") as f:
             json.dump(ds, f)
-        nrand = 24 if ds["flavour"] in ("age2q", "age2i") else 32
+        nrand = 24 if ds["flavour"] in ("age2q", "age2i", "age2x") else 32
         g = golden(ds, nrand, 1234)
         with open(os.path.join(GOLD_DIR, "golden_" + ds["name"] + ".json"), "w") as f:
             json.dump(g, f)

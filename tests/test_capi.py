@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     lib = C.CDLL(_capi.LIB_PATH)
     for name in _header_symbols():
         assert hasattr(lib, name), name
-    assert lib.epi_abi_version() == 1
+    assert lib.epi_abi_version() == 2
 
 
 def test_no_cpu_fallback():

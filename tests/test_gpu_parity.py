@@ -60,7 +60,7 @@ def test_golden_vectors(name, m):
     M.close()
 
 
-@pytest.mark.parametrize("name,n", [("S120", 2048), ("NE120", 2048), ("A300", 1024), ("I290", 1024), ("SE_NE", 1024)])
+@pytest.mark.parametrize("name,n", [("S120", 2048), ("NE120", 2048), ("A300", 1024), ("I290", 1024), ("X300", 1024), ("SE_NE", 1024)])
 def test_oracle_live_random_theta(name, n, oracle):
     from epi_mcmc_b200.model import load_dataset
     ds = load_dataset(name)
@@ -94,7 +94,7 @@ def test_oracle_live_random_theta(name, n, oracle):
     M.close()
 
 
-@pytest.mark.parametrize("name,n", [("S365", 512), ("A300", 512), ("A365", 256), ("I290", 512)])
+@pytest.mark.parametrize("name,n", [("S365", 512), ("A300", 512), ("A365", 256), ("I290", 512), ("X300", 512)])
 def test_well_conditioned_strict(name, n, oracle):
     """theta close to the model file's init (where the posterior
     mass of the synthetic data sits; +-0.5 % of the box width: the north_star bar holds as stated, 1e-10 relative on
@@ -111,6 +111,75 @@ def test_well_conditioned_strict(name, n, oracle):
     good = status == 0
     assert good.sum() > n // 2
     assert rel_err((logl + logp)[good], (ref["logl"] + ref["logp"])[good]).max() <= TOL_LOGL
+    M.close()
+
+
+@pytest.mark.parametrize("name", ["A300", "I290", "X300", "S365", "NE120"])
+def test_mirrored_oracle_states_are_bit_identical(name, oracle):
+    """oracle_set_mirror(1): the oracle evaluates the fixed-step scheme in the kernels' operation order (curves
+    pre-divided by the population, explicit fma everywhere).  Every operation is correctly rounded IEEE on both
+    sides, so the ODE state series the GPU reports (S, and E / I / R of the ext trajectories) must then equal the
+    oracle's BIT FOR BIT — over box-wide theta, breakpoints inside sub-steps, guard hits and all."""
+    from epi_mcmc_b200.model import load_dataset
+    ds = load_dataset(name)
+    M = _model(name, 4)
+    mn, mx, init = M.df_params["min"], M.df_params["max"], M.df_params["init"]
+    rng = np.random.default_rng(23)
+    theta = np.vstack([init[None], np.clip(init + (rng.uniform(size=(24, M.d)) - 0.5) * 0.3 * (mx - mn), mn, mx),
+                       mn + rng.uniform(size=(24, M.d)) * (mx - mn)])
+    model_th = M.transformParams(theta)
+    series, off, pad = M.calculateModel_batch(model_th, ds["period"], ext=True)
+    names = M.series_names_ext
+    state_cols = [k for k, nm in enumerate(names) if nm.split(".")[-1] in ("S", "E", "I", "R")]
+    assert len(state_cols) >= 4
+    oracle.set_mirror(True)
+    try:
+        n_checked = 0
+        for i in range(len(theta)):
+            try:
+                ref, _, roff, rpad = oracle.trajectory(ds["flavour"], ds, model_th[i], ds["period"], 4, ext=True)
+            except ValueError:
+                continue
+            if off[i] != roff or pad[i] != rpad:
+                continue   # the threshold search reads the death profile too: not what this test is about
+            for k in state_cols:
+                assert np.array_equal(series[i, k], ref[k], equal_nan=True), (i, names[k], np.abs(series[i, k] - ref[k]).max())
+            n_checked += 1
+        assert n_checked >= 40
+    finally:
+        oracle.set_mirror(False)
+    M.close()
+
+
+@pytest.mark.parametrize("name,n", [("A300", 1024), ("I290", 1024), ("S120", 1024)])
+def test_box_uniform_against_the_mirrored_oracle(name, n, oracle):
+    """With the ODE states bit-identical (mirrored oracle), what is left of a GPU <-> oracle difference in logl is the
+    latency profiles (incomplete-gamma series in a different summation order) and the table-driven logarithm: the
+    1e-10 bar then holds for (nearly) every box-uniform theta, with no conditioning allowance — the misses of
+    test_oracle_live_random_theta against the reference's operation order are the cancellation of
+    diff(N - filter(S)) amplifying a-few-ulp differences of the states, not a property of the kernels."""
+    from epi_mcmc_b200.model import load_dataset
+    ds = load_dataset(name)
+    M = _model(name, 4)
+    mn, mx = M.df_params["min"], M.df_params["max"]
+    rng = np.random.default_rng(7)
+    theta = mn + rng.uniform(size=(n, M.d)) * (mx - mn)
+    logl, logp, status = M.calclogpost_batch(theta)
+    off, pad, _ = M.eval_detail(theta)
+    oracle.set_mirror(True)
+    try:
+        ref = oracle.evaluate(ds["flavour"], ds, theta, ds["period"], 4, n_threads=8)
+    finally:
+        oracle.set_mirror(False)
+    ok = (off == ref["offset"]) & (status == ref["status"]) & (pad == ref["padding"])
+    assert (~ok).sum() <= max(1, n // 1000)
+    fin = ok & np.isfinite(ref["logl"])
+    err = rel_err(logl[fin], ref["logl"][fin])
+    rate = float((err <= TOL_LOGL).mean())
+    print(name, "box-uniform theta within 1e-10 of the mirrored oracle:", rate, "of", int(fin.sum()), "max rel err", err.max())
+    # measured: S120 and I290 >= 0.97; A300 0.92 (against 0.85 with the reference's operation order) — its misses are
+    # the profile weights, a few ulp apart, amplified by the same cancellation in burnt-out epidemics
+    assert rate >= (0.90 if name == "A300" else 0.97), rate
     M.close()
 
 
@@ -167,7 +236,7 @@ def test_edge_statuses():
     M.close()
 
 
-@pytest.mark.parametrize("name", ["A300", "I290", "S120", "NE120"])
+@pytest.mark.parametrize("name", ["A300", "I290", "X300", "S120", "NE120"])
 def test_trajectories_match_oracle(name, oracle):
     """calculateModel(params, period) series, also for a horizon other than FitTotalPeriod
     (quantileData calls it with 3 * period, libMCMC.R:160-161)."""

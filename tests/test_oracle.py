@@ -140,6 +140,40 @@ def test_rhs_agef_matches_reference_binary(oracle):
             assert np.array_equal(yo[:4], oracle.yout_age(parms, t, y), equal_nan=True)
 
 
+def test_rhs_ager_matches_reference_binary(oracle):
+    """The RHS of the later model generation (model-ager.cpp, parms[60]: waning immunity, effective-susceptible cap,
+    13-breakpoint schedule, uncertain()) and its nine output variables, incl. the infection incidences y.i / o.i that
+    model-age-groups2x.R convolves: the restatement is bit-exact against the reference binary."""
+    try:
+        ref = oracle.RefRHS("model-ager", 60)
+    except FileNotFoundError:
+        pytest.skip("oracle/_ref not built (reference tree absent)")
+    rng = np.random.default_rng(5)
+    gamma = oracle.lib().oracle_age_gamma()
+    tidx = [8, 9, 10] + [20 + 4 * k for k in range(10)]
+    for trial in range(800):
+        parms = np.zeros(60)
+        parms[:8] = [8.55e6, 2.95e6, 1 / 3, 1, gamma, 1 / (0.75 * 356), rng.uniform(100, 400), 1.0 if trial % 4 else rng.uniform(0.7, 1.4)]
+        ts = np.sort(rng.uniform(30, 330, 13)) if trial % 3 else rng.uniform(30, 330, 13)
+        for k, i in enumerate(tidx):
+            parms[i] = ts[k]
+        for i in range(11, 60):
+            if i not in tidx:
+                parms[i] = rng.uniform(0.01, 4)
+        y = np.concatenate([rng.dirichlet(np.ones(5)) * 8.55e6, rng.dirichlet(np.ones(5)) * 2.95e6])
+        if trial % 5 == 0:   # younger susceptibles below the 20 % floor of the effective-susceptible cap
+            y[0] = rng.uniform(0, 0.25) * 8.55e6 * 0.5
+        if trial % 50 == 0:
+            y[rng.integers(10)] = -1.0
+        t = rng.uniform(0, 360) if trial % 7 else ts[rng.integers(13)]
+        ref.init(parms)
+        a, yo = ref.derivs(t, y, nout=9)
+        b, yb = oracle.derivs_ager(parms, t, y)
+        assert np.array_equal(a, b), (trial, a, b)
+        if y.min() >= 0 and (y[:5] <= 8.55e6).all() and (y[5:] <= 2.95e6).all():
+            assert np.array_equal(yo[:9], yb, equal_nan=True), (trial, yo[:9], yb)
+
+
 @pytest.mark.parametrize("name", ["A300", "I290", "S120", "NE120", "DE"])
 def test_oracle_vs_numpy_transliteration_same_scheme(name, oracle):
     """Index semantics (filter alignment + mirror, two-pass offset, rate-map slices, dnbinom
@@ -305,6 +339,51 @@ def test_ode_path_2i_through_the_reference_binary(oracle):
         Y0 = [ds["y_N"] - 1, 1, 0, 0, 0, ds["o_N"], 0, 0, 0, 0]
         times = np.arange(pad + 1, pad + P + 1, dtype=float)
         sol = integrate.solve_ivp(lambda t, y: ref.derivs(t, y)[0], (times[0], times[-1]), Y0, method="LSODA",
+                                  t_eval=times, rtol=1e-12, atol=1e-9, max_step=0.1)
+        assert sol.success and sol.y.shape[1] == P
+        got = sol.y.T
+        scale = np.maximum(np.abs(got), 1.0)
+        e8, e16 = ((np.abs(st - got) / scale).max() for st in (states, states16))
+        assert e8 < 1e-4 and e16 < 1e-5 and e16 < e8 / 8, (e8, e16)
+        checked += 1
+    assert checked >= 2
+
+
+def test_ode_path_2x_through_the_reference_binary(oracle):
+    """The later generation: parms as model-age-groups2x.R:222-238 builds them (60 values, position-coupled to
+    model-ager.cpp:7-66), the reference's model-ager.so under scipy LSODA, fourth-order convergence of the oracle's
+    states AND of its incidence series y.i / o.i (output variables 5 and 6, what the observation models convolve)."""
+    from scipy import integrate
+    try:
+        ref = oracle.RefRHS("model-ager", 60)
+    except FileNotFoundError:
+        pytest.skip("oracle/_ref not built (reference tree absent)")
+    ds = ds_load("X300")
+    P = ds["period"]
+    checked = 0
+    for th in np.array(load_golden("X300")["theta"])[[0, 26, 27, 30]]:
+        series, states, off, pad = oracle.trajectory("age2x", ds, th, P, 8)
+        if off == 10000:
+            continue
+        states16 = oracle.trajectory("age2x", ds, th, P, 16)[1]
+        p = lambda i: th[i - 1]   # 1-based like the R file (:56-119)
+        lo, ltp = ds["lockdown_offset"], ds["lockdown_transition_period"]
+        t2 = off + lo + ltp; t3 = t2 + p(24); t4 = t3 + p(28); t5 = off + ds["d5"]; t6 = t5 + p(35); t7 = t6 + p(39)
+        t8 = off + ds["d8"]; t9 = off + ds["d9"]; t10 = off + p(49); t11 = t10 + 3; t12 = off + ds["d12"]
+        b = {0: (p(1), p(2), p(3)), 1: (p(4), p(5), p(6)), 2: (p(7), p(8), p(9)), 3: (p(25), p(26), p(27)),
+             4: (p(29), p(30), p(31)), 5: (p(32), p(33), p(34)), 6: (p(36), p(37), p(38)), 7: (p(40), p(41), p(42)),
+             8: (p(40), p(41), p(42)), 9: (p(43), p(44), p(45)), 10: (p(43), p(44), p(45)), 11: (p(50), p(51), p(52)),
+             12: (p(43), p(44), p(45))}
+        gamma = oracle.lib().oracle_age_gamma()
+        parms = [ds["y_N"], ds["o_N"], 1 / 3, 1.0, gamma, 1 / (0.75 * 356), off + ds["duncertain"], 1.0,
+                 off + lo + p(19), off + lo + max(p(19), 0), t2, *b[0], *b[1], *b[2]]
+        for k, tk in zip(range(3, 13), (t3, t4, t5, t6, t7, t8, t9, t10, t11, t12)):
+            parms += [tk, *b[k]]
+        assert len(parms) == 60
+        ref.init(np.array(parms))
+        Y0 = [ds["y_N"] - 1, 1, 0, 0, 0, ds["o_N"], 0, 0, 0, 0]
+        times = np.arange(pad + 1, pad + P + 1, dtype=float)
+        sol = integrate.solve_ivp(lambda t, y: ref.derivs(t, y, nout=9)[0], (times[0], times[-1]), Y0, method="LSODA",
                                   t_eval=times, rtol=1e-12, atol=1e-9, max_step=0.1)
         assert sol.success and sol.y.shape[1] == P
         got = sol.y.T
