@@ -106,7 +106,7 @@ _lib = None
 SYMBOLS = (
     "epi_create", "epi_destroy", "epi_last_error", "epi_abi_version", "epi_n_params",
     "epi_param_name", "epi_df_params", "epi_eval", "epi_eval_submit", "epi_eval_wait", "epi_eval_device", "epi_eval_device_range", "epi_reserve", "epi_eval_detail",
-    "epi_n_series", "epi_trajectories", "epi_n_series_ext", "epi_trajectories_ext", "epi_quantiles", "epi_sampler_init", "epi_sampler_run",
+    "epi_n_series", "epi_trajectories", "epi_n_series_ext", "epi_trajectories_ext", "epi_quantiles", "epi_marginalize", "epi_sampler_init", "epi_sampler_run",
     "epi_sampler_adapt", "epi_sampler_set_scale", "epi_sampler_state_device", "epi_sampler_set_population",
     "epi_sampler_get", "epi_sampler_stats", "epi_sampler_pt_stats", "epi_sampler_record", "epi_sampler_draws", "epi_sampler_draws_subset",
     "epi_sampler_draws_device", "epi_sampler_bandwidths", "epi_k2_bench",
@@ -147,6 +147,7 @@ def load():
     lib.epi_n_series_ext.argtypes = [vp]
     lib.epi_trajectories_ext.argtypes = [vp, _dp, i64, C.c_int, i32, _dp, ip, ip]
     lib.epi_quantiles.argtypes = [vp, _dp, i64, C.c_int, i32, i32, i32, i32, _dp, i32, _dp]
+    lib.epi_marginalize.argtypes = [vp, _dp, i64, C.c_int, i32, i32, i32, i32, i32, i32, i32, _dp]
     lib.epi_sampler_draws_device.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), ip, C.POINTER(i64)]
     lib.epi_sampler_bandwidths.argtypes = [vp, _dp]
     lib.epi_k2_bench.argtypes = [vp, i32, i64, i32, _dp, _dp, _dp]

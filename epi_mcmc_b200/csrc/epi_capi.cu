@@ -308,6 +308,73 @@ static std::vector<PriorTerm> build_prior(int flavour, const epi_data &D) {
   return p;
 }
 
+// ------------------------------------------------------------ schedule table
+// The beta(t) schedule of an age model file as data (Schedule, epi_device.cuh): breakpoints as running sums of
+// data constants and parameters, the beta triple of every breakpoint, which segments interpolate linearly.
+// 0-based theta indices; data_offset is added on the device.
+static void sched_bp(Schedule &S, int k, double c, int ia = -1, int ib = -1, bool clamp = false, double post = 0.0) {
+  S.bp[k] = SchedBp{c, post, (short)ia, (short)ib, (short)(clamp ? 1 : 0), 0};
+}
+static void sched_beta(Schedule &S, int k, int first, int my = -1, int mo = -1, int myo = -1) {
+  S.beta[k] = SchedBeta{{(short)first, (short)(first + 1), (short)(first + 2)}, {(short)my, (short)mo, (short)myo}};
+}
+static void build_schedule(int flavour, const epi_data &D, Schedule &S) {
+  std::memset(&S, 0, sizeof S);
+  const double lo = D.lockdown_offset, t2 = lo + D.lockdown_transition_period;
+  if (flavour == EPI_FLAVOUR_AGE2Q) {
+    // breakpoints, model-age-groups2q.R:184-197; segment kinds, model-agen.cpp:78-99; betas, :52-99
+    S.n = 10; S.linear = 0x10F;
+    sched_bp(S, 0, lo, 18);                 // t0 = data_offset + lockdown_offset + t0o
+    sched_bp(S, 1, lo, 18, -1, true);       // t1 = ... + max(t0o, 0)
+    sched_bp(S, 2, t2);
+    sched_bp(S, 3, t2, 23);                 // t3 = t2 + t3o
+    sched_bp(S, 4, t2, 23, 24);             // t4 = t3 + t4o
+    sched_bp(S, 5, D.d5);
+    sched_bp(S, 6, D.d5, 31);               // t6 = t5 + t6o
+    sched_bp(S, 7, D.d5, 31, 35);           // t7 = t6 + t7o
+    sched_bp(S, 8, D.d8);
+    sched_bp(S, 9, (double)D.d8 + 7);       // t9 = t8 + 7
+    sched_beta(S, 0, 0); sched_beta(S, 1, 3); sched_beta(S, 2, 6);
+    S.beta[3] = SchedBeta{{6, 26, 27}, {-1, -1, -1}};  // betay3 = betay2, betao3 = betao4, betayo3 = betayo4
+    sched_beta(S, 4, 25); sched_beta(S, 5, 28); sched_beta(S, 6, 32);
+    sched_beta(S, 7, 36); sched_beta(S, 8, 36);        // beta8 = beta7
+    sched_beta(S, 9, 36, 39, 40, 41);                  // beta9 = f9 * beta8
+  } else if (flavour == EPI_FLAVOUR_AGE2I) {
+    // model-age-groups2i.R:169-183, model-agef.cpp:66-87, :52-93
+    S.n = 8; S.linear = 0x03F;
+    sched_bp(S, 0, lo, 20);
+    sched_bp(S, 1, lo, 20, -1, true);
+    sched_bp(S, 2, t2);
+    sched_bp(S, 3, t2, 24);
+    sched_bp(S, 4, t2, 24, 25);
+    sched_bp(S, 5, D.d5);
+    sched_bp(S, 6, D.d5, 29);
+    sched_bp(S, 7, D.d7);
+    sched_beta(S, 0, 0); sched_beta(S, 1, 3); sched_beta(S, 2, 6); sched_beta(S, 3, 6);  // beta3 = beta2
+    sched_beta(S, 4, 26); sched_beta(S, 5, 26);                                          // beta5 = beta4
+    sched_beta(S, 6, 30);
+    sched_beta(S, 7, 30, 33, 35, 34);  // betay7 = fy7 betay6, betao7 = params[36] betao6, betayo7 = params[35] betayo6 (:91-93)
+  } else if (flavour == EPI_FLAVOUR_AGE2X) {
+    // model-age-groups2x.R:206-219, model-ager.cpp:88-124, :56-119
+    S.n = 13; S.linear = 0xD0F;
+    sched_bp(S, 0, lo, 18);
+    sched_bp(S, 1, lo, 18, -1, true);
+    sched_bp(S, 2, t2);
+    sched_bp(S, 3, t2, 23);
+    sched_bp(S, 4, t2, 23, 27);
+    sched_bp(S, 5, D.d5);
+    sched_bp(S, 6, D.d5, 34);
+    sched_bp(S, 7, D.d5, 34, 38);
+    sched_bp(S, 8, D.d8);
+    sched_bp(S, 9, D.d9);
+    sched_bp(S, 10, 0.0, 48);                    // t10 = data_offset + t10o
+    sched_bp(S, 11, 0.0, 48, -1, false, 3.0);    // t11 = t10 + 3
+    sched_bp(S, 12, D.d12);
+    const int first[13] = {0, 3, 6, 24, 28, 31, 35, 39, 39, 42, 42, 49, 42};  // beta8 = beta7, beta10 = beta12 = beta9
+    for (int k = 0; k < 13; ++k) sched_beta(S, k, first[k]);
+  }
+}
+
 // -------------------------------------------------------------------- create
 static int fill_model(epi_handle *h, const epi_model_desc &desc, const epi_data &D) {
   DevModel &M = h->M;
@@ -319,6 +386,15 @@ static int fill_model(epi_handle *h, const epi_model_desc &desc, const epi_data 
   M.ltp = D.lockdown_transition_period;
   std::vector<NbCall> calls;
   int n_obs[kMaxSeries] = {0, 0, 0, 0, 0};
+  if (is_age(desc.flavour)) {
+    Schedule S;
+    build_schedule(desc.flavour, D, S);
+    Schedule *dS = nullptr;
+    CUDA_OK(h, cudaMalloc(&dS, sizeof(Schedule)));
+    h->owned.push_back(dS);
+    CUDA_OK(h, cudaMemcpy(dS, &S, sizeof(Schedule), cudaMemcpyHostToDevice));
+    M.sched = dS;
+  }
   if (desc.flavour == EPI_FLAVOUR_AGE2Q) {
     M.d = 45;
     M.P1 = 60;  // period1, model-age-groups2q.R:160
@@ -927,6 +1003,42 @@ extern "C" int epi_quantiles(epi_handle *h, const double *theta, int64_t n, int 
   cudaFree(d_probs);
   cudaFree(d_out);
   if (e != cudaSuccess) return epi_fail(h, EPI_ERR_CUDA, "epi_quantiles: %s", cudaGetErrorString(e));
+  return EPI_OK;
+}
+
+extern "C" int epi_marginalize(epi_handle *h, const double *theta, int64_t n, int layout, int32_t period, int32_t startoffset,
+                               int32_t series_a, int32_t series_b, int32_t kind, int32_t j1, int32_t j2, double *out) {
+  if (!h || !theta || !out || n < 1 || period < 1) return epi_fail(h, EPI_ERR_ARG, "bad argument");
+  const bool age = is_age(h->M.flavour), fixed_p1 = fixed_pass1(h->M.flavour);
+  const int NSb = n_series_of(h->M.flavour, false), NSx = n_series_of(h->M.flavour, true);
+  if (series_a < 0 || series_a >= NSx || series_b >= NSx) return epi_fail(h, EPI_ERR_ARG, "series index out of range");
+  const int simperiod = 3 * period;  // libMCMC.R:176
+  if (kind < 0 || kind > 3 || j1 < 1 || j2 < j1 || j2 > simperiod) return epi_fail(h, EPI_ERR_ARG, "bad marginal (kind 0..3, 1 <= j1 <= j2 <= 3 * period)");
+  if (simperiod < (fixed_p1 ? 60 : 2) || simperiod > (age ? 2048 : 4096)) return epi_fail(h, EPI_ERR_ARG, "period out of range");
+  const int NS = (series_a >= NSb || series_b >= NSb || h->M.flavour == EPI_FLAVOUR_AGE2X) ? NSx : NSb;
+  CUDA_OK(h, cudaSetDevice(h->device));
+  DevModel M = h->M;
+  M.P = simperiod;
+  if (!fixed_p1) M.P1 = simperiod;
+  int rc = epi_ensure_workspace(h, h->ws_traj, M, n, NS);
+  if (rc) return rc;
+  Workspace &w = h->ws_traj;
+  if ((rc = stage_theta(h, w, theta, n, layout, M.d))) return rc;
+  if ((rc = epi_launch_eval_ws(h, w, M, w.theta, w.ld, n, 1, nullptr, nullptr, nullptr, nullptr, w.series, h->stream, NS))) return rc;
+  auto prefill = [&](int sidx) -> double {  // values before padding + 1, as in epi_quantiles
+    if (sidx < 0) return 0.0;
+    if (age) return sidx == 0 ? M.Ny - 1.0 : sidx == 1 ? M.No : (sidx == 8 || sidx == 11) ? NAN : 0.0;
+    return sidx == 0 ? M.N - 1.0 : sidx == 3 ? 1.0 : 0.0;
+  };
+  double *d_out = nullptr;
+  CUDA_OK(h, cudaMalloc(&d_out, sizeof(double) * (size_t)n));
+  cudaError_t e = launch_marginal(w.series, w.offset, w.pad, n, NS, simperiod, startoffset, series_a, series_b,
+                                  prefill(series_a), prefill(series_b), kind, j1, j2, d_out, h->stream);
+  h->launches += 1;
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  cudaFree(d_out);
+  if (e != cudaSuccess) return epi_fail(h, EPI_ERR_CUDA, "epi_marginalize: %s", cudaGetErrorString(e));
   return EPI_OK;
 }
 

@@ -36,6 +36,22 @@ __device__ __forceinline__ Slot ldg_slot(const Slot *p) {
   return s;
 }
 
+// Generalised beta(t) schedule of the two-age-group flavours, built on the host per model file
+// (epi_capi.cu:build_schedule) — a new schedule is a new table, not new kernel code:
+//   breakpoint k   t_k = ((data_offset + c) + A + B) + post,  A = theta[ia] (max(theta[ia], 0) when clamp), B = theta[ib]
+//                  (ia / ib = -1: term absent; the operations run in exactly this order: the reference files build
+//                  their breakpoints as running sums, e.g. t4 = (t2 + t3o) + t4o, model-age-groups2q.R:184-197)
+//   beta triple k  beta_c = theta[i[c]] * (m[c] >= 0 ? theta[m[c]] : 1),  c = y, o, yo
+//   segment k      linear towards k + 1 when bit k of `linear` is set, else constant (model-agen.cpp:78-99)
+struct SchedBp { double c, post; short ia, ib, clamp, pad_; };
+struct SchedBeta { short i[3], m[3]; };
+struct Schedule {
+  int n;
+  unsigned linear;
+  SchedBp bp[kMaxBp];
+  SchedBeta beta[kMaxBp];
+};
+
 struct DevModel {
   int flavour, P, m, d;
   int P1;  // days integrated by pass 1 (60 for age-2q, P for simple/Ne)
@@ -56,6 +72,8 @@ struct DevModel {
   // symptomatic-testing factor window of the case series (:278-279,293-294)
   double eta, symp_factor;
   int d9, d12, d_symp, d_all;
+  const Schedule *sched;  // device; age flavours: breakpoints, beta triples and segment kinds (read through the
+                          // read-only cache: a by-value table would be copied to every thread's stack to be indexed)
   const double *y_ifr, *o_ifr, *y_hr, *o_hr, *g, *gtrimp;  // device, n_rate each
   const Slot *slots[kMaxSeries];                           // device, [n_obs][K]
   int multi_begin[kMaxSeries];  // first relative day with more than one slot (n_obs when K == 1)

@@ -103,63 +103,23 @@ struct Traits {
 };
 
 // ------------------------------------------------------------------ theta map
-// beta triple (y, o, yo) of schedule index k for the age flavour,
-// R/models/model-age-groups2q.R:52-99 (0-based theta indices here).
+// beta triple (y, o, yo) of schedule index k for the age flavours, from the host-built schedule table
+// (R/models/model-age-groups2q.R:52-99, model-age-groups2i.R:52-93, model-age-groups2x.R:56-119).
 template <int FL>
-__device__ __forceinline__ void age_beta(const double *__restrict__ th, int64_t ld, int k, double &by,
+__device__ __forceinline__ void age_beta(const DevModel &M, const double *__restrict__ th, int64_t ld, int k, double &by,
                                          double &bo, double &byo) {
+  static_assert(Traits<FL>::kAge, "age flavours only");
   auto T = [&](int i) { return th[(int64_t)i * ld]; };
-  if constexpr (Traits<FL>::k2i) {
-    // R/models/model-age-groups2i.R:52-93: beta3 = beta2, beta5 = beta4, beta7 = f7 * beta6
-    switch (k) {
-      case 0: by = T(0); bo = T(1); byo = T(2); break;
-      case 1: by = T(3); bo = T(4); byo = T(5); break;
-      case 2:
-      case 3: by = T(6); bo = T(7); byo = T(8); break;
-      case 4:
-      case 5: by = T(26); bo = T(27); byo = T(28); break;
-      case 6: by = T(30); bo = T(31); byo = T(32); break;
-      default: by = T(33) * T(30); byo = T(34) * T(32); bo = T(35) * T(31); break;  // :91-93 (fy7, fyo7, fo7)
-    }
-    return;
-  }
-  if constexpr (Traits<FL>::k2x) {
-    // R/models/model-age-groups2x.R:56-119: beta8 = beta7, beta10 = beta12 = beta9
-    int b;
-    switch (k) {
-      case 0: b = 0; break;
-      case 1: b = 3; break;
-      case 2: b = 6; break;
-      case 3: b = 24; break;
-      case 4: b = 28; break;
-      case 5: b = 31; break;
-      case 6: b = 35; break;
-      case 7:
-      case 8: b = 39; break;
-      case 11: b = 49; break;
-      default: b = 42; break;  // 9, 10, 12
-    }
-    by = T(b); bo = T(b + 1); byo = T(b + 2);
-    return;
-  }
-  switch (k) {
-    case 0: by = T(0); bo = T(1); byo = T(2); break;
-    case 1: by = T(3); bo = T(4); byo = T(5); break;
-    case 2: by = T(6); bo = T(7); byo = T(8); break;
-    case 3: by = T(6); bo = T(26); byo = T(27); break;      // betay3 = betay2, betao3 = betao4, betayo3 = betayo4
-    case 4: by = T(25); bo = T(26); byo = T(27); break;
-    case 5: by = T(28); bo = T(29); byo = T(30); break;
-    case 6: by = T(32); bo = T(33); byo = T(34); break;
-    case 7:
-    case 8: by = T(36); bo = T(37); byo = T(38); break;     // beta8 = beta7
-    default: by = T(39) * T(36); bo = T(40) * T(37); byo = T(41) * T(38); break;  // beta9 = f9 * beta8
-  }
+  const SchedBeta b = M.sched->beta[k];
+  by = T(b.i[0]); bo = T(b.i[1]); byo = T(b.i[2]);
+  if (b.m[0] >= 0) by = T(b.m[0]) * by;
+  if (b.m[1] >= 0) bo = T(b.m[1]) * bo;
+  if (b.m[2] >= 0) byo = T(b.m[2]) * byo;
 }
 
 // segment kinds: 1 = linear towards k+1, 0 = hold.  model-agen.cpp:78-99: k = 0,1,2,3,8 linear;
 // model-agef.cpp:66-87: k = 0..5 linear, 6 and 7 hold; model-ager.cpp:88-124: k = 0,1,2,3,8,10,11 linear
-template <int FL>
-__device__ __forceinline__ bool age_linear(int k) { return ((Traits<FL>::k2i ? 0x03F : Traits<FL>::k2x ? 0xD0F : 0x10F) >> k) & 1; }
+__device__ __forceinline__ bool age_linear(const DevModel &M, int k) { return (M.sched->linear >> k) & 1u; }
 
 // ---------------------------------------------------------------------- K_ode
 // Fixed-step classical RK4, m sub-steps per day, each sub-step cut again at the
@@ -413,48 +373,20 @@ __device__ __forceinline__ void rk4_piece(const DevModel &M, const Seg &sg, doub
 template <int FL>
 __device__ __forceinline__ int breakpoints(const DevModel &M, const double *__restrict__ th, int64_t ld,
                                            double data_offset, double *bp) {
-  if constexpr (Traits<FL>::k2i) {
-    // model-age-groups2i.R:169-183
-    auto T = [&](int i) { return th[(int64_t)i * ld]; };
-    const double lo = M.lockdown_offset, t0o = T(20);
-    const double t2 = data_offset + lo + M.ltp;
-    const double t3 = t2 + T(24);
-    const double t4 = t3 + T(25);
-    const double t5 = data_offset + M.d5;
-    bp[0] = data_offset + lo + t0o;
-    bp[1] = data_offset + lo + fmax(t0o, 0.0);
-    bp[2] = t2; bp[3] = t3; bp[4] = t4; bp[5] = t5; bp[6] = t5 + T(29); bp[7] = data_offset + M.d7;
-    return 8;
-  } else if constexpr (Traits<FL>::k2x) {
-    // model-age-groups2x.R:206-219
-    auto T = [&](int i) { return th[(int64_t)i * ld]; };
-    const double lo = M.lockdown_offset, t0o = T(18);
-    const double t2 = data_offset + lo + M.ltp;
-    const double t3 = t2 + T(23);
-    const double t4 = t3 + T(27);
-    const double t5 = data_offset + M.d5;
-    const double t6 = t5 + T(34);
-    const double t7 = t6 + T(38);
-    const double t10 = data_offset + T(48);
-    bp[0] = data_offset + lo + t0o;
-    bp[1] = data_offset + lo + fmax(t0o, 0.0);
-    bp[2] = t2; bp[3] = t3; bp[4] = t4; bp[5] = t5; bp[6] = t6; bp[7] = t7;
-    bp[8] = data_offset + M.d8; bp[9] = data_offset + M.d9; bp[10] = t10; bp[11] = t10 + 3; bp[12] = data_offset + M.d12;
-    return 13;
-  } else if constexpr (Traits<FL>::kAge) {
-    auto T = [&](int i) { return th[(int64_t)i * ld]; };
-    const double lo = M.lockdown_offset, t0o = T(18);
-    const double t2 = data_offset + lo + M.ltp;
-    const double t3 = t2 + T(23);
-    const double t4 = t3 + T(24);
-    const double t5 = data_offset + M.d5;
-    const double t6 = t5 + T(31);
-    const double t7 = t6 + T(35);
-    const double t8 = data_offset + M.d8;
-    bp[0] = data_offset + lo + t0o;
-    bp[1] = data_offset + lo + fmax(t0o, 0.0);
-    bp[2] = t2; bp[3] = t3; bp[4] = t4; bp[5] = t5; bp[6] = t6; bp[7] = t7; bp[8] = t8; bp[9] = t8 + 7;
-    return 10;
+  if constexpr (Traits<FL>::kAge) {
+    // the schedule table of the model file (model-age-groups2q.R:184-197, 2i :169-183, 2x :206-219)
+    const int n = M.sched->n;
+    for (int k = 0; k < n; ++k) {
+      const SchedBp e = M.sched->bp[k];
+      double t = data_offset + e.c;
+      if (e.ia >= 0) {
+        const double a = th[(int64_t)e.ia * ld];
+        t = t + (e.clamp ? fmax(a, 0.0) : a);
+      }
+      if (e.ib >= 0) t = t + th[(int64_t)e.ib * ld];
+      bp[k] = t + e.post;
+    }
+    return n;
   } else {
     bp[0] = data_offset + M.lockdown_offset;
     bp[1] = data_offset + M.lockdown_offset + M.ltp;
@@ -490,13 +422,13 @@ __device__ __noinline__ Seg select_segment(const DevModel &M, const double *__re
   Seg sg;
   if constexpr (Traits<FL>::kAge) {
     double by, bo, byo;
-    age_beta<FL>(th, ld, k < 0 ? 0 : k, by, bo, byo);
+    age_beta<FL>(M, th, ld, k < 0 ? 0 : k, by, bo, byo);
     sg.b0 = by; sg.b1 = bo; sg.b2 = byo;
     sg.s0 = sg.s1 = sg.s2 = 0.0;
     sg.tk = 0.0;
-    if (k >= 0 && age_linear<FL>(k)) {
+    if (k >= 0 && age_linear(M, k)) {
       double ny, no, nyo;
-      age_beta<FL>(th, ld, k + 1, ny, no, nyo);
+      age_beta<FL>(M, th, ld, k + 1, ny, no, nyo);
       const double len = bp[k + 1] - bp[k];
       sg.tk = bp[k];
       sg.s0 = (ny - by) / len; sg.s1 = (no - bo) / len; sg.s2 = (nyo - byo) / len;
@@ -570,10 +502,10 @@ __device__ __noinline__ void write_ext(const DevModel &M, const double *__restri
       for (int i = nbp - 1; i >= 0; --i)
         if (t > bp[i]) { k = i; break; }
       double by, bo, byo;
-      age_beta<FL>(th, ld, k < 0 ? 0 : k, by, bo, byo);
-      if (k >= 0 && age_linear<FL>(k)) {
+      age_beta<FL>(M, th, ld, k < 0 ? 0 : k, by, bo, byo);
+      if (k >= 0 && age_linear(M, k)) {
         double ny, no, nyo;
-        age_beta<FL>(th, ld, k + 1, ny, no, nyo);
+        age_beta<FL>(M, th, ld, k + 1, ny, no, nyo);
         const double f = (t - bp[k]) / (bp[k + 1] - bp[k]);
         by = by + f * (ny - by); bo = bo + f * (no - bo); byo = byo + f * (nyo - byo);
       }
@@ -629,10 +561,10 @@ __device__ __noinline__ void incidence_out(const DevModel &M, const double *__re
   for (int i = nbp - 1; i >= 0; --i)
     if (t > bp[i]) { k = i; break; }
   double by, bo, byo;
-  age_beta<FL>(th, ld, k < 0 ? 0 : k, by, bo, byo);
-  if (k >= 0 && age_linear<FL>(k)) {
+  age_beta<FL>(M, th, ld, k < 0 ? 0 : k, by, bo, byo);
+  if (k >= 0 && age_linear(M, k)) {
     double ny, no, nyo;
-    age_beta<FL>(th, ld, k + 1, ny, no, nyo);
+    age_beta<FL>(M, th, ld, k + 1, ny, no, nyo);
     const double f = __ddiv_rn(__dsub_rn(t, bp[k]), __dsub_rn(bp[k + 1], bp[k]));
     by = __dadd_rn(by, __dmul_rn(f, __dsub_rn(ny, by)));
     bo = __dadd_rn(bo, __dmul_rn(f, __dsub_rn(no, bo)));
@@ -941,7 +873,7 @@ __device__ __forceinline__ void rk4_piece_age2(double a1, double gamma, const Se
 }
 
 template <int FL>
-__device__ __noinline__ Seg2 select_segment_age2(const double *__restrict__ th, int64_t ld, const double *bp, int nbp,
+__device__ __noinline__ Seg2 select_segment_age2(const DevModel &M, const double *__restrict__ th, int64_t ld, const double *bp, int nbp,
                                                  double pa, int is_o, double *tcut, double invy, double invo) {
   int k = -1;
   double tc = INFINITY;
@@ -951,14 +883,14 @@ __device__ __noinline__ Seg2 select_segment_age2(const double *__restrict__ th, 
   }
   *tcut = tc;
   double by, bo, byo;
-  age_beta<FL>(th, ld, k < 0 ? 0 : k, by, bo, byo);
+  age_beta<FL>(M, th, ld, k < 0 ? 0 : k, by, bo, byo);
   Seg2 sg;
   sg.tk = 0.0; sg.sA = 0.0; sg.sB = 0.0;
   sg.bA = is_o ? bo : by;
   sg.bB = is_o ? byo : 0.0;
-  if (k >= 0 && age_linear<FL>(k)) {
+  if (k >= 0 && age_linear(M, k)) {
     double ny, no, nyo;
-    age_beta<FL>(th, ld, k + 1, ny, no, nyo);
+    age_beta<FL>(M, th, ld, k + 1, ny, no, nyo);
     const double len = bp[k + 1] - bp[k];
     sg.tk = bp[k];
     sg.sA = is_o ? (no - bo) / len : (ny - by) / len;
@@ -1044,7 +976,7 @@ k_ode_age2(const DevModel M, const double *__restrict__ theta, int64_t ld, int64
       }
     }
   }
-  Seg2 sg = select_segment_age2<FL>(th, ld, bp, nbp, (double)(t0 + d0), g, &tcut, 1.0 / M.Ny, 1.0 / M.No);
+  Seg2 sg = select_segment_age2<FL>(M, th, ld, bp, nbp, (double)(t0 + d0), g, &tcut, 1.0 / M.Ny, 1.0 / M.No);
 
   const int m = M.m;
   const double h = 1.0 / (double)m, a1 = M.a1, gamma = M.gamma;
@@ -1062,11 +994,11 @@ k_ode_age2(const DevModel M, const double *__restrict__ theta, int64_t ld, int64
       const double b = (s == m - 1) ? tday + 1.0 : tday + (double)(s + 1) * h;
       double pa = a;
       if constexpr (PASS2) {
-        if (a >= tcut) sg = select_segment_age2<FL>(th, ld, bp, nbp, a, g, &tcut, 1.0 / M.Ny, 1.0 / M.No);
+        if (a >= tcut) sg = select_segment_age2<FL>(M, th, ld, bp, nbp, a, g, &tcut, 1.0 / M.Ny, 1.0 / M.No);
         while (tcut < b) {
           rk4_piece_age2<TR>(a1, gamma, sg, y, pa, tcut, invN, Ngrp, nb, pairmask, even_lane, need_r);
           pa = tcut;
-          sg = select_segment_age2<FL>(th, ld, bp, nbp, pa, g, &tcut, 1.0 / M.Ny, 1.0 / M.No);
+          sg = select_segment_age2<FL>(M, th, ld, bp, nbp, pa, g, &tcut, 1.0 / M.Ny, 1.0 / M.No);
         }
       }
       rk4_piece_age2<TR>(a1, gamma, sg, y, pa, b, invN, Ngrp, nb, pairmask, even_lane, need_r);
@@ -1105,7 +1037,7 @@ struct Seg4 {
 };
 
 template <int FL>
-__device__ __noinline__ Seg4 select_segment4(const double *__restrict__ th, int64_t ld, const double *bp, int nbp,
+__device__ __noinline__ Seg4 select_segment4(const DevModel &M, const double *__restrict__ th, int64_t ld, const double *bp, int nbp,
                                              double pa, int is_o, int half, double *tcut, double invy, double invo,
                                              int *kcur, bool sorted) {
   int k = -1;
@@ -1123,14 +1055,14 @@ __device__ __noinline__ Seg4 select_segment4(const double *__restrict__ th, int6
   *kcur = k;
   *tcut = tc;
   double by, bo, byo;
-  age_beta<FL>(th, ld, k < 0 ? 0 : k, by, bo, byo);
+  age_beta<FL>(M, th, ld, k < 0 ? 0 : k, by, bo, byo);
   Seg4 sg;
   sg.tk = 0.0; sg.sA = 0.0; sg.sB = 0.0;
   sg.bA = is_o ? bo : by;
   sg.bB = is_o ? byo : 0.0;
-  if (k >= 0 && age_linear<FL>(k)) {
+  if (k >= 0 && age_linear(M, k)) {
     double ny, no, nyo;
-    age_beta<FL>(th, ld, k + 1, ny, no, nyo);
+    age_beta<FL>(M, th, ld, k + 1, ny, no, nyo);
     const double len = bp[k + 1] - bp[k];
     sg.tk = bp[k];
     sg.sA = is_o ? (no - bo) / len : (ny - by) / len;
@@ -1320,7 +1252,7 @@ k_ode_age4(const DevModel M, const double *__restrict__ theta, int64_t ld, int64
   for (int k = 1; k < nbp; ++k) bp_sorted = bp_sorted && bp[k - 1] <= bp[k];
   int kseg = -2;
   const double invy = 1.0 / M.Ny, invo = 1.0 / M.No;
-  Seg4 sg = select_segment4<FL>(th, ld, bp, nbp, (double)(t0 + d0), g, L.half, &tcut, invy, invo, &kseg, bp_sorted);
+  Seg4 sg = select_segment4<FL>(M, th, ld, bp, nbp, (double)(t0 + d0), g, L.half, &tcut, invy, invo, &kseg, bp_sorted);
 
   const int m = M.m;
   const double h = 1.0 / (double)m;
@@ -1356,7 +1288,7 @@ k_ode_age4(const DevModel M, const double *__restrict__ theta, int64_t ld, int64
         double pb = b;
         if constexpr (PASS2) {
           if (pending && pa >= tcut)
-            sg = select_segment4<FL>(th, ld, bp, nbp, pa, g, L.half, &tcut, invy, invo, &kseg, bp_sorted);
+            sg = select_segment4<FL>(M, th, ld, bp, nbp, pa, g, L.half, &tcut, invy, invo, &kseg, bp_sorted);
           if (tcut < b) { pb = tcut; step_done = false; }  // a breakpoint strictly inside (pa, b): cut there
         }
         const double hh = pending ? pb - pa : 0.0, hh2 = 0.5 * hh, h6 = hh / 6.0;
@@ -2523,6 +2455,42 @@ k_quantiles(const double *__restrict__ series, const int *__restrict__ offset, c
 
 // AoS (n x d, one proposal per row) -> SoA (d x ld) transpose, optionally applying
 // transformParams (used by the host-buffer entry points).
+// marginalizeData (R/lib/libMCMC.R:174-188): per posterior draw v = takeAndPad(fun(state), offset - startoffset,
+// simperiod) and ONE number marginfun(v).  marginfun here: max / sum / min / mean of v[j1..j2] (the reference's only
+// call takes the maximum of Re over a 60-day window, R/MCMC/predictMCMC.R:714-717); like R's max() and sum() an NA in
+// the range makes the result NA.  One warp per draw.
+__global__ void __launch_bounds__(128)
+k_marginal(const double *__restrict__ series, const int *__restrict__ offset, const int *__restrict__ padv, int64_t n,
+           int NS, int simperiod, int startoffset, int sa, int sb, double prefill_a, double prefill_b, int kind, int j1,
+           int j2, double *__restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (i >= n) return;
+  const int off = offset[i], pad = padv[i];
+  const double *base = series + i * NS * (int64_t)simperiod;
+  double acc = kind == 0 ? -INFINITY : kind == 2 ? INFINITY : 0.0;
+  bool na = false;
+  for (int j = j1 + lane; j <= j2; j += 32) {
+    double a = NAN;
+    const long long sidx = (long long)off - startoffset - 1 + j;  // sim index read by takeAndPad
+    if (off != EPI_INVALID_DATA_OFFSET && sidx >= 1 && sidx <= simperiod && off - startoffset >= 1) {
+      const int k = (int)sidx - pad - 1;
+      a = k >= 0 ? base[(int64_t)sa * simperiod + k] : prefill_a;
+      if (sb >= 0) a += k >= 0 ? base[(int64_t)sb * simperiod + k] : prefill_b;
+    }
+    if (a != a) na = true;
+    else acc = kind == 0 ? fmax(acc, a) : kind == 2 ? fmin(acc, a) : acc + a;
+  }
+  na = __any_sync(0xffffffffu, na);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double b = __shfl_xor_sync(0xffffffffu, acc, o);
+    acc = kind == 0 ? fmax(acc, b) : kind == 2 ? fmin(acc, b) : acc + b;
+  }
+  if (kind == 3) acc /= (double)(j2 - j1 + 1);
+  if (lane == 0) out[i] = na ? NAN : acc;
+}
+
 __global__ void k_aos_to_soa(const double *__restrict__ aos, double *__restrict__ soa, int64_t n, int d, int64_t ld) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n * d) return;
@@ -2681,6 +2649,14 @@ cudaError_t launch_quantiles(const double *series, const int *offset, const int 
   cudaFuncSetAttribute(k_quantiles, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   k_quantiles<<<period, 256, smem, s>>>(series, offset, pad, n, NS, simperiod, startoffset, sa, sb, prefill_a, prefill_b,
                                         d_probs, n_probs, npow2, d_out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_marginal(const double *series, const int *offset, const int *pad, int64_t n, int NS, int simperiod,
+                            int startoffset, int sa, int sb, double prefill_a, double prefill_b, int kind, int j1, int j2,
+                            double *d_out, cudaStream_t s) {
+  k_marginal<<<(unsigned)((n + 3) / 4), 128, 0, s>>>(series, offset, pad, n, NS, simperiod, startoffset, sa, sb, prefill_a,
+                                                     prefill_b, kind, j1, j2, d_out);
   return cudaGetLastError();
 }
 

@@ -37,6 +37,9 @@ cudaError_t launch_aos_to_soa(const double *aos, double *soa, int64_t n, int d, 
 cudaError_t launch_quantiles(const double *series, const int *offset, const int *pad, int64_t n, int NS, int simperiod,
                              int period, int startoffset, int sa, int sb, double prefill_a, double prefill_b,
                              const double *d_probs, int n_probs, double *d_out, cudaStream_t s);
+cudaError_t launch_marginal(const double *series, const int *offset, const int *pad, int64_t n, int NS, int simperiod,
+                            int startoffset, int sa, int sb, double prefill_a, double prefill_b, int kind, int j1, int j2,
+                            double *d_out, cudaStream_t s);
 cudaError_t launch_dfma(double *out, int blocks, int threads, int iters, cudaStream_t s);
 
 }  // namespace epi

@@ -238,6 +238,21 @@ class Model:
                                             _capi.as_dp(out)), self._h)
         return out
 
+    def marginalizeData(self, sample, fun, startoffset: int, period: int, marginfun):
+        """libMCMC.R:174-188: one number per posterior draw, marginfun(takeAndPad(fun(state), offset - startoffset,
+        3 * period)).  fun as in quantileData; marginfun = (kind, j1, j2) with kind in "max" | "sum" | "min" | "mean"
+        over v[j1..j2] (1-based, inclusive) — e.g. ("max", today, today + 60) of "Re" is predictMCMC.R:714-717.
+        Returns an array of len(sample); everything runs on the device."""
+        names = (fun,) if isinstance(fun, str) else tuple(fun)
+        idx = [self.series_names_ext.index(nm) for nm in names] + [-1]
+        kind, j1, j2 = marginfun
+        th = np.ascontiguousarray(self.transformParams(np.atleast_2d(np.asarray(sample, dtype=np.float64))))
+        out = np.empty(th.shape[0])
+        _capi.check(self._lib.epi_marginalize(self._h, _capi.as_dp(th), th.shape[0], _capi.LAYOUT_AOS, int(period),
+                                              int(startoffset), idx[0], idx[1], {"max": 0, "sum": 1, "min": 2, "mean": 3}[kind],
+                                              int(j1), int(j2), _capi.as_dp(out)), self._h)
+        return out
+
     def calcNominalState(self, state: dict) -> dict:
         """model-age-groups2q.R:367-376"""
         s = dict(state)

@@ -270,6 +270,18 @@ int epi_trajectories_ext(epi_handle *h, const double *theta, int64_t n, int layo
 int epi_quantiles(epi_handle *h, const double *theta, int64_t n, int layout, int32_t period, int32_t startoffset,
                   int32_t series_a, int32_t series_b, const double *probs, int32_t n_probs, double *out);
 
+/* marginalizeData(sample, fun, startoffset, period, marginfun) of R/lib/libMCMC.R:174-188: per posterior draw
+ * v = takeAndPad(fun(state), state$offset - startoffset, 3*period) and ONE number marginfun(v), for the marginals
+ * the reference computes (R/MCMC/predictMCMC.R:714-717 takes max(v[j1:j2]) of Re): kind 0 = max, 1 = sum, 2 = min,
+ * 3 = mean of v[j1..j2] (1-based, inclusive, <= 3*period); an NA inside the range gives NA, as R's max()/sum() do.
+ * theta, series_a/series_b as for epi_quantiles (no limit on n).  out: HOST, n doubles.                          */
+#define EPI_MARGIN_MAX 0
+#define EPI_MARGIN_SUM 1
+#define EPI_MARGIN_MIN 2
+#define EPI_MARGIN_MEAN 3
+int epi_marginalize(epi_handle *h, const double *theta, int64_t n, int layout, int32_t period, int32_t startoffset,
+                    int32_t series_a, int32_t series_b, int32_t kind, int32_t j1, int32_t j2, double *out);
+
 /* ---- on-device sampler (chain state never leaves the GPU) ------------------ */
 typedef struct epi_sampler_cfg {
   int32_t kind;        /* EPI_SAMPLER_* */

@@ -97,6 +97,11 @@ SEXP C_epi_create(SEXP flavour, SEXP period, SEXP substeps, SEXP g, SEXP device)
   D.case_nbinom_size1 = num(g, "case_nbinom_size1", 0); D.case_nbinom_sizey2 = num(g, "case_nbinom_sizey2", 0);
   D.case_nbinom_sizeo2 = num(g, "case_nbinom_sizeo2", 0); D.hosp_nbinom_size1 = num(g, "hosp_nbinom_size1", 0);
   D.hosp_nbinom_size2 = num(g, "hosp_nbinom_size2", 0); D.hosp_last7 = num(g, "hosp_last7", 0);
+  /* age-2x only (R/models/model-age-groups2x.R:216-221,278-279,734,749) */
+  D.d9 = (int)num(g, "d9", 0); D.d10 = (int)num(g, "d10", 0); D.d12 = (int)num(g, "d12", 0);
+  D.duncertain = (int)num(g, "duncertain", 0);
+  D.d_symp_cases = (int)num(g, "d_symp_cases", 0); D.d_all_cases = (int)num(g, "d_all_cases", 0);
+  D.symp_cases_factor = num(g, "symp_cases_factor", 0);
   epi_handle *h = NULL;
   int rc = epi_create(&desc, &D, Rf_asInteger(device), &h);
   if (rc) Rf_error("epi_create failed (%d): %s", rc, epi_last_error(NULL));

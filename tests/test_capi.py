@@ -84,7 +84,7 @@ def test_r_shim_type_checks_against_the_header():
         assert m and len(m.group(1).split(",")) == int(arity), name
     # every .Call in the drop-in model files names a registered routine with that many arguments
     registered = dict(re.findall(r'\{"(C_\w+)", \(DL_FUNC\)&\w+, (\d+)\}', text))
-    for fn in ("model-age-groups2q-gpu.R", "model-age-groups2i-gpu.R", "model-simple-ode-drj-cmp-gpu.R"):
+    for fn in ("model-age-groups2q-gpu.R", "model-age-groups2i-gpu.R", "model-age-groups2x-gpu.R", "model-simple-ode-drj-cmp-gpu.R"):
         rsrc = open(os.path.join(ROOT, "r", fn)).read()
         for call in re.findall(r'\.Call\("(C_\w+)"', rsrc):
             assert call in registered, (fn, call)
@@ -149,6 +149,8 @@ def test_r_model_files_pass_only_globals_the_shim_reads():
     assert len(looked_up) > 30
     need = {"model-age-groups2q-gpu.R": {"y_N", "o_N", "y_ifr", "o_wdmorti", "d8", "hosp_last7", "g", "gtrimp"},
             "model-age-groups2i-gpu.R": {"y_N", "o_N", "y_ifr", "d7", "hosp_nbinom_size"},
+            "model-age-groups2x-gpu.R": {"y_N", "o_N", "y_ifr", "o_wdmorti", "d9", "d10", "d12", "duncertain", "d_symp_cases",
+                                         "d_all_cases", "symp_cases_factor", "hosp_last7", "g", "gtrimp"},
             "model-simple-ode-drj-cmp-gpu.R": {"N", "dhospi", "dmorti", "mort_nbinom_size"}}
     for fn, essentials in need.items():
         text = re.sub(r"#[^\n]*", "", open(os.path.join(rdir, fn)).read())

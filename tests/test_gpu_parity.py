@@ -304,6 +304,44 @@ def test_quantile_data_matches_reference_semantics(name, fun, oracle):
     M.close()
 
 
+@pytest.mark.parametrize("name,fun,margin", [("A300", "Re", ("max", 40, 100)), ("A300", ("y.hospi", "o.hospi"), ("sum", 1, 120)),
+                                             ("X300", "y.casei", ("mean", 100, 160)), ("S120", "hospi", ("min", 5, 30))])
+def test_marginalize_data_matches_reference_semantics(name, fun, margin, oracle):
+    """marginalizeData (libMCMC.R:174-188; predictMCMC.R:714-717 takes the maximum of Re over a window) on the device
+    against the oracle + numpy: calculateModel(params, 3 * period), takeAndPad by the draw's data_offset, one number
+    per draw, NA when the range holds an NA."""
+    from epi_mcmc_b200.model import load_dataset
+    ds = load_dataset(name)
+    M = _model(name, 4)
+    mn, mx, init = M.df_params["min"], M.df_params["max"], M.df_params["init"]
+    rng = np.random.default_rng(6)
+    n, period, startoffset = 300, 100, 2
+    sample = np.clip(init + (rng.uniform(size=(n, M.d)) - 0.5) * 0.04 * (mx - mn), mn, mx)
+    got = M.marginalizeData(sample, fun, startoffset, period, margin)
+    names = (fun,) if isinstance(fun, str) else fun
+    kind, j1, j2 = margin
+    simperiod = 3 * period
+    model_th = M.transformParams(sample)
+    ref = np.full(n, np.nan)
+    for i in range(n):
+        ser, _, off, pad = oracle.trajectory(ds["flavour"], ds, model_th[i], ds["period"], 4, calc_period=simperiod, ext=True)
+        if off == 10000:
+            continue
+        vec = np.zeros(pad + simperiod)
+        for nm in names:
+            vec[pad:] += ser[M.series_names_ext.index(nm)]
+        v = np.full(simperiod, np.nan)
+        take = vec[off - startoffset - 1:simperiod]
+        v[:len(take)] = take
+        ref[i] = {"max": np.max, "sum": np.sum, "min": np.min, "mean": np.mean}[kind](v[j1 - 1:j2])
+    assert np.array_equal(np.isnan(got), np.isnan(ref))
+    ok = ~np.isnan(ref)
+    assert ok.sum() > n // 2
+    scale = np.abs(ref[ok]).max() + 1e-300
+    assert np.abs(got[ok] - ref[ok]).max() <= 1e-9 * scale + 64 * 2.0 ** -52 * ds["N"]
+    M.close()
+
+
 @pytest.mark.parametrize("name,m", [("A300", 4), ("I290", 4), ("S365", 2), ("NE120", 1)])
 def test_pass2_restart_is_bit_identical(name, m, monkeypatch):
     """Pass 2 resumes from the pass-1 checkpoint after its first floor(min breakpoint) - t0 days
