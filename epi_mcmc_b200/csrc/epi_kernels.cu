@@ -2545,14 +2545,16 @@ static cudaError_t launch_eval_fl(const EvalArgs &a) {
   cudaStream_t s = a.stream;
   if (a.ev) cudaEventRecord(a.ev[0], s);
   const unsigned pair_blocks = (unsigned)((2 * n + 63) / 64);
-  // Two lanes per chain double the resident warps, but need ~124 registers per lane: they win
-  // while all 2n lanes fit one wave (n <= 256 chains per SM), thread-per-chain wins above that
-  // (measured on B200, 65,536 chains: 2.25 ms vs 2.07 ms for pass 2).
-  // Four lanes per chain (k_ode_age4) while a thread-per-chain launch would leave the SMs short of warps; the
-  // thresholds are measured (profiles/r2_summary.md).  EPI_ODE_LANES = 1 | 2 | 4 forces one mapping (tests, bench).
+  // Lanes per chain of the age ODE passes.  Thread per chain for full batches; four lanes per chain (k_ode_age4)
+  // while a thread-per-chain launch would leave most schedulers with a single warp (<= 64 chains per SM: the
+  // 8,192-chain shard of the strong-scaled BASELINE configuration).  Two lanes per chain (k_ode_age2, round 1) lose
+  // at every size since the other two were tuned; kept for EPI_ODE_LANES = 2.  EPI_ODE_LANES = 1 | 2 | 4 forces one
+  // mapping (tests, bench).
   int lanes = 1;
   if constexpr (Traits<FL>::kAge && !Traits<FL>::k2x) {  // (age-2x: thread per chain only)
-    lanes = a.ode_lanes ? a.ode_lanes : (n <= (int64_t)n_sm * 256 ? 4 : 1);
+    // measured on the posterior cloud (profiles/r2_summary.md): 4,096 chains 0.59 ms (four lanes) vs 0.69 (one), 8,192
+    // 0.77 vs 0.82, 12,288 0.96 vs 0.95, 16,384 1.18 vs 1.07, 32,768 2.20 vs 1.70; two lanes per chain never win
+    lanes = a.ode_lanes ? a.ode_lanes : (n <= (int64_t)n_sm * 64 ? 4 : 1);
   }
   constexpr bool kFallback = !Traits<FL>::k2x;  // the R-tracking fallback instance exists where the hot one does not integrate R
   const bool use_pair = lanes == 2, use_quad = lanes == 4;

@@ -16,6 +16,7 @@
  *   C_epi_logpost     -> epi_eval        batched calclogl(transformParams(.)) + calclogp(.)
  *   C_epi_trajectories-> epi_trajectories / epi_trajectories_ext   calculateModel(params, period) for many draws
  *   C_epi_quantiles   -> epi_quantiles   quantileData (libMCMC.R:151-172)
+ *   C_epi_marginalize -> epi_marginalize marginalizeData (libMCMC.R:174-188)
  *   C_epi_df_params   -> epi_df_params
  *   C_epi_run_mcmc    -> epi_sampler_*   drjacoby::run_mcmc (fitMCMC-drj.R:48-57) for a population of chains
  *                                        that stays on the GPU: burn-in, then recorded sampling draws
@@ -173,6 +174,25 @@ SEXP C_epi_quantiles(SEXP ptr, SEXP params, SEXP period, SEXP startoffset, SEXP 
   return out;
 }
 
+/* .Call(C_epi_marginalize, handle, params, period, startoffset, series_a, series_b, kind, j1, j2): marginalizeData of
+ * R/lib/libMCMC.R:174-188 for marginfun = max (kind 0) / sum (1) / min (2) / mean (3) of v[j1:j2]
+ * (R/MCMC/predictMCMC.R:714-717 takes the maximum of Re over the next 60 days).  Returns one number per draw. */
+SEXP C_epi_marginalize(SEXP ptr, SEXP params, SEXP period, SEXP startoffset, SEXP series_a, SEXP series_b, SEXP kind,
+                       SEXP j1, SEXP j2) {
+  epi_handle *h = get_handle(ptr);
+  const int d = epi_n_params(h);
+  if (!Rf_isReal(params) || XLENGTH(params) == 0 || XLENGTH(params) % d)
+    Rf_error("epimcmc: params must be a numeric (double) matrix with %d rows", d);
+  const R_xlen_t n = XLENGTH(params) / d;
+  SEXP out = PROTECT(Rf_allocVector(REALSXP, n));
+  int rc = epi_marginalize(h, REAL(params), (int64_t)n, EPI_LAYOUT_AOS, Rf_asInteger(period), Rf_asInteger(startoffset),
+                           Rf_asInteger(series_a), Rf_asInteger(series_b), Rf_asInteger(kind), Rf_asInteger(j1),
+                           Rf_asInteger(j2), REAL(out));
+  UNPROTECT(1);
+  if (rc) Rf_error("epi_marginalize failed (%d): %s", rc, epi_last_error(h));
+  return out;
+}
+
 SEXP C_epi_df_params(SEXP ptr) {
   epi_handle *h = get_handle(ptr);
   const int d = epi_n_params(h);
@@ -189,7 +209,9 @@ SEXP C_epi_df_params(SEXP ptr) {
 /* .Call(C_epi_run_mcmc, handle, theta0, chains, burnin, samples, thin, rungs, GTI_pow, seed, kind): what
  * fitMCMC-drj.R:48-57 asks of drjacoby::run_mcmc, for `chains` chains per rung on the device.
  *   theta0: NULL (start at init + jitter) or a d x (chains * rungs) numeric matrix of starting points;
- *   kind:   1 = DE-MC (population proposals), 0 = adaptive random-walk Metropolis;
+ *   kind:   1 = DE-MC (population proposals), 0 = adaptive random-walk Metropolis, 2 = drjacoby's own update
+ *           (one parameter at a time on the logit-reparameterised box, Robbins-Monro bandwidths; burnin / samples
+ *           then count SWEEPS of d evaluations, as drjacoby's iterations do);
  *   rungs / GTI_pow: drjacoby's tempering ladder (1 = no tempering); draws are the COLD rung's.
  * Burn-in adapts the proposal shape from the population and refreshes the DE-MC partner snapshot every 10
  * iterations; both are frozen for the sampling phase.  Returns list(draws = d x chains x kept array,
@@ -205,7 +227,7 @@ SEXP C_epi_run_mcmc(SEXP ptr, SEXP theta0, SEXP chains, SEXP burnin, SEXP sample
     Rf_error("epimcmc: theta0 must be NULL or a numeric %d x %d matrix", d, n);
   epi_sampler_cfg cfg;
   memset(&cfg, 0, sizeof cfg);
-  cfg.kind = Rf_asInteger(kind) ? EPI_SAMPLER_DEMC : EPI_SAMPLER_RWM;
+  cfg.kind = Rf_asInteger(kind) == 2 ? EPI_SAMPLER_DRJ : Rf_asInteger(kind) ? EPI_SAMPLER_DEMC : EPI_SAMPLER_RWM;
   cfg.n_chains = n;
   cfg.seed = (uint64_t)Rf_asReal(seed);
   cfg.scale = 1.0;
@@ -250,7 +272,8 @@ SEXP C_epi_run_mcmc(SEXP ptr, SEXP theta0, SEXP chains, SEXP burnin, SEXP sample
   SET_VECTOR_ELT(out, 0, draws);
   SET_VECTOR_ELT(out, 1, logpost);
   /* acceptance of the SAMPLING phase (all rungs pooled; drjacoby reports it per phase too) */
-  SET_VECTOR_ELT(out, 2, Rf_ScalarReal(it > it0 ? (double)(acc - acc0) / ((double)(it - it0) * n) : 0.0));
+  const double moves = (double)(it - it0) * n * (cfg.kind == EPI_SAMPLER_DRJ ? d : 1);  /* a sweep decides d moves per chain */
+  SET_VECTOR_ELT(out, 2, Rf_ScalarReal(it > it0 ? (double)(acc - acc0) / moves : 0.0));
   SET_VECTOR_ELT(out, 3, Rf_ScalarReal((double)ev));
   UNPROTECT(3);
   return out;
@@ -261,6 +284,7 @@ static const R_CallMethodDef call_methods[] = {
     {"C_epi_logpost", (DL_FUNC)&C_epi_logpost, 2},
     {"C_epi_trajectories", (DL_FUNC)&C_epi_trajectories, 4},
     {"C_epi_quantiles", (DL_FUNC)&C_epi_quantiles, 7},
+    {"C_epi_marginalize", (DL_FUNC)&C_epi_marginalize, 9},
     {"C_epi_df_params", (DL_FUNC)&C_epi_df_params, 1},
     {"C_epi_run_mcmc", (DL_FUNC)&C_epi_run_mcmc, 10},
     {NULL, NULL, 0}};

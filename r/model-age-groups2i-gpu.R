@@ -106,6 +106,15 @@ quantileData_gpu <- function(sample, series, startoffset, period, quantiles) {
           if (length(idx) > 1) idx[2] else -1L, as.numeric(quantiles))
 }
 
+## marginalizeData (libMCMC.R:174-188) on the GPU for marginfun = max / sum / min / mean of v[j1:j2], e.g. the
+## maximum of Re over the next two months (predictMCMC.R:714-717): marginalizeData_gpu(data_sample, "Re", 0, Range, "max", j1, j2)
+marginalizeData_gpu <- function(sample, series, startoffset, period, kind, j1, j2) {
+    params <- apply(sample[, fit.paramnames], 1, function(p) transformParams(unlist(p, use.names = FALSE)))
+    idx <- match(series, series.names) - 1L
+    .Call("C_epi_marginalize", epi_handle, params, as.integer(period), as.integer(startoffset), idx[1],
+          if (length(idx) > 1) idx[2] else -1L, match(kind, c("max", "sum", "min", "mean")) - 1L, as.integer(j1), as.integer(j2))
+}
+
 calcNominalState <- function(state) {
     state$case <- state$y.case + state$o.case
     state$died <- state$y.died + state$o.died
