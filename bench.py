@@ -134,9 +134,9 @@ def r_probe():
 
 def f_alg(flavour, P, m, taps_mean, n_terms, n_prior):
     """ALGORITHMIC FLOP per evaluation, SURVEY.md §8d"""
-    age = flavour in ("age2q", "age2i")
+    age = flavour in ("age2q", "age2i", "age2x")
     S, K, C1, C2 = (10, 6, 2, 6) if age else (4, 2, 1, 2)
-    P1 = 60 if flavour == "age2q" else P  # pass 1: 60 days in 2q, the whole period in 2i / simple
+    P1 = 60 if flavour in ("age2q", "age2x") else P  # pass 1: 60 days in 2q / 2x, the whole period in 2i / simple
     F_rhs = 124 if age else 72
     steps = m * (P1 + P)
     ode = steps * (4 * F_rhs + 14 * S)
@@ -149,16 +149,19 @@ def f_alg(flavour, P, m, taps_mean, n_terms, n_prior):
     }
     # the removed compartment(s) are not integrated on the hot path (bit-identical): the RK4
     # update of 2 (age) / 1 (simple) of the S states is not executed
-    n_r = 2 if age else 1
+    n_r = 0 if flavour == "age2x" else 2 if age else 1   # (2x: waning immunity, R is always integrated)
     return dict(total=total, ode=ode, per_kernel=per_kernel, score_per_day=C2 * 2 * taps_mean + 6 * C2,
                 ode_executed_share=(4 * F_rhs + 14 * (S - n_r)) / (4 * F_rhs + 14 * S))
 
 
 def mean_taps(flavour, theta):
-    if flavour not in ("age2q", "age2i"):
+    if flavour not in ("age2q", "age2i", "age2x"):
         return 16.0
     t = []
-    if flavour == "age2q":
+    if flavour == "age2x":
+        prof = ((theta[:, 46], 2.5), (theta[:, 11], theta[:, 19]), (theta[:, 12], theta[:, 20]),
+                (theta[:, 47], 2.5), (theta[:, 15], theta[:, 19]), (theta[:, 16], theta[:, 20]))
+    elif flavour == "age2q":
         prof = ((theta[:, 43], 5.0), (theta[:, 11], theta[:, 19]), (theta[:, 12], theta[:, 20]),
                 (theta[:, 44], 5.0), (theta[:, 15], theta[:, 19]), (theta[:, 16], theta[:, 20]))
     else:
@@ -415,13 +418,13 @@ def rooflines(M, ds, args_substeps, theta, n, kms, step_ms, peak_tf, ncu):
     with SURVEY 8d's formula (the reference's arithmetic, reductions applied) and can exceed 1 for the ODE launches."""
     d = M.d
     fa = f_alg(ds["flavour"], ds["period"], args_substeps, mean_taps(ds["flavour"], theta), _n_terms(M),
-               {"age2q": 38, "age2i": 24}.get(ds["flavour"], 3))
+               {"age2q": 38, "age2i": 24, "age2x": 41}.get(ds["flavour"], 3))
     # pass-2 restart: D leading days are taken from the pass-1 checkpoint instead of being integrated
     # again (bit-identical, DESIGN.md §3).  SURVEY §8d: report F_alg with the reduced step count too.
     off_s, pad_s, _ = M.eval_detail(theta[:4096])
     th = theta[:4096]
     lo_ = ds["lockdown_offset"]
-    if ds["flavour"] == "age2q":
+    if ds["flavour"] in ("age2q", "age2x"):
         minbp = off_s + lo_ + th[:, 18]
         cap = 59
     elif ds["flavour"] == "age2i":
@@ -440,7 +443,7 @@ def rooflines(M, ds, args_substeps, theta, n, kms, step_ms, peak_tf, ncu):
     # SURVEY §8d's list of admissible reductions.  Same window arithmetic as the kernels, in numpy.
     P_ = ds["period"]
     n_obs = ([ds["n_dcasei"], ds["n_dcasei"], ds["n_dhospi"], ds["n_dmorti"], ds["n_dmorti"]]
-             if ds["flavour"] in ("age2q", "age2i") else [ds["n_dhospi"], ds["n_dmorti"]])
+             if ds["flavour"] in ("age2q", "age2i", "age2x") else [ds["n_dhospi"], ds["n_dmorti"]])
     off_e = np.where(off_s == 10000, 1, off_s).astype(np.int64)
     T_ = pad_s.astype(np.int64) + P_
     tlo, thi = T_.copy(), np.ones_like(T_)
@@ -457,7 +460,7 @@ def rooflines(M, ds, args_substeps, theta, n, kms, step_ms, peak_tf, ncu):
     step_flop = fa["per_kernel"]["ode_pass2"] / P_                        # per integrated day
     # whole-period pass 1 (simple / Ne / age-2i) in two rounds: 128 days for everybody, all days again for the
     # chains that did not cross the threshold there (kPass1Chunk in epi_kernels.cu)
-    P1_ = 60 if ds["flavour"] == "age2q" else P_
+    P1_ = 60 if ds["flavour"] in ("age2q", "age2x") else P_
     chunk_on = os.environ.get("EPI_PASS1_CHUNK", "1") != "0" and P1_ > 160
     if chunk_on:
         first = off_s + lo_ - pad_s - 1
@@ -471,8 +474,8 @@ def rooflines(M, ds, args_substeps, theta, n, kms, step_ms, peak_tf, ncu):
                                      score=fa["per_kernel"]["score"] - (P_ - min(days_swept, P_)) * fa["score_per_day"])
     fa["total_executed"] = sum(fa["per_kernel_executed"].values())
     hbm, hbm_src = hbm_peak()
-    age = ds["flavour"] in ("age2q", "age2i")
-    NGb, NEQb, padb = (2, 8, 80 if ds["flavour"] == "age2i" else 64) if age else (1, 3, 64)
+    age = ds["flavour"] in ("age2q", "age2i", "age2x")
+    NGb, NEQb, padb = (2, 10 if ds["flavour"] == "age2x" else 8, 80 if ds["flavour"] == "age2i" else 64) if age else (1, 3, 64)
     ck_days = min(P1_, 64)
     row = lambda days: NGb * ((days + 1) & ~1) * 8
     bytes_alg = {
@@ -543,7 +546,8 @@ def secondary_legs(args, comm, dev, stream, peak_tf, ncu_all):
             ("NE120", 4096, 4, "configs[1]: model-Ne, 4,096 chains"),
             ("A365", 65536, 4, "configs[2] at the 365-day horizon"),
             ("A300", 65536, 1, "configs[2] on the daily grid (m = 1, the north_star's wording)"),
-            ("I290", 65536, 4, "configs[2], secondary anchor model-age-groups2i")]
+            ("I290", 65536, 4, "configs[2], secondary anchor model-age-groups2i"),
+            ("X300", 65536, 4, "configs[2], later generation model-age-groups2x (waning immunity, incidence-based observation model)")]
     out = []
     for wl, total, m, what in legs:
         try:
@@ -748,9 +752,9 @@ def main():
 def _n_terms(M):
     # rows of the likelihood term table (a-7): age-2q with n obs days: 2(n+2) + (n+10) + 1 + 2n
     ds = M.data
-    if ds["flavour"] == "age2q":
+    if ds["flavour"] in ("age2q", "age2x"):
         n = ds["n_dcasei"]
-        return 2 * (n + 2) + (ds["n_dhospi"] + 10) + 1 + 2 * ds["n_dmorti"]
+        return 2 * (n + 2) + (ds["n_dhospi"] + 10) + 1 + 2 * ds["n_dmorti"] + (16 if ds["flavour"] == "age2x" else 0)
     if ds["flavour"] == "age2i":
         return 2 * (ds["n_dcasei"] + 2) + ds["n_dhospi"] + 2 * ds["n_dmorti"]
     return ds["n_dhospi"] + ds["n_dmorti"] + 1
@@ -758,7 +762,7 @@ def _n_terms(M):
 
 def _ws_mb(ds, n):
     P = ds["period"]
-    if ds["flavour"] == "age2q":
+    if ds["flavour"] in ("age2q", "age2x"):
         return n * ((P + 60) * 2 * 8 + 6 * 64 * 8) / 1e6
     if ds["flavour"] == "age2i":
         return n * (2 * P * 2 * 8 + 2 * 80 * 4 * 8) / 1e6

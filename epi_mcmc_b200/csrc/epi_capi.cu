@@ -646,6 +646,7 @@ extern "C" void epi_destroy(epi_handle *h) {
   for (auto &ev : h->ev) if (ev) cudaEventDestroy(ev);
   if (h->stream) cudaStreamDestroy(h->stream);
   if (h->stream2) cudaStreamDestroy(h->stream2);
+  if (h->ev_ws) cudaEventDestroy(h->ev_ws);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   for (int k = 0; k < epi_handle::kMaxWays - 1; ++k) {
     if (h->split_stream[k]) { cudaStreamSynchronize(h->split_stream[k]); cudaStreamDestroy(h->split_stream[k]); }
@@ -694,6 +695,7 @@ int epi_ensure_workspace(epi_handle *h, Workspace &w, const DevModel &M, int64_t
   const int NG = is_age(M.flavour) ? 2 : 1, NK = is_age(M.flavour) ? 6 : 2;
   if (n <= w.cap && M.P <= w.P && want_series <= w.ns) return EPI_OK;
   cudaStreamSynchronize(h->stream);
+  if (h->ws_busy) cudaEventSynchronize(h->ev_ws);  // an evaluation on a caller's stream may still be using the buffers
   const int64_t cap = std::max<int64_t>(n, w.cap);
   const int P = std::max(M.P, w.P), P1 = std::max(M.P1, w.P1);
   const int NS = std::max(want_series, w.ns);
@@ -761,10 +763,17 @@ static EvalArgs make_args(epi_handle *h, Workspace &w, const DevModel &M, const 
 int epi_launch_eval_ws(epi_handle *h, Workspace &w, const DevModel &M, const double *d_theta, int64_t ld, int64_t n,
                        int model_space, double *d_logl, double *d_logp, int *d_status, double *d_terms,
                        double *d_series, cudaStream_t stream, int ns_total) {
+  // every whole-batch evaluation uses the SAME scratch (histories, checkpoints, profiles, offsets): one that runs on
+  // another stream than its predecessor waits for the predecessor's last kernel
+  if (!h->ev_ws) cudaEventCreateWithFlags(&h->ev_ws, cudaEventDisableTiming);
+  if (h->ws_busy && h->ws_stream != stream) cudaStreamWaitEvent(stream, h->ev_ws, 0);
   EvalArgs a = make_args(h, w, M, d_theta, ld, n, 0, model_space, d_logl, d_logp, d_status, d_terms, d_series, stream, ns_total);
   a.ev = h->timing ? h->ev : nullptr;
   const cudaError_t e = launch_eval(a);
   if (e != cudaSuccess) return epi_fail(h, EPI_ERR_CUDA, "kernel launch: %s", cudaGetErrorString(e));
+  cudaEventRecord(h->ev_ws, stream);
+  h->ws_stream = stream;
+  h->ws_busy = true;
   return EPI_OK;
 }
 
@@ -967,7 +976,13 @@ extern "C" int epi_trajectories_ext(epi_handle *h, const double *theta, int64_t 
 extern "C" int epi_quantiles(epi_handle *h, const double *theta, int64_t n, int layout, int32_t period, int32_t startoffset,
                              int32_t series_a, int32_t series_b, const double *probs, int32_t n_probs, double *out) {
   if (!h || !theta || !probs || !out || n < 1 || n_probs < 1 || period < 1) return epi_fail(h, EPI_ERR_ARG, "bad argument");
-  if (n > 8192) return epi_fail(h, EPI_ERR_ARG, "epi_quantiles supports at most 8192 draws (got %lld)", (long long)n);
+  // up to 8,192 draws a day's values are sorted in shared memory, beyond that in a global scratch buffer of
+  // period x 2^ceil(log2 n) doubles (capped at 4 GiB)
+  int64_t npow2 = 1;
+  while (npow2 < n) npow2 <<= 1;
+  const bool big = n > 8192;
+  if (big && (double)npow2 * period * 8.0 > 4294967296.0)
+    return epi_fail(h, EPI_ERR_ARG, "epi_quantiles: %lld draws x %d days need more than 4 GiB of sort scratch", (long long)n, period);
   const bool age = is_age(h->M.flavour), fixed_p1 = fixed_pass1(h->M.flavour);
   const int NSb = n_series_of(h->M.flavour, false), NSx = n_series_of(h->M.flavour, true);
   if (series_a < 0 || series_a >= NSx || series_b >= NSx) return epi_fail(h, EPI_ERR_ARG, "series index out of range");
@@ -995,13 +1010,16 @@ extern "C" int epi_quantiles(epi_handle *h, const double *theta, int64_t n, int 
     if (age) return sidx == 0 ? M.Ny - 1.0 : sidx == 1 ? M.No : (sidx == 8 || sidx == 11) ? NAN : 0.0;
     return sidx == 0 ? M.N - 1.0 : sidx == 3 ? 1.0 : 0.0;
   };
+  double *d_scratch = nullptr;
+  if (big) CUDA_OK(h, cudaMalloc(&d_scratch, sizeof(double) * (size_t)npow2 * period));
   cudaError_t e = launch_quantiles(w.series, w.offset, w.pad, n, NS, simperiod, period, startoffset, series_a, series_b,
-                                   prefill(series_a), prefill(series_b), d_probs, n_probs, d_out, h->stream);
+                                   prefill(series_a), prefill(series_b), d_probs, n_probs, d_out, d_scratch, h->stream);
   h->launches += 1;
   if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, sizeof(double) * (size_t)period * n_probs, cudaMemcpyDeviceToHost, h->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
   cudaFree(d_probs);
   cudaFree(d_out);
+  cudaFree(d_scratch);
   if (e != cudaSuccess) return epi_fail(h, EPI_ERR_CUDA, "epi_quantiles: %s", cudaGetErrorString(e));
   return EPI_OK;
 }

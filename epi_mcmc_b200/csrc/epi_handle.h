@@ -61,6 +61,11 @@ struct epi_handle {
   cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
   bool slot_used[2] = {false, false}, slot_pending[2] = {false, false};
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  // whole-batch evaluations share one scratch workspace: the stream the last one ran on and an event at its tail,
+  // so that an evaluation on ANOTHER stream (epi_eval_device with a caller's stream) is ordered behind it
+  cudaStream_t ws_stream = nullptr;
+  cudaEvent_t ev_ws = nullptr;
+  bool ws_busy = false;
   bool timing = false;
   int64_t launches = 0;
   std::string err;

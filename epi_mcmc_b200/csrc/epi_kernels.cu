@@ -2401,11 +2401,15 @@ k_series(const DevModel M, const double *__restrict__ theta, int64_t ld, int64_t
 // quantileData (R/lib/libMCMC.R:151-172): one block per output day; the n draws' values of that
 // day are gathered (takeAndPad alignment by each draw's data_offset), bitonic-sorted in shared
 // memory with NA last, and the R type-7 quantiles are interpolated.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 k_quantiles(const double *__restrict__ series, const int *__restrict__ offset, const int *__restrict__ padv, int64_t n,
             int NS, int simperiod, int startoffset, int sa, int sb, double prefill_a, double prefill_b,
-            const double *__restrict__ probs, int n_probs, int npow2, double *__restrict__ out) {
-  extern __shared__ double v[];
+            const double *__restrict__ probs, int n_probs, int npow2, double *__restrict__ out,
+            double *__restrict__ gscratch) {
+  // the day's values: in shared memory up to 8,192 draws, else in this block's slice of a global scratch buffer
+  // (the same block-wide bitonic network, through L2)
+  extern __shared__ double vsh[];
+  double *v = gscratch ? gscratch + (size_t)blockIdx.x * npow2 : vsh;
   __shared__ int n_valid;
   const int j = blockIdx.x + 1;  // day, 1-based
   if (threadIdx.x == 0) n_valid = 0;
@@ -2644,13 +2648,13 @@ cudaError_t launch_aos_to_soa(const double *aos, double *soa, int64_t n, int d, 
 
 cudaError_t launch_quantiles(const double *series, const int *offset, const int *pad, int64_t n, int NS, int simperiod,
                              int period, int startoffset, int sa, int sb, double prefill_a, double prefill_b,
-                             const double *d_probs, int n_probs, double *d_out, cudaStream_t s) {
+                             const double *d_probs, int n_probs, double *d_out, double *d_scratch, cudaStream_t s) {
   int npow2 = 1;
   while (npow2 < n) npow2 <<= 1;
-  const size_t smem = sizeof(double) * (size_t)npow2;
+  const size_t smem = d_scratch ? 0 : sizeof(double) * (size_t)npow2;
   cudaFuncSetAttribute(k_quantiles, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  k_quantiles<<<period, 256, smem, s>>>(series, offset, pad, n, NS, simperiod, startoffset, sa, sb, prefill_a, prefill_b,
-                                        d_probs, n_probs, npow2, d_out);
+  k_quantiles<<<period, d_scratch ? 1024 : 256, smem, s>>>(series, offset, pad, n, NS, simperiod, startoffset, sa, sb,
+                                                         prefill_a, prefill_b, d_probs, n_probs, npow2, d_out, d_scratch);
   return cudaGetLastError();
 }
 

@@ -36,7 +36,7 @@ cudaError_t launch_eval(const EvalArgs &a);
 cudaError_t launch_aos_to_soa(const double *aos, double *soa, int64_t n, int d, int64_t ld, cudaStream_t s);
 cudaError_t launch_quantiles(const double *series, const int *offset, const int *pad, int64_t n, int NS, int simperiod,
                              int period, int startoffset, int sa, int sb, double prefill_a, double prefill_b,
-                             const double *d_probs, int n_probs, double *d_out, cudaStream_t s);
+                             const double *d_probs, int n_probs, double *d_out, double *d_scratch, cudaStream_t s);
 cudaError_t launch_marginal(const double *series, const int *offset, const int *pad, int64_t n, int NS, int simperiod,
                             int startoffset, int sa, int sb, double prefill_a, double prefill_b, int kind, int j1, int j2,
                             double *d_out, cudaStream_t s);

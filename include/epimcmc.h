@@ -212,19 +212,24 @@ int epi_eval_wait(epi_handle *h, int slot);
 
 /* Same, all buffers already resident on the handle's device.  theta_soa is
  * d x n (EPI_LAYOUT_SOA).  Launches on `stream` (a cudaStream_t passed as
- * void*, NULL = the handle's own stream) and does not synchronise.            */
+ * void*, NULL = the handle's own stream) and does not synchronise the host.
+ * Whole-batch evaluations of one handle share its scratch buffers: the library
+ * orders each of them behind the previous one on the device (an event), on
+ * whichever streams they run, so they never overlap; the caller orders the
+ * call against whatever produces theta and consumes the results.             */
 int epi_eval_device(epi_handle *h, const double *d_theta_soa, int64_t n,
                     double *d_logl, double *d_logp, int32_t *d_status, void *stream);
 
 /* The chains [first, first + n) of a device-resident batch of n_total chains
  * (theta_soa d x ld, outputs indexed by chain like epi_eval_device's).  Ranges
- * that do not overlap may be in flight on different streams at the same time —
- * how a small batch keeps the GPU busy: the ODE passes of <= 16 k chains are
- * latency bound, so K ranges on K streams, each a free-running pipeline, overlap
- * the score kernel of one range with the ODE passes of the others (bench.py's
- * strong-scaled runs, 65,536 chains over 8 GPUs).  `first` must be a multiple
- * of 128; epi_reserve(h, n_total) must have sized the workspace before the first
- * range call (growing it would free buffers other ranges are using).          */
+ * that do not overlap use disjoint scratch rows and may be in flight on
+ * different streams at the same time (the library does not order them; the
+ * caller does, against the producer of theta and the consumer of the results).
+ * Measured (profiles/r2_summary.md): slicing a latency-bound shard of <= 16 k
+ * chains this way buys no throughput — each slice's ODE passes take as long as
+ * the whole shard's.  `first` must be a multiple of 128; epi_reserve(h, n_total)
+ * must have sized the workspace before the first range call (growing it would
+ * free buffers other ranges are using).                                       */
 int epi_eval_device_range(epi_handle *h, const double *d_theta_soa, int64_t ld, int64_t n_total,
                           int64_t first, int64_t n, double *d_logl, double *d_logp, int32_t *d_status,
                           void *stream);
@@ -265,7 +270,8 @@ int epi_trajectories_ext(epi_handle *h, const double *theta, int64_t n, int layo
  * (libMCMC.R:26-36), then per day j = 1..period the R type-7 quantiles of v[j]
  * over the draws with na.rm = TRUE — all on the device (one sort per day).
  * fun(state) = series_a (+ series_b when >= 0), indices into the epi_trajectories
- * series order.  Draws with an invalid data_offset count as NA.  n <= 8192.
+ * series order.  Draws with an invalid data_offset count as NA.  Up to 8,192 draws a day is sorted in shared memory,
+ * beyond that in a global scratch buffer (period x 2^ceil(log2 n) doubles, at most 4 GiB).
  * out: HOST, period x n_probs, row-major (NaN where every draw is NA).          */
 int epi_quantiles(epi_handle *h, const double *theta, int64_t n, int layout, int32_t period, int32_t startoffset,
                   int32_t series_a, int32_t series_b, const double *probs, int32_t n_probs, double *out);

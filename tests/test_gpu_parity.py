@@ -304,6 +304,32 @@ def test_quantile_data_matches_reference_semantics(name, fun, oracle):
     M.close()
 
 
+def test_quantile_data_beyond_the_shared_memory_sort():
+    """More than 8,192 posterior draws: the per-day sort runs in a global scratch buffer.  Checked against numpy on the
+    GPU's own trajectories (which the tests above compare with the oracle): same takeAndPad alignment, type-7
+    quantiles, na.rm."""
+    M = _model("S120", 2)
+    mn, mx, init = M.df_params["min"], M.df_params["max"], M.df_params["init"]
+    rng = np.random.default_rng(9)
+    n, period, startoffset = 10000, 60, 3
+    sample = np.clip(init + (rng.uniform(size=(n, M.d)) - 0.5) * 0.06 * (mx - mn), mn, mx)
+    probs = [0.05, 0.25, 0.5, 0.95]
+    got = M.quantileData(sample, "hospi", startoffset, period, probs)
+    simperiod = 3 * period
+    series, off, pad = M.calculateModel_batch(M.transformParams(sample), simperiod)
+    data = np.full((simperiod, n), np.nan)
+    k = M.series_names.index("hospi")
+    for i in range(n):
+        if off[i] == 10000 or off[i] - startoffset < 1:
+            continue
+        vec = np.concatenate([np.zeros(pad[i]), series[i, k]])
+        take = vec[off[i] - startoffset - 1:simperiod]
+        data[:len(take), i] = take
+    ref = np.nanquantile(data[:period], probs, axis=1).T
+    assert np.abs(got - ref).max() <= 1e-12 * (np.nanmax(np.abs(ref)) + 1e-300)
+    M.close()
+
+
 @pytest.mark.parametrize("name,fun,margin", [("A300", "Re", ("max", 40, 100)), ("A300", ("y.hospi", "o.hospi"), ("sum", 1, 120)),
                                              ("X300", "y.casei", ("mean", 100, 160)), ("S120", "hospi", ("min", 5, 30))])
 def test_marginalize_data_matches_reference_semantics(name, fun, margin, oracle):

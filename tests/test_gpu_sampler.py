@@ -470,6 +470,17 @@ def test_age_model_statistical_parity(oracle):
     # the cold rung is still the posterior's neighbourhood: far narrower than the prior in the identified parameters
     cold = S.draws()[0][:, cpr:, :].reshape(-1, M.d)
     assert (cold.std(axis=0)[:9] < 0.5 * dg.std(axis=0)[:9]).all()
+    # the drjacoby-style kernel on the same rung of the same model: one-parameter moves on the reparameterised box
+    # (45 Jacobian terms, 45 bandwidths per chain) must land on the same 45 marginals
+    D = Sampler(M, 2 * 2048, kind="drj", seed=2, rungs=2)
+    D.adapt(True); D.run(120); D.adapt(False)
+    D.record(4, 20); D.run(80)
+    dd = D.draws()[0][:, :2048, :].reshape(-1, M.d)
+    md, sd_ = _robust(dd)
+    zd = np.abs(md - mc) / sc
+    print("drj prior rung: z", np.round(zd, 2), "spread ratio", np.round(sd_ / sc, 2))
+    assert (zd < 0.5).all() and np.median(zd) < 0.15, np.round(zd, 2)
+    assert (np.abs(sd_ / sc - 1) < 0.3).all(), np.round(sd_ / sc, 2)
     M.close()
 
 
