@@ -868,6 +868,35 @@ def sampler_leg(M, comm, args, n):
                     "ess_method": f"between-replicate variance of the posterior-mean estimator over {full['n_replicates']} independent "
                                   f"replicate populations (relative sd of the estimate ~ sqrt(2 / {full['n_replicates'] - 1})), "
                                   f"{len(keys)} key parameters; split R-hat over one chain per replicate"})
+    # ---- the drjacoby-style kernel on the same target, measured the same way, for the same number of evaluations per
+    # chain as the recorded DE-MC phase, started from the DE-MC population (like-for-like with the reference's sampler)
+    if B > 1:
+        start = S.get()[0]
+        nfree = int((np.asarray(M.df_params["max"]) > np.asarray(M.df_params["min"])).sum())
+        sweeps = max(8, iters // nfree)
+        D = Sampler(M, n, kind="drj", seed=43, chain_id0=comm.rank * n, rungs=B, replicates=True, theta0=start)
+        D.adapt(True)
+        D.run(20)
+        D.adapt(False)
+        D.record(1, sweeps)
+        e0, a0 = D.stats()["evals"], D.stats()["accepted"]
+        torch.cuda.synchronize()
+        comm.barrier()
+        t0 = time.perf_counter()
+        D.run(sweeps)
+        torch.cuda.synchronize()
+        ddt = comm.max_over_ranks(time.perf_counter() - t0)
+        dst = D.stats()
+        dfull, dhalf = D.replicate_stats(keys, comm), D.replicate_stats(keys, comm, last=sweeps // 2)
+        devals = comm.world * (dst["evals"] - e0)
+        df_, dh_ = float(np.median(dfull["ess"])), float(np.median(dhalf["ess"]))
+        out["drj"] = {"kind": "drjacoby's own update (one parameter at a time on the logit-reparameterised box, Robbins-Monro "
+                              "bandwidths frozen after 20 sweeps), started from the DE-MC population above",
+                      "sweeps": sweeps, "evals_per_chain": (dst["evals"] - e0) // n, "sampling_s": ddt, "evals_per_s": devals / ddt,
+                      "accept_rate": (dst["accepted"] - a0) / max(1, dst["evals"] - e0),
+                      "ess_median": df_, "ess_median_first_half": dh_, "ess_per_s_median": df_ / ddt,
+                      "ess_growth_per_s": (df_ - dh_) / (ddt / 2), "ess_per_eval_median": df_ / max(1, devals),
+                      "split_rhat_median": float(np.median(dfull["rhat"])), "split_rhat_max": float(dfull["rhat"].max())}
     if comm.rank == 0:
         out["k2"] = k2_roofline(M)
     return out

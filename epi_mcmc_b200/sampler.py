@@ -198,7 +198,10 @@ class Sampler:
         rep_mean_np, hm_np, hv_np = rep_mean.cpu().numpy(), hm.cpu().numpy(), hv.cpu().numpy()
         sums = np.concatenate([[cnt], (tot_mean * cnt).cpu().numpy(), ss_tot.cpu().numpy()])
         if comm is not None and comm.world > 1:
-            rep_mean_np = np.concatenate(comm.allgather_np(rep_mean_np), axis=1)
+            parts = comm.allgather_np(rep_mean_np)
+            # DE-MC: replicate b spans the ranks (its chains draw partners from all of them), so its mean is the mean
+            # of the ranks' parts (equal chain counts); chains without partners (RWM, DRJ) are independent everywhere
+            rep_mean_np = np.mean(parts, axis=0) if self.kind == "demc" else np.concatenate(parts, axis=1)
             hm_np = np.concatenate(comm.allgather_np(hm_np), axis=2)
             hv_np = np.concatenate(comm.allgather_np(hv_np), axis=2)
             # pooled variance across ranks: combine (count, sum, sum of squares about the LOCAL mean)
