@@ -360,6 +360,242 @@ class Age2q:
         return float(lp)
 
 
+# ------------------------------------------------------------------- age2x --
+
+class Age2x(Age2q):
+    """R/models/model-age-groups2x.R + R/models/model-ager.cpp (the later generation), transliterated from the R file."""
+    KIND = (1, 1, 1, 1, 0, 0, 0, 0, 1, 0, 1, 1, 0)
+    eta = 1 / (0.75 * 356)
+    CLsd = 2.5
+
+    @staticmethod
+    def active(t, T):
+        for k in range(12, -1, -1):
+            if t > T[k]:
+                return k
+        return -1
+
+    # model-ager.cpp:88-124
+    @staticmethod
+    def interpolate(t, T, v):
+        if t > T[12]: return v[12]
+        elif t > T[11]: return v[11] + (t - T[11]) / (T[12] - T[11]) * (v[12] - v[11])
+        elif t > T[10]: return v[10] + (t - T[10]) / (T[11] - T[10]) * (v[11] - v[10])
+        elif t > T[9]: return v[9]
+        elif t > T[8]: return v[8] + (t - T[8]) / (T[9] - T[8]) * (v[9] - v[8])
+        elif t > T[7]: return v[7]
+        elif t > T[6]: return v[6]
+        elif t > T[5]: return v[5]
+        elif t > T[4]: return v[4]
+        elif t > T[3]: return v[3] + (t - T[3]) / (T[4] - T[3]) * (v[4] - v[3])
+        elif t > T[2]: return v[2] + (t - T[2]) / (T[3] - T[2]) * (v[3] - v[2])
+        elif t > T[1]: return v[1] + (t - T[1]) / (T[2] - T[1]) * (v[2] - v[1])
+        elif t > T[0]: return v[0] + (t - T[0]) / (T[1] - T[0]) * (v[1] - v[0])
+        return v[0]
+
+    # model-ager.cpp:135-214; returns (ydot, y.i, o.i)
+    def derivs_out(self, t, y, T, by, bo, byo, seg=None):
+        Ny, No = self.D["y_N"], self.D["o_N"]
+        Sy, E1y, E2y, Iy, Ry, So, E1o, E2o, Io, Ro = y
+        if (min(y[:5]) < 0 or max(y[:5]) > Ny or min(y[5:]) < 0 or max(y[5:]) > No):
+            return np.zeros(10), np.nan, np.nan
+        f = (lambda v: self.interpolate(t, T, v)) if seg is None else (lambda v: self.interp_seg(seg, t, T, v))
+        betay, betao, betayo = f(by), f(bo), f(byo)           # uncertain(): funcertain = 1 (:221)
+        Syeff = max(0.0, Ny * 0.8 - (Ny - Sy))
+        yinf = (betay * Iy) / Ny * Syeff
+        oinf = ((betao * Io) / No + (betayo * Iy) / Ny) * So
+        yrev, orev = self.eta * Ry, self.eta * Ro
+        d = np.array([-yinf + yrev, yinf - self.a1 * E1y, self.a1 * E1y - self.a2 * E2y, self.a2 * E2y - self.gamma * Iy,
+                      self.gamma * Iy - yrev,
+                      -oinf + orev, oinf - self.a1 * E1o, self.a1 * E1o - self.a2 * E2o, self.a2 * E2o - self.gamma * Io,
+                      self.gamma * Io - orev])
+        return d, yinf, oinf
+
+    def derivs(self, t, y, T, by, bo, byo, seg=None):
+        return self.derivs_out(t, y, T, by, bo, byo, seg)[0]
+
+    def _incidence(self, out, times, Tb, by, bo, byo):
+        """the output variables y.i / o.i as deSolve reports them: one derivs() call per output time"""
+        yi, oi = np.zeros(len(times)), np.zeros(len(times))
+        for k, t in enumerate(times):
+            _, yi[k], oi[k] = self.derivs_out(float(t), out[k], Tb, by, bo, byo)
+        return yi, oi
+
+    # model-age-groups2x.R:55-380
+    def calculateModel(self, params, period):
+        D = self.D
+        p = lambda i: params[i - 1]
+        y_N, o_N = D["y_N"], D["o_N"]
+        y_ifr, o_ifr, y_hr, o_hr = (np.asarray(D[k], dtype=float) for k in ("y_ifr", "o_ifr", "y_hr", "o_hr"))
+        g, gtrimp = np.asarray(D["g"], dtype=float), np.asarray(D["gtrimp"], dtype=float)
+        y_died_rate, o_died_rate = y_ifr[0], o_ifr[0]
+        lockdown_offset, ltp = D["lockdown_offset"], D["lockdown_transition_period"]
+        first = [1, 4, 7, 25, 29, 32, 36, 40, 40, 43, 43, 50, 43]     # beta8 = beta7, beta10 = beta12 = beta9 (:56-119)
+        by, bo, byo = [p(i) for i in first], [p(i + 1) for i in first], [p(i + 2) for i in first]
+        ycase_rate, yhosp_rate, yhosp_latency, ydied_latency = p(10), p(11), p(12), p(13)
+        ocase_rate, ohosp_rate, ohosp_latency, odied_latency = p(14), p(15), p(16), p(17)
+        t0_morts, t0o, HLsd, DLsd, fyifr, fyhr = p(18), p(19), p(20), p(21), p(22), p(23)
+        t3o, t4o, t6o, t7o, ifrred, ycase_latency, ocase_latency, t10o = p(24), p(28), p(35), p(39), p(46), p(47), p(48), p(49)
+        CLsd = self.CLsd
+        prof = dict(ycase=self.calcGammaProfile(ycase_latency, CLsd), ocase=self.calcGammaProfile(ocase_latency, CLsd),
+                    yhosp=self.calcGammaProfile(yhosp_latency, HLsd), ohosp=self.calcGammaProfile(ohosp_latency, HLsd),
+                    ydied=self.calcGammaProfile(ydied_latency, DLsd), odied=self.calcGammaProfile(odied_latency, DLsd))
+        padding = max(-prof["ycase"]["kbegin"], -prof["ydied"]["kbegin"], -prof["ocase"]["kbegin"],
+                      -prof["odied"]["kbegin"]) + 1
+        T = padding + period
+        Y0 = [y_N - Initial, Initial, 0, 0, 0, o_N, 0, 0, 0, 0]
+        Tb = [1e10] * 13
+        period1 = 60
+        times = np.arange(padding + 1, padding + period1 + 1)
+        out = self._solve(Y0, times, Tb, by, bo, byo)
+        yi_out, oi_out = self._incidence(out, times, Tb, by, bo, byo)
+        L1 = max(T, padding + period1)
+        yi1, oi1 = np.zeros(L1), np.zeros(L1)
+        yi1[padding:padding + period1] = yi_out
+        oi1[padding:padding + period1] = oi_out
+        ydeadi = self.convolute(yi1, padding + 1, padding + period1, prof["ydied"]) * y_died_rate
+        odeadi = self.convolute(oi1, padding + 1, padding + period1, prof["odied"]) * o_died_rate
+        died = np.full(padding + period1, np.nan)
+        died[padding:] = np.cumsum(ydeadi) + np.cumsum(odeadi)
+        data_offset = InvalidDataOffset
+        with np.errstate(invalid="ignore"):
+            lds = np.nonzero(died > t0_morts)[0] + 1
+        if len(lds) > 0:
+            data_offset = lds[0] - lockdown_offset
+            t2 = data_offset + lockdown_offset + ltp
+            t3 = t2 + t3o
+            t4 = t3 + t4o
+            t5 = data_offset + D["d5"]
+            t6 = t5 + t6o
+            t7 = t6 + t7o
+            t10 = data_offset + t10o
+            Tb = [data_offset + lockdown_offset + t0o, data_offset + lockdown_offset + max(t0o, 0), t2, t3, t4, t5, t6, t7,
+                  data_offset + D["d8"], data_offset + D["d9"], t10, t10 + 3, data_offset + D["d12"]]
+            times = np.arange(padding + 1, padding + period + 1)
+            out = self._solve(Y0, times, Tb, by, bo, byo)
+            yi_out, oi_out = self._incidence(out, times, Tb, by, bo, byo)
+        yi, oi = np.zeros(T), np.zeros(T)
+        yi[padding:] = np.resize(yi_out, period)   # recycled when pass 2 was skipped
+        oi[padding:] = np.resize(oi_out, period)
+        yS = np.full(T, y_N - Initial, dtype=float)
+        oS = np.full(T, o_N, dtype=float)
+        yS[padding:] = np.resize(out[:, 0], period)
+        oS[padding:] = np.resize(out[:, 5], period)
+
+        gycr = np.minimum(1, ycase_rate * y_ifr * (1 + (fyifr - 1) * g))
+        gyifr = y_ifr * (1 + (fyifr - 1) * g) * (1 - ifrred * gtrimp)
+        gyhr = yhosp_rate * y_hr * (1 + (fyhr - 1) * g)
+        gocr = np.minimum(1, ocase_rate * o_ifr)
+        goifr = o_ifr * (1 - ifrred * gtrimp)
+        gohr = ohosp_rate * o_hr
+        t_symp = data_offset + D["d_symp_cases"]
+        t_all = data_offset + D["d_all_cases"] - 1
+
+        def series(inc, profile, t1, rate, cases=False):
+            dst = np.zeros(T)
+            s2i = self.convolute(inc, padding + 1, padding + period, profile)
+            if data_offset != InvalidDataOffset:
+                t1 = int(t1)
+                t2 = min(padding + period, t1 + len(rate) - 1)
+                if t1 > padding and t2 > t1:
+                    dst[padding:t1] = s2i[0:t1 - padding] * rate[0]
+                    dst[t1 - 1:t2] = s2i[t1 - padding - 1:t2 - padding] * rate[0:t2 - t1 + 1]
+                    dst[t2 - 1:padding + period] = s2i[t2 - padding - 1:period] * rate[-1]
+                if cases:   # state$y.casei[t.symp:min(t.all, length)] *= symp.cases.factor (R's a:b may run downwards)
+                    a, b = t_symp, min(t_all, len(dst))
+                    assert 1 <= a <= len(dst) and b >= 1, "window beyond the vector: R would grow it"
+                    lo_, hi_ = min(a, b), max(a, b)
+                    dst[lo_ - 1:hi_] = dst[lo_ - 1:hi_] * D["symp_cases_factor"]
+            else:
+                dst[padding:padding + period] = s2i * rate[0]
+            return dst
+
+        st = dict(padding=padding, offset=data_offset, y_S=yS, o_S=oS, y_i=yi, o_i=oi)
+        st["y_casei"] = series(yi, prof["ycase"], data_offset + r_round(-ydied_latency + ycase_latency), gycr, True)
+        st["y_hospi"] = series(yi, prof["yhosp"], data_offset + r_round(-ydied_latency + yhosp_latency), gyhr)
+        st["y_deadi"] = series(yi, prof["ydied"], data_offset, gyifr)
+        st["o_casei"] = series(oi, prof["ocase"], data_offset + r_round(-ydied_latency + ocase_latency), gocr, True)
+        st["o_hospi"] = series(oi, prof["ohosp"], data_offset + r_round(-ydied_latency + ohosp_latency), gohr)
+        st["o_deadi"] = series(oi, prof["odied"], data_offset, goifr)
+        return st
+
+    # model-age-groups2x.R:547-681
+    def calclogl(self, params):
+        D = self.D
+        state = self.calculateModel(params, self.P)
+        if state["offset"] == InvalidDataOffset:
+            state["offset"] = 1
+        y_dcasei, o_dcasei = np.asarray(D["y_dcasei"], float), np.asarray(D["o_dcasei"], float)
+        dhospi = np.asarray(D["dhospi"], float)
+        y_dmorti, o_dmorti = np.asarray(D["y_dmorti"], float), np.asarray(D["o_dmorti"], float)
+        o_wdmorti = np.asarray(D["o_wdmorti"], float)
+        r, rh, n_dhosp, last7 = D["d_reliable_cases"], D["d_reliable_hosp"], D["n_dhosp"], D["hosp_last7"]
+
+        def window(n, L):
+            dstart = state["offset"]
+            dend = state["offset"] + n - 1
+            if dend > L:
+                dend = L
+                dstart = dend - n + 1
+            if dstart < 1:
+                dstart = 1
+                dend = dstart + n - 1
+            return dstart, dend
+
+        nb = lambda x, mu, size, fl: np.sum(dnbinom_log(x, pmax(fl, mu), size))
+        nc = len(y_dcasei)
+        dstart, dend = window(nc, len(state["y_casei"]))
+        y_loglC = (nb(rslice(y_dcasei, 1, r - 1), rslice(state["y_casei"], dstart, dstart + r), D["case_nbinom_size1"], 0.1)
+                   + nb(rslice(y_dcasei, r, nc), rslice(state["y_casei"], dstart + r + 1, dend), D["case_nbinom_sizey2"], 0.1))
+        o_loglC = (nb(rslice(o_dcasei, 1, r - 1), rslice(state["o_casei"], dstart, dstart + r), D["case_nbinom_size1"], 0.1)
+                   + nb(rslice(o_dcasei, r, nc), rslice(state["o_casei"], dstart + r + 1, dend), D["case_nbinom_sizeo2"], 0.1)
+                   + nb(rslice(o_dcasei, nc - 7, nc), rslice(state["o_casei"], dend - 7, dend), D["case_nbinom_sizeo2"] * last7, 0.1))
+        dstart, dend = window(len(dhospi), len(state["y_hospi"]))
+        H = state["y_hospi"] + state["o_hospi"]
+        loglH = (nb(rslice(dhospi, 1, rh - 1), rslice(H, dstart, dstart + rh), D["hosp_nbinom_size1"], 0.1)
+                 + nb(rslice(dhospi, rh, n_dhosp), rslice(H, dstart + rh + 1, dend), D["hosp_nbinom_size2"], 0.1)
+                 + nb(rslice(dhospi, n_dhosp - 7, n_dhosp), rslice(H, dend - 7, dend), D["hosp_nbinom_size2"] * last7, 0.1))
+        ytotal = np.sum(rslice(state["y_hospi"], dstart + D["d_hosp_o1"], dstart + D["d_hosp_o2"]))
+        ototal = np.sum(rslice(state["o_hospi"], dstart + D["d_hosp_o1"], dstart + D["d_hosp_o2"]))
+        loglHRatio = dlnorm_log(ytotal / (ytotal + ototal), np.log(56.7 / 100), np.log(1.05))
+        nm = len(y_dmorti)
+        dstart, dend = window(nm, len(state["y_deadi"]))
+        y_loglD = nb(y_dmorti, rslice(state["y_deadi"], dstart, dend), D["mort_nbinom_size"] * 5, 0.001)
+        o_loglD = (nb(o_dmorti, rslice(state["o_deadi"], dstart, dend), o_wdmorti * D["mort_nbinom_size"], 0.001)
+                   + nb(rslice(o_dmorti, nm - 7, nm), rslice(state["o_deadi"], dend - 7, dend), D["mort_nbinom_size"] * last7, 0.001))
+        terms = [y_loglC, o_loglC, loglH, loglHRatio, y_loglD, o_loglD]
+        return float(np.sum(terms)), terms, state
+
+    # model-age-groups2x.R:427-545
+    def calclogp(self, params):
+        D = self.D
+        p = lambda i: params[i - 1]
+        lo, ltp = D["lockdown_offset"], D["lockdown_transition_period"]
+        SD, lSD, llSD = np.log(2), np.log(1.3), np.log(1.2)
+        b = {0: 1, 1: 4, 2: 7, 3: 25, 4: 29, 5: 32, 6: 36, 7: 40, 9: 43, 11: 50}
+        ratio3 = lambda i, j, m, s: sum(dlnorm_log(p(b[i] + c) / p(b[j] + c), m, s) for c in range(3))
+        lp = 0.0
+        lp += dnorm_log(p(19), 0, 10)
+        lp += dnorm_log(lo + ltp + p(24), D["d3"], 10)
+        lp += dnorm_log(lo + ltp + p(24) + p(28), D["d4"], 10)
+        lp += dnorm_log(D["d5"] + p(35), D["d6"], 5)
+        lp += dnorm_log(D["d5"] + p(35) + p(39), D["d7"] - lo, 2)
+        lp += dnorm_log(p(49), D["d10"], 3)
+        lp += ratio3(0, 1, 0, llSD)
+        for i, j in ((1, 2), (2, 3), (3, 4), (5, 6), (6, 7)):
+            lp += ratio3(i, j, 0, SD)
+        lp += ratio3(7, 9, np.log(1.3), lSD)
+        lp += ratio3(9, 11, 0, lSD)
+        lp += dnorm_log(p(20), 4, 1) + dnorm_log(p(21), 5, 1)
+        lp += dnorm_log(p(47), 7, 3) + dnorm_log(p(48), 7, 3)
+        lp += dnorm_log(p(12), 13, 1) + dnorm_log(p(16), 13, 1)
+        lp += dnorm_log(p(13), 21, 0.5) + dnorm_log(p(17), 21, 0.5)
+        lp += dlnorm_log(p(22), np.log(0.6), np.log(1.5))
+        lp += dlnorm_log(p(46), np.log(0.35), np.log(1.3))
+        lp += dlnorm_log(p(11), 0, lSD) + dlnorm_log(p(15), 0, lSD)
+        return float(lp)
+
+
 # ------------------------------------------------------------------- age2i --
 
 class Age2i(Age2q):

@@ -174,7 +174,7 @@ def test_rhs_ager_matches_reference_binary(oracle):
             assert np.array_equal(yo[:9], yb, equal_nan=True), (trial, yo[:9], yb)
 
 
-@pytest.mark.parametrize("name", ["A300", "I290", "S120", "NE120", "DE"])
+@pytest.mark.parametrize("name", ["A300", "I290", "X300", "S120", "NE120", "DE"])
 def test_oracle_vs_numpy_transliteration_same_scheme(name, oracle):
     """Index semantics (filter alignment + mirror, two-pass offset, rate-map slices, dnbinom
     recycling, window clamps, NA and invalid-offset branches) against an independent
@@ -185,9 +185,13 @@ def test_oracle_vs_numpy_transliteration_same_scheme(name, oracle):
     idx = list(range(0, len(theta), 3))[:14]
     res = oracle.evaluate(ds["flavour"], ds, theta[idx], ds["period"], 4)
     for k, i in enumerate(idx):
-        if ds["flavour"] in ("age2q", "age2i"):
-            M = (R.Age2q if ds["flavour"] == "age2q" else R.Age2i)(ds, ds["period"], "rk4", 4)
-            ll, terms, st = M.calclogl(theta[i])
+        if ds["flavour"] in ("age2q", "age2i", "age2x"):
+            M = {"age2q": R.Age2q, "age2i": R.Age2i, "age2x": R.Age2x}[ds["flavour"]](ds, ds["period"], "rk4", 4)
+            try:
+                ll, terms, st = M.calclogl(theta[i])
+            except AssertionError:   # (age-2x: a symptomatic-testing window beyond the simulated period)
+                assert res["status"][k] & 16
+                continue
         else:
             M = R.Simple(ds, ds["period"], "rk4", 4, ne=ds["flavour"] == "ne")
             p = theta[i].copy()
