@@ -625,7 +625,7 @@ def main():
                                                            peak_tf, ncu, total_chains)
     value, step_ms = head["value"], head["ms_per_step"]
     # ---- the same step for >= 1 s (the contract's K steps last ~60 ms at K = 20)
-    sus_steps = int(max(args.steps, np.ceil(1000.0 / step_ms)))
+    sus_steps = int(max(args.steps, np.ceil(1100.0 / step_ms)))
     ms_s, _ = timed(hb, sus_steps, 1, comm, dev)
     sustained = {"steps": sus_steps, "ms_per_step": ms_s / sus_steps, "value": total_chains * sus_steps / (ms_s * 1e-3), "unit": UNIT}
     ref_logl = hb.logl.cpu().numpy().copy()

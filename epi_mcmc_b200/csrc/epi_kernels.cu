@@ -781,106 +781,40 @@ k_ode(const DevModel M, const double *__restrict__ theta, int64_t ld, int64_t n,
   }
 }
 
-// ------------------------------------------------------- K_ode, age flavour
-// Two lanes per chain: the even lane integrates the younger group (Sy,E1y,E2y,Iy,Ry), the odd
-// lane the older group; the only coupling is Iy/Ny, one shuffle per RK4 stage
-// (model-agen.cpp:136-144).  With 65,536 chains per GPU a thread-per-chain launch leaves
-// 2.5 warps per scheduler and the FP64 pipe 42 % busy, stalled on fixed-latency dependencies
-// (ncu, profiles/r1_v2); the pair split doubles the warps and halves registers per thread.
+// ------------------------------------------------- K_ode, two lanes per chain
+// One lane per age group: the even lane integrates (Sy, E1y, E2y, Iy), the odd lane (So, E1o, E2o, Io); the only
+// coupling is I_y, one shuffle per RK4 stage (model-agen.cpp:136-144), which the younger group's lane does not
+// even wait for.  Like the four-lane kernel below it is WARP-SYNCHRONOUS (all 16 chains of a warp execute every
+// piece together, full-warp shuffles and votes, `commit` freezes the chains that have nothing to do): round 1's
+// two-lane kernel shuffled over per-pair masks behind early returns and never beat the other mappings.  Every
+// operation is the explicitly rounded one of rhs<> (the younger group's beta_yo = 0 term adds an exact +0): same bits
+// as the thread-per-chain kernel.  R is not integrated; chains whose guard decision could have depended on it are
+// flagged for the R-tracking instance of k_ode.
 struct Seg2 {
-  double tk, bA, sA, bB, sB;  // y lane: A = betay, B = 0;  o lane: A = betao, B = betayo
+  double tk, bA, sA, bB, sB;  // y lane: A = betay, B = 0;  o lane: A = betao, B = betayo (already divided by N)
   bool fast_ok;               // all three beta curves >= 0 on the segment (premise of the fast guard)
+  bool hold;                  // all three slopes of the CHAIN are zero
 };
 
-// TRACKR = false: R (y[4]) is not integrated, exactly as in rhs<> (see below_one)
-template <bool GUARDED, bool TRACKR>
-__device__ __forceinline__ void rhs_age2(double a1, double gamma, const Seg2 &sg, double t, const double *y, double *dy,
-                                         double invN, double Ngrp, unsigned nb, unsigned pairmask, int even_lane,
-                                         unsigned &flag) {
-  const double S = y[0], E1 = y[1], E2 = y[2], I = y[3], R = TRACKR ? y[4] : 0.0;
-  if constexpr (GUARDED) {
-    // bounds guard over all ten states of the chain, model-agen.cpp:109-124
-    const int bad_own = (S < 0 || E1 < 0 || E2 < 0 || I < 0 || R < 0 || S > Ngrp || E1 > Ngrp || E2 > Ngrp ||
-                         I > Ngrp || R > Ngrp);
-    const int bad = bad_own | __shfl_xor_sync(pairmask, bad_own, 1);
-    // (the shuffle below must still be executed by both lanes)
-    const double fy = __shfl_sync(pairmask, I, even_lane);  // I of the younger group
-    if (bad) {
-#pragma unroll
-      for (int i = 0; i < 5; ++i) dy[i] = 0.0;
-      return;
-    }
-    if constexpr (!TRACKR) flag |= (S < 1.0) ? 1u : 0u;  // the R test is undecidable here
-    // the same explicitly rounded operations as rhs<>: both ODE kernels produce the same bits
-    const double dt = t - sg.tk;
-    const double bA = fma(dt, sg.sA, sg.bA), bB = fma(dt, sg.sB, sg.bB);
-    const double inf = __dmul_rn(fma(bA, I, __dmul_rn(bB, fy)), S);
-    dy[0] = -inf; dy[1] = fma(-a1, E1, inf); dy[2] = fma(a1, E1, -E2); dy[3] = fma(-gamma, I, E2);
-    if constexpr (TRACKR) dy[4] = __dmul_rn(gamma, I);
-  } else {
-    if constexpr (TRACKR) flag |= oob_group5(S, E1, E2, I, R, nb);
-    else flag |= oob_group4_nor(S, E1, E2, I, nb);
-    const double fy = __shfl_sync(pairmask, I, even_lane);  // I of the younger group
-    const double dt = t - sg.tk;
-    const double bA = fma(dt, sg.sA, sg.bA), bB = fma(dt, sg.sB, sg.bB);
-    const double inf = __dmul_rn(fma(bA, I, __dmul_rn(bB, fy)), S);  // y: (betay/Ny*Iy)*Sy; o: (betao/No*Io + betayo/Ny*Iy)*So
-    dy[0] = -inf; dy[1] = fma(-a1, E1, inf); dy[2] = fma(a1, E1, -E2); dy[3] = fma(-gamma, I, E2);
-    if constexpr (TRACKR) dy[4] = __dmul_rn(gamma, I);
-  }
-}
-
-template <bool GUARDED, bool TRACKR>
-__device__ __forceinline__ bool rk4_try_age2(double a1, double gamma, const Seg2 &sg, const double *y, double *ynew,
-                                             double pa, double pb, double invN, double Ngrp, unsigned nb,
-                                             unsigned pairmask, int even_lane, bool &need_r) {
-  constexpr int NS = TRACKR ? 5 : 4;
-  const double hh = pb - pa, hh2 = 0.5 * hh, tm = pa + hh2;
-  double k[5], acc[5], yt[5];
-  unsigned flag = 0;
-  rhs_age2<GUARDED, TRACKR>(a1, gamma, sg, pa, y, k, invN, Ngrp, nb, pairmask, even_lane, flag);
-#pragma unroll
-  for (int i = 0; i < NS; ++i) { acc[i] = k[i]; yt[i] = fma(hh2, k[i], y[i]); }
-  rhs_age2<GUARDED, TRACKR>(a1, gamma, sg, tm, yt, k, invN, Ngrp, nb, pairmask, even_lane, flag);
-#pragma unroll
-  for (int i = 0; i < NS; ++i) { acc[i] = fma(2.0, k[i], acc[i]); yt[i] = fma(hh2, k[i], y[i]); }
-  rhs_age2<GUARDED, TRACKR>(a1, gamma, sg, tm, yt, k, invN, Ngrp, nb, pairmask, even_lane, flag);
-#pragma unroll
-  for (int i = 0; i < NS; ++i) { acc[i] = fma(2.0, k[i], acc[i]); yt[i] = fma(hh, k[i], y[i]); }
-  rhs_age2<GUARDED, TRACKR>(a1, gamma, sg, pb, yt, k, invN, Ngrp, nb, pairmask, even_lane, flag);
-  const double h6 = hh / 6.0;
-#pragma unroll
-  for (int i = 0; i < NS; ++i) ynew[i] = fma(h6, __dadd_rn(acc[i], k[i]), y[i]);
-  if constexpr (!TRACKR) ynew[4] = 0.0;
-  if constexpr (GUARDED) {
-    if (!TRACKR && (flag & 1u)) need_r = true;
-    return true;
-  }
-  const int own_bad = (int)flag < 0;
-  return !(own_bad | __shfl_xor_sync(pairmask, own_bad, 1));
-}
-
-template <bool TRACKR>
-__device__ __forceinline__ void rk4_piece_age2(double a1, double gamma, const Seg2 &sg, double *y, double pa, double pb,
-                                               double invN, double Ngrp, unsigned nb, unsigned pairmask,
-                                               int even_lane, bool &need_r) {
-  double yn[5];
-  if (!sg.fast_ok || !rk4_try_age2<false, TRACKR>(a1, gamma, sg, y, yn, pa, pb, invN, Ngrp, nb, pairmask, even_lane, need_r)) {
-    // rare: redo the step with the reference's guard evaluated exactly in FP64
-    rk4_try_age2<true, TRACKR>(a1, gamma, sg, y, yn, pa, pb, invN, Ngrp, nb, pairmask, even_lane, need_r);
-  }
-#pragma unroll
-  for (int i = 0; i < 5; ++i) y[i] = yn[i];
-}
+constexpr unsigned kFull = 0xffffffffu;
 
 template <int FL>
 __device__ __noinline__ Seg2 select_segment_age2(const DevModel &M, const double *__restrict__ th, int64_t ld, const double *bp, int nbp,
-                                                 double pa, int is_o, double *tcut, double invy, double invo) {
+                                                 double pa, int is_o, double *tcut, double invy, double invo, int *kcur,
+                                                 bool sorted) {
   int k = -1;
   double tc = INFINITY;
-  for (int i = 0; i < nbp; ++i) {
-    if (bp[i] <= pa) k = i;
-    if (bp[i] > pa && bp[i] < tc) tc = bp[i];
+  if (sorted && *kcur >= -1) {
+    k = *kcur;
+    while (k + 1 < nbp && bp[k + 1] <= pa) ++k;
+    if (k + 1 < nbp) tc = bp[k + 1];
+  } else {
+    for (int i = 0; i < nbp; ++i) {
+      if (bp[i] <= pa) k = i;
+      if (bp[i] > pa && bp[i] < tc) tc = bp[i];
+    }
   }
+  *kcur = k;
   *tcut = tc;
   double by, bo, byo;
   age_beta<FL>(M, th, ld, k < 0 ? 0 : k, by, bo, byo);
@@ -896,8 +830,12 @@ __device__ __noinline__ Seg2 select_segment_age2(const DevModel &M, const double
     sg.sA = is_o ? (no - bo) / len : (ny - by) / len;
     sg.sB = is_o ? (nyo - byo) / len : 0.0;
     sg.fast_ok = by >= 0 && bo >= 0 && byo >= 0 && ny >= 0 && no >= 0 && nyo >= 0 && len > 0;
+    // hold <=> all three slopes of the chain are zero (the same test as select_segment, on the same roundings)
+    sg.hold = __dmul_rn((ny - by) / len, invy) == 0.0 && __dmul_rn((no - bo) / len, invo) == 0.0 &&
+              __dmul_rn((nyo - byo) / len, invy) == 0.0;
   } else {
     sg.fast_ok = by >= 0 && bo >= 0 && byo >= 0;
+    sg.hold = true;
   }
   // the same normalisation (and the same roundings) as select_segment
   const double invA = is_o ? invo : invy;
@@ -906,41 +844,120 @@ __device__ __noinline__ Seg2 select_segment_age2(const DevModel &M, const double
   return sg;
 }
 
-// Like k_ode, this instance does not integrate R (4 states per lane); chains it flags are redone by the R-tracking
-// instance of the thread-per-chain kernel, which computes the same bits.  (Capped at 72 registers so that all
-// 2 x 65,536 lanes of a full batch are resident at once it spills and takes 1.71 ms for pass 2 against 1.00 ms
-// thread-per-chain: the two-lane form stays a small-batch kernel.)
-constexpr int kPairRegs = 128;
+struct Lane2 {
+  double a1, gamma, Ngrp;
+  int shift;     // first lane of this chain's pair == the lane that holds I_y
+  unsigned nb;   // hi(N) - 1
+};
+
+template <bool GUARDED, bool HOLD>
+__device__ __forceinline__ void rhs2w(const Lane2 &L, const Seg2 &sg, double t, const double *y, double *dy, unsigned &flag) {
+  const double S = y[0], E1 = y[1], E2 = y[2], I = y[3];
+  const double iy = __shfl_sync(kFull, I, L.shift);  // I of the younger group
+  bool bad = false;
+  if constexpr (GUARDED) {
+    // bounds guard over the chain's states, model-agen.cpp:109-124 (R is not integrated here: see below_one)
+    const int bad_own = (S < 0 || E1 < 0 || E2 < 0 || I < 0 || S > L.Ngrp || E1 > L.Ngrp || E2 > L.Ngrp || I > L.Ngrp);
+    bad = ((__ballot_sync(kFull, bad_own) >> L.shift) & 3u) != 0u;
+    flag |= (!bad && S < 1.0) ? 1u : 0u;  // the R test is undecidable here
+  } else {
+    flag |= oob_group4_nor(S, E1, E2, I, L.nb);  // bit 31 set <=> maybe out of bounds
+  }
+  const double dt = HOLD ? 0.0 : t - sg.tk;
+  const double bA = HOLD ? sg.bA : fma(dt, sg.sA, sg.bA), bB = HOLD ? sg.bB : fma(dt, sg.sB, sg.bB);
+  const double inf = __dmul_rn(fma(bA, I, __dmul_rn(bB, iy)), S);  // y: (betay/Ny*Iy)*Sy; o: (betao/No*Io + betayo/Ny*Iy)*So
+  dy[0] = -inf;
+  dy[1] = fma(-L.a1, E1, inf);
+  dy[2] = fma(L.a1, E1, -E2);
+  dy[3] = fma(-L.gamma, I, E2);
+  if constexpr (GUARDED) {
+    if (bad) { dy[0] = 0.0; dy[1] = 0.0; dy[2] = 0.0; dy[3] = 0.0; }  // the guard freezes the whole state
+  }
+}
+
+// returns (fast instance) whether no lane of the chain raised the maybe-out-of-bounds bit
+template <bool GUARDED, bool HOLD>
+__device__ __forceinline__ bool rk4_try2w(const Lane2 &L, const Seg2 &sg, const double *y, double *yn, double pa, double pb,
+                                          double hh, double hh2, double h6, bool &need_r) {
+  const double tm = pa + hh2;
+  double k[4], acc[4], yt[4];
+  unsigned flag = 0;
+  rhs2w<GUARDED, HOLD>(L, sg, pa, y, k, flag);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { acc[i] = k[i]; yt[i] = fma(hh2, k[i], y[i]); }
+  rhs2w<GUARDED, HOLD>(L, sg, tm, yt, k, flag);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { acc[i] = fma(2.0, k[i], acc[i]); yt[i] = fma(hh2, k[i], y[i]); }
+  rhs2w<GUARDED, HOLD>(L, sg, tm, yt, k, flag);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { acc[i] = fma(2.0, k[i], acc[i]); yt[i] = fma(hh, k[i], y[i]); }
+  rhs2w<GUARDED, HOLD>(L, sg, pb, yt, k, flag);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) yn[i] = fma(h6, __dadd_rn(acc[i], k[i]), y[i]);
+  if constexpr (GUARDED) {
+    need_r = (flag & 1u) != 0u;
+    return true;
+  }
+  return ((__ballot_sync(kFull, (int)flag < 0) >> L.shift) & 3u) == 0u;
+}
+
+// one RK4 piece for all sixteen chains of the warp; a chain takes the result only when `commit`
+__device__ __forceinline__ void rk4_step2w(const Lane2 &L, const Seg2 &sg, double *y, bool commit, double pa, double pb,
+                                           double hh, double hh2, double h6, bool &need_r) {
+  double yn[4];
+  bool nr = false;
+  const bool hold = __all_sync(kFull, sg.hold);
+  bool ok = hold ? rk4_try2w<false, true>(L, sg, y, yn, pa, pb, hh, hh2, h6, nr)
+                 : rk4_try2w<false, false>(L, sg, y, yn, pa, pb, hh, hh2, h6, nr);
+  ok = ok && sg.fast_ok;
+  if (__any_sync(kFull, commit && !ok)) {
+    // rare: the reference's guard evaluated exactly in FP64, by the whole warp; taken by the chains that need it
+    double gy[4];
+    bool gnr = false;
+    rk4_try2w<true, false>(L, sg, y, gy, pa, pb, hh, hh2, h6, gnr);
+    if (!ok) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) yn[i] = gy[i];
+      nr = gnr;
+    }
+  }
+  if (commit) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) y[i] = yn[i];
+    need_r = need_r || nr;
+  }
+}
+
 template <int FL, bool PASS2>
-__global__ void __maxnreg__(kPairRegs)
+__global__ void __launch_bounds__(128, 4)
 k_ode_age2(const DevModel M, const double *__restrict__ theta, int64_t ld, int64_t n, const int *__restrict__ offset,
            const int *__restrict__ padv, const double *__restrict__ hist1, double *__restrict__ hist_out,
            double *__restrict__ ckpt, int window_only = 0, int ndays_limit = 0,
            const int *__restrict__ retry_status = nullptr, int *__restrict__ need_r_flag = nullptr,
            int force_need_r = 0) {
-  constexpr bool TR = false;
   bool need_r = false;
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t i = tid >> 1;  // chain
-  if (i >= n) return;
-  const int g = (int)(tid & 1);  // 0 = younger group, 1 = older group
-  const int lane = threadIdx.x & 31, even_lane = lane & ~1;
-  const unsigned pairmask = 3u << even_lane;
+  const bool exists = (tid >> 1) < n;
+  const int64_t i = exists ? (tid >> 1) : n - 1;  // lanes behind the batch shadow its last chain and never store
+  const int lane = threadIdx.x & 31;
+  const int g = lane & 1;  // 0 = younger group, 1 = older group
+  Lane2 L;
+  L.shift = lane & ~1;
+  L.a1 = M.a1; L.gamma = M.gamma;
+  L.Ngrp = g ? M.No : M.Ny;
+  L.nb = (unsigned)__double2hiint(L.Ngrp) - 1u;
   const double *th = theta + i;
   const int ndays = PASS2 ? M.P : M.P1;
   int nint = ndays;  // days integrated here
+  bool alive = exists;
   if constexpr (!PASS2) {  // two-round pass 1, see k_ode
-    if (retry_status && !(retry_status[i] & kStRetry)) return;
+    if (retry_status && !(retry_status[i] & kStRetry)) alive = false;
     if (ndays_limit > 0) nint = min(nint, ndays_limit);
   }
   const int pitch = PASS2 ? hist_pitch2(ndays) : hist_pitch(ndays), Q = pitch >> 2;
   double *out = hist_out + (i * 2 + g) * (int64_t)pitch;
-
-  const double Ngrp = g ? M.No : M.Ny;
-  const double invN = 1.0 / Ngrp;
-  const unsigned nb = (unsigned)__double2hiint(Ngrp) - 1u;
-  double y[5];
-  y[0] = g ? M.No : M.Ny - 1.0; y[1] = g ? 0.0 : 1.0; y[2] = y[3] = y[4] = 0.0;  // model-age-groups2q.R:157-158
+  // model-age-groups2q.R:157-158
+  double y[4] = {g ? M.No : M.Ny - 1.0, g ? 0.0 : 1.0, 0.0, 0.0};
 
   double bp[kMaxBp];
   int nbp = 0;
@@ -950,20 +967,25 @@ k_ode_age2(const DevModel M, const double *__restrict__ theta, int64_t ld, int64
     const int off = offset[i];
     if (off == EPI_INVALID_DATA_OFFSET) {
       // pass 2 skipped: the pass-1 rows are recycled into the P-length slices (:216-223)
-      const double *in = hist1 + (i * 2 + g) * (int64_t)hist_pitch(M.P1);
-      for (int d = 0; d < M.P; ++d) out[hist_index<PASS2>(d, Q)] = in[d % M.P1];
-      if (g == 0 && need_r_flag) need_r_flag[i] = 0;
-      return;
+      if (alive) {
+        const double *in = hist1 + (i * 2 + g) * (int64_t)hist_pitch(M.P1);
+        for (int d = 0; d < M.P; ++d) out[hist_index<PASS2>(d, Q)] = in[d % M.P1];
+      }
+      if (alive && g == 0 && need_r_flag) need_r_flag[i] = 0;
+      alive = false;
+    } else {
+      t0 = padv[i] + 1;
+      nbp = breakpoints<FL>(M, th, ld, (double)off, bp);
+      if (window_only) nint = min(nint, max(last_window_day(M, off, padv[i]) - padv[i], 1));
     }
-    t0 = padv[i] + 1;
-    nbp = breakpoints<FL>(M, th, ld, (double)off, bp);
-    if (window_only) nint = min(nint, max(last_window_day(M, off, padv[i]) - padv[i], 1));
   }
+  const bool flags_r = alive;  // this chain reports need_r at the end
   const int cdays = ckpt_days(M.P1);
+  // states of this lane in the checkpoint tile: q = g * 5 + j, j = 0..3
   double *ck = ckpt ? ckpt + ((i / kTile) * (int64_t)cdays * 10 + g * 5) * kTile + (i % kTile) : nullptr;
   int d0 = 0;
   if constexpr (PASS2) {
-    if (ck) {
+    if (ck && alive) {
       double minbp = INFINITY;
       for (int k = 0; k < nbp; ++k) minbp = fmin(minbp, bp[k]);
       const double dd = floor(minbp) - (double)t0;
@@ -972,48 +994,73 @@ k_ode_age2(const DevModel M, const double *__restrict__ theta, int64_t ld, int64
         const double *in = hist1 + (i * 2 + g) * (int64_t)hist_pitch(M.P1);
         for (int d = 0; d <= d0; ++d) out[hist_index<PASS2>(d, Q)] = in[d];
 #pragma unroll
-        for (int q = 0; q < (TR ? 5 : 4); ++q) y[q] = ck[((int64_t)d0 * 10 + q) * kTile];
+        for (int j = 0; j < 4; ++j) y[j] = ck[((int64_t)d0 * 10 + j) * kTile];
       }
     }
   }
-  Seg2 sg = select_segment_age2<FL>(M, th, ld, bp, nbp, (double)(t0 + d0), g, &tcut, 1.0 / M.Ny, 1.0 / M.No);
+  bool bp_sorted = true;
+  for (int k = 1; k < nbp; ++k) bp_sorted = bp_sorted && bp[k - 1] <= bp[k];
+  int kseg = -2;
+  const double invy = 1.0 / M.Ny, invo = 1.0 / M.No;
+  Seg2 sg = select_segment_age2<FL>(M, th, ld, bp, nbp, (double)(t0 + d0), g, &tcut, invy, invo, &kseg, bp_sorted);
 
   const int m = M.m;
-  const double h = 1.0 / (double)m, a1 = M.a1, gamma = M.gamma;
-  if (d0 == 0) out[0] = y[0];
+  const double h = 1.0 / (double)m;
+  if (alive && d0 == 0) out[0] = y[0];
   if constexpr (!PASS2) {
-    if (ck) {
+    if (ck && alive) {
 #pragma unroll
-      for (int q = 0; q < (TR ? 5 : 4); ++q) ck[q * kTile] = y[q];
+      for (int j = 0; j < 4; ++j) ck[j * kTile] = y[j];
     }
   }
-  for (int d = d0 + 1; d < nint; ++d) {
+  // day range of the warp: every chain walks it, live only inside its own (d0, nint)
+  const int d_first = __reduce_min_sync(kFull, alive ? d0 + 1 : 0x7fffffff);
+  const int d_end = __reduce_max_sync(kFull, alive ? nint : 0);
+  const bool pow2 = (m & (m - 1)) == 0;
+  const double hh2reg = 0.5 * h, h6reg = h / 6.0;
+  for (int d = d_first; d < d_end; ++d) {
+    const bool live = alive && d > d0 && d < nint;
     const double tday = (double)(t0 + d - 1);
-    for (int s = 0; s < m; ++s) {
-      const double a = tday + (double)s * h;
-      const double b = (s == m - 1) ? tday + 1.0 : tday + (double)(s + 1) * h;
-      double pa = a;
-      if constexpr (PASS2) {
-        if (a >= tcut) sg = select_segment_age2<FL>(M, th, ld, bp, nbp, a, g, &tcut, 1.0 / M.Ny, 1.0 / M.No);
-        while (tcut < b) {
-          rk4_piece_age2<TR>(a1, gamma, sg, y, pa, tcut, invN, Ngrp, nb, pairmask, even_lane, need_r);
-          pa = tcut;
-          sg = select_segment_age2<FL>(M, th, ld, bp, nbp, pa, g, &tcut, 1.0 / M.Ny, 1.0 / M.No);
+    const bool regular = pow2 && __all_sync(kFull, !live || tcut >= tday + 1.0);
+    double pa = tday;
+    if (regular) {
+      for (int s = 0; s < m; ++s) {
+        const double pb = pa + h;
+        rk4_step2w(L, sg, y, live, pa, pb, h, hh2reg, h6reg, need_r);
+        pa = pb;
+      }
+    } else {
+      int s = 0;
+      for (;;) {
+        const bool pending = live && s < m;
+        if (!__any_sync(kFull, pending)) break;
+        const double b = (s == m - 1) ? tday + 1.0 : tday + (double)(s + 1) * h;
+        bool step_done = true;
+        double pb = b;
+        if constexpr (PASS2) {
+          if (pending && pa >= tcut)
+            sg = select_segment_age2<FL>(M, th, ld, bp, nbp, pa, g, &tcut, invy, invo, &kseg, bp_sorted);
+          if (tcut < b) { pb = tcut; step_done = false; }  // a breakpoint strictly inside (pa, b): cut there
+        }
+        const double hh = pending ? pb - pa : 0.0, hh2 = 0.5 * hh, h6 = hh / 6.0;
+        rk4_step2w(L, sg, y, pending, pa, pending ? pb : pa, hh, hh2, h6, need_r);
+        if (pending) {
+          pa = pb;
+          if (step_done) ++s;
         }
       }
-      rk4_piece_age2<TR>(a1, gamma, sg, y, pa, b, invN, Ngrp, nb, pairmask, even_lane, need_r);
     }
-    out[hist_index<PASS2>(d, Q)] = y[0];
+    if (live) out[hist_index<PASS2>(d, Q)] = y[0];
     if constexpr (!PASS2) {
-      if (ck && d < cdays) {
+      if (ck && live && d < cdays) {
 #pragma unroll
-        for (int q = 0; q < (TR ? 5 : 4); ++q) ck[((int64_t)d * 10 + q) * kTile] = y[q];
+        for (int j = 0; j < 4; ++j) ck[((int64_t)d * 10 + j) * kTile] = y[j];
       }
     }
   }
   // either lane may have met an undecidable R test: the chain is flagged if one of them did
-  const int nr = (need_r ? 1 : 0) | __shfl_xor_sync(pairmask, need_r ? 1 : 0, 1);
-  if (g == 0 && need_r_flag) need_r_flag[i] = (nr || force_need_r) ? 1 : 0;
+  const unsigned nr = (__ballot_sync(kFull, need_r) >> L.shift) & 3u;
+  if (flags_r && g == 0 && need_r_flag) need_r_flag[i] = (nr || force_need_r) ? 1 : 0;
 }
 
 // ------------------------------------------------ K_ode, four lanes per chain
@@ -1096,7 +1143,6 @@ struct Lane4 {
 // MATCH.ANY + REDUX.OR + a divergence check in front of every RK4 step — 400 cycles per stage at 8,192 chains,
 // twice the thread-per-chain kernel.)  Chains that have nothing to do in a piece — finished, not started, fewer
 // pieces on a day a breakpoint cuts for a neighbour — run it with their state frozen (`commit` false).
-constexpr unsigned kFull = 0xffffffffu;
 
 template <bool GUARDED, bool HOLD>
 __device__ __forceinline__ void rhs4(const Lane4 &L, const Seg4 &sg, double t, double u, double v, double &du,
@@ -2548,17 +2594,15 @@ static cudaError_t launch_eval_fl(const EvalArgs &a) {
   const int n_sm = n_sm_of[di];
   cudaStream_t s = a.stream;
   if (a.ev) cudaEventRecord(a.ev[0], s);
-  const unsigned pair_blocks = (unsigned)((2 * n + 63) / 64);
-  // Lanes per chain of the age ODE passes.  Thread per chain for full batches; four lanes per chain (k_ode_age4)
-  // while a thread-per-chain launch would leave most schedulers with a single warp (<= 64 chains per SM: the
-  // 8,192-chain shard of the strong-scaled BASELINE configuration).  Two lanes per chain (k_ode_age2, round 1) lose
-  // at every size since the other two were tuned; kept for EPI_ODE_LANES = 2.  EPI_ODE_LANES = 1 | 2 | 4 forces one
-  // mapping (tests, bench).
+  const unsigned pair_blocks = (unsigned)((2 * n + 127) / 128);
+  // Lanes per chain of the age ODE passes.  Thread per chain for full batches; two lanes per chain (one per age group,
+  // warp-synchronous k_ode_age2) while a thread-per-chain launch would leave the schedulers short of warps — measured
+  // on the posterior cloud (step ms, one / two / four lanes; profiles/r2_summary.md): 4,096 chains 0.69 / 0.56 / 0.59,
+  // 8,192 0.82 / 0.69 / 0.77, 16,384 1.08 / 1.00 / 1.19, 24,576 1.46 / 1.36 / 1.80, 32,768 1.71 / 1.73 / 2.20.  The
+  // four-lane kernel (k_ode_age4) is kept for EPI_ODE_LANES = 4; EPI_ODE_LANES = 1 | 2 | 4 forces one mapping.
   int lanes = 1;
   if constexpr (Traits<FL>::kAge && !Traits<FL>::k2x) {  // (age-2x: thread per chain only)
-    // measured on the posterior cloud (profiles/r2_summary.md): 4,096 chains 0.59 ms (four lanes) vs 0.69 (one), 8,192
-    // 0.77 vs 0.82, 12,288 0.96 vs 0.95, 16,384 1.18 vs 1.07, 32,768 2.20 vs 1.70; two lanes per chain never win
-    lanes = a.ode_lanes ? a.ode_lanes : (n <= (int64_t)n_sm * 64 ? 4 : 1);
+    lanes = a.ode_lanes ? a.ode_lanes : (n <= (int64_t)n_sm * 176 ? 2 : 1);
   }
   constexpr bool kFallback = !Traits<FL>::k2x;  // the R-tracking fallback instance exists where the hot one does not integrate R
   const bool use_pair = lanes == 2, use_quad = lanes == 4;
@@ -2578,7 +2622,7 @@ static cudaError_t launch_eval_fl(const EvalArgs &a) {
         else k_ode_age4<FL, false, 7><<<quad_blocks, 128, 0, s>>>(M, a.theta, a.ld, n, nullptr, nullptr, nullptr, a.hist1, a.ckpt, 0, limit, retry, a.need_r, a.force_need_r);
       }
     } else if (use_pair) {
-      if constexpr (Traits<FL>::kAge) k_ode_age2<FL, false><<<pair_blocks, 64, 0, s>>>(M, a.theta, a.ld, n, nullptr, nullptr, nullptr, a.hist1, a.ckpt, 0, limit, retry, a.need_r, a.force_need_r);
+      if constexpr (Traits<FL>::kAge) k_ode_age2<FL, false><<<pair_blocks, 128, 0, s>>>(M, a.theta, a.ld, n, nullptr, nullptr, nullptr, a.hist1, a.ckpt, 0, limit, retry, a.need_r, a.force_need_r);
     } else {
       k_ode<FL, false><<<ode_blocks, 32, 0, s>>>(M, a.theta, a.ld, n, nullptr, nullptr, nullptr, a.hist1, a.ckpt, nullptr, 0, 0, limit, retry, a.need_r, a.force_need_r);
     }
@@ -2602,7 +2646,7 @@ static cudaError_t launch_eval_fl(const EvalArgs &a) {
     if constexpr (Traits<FL>::kAge) {
       if (use_quad && quad_roomy) k_ode_age4<FL, true, 4><<<quad_blocks, 128, 0, s>>>(M, a.theta, a.ld, n, a.offset, a.pad, a.hist1, a.hist2, a.ckpt, window_only, 0, nullptr, a.need_r, a.force_need_r);
       else if (use_quad) k_ode_age4<FL, true, 7><<<quad_blocks, 128, 0, s>>>(M, a.theta, a.ld, n, a.offset, a.pad, a.hist1, a.hist2, a.ckpt, window_only, 0, nullptr, a.need_r, a.force_need_r);
-      else k_ode_age2<FL, true><<<pair_blocks, 64, 0, s>>>(M, a.theta, a.ld, n, a.offset, a.pad, a.hist1, a.hist2, a.ckpt, window_only, 0, nullptr, a.need_r, a.force_need_r);
+      else k_ode_age2<FL, true><<<pair_blocks, 128, 0, s>>>(M, a.theta, a.ld, n, a.offset, a.pad, a.hist1, a.hist2, a.ckpt, window_only, 0, nullptr, a.need_r, a.force_need_r);
     }
     k_ode<FL, true, false, true><<<ode_blocks, 32, 0, s>>>(M, a.theta, a.ld, n, a.offset, a.pad, a.hist1, a.hist2, a.ckpt, nullptr, 0, window_only, 0, nullptr, a.need_r, 0);
     nl += 2;

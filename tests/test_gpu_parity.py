@@ -622,12 +622,12 @@ def test_removed_compartment_fallback_is_bit_identical(name, m, monkeypatch):
 
 @pytest.mark.parametrize("name", ["A300", "I290"])
 def test_both_ode_kernels_produce_the_same_bits(name):
-    """Small batches of the age flavours use four lanes per chain (k_ode_age4), large ones a thread per chain
+    """Small batches of the age flavours use two lanes per chain (k_ode_age2), large ones a thread per chain
     (k_ode): the same theta must give the same bits through either."""
     M = _model(name, 4)
     theta = np.array(load_golden(name)["theta"])
     small = M.calclogpost_batch(theta)
-    reps = 45000 // len(theta) + 1          # > 256 chains per SM: thread-per-chain launch
+    reps = 45000 // len(theta) + 1          # > 176 chains per SM: thread-per-chain launch
     big = M.calclogpost_batch(np.tile(theta, (reps, 1)))
     for a, b in zip(small, big):
         assert np.array_equal(a, b[:len(theta)], equal_nan=True)
