@@ -30,7 +30,9 @@ source("settings.R")
 
 if (!exists("gpu_chains")) gpu_chains <- 4096     # chains per rung on the device
 if (!exists("gpu_files")) gpu_files <- 4          # sample files written (the reference writes 4 chains)
-if (!exists("gpu_kind")) gpu_kind <- 1L           # 1 = DE-MC, 0 = adaptive random-walk Metropolis
+if (!exists("gpu_kind")) gpu_kind <- 1L           # 1 = DE-MC, 0 = adaptive random-walk Metropolis, 2 = drjacoby's own
+                                                  # one-parameter update (burn-in / samples then count sweeps, as in drjacoby;
+                                                  # use it with gpu_rungs <- 20L for the reference's tempering ladder)
 if (!exists("gpu_rungs")) gpu_rungs <- 1L         # drjacoby's rungs = 20 is available; DE-MC does not need it
 if (!exists("gpu_seed")) gpu_seed <- 42
 
