@@ -383,17 +383,17 @@ def timed(batch, steps, warmup, comm, dev):
 
 
 def kernel_ms(batch, reps, dev):
-    """mean device time of the four launches of a step (CUDA events on the launching stream)"""
+    """median device time of the four launches of a step over `reps` steps (CUDA events on the launching stream)"""
     import torch
     M = batch.M
     M.set_timing(True)
-    k = np.zeros(4)
+    k = []
     for _ in range(reps):
         batch.step()
-        k += np.array(M.last_kernel_ms())
+        k.append(M.last_kernel_ms())
     M.set_timing(False)
     torch.cuda.synchronize(dev)
-    return k / reps
+    return np.median(np.array(k), axis=0)   # (median: one disturbed repetition must not colour the per-kernel split)
 
 
 KNAMES = ["ode_pass1", "profiles_threshold", "ode_pass2", "score"]

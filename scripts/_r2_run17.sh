@@ -1,3 +1,3 @@
 set -x
 N=$1
-python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/r2_bench_n${N}_d.json 2> gpurun_out/r2_bench_n${N}_d.err; echo rc=$?; tail -3 gpurun_out/r2_bench_n${N}_d.err
+python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/r2_bench_n${N}_f.json 2> gpurun_out/r2_bench_n${N}_f.err; echo rc=$?; tail -3 gpurun_out/r2_bench_n${N}_f.err

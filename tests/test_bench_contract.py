@@ -20,7 +20,7 @@ BASE_KEYS = ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_ste
              "vs_baseline", "dtype", "data", "config", "e2e")
 
 
-OWN_LINES = [("r2_bench_n1_e.json", 1), ("r2_bench_n8_d.json", 8)]
+OWN_LINES = [("r2_bench_n1_e.json", 1), ("r2_bench_n8_f.json", 8)]
 
 
 @pytest.mark.parametrize("name,n_gpus", OWN_LINES)
