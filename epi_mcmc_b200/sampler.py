@@ -195,35 +195,19 @@ class Sampler:
         halves = torch.stack([c[:h], c[h:2 * h]], dim=0)                     # [2, h, p, B]
         hm = halves.mean(dim=1)                                              # [2, p, B]
         hv = halves.var(dim=1, unbiased=True)                                # [2, p, B]
-        rep_mean_np, hm_np, hv_np = rep_mean.cpu().numpy(), hm.cpu().numpy(), hv.cpu().numpy()
-        sums = np.concatenate([[cnt], (tot_mean * cnt).cpu().numpy(), ss_tot.cpu().numpy()])
+        part = dict(rep_mean=rep_mean.cpu().numpy(), hm=hm.cpu().numpy(), hv=hv.cpu().numpy(), cnt=cnt,
+                    s1=(tot_mean * cnt).cpu().numpy(), s2=ss_tot.cpu().numpy())
+        parts = [part]
         if comm is not None and comm.world > 1:
-            parts = comm.allgather_np(rep_mean_np)
-            # DE-MC: replicate b spans the ranks (its chains draw partners from all of them), so its mean is the mean
-            # of the ranks' parts (equal chain counts); chains without partners (RWM, DRJ) are independent everywhere
-            rep_mean_np = np.mean(parts, axis=0) if self.kind == "demc" else np.concatenate(parts, axis=1)
-            hm_np = np.concatenate(comm.allgather_np(hm_np), axis=2)
-            hv_np = np.concatenate(comm.allgather_np(hv_np), axis=2)
-            # pooled variance across ranks: combine (count, sum, sum of squares about the LOCAL mean)
-            parts = comm.allgather_np(sums)
-            P = len(idx)
-            cnts = np.array([q[0] for q in parts]); s1 = np.array([q[1:1 + P] for q in parts]); s2 = np.array([q[1 + P:] for q in parts])
-            gmean = s1.sum(0) / cnts.sum()
-            lmean = s1 / cnts[:, None]
-            ss = (s2 + cnts[:, None] * (lmean - gmean) ** 2).sum(0)
-            var_post = ss / (cnts.sum() - 1)
-        else:
-            var_post = sums[1 + len(idx):] / (cnt - 1)
-        Bt = rep_mean_np.shape[1]
-        var_rep = rep_mean_np.var(axis=1, ddof=1)
-        ess = Bt * var_post / np.maximum(var_rep, 1e-300)
-        # split R-hat (Gelman et al. 2013): chains = 2 * Bt half-chains of length h
-        m_ = np.concatenate([hm_np[0], hm_np[1]], axis=1)   # [p, 2 Bt]
-        v_ = np.concatenate([hv_np[0], hv_np[1]], axis=1)
-        W = v_.mean(axis=1)
-        Bv = h * m_.var(axis=1, ddof=1)
-        rhat = np.sqrt(((h - 1) / h * W + Bv / h) / np.maximum(W, 1e-300))
-        return dict(ess=ess, rhat=rhat, post_sd=np.sqrt(var_post), n_replicates=Bt, kept=k)
+            keys_ = ("rep_mean", "hm", "hv", "s1", "s2")
+            gathered = {kk: comm.allgather_np(part[kk]) for kk in keys_}
+            cnts = comm.allgather_np(np.array([cnt]))
+            parts = [dict({kk: gathered[kk][r] for kk in keys_}, cnt=float(cnts[r][0])) for r in range(comm.world)]
+        # DE-MC: replicate b spans the ranks (its chains draw partners from all of them); chains without partners
+        # (RWM, DRJ) are independent everywhere, so every rank's replicates count separately
+        out = combine_replicate_stats(parts, pooled=self.kind == "demc", half_len=h)
+        out["kept"] = k
+        return out
 
     def draws(self):
         """(draws[k, chain, d], logpost[k, chain]) of the recorded thinned states"""
@@ -238,6 +222,32 @@ class Sampler:
 
 
 # ----------------------------------------------------------------------------- ESS
+def combine_replicate_stats(parts, pooled: bool, half_len: int) -> dict:
+    """Replicate statistics of a whole run from the per-rank pieces Sampler.replicate_stats reduces on the device.
+    Each part: rep_mean[p, B] (mean of replicate b over its chains of that rank and the recorded draws), hm / hv[2, p, B]
+    (mean / variance of the two halves of one chain per replicate), cnt (states behind the rank's sums), s1[p] (sum),
+    s2[p] (sum of squares about the rank's own mean).  pooled: replicate b of every rank is ONE replicate (DE-MC across
+    ranks: equal chain counts, so its mean is the mean of the ranks' means); else the ranks' replicates are distinct.
+    ESS of the posterior-mean estimator = B_total * var_posterior / var(replicate means); split R-hat over the
+    2 * B half-chains (Gelman et al. 2013)."""
+    rep = np.mean([q["rep_mean"] for q in parts], axis=0) if pooled else np.concatenate([q["rep_mean"] for q in parts], axis=1)
+    hm = np.concatenate([q["hm"] for q in parts], axis=2)
+    hv = np.concatenate([q["hv"] for q in parts], axis=2)
+    cnts = np.array([q["cnt"] for q in parts], dtype=float)
+    s1 = np.array([q["s1"] for q in parts])
+    s2 = np.array([q["s2"] for q in parts])
+    gmean = s1.sum(0) / cnts.sum()
+    lmean = s1 / cnts[:, None]
+    var_post = (s2 + cnts[:, None] * (lmean - gmean) ** 2).sum(0) / (cnts.sum() - 1)
+    Bt = rep.shape[1]
+    ess = Bt * var_post / np.maximum(rep.var(axis=1, ddof=1), 1e-300)
+    m_ = np.concatenate([hm[0], hm[1]], axis=1)   # [p, 2 B]
+    W = np.concatenate([hv[0], hv[1]], axis=1).mean(axis=1)
+    h = float(half_len)
+    rhat = np.sqrt(((h - 1) / h * W + m_.var(axis=1, ddof=1)) / np.maximum(W, 1e-300))
+    return dict(ess=ess, rhat=rhat, post_sd=np.sqrt(var_post), n_replicates=Bt)
+
+
 def _spectrum0_ar(x: np.ndarray) -> float:
     """coda::spectrum0.ar: spectral density at frequency zero from an AR(p) fit (Yule-Walker,
     order by AIC, p <= 10*log10(n)).  This is what coda::effectiveSize — and the ESS drjacoby

@@ -33,6 +33,8 @@ def _worker(rank, world, port, q):
     mx = comm.max_over_ranks(1.0 + rank)
     tot = comm.allreduce_sum([10.0 + rank, 100.0])     # the acceptance totals Sampler.tune_scale reduces
     ok &= bool(tot[0] == 21.0 and tot[1] == 200.0)
+    parts = comm.allgather_np(np.full((2, 3), float(rank)))   # the per-rank replicate statistics of Sampler.replicate_stats
+    ok &= len(parts) == world and all(parts[r].shape == (2, 3) and (parts[r] == r).all() for r in range(world))
     comm.barrier()
     q.put((rank, bool(ok), mx, first, cnt))
     comm.close()
@@ -89,3 +91,40 @@ def test_ess_estimator_on_known_ar1():
         for i in range(1, n):
             x[i] = rho * x[i - 1] + e[i]
         assert effective_size(x) / n == pytest.approx((1 - rho) / (1 + rho), rel=0.15)
+
+
+def test_replicate_statistics_on_iid_draws():
+    """combine_replicate_stats (the cross-rank half of Sampler.replicate_stats): for independent N(3, 2^2) draws the ESS
+    of the posterior-mean estimator is the number of states (within the sqrt(2 / (B - 1)) noise of a variance
+    estimated from B replicate means), split R-hat is 1, the pooled variance is exact across ranks with different
+    means; a replicate that spans two ranks (DE-MC) counts once."""
+    sys.path.insert(0, ROOT)
+    from epi_mcmc_b200.sampler import combine_replicate_stats
+    rng = np.random.default_rng(0)
+
+    def part(x):   # x[k, p, B, cpr], what the device reduction produces for one rank
+        k = x.shape[0]
+        rep = x.mean(axis=(0, 3))
+        tot = rep.mean(axis=1)
+        cnt = float(x.size / x.shape[1])
+        c, h = x[:, :, :, 0], k // 2
+        halves = np.stack([c[:h], c[h:2 * h]])
+        return dict(rep_mean=rep, hm=halves.mean(axis=1), hv=halves.var(axis=1, ddof=1), cnt=cnt, s1=tot * cnt,
+                    s2=((x - tot[None, :, None, None]) ** 2).sum(axis=(0, 2, 3)))
+
+    xs = [3 + 2 * rng.standard_normal((40, 2, 32, 64)) for _ in range(2)]
+    n_states = 2 * 40 * 32 * 64
+    for pooled, B in ((False, 64), (True, 32)):
+        r = combine_replicate_stats([part(x) for x in xs], pooled, 20)
+        assert r["n_replicates"] == B
+        assert np.all(np.abs(r["ess"] / n_states - 1) < 4 * np.sqrt(2 / (B - 1)))
+        assert np.all(np.abs(r["rhat"] - 1) < 0.02) and np.allclose(r["post_sd"], 2.0, rtol=0.01)
+    # ranks with different means: the pooled variance is the variance of the union
+    ys = [xs[0], xs[1] + 5.0]
+    r = combine_replicate_stats([part(y) for y in ys], False, 20)
+    union = np.concatenate([y.transpose(1, 0, 2, 3).reshape(2, -1) for y in ys], axis=1)
+    assert np.allclose(r["post_sd"], union.std(axis=1, ddof=1), rtol=1e-12)
+    # strongly autocorrelated replicates (every chain of a replicate shares one draw): ESS = number of replicates
+    z = np.repeat(rng.standard_normal((1, 2, 64, 1)), 40, axis=0).repeat(16, axis=3)
+    r = combine_replicate_stats([part(z)], False, 20)
+    assert np.all(np.abs(r["ess"] / 64 - 1) < 0.05)
