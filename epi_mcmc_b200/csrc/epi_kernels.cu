@@ -928,6 +928,28 @@ __device__ __forceinline__ void rk4_step2w(const Lane2 &L, const Seg2 &sg, doubl
   }
 }
 
+// the same piece when EVERY chain of the warp takes the result (the usual case on a regular day): from yin into a
+// distinct array yout, no per-lane selects and no copy back (the caller ping-pongs between two state arrays)
+__device__ __forceinline__ void rk4_step2w_all(const Lane2 &L, const Seg2 &sg, const double *yin, double *yout, double pa,
+                                               double pb, double hh, double hh2, double h6, bool &need_r) {
+  bool nr = false;
+  const bool hold = __all_sync(kFull, sg.hold);
+  bool ok = hold ? rk4_try2w<false, true>(L, sg, yin, yout, pa, pb, hh, hh2, h6, nr)
+                 : rk4_try2w<false, false>(L, sg, yin, yout, pa, pb, hh, hh2, h6, nr);
+  ok = ok && sg.fast_ok;
+  if (__any_sync(kFull, !ok)) {
+    double gy[4];
+    bool gnr = false;
+    rk4_try2w<true, false>(L, sg, yin, gy, pa, pb, hh, hh2, h6, gnr);
+    if (!ok) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) yout[i] = gy[i];
+      nr = gnr;
+    }
+  }
+  need_r = need_r || nr;
+}
+
 template <int FL, bool PASS2>
 __global__ void __launch_bounds__(128, 4)
 k_ode_age2(const DevModel M, const double *__restrict__ theta, int64_t ld, int64_t n, const int *__restrict__ offset,
@@ -1023,7 +1045,16 @@ k_ode_age2(const DevModel M, const double *__restrict__ theta, int64_t ld, int64
     const double tday = (double)(t0 + d - 1);
     const bool regular = pow2 && __all_sync(kFull, !live || tcut >= tday + 1.0);
     double pa = tday;
-    if (regular) {
+    if (regular && (m & 1) == 0 && __all_sync(kFull, live)) {
+      // every chain of the warp integrates this day: sub-steps in pairs, ping-pong between two state arrays
+      double z[4];
+      for (int s = 0; s < m; s += 2) {
+        const double pm = pa + h, pb = pm + h;
+        rk4_step2w_all(L, sg, y, z, pa, pm, h, hh2reg, h6reg, need_r);
+        rk4_step2w_all(L, sg, z, y, pm, pb, h, hh2reg, h6reg, need_r);
+        pa = pb;
+      }
+    } else if (regular) {
       for (int s = 0; s < m; ++s) {
         const double pb = pa + h;
         rk4_step2w(L, sg, y, live, pa, pb, h, hh2reg, h6reg, need_r);
