@@ -26,7 +26,7 @@ INVALID_DATA_OFFSET = 10000
 ST_INVALID_OFFSET, ST_NA, ST_OUT_OF_BOX, ST_UNSUPPORTED = 1, 2, 8, 16
 LAYOUT_AOS, LAYOUT_SOA = 0, 1
 SAMPLER_RWM, SAMPLER_DEMC, SAMPLER_DRJ = 0, 1, 2
-SAMPLER_FLAG_FULLDIM, SAMPLER_FLAG_REPLICATES = 1, 2
+SAMPLER_FLAG_FULLDIM, SAMPLER_FLAG_REPLICATES, SAMPLER_FLAG_NO_SINGLE = 1, 2, 4
 
 ERR_NAMES = {0: "EPI_OK", 1: "EPI_ERR_ARG", 2: "EPI_ERR_NO_DEVICE", 3: "EPI_ERR_CUDA",
              4: "EPI_ERR_NOMEM", 5: "EPI_ERR_STATE"}

@@ -24,7 +24,7 @@ KINDS = {"rwm": _capi.SAMPLER_RWM, "demc": _capi.SAMPLER_DEMC, "drj": _capi.SAMP
 class Sampler:
     def __init__(self, model, n_chains: int, kind: str = "demc", seed: int = 42, scale: float | None = None,
                  de_eps: float = 1e-4, beta: float = 1.0, chain_id0: int = 0, theta0=None, rungs: int = 1,
-                 GTI_pow: float = 1.0, subspace: bool = True, replicates: bool = False):
+                 GTI_pow: float = 1.0, subspace: bool = True, replicates: bool = False, single: bool = True):
         """n_chains is the total on this device; with `rungs` > 1 (parallel tempering, the
         reference driver uses rungs = 20, GTI_pow = 1: fitMCMC-drj.R:53-56) chain i sits on rung
         i // (n_chains // rungs) and the LAST rung is the cold one.
@@ -32,6 +32,8 @@ class Sampler:
         kind "drj" is drjacoby's own update (one parameter at a time on the logit-reparameterised box,
         per-parameter Robbins-Monro bandwidths towards 0.44 acceptance during burn-in, Metropolis coupling of
         adjacent rungs after every sweep): one `run` iteration is one sweep = d evaluations per chain.
+
+        single=True (default): a quarter of the DE-MC proposals moves one coordinate only (see epi_sampler.cu).
 
         replicates=True turns the `rungs` into independent replicate populations at beta = 1 (no swaps): the
         spread of their means measures the Monte-Carlo error of the run (`replicate_stats`)."""
@@ -49,7 +51,8 @@ class Sampler:
             scale = 1.0
         cfg = _capi.SamplerCfg(KINDS[kind], self.n_chains, int(chain_id0), int(seed), float(scale), float(de_eps),
                                float(beta), self.rungs,
-                               (0 if subspace else _capi.SAMPLER_FLAG_FULLDIM) | (_capi.SAMPLER_FLAG_REPLICATES if replicates else 0),
+                               (0 if subspace else _capi.SAMPLER_FLAG_FULLDIM) | (_capi.SAMPLER_FLAG_REPLICATES if replicates else 0)
+                               | (0 if single else _capi.SAMPLER_FLAG_NO_SINGLE),
                                float(GTI_pow))
         # subspace: DE-MC proposals move a random subset of the coordinates (DREAM-style crossover)
         t0 = None

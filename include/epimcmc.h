@@ -100,7 +100,7 @@ extern "C" {
 #define EPI_SAMPLER_RWM 0 /* random-walk Metropolis, per-parameter Gaussian scale */
 #define EPI_SAMPLER_DEMC 1 /* differential evolution MC (ter Braak 2006) on a population snapshot */
 /* epi_sampler_cfg.reserved carries flags.  By default a DE-MC proposal moves a random subset of the coordinates
- * (DREAM-style crossover, CR drawn from {0.1, 0.25, 0.5, 1}); this flag restores full-dimensional moves.        */
+ * (DREAM-style crossover, CR drawn from {0.1, 0.25, 0.5, single coordinate}); this flag restores full-dimensional moves. */
 #define EPI_SAMPLER_FLAG_FULLDIM 1
 /* drjacoby's own update (the sampler R/MCMC/fitMCMC-drj.R:48-57 drives): one parameter at a time, a Gaussian step
  * of per-chain, per-parameter bandwidth on the logit-reparameterised box phi = log((theta - min) / (max - theta))
@@ -113,6 +113,10 @@ extern "C" {
  * replicate draw their DE-MC partners from that replicate only.  The spread of the replicate means is an honest
  * estimate of the Monte-Carlo error of the whole run (bench.py's ESS figure).                                   */
 #define EPI_SAMPLER_FLAG_REPLICATES 2
+/* DE-MC: by default a quarter of the proposals (the CR = 1 slot of the crossover mixture) moves a single coordinate,
+ * chosen uniformly, with gamma = 2.38 / sqrt(2) times the scale mixture — one-parameter moves from the population's
+ * own differences; this flag puts CR = 1 back into that slot.                                                     */
+#define EPI_SAMPLER_FLAG_NO_SINGLE 4
 
 typedef struct epi_handle epi_handle;
 

@@ -20,8 +20,8 @@ for _ in range(600):
     S.run(10); S.refresh_population()
 S.adapt(False)
 start = S.get()[0]
-for kind, burn, rec, thin in (("demc", 0, 4500, 15), ("drj", 20, 100, 1)):
-    T = Sampler(M, n, kind=kind, seed=7, rungs=B, replicates=True, theta0=start)
+for kind, burn, rec, thin, kw in (("demc", 0, 4500, 15, {"single": False}), ("demc", 0, 4500, 15, {}), ("drj", 20, 100, 1, {})):
+    T = Sampler(M, n, kind=kind, seed=7, rungs=B, replicates=True, theta0=start, **kw)
     if burn:
         T.adapt(True); T.run(burn); T.adapt(False)
     e0 = T.stats()["evals"]
@@ -31,7 +31,7 @@ for kind, burn, rec, thin in (("demc", 0, 4500, 15), ("drj", 20, 100, 1)):
     full, half = T.replicate_stats(keys), T.replicate_stats(keys, last=(rec // thin) // 2)
     ev = st["evals"] - e0
     ef, eh = np.median(full["ess"]), np.median(half["ess"])
-    print(f"{kind}: {rec} iterations, {ev / n:.0f} evals per chain in {dt:.1f} s, acceptance {st['accept_rate']:.3f}; "
+    print(f"{kind} {kw}: {rec} iterations, {ev / n:.0f} evals per chain in {dt:.1f} s, acceptance {st['accept_rate']:.3f}; "
           f"ESS median whole window {ef:.0f}, first half {eh:.0f}; growth per 1000 evals per chain "
           f"{(ef - eh) / (ev / n / 2) * 1000:.0f}; split R-hat median {np.median(full['rhat']):.2f}", flush=True)
 M.close()
