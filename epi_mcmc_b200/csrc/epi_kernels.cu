@@ -844,6 +844,99 @@ __device__ __noinline__ Seg2 select_segment_age2(const DevModel &M, const double
   return sg;
 }
 
+// The schedule of one chain as a TABLE in shared memory (pass 2): entry e = k + 1 holds the lane's Seg2 of schedule
+// index k = -1 .. nbp - 1 (beta pair and slopes already divided by N, flags), computed once in the kernel prologue
+// with the operations of select_segment_age2 — same bits.  Cycle counters in the kernel (profiles/r2_summary.md,
+// 8,192 chains): a warp re-selected ~60 times per launch at ~1,500 cycles each (two dependent global loads through
+// the schedule entry and theta, three divisions) = 14 % of pass 2; from the table it is a scan of bp[] and five LDS.
+// Layout [entry][field][thread]: consecutive lanes -> consecutive banks.
+constexpr int kSegFields = 5;  // bA, sA, bB, sB, flags
+// shared memory of a block: the breakpoints [NBP][thread] (the re-selection scans them: in local memory every probe
+// was an L1 miss, ~800 cycles per call), then the entries [NBP + 1][field][thread]
+template <int FL>
+__host__ __device__ constexpr size_t seg_table_bytes(int threads) {
+  return (size_t)(Traits<FL>::NBP + (Traits<FL>::NBP + 1) * kSegFields) * threads * sizeof(double);
+}
+
+template <int FL>
+__device__ __forceinline__ void fill_segment_table(const DevModel &M, const double *__restrict__ th, int64_t ld, const double *bp,
+                                                   int nbp, int is_o, double invy, double invo, double *bps, double *tab,
+                                                   int nthreads) {
+  constexpr int NBP = Traits<FL>::NBP;
+  // raw beta triples first, all loads of the schedule issued back to back (they are independent; entry by entry the
+  // prologue paid two dependent global round trips per entry); parked in the fields 0..2 of entry k + 1
+#pragma unroll
+  for (int k = 0; k < NBP; ++k) {
+    double by = 0.0, bo = 0.0, byo = 0.0;
+    if (k < nbp) age_beta<FL>(M, th, ld, k, by, bo, byo);
+    double *t = tab + (size_t)(k + 1) * kSegFields * nthreads;
+    t[0] = by; t[nthreads] = bo; t[2 * nthreads] = byo;
+    bps[k * nthreads] = k < nbp ? bp[k] : INFINITY;
+  }
+  // entry k + 1 from the triples k and k + 1, in ascending order (entry k + 1 overwrites triple k only after its use;
+  // triple k + 1 is still raw).  Entry 0 (k = -1: before the first breakpoint) is beta_0 held.
+  double by = tab[(size_t)kSegFields * nthreads], bo = tab[(size_t)(kSegFields + 1) * nthreads],
+         byo = tab[(size_t)(kSegFields + 2) * nthreads];
+#pragma unroll 1
+  for (int e = 0; e <= nbp; ++e) {
+    const int k = e - 1;
+    double ny = 0.0, no = 0.0, nyo = 0.0;
+    if (k + 1 < nbp && k + 1 >= 1) {
+      const double *t = tab + (size_t)(k + 2) * kSegFields * nthreads;
+      ny = t[0]; no = t[nthreads]; nyo = t[2 * nthreads];
+    }
+    double bA = is_o ? bo : by, bB = is_o ? byo : 0.0, sA = 0.0, sB = 0.0;
+    bool fast_ok, hold, lin = false;
+    if (k >= 0 && age_linear(M, k)) {
+      const double len = bps[(k + 1) * nthreads] - bps[k * nthreads];
+      lin = true;
+      sA = is_o ? (no - bo) / len : (ny - by) / len;
+      sB = is_o ? (nyo - byo) / len : 0.0;
+      fast_ok = by >= 0 && bo >= 0 && byo >= 0 && ny >= 0 && no >= 0 && nyo >= 0 && len > 0;
+      hold = __dmul_rn((ny - by) / len, invy) == 0.0 && __dmul_rn((no - bo) / len, invo) == 0.0 &&
+             __dmul_rn((nyo - byo) / len, invy) == 0.0;
+    } else {
+      fast_ok = by >= 0 && bo >= 0 && byo >= 0;
+      hold = true;
+    }
+    const double invA = is_o ? invo : invy;
+    double *t = tab + (size_t)e * kSegFields * nthreads;
+    t[0] = __dmul_rn(bA, invA);
+    t[nthreads] = __dmul_rn(sA, invA);
+    t[2 * nthreads] = __dmul_rn(bB, invy);
+    t[3 * nthreads] = __dmul_rn(sB, invy);
+    t[4 * nthreads] = __hiloint2double(0, (fast_ok ? 1 : 0) | (hold ? 2 : 0) | (lin ? 4 : 0));
+    if (k >= 0) { by = ny; bo = no; byo = nyo; }  // (k = -1 and k = 0 both start from beta_0)
+  }
+}
+
+// the segment active on a piece that starts at pa (the rule of select_segment), read from the table
+__device__ __forceinline__ Seg2 select_segment_tab(const double *tab, const double *bps, int nthreads, int nbp, double pa,
+                                                   double *tcut, int *kcur, bool sorted) {
+  int k = -1;
+  double tc = INFINITY;
+  if (sorted && *kcur >= -1) {
+    k = *kcur;
+    while (k + 1 < nbp && bps[(k + 1) * nthreads] <= pa) ++k;
+    if (k + 1 < nbp) tc = bps[(k + 1) * nthreads];
+  } else {
+    for (int i = 0; i < nbp; ++i) {
+      const double b = bps[i * nthreads];
+      if (b <= pa) k = i;
+      if (b > pa && b < tc) tc = b;
+    }
+  }
+  *kcur = k;
+  *tcut = tc;
+  const double *t = tab + (size_t)(k + 1) * kSegFields * nthreads;
+  Seg2 sg;
+  sg.bA = t[0]; sg.sA = t[nthreads]; sg.bB = t[2 * nthreads]; sg.sB = t[3 * nthreads];
+  const int fl = __double2loint(t[4 * nthreads]);
+  sg.fast_ok = fl & 1; sg.hold = fl & 2;
+  sg.tk = (fl & 4) ? bps[k * nthreads] : 0.0;
+  return sg;
+}
+
 struct Lane2 {
   double a1, gamma, Ngrp;
   int shift;     // first lane of this chain's pair == the lane that holds I_y
@@ -1024,7 +1117,17 @@ k_ode_age2(const DevModel M, const double *__restrict__ theta, int64_t ld, int64
   for (int k = 1; k < nbp; ++k) bp_sorted = bp_sorted && bp[k - 1] <= bp[k];
   int kseg = -2;
   const double invy = 1.0 / M.Ny, invo = 1.0 / M.No;
-  Seg2 sg = select_segment_age2<FL>(M, th, ld, bp, nbp, (double)(t0 + d0), g, &tcut, invy, invo, &kseg, bp_sorted);
+  Seg2 sg;
+  [[maybe_unused]] const double *tab = nullptr, *bps = nullptr;
+  if constexpr (PASS2) {
+    extern __shared__ double seg_smem[];
+    bps = seg_smem + threadIdx.x;
+    tab = bps + Traits<FL>::NBP * blockDim.x;
+    fill_segment_table<FL>(M, th, ld, bp, nbp, g, invy, invo, seg_smem + threadIdx.x, seg_smem + Traits<FL>::NBP * blockDim.x + threadIdx.x, blockDim.x);
+    sg = select_segment_tab(tab, bps, blockDim.x, nbp, (double)(t0 + d0), &tcut, &kseg, bp_sorted);
+  } else {
+    sg = select_segment_age2<FL>(M, th, ld, bp, nbp, (double)(t0 + d0), g, &tcut, invy, invo, &kseg, bp_sorted);
+  }
 
   const int m = M.m;
   const double h = 1.0 / (double)m;
@@ -1054,6 +1157,43 @@ k_ode_age2(const DevModel M, const double *__restrict__ theta, int64_t ld, int64
         rk4_step2w_all(L, sg, z, y, pm, pb, h, hh2reg, h6reg, need_r);
         pa = pb;
       }
+    } else if (PASS2 && pow2 && (m & 1) == 0) {
+      // A day some chain of the warp has a breakpoint in.  Only the SUB-STEP a breakpoint falls into is cut into
+      // pieces; the others keep the constants of a regular sub-step (for power-of-two m a whole sub-step has
+      // hh == h exactly, so these are the bits the general loop below computes), pairs of quiet sub-steps even the
+      // ping-pong form.  Cycle counters (8,192 chains): the general loop took such a day through five pieces of
+      // ~930 cycles against ~390 for a regular sub-step, 17 % of the days were 40 % of pass 2.
+      const bool all_live = __all_sync(kFull, live);
+      for (int s = 0; s < m; s += 2) {
+        const double pm = pa + h, pe = pm + h;
+        const bool quiet = __all_sync(kFull, !live || tcut >= pe);  // no breakpoint in [pa, pe) of any chain
+        if (quiet && all_live) {
+          double z[4];
+          rk4_step2w_all(L, sg, y, z, pa, pm, h, hh2reg, h6reg, need_r);
+          rk4_step2w_all(L, sg, z, y, pm, pe, h, hh2reg, h6reg, need_r);
+        } else {
+#pragma unroll 1
+          for (int u = 0; u < 2; ++u) {
+            const double a = u ? pm : pa, b = u ? pe : pm;
+            if (quiet || __all_sync(kFull, !live || tcut >= b)) {
+              rk4_step2w(L, sg, y, live, a, b, h, hh2reg, h6reg, need_r);
+              continue;
+            }
+            double pl = a;
+            bool open = live;
+            while (__any_sync(kFull, open)) {
+              if (open && pl >= tcut) sg = select_segment_tab(tab, bps, blockDim.x, nbp, pl, &tcut, &kseg, bp_sorted);
+              double pb = b;
+              bool done = true;
+              if (tcut < b) { pb = tcut; done = false; }  // a breakpoint strictly inside (pl, b): cut there
+              const double hh = open ? pb - pl : 0.0, hh2 = 0.5 * hh, h6 = hh / 6.0;
+              rk4_step2w(L, sg, y, open, pl, open ? pb : pl, hh, hh2, h6, need_r);
+              if (open) { pl = pb; open = !done; }
+            }
+          }
+        }
+        pa = pe;
+      }
     } else if (regular) {
       for (int s = 0; s < m; ++s) {
         const double pb = pa + h;
@@ -1069,8 +1209,7 @@ k_ode_age2(const DevModel M, const double *__restrict__ theta, int64_t ld, int64
         bool step_done = true;
         double pb = b;
         if constexpr (PASS2) {
-          if (pending && pa >= tcut)
-            sg = select_segment_age2<FL>(M, th, ld, bp, nbp, pa, g, &tcut, invy, invo, &kseg, bp_sorted);
+          if (pending && pa >= tcut) sg = select_segment_tab(tab, bps, blockDim.x, nbp, pa, &tcut, &kseg, bp_sorted);
           if (tcut < b) { pb = tcut; step_done = false; }  // a breakpoint strictly inside (pa, b): cut there
         }
         const double hh = pending ? pb - pa : 0.0, hh2 = 0.5 * hh, h6 = hh / 6.0;
@@ -2617,6 +2756,12 @@ static cudaError_t launch_eval_fl(const EvalArgs &a) {
     cudaFuncSetAttribute(k_mid<FL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(k_score<FL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(k_series<FL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if constexpr (Traits<FL>::kAge)
+    {
+      cudaFuncSetAttribute(k_ode_age2<FL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seg_table_bytes<FL>(128));
+      // (without it the driver sizes the carve-out for ONE block per SM and a 16,384-chain shard runs in two waves)
+      cudaFuncSetAttribute(k_ode_age2<FL, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    }
     cudaDeviceGetAttribute(&n_sm_of[di], cudaDevAttrMultiProcessorCount, dev);
     k_fill_log_table<<<1, kLogTabN, 0, a.stream>>>();
     cudaStreamSynchronize(a.stream);  // once per device and process: other streams may launch k_score next
@@ -2677,7 +2822,7 @@ static cudaError_t launch_eval_fl(const EvalArgs &a) {
     if constexpr (Traits<FL>::kAge) {
       if (use_quad && quad_roomy) k_ode_age4<FL, true, 4><<<quad_blocks, 128, 0, s>>>(M, a.theta, a.ld, n, a.offset, a.pad, a.hist1, a.hist2, a.ckpt, window_only, 0, nullptr, a.need_r, a.force_need_r);
       else if (use_quad) k_ode_age4<FL, true, 7><<<quad_blocks, 128, 0, s>>>(M, a.theta, a.ld, n, a.offset, a.pad, a.hist1, a.hist2, a.ckpt, window_only, 0, nullptr, a.need_r, a.force_need_r);
-      else k_ode_age2<FL, true><<<pair_blocks, 128, 0, s>>>(M, a.theta, a.ld, n, a.offset, a.pad, a.hist1, a.hist2, a.ckpt, window_only, 0, nullptr, a.need_r, a.force_need_r);
+      else k_ode_age2<FL, true><<<pair_blocks, 128, seg_table_bytes<FL>(128), s>>>(M, a.theta, a.ld, n, a.offset, a.pad, a.hist1, a.hist2, a.ckpt, window_only, 0, nullptr, a.need_r, a.force_need_r);
     }
     k_ode<FL, true, false, true><<<ode_blocks, 32, 0, s>>>(M, a.theta, a.ld, n, a.offset, a.pad, a.hist1, a.hist2, a.ckpt, nullptr, 0, window_only, 0, nullptr, a.need_r, 0);
     nl += 2;
