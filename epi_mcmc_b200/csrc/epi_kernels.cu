@@ -994,6 +994,45 @@ __device__ __forceinline__ bool rk4_try2w(const Lane2 &L, const Seg2 &sg, const 
   return ((__ballot_sync(kFull, (int)flag < 0) >> L.shift) & 3u) == 0u;
 }
 
+// the fast instance of a step without its verdict: returns the accumulated maybe-out-of-bounds flag (bit 31) for the
+// caller to vote on — k_ode_age2 votes once per DAY on its regular days
+template <bool HOLD>
+__device__ __forceinline__ unsigned rk4_raw2w(const Lane2 &L, const Seg2 &sg, const double *y, double *yn, double pa, double pb,
+                                             double hh, double hh2, double h6) {
+  const double tm = pa + hh2;
+  double k[4], acc[4], yt[4];
+  unsigned flag = 0;
+  rhs2w<false, HOLD>(L, sg, pa, y, k, flag);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { acc[i] = k[i]; yt[i] = fma(hh2, k[i], y[i]); }
+  rhs2w<false, HOLD>(L, sg, tm, yt, k, flag);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { acc[i] = fma(2.0, k[i], acc[i]); yt[i] = fma(hh2, k[i], y[i]); }
+  rhs2w<false, HOLD>(L, sg, tm, yt, k, flag);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { acc[i] = fma(2.0, k[i], acc[i]); yt[i] = fma(hh, k[i], y[i]); }
+  rhs2w<false, HOLD>(L, sg, pb, yt, k, flag);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) yn[i] = fma(h6, __dadd_rn(acc[i], k[i]), y[i]);
+  return flag;
+}
+
+// a whole regular day (m even) of fast steps from y into w, ping-pong over z; returns the accumulated flag
+template <bool HOLD>
+__device__ __forceinline__ unsigned rk4_day2w(const Lane2 &L, const Seg2 &sg, const double *y, double *w, double tday, double h,
+                                             double hh2, double h6, int m) {
+  double z[4];
+  double pa = tday, pm = pa + h, pb = pm + h;
+  unsigned flag = rk4_raw2w<HOLD>(L, sg, y, z, pa, pm, h, hh2, h6);
+  flag |= rk4_raw2w<HOLD>(L, sg, z, w, pm, pb, h, hh2, h6);
+  for (int s = 2; s < m; s += 2) {
+    pa = pb; pm = pa + h; pb = pm + h;
+    flag |= rk4_raw2w<HOLD>(L, sg, w, z, pa, pm, h, hh2, h6);
+    flag |= rk4_raw2w<HOLD>(L, sg, z, w, pm, pb, h, hh2, h6);
+  }
+  return flag;
+}
+
 // one RK4 piece for all sixteen chains of the warp; a chain takes the result only when `commit`
 __device__ __forceinline__ void rk4_step2w(const Lane2 &L, const Seg2 &sg, double *y, bool commit, double pa, double pb,
                                            double hh, double hh2, double h6, bool &need_r) {
@@ -1148,7 +1187,25 @@ k_ode_age2(const DevModel M, const double *__restrict__ theta, int64_t ld, int64
     const double tday = (double)(t0 + d - 1);
     const bool regular = pow2 && __all_sync(kFull, !live || tcut >= tday + 1.0);
     double pa = tday;
-    if (regular && (m & 1) == 0 && __all_sync(kFull, live)) {
+    // The usual day — every chain of the warp live, no breakpoint inside, beta >= 0 — with its votes in front and ONE
+    // behind: the fast steps run back to back (ping-pong between two state arrays) and only accumulate their
+    // maybe-out-of-bounds flag; if some chain
+    // raised it during the day (never in practice) the day is redone from its first state by the checked route below.
+    // Step probe (profiles/microbench/step_probe.cu, one warp per scheduler): 228 cycles per step against 265 with
+    // the three votes of a checked step; in the kernel the regular day took 1,520 cycles.
+    bool day_done = false;
+    if (regular && (m & 1) == 0 && __all_sync(kFull, live && sg.fast_ok)) {
+      double w[4];
+      const unsigned flag = __all_sync(kFull, sg.hold) ? rk4_day2w<true>(L, sg, y, w, tday, h, hh2reg, h6reg, m)
+                                                       : rk4_day2w<false>(L, sg, y, w, tday, h, hh2reg, h6reg, m);
+      if (!__any_sync(kFull, (int)flag < 0)) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) y[i] = w[i];
+        day_done = true;
+      }
+    }
+    if (day_done) {
+    } else if (regular && (m & 1) == 0 && __all_sync(kFull, live)) {
       // every chain of the warp integrates this day: sub-steps in pairs, ping-pong between two state arrays
       double z[4];
       for (int s = 0; s < m; s += 2) {
