@@ -135,6 +135,19 @@ __device__ __forceinline__ bool age_linear(const DevModel &M, int k) { return (M
 // step raises it the unguarded arithmetic is exactly what the guarded code would
 // have produced, otherwise the step is redone by the exact guarded slow path.
 
+// hh / 6 (the RK4 weight of a piece a breakpoint cut), correctly rounded without the division subroutine:
+//   z = RN(1/6) = (1/6)(1 - 2^-54);  q = RN(x z) is RN(x/6) or its lower neighbour;  r = x - 6 q is exact (a small
+//   multiple of 2 ulp(q));  q + r z = x/6 - (r/6) 2^-54 lies within 2^-54 ulp of x/6, and x/6 is never closer than
+//   ulp/6 to a rounding boundary (3 does not divide a power of two)  =>  RN(q + r z) == RN(x / 6) for every normal x.
+// (Markstein's division by a constant; tests/test_oracle.py checks it against the division on 10^6 values.)  The
+// division's slow-path branch kept the compiler from overlapping it with the stages of the piece it belongs to.
+__device__ __forceinline__ double div6(double x) {
+  constexpr double z = 1.0 / 6.0;
+  const double q = __dmul_rn(x, z);
+  const double r = fma(-6.0, q, x);
+  return fma(r, z, q);
+}
+
 // current schedule segment: value at tk and slope per curve (slope 0 = hold)
 struct Seg {
   double tk, b0, b1, b2, s0, s1, s2;  // age: betay/betao/betayo; simple: beta, Tinf, 1/Tinf cache
@@ -740,7 +753,7 @@ k_ode(const DevModel M, const double *__restrict__ theta, int64_t ld, int64_t n,
         if constexpr (PASS2) {
           if (tcut < b) { pb = tcut; step_done = false; }  // a breakpoint strictly inside (pa, b): cut there
         }
-        hh = pb - pa; hh2 = 0.5 * hh; h6 = hh / 6.0;
+        hh = pb - pa; hh2 = 0.5 * hh; h6 = div6(hh);
       }
       rk4_piece<FL, TR>(M, sg, y, pa, pb, hh, hh2, h6, inv0, inv1, nb0, nb1, need_r);
       pa = pb;
@@ -1243,7 +1256,7 @@ k_ode_age2(const DevModel M, const double *__restrict__ theta, int64_t ld, int64
               double pb = b;
               bool done = true;
               if (tcut < b) { pb = tcut; done = false; }  // a breakpoint strictly inside (pl, b): cut there
-              const double hh = open ? pb - pl : 0.0, hh2 = 0.5 * hh, h6 = hh / 6.0;
+              const double hh = open ? pb - pl : 0.0, hh2 = 0.5 * hh, h6 = div6(hh);
               rk4_step2w(L, sg, y, open, pl, open ? pb : pl, hh, hh2, h6, need_r);
               if (open) { pl = pb; open = !done; }
             }
@@ -1269,7 +1282,7 @@ k_ode_age2(const DevModel M, const double *__restrict__ theta, int64_t ld, int64
           if (pending && pa >= tcut) sg = select_segment_tab(tab, bps, blockDim.x, nbp, pa, &tcut, &kseg, bp_sorted);
           if (tcut < b) { pb = tcut; step_done = false; }  // a breakpoint strictly inside (pa, b): cut there
         }
-        const double hh = pending ? pb - pa : 0.0, hh2 = 0.5 * hh, h6 = hh / 6.0;
+        const double hh = pending ? pb - pa : 0.0, hh2 = 0.5 * hh, h6 = div6(hh);
         rk4_step2w(L, sg, y, pending, pa, pending ? pb : pa, hh, hh2, h6, need_r);
         if (pending) {
           pa = pb;
@@ -1564,7 +1577,7 @@ k_ode_age4(const DevModel M, const double *__restrict__ theta, int64_t ld, int64
             sg = select_segment4<FL>(M, th, ld, bp, nbp, pa, g, L.half, &tcut, invy, invo, &kseg, bp_sorted);
           if (tcut < b) { pb = tcut; step_done = false; }  // a breakpoint strictly inside (pa, b): cut there
         }
-        const double hh = pending ? pb - pa : 0.0, hh2 = 0.5 * hh, h6 = hh / 6.0;
+        const double hh = pending ? pb - pa : 0.0, hh2 = 0.5 * hh, h6 = div6(hh);
         rk4_step4(L, sg, u, v, pending, pa, pending ? pb : pa, hh, hh2, h6, need_r);
         if (pending) {
           pa = pb;

@@ -396,3 +396,25 @@ def test_ode_path_2x_through_the_reference_binary(oracle):
         assert e8 < 1e-4 and e16 < 1e-5 and e16 < e8 / 8, (e8, e16)
         checked += 1
     assert checked >= 2
+
+
+def test_division_by_six_through_fma_is_the_division():
+    """The ODE kernels compute hh / 6 of a cut RK4 piece as q = x * RN(1/6); r = fma(-6, q, x); q + r * RN(1/6)
+    (epi_kernels.cu:div6) while the oracle divides: the two must agree in every bit (proof in the kernel source;
+    here 10^6 random piece lengths, values next to powers of two and next to multiples of six ulps)."""
+    import ctypes
+    libm = ctypes.CDLL("libm.so.6")
+    libm.fma.restype = ctypes.c_double
+    libm.fma.argtypes = [ctypes.c_double] * 3
+    z = 1.0 / 6.0
+    rng = np.random.default_rng(5)
+    xs = np.concatenate([rng.uniform(0.0, 0.25, 400000), 10.0 ** rng.uniform(-17, 2, 400000),
+                         np.ldexp(rng.integers(1, 1 << 53, 200000).astype(np.float64), -rng.integers(50, 70, 200000)),
+                         np.nextafter(2.0 ** np.arange(-40.0, 4.0), 0.0), np.nextafter(2.0 ** np.arange(-40.0, 4.0), 9.0),
+                         2.0 ** np.arange(-40.0, 4.0), [0.0, 0.25, 0.125, 1.0, 6.0, 3.0]])
+    bad = 0
+    for x in xs.tolist():
+        q = x * z
+        r = libm.fma(-6.0, q, x)
+        bad += libm.fma(r, z, q) != x / 6.0
+    assert bad == 0
