@@ -1206,7 +1206,7 @@ k_ode_age2(const DevModel M, const double *__restrict__ theta, int64_t ld, int64
     // raised it during the day (never in practice) the day is redone from its first state by the checked route below.
     // Step probe (profiles/microbench/step_probe.cu, one warp per scheduler): 228 cycles per step against 265 with
     // the three votes of a checked step; in the kernel the regular day took 1,520 cycles.
-    bool day_done = false;
+    bool day_done = false, general = false;
     if (regular && (m & 1) == 0 && __all_sync(kFull, live && sg.fast_ok)) {
       double w[4];
       const unsigned flag = __all_sync(kFull, sg.hold) ? rk4_day2w<true>(L, sg, y, w, tday, h, hh2reg, h6reg, m)
@@ -1228,41 +1228,45 @@ k_ode_age2(const DevModel M, const double *__restrict__ theta, int64_t ld, int64
         pa = pb;
       }
     } else if (PASS2 && pow2 && (m & 1) == 0) {
-      // A day some chain of the warp has a breakpoint in.  Only the SUB-STEP a breakpoint falls into is cut into
-      // pieces; the others keep the constants of a regular sub-step (for power-of-two m a whole sub-step has
-      // hh == h exactly, so these are the bits the general loop below computes), pairs of quiet sub-steps even the
-      // ping-pong form.  Cycle counters (8,192 chains): the general loop took such a day through five pieces of
-      // ~930 cycles against ~390 for a regular sub-step, 17 % of the days were 40 % of pass 2.
-      const bool all_live = __all_sync(kFull, live);
-      for (int s = 0; s < m; s += 2) {
-        const double pm = pa + h, pe = pm + h;
-        const bool quiet = __all_sync(kFull, !live || tcut >= pe);  // no breakpoint in [pa, pe) of any chain
-        if (quiet && all_live) {
-          double z[4];
-          rk4_step2w_all(L, sg, y, z, pa, pm, h, hh2reg, h6reg, need_r);
-          rk4_step2w_all(L, sg, z, y, pm, pe, h, hh2reg, h6reg, need_r);
-        } else {
-#pragma unroll 1
-          for (int u = 0; u < 2; ++u) {
-            const double a = u ? pm : pa, b = u ? pe : pm;
-            if (quiet || __all_sync(kFull, !live || tcut >= b)) {
-              rk4_step2w(L, sg, y, live, a, b, h, hh2reg, h6reg, need_r);
-              continue;
-            }
-            double pl = a;
-            bool open = live;
-            while (__any_sync(kFull, open)) {
-              if (open && pl >= tcut) sg = select_segment_tab(tab, bps, blockDim.x, nbp, pl, &tcut, &kseg, bp_sorted);
-              double pb = b;
-              bool done = true;
-              if (tcut < b) { pb = tcut; done = false; }  // a breakpoint strictly inside (pl, b): cut there
-              const double hh = open ? pb - pl : 0.0, hh2 = 0.5 * hh, h6 = div6(hh);
-              rk4_step2w(L, sg, y, open, pl, open ? pb : pl, hh, hh2, h6, need_r);
-              if (open) { pl = pb; open = !done; }
-            }
-          }
+      // A day some chain of the warp has a breakpoint in (or is not live): the chains walk their pieces together
+      // (a lane with a cut sub-step has one piece more and the others wait for it), every piece by the FAST step on
+      // the general (linear-segment) instance, flags accumulated, one vote at the end of the day — and the day redone
+      // from its first state by the checked loop below if some chain raised the flag or sits on a segment with a
+      // negative beta (never on a posterior).  Same pieces, same operations, same bits.  Cycle counters (8,192
+      // chains, profiles/r2_summary.md): the checked loop took such a day through five pieces of ~930 cycles (three
+      // votes, a division and a re-selection through global memory each) against ~390 for a regular sub-step; 17 %
+      // of the days were 40 % of pass 2.
+      double y0[4] = {y[0], y[1], y[2], y[3]};
+      unsigned flag = 0;
+      bool fok = true;
+      int s = 0;
+      double sb = tday, pl = tday;  // start of the current sub-step, start of the next piece
+      for (;;) {
+        const bool pending = live && s < m;
+        if (!__any_sync(kFull, pending)) break;
+        const double b = sb + h;  // (exact for power-of-two m: == tday + (s + 1) * h)
+        if (pending && pl >= tcut) sg = select_segment_tab(tab, bps, blockDim.x, nbp, pl, &tcut, &kseg, bp_sorted);
+        double pb = b;
+        bool done = true;
+        if (tcut < b) { pb = tcut; done = false; }  // a breakpoint strictly inside (pl, b): cut there
+        const double hh = pending ? pb - pl : 0.0, hh2 = 0.5 * hh, h6 = div6(hh);
+        fok = fok && (!pending || sg.fast_ok);
+        double yn[4];
+        const unsigned f = rk4_raw2w<false>(L, sg, y, yn, pl, pending ? pb : pl, hh, hh2, h6);
+        if (pending) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) y[i] = yn[i];
+          flag |= f;
+          pl = pb;
+          if (done) { ++s; sb = b; }
         }
-        pa = pe;
+      }
+      if (__any_sync(kFull, (int)flag < 0 || !fok)) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) y[i] = y0[i];
+        kseg = -2;  // (segment index unknown again: full scan)
+        sg = select_segment_tab(tab, bps, blockDim.x, nbp, tday, &tcut, &kseg, bp_sorted);
+        general = true;
       }
     } else if (regular) {
       for (int s = 0; s < m; ++s) {
@@ -1271,6 +1275,9 @@ k_ode_age2(const DevModel M, const double *__restrict__ theta, int64_t ld, int64
         pa = pb;
       }
     } else {
+      general = true;
+    }
+    if (general) {
       int s = 0;
       for (;;) {
         const bool pending = live && s < m;
