@@ -1195,30 +1195,53 @@ k_ode_age2(const DevModel M, const double *__restrict__ theta, int64_t ld, int64
   const int d_end = __reduce_max_sync(kFull, alive ? nint : 0);
   const bool pow2 = (m & (m - 1)) == 0;
   const double hh2reg = 0.5 * h, h6reg = h / 6.0;
-  for (int d = d_first; d < d_end; ++d) {
-    const bool live = alive && d > d0 && d < nint;
-    const double tday = (double)(t0 + d - 1);
-    const bool regular = pow2 && __all_sync(kFull, !live || tcut >= tday + 1.0);
-    double pa = tday;
-    // The usual day — every chain of the warp live, no breakpoint inside, beta >= 0 — with its votes in front and ONE
-    // behind: the fast steps run back to back (ping-pong between two state arrays) and only accumulate their
-    // maybe-out-of-bounds flag; if some chain
-    // raised it during the day (never in practice) the day is redone from its first state by the checked route below.
-    // Step probe (profiles/microbench/step_probe.cu, one warp per scheduler): 228 cycles per step against 265 with
-    // the three votes of a checked step; in the kernel the regular day took 1,520 cycles.
-    bool day_done = false, general = false;
-    if (regular && (m & 1) == 0 && __all_sync(kFull, live && sg.fast_ok)) {
-      double w[4];
-      const unsigned flag = __all_sync(kFull, sg.hold) ? rk4_day2w<true>(L, sg, y, w, tday, h, hh2reg, h6reg, m)
-                                                       : rk4_day2w<false>(L, sg, y, w, tday, h, hh2reg, h6reg, m);
-      if (!__any_sync(kFull, (int)flag < 0)) {
+  // end-of-day outputs of this lane: its S into the history row, and (pass 1) the checkpoint of its four states
+  auto day_out = [&](int d) {
+    out[hist_index<PASS2>(d, Q)] = y[0];
+    if constexpr (!PASS2) {
+      if (ck && d < cdays) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) y[i] = w[i];
-        day_done = true;
+        for (int j = 0; j < 4; ++j) ck[((int64_t)d * 10 + j) * kTile] = y[j];
       }
     }
-    if (day_done) {
-    } else if (regular && (m & 1) == 0 && __all_sync(kFull, live)) {
+  };
+  for (int d = d_first; d < d_end; ++d) {
+    bool live = alive && d > d0 && d < nint;
+    double tday = (double)(t0 + d - 1);
+    // RUNS of usual days — every chain of the warp live, no breakpoint inside, beta >= 0 — cost two votes per run and
+    // ONE per day: the run length is the warp minimum of the days each chain has left before its next breakpoint /
+    // its last day; the fast steps of a day run back to back (ping-pong between state arrays) and only accumulate
+    // their maybe-out-of-bounds flag, voted on at the end of the day; a day some chain raised it in (never in
+    // practice) is redone from its first state by the checked routes below.  Step probe (profiles/microbench/
+    // step_probe.cu, one warp per scheduler): 228 cycles per step against 265 with the three votes of a checked
+    // step; cycle counters in the kernel: the regular day 1,520 -> 1,100 cycles with one vote per day.
+    if (pow2 && (m & 1) == 0) {
+      // (lanes without a chain to integrate — behind the batch, invalid data_offset, not in the retry round — tag along)
+      int nf = !alive ? 0x7fffffff : (live && sg.fast_ok) ? (int)fmin((double)(nint - d), floor(tcut) - tday) : 0;
+      nf = __reduce_min_sync(kFull, nf);
+      if (nf == 0x7fffffff) nf = 0;
+      if (nf > 0) {
+        const bool hold = __all_sync(kFull, sg.hold);
+        int j = 0;
+        for (; j < nf; ++j) {
+          double w[4];
+          const unsigned flag = hold ? rk4_day2w<true>(L, sg, y, w, tday, h, hh2reg, h6reg, m)
+                                     : rk4_day2w<false>(L, sg, y, w, tday, h, hh2reg, h6reg, m);
+          if (__any_sync(kFull, alive && (int)flag < 0)) break;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) y[i] = w[i];
+          if (alive) day_out(d + j);
+          tday += 1.0;
+        }
+        d += j;
+        if (j == nf) { --d; continue; }  // (the loop header steps to the day behind the run)
+        live = alive && d > d0 && d < nint;  // day d of the run raised the flag: the checked route takes it
+      }
+    }
+    const bool regular = pow2 && __all_sync(kFull, !live || tcut >= tday + 1.0);
+    double pa = tday;
+    bool general = false;
+    if (regular && (m & 1) == 0 && __all_sync(kFull, live)) {
       // every chain of the warp integrates this day: sub-steps in pairs, ping-pong between two state arrays
       double z[4];
       for (int s = 0; s < m; s += 2) {
@@ -1297,13 +1320,7 @@ k_ode_age2(const DevModel M, const double *__restrict__ theta, int64_t ld, int64
         }
       }
     }
-    if (live) out[hist_index<PASS2>(d, Q)] = y[0];
-    if constexpr (!PASS2) {
-      if (ck && live && d < cdays) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) ck[((int64_t)d * 10 + j) * kTile] = y[j];
-      }
-    }
+    if (live) day_out(d);
   }
   // either lane may have met an undecidable R test: the chain is flagged if one of them did
   const unsigned nr = (__ballot_sync(kFull, need_r) >> L.shift) & 3u;
