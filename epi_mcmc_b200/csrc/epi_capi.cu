@@ -614,6 +614,7 @@ extern "C" int epi_create(const epi_model_desc *desc, const epi_data *data, int 
     { const char *env = getenv("EPI_PASS1_CHUNK"); h->pass1_chunk = !(env && env[0] == '0'); }
     { const char *env = getenv("EPI_FORCE_R_FALLBACK"); h->force_need_r = (env && env[0] == '1'); }
     { const char *env = getenv("EPI_ODE_LANES"); h->ode_lanes = (env && (env[0] == '1' || env[0] == '2' || env[0] == '4')) ? env[0] - '0' : 0; }
+    { const char *env = getenv("EPI_ODE_MINB"); h->ode_minb = (env && (env[0] == '4' || env[0] == '5')) ? env[0] - '0' : 0; }
     { const char *env = getenv("EPI_SPLIT_WAYS"); h->split_ways = (env && env[0] >= '1' && env[0] <= '8') ? env[0] - '0' : 0; }
     for (auto &ev : h->ev) cudaEventCreate(&ev);
     rc = fill_model(h, *desc, *data);
@@ -752,6 +753,7 @@ static EvalArgs make_args(epi_handle *h, Workspace &w, const DevModel &M, const 
   a.window_only = h->window_only ? 1 : 0;
   a.pass1_chunk = h->pass1_chunk ? 1 : 0;
   a.ode_lanes = h->ode_lanes;
+  a.ode_minb = h->ode_minb;
   a.need_r = w.need_r + first;
   a.force_need_r = h->force_need_r ? 1 : 0;
   a.n_launches = &h->launches;

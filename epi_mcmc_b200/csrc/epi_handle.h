@@ -53,6 +53,7 @@ struct epi_handle {
   bool pass1_chunk = true;  // EPI_PASS1_CHUNK=0: whole-period pass 1 in one round (bit-identical results)
   bool window_only = true;  // EPI_WINDOW_ONLY=0: pass 2 and the score sweep cover the whole period (bit-identical results)
   int ode_lanes = 0;  // EPI_ODE_LANES=1|2|4: force the lanes-per-chain mapping of the age ODE kernels (0: by batch size)
+  int ode_minb = 0;   // EPI_ODE_MINB=4|5: force the register budget (blocks per SM) of the two-lane ODE kernel
   bool restart = true;  // pass 2 resumes from the pass-1 checkpoint (EPI_PASS2_RESTART=0: re-integrate everything)
   // epi_eval_submit/wait: two staging buffers for the raw host theta and the events that order
   // copy stream (stream2) and compute stream

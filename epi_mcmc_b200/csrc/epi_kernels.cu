@@ -863,90 +863,121 @@ __device__ __noinline__ Seg2 select_segment_age2(const DevModel &M, const double
 // 8,192 chains): a warp re-selected ~60 times per launch at ~1,500 cycles each (two dependent global loads through
 // the schedule entry and theta, three divisions) = 14 % of pass 2; from the table it is a scan of bp[] and five LDS.
 // Layout [entry][field][thread]: consecutive lanes -> consecutive banks.
-constexpr int kSegFields = 5;  // bA, sA, bB, sB, flags
-// shared memory of a block: the breakpoints [NBP][thread] (the re-selection scans them: in local memory every probe
-// was an L1 miss, ~800 cycles per call), then the entries [NBP + 1][field][thread]
+constexpr int kSegFields = 6;  // by', sy', bo', so', byo', syo'  (beta and slope of the three curves, divided by N)
+// Shared memory of a block, per PAIR of lanes (np = blockDim.x / 2 pairs; a per-lane copy was 66 KB per block and
+// three blocks per SM): the breakpoints [NBP][np] (the re-selection scans them: in local memory every probe was an
+// L1 miss, ~800 cycles per call), the entries [NBP + 1][field][np], then the flags [NBP + 1][np] as ints.
 template <int FL>
 __host__ __device__ constexpr size_t seg_table_bytes(int threads) {
-  return (size_t)(Traits<FL>::NBP + (Traits<FL>::NBP + 1) * kSegFields) * threads * sizeof(double);
+  return (size_t)(Traits<FL>::NBP + (Traits<FL>::NBP + 1) * kSegFields) * (threads / 2) * sizeof(double) +
+         (size_t)(Traits<FL>::NBP + 1) * (threads / 2) * sizeof(int);
 }
 
+struct SegTab {
+  double *bps;  // + pair index
+  double *tab;
+  int *flags;
+  int np;
+};
+
+template <int FL>
+__device__ __forceinline__ SegTab seg_tab_of(double *smem, int nthreads, int tid) {
+  SegTab T;
+  T.np = nthreads >> 1;
+  T.bps = smem + (tid >> 1);
+  T.tab = smem + Traits<FL>::NBP * T.np + (tid >> 1);
+  T.flags = reinterpret_cast<int *>(smem + (Traits<FL>::NBP + (Traits<FL>::NBP + 1) * kSegFields) * T.np) + (tid >> 1);
+  return T;
+}
+
+// Warp-synchronous (every lane of the warp calls it, uniform trip counts).  The younger group's lane writes the
+// breakpoints, its own curve and the flags, the older group's lane its two curves.
 template <int FL>
 __device__ __forceinline__ void fill_segment_table(const DevModel &M, const double *__restrict__ th, int64_t ld, const double *bp,
-                                                   int nbp, int is_o, double invy, double invo, double *bps, double *tab,
-                                                   int nthreads) {
+                                                   int nbp, int is_o, double invy, double invo, const SegTab &T) {
   constexpr int NBP = Traits<FL>::NBP;
+  const int np = T.np;
   // raw beta triples first, all loads of the schedule issued back to back (they are independent; entry by entry the
-  // prologue paid two dependent global round trips per entry); parked in the fields 0..2 of entry k + 1
+  // prologue paid two dependent global round trips per entry); parked in the beta fields of entry k + 1
 #pragma unroll
   for (int k = 0; k < NBP; ++k) {
     double by = 0.0, bo = 0.0, byo = 0.0;
     if (k < nbp) age_beta<FL>(M, th, ld, k, by, bo, byo);
-    double *t = tab + (size_t)(k + 1) * kSegFields * nthreads;
-    t[0] = by; t[nthreads] = bo; t[2 * nthreads] = byo;
-    bps[k * nthreads] = k < nbp ? bp[k] : INFINITY;
+    if (!is_o) {
+      double *t = T.tab + (size_t)(k + 1) * kSegFields * np;
+      t[0] = by; t[2 * np] = bo; t[4 * np] = byo;
+      T.bps[k * np] = k < nbp ? bp[k] : INFINITY;
+    }
   }
-  // entry k + 1 from the triples k and k + 1, in ascending order (entry k + 1 overwrites triple k only after its use;
-  // triple k + 1 is still raw).  Entry 0 (k = -1: before the first breakpoint) is beta_0 held.
-  double by = tab[(size_t)kSegFields * nthreads], bo = tab[(size_t)(kSegFields + 1) * nthreads],
-         byo = tab[(size_t)(kSegFields + 2) * nthreads];
+  __syncwarp();
+  // entry k + 1 from the triples k and k + 1, in ascending order (entry k + 1 overwrites triple k only after both
+  // lanes hold it in registers; triple k + 1 is still raw).  Entry 0 (k = -1: before the first breakpoint) is beta_0 held.
+  double by = T.tab[(size_t)kSegFields * np], bo = T.tab[(size_t)(kSegFields + 2) * np], byo = T.tab[(size_t)(kSegFields + 4) * np];
+  __syncwarp();
 #pragma unroll 1
-  for (int e = 0; e <= nbp; ++e) {
+  for (int e = 0; e <= NBP; ++e) {
     const int k = e - 1;
-    double ny = 0.0, no = 0.0, nyo = 0.0;
-    if (k + 1 < nbp && k + 1 >= 1) {
-      const double *t = tab + (size_t)(k + 2) * kSegFields * nthreads;
-      ny = t[0]; no = t[nthreads]; nyo = t[2 * nthreads];
+    if (e <= nbp) {
+      double ny = 0.0, no = 0.0, nyo = 0.0;
+      if (k + 1 < nbp && k + 1 >= 1) {
+        const double *t = T.tab + (size_t)(k + 2) * kSegFields * np;
+        ny = t[0]; no = t[2 * np]; nyo = t[4 * np];
+      }
+      double sy = 0.0, so = 0.0, syo = 0.0;
+      bool fast_ok, hold, lin = false;
+      if (k >= 0 && age_linear(M, k)) {
+        const double len = T.bps[(k + 1) * np] - T.bps[k * np];
+        lin = true;
+        sy = (ny - by) / len; so = (no - bo) / len; syo = (nyo - byo) / len;
+        fast_ok = by >= 0 && bo >= 0 && byo >= 0 && ny >= 0 && no >= 0 && nyo >= 0 && len > 0;
+        hold = __dmul_rn(sy, invy) == 0.0 && __dmul_rn(so, invo) == 0.0 && __dmul_rn(syo, invy) == 0.0;
+      } else {
+        fast_ok = by >= 0 && bo >= 0 && byo >= 0;
+        hold = true;
+      }
+      double *t = T.tab + (size_t)e * kSegFields * np;
+      if (!is_o) {
+        t[0] = __dmul_rn(by, invy);
+        t[np] = __dmul_rn(sy, invy);
+        T.flags[e * np] = (fast_ok ? 1 : 0) | (hold ? 2 : 0) | (lin ? 4 : 0);
+      } else {
+        t[2 * np] = __dmul_rn(bo, invo);
+        t[3 * np] = __dmul_rn(so, invo);
+        t[4 * np] = __dmul_rn(byo, invy);
+        t[5 * np] = __dmul_rn(syo, invy);
+      }
+      if (k >= 0) { by = ny; bo = no; byo = nyo; }  // (k = -1 and k = 0 both start from beta_0)
     }
-    double bA = is_o ? bo : by, bB = is_o ? byo : 0.0, sA = 0.0, sB = 0.0;
-    bool fast_ok, hold, lin = false;
-    if (k >= 0 && age_linear(M, k)) {
-      const double len = bps[(k + 1) * nthreads] - bps[k * nthreads];
-      lin = true;
-      sA = is_o ? (no - bo) / len : (ny - by) / len;
-      sB = is_o ? (nyo - byo) / len : 0.0;
-      fast_ok = by >= 0 && bo >= 0 && byo >= 0 && ny >= 0 && no >= 0 && nyo >= 0 && len > 0;
-      hold = __dmul_rn((ny - by) / len, invy) == 0.0 && __dmul_rn((no - bo) / len, invo) == 0.0 &&
-             __dmul_rn((nyo - byo) / len, invy) == 0.0;
-    } else {
-      fast_ok = by >= 0 && bo >= 0 && byo >= 0;
-      hold = true;
-    }
-    const double invA = is_o ? invo : invy;
-    double *t = tab + (size_t)e * kSegFields * nthreads;
-    t[0] = __dmul_rn(bA, invA);
-    t[nthreads] = __dmul_rn(sA, invA);
-    t[2 * nthreads] = __dmul_rn(bB, invy);
-    t[3 * nthreads] = __dmul_rn(sB, invy);
-    t[4 * nthreads] = __hiloint2double(0, (fast_ok ? 1 : 0) | (hold ? 2 : 0) | (lin ? 4 : 0));
-    if (k >= 0) { by = ny; bo = no; byo = nyo; }  // (k = -1 and k = 0 both start from beta_0)
+    __syncwarp();
   }
 }
 
 // the segment active on a piece that starts at pa (the rule of select_segment), read from the table
-__device__ __forceinline__ Seg2 select_segment_tab(const double *tab, const double *bps, int nthreads, int nbp, double pa,
-                                                   double *tcut, int *kcur, bool sorted) {
+__device__ __forceinline__ Seg2 select_segment_tab(const SegTab &T, int is_o, int nbp, double pa, double *tcut, int *kcur,
+                                                   bool sorted) {
+  const int np = T.np;
   int k = -1;
   double tc = INFINITY;
   if (sorted && *kcur >= -1) {
     k = *kcur;
-    while (k + 1 < nbp && bps[(k + 1) * nthreads] <= pa) ++k;
-    if (k + 1 < nbp) tc = bps[(k + 1) * nthreads];
+    while (k + 1 < nbp && T.bps[(k + 1) * np] <= pa) ++k;
+    if (k + 1 < nbp) tc = T.bps[(k + 1) * np];
   } else {
     for (int i = 0; i < nbp; ++i) {
-      const double b = bps[i * nthreads];
+      const double b = T.bps[i * np];
       if (b <= pa) k = i;
       if (b > pa && b < tc) tc = b;
     }
   }
   *kcur = k;
   *tcut = tc;
-  const double *t = tab + (size_t)(k + 1) * kSegFields * nthreads;
+  const double *t = T.tab + (size_t)(k + 1) * kSegFields * np;
   Seg2 sg;
-  sg.bA = t[0]; sg.sA = t[nthreads]; sg.bB = t[2 * nthreads]; sg.sB = t[3 * nthreads];
-  const int fl = __double2loint(t[4 * nthreads]);
+  if (is_o) { sg.bA = t[2 * np]; sg.sA = t[3 * np]; sg.bB = t[4 * np]; sg.sB = t[5 * np]; }
+  else { sg.bA = t[0]; sg.sA = t[np]; sg.bB = 0.0; sg.sB = 0.0; }
+  const int fl = T.flags[(k + 1) * np];
   sg.fast_ok = fl & 1; sg.hold = fl & 2;
-  sg.tk = (fl & 4) ? bps[k * nthreads] : 0.0;
+  sg.tk = (fl & 4) ? T.bps[k * np] : 0.0;
   return sg;
 }
 
@@ -1095,8 +1126,8 @@ __device__ __forceinline__ void rk4_step2w_all(const Lane2 &L, const Seg2 &sg, c
   need_r = need_r || nr;
 }
 
-template <int FL, bool PASS2>
-__global__ void __launch_bounds__(128, 4)
+template <int FL, bool PASS2, int MINB = 4>
+__global__ void __launch_bounds__(128, MINB)
 k_ode_age2(const DevModel M, const double *__restrict__ theta, int64_t ld, int64_t n, const int *__restrict__ offset,
            const int *__restrict__ padv, const double *__restrict__ hist1, double *__restrict__ hist_out,
            double *__restrict__ ckpt, int window_only = 0, int ndays_limit = 0,
@@ -1170,13 +1201,12 @@ k_ode_age2(const DevModel M, const double *__restrict__ theta, int64_t ld, int64
   int kseg = -2;
   const double invy = 1.0 / M.Ny, invo = 1.0 / M.No;
   Seg2 sg;
-  [[maybe_unused]] const double *tab = nullptr, *bps = nullptr;
+  [[maybe_unused]] SegTab T{};
   if constexpr (PASS2) {
     extern __shared__ double seg_smem[];
-    bps = seg_smem + threadIdx.x;
-    tab = bps + Traits<FL>::NBP * blockDim.x;
-    fill_segment_table<FL>(M, th, ld, bp, nbp, g, invy, invo, seg_smem + threadIdx.x, seg_smem + Traits<FL>::NBP * blockDim.x + threadIdx.x, blockDim.x);
-    sg = select_segment_tab(tab, bps, blockDim.x, nbp, (double)(t0 + d0), &tcut, &kseg, bp_sorted);
+    T = seg_tab_of<FL>(seg_smem, blockDim.x, threadIdx.x);
+    fill_segment_table<FL>(M, th, ld, bp, nbp, g, invy, invo, T);
+    sg = select_segment_tab(T, g, nbp, (double)(t0 + d0), &tcut, &kseg, bp_sorted);
   } else {
     sg = select_segment_age2<FL>(M, th, ld, bp, nbp, (double)(t0 + d0), g, &tcut, invy, invo, &kseg, bp_sorted);
   }
@@ -1268,7 +1298,7 @@ k_ode_age2(const DevModel M, const double *__restrict__ theta, int64_t ld, int64
         const bool pending = live && s < m;
         if (!__any_sync(kFull, pending)) break;
         const double b = sb + h;  // (exact for power-of-two m: == tday + (s + 1) * h)
-        if (pending && pl >= tcut) sg = select_segment_tab(tab, bps, blockDim.x, nbp, pl, &tcut, &kseg, bp_sorted);
+        if (pending && pl >= tcut) sg = select_segment_tab(T, g, nbp, pl, &tcut, &kseg, bp_sorted);
         double pb = b;
         bool done = true;
         if (tcut < b) { pb = tcut; done = false; }  // a breakpoint strictly inside (pl, b): cut there
@@ -1288,7 +1318,7 @@ k_ode_age2(const DevModel M, const double *__restrict__ theta, int64_t ld, int64
 #pragma unroll
         for (int i = 0; i < 4; ++i) y[i] = y0[i];
         kseg = -2;  // (segment index unknown again: full scan)
-        sg = select_segment_tab(tab, bps, blockDim.x, nbp, tday, &tcut, &kseg, bp_sorted);
+        sg = select_segment_tab(T, g, nbp, tday, &tcut, &kseg, bp_sorted);
         general = true;
       }
     } else if (regular) {
@@ -1309,7 +1339,7 @@ k_ode_age2(const DevModel M, const double *__restrict__ theta, int64_t ld, int64
         bool step_done = true;
         double pb = b;
         if constexpr (PASS2) {
-          if (pending && pa >= tcut) sg = select_segment_tab(tab, bps, blockDim.x, nbp, pa, &tcut, &kseg, bp_sorted);
+          if (pending && pa >= tcut) sg = select_segment_tab(T, g, nbp, pa, &tcut, &kseg, bp_sorted);
           if (tcut < b) { pb = tcut; step_done = false; }  // a breakpoint strictly inside (pa, b): cut there
         }
         const double hh = pending ? pb - pa : 0.0, hh2 = 0.5 * hh, h6 = div6(hh);
@@ -2853,8 +2883,10 @@ static cudaError_t launch_eval_fl(const EvalArgs &a) {
     if constexpr (Traits<FL>::kAge)
     {
       cudaFuncSetAttribute(k_ode_age2<FL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seg_table_bytes<FL>(128));
+      cudaFuncSetAttribute(k_ode_age2<FL, true, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seg_table_bytes<FL>(128));
       // (without it the driver sizes the carve-out for ONE block per SM and a 16,384-chain shard runs in two waves)
       cudaFuncSetAttribute(k_ode_age2<FL, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      cudaFuncSetAttribute(k_ode_age2<FL, true, 5>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     }
     cudaDeviceGetAttribute(&n_sm_of[di], cudaDevAttrMultiProcessorCount, dev);
     k_fill_log_table<<<1, kLogTabN, 0, a.stream>>>();
@@ -2865,17 +2897,20 @@ static cudaError_t launch_eval_fl(const EvalArgs &a) {
   cudaStream_t s = a.stream;
   if (a.ev) cudaEventRecord(a.ev[0], s);
   const unsigned pair_blocks = (unsigned)((2 * n + 127) / 128);
-  // Lanes per chain of the age ODE passes.  Thread per chain for full batches; two lanes per chain (one per age group,
-  // warp-synchronous k_ode_age2) while a thread-per-chain launch would leave the schedulers short of warps — measured
-  // on the posterior cloud (step ms, one / two / four lanes; profiles/r2_summary.md): 4,096 chains 0.69 / 0.56 / 0.59,
-  // 8,192 0.82 / 0.69 / 0.77, 16,384 1.08 / 1.00 / 1.19, 24,576 1.46 / 1.36 / 1.80, 32,768 1.71 / 1.73 / 2.20.  The
-  // four-lane kernel (k_ode_age4) is kept for EPI_ODE_LANES = 4; EPI_ODE_LANES = 1 | 2 | 4 forces one mapping.
+  // Lanes per chain of the age ODE passes: two (one per age group, warp-synchronous k_ode_age2) at every batch size
+  // since the kernel votes once per day and reads the chain's schedule from a shared-memory table — step ms on the
+  // posterior cloud, one / two lanes (profiles/r2_summary.md): 8,192 chains 0.82 / 0.52, 24,576 1.45 / 1.20,
+  // 32,768 1.71 / 1.59, 65,536 3.09 / 2.94 (1,024 blocks at four per SM: 1.7 waves).  Thread per chain (k_ode) stays
+  // the kernel of the other flavours, of the trajectories with the extended series and of the R-tracking fallback;
+  // the four-lane kernel (k_ode_age4) is kept for EPI_ODE_LANES = 4.  EPI_ODE_LANES = 1 | 2 | 4 forces one mapping.
   int lanes = 1;
   if constexpr (Traits<FL>::kAge && !Traits<FL>::k2x) {  // (age-2x: thread per chain only)
-    lanes = a.ode_lanes ? a.ode_lanes : (n <= (int64_t)n_sm * 176 ? 2 : 1);
+    lanes = a.ode_lanes ? a.ode_lanes : 2;
   }
   constexpr bool kFallback = !Traits<FL>::k2x;  // the R-tracking fallback instance exists where the hot one does not integrate R
   const bool use_pair = lanes == 2, use_quad = lanes == 4;
+  // EPI_ODE_MINB=5: the 96-register instance of the two-lane kernel, five blocks per SM
+  const bool pair_dense = a.ode_minb == 5;  // (measured: 65,536 chains 2.926 ms against 2.937 at four, 8,192 chains 0.550 against 0.523)
   const unsigned quad_blocks = (unsigned)((4 * n + 127) / 128);
   const bool quad_roomy = (int64_t)quad_blocks <= (int64_t)n_sm * 4;  // all blocks resident at 128 registers
   // pass 1 that covers the whole period (simple / age-2i) is integrated for its first kPass1Chunk days first:
@@ -2892,7 +2927,10 @@ static cudaError_t launch_eval_fl(const EvalArgs &a) {
         else k_ode_age4<FL, false, 7><<<quad_blocks, 128, 0, s>>>(M, a.theta, a.ld, n, nullptr, nullptr, nullptr, a.hist1, a.ckpt, 0, limit, retry, a.need_r, a.force_need_r);
       }
     } else if (use_pair) {
-      if constexpr (Traits<FL>::kAge) k_ode_age2<FL, false><<<pair_blocks, 128, 0, s>>>(M, a.theta, a.ld, n, nullptr, nullptr, nullptr, a.hist1, a.ckpt, 0, limit, retry, a.need_r, a.force_need_r);
+      if constexpr (Traits<FL>::kAge) {
+        if (pair_dense) k_ode_age2<FL, false, 5><<<pair_blocks, 128, 0, s>>>(M, a.theta, a.ld, n, nullptr, nullptr, nullptr, a.hist1, a.ckpt, 0, limit, retry, a.need_r, a.force_need_r);
+        else k_ode_age2<FL, false><<<pair_blocks, 128, 0, s>>>(M, a.theta, a.ld, n, nullptr, nullptr, nullptr, a.hist1, a.ckpt, 0, limit, retry, a.need_r, a.force_need_r);
+      }
     } else {
       k_ode<FL, false><<<ode_blocks, 32, 0, s>>>(M, a.theta, a.ld, n, nullptr, nullptr, nullptr, a.hist1, a.ckpt, nullptr, 0, 0, limit, retry, a.need_r, a.force_need_r);
     }
@@ -2916,6 +2954,7 @@ static cudaError_t launch_eval_fl(const EvalArgs &a) {
     if constexpr (Traits<FL>::kAge) {
       if (use_quad && quad_roomy) k_ode_age4<FL, true, 4><<<quad_blocks, 128, 0, s>>>(M, a.theta, a.ld, n, a.offset, a.pad, a.hist1, a.hist2, a.ckpt, window_only, 0, nullptr, a.need_r, a.force_need_r);
       else if (use_quad) k_ode_age4<FL, true, 7><<<quad_blocks, 128, 0, s>>>(M, a.theta, a.ld, n, a.offset, a.pad, a.hist1, a.hist2, a.ckpt, window_only, 0, nullptr, a.need_r, a.force_need_r);
+      else if (pair_dense) k_ode_age2<FL, true, 5><<<pair_blocks, 128, seg_table_bytes<FL>(128), s>>>(M, a.theta, a.ld, n, a.offset, a.pad, a.hist1, a.hist2, a.ckpt, window_only, 0, nullptr, a.need_r, a.force_need_r);
       else k_ode_age2<FL, true><<<pair_blocks, 128, seg_table_bytes<FL>(128), s>>>(M, a.theta, a.ld, n, a.offset, a.pad, a.hist1, a.hist2, a.ckpt, window_only, 0, nullptr, a.need_r, a.force_need_r);
     }
     k_ode<FL, true, false, true><<<ode_blocks, 32, 0, s>>>(M, a.theta, a.ld, n, a.offset, a.pad, a.hist1, a.hist2, a.ckpt, nullptr, 0, window_only, 0, nullptr, a.need_r, 0);

@@ -26,6 +26,7 @@ struct EvalArgs {
   int64_t *n_launches = nullptr;  // incremented by the number of kernels enqueued
   int pass1_chunk = 1;          // whole-period pass 1 in two rounds (EPI_PASS1_CHUNK=0: one round over all days)
   int ode_lanes = 0;            // lanes per chain of the age-flavour ODE kernels: 0 = by batch size, 1 | 2 | 4 forced (EPI_ODE_LANES)
+  int ode_minb = 0;             // two-lane ODE kernel: 0 = by batch size, 4 | 5 = blocks per SM its instance is built for (EPI_ODE_MINB)
   int window_only = 1;          // scoring path: integrate / sweep only up to the data windows (EPI_WINDOW_ONLY=0: whole period)
   cudaStream_t stream;
   cudaEvent_t *ev;  // null or 5 events bracketing the 4 launches
