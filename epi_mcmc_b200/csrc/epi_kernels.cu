@@ -1061,15 +1061,26 @@ __device__ __forceinline__ unsigned rk4_raw2w(const Lane2 &L, const Seg2 &sg, co
   return flag;
 }
 
-// a whole regular day (m even) of fast steps from y into w, ping-pong over z; returns the accumulated flag
+// a whole regular day (m sub-steps, m a power of two) of fast steps from y into w, ping-pong over z; returns the
+// accumulated flag
 template <bool HOLD>
 __device__ __forceinline__ unsigned rk4_day2w(const Lane2 &L, const Seg2 &sg, const double *y, double *w, double tday, double h,
                                              double hh2, double h6, int m) {
   double z[4];
-  double pa = tday, pm = pa + h, pb = pm + h;
-  unsigned flag = rk4_raw2w<HOLD>(L, sg, y, z, pa, pm, h, hh2, h6);
-  flag |= rk4_raw2w<HOLD>(L, sg, z, w, pm, pb, h, hh2, h6);
-  for (int s = 2; s < m; s += 2) {
+  double pa = tday, pm, pb;
+  unsigned flag;
+  int s;
+  if (m & 1) {  // (m == 1)
+    pb = pa + h;
+    flag = rk4_raw2w<HOLD>(L, sg, y, w, pa, pb, h, hh2, h6);
+    s = 1;
+  } else {
+    pm = pa + h; pb = pm + h;
+    flag = rk4_raw2w<HOLD>(L, sg, y, z, pa, pm, h, hh2, h6);
+    flag |= rk4_raw2w<HOLD>(L, sg, z, w, pm, pb, h, hh2, h6);
+    s = 2;
+  }
+  for (; s < m; s += 2) {
     pa = pb; pm = pa + h; pb = pm + h;
     flag |= rk4_raw2w<HOLD>(L, sg, w, z, pa, pm, h, hh2, h6);
     flag |= rk4_raw2w<HOLD>(L, sg, z, w, pm, pb, h, hh2, h6);
@@ -1245,7 +1256,7 @@ k_ode_age2(const DevModel M, const double *__restrict__ theta, int64_t ld, int64
     // practice) is redone from its first state by the checked routes below.  Step probe (profiles/microbench/
     // step_probe.cu, one warp per scheduler): 228 cycles per step against 265 with the three votes of a checked
     // step; cycle counters in the kernel: the regular day 1,520 -> 1,100 cycles with one vote per day.
-    if (pow2 && (m & 1) == 0) {
+    if (pow2) {
       // (lanes without a chain to integrate — behind the batch, invalid data_offset, not in the retry round — tag along)
       int nf = !alive ? 0x7fffffff : (live && sg.fast_ok) ? (int)fmin((double)(nint - d), floor(tcut) - tday) : 0;
       nf = __reduce_min_sync(kFull, nf);
@@ -1280,7 +1291,7 @@ k_ode_age2(const DevModel M, const double *__restrict__ theta, int64_t ld, int64
         rk4_step2w_all(L, sg, z, y, pm, pb, h, hh2reg, h6reg, need_r);
         pa = pb;
       }
-    } else if (PASS2 && pow2 && (m & 1) == 0) {
+    } else if (PASS2 && pow2) {
       // A day some chain of the warp has a breakpoint in (or is not live): the chains walk their pieces together
       // (a lane with a cut sub-step has one piece more and the others wait for it), every piece by the FAST step on
       // the general (linear-segment) instance, flags accumulated, one vote at the end of the day — and the day redone
@@ -2905,7 +2916,9 @@ static cudaError_t launch_eval_fl(const EvalArgs &a) {
   // the four-lane kernel (k_ode_age4) is kept for EPI_ODE_LANES = 4.  EPI_ODE_LANES = 1 | 2 | 4 forces one mapping.
   int lanes = 1;
   if constexpr (Traits<FL>::kAge && !Traits<FL>::k2x) {  // (age-2x: thread per chain only)
-    lanes = a.ode_lanes ? a.ode_lanes : 2;
+    // (age-2i, whose schedule is mostly linear ramps — three more FP64 operations per stage that two lanes pay twice:
+    //  65,536 chains 3.15 ms thread per chain against 3.29; two lanes there only while the SMs are short of warps)
+    lanes = a.ode_lanes ? a.ode_lanes : (!Traits<FL>::k2i || n <= (int64_t)n_sm * 176) ? 2 : 1;
   }
   constexpr bool kFallback = !Traits<FL>::k2x;  // the R-tracking fallback instance exists where the hot one does not integrate R
   const bool use_pair = lanes == 2, use_quad = lanes == 4;
