@@ -661,6 +661,36 @@ def test_ode_lane_mappings_produce_the_same_bits(name, m, monkeypatch):
             assert np.array_equal(a, b, equal_nan=True), lanes
 
 
+@pytest.mark.parametrize("ny,no,beta_scale", [(300.0, 120.0, 1.0), (4000.0, 1500.0, 1.0), (4000.0, 1500.0, 4.0), (8.55e6, 2.95e6, 4.0)])
+def test_two_lane_kernel_under_stress(ny, no, beta_scale, monkeypatch):
+    """The two-lane kernel only accumulates its maybe-out-of-bounds flags and votes once per day (the checked loop
+    redoes a day some chain raised one in).  Small populations (S runs through [1, 4) and below 1: the R-tracking
+    fallback), explosive epidemics (E, I beyond N/2) and the usual case must give the bits, offsets, statuses and
+    fallback counts of the thread-per-chain kernel, which decides every step on its own."""
+    from epi_mcmc_b200.model import Model, load_dataset
+    ds = dict(load_dataset("A300"))
+    ds["y_N"], ds["o_N"], ds["N"] = ny, no, ny + no
+    outs = {}
+    for lanes in (1, 2):
+        monkeypatch.setenv("EPI_ODE_LANES", str(lanes))
+        M = Model(ds, substeps=4)
+        mn, mx, init = M.df_params["min"], M.df_params["max"], M.df_params["init"]
+        rng = np.random.default_rng(3)
+        theta = np.clip(init + (rng.uniform(size=(777, 45)) - 0.5) * 0.3 * (mx - mn), mn, mx)
+        names = list(M.fit_paramnames)
+        for k, nm in enumerate(names):
+            if nm.startswith("beta") or nm.startswith("y.beta") or nm.startswith("o.beta") or nm.startswith("yo.beta"):
+                theta[:, k] = np.minimum(theta[:, k] * beta_scale, mx[k])
+        if ny < 1e5:
+            theta[:, 17] = rng.uniform(0.0, 0.5, size=len(theta))   # t0_morts: a threshold a small epidemic can cross
+        series, off, pad = M.calculateModel_batch(theta[:256])
+        outs[lanes] = M.calclogpost_batch(theta) + (M.fallback_count(), series, off, pad)
+        M.close()
+    assert np.isfinite(outs[1][0]).any()
+    for a, b in zip(outs[1], outs[2]):
+        assert np.array_equal(a, b, equal_nan=True)
+
+
 def test_four_lane_kernel_through_the_r_fallback(monkeypatch):
     """Tiny population: S falls below 1, the four-lane kernel flags the chains and the R-tracking thread-per-chain
     instance recomputes them — same bits as the thread-per-chain hot path followed by the same fallback."""
