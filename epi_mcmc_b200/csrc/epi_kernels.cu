@@ -2050,16 +2050,17 @@ __device__ __noinline__ double score_more_slots(const Slot *__restrict__ day, in
 // `first` is slot 0, already loaded by the caller together with the other series' (ILP).
 __device__ __forceinline__ double score_slots(const DevModel &M, const double2 *__restrict__ ltab, int s, int r, bool in_range,
                                               const Slot &first, double v) {
-  if (!in_range) return 0.0;
+  // Branch-free up to the rare multi-slot days: the two or three series a lane scores per day then sit in ONE basic
+  // block and their logarithm chains overlap (cycle counters: scoring was 60 % of k_score, 25 % of its stall samples
+  // fixed-latency waits).  A day outside the window or an empty slot computes the two logarithms of a harmless mean
+  // and discards them; tlog_pos() of a NaN / inf mean returns garbage that the NA select below replaces.
   const double mu = dev_pmax(M.floor_[s], v);
-  if (!(mu < 1e300)) return NAN;  // NA (or overflow) in the model series: the reference's sum is NA
-  double acc = 0.0;
-  if (first.n != 0.0f) {
-    const double x = (double)first.x;
-    acc = x * tlog_pos(mu, ltab) - fma((double)first.n, first.size, x) * tlog_pos(first.size + mu, ltab);
-  }
-  if (r < M.multi_begin[s]) return acc;
-  return acc + score_more_slots(M.slots[s] + (size_t)r * M.K[s], M.K[s], ltab, mu);
+  const double x = (double)first.x;
+  const double a = x * tlog_pos(mu, ltab) - fma((double)first.n, first.size, x) * tlog_pos(first.size + mu, ltab);
+  double acc = (in_range && first.n != 0.0f) ? a : 0.0;
+  acc = (!in_range || mu < 1e300) ? acc : NAN;  // NA (or overflow) in the model series: the reference's sum is NA
+  if (in_range && r >= M.multi_begin[s]) acc += score_more_slots(M.slots[s] + (size_t)r * M.K[s], M.K[s], ltab, mu);
+  return acc;
 }
 
 // all scored series of one model day: slot 0 of every series is fetched (DaySlots::load, issued
@@ -2157,6 +2158,11 @@ __device__ __forceinline__ void stage_score(const DevModel &M, const ScoreSmem &
     const double s0 = Traits<FL>::k2x ? 0.0 : Traits<FL>::kAge ? (g == 0 ? M.Ny - 1.0 : M.No) : M.N - 1.0;
     for (int j = lane; j < PAD; j += 32) w.S[(g * 4 + (j & 3)) * AS + (j >> 2)] = s0;
   }
+  __syncwarp();
+}
+// ... and wait for the bulk copies stage_score issued (the caller does what needs only theta in between: cycle
+// counters in k_score showed 5.5 k cycles per chain in this wait and 5 k in the prior that followed it)
+__device__ __forceinline__ void stage_score_wait(const ScoreSmem &w) {
   mbar_wait(w.mbar, 0);
   __syncwarp();
 }
@@ -2429,10 +2435,12 @@ k_score(const DevModel M, const PriorTerm *__restrict__ PT, int n_prior, const d
   stage_score<FL>(M, w, theta, ld, chain, true, hist2, Wg, pmeta, P, lane, dmin_, n_, lo, hi);
 
   // prior on the UNTRANSFORMED vector (R/MCMC/fitMCMC-drj.R:51); no prior term reads
-  // theta[4] in the simple flavour, so the staged model-space copy serves
+  // theta[4] in the simple flavour, so the staged model-space copy serves.  (While the S history and the profile
+  // table are still in flight.)
   double lp = 0.0;
   for (int k = lane; k < n_prior; k += 32) lp += prior_term(PT[k], w.theta);
   lp = warp_sum(lp);
+  stage_score_wait(w);
 
   const int pad = padv[chain];
   const int T = pad + P;
@@ -2654,6 +2662,7 @@ k_series(const DevModel M, const double *__restrict__ theta, int64_t ld, int64_t
   // theta is already in MODEL space here (calculateModel is called with transformed params)
   int dmin_[NK], n_[NK], lo[NG], hi[NG];
   stage_score<FL>(M, w, theta, ld, chain, false, hist2, Wg, pmeta, P, lane, dmin_, n_, lo, hi);
+  stage_score_wait(w);
   const int pad = padv[chain];
   const int off_raw = offset[chain];
   constexpr int PAD = Traits<FL>::kPad;
