@@ -1,0 +1,3 @@
+python -m pytest tests -m gpu -x -q 2>&1 | grep -v "^$" | tail -3
+python bench.py --gpus 1 --steps 300 --warmup 5 > gpurun_out/r2_bench_n1_i.json 2> gpurun_out/r2_bench_n1_i.err; echo rc=$?; tail -2 gpurun_out/r2_bench_n1_i.err
+python bench.py --impl reference --gpus 1 --steps 3 --warmup 1 > gpurun_out/r2_bench_ref_i.json 2> gpurun_out/r2_bench_ref_i.err; echo rc=$?; tail -2 gpurun_out/r2_bench_ref_i.err
