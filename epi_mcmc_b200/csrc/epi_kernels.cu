@@ -2931,6 +2931,9 @@ static cudaError_t launch_eval_fl(const EvalArgs &a) {
   }
   constexpr bool kFallback = !Traits<FL>::k2x;  // the R-tracking fallback instance exists where the hot one does not integrate R
   const bool use_pair = lanes == 2, use_quad = lanes == 4;
+  // pass 1 has beta_0 forever (a HOLD segment in every flavour): two lanes there even where pass 2 keeps one
+  // (age-2i at 65,536 chains: pass 1 0.40 -> 0.34 ms; the checkpoint and history layouts of the two kernels are the same)
+  const bool use_pair1 = use_pair || (Traits<FL>::k2i && !a.ode_lanes);
   // EPI_ODE_MINB=5: the 96-register instance of the two-lane kernel, five blocks per SM
   const bool pair_dense = a.ode_minb == 5;  // (measured: 65,536 chains 2.926 ms against 2.937 at four, 8,192 chains 0.550 against 0.523)
   const unsigned quad_blocks = (unsigned)((4 * n + 127) / 128);
@@ -2948,7 +2951,7 @@ static cudaError_t launch_eval_fl(const EvalArgs &a) {
         if (quad_roomy) k_ode_age4<FL, false, 4><<<quad_blocks, 128, 0, s>>>(M, a.theta, a.ld, n, nullptr, nullptr, nullptr, a.hist1, a.ckpt, 0, limit, retry, a.need_r, a.force_need_r);
         else k_ode_age4<FL, false, 7><<<quad_blocks, 128, 0, s>>>(M, a.theta, a.ld, n, nullptr, nullptr, nullptr, a.hist1, a.ckpt, 0, limit, retry, a.need_r, a.force_need_r);
       }
-    } else if (use_pair) {
+    } else if (use_pair1) {
       if constexpr (Traits<FL>::kAge) {
         if (pair_dense) k_ode_age2<FL, false, 5><<<pair_blocks, 128, 0, s>>>(M, a.theta, a.ld, n, nullptr, nullptr, nullptr, a.hist1, a.ckpt, 0, limit, retry, a.need_r, a.force_need_r);
         else k_ode_age2<FL, false><<<pair_blocks, 128, 0, s>>>(M, a.theta, a.ld, n, nullptr, nullptr, nullptr, a.hist1, a.ckpt, 0, limit, retry, a.need_r, a.force_need_r);
