@@ -2925,15 +2925,14 @@ static cudaError_t launch_eval_fl(const EvalArgs &a) {
   // the four-lane kernel (k_ode_age4) is kept for EPI_ODE_LANES = 4.  EPI_ODE_LANES = 1 | 2 | 4 forces one mapping.
   int lanes = 1;
   if constexpr (Traits<FL>::kAge && !Traits<FL>::k2x) {  // (age-2x: thread per chain only)
-    // (age-2i, whose schedule is mostly linear ramps — three more FP64 operations per stage that two lanes pay twice:
-    //  65,536 chains 3.15 ms thread per chain against 3.29; two lanes there only while the SMs are short of warps)
-    lanes = a.ode_lanes ? a.ode_lanes : (!Traits<FL>::k2i || n <= (int64_t)n_sm * 176) ? 2 : 1;
+    // (age-2i, whose schedule is mostly linear ramps — three more FP64 operations per stage that two lanes pay twice —
+    //  at 65,536 chains: on the posterior cloud of a sampler 3.14 ms thread per chain against 2.93 with two lanes; on
+    //  the narrow cloud, whose warps run in lock-step, 3.15 against 3.29.  The sampler is the use case.)
+    lanes = a.ode_lanes ? a.ode_lanes : 2;
   }
   constexpr bool kFallback = !Traits<FL>::k2x;  // the R-tracking fallback instance exists where the hot one does not integrate R
   const bool use_pair = lanes == 2, use_quad = lanes == 4;
-  // pass 1 has beta_0 forever (a HOLD segment in every flavour): two lanes there even where pass 2 keeps one
-  // (age-2i at 65,536 chains: pass 1 0.40 -> 0.34 ms; the checkpoint and history layouts of the two kernels are the same)
-  const bool use_pair1 = use_pair || (Traits<FL>::k2i && !a.ode_lanes);
+  const bool use_pair1 = use_pair;
   // EPI_ODE_MINB=5: the 96-register instance of the two-lane kernel, five blocks per SM
   const bool pair_dense = a.ode_minb == 5;  // (measured: 65,536 chains 2.926 ms against 2.937 at four, 8,192 chains 0.550 against 0.523)
   const unsigned quad_blocks = (unsigned)((4 * n + 127) / 128);
