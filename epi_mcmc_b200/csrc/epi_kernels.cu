@@ -561,8 +561,12 @@ __device__ __noinline__ void write_ext(const DevModel &M, const double *__restri
 // schedule, in the reference's own operation order (explicit roundings: bit-identical to the oracle's restatement
 // for the same state).  When the bounds guard returns early the reference leaves them stale: NaN here.
 template <int FL>
+// kknown >= -1: the caller knows the schedule index of the literal rule (at the end of a day it is the segment of the
+// day's last piece: pieces are cut at the breakpoints, so no breakpoint lies in (start of the piece, t), and one AT t
+// belongs to neither rule) — the scan below reads bp[] from local memory, thirteen dependent L1 misses per day and
+// chain (age-2x pass 2 at 8,192 chains: 7,800 cycles per day against 1,100-1,500 for age-2q).
 __device__ __noinline__ void incidence_out(const DevModel &M, const double *__restrict__ th, int64_t ld, const double *bp,
-                                           int nbp, double t, const double *y, double &yi, double &oi) {
+                                           int nbp, double t, const double *y, double &yi, double &oi, int kknown = -2) {
   const double Sy = y[0], E1y = y[1], E2y = y[2], Iy = y[3], Ry = y[4];
   const double So = y[5], E1o = y[6], E2o = y[7], Io = y[8], Ro = y[9];
   const double Ny = M.Ny, No = M.No;
@@ -570,9 +574,12 @@ __device__ __noinline__ void incidence_out(const DevModel &M, const double *__re
   if (Sy < 0 || E1y < 0 || E2y < 0 || Iy < 0 || Ry < 0 || Sy > Ny || E1y > Ny || E2y > Ny || Iy > Ny || Ry > Ny ||
       So < 0 || E1o < 0 || E2o < 0 || Io < 0 || Ro < 0 || So > No || E1o > No || E2o > No || Io > No || Ro > No)
     return;
-  int k = -1;
-  for (int i = nbp - 1; i >= 0; --i)
-    if (t > bp[i]) { k = i; break; }
+  int k = kknown;
+  if (kknown < -1) {
+    k = -1;
+    for (int i = nbp - 1; i >= 0; --i)
+      if (t > bp[i]) { k = i; break; }
+  }
   double by, bo, byo;
   age_beta<FL>(M, th, ld, k < 0 ? 0 : k, by, bo, byo);
   if (k >= 0 && age_linear(M, k)) {
@@ -761,7 +768,7 @@ k_ode(const DevModel M, const double *__restrict__ theta, int64_t ld, int64_t n,
     }
     if constexpr (Traits<FL>::k2x) {
       double yi, oi;
-      incidence_out<FL>(M, th, ld, bp, nbp, (double)(t0 + d), y, yi, oi);
+      incidence_out<FL>(M, th, ld, bp, nbp, (double)(t0 + d), y, yi, oi, bp_sorted ? kseg : -2);
       out[hist_index<PASS2>(d, Q)] = yi; out[pitch + hist_index<PASS2>(d, Q)] = oi;
       if constexpr (FULL) { eo[-8 * (int64_t)M.P + d] = y[0]; eo[-7 * (int64_t)M.P + d] = y[5]; }
     } else {
@@ -983,54 +990,74 @@ __device__ __forceinline__ Seg2 select_segment_tab(const SegTab &T, int is_o, in
 
 struct Lane2 {
   double a1, gamma, Ngrp;
+  double eta, cap;  // age-2x: waning rate; 0.8 * N_y (the younger group's effective-susceptible cap, model-ager.cpp:176-178)
+  bool is_y;
   int shift;     // first lane of this chain's pair == the lane that holds I_y
   unsigned nb;   // hi(N) - 1
 };
 
-template <bool GUARDED, bool HOLD>
+// NS = 4: (S, E1, E2, I) per lane, R not integrated (age-2q / 2i).  NS = 5: age-2x (model-ager.cpp:176-200) — R is a
+// state (it flows back into S at rate eta), the younger group is infected through its effective susceptibles, and
+// "S > N" gets its own exact test (S is no longer monotone); the operations are those of rhs<> for that flavour.
+template <bool GUARDED, bool HOLD, int NS = 4>
 __device__ __forceinline__ void rhs2w(const Lane2 &L, const Seg2 &sg, double t, const double *y, double *dy, unsigned &flag) {
-  const double S = y[0], E1 = y[1], E2 = y[2], I = y[3];
+  constexpr bool X2 = NS == 5;
+  const double S = y[0], E1 = y[1], E2 = y[2], I = y[3], R = X2 ? y[NS - 1] : 0.0;
   const double iy = __shfl_sync(kFull, I, L.shift);  // I of the younger group
   bool bad = false;
   if constexpr (GUARDED) {
-    // bounds guard over the chain's states, model-agen.cpp:109-124 (R is not integrated here: see below_one)
-    const int bad_own = (S < 0 || E1 < 0 || E2 < 0 || I < 0 || S > L.Ngrp || E1 > L.Ngrp || E2 > L.Ngrp || I > L.Ngrp);
+    // bounds guard over the chain's states, model-agen.cpp:109-124 (NS = 4: R is not integrated here, see below_one)
+    const int bad_own = (S < 0 || E1 < 0 || E2 < 0 || I < 0 || R < 0 || S > L.Ngrp || E1 > L.Ngrp || E2 > L.Ngrp ||
+                         I > L.Ngrp || R > L.Ngrp);
     bad = ((__ballot_sync(kFull, bad_own) >> L.shift) & 3u) != 0u;
-    flag |= (!bad && S < 1.0) ? 1u : 0u;  // the R test is undecidable here
+    if constexpr (!X2) flag |= (!bad && S < 1.0) ? 1u : 0u;  // the R test is undecidable here
+  } else if constexpr (X2) {
+    flag |= oob_group5(S, E1, E2, I, R, L.nb) | ((S > L.Ngrp) ? 0x80000000u : 0u);
   } else {
     flag |= oob_group4_nor(S, E1, E2, I, L.nb);  // bit 31 set <=> maybe out of bounds
   }
   const double dt = HOLD ? 0.0 : t - sg.tk;
   const double bA = HOLD ? sg.bA : fma(dt, sg.sA, sg.bA), bB = HOLD ? sg.bB : fma(dt, sg.sB, sg.bB);
-  const double inf = __dmul_rn(fma(bA, I, __dmul_rn(bB, iy)), S);  // y: (betay/Ny*Iy)*Sy; o: (betao/No*Io + betayo/Ny*Iy)*So
-  dy[0] = -inf;
+  double Sx = S;
+  if constexpr (X2) Sx = L.is_y ? fmax(0.0, __dsub_rn(L.cap, __dsub_rn(L.Ngrp, S))) : S;
+  const double inf = __dmul_rn(fma(bA, I, __dmul_rn(bB, iy)), Sx);  // y: (betay/Ny*Iy)*Sy; o: (betao/No*Io + betayo/Ny*Iy)*So
+  if constexpr (X2) {
+    const double rev = __dmul_rn(L.eta, R);
+    dy[0] = __dsub_rn(rev, inf);
+    dy[4] = fma(L.gamma, I, -rev);
+  } else {
+    dy[0] = -inf;
+  }
   dy[1] = fma(-L.a1, E1, inf);
   dy[2] = fma(L.a1, E1, -E2);
   dy[3] = fma(-L.gamma, I, E2);
   if constexpr (GUARDED) {
-    if (bad) { dy[0] = 0.0; dy[1] = 0.0; dy[2] = 0.0; dy[3] = 0.0; }  // the guard freezes the whole state
+    if (bad) {  // the guard freezes the whole state
+#pragma unroll
+      for (int i = 0; i < NS; ++i) dy[i] = 0.0;
+    }
   }
 }
 
 // returns (fast instance) whether no lane of the chain raised the maybe-out-of-bounds bit
-template <bool GUARDED, bool HOLD>
+template <bool GUARDED, bool HOLD, int NS = 4>
 __device__ __forceinline__ bool rk4_try2w(const Lane2 &L, const Seg2 &sg, const double *y, double *yn, double pa, double pb,
                                           double hh, double hh2, double h6, bool &need_r) {
   const double tm = pa + hh2;
-  double k[4], acc[4], yt[4];
+  double k[NS], acc[NS], yt[NS];
   unsigned flag = 0;
-  rhs2w<GUARDED, HOLD>(L, sg, pa, y, k, flag);
+  rhs2w<GUARDED, HOLD, NS>(L, sg, pa, y, k, flag);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) { acc[i] = k[i]; yt[i] = fma(hh2, k[i], y[i]); }
-  rhs2w<GUARDED, HOLD>(L, sg, tm, yt, k, flag);
+  for (int i = 0; i < NS; ++i) { acc[i] = k[i]; yt[i] = fma(hh2, k[i], y[i]); }
+  rhs2w<GUARDED, HOLD, NS>(L, sg, tm, yt, k, flag);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) { acc[i] = fma(2.0, k[i], acc[i]); yt[i] = fma(hh2, k[i], y[i]); }
-  rhs2w<GUARDED, HOLD>(L, sg, tm, yt, k, flag);
+  for (int i = 0; i < NS; ++i) { acc[i] = fma(2.0, k[i], acc[i]); yt[i] = fma(hh2, k[i], y[i]); }
+  rhs2w<GUARDED, HOLD, NS>(L, sg, tm, yt, k, flag);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) { acc[i] = fma(2.0, k[i], acc[i]); yt[i] = fma(hh, k[i], y[i]); }
-  rhs2w<GUARDED, HOLD>(L, sg, pb, yt, k, flag);
+  for (int i = 0; i < NS; ++i) { acc[i] = fma(2.0, k[i], acc[i]); yt[i] = fma(hh, k[i], y[i]); }
+  rhs2w<GUARDED, HOLD, NS>(L, sg, pb, yt, k, flag);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) yn[i] = fma(h6, __dadd_rn(acc[i], k[i]), y[i]);
+  for (int i = 0; i < NS; ++i) yn[i] = fma(h6, __dadd_rn(acc[i], k[i]), y[i]);
   if constexpr (GUARDED) {
     need_r = (flag & 1u) != 0u;
     return true;
@@ -1040,101 +1067,136 @@ __device__ __forceinline__ bool rk4_try2w(const Lane2 &L, const Seg2 &sg, const 
 
 // the fast instance of a step without its verdict: returns the accumulated maybe-out-of-bounds flag (bit 31) for the
 // caller to vote on — k_ode_age2 votes once per DAY on its regular days
-template <bool HOLD>
+template <bool HOLD, int NS = 4>
 __device__ __forceinline__ unsigned rk4_raw2w(const Lane2 &L, const Seg2 &sg, const double *y, double *yn, double pa, double pb,
                                              double hh, double hh2, double h6) {
   const double tm = pa + hh2;
-  double k[4], acc[4], yt[4];
+  double k[NS], acc[NS], yt[NS];
   unsigned flag = 0;
-  rhs2w<false, HOLD>(L, sg, pa, y, k, flag);
+  rhs2w<false, HOLD, NS>(L, sg, pa, y, k, flag);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) { acc[i] = k[i]; yt[i] = fma(hh2, k[i], y[i]); }
-  rhs2w<false, HOLD>(L, sg, tm, yt, k, flag);
+  for (int i = 0; i < NS; ++i) { acc[i] = k[i]; yt[i] = fma(hh2, k[i], y[i]); }
+  rhs2w<false, HOLD, NS>(L, sg, tm, yt, k, flag);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) { acc[i] = fma(2.0, k[i], acc[i]); yt[i] = fma(hh2, k[i], y[i]); }
-  rhs2w<false, HOLD>(L, sg, tm, yt, k, flag);
+  for (int i = 0; i < NS; ++i) { acc[i] = fma(2.0, k[i], acc[i]); yt[i] = fma(hh2, k[i], y[i]); }
+  rhs2w<false, HOLD, NS>(L, sg, tm, yt, k, flag);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) { acc[i] = fma(2.0, k[i], acc[i]); yt[i] = fma(hh, k[i], y[i]); }
-  rhs2w<false, HOLD>(L, sg, pb, yt, k, flag);
+  for (int i = 0; i < NS; ++i) { acc[i] = fma(2.0, k[i], acc[i]); yt[i] = fma(hh, k[i], y[i]); }
+  rhs2w<false, HOLD, NS>(L, sg, pb, yt, k, flag);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) yn[i] = fma(h6, __dadd_rn(acc[i], k[i]), y[i]);
+  for (int i = 0; i < NS; ++i) yn[i] = fma(h6, __dadd_rn(acc[i], k[i]), y[i]);
   return flag;
 }
 
 // a whole regular day (m sub-steps, m a power of two) of fast steps from y into w, ping-pong over z; returns the
 // accumulated flag
-template <bool HOLD>
+template <bool HOLD, int NS = 4>
 __device__ __forceinline__ unsigned rk4_day2w(const Lane2 &L, const Seg2 &sg, const double *y, double *w, double tday, double h,
                                              double hh2, double h6, int m) {
-  double z[4];
+  double z[NS];
   double pa = tday, pm, pb;
   unsigned flag;
   int s;
   if (m & 1) {  // (m == 1)
     pb = pa + h;
-    flag = rk4_raw2w<HOLD>(L, sg, y, w, pa, pb, h, hh2, h6);
+    flag = rk4_raw2w<HOLD, NS>(L, sg, y, w, pa, pb, h, hh2, h6);
     s = 1;
   } else {
     pm = pa + h; pb = pm + h;
-    flag = rk4_raw2w<HOLD>(L, sg, y, z, pa, pm, h, hh2, h6);
-    flag |= rk4_raw2w<HOLD>(L, sg, z, w, pm, pb, h, hh2, h6);
+    flag = rk4_raw2w<HOLD, NS>(L, sg, y, z, pa, pm, h, hh2, h6);
+    flag |= rk4_raw2w<HOLD, NS>(L, sg, z, w, pm, pb, h, hh2, h6);
     s = 2;
   }
   for (; s < m; s += 2) {
     pa = pb; pm = pa + h; pb = pm + h;
-    flag |= rk4_raw2w<HOLD>(L, sg, w, z, pa, pm, h, hh2, h6);
-    flag |= rk4_raw2w<HOLD>(L, sg, z, w, pm, pb, h, hh2, h6);
+    flag |= rk4_raw2w<HOLD, NS>(L, sg, w, z, pa, pm, h, hh2, h6);
+    flag |= rk4_raw2w<HOLD, NS>(L, sg, z, w, pm, pb, h, hh2, h6);
   }
   return flag;
 }
 
 // one RK4 piece for all sixteen chains of the warp; a chain takes the result only when `commit`
+template <int NS = 4>
 __device__ __forceinline__ void rk4_step2w(const Lane2 &L, const Seg2 &sg, double *y, bool commit, double pa, double pb,
                                            double hh, double hh2, double h6, bool &need_r) {
-  double yn[4];
+  double yn[NS];
   bool nr = false;
   const bool hold = __all_sync(kFull, sg.hold);
-  bool ok = hold ? rk4_try2w<false, true>(L, sg, y, yn, pa, pb, hh, hh2, h6, nr)
-                 : rk4_try2w<false, false>(L, sg, y, yn, pa, pb, hh, hh2, h6, nr);
+  bool ok = hold ? rk4_try2w<false, true, NS>(L, sg, y, yn, pa, pb, hh, hh2, h6, nr)
+                 : rk4_try2w<false, false, NS>(L, sg, y, yn, pa, pb, hh, hh2, h6, nr);
   ok = ok && sg.fast_ok;
   if (__any_sync(kFull, commit && !ok)) {
     // rare: the reference's guard evaluated exactly in FP64, by the whole warp; taken by the chains that need it
-    double gy[4];
+    double gy[NS];
     bool gnr = false;
-    rk4_try2w<true, false>(L, sg, y, gy, pa, pb, hh, hh2, h6, gnr);
+    rk4_try2w<true, false, NS>(L, sg, y, gy, pa, pb, hh, hh2, h6, gnr);
     if (!ok) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) yn[i] = gy[i];
+      for (int i = 0; i < NS; ++i) yn[i] = gy[i];
       nr = gnr;
     }
   }
   if (commit) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) y[i] = yn[i];
+    for (int i = 0; i < NS; ++i) y[i] = yn[i];
     need_r = need_r || nr;
   }
 }
 
 // the same piece when EVERY chain of the warp takes the result (the usual case on a regular day): from yin into a
 // distinct array yout, no per-lane selects and no copy back (the caller ping-pongs between two state arrays)
+template <int NS = 4>
 __device__ __forceinline__ void rk4_step2w_all(const Lane2 &L, const Seg2 &sg, const double *yin, double *yout, double pa,
                                                double pb, double hh, double hh2, double h6, bool &need_r) {
   bool nr = false;
   const bool hold = __all_sync(kFull, sg.hold);
-  bool ok = hold ? rk4_try2w<false, true>(L, sg, yin, yout, pa, pb, hh, hh2, h6, nr)
-                 : rk4_try2w<false, false>(L, sg, yin, yout, pa, pb, hh, hh2, h6, nr);
+  bool ok = hold ? rk4_try2w<false, true, NS>(L, sg, yin, yout, pa, pb, hh, hh2, h6, nr)
+                 : rk4_try2w<false, false, NS>(L, sg, yin, yout, pa, pb, hh, hh2, h6, nr);
   ok = ok && sg.fast_ok;
   if (__any_sync(kFull, !ok)) {
-    double gy[4];
+    double gy[NS];
     bool gnr = false;
-    rk4_try2w<true, false>(L, sg, yin, gy, pa, pb, hh, hh2, h6, gnr);
+    rk4_try2w<true, false, NS>(L, sg, yin, gy, pa, pb, hh, hh2, h6, gnr);
     if (!ok) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) yout[i] = gy[i];
+      for (int i = 0; i < NS; ++i) yout[i] = gy[i];
       nr = gnr;
     }
   }
   need_r = need_r || nr;
+}
+
+// age-2x: what the history rows hold at simulation day t — this lane's infection incidence (derivs()' output variable
+// y.i resp. o.i, model-ager.cpp:206-207) as deSolve evaluates it for the output matrix: the LITERAL `t > tk` schedule,
+// the reference's own operation order (the roundings of incidence_out(), bit for bit); NaN when the bounds guard over
+// the chain's ten states returns early.  Warp-synchronous (ballot + shuffle): every lane calls it.
+template <int FL>
+__device__ __noinline__ double incidence_out2(const DevModel &M, const double *__restrict__ th, int64_t ld, const double *bps,
+                                              int bstride, int nbp, double t, const Lane2 &L, const double *y, int is_o) {
+  const double S = y[0], E1 = y[1], E2 = y[2], I = y[3], R = y[4];
+  const int bad_own = (S < 0 || E1 < 0 || E2 < 0 || I < 0 || R < 0 || S > L.Ngrp || E1 > L.Ngrp || E2 > L.Ngrp ||
+                       I > L.Ngrp || R > L.Ngrp);
+  const bool bad = ((__ballot_sync(kFull, bad_own) >> L.shift) & 3u) != 0u;
+  const double Iy = __shfl_sync(kFull, I, L.shift);
+  int k = -1;
+  for (int i = nbp - 1; i >= 0; --i)
+    if (t > bps[i * bstride]) { k = i; break; }
+  double by, bo, byo;
+  age_beta<FL>(M, th, ld, k < 0 ? 0 : k, by, bo, byo);
+  if (k >= 0 && age_linear(M, k)) {
+    double ny, no, nyo;
+    age_beta<FL>(M, th, ld, k + 1, ny, no, nyo);
+    const double f = __ddiv_rn(__dsub_rn(t, bps[k * bstride]), __dsub_rn(bps[(k + 1) * bstride], bps[k * bstride]));
+    by = __dadd_rn(by, __dmul_rn(f, __dsub_rn(ny, by)));
+    bo = __dadd_rn(bo, __dmul_rn(f, __dsub_rn(no, bo)));
+    byo = __dadd_rn(byo, __dmul_rn(f, __dsub_rn(nyo, byo)));
+  }
+  if (bad) return NAN;
+  if (!is_o) {
+    const double Syeff = fmax(0.0, __dsub_rn(__dmul_rn(M.Ny, 0.8), __dsub_rn(M.Ny, S)));
+    return __dmul_rn(__ddiv_rn(__dmul_rn(by, I), M.Ny), Syeff);
+  }
+  return __dmul_rn(__dadd_rn(__ddiv_rn(__dmul_rn(bo, I), M.No), __ddiv_rn(__dmul_rn(byo, Iy), M.Ny)), S);
 }
 
 template <int FL, bool PASS2, int MINB = 4>
@@ -1144,6 +1206,8 @@ k_ode_age2(const DevModel M, const double *__restrict__ theta, int64_t ld, int64
            double *__restrict__ ckpt, int window_only = 0, int ndays_limit = 0,
            const int *__restrict__ retry_status = nullptr, int *__restrict__ need_r_flag = nullptr,
            int force_need_r = 0) {
+  constexpr bool X2 = Traits<FL>::k2x;
+  constexpr int NS = X2 ? 5 : 4;  // states per lane: (S, E1, E2, I) and, age-2x, R
   bool need_r = false;
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool exists = (tid >> 1) < n;
@@ -1155,6 +1219,9 @@ k_ode_age2(const DevModel M, const double *__restrict__ theta, int64_t ld, int64
   L.a1 = M.a1; L.gamma = M.gamma;
   L.Ngrp = g ? M.No : M.Ny;
   L.nb = (unsigned)__double2hiint(L.Ngrp) - 1u;
+  L.is_y = g == 0;
+  L.eta = X2 ? M.eta : 0.0;
+  L.cap = __dmul_rn(M.Ny, 0.8);
   const double *th = theta + i;
   const int ndays = PASS2 ? M.P : M.P1;
   int nint = ndays;  // days integrated here
@@ -1166,7 +1233,10 @@ k_ode_age2(const DevModel M, const double *__restrict__ theta, int64_t ld, int64
   const int pitch = PASS2 ? hist_pitch2(ndays) : hist_pitch(ndays), Q = pitch >> 2;
   double *out = hist_out + (i * 2 + g) * (int64_t)pitch;
   // model-age-groups2q.R:157-158
-  double y[4] = {g ? M.No : M.Ny - 1.0, g ? 0.0 : 1.0, 0.0, 0.0};
+  double y[NS];
+  y[0] = g ? M.No : M.Ny - 1.0; y[1] = g ? 0.0 : 1.0;
+#pragma unroll
+  for (int j = 2; j < NS; ++j) y[j] = 0.0;
 
   double bp[kMaxBp];
   int nbp = 0;
@@ -1203,7 +1273,7 @@ k_ode_age2(const DevModel M, const double *__restrict__ theta, int64_t ld, int64
         const double *in = hist1 + (i * 2 + g) * (int64_t)hist_pitch(M.P1);
         for (int d = 0; d <= d0; ++d) out[hist_index<PASS2>(d, Q)] = in[d];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) y[j] = ck[((int64_t)d0 * 10 + j) * kTile];
+        for (int j = 0; j < NS; ++j) y[j] = ck[((int64_t)d0 * 10 + j) * kTile];
       }
     }
   }
@@ -1224,11 +1294,22 @@ k_ode_age2(const DevModel M, const double *__restrict__ theta, int64_t ld, int64
 
   const int m = M.m;
   const double h = 1.0 / (double)m;
-  if (alive && d0 == 0) out[0] = y[0];
+  // what a history row holds: S of this lane's group — age-2x: its incidence (incidence_out2, every lane calls it)
+  [[maybe_unused]] const double *bps_inc = bp;
+  [[maybe_unused]] int bstride_inc = 1;
+  if constexpr (PASS2) { bps_inc = T.bps; bstride_inc = T.np; }
+  auto row_value = [&](int d) -> double {
+    if constexpr (X2) return incidence_out2<FL>(M, th, ld, bps_inc, bstride_inc, nbp, (double)(t0 + d), L, y, g);
+    return y[0];
+  };
+  {
+    const double v0 = row_value(0);
+    if (alive && d0 == 0) out[0] = v0;
+  }
   if constexpr (!PASS2) {
     if (ck && alive) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) ck[j * kTile] = y[j];
+      for (int j = 0; j < NS; ++j) ck[j * kTile] = y[j];
     }
   }
   // day range of the warp: every chain walks it, live only inside its own (d0, nint)
@@ -1237,12 +1318,14 @@ k_ode_age2(const DevModel M, const double *__restrict__ theta, int64_t ld, int64
   const bool pow2 = (m & (m - 1)) == 0;
   const double hh2reg = 0.5 * h, h6reg = h / 6.0;
   // end-of-day outputs of this lane: its S into the history row, and (pass 1) the checkpoint of its four states
-  auto day_out = [&](int d) {
-    out[hist_index<PASS2>(d, Q)] = y[0];
+  auto day_out = [&](int d, bool store) {
+    const double v = row_value(d);
+    if (!store) return;
+    out[hist_index<PASS2>(d, Q)] = v;
     if constexpr (!PASS2) {
       if (ck && d < cdays) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) ck[((int64_t)d * 10 + j) * kTile] = y[j];
+        for (int j = 0; j < NS; ++j) ck[((int64_t)d * 10 + j) * kTile] = y[j];
       }
     }
   };
@@ -1265,13 +1348,13 @@ k_ode_age2(const DevModel M, const double *__restrict__ theta, int64_t ld, int64
         const bool hold = __all_sync(kFull, sg.hold);
         int j = 0;
         for (; j < nf; ++j) {
-          double w[4];
-          const unsigned flag = hold ? rk4_day2w<true>(L, sg, y, w, tday, h, hh2reg, h6reg, m)
-                                     : rk4_day2w<false>(L, sg, y, w, tday, h, hh2reg, h6reg, m);
+          double w[NS];
+          const unsigned flag = hold ? rk4_day2w<true, NS>(L, sg, y, w, tday, h, hh2reg, h6reg, m)
+                                     : rk4_day2w<false, NS>(L, sg, y, w, tday, h, hh2reg, h6reg, m);
           if (__any_sync(kFull, alive && (int)flag < 0)) break;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) y[i] = w[i];
-          if (alive) day_out(d + j);
+          for (int i = 0; i < NS; ++i) y[i] = w[i];
+          day_out(d + j, alive);
           tday += 1.0;
         }
         d += j;
@@ -1284,11 +1367,11 @@ k_ode_age2(const DevModel M, const double *__restrict__ theta, int64_t ld, int64
     bool general = false;
     if (regular && (m & 1) == 0 && __all_sync(kFull, live)) {
       // every chain of the warp integrates this day: sub-steps in pairs, ping-pong between two state arrays
-      double z[4];
+      double z[NS];
       for (int s = 0; s < m; s += 2) {
         const double pm = pa + h, pb = pm + h;
-        rk4_step2w_all(L, sg, y, z, pa, pm, h, hh2reg, h6reg, need_r);
-        rk4_step2w_all(L, sg, z, y, pm, pb, h, hh2reg, h6reg, need_r);
+        rk4_step2w_all<NS>(L, sg, y, z, pa, pm, h, hh2reg, h6reg, need_r);
+        rk4_step2w_all<NS>(L, sg, z, y, pm, pb, h, hh2reg, h6reg, need_r);
         pa = pb;
       }
     } else if (PASS2 && pow2) {
@@ -1300,7 +1383,9 @@ k_ode_age2(const DevModel M, const double *__restrict__ theta, int64_t ld, int64
       // chains, profiles/r2_summary.md): the checked loop took such a day through five pieces of ~930 cycles (three
       // votes, a division and a re-selection through global memory each) against ~390 for a regular sub-step; 17 %
       // of the days were 40 % of pass 2.
-      double y0[4] = {y[0], y[1], y[2], y[3]};
+      double y0[NS];
+#pragma unroll
+      for (int i = 0; i < NS; ++i) y0[i] = y[i];
       unsigned flag = 0;
       bool fok = true;
       int s = 0;
@@ -1315,11 +1400,11 @@ k_ode_age2(const DevModel M, const double *__restrict__ theta, int64_t ld, int64
         if (tcut < b) { pb = tcut; done = false; }  // a breakpoint strictly inside (pl, b): cut there
         const double hh = pending ? pb - pl : 0.0, hh2 = 0.5 * hh, h6 = div6(hh);
         fok = fok && (!pending || sg.fast_ok);
-        double yn[4];
-        const unsigned f = rk4_raw2w<false>(L, sg, y, yn, pl, pending ? pb : pl, hh, hh2, h6);
+        double yn[NS];
+        const unsigned f = rk4_raw2w<false, NS>(L, sg, y, yn, pl, pending ? pb : pl, hh, hh2, h6);
         if (pending) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) y[i] = yn[i];
+          for (int i = 0; i < NS; ++i) y[i] = yn[i];
           flag |= f;
           pl = pb;
           if (done) { ++s; sb = b; }
@@ -1327,7 +1412,7 @@ k_ode_age2(const DevModel M, const double *__restrict__ theta, int64_t ld, int64
       }
       if (__any_sync(kFull, (int)flag < 0 || !fok)) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) y[i] = y0[i];
+        for (int i = 0; i < NS; ++i) y[i] = y0[i];
         kseg = -2;  // (segment index unknown again: full scan)
         sg = select_segment_tab(T, g, nbp, tday, &tcut, &kseg, bp_sorted);
         general = true;
@@ -1335,7 +1420,7 @@ k_ode_age2(const DevModel M, const double *__restrict__ theta, int64_t ld, int64
     } else if (regular) {
       for (int s = 0; s < m; ++s) {
         const double pb = pa + h;
-        rk4_step2w(L, sg, y, live, pa, pb, h, hh2reg, h6reg, need_r);
+        rk4_step2w<NS>(L, sg, y, live, pa, pb, h, hh2reg, h6reg, need_r);
         pa = pb;
       }
     } else {
@@ -1354,14 +1439,14 @@ k_ode_age2(const DevModel M, const double *__restrict__ theta, int64_t ld, int64
           if (tcut < b) { pb = tcut; step_done = false; }  // a breakpoint strictly inside (pa, b): cut there
         }
         const double hh = pending ? pb - pa : 0.0, hh2 = 0.5 * hh, h6 = div6(hh);
-        rk4_step2w(L, sg, y, pending, pa, pending ? pb : pa, hh, hh2, h6, need_r);
+        rk4_step2w<NS>(L, sg, y, pending, pa, pending ? pb : pa, hh, hh2, h6, need_r);
         if (pending) {
           pa = pb;
           if (step_done) ++s;
         }
       }
     }
-    if (live) day_out(d);
+    day_out(d, live);
   }
   // either lane may have met an undecidable R test: the chain is flagged if one of them did
   const unsigned nr = (__ballot_sync(kFull, need_r) >> L.shift) & 3u;
@@ -2924,11 +3009,15 @@ static cudaError_t launch_eval_fl(const EvalArgs &a) {
   // the kernel of the other flavours, of the trajectories with the extended series and of the R-tracking fallback;
   // the four-lane kernel (k_ode_age4) is kept for EPI_ODE_LANES = 4.  EPI_ODE_LANES = 1 | 2 | 4 forces one mapping.
   int lanes = 1;
-  if constexpr (Traits<FL>::kAge && !Traits<FL>::k2x) {  // (age-2x: thread per chain only)
+  if constexpr (Traits<FL>::kAge) {
     // (age-2i, whose schedule is mostly linear ramps — three more FP64 operations per stage that two lanes pay twice —
     //  at 65,536 chains: on the posterior cloud of a sampler 3.14 ms thread per chain against 2.93 with two lanes; on
     //  the narrow cloud, whose warps run in lock-step, 3.15 against 3.29.  The sampler is the use case.)
     lanes = a.ode_lanes ? a.ode_lanes : 2;
+    // age-2x (five states per lane, R integrated; k_ode_age2<.., NS = 5>, bit-identical, tests): thread per chain wins
+    // at every size measured — 65,536 chains 4.51 ms against 5.06, 8,192 chains 1.27 against 1.30 (posterior cloud) —
+    // so two lanes there only on request
+    if (Traits<FL>::k2x) lanes = a.ode_lanes == 2 || a.ode_lanes == 4 ? 2 : 1;
   }
   constexpr bool kFallback = !Traits<FL>::k2x;  // the R-tracking fallback instance exists where the hot one does not integrate R
   const bool use_pair = lanes == 2, use_quad = lanes == 4;

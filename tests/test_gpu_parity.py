@@ -691,6 +691,33 @@ def test_two_lane_kernel_under_stress(ny, no, beta_scale, monkeypatch):
         assert np.array_equal(a, b, equal_nan=True)
 
 
+@pytest.mark.parametrize("m", [4, 1, 3])
+def test_two_lane_kernel_of_the_waning_immunity_flavour(m, monkeypatch):
+    """age-2x on two lanes per chain (five states per lane: R is integrated and flows back into S, the younger group's
+    effective-susceptible cap, the history rows hold the incidence) against thread per chain: golden theta,
+    box-uniform theta and a ragged batch must give identical bits, offsets, statuses and trajectories."""
+    from epi_mcmc_b200.model import Model, load_dataset
+    ds = load_dataset("X300")
+    theta = np.array(load_golden("X300")["theta"])
+    rng = np.random.default_rng(29)
+    outs = {}
+    for lanes in (1, 2):
+        monkeypatch.setenv("EPI_ODE_LANES", str(lanes))
+        M = Model(ds, substeps=m)
+        mn, mx, init = M.df_params["min"], M.df_params["max"], M.df_params["init"]
+        if lanes == 1:
+            box = mn + rng.uniform(size=(1003, M.d)) * (mx - mn)
+            near = np.clip(init + (rng.uniform(size=(1000, M.d)) - 0.5) * 0.3 * (mx - mn), mn, mx)
+            th = np.vstack([theta, box, near])
+        logl, logp, status = M.calclogpost_batch(th)
+        off, pad, terms = M.eval_detail(th)
+        outs[lanes] = (logl, logp, status, off, pad, terms)
+        M.close()
+    assert np.isfinite(outs[1][0]).mean() > 0.3
+    for a, b in zip(outs[1], outs[2]):
+        assert np.array_equal(a, b, equal_nan=True)
+
+
 def test_four_lane_kernel_through_the_r_fallback(monkeypatch):
     """Tiny population: S falls below 1, the four-lane kernel flags the chains and the R-tracking thread-per-chain
     instance recomputes them — same bits as the thread-per-chain hot path followed by the same fallback."""
