@@ -2987,6 +2987,9 @@ static cudaError_t launch_eval_fl(const EvalArgs &a) {
     cudaFuncSetAttribute(k_series<FL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if constexpr (Traits<FL>::kAge)
     {
+      // four 128-thread blocks per SM (the register budget of the default instance) must also fit the SM's 227 KB of
+      // shared memory, 1 KB of it reserved per block
+      static_assert(4 * (seg_table_bytes<FL>(128) + 1024) <= 227 * 1024, "schedule table too large for four blocks per SM");
       cudaFuncSetAttribute(k_ode_age2<FL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seg_table_bytes<FL>(128));
       cudaFuncSetAttribute(k_ode_age2<FL, true, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seg_table_bytes<FL>(128));
       // (without it the driver sizes the carve-out for ONE block per SM and a 16,384-chain shard runs in two waves)
